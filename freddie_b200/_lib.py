@@ -1,0 +1,125 @@
+"""ctypes binding of ``libfreddie_b200.so`` (C ABI in ``include/freddie_b200.h``).
+
+There is no CPU fallback: if the shared library is missing, cannot be loaded, or no CUDA device is
+present, the product path raises.  Build with ``python -c "import __graft_entry__ as g; g.build()"``
+or ``make -C freddie_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfreddie_b200.so")
+
+FRS_MAX_STAGES = 32
+
+# taps (frs_get_intermediate)
+TAP_Y_RAW, TAP_Y, TAP_THR, TAP_CAND, TAP_FIXED, TAP_DP_FINAL, TAP_SUB_START, TAP_SUB_N = 1, 2, 3, 4, 5, 6, 7, 8
+TAP_COVERAGE, TAP_INS, TAP_OUT, TAP_COV_OFF, TAP_SUB_PAIR_OFF, TAP_SUB_TRIPLE_OFF = 9, 10, 11, 12, 13, 14
+
+_p = C.c_void_p
+
+
+class FrsParams(C.Structure):
+    _fields_ = [
+        ("sigma", C.c_double), ("tp", C.c_double), ("vf", C.c_double),
+        ("mps", C.c_int32), ("lo", C.c_int32), ("ignore_ends", C.c_int32), ("thr_table_len", C.c_int32),
+        ("thr_table", _p), ("gauss_w", _p), ("refine_w", _p),
+        ("gauss_radius", C.c_int32), ("refine_radius", C.c_int32),
+    ]
+
+
+BATCH_COUNTS = ["n_tints", "n_islands", "n_reps", "n_rep_ivs", "n_reads", "n_read_ivs", "n_cigar_ops", "n_samples"]
+BATCH_ARRAYS = [
+    "tint_island_off", "tint_rep_off", "tint_read_off", "island_start", "island_sample_off",
+    "rep_iv_off", "rep_weight", "rep_iv_fs", "rep_iv_fe",
+    "read_rep", "read_strand", "read_len", "read_iv_off", "read_seq_off",
+    "riv_ts", "riv_te", "riv_qs", "riv_qe", "riv_cig_off", "cigar", "seq_is_a", "seq_is_t",
+]
+
+
+class FrsBatch(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in BATCH_COUNTS] + [("n_seq_words", C.c_int64)]
+                + [(n, _p) for n in BATCH_ARRAYS])
+
+
+class FrsResultSizes(C.Structure):
+    _fields_ = [
+        ("n_final", C.c_int64), ("n_digit_bytes", C.c_int64), ("n_gap_records", C.c_int64),
+        ("n_candidates", C.c_int64), ("n_subproblems", C.c_int64), ("dp_cells", C.c_int64),
+        ("dp_read_cells", C.c_int64), ("max_subproblem", C.c_int32), ("pad", C.c_int32),
+    ]
+
+
+RESULT_ARRAYS = ["tint_final_off", "final_pos", "tint_digit_off", "digits", "read_head", "read_gap_off", "gap_rec"]
+
+
+class FrsResult(C.Structure):
+    _fields_ = [(n, _p) for n in RESULT_ARRAYS]
+
+
+class FrsError(RuntimeError):
+    """Raised for every non-zero status of the library.  ``code`` is the FRS_ERR_* value."""
+
+    def __init__(self, code, msg):
+        super().__init__("[libfreddie_b200 %d] %s" % (code, msg))
+        self.code = code
+        self.msg = msg
+
+
+_lib = None
+
+
+def load():
+    """Loads the library (once) and declares every prototype of the header."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FrsError(-100, "%s not found: the CUDA extension is not built (run __graft_entry__.build()); "
+                             "there is no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.frs_abi_version.restype = C.c_int
+    lib.frs_device_count.restype = C.c_int
+    lib.frs_create.argtypes = [C.c_int, C.POINTER(_p)]
+    lib.frs_destroy.argtypes = [_p]
+    lib.frs_destroy.restype = None
+    lib.frs_last_error.argtypes = [_p]
+    lib.frs_last_error.restype = C.c_char_p
+    lib.frs_stream.argtypes = [_p]
+    lib.frs_stream.restype = _p
+    lib.frs_upload.argtypes = [_p, C.POINTER(FrsBatch)]
+    lib.frs_run.argtypes = [_p, C.POINTER(FrsParams), C.POINTER(FrsResultSizes)]
+    lib.frs_download.argtypes = [_p, C.POINTER(FrsResult)]
+    lib.frs_segment_batch.argtypes = [_p, C.POINTER(FrsBatch), C.POINTER(FrsParams), C.POINTER(FrsResultSizes)]
+    lib.frs_get_intermediate.argtypes = [_p, C.c_int, _p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.frs_set_profiling.argtypes = [_p, C.c_int]
+    lib.frs_get_timings.argtypes = [_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    lib.frs_last_launch_count.argtypes = [_p]
+    for fn in ("frs_create", "frs_upload", "frs_run", "frs_download", "frs_segment_batch", "frs_get_intermediate",
+               "frs_set_profiling", "frs_get_timings", "frs_last_launch_count"):
+        getattr(lib, fn).restype = C.c_int
+    if hasattr(lib, "frs_parse_tints"):
+        lib.frs_parse_tints.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int, C.c_int,
+                                        C.POINTER(_p), C.c_char_p, C.c_size_t]
+        lib.frs_parse_tints.restype = C.c_int
+        lib.frs_parsed_batch.argtypes = [_p, C.POINTER(FrsBatch)]
+        lib.frs_parsed_batch.restype = C.c_int
+        lib.frs_parsed_free.argtypes = [_p]
+        lib.frs_parsed_free.restype = None
+        lib.frs_format_tints.argtypes = [_p, C.POINTER(FrsResult), C.POINTER(C.c_char_p), C.POINTER(C.c_char_p),
+                                         C.c_int, C.c_char_p, C.c_size_t]
+        lib.frs_format_tints.restype = C.c_int
+    if lib.frs_abi_version() != 1:
+        raise FrsError(-101, "ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+EXPORTED = [
+    "frs_abi_version", "frs_device_count", "frs_create", "frs_destroy", "frs_last_error", "frs_stream",
+    "frs_upload", "frs_run", "frs_download", "frs_segment_batch", "frs_get_intermediate", "frs_set_profiling",
+    "frs_get_timings", "frs_last_launch_count", "frs_parse_tints", "frs_parsed_batch", "frs_parsed_free",
+    "frs_format_tints",
+]

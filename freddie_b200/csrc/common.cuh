@@ -1,0 +1,185 @@
+// common.cuh -- shared helpers: error handling, device scans / compaction, threshold arithmetic.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+typedef long long i64;
+typedef unsigned int u32;
+typedef unsigned char u8;
+
+#define FRS_NEG_INF (-0x3fffffff)  // "-inf" of the DP (scores fit in 30 bits)
+
+// device-side assert channel: first failing code wins
+enum {
+  DEVERR_NONE = 0,
+  DEVERR_BREAK_LARGE_POS = 1,   // freddie_segment.py:643  assert max_c_idx_y_v > 0
+  DEVERR_BREAK_LARGE_RANGE = 2, // freddie_segment.py:640  window leaves the candidate list
+  DEVERR_RATIO_RANGE = 3,       // freddie_segment.py:821  assert 0 <= cov_ratio <= 1
+  DEVERR_THREAD_CIGAR = 4,      // freddie_segment.py:303,326,349  CIGAR threading failed
+  DEVERR_Q_RANGE = 5,           // freddie_segment.py:389  0 <= q_ssc <= q_esc <= length
+  DEVERR_GAP_RANGE = 6,         // freddie_segment.py:462,466
+  DEVERR_POLY_RANGE = 7,        // freddie_segment.py:410,441,450
+  DEVERR_BACKTRACE = 8,         // internal: DP backtrace ran off the table
+  DEVERR_ISLAND = 9,            // freddie_segment.py:668  interval ends in different islands
+};
+
+__device__ __forceinline__ void dev_fail(int* err, int code, int where) {
+  if (atomicCAS(&err[0], 0, code) == 0) err[1] = where;
+}
+
+// ---------------------------------------------------------------------------------------------
+// thresholds: the reference compares the IEEE quotient  double(cov)/double(len)  against h and
+// l = 1-h (freddie_segment.py:490-495, :816-828).  The quotient is monotone in cov, so the two
+// compares are equivalent to integer cuts computed once per length with true fp64 divides:
+//   yea  <=>  cov >= ty      nay  <=>  cov <= tn
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void length_cuts(int len, const double* __restrict__ tbl, int tbl_len, double tp,
+                                            int& ty, int& tn) {
+  double h = (len < tbl_len) ? tbl[len] : tp;
+  double l = __dsub_rn(1.0, h);
+  double dl = (double)len;
+  int c = (int)floor(h * dl);
+  if (c < 0) c = 0;
+  while (c > 0 && __ddiv_rn((double)(c - 1), dl) > h) --c;
+  while (!(__ddiv_rn((double)c, dl) > h)) ++c;  // ends at len+1 at the latest (ratio > 1 >= h)
+  ty = c;
+  int d = (int)floor(l * dl);
+  if (d < 0) d = 0;
+  while (__ddiv_rn((double)d, dl) < l) ++d;  // first d with d/len >= l
+  while (d > 0 && !(__ddiv_rn((double)(d - 1), dl) < l)) --d;
+  tn = d - 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// block-wide exclusive scan of one value per thread (blockDim.x <= 1024, multiple of 32)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T block_exclusive_scan(T v, T* total_out, T* smem /* >= 33 entries */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  T x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    T y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) smem[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    T s = (lane < nw) ? smem[lane] : (T)0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      T y = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += y;
+    }
+    if (lane < nw) smem[lane] = s;  // inclusive warp totals
+    if (lane == 31) smem[32] = s;
+  }
+  __syncthreads();
+  T base = (warp > 0) ? smem[warp - 1] : (T)0;
+  if (total_out) *total_out = smem[32 > nw ? nw - 1 : 31];
+  T r = base + x - v;
+  __syncthreads();
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-wide exclusive scan / flag compaction: 3 launches (block sums, scan of sums, apply)
+// ---------------------------------------------------------------------------------------------
+#define SCAN_THREADS 512
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+template <typename TIn>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_block_sums(const TIn* __restrict__ in, i64 n,
+                                                                 i64* __restrict__ bsum) {
+  __shared__ i64 sm[40];
+  i64 base = (i64)blockIdx.x * SCAN_TILE + (i64)threadIdx.x * SCAN_ITEMS;
+  i64 s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k)
+    if (base + k < n) s += (i64)in[base + k];
+  i64 tot;
+  block_exclusive_scan<i64>(s, &tot, sm);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+
+// single CTA: in-place exclusive scan of bsum[0..nb), total written to bsum[nb]
+__global__ void __launch_bounds__(1024) k_scan_bsums(i64* __restrict__ bsum, int nb) {
+  __shared__ i64 sm[40];
+  __shared__ i64 carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    int i = base + threadIdx.x;
+    i64 v = (i < nb) ? bsum[i] : 0;
+    i64 tot;
+    i64 ex = block_exclusive_scan<i64>(v, &tot, sm);
+    i64 c = carry;
+    if (i < nb) bsum[i] = c + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry = c + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) bsum[nb] = carry;
+}
+
+// out[i] = exclusive prefix (TOut), out[n] = total
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const TIn* __restrict__ in, i64 n,
+                                                            const i64* __restrict__ bsum, TOut* __restrict__ out) {
+  __shared__ i64 sm[40];
+  i64 base = (i64)blockIdx.x * SCAN_TILE + (i64)threadIdx.x * SCAN_ITEMS;
+  i64 v[SCAN_ITEMS];
+  i64 s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    v[k] = (base + k < n) ? (i64)in[base + k] : 0;
+    s += v[k];
+  }
+  i64 ex = block_exclusive_scan<i64>(s, (i64*)nullptr, sm) + bsum[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    if (base + k < n) out[base + k] = (TOut)ex;
+    ex += v[k];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = (TOut)bsum[gridDim.x];
+}
+
+// idx_out[rank] = i for every i with flags[i] != 0 (ascending)
+template <typename TIn>
+__global__ void __launch_bounds__(SCAN_THREADS) k_compact(const TIn* __restrict__ flags, i64 n,
+                                                         const i64* __restrict__ bsum, int* __restrict__ idx_out) {
+  __shared__ i64 sm[40];
+  i64 base = (i64)blockIdx.x * SCAN_TILE + (i64)threadIdx.x * SCAN_ITEMS;
+  int f[SCAN_ITEMS];
+  i64 s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    f[k] = (base + k < n) ? (flags[base + k] != 0) : 0;
+    s += f[k];
+  }
+  i64 ex = block_exclusive_scan<i64>(s, (i64*)nullptr, sm) + bsum[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    if (f[k]) idx_out[ex++] = (int)(base + k);
+  }
+}
+
+// largest i in [0, n) with off[i] <= x  (off ascending, off[0] <= x)
+__device__ __forceinline__ int upper_row(const int* __restrict__ off, int n, int x) {
+  int lo = 0, hi = n;  // invariant: off[lo] <= x, (hi == n or off[hi] > x)
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (off[mid] <= x) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ int upper_row64(const i64* __restrict__ off, int n, i64 x) {
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (off[mid] <= x) lo = mid; else hi = mid;
+  }
+  return lo;
+}

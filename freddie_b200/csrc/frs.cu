@@ -1,0 +1,766 @@
+// frs.cu -- context, pipeline driver and C ABI of libfreddie_b200.so (see include/freddie_b200.h).
+// The pipeline replaces segment() (freddie_segment.py:738-844) for a whole batch of tints.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/freddie_b200.h"
+#include "common.cuh"
+#include "kernels_signal.cuh"
+#include "kernels_dp.cuh"
+#include "kernels_finish.cuh"
+
+static thread_local char g_err[512] = "";
+
+struct DBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  template <typename T> T* as() const { return (T*)p; }
+};
+
+struct Stage {
+  const char* name;
+  cudaEvent_t ev0, ev1;
+  int launches;
+  bool used;
+};
+
+struct frs_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  char err[512] = "";
+  bool uploaded = false, ran = false;
+  bool profiling = false;
+  // host copy of the batch sizes and small offset arrays
+  frs_batch hb;  // pointers here are DEVICE pointers after upload
+  std::vector<int> h_tint_island_off, h_tint_rep_off, h_tint_read_off, h_island_sample_off;
+  int n_sig_work = 0, n_tiles = 0, n_cov_tiles = 0, n_dig_tiles = 0;
+  // device buffers (grow-only)
+  std::vector<DBuf*> all;
+  DBuf b_tint_island_off, b_tint_rep_off, b_tint_read_off, b_island_start, b_island_sample_off, b_island_tint,
+      b_rep_iv_off, b_rep_weight, b_rep_fs, b_rep_fe, b_rep_tint, b_read_rep, b_read_strand, b_read_len,
+      b_read_iv_off, b_read_seq_off, b_read_tint, b_riv_ts, b_riv_te, b_riv_qs, b_riv_qe, b_riv_cig_off, b_cigar,
+      b_seq_a, b_seq_t;
+  DBuf b_sig_work, b_tiles, b_cov_tiles, b_dig_tiles;
+  DBuf b_params;  // thr table | gauss w | refine w
+  DBuf b_yraw, b_y, b_sflag, b_bsum, b_cand_flat, b_cand_island, b_island_cand_off, b_tint_cand_off, b_thr, b_vbuf,
+      b_leaf_off, b_leaf_len, b_leaf_sum, b_fixed0, b_fixed1, b_fixed_list, b_sub_flag, b_sub_fidx, b_sub_start,
+      b_sub_n, b_sub_tint, b_sz_pair, b_sz_triple, b_sz_work, b_sub_pair_off, b_sub_triple_off, b_sub_work_off,
+      b_cov_sz, b_tint_cov_off, b_P, b_ins, b_out, b_dpfinal, b_pf_list, b_gbuf, b_pstate, b_final_flat,
+      b_final_pos, b_final_island, b_tint_final_off, b_dig_sz, b_tint_digit_off, b_seg_ty, b_seg_tn, b_digits,
+      b_run_cnt, b_run_off, b_runs, b_gap_cnt, b_read_gap_off, b_read_head, b_gap_rec, b_counters, b_stats, b_err;
+  i64* h_pin = nullptr;  // pinned scratch for small D2H reads
+  // results of the last run
+  frs_result_sizes sizes;
+  i64 n_cand = 0, n_fixed = 0, n_sub = 0, cov_elems = 0, n_pairs = 0, n_triples = 0;
+  // timing
+  Stage stages[FRS_MAX_STAGES];
+  int n_stages = 0, cur_stage = -1, launch_count = 0;
+};
+
+static int fail(frs_context* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) snprintf(c->err, sizeof c->err, "%s", buf);
+  snprintf(g_err, sizeof g_err, "%s", buf);
+  return code;
+}
+
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess)                                                                            \
+      return fail(c, FRS_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__,   \
+                  __LINE__, #call);                                                                   \
+  } while (0)
+
+static int ensure(frs_context* c, DBuf& b, size_t bytes) {
+  if (bytes < 16) bytes = 16;
+  if (b.cap >= bytes) return 0;
+  if (b.p) CK(cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = bytes + bytes / 8 + 256;
+  CK(cudaMalloc(&b.p, want));
+  b.cap = want;
+  bool known = false;
+  for (DBuf* q : c->all) known |= (q == &b);
+  if (!known) c->all.push_back(&b);
+  return 0;
+}
+#define ENS(buf, bytes)                          \
+  do {                                           \
+    int r_ = ensure(c, c->buf, (size_t)(bytes)); \
+    if (r_) return r_;                           \
+  } while (0)
+
+static void stage_begin(frs_context* c, const char* name) {
+  int s = -1;
+  for (int i = 0; i < c->n_stages; ++i)
+    if (c->stages[i].name == name) s = i;
+  if (s < 0 && c->n_stages < FRS_MAX_STAGES) {
+    s = c->n_stages++;
+    c->stages[s].name = name;
+    c->stages[s].launches = 0;
+    c->stages[s].used = false;
+    cudaEventCreate(&c->stages[s].ev0);
+    cudaEventCreate(&c->stages[s].ev1);
+  }
+  if (c->cur_stage >= 0 && c->profiling) cudaEventRecord(c->stages[c->cur_stage].ev1, c->stream);
+  c->cur_stage = s;
+  if (s >= 0) {
+    c->stages[s].used = true;
+    if (c->profiling) cudaEventRecord(c->stages[s].ev0, c->stream);
+  }
+}
+static void stage_end(frs_context* c) {
+  if (c->cur_stage >= 0 && c->profiling) cudaEventRecord(c->stages[c->cur_stage].ev1, c->stream);
+  c->cur_stage = -1;
+}
+#define LAUNCHED()                                           \
+  do {                                                       \
+    c->launch_count++;                                       \
+    if (c->cur_stage >= 0) c->stages[c->cur_stage].launches++; \
+  } while (0)
+
+static inline int cdiv(i64 a, i64 b) { return (int)((a + b - 1) / b); }
+
+// device-wide helpers ------------------------------------------------------------------------
+template <typename TIn, typename TOut>
+static int scan_exclusive(frs_context* c, const TIn* in, i64 n, TOut* out) {
+  int nb = cdiv(n > 0 ? n : 1, SCAN_TILE);
+  ENS(b_bsum, (size_t)(nb + 1) * 8);
+  i64* bs = c->b_bsum.as<i64>();
+  k_scan_block_sums<TIn><<<nb, SCAN_THREADS, 0, c->stream>>>(in, n, bs); LAUNCHED();
+  k_scan_bsums<<<1, 1024, 0, c->stream>>>(bs, nb); LAUNCHED();
+  k_scan_apply<TIn, TOut><<<nb, SCAN_THREADS, 0, c->stream>>>(in, n, bs, out); LAUNCHED();
+  return 0;
+}
+// compaction; the count ends up in bsum[nb] and is copied to counters[slot]
+template <typename TIn>
+static int compact(frs_context* c, const TIn* flags, i64 n, int* idx_out, int counter_slot) {
+  int nb = cdiv(n > 0 ? n : 1, SCAN_TILE);
+  ENS(b_bsum, (size_t)(nb + 1) * 8);
+  i64* bs = c->b_bsum.as<i64>();
+  k_scan_block_sums<TIn><<<nb, SCAN_THREADS, 0, c->stream>>>(flags, n, bs); LAUNCHED();
+  k_scan_bsums<<<1, 1024, 0, c->stream>>>(bs, nb); LAUNCHED();
+  k_compact<TIn><<<nb, SCAN_THREADS, 0, c->stream>>>(flags, n, bs, idx_out); LAUNCHED();
+  CK(cudaMemcpyAsync(c->b_counters.as<i64>() + counter_slot, bs + nb, 8, cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
+static int read_counters(frs_context* c, int n) {
+  CK(cudaMemcpyAsync(c->h_pin, c->b_counters.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+static const char* deverr_text(int code) {
+  switch (code) {
+    case DEVERR_BREAK_LARGE_POS: return "assert max_c_idx_y_v > 0 (freddie_segment.py:643)";
+    case DEVERR_BREAK_LARGE_RANGE: return "break_large_problems window leaves the candidate list (freddie_segment.py:640)";
+    case DEVERR_RATIO_RANGE: return "assert 0 <= cov_ratio <= 1 (freddie_segment.py:821)";
+    case DEVERR_THREAD_CIGAR: return "CIGAR threading failed (freddie_segment.py:303/326/349)";
+    case DEVERR_Q_RANGE: return "assert 0 <= q_ssc_pos <= q_esc_pos <= length (freddie_segment.py:389)";
+    case DEVERR_GAP_RANGE: return "assert on unaligned gap coordinates (freddie_segment.py:462/466)";
+    case DEVERR_POLY_RANGE: return "assert on poly-A/T coordinates (freddie_segment.py:410/441/450)";
+    case DEVERR_BACKTRACE: return "internal: DP backtrace left the table";
+    default: return "unknown device assert";
+  }
+}
+static int check_dev_err(frs_context* c) {
+  int h[2];
+  CK(cudaMemcpyAsync(h, c->b_err.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (h[0]) return fail(c, FRS_ERR_ASSERT, "AssertionError: %s [item %d]", deverr_text(h[0]), h[1]);
+  return 0;
+}
+
+// C ABI ----------------------------------------------------------------------------------------
+extern "C" {
+
+int frs_abi_version(void) { return FRS_ABI_VERSION; }
+
+int frs_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+const char* frs_last_error(const frs_context* ctx) { return ctx ? ctx->err : g_err; }
+
+int frs_create(int device, frs_context** out) {
+  frs_context* c = nullptr;
+  if (!out) return fail(c, FRS_ERR_ARG, "frs_create: out is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(c, FRS_ERR_CUDA, "frs_create: no CUDA device (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(c, FRS_ERR_ARG, "frs_create: device %d out of range (%d devices)", device, n);
+  c = new frs_context();
+  c->device = device;
+  memset(&c->hb, 0, sizeof c->hb);
+  memset(&c->sizes, 0, sizeof c->sizes);
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost((void**)&c->h_pin, 64 * 8) != cudaSuccess) {
+    int r = fail(nullptr, FRS_ERR_CUDA, "frs_create: %s", cudaGetErrorString(cudaGetLastError()));
+    delete c;
+    return r;
+  }
+  cudaFuncSetAttribute(k_signal, cudaFuncAttributeMaxDynamicSharedMemorySize, SIG_BINS * 4);
+  cudaFuncSetAttribute(k_dp_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(k_dp_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  *out = c;
+  return 0;
+}
+
+void frs_destroy(frs_context* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (DBuf* b : c->all)
+    if (b->p) cudaFree(b->p);
+  for (int i = 0; i < c->n_stages; ++i) {
+    cudaEventDestroy(c->stages[i].ev0);
+    cudaEventDestroy(c->stages[i].ev1);
+  }
+  if (c->h_pin) cudaFreeHost(c->h_pin);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+void* frs_stream(frs_context* c) { return c ? (void*)c->stream : nullptr; }
+
+int frs_set_profiling(frs_context* c, int enabled) {
+  if (!c) return FRS_ERR_ARG;
+  c->profiling = enabled != 0;
+  return 0;
+}
+
+int frs_last_launch_count(frs_context* c) { return c ? c->launch_count : 0; }
+
+int frs_get_timings(frs_context* c, const char** names, float* ms, int* launches) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  int k = 0;
+  for (int i = 0; i < c->n_stages; ++i) {
+    if (!c->stages[i].used) continue;
+    float t = 0.f;
+    if (c->profiling) cudaEventElapsedTime(&t, c->stages[i].ev0, c->stages[i].ev1);
+    names[k] = c->stages[i].name;
+    ms[k] = t;
+    launches[k] = c->stages[i].launches;
+    ++k;
+  }
+  return k;
+}
+
+#define H2D(buf, src, bytes)                                                                      \
+  do {                                                                                            \
+    ENS(buf, bytes);                                                                              \
+    if ((bytes) > 0) CK(cudaMemcpyAsync(c->buf.p, src, (size_t)(bytes), cudaMemcpyHostToDevice, c->stream)); \
+  } while (0)
+
+int frs_upload(frs_context* c, const frs_batch* b) {
+  if (!c || !b) return fail(c, FRS_ERR_ARG, "frs_upload: NULL argument");
+  CK(cudaSetDevice(c->device));
+  if (b->n_tints <= 0) return fail(c, FRS_ERR_ARG, "frs_upload: empty batch");
+  if (b->n_samples <= 0 || b->n_islands <= 0) return fail(c, FRS_ERR_ARG, "frs_upload: batch without islands");
+  const int T = b->n_tints, NI = b->n_islands, NR = b->n_reps, N = b->n_reads;
+  // ---- validate the offset tables (the reference asserts the same facts while parsing) ----
+  if (b->tint_island_off[0] != 0 || b->tint_island_off[T] != NI || b->tint_rep_off[0] != 0 ||
+      b->tint_rep_off[T] != NR || b->tint_read_off[0] != 0 || b->tint_read_off[T] != N ||
+      b->island_sample_off[0] != 0 || b->island_sample_off[NI] != b->n_samples || b->rep_iv_off[0] != 0 ||
+      b->rep_iv_off[NR] != b->n_rep_ivs || b->read_iv_off[0] != 0 || b->read_iv_off[N] != b->n_read_ivs ||
+      b->riv_cig_off[0] != 0 || b->riv_cig_off[b->n_read_ivs] != b->n_cigar_ops || b->read_seq_off[0] != 0 ||
+      b->read_seq_off[N] != b->n_seq_words)
+    return fail(c, FRS_ERR_ARG, "frs_upload: inconsistent offset tables");
+  for (int t = 0; t < T; ++t)
+    if (b->tint_island_off[t + 1] <= b->tint_island_off[t] || b->tint_rep_off[t + 1] <= b->tint_rep_off[t] ||
+        b->tint_read_off[t + 1] < b->tint_read_off[t])
+      return fail(c, FRS_ERR_ARG, "frs_upload: tint %d has no islands or no read reps", t);
+  for (int i = 0; i < NI; ++i)
+    if (b->island_sample_off[i + 1] - b->island_sample_off[i] < 2)
+      return fail(c, FRS_ERR_ARG, "AssertionError: island %d is empty (freddie_segment.py:140)", i);
+  c->hb = *b;
+  c->h_tint_island_off.assign(b->tint_island_off, b->tint_island_off + T + 1);
+  c->h_tint_rep_off.assign(b->tint_rep_off, b->tint_rep_off + T + 1);
+  c->h_tint_read_off.assign(b->tint_read_off, b->tint_read_off + T + 1);
+  c->h_island_sample_off.assign(b->island_sample_off, b->island_sample_off + NI + 1);
+  // ---- derived host tables ----
+  std::vector<int> island_tint(NI), rep_tint(NR), read_tint(N);
+  std::vector<SigWork> sig;
+  std::vector<TileWork> tiles;
+  std::vector<RepTile> cov_tiles, dig_tiles;
+  const int DIG_REPS = 64;
+  for (int t = 0; t < T; ++t) {
+    for (int i = b->tint_island_off[t]; i < b->tint_island_off[t + 1]; ++i) {
+      island_tint[i] = t;
+      int n = b->island_sample_off[i + 1] - b->island_sample_off[i];
+      for (int lo = 0; lo < n; lo += TILE_SAMPLES) tiles.push_back(TileWork{i, lo});
+    }
+    int r0 = b->tint_rep_off[t], r1 = b->tint_rep_off[t + 1];
+    for (int r = r0; r < r1; ++r) rep_tint[r] = t;
+    for (int r = b->tint_read_off[t]; r < b->tint_read_off[t + 1]; ++r) read_tint[r] = t;
+    int s0 = b->island_sample_off[b->tint_island_off[t]], s1 = b->island_sample_off[b->tint_island_off[t + 1]];
+    int single = (r1 - r0) <= SIG_REPS;
+    for (int w = s0; w < s1; w += SIG_BINS)
+      for (int r = r0; r < r1; r += SIG_REPS)
+        sig.push_back(SigWork{t, w, w + SIG_BINS < s1 ? w + SIG_BINS : s1, r, r + SIG_REPS < r1 ? r + SIG_REPS : r1, single});
+    int R = r1 - r0, Rp = (R + 3) & ~3;
+    for (int r = 0; r < Rp; r += COV_THREADS) cov_tiles.push_back(RepTile{t, r});
+    for (int r = 0; r < R; r += DIG_REPS) dig_tiles.push_back(RepTile{t, r});
+  }
+  for (int r = 0; r < N; ++r) {
+    int rep = b->read_rep[r];
+    if (rep < 0 || rep >= NR || rep_tint[rep] != read_tint[r])
+      return fail(c, FRS_ERR_ARG, "frs_upload: read %d points at rep %d of another tint", r, rep);
+  }
+  c->n_sig_work = (int)sig.size();
+  c->n_tiles = (int)tiles.size();
+  c->n_cov_tiles = (int)cov_tiles.size();
+  c->n_dig_tiles = (int)dig_tiles.size();
+  // ---- copies ----
+  H2D(b_tint_island_off, b->tint_island_off, (size_t)(T + 1) * 4);
+  H2D(b_tint_rep_off, b->tint_rep_off, (size_t)(T + 1) * 4);
+  H2D(b_tint_read_off, b->tint_read_off, (size_t)(T + 1) * 4);
+  H2D(b_island_start, b->island_start, (size_t)NI * 4);
+  H2D(b_island_sample_off, b->island_sample_off, (size_t)(NI + 1) * 4);
+  H2D(b_rep_iv_off, b->rep_iv_off, (size_t)(NR + 1) * 4);
+  H2D(b_rep_weight, b->rep_weight, (size_t)NR * 4);
+  H2D(b_rep_fs, b->rep_iv_fs, (size_t)b->n_rep_ivs * 4);
+  H2D(b_rep_fe, b->rep_iv_fe, (size_t)b->n_rep_ivs * 4);
+  H2D(b_read_rep, b->read_rep, (size_t)N * 4);
+  H2D(b_read_strand, b->read_strand, (size_t)N);
+  H2D(b_read_len, b->read_len, (size_t)N * 4);
+  H2D(b_read_iv_off, b->read_iv_off, (size_t)(N + 1) * 4);
+  H2D(b_read_seq_off, b->read_seq_off, (size_t)(N + 1) * 8);
+  H2D(b_riv_ts, b->riv_ts, (size_t)b->n_read_ivs * 4);
+  H2D(b_riv_te, b->riv_te, (size_t)b->n_read_ivs * 4);
+  H2D(b_riv_qs, b->riv_qs, (size_t)b->n_read_ivs * 4);
+  H2D(b_riv_qe, b->riv_qe, (size_t)b->n_read_ivs * 4);
+  H2D(b_riv_cig_off, b->riv_cig_off, (size_t)(b->n_read_ivs + 1) * 4);
+  H2D(b_cigar, b->cigar, (size_t)b->n_cigar_ops * 4);
+  H2D(b_seq_a, b->seq_is_a, (size_t)b->n_seq_words * 4);
+  H2D(b_seq_t, b->seq_is_t, (size_t)b->n_seq_words * 4);
+  // the derived tables live in pageable vectors: stage synchronously before they go out of scope
+  H2D(b_island_tint, island_tint.data(), (size_t)NI * 4);
+  H2D(b_rep_tint, rep_tint.data(), (size_t)NR * 4);
+  H2D(b_read_tint, read_tint.data(), (size_t)N * 4);
+  H2D(b_sig_work, sig.data(), sig.size() * sizeof(SigWork));
+  H2D(b_tiles, tiles.data(), tiles.size() * sizeof(TileWork));
+  H2D(b_cov_tiles, cov_tiles.data(), cov_tiles.size() * sizeof(RepTile));
+  H2D(b_dig_tiles, dig_tiles.data(), dig_tiles.size() * sizeof(RepTile));
+  CK(cudaStreamSynchronize(c->stream));
+  c->uploaded = true;
+  c->ran = false;
+  return 0;
+}
+
+int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) {
+  if (!c || !prm) return fail(c, FRS_ERR_ARG, "frs_run: NULL argument");
+  if (!c->uploaded) return fail(c, FRS_ERR_STATE, "frs_run: no batch uploaded");
+  CK(cudaSetDevice(c->device));
+  // parse_args asserts (freddie_segment.py:104-109)
+  if (!(prm->tp >= 0.5 && prm->tp <= 1.0)) return fail(c, FRS_ERR_ARG, "AssertionError: 1 >= threshold_rate >= 0.5");
+  if (!(prm->vf > 0 && prm->vf < 10)) return fail(c, FRS_ERR_ARG, "AssertionError: 10 > variance_factor > 0");
+  if (!(prm->sigma > 0 && prm->sigma <= 50)) return fail(c, FRS_ERR_ARG, "AssertionError: 50 >= sigma > 0");
+  if (!(prm->mps > 3)) return fail(c, FRS_ERR_ARG, "AssertionError: max_problem_size > 3");
+  if (prm->mps < 11)
+    return fail(c, FRS_ERR_LIMIT, "max_problem_size < 11 is not supported: the reference's +-5 anchor window "
+                                  "(freddie_segment.py:639) indexes outside the problem there (IndexError / wrap)");
+  if (!(prm->lo >= 0)) return fail(c, FRS_ERR_ARG, "AssertionError: min_read_support_outside >= 0");
+  if (prm->gauss_radius != (int)(4.0 * prm->sigma + 0.5) || prm->refine_radius != (int)(1.0 * prm->sigma + 0.5))
+    return fail(c, FRS_ERR_ARG, "frs_run: kernel radii do not match sigma");
+  if (prm->gauss_radius > 1000) return fail(c, FRS_ERR_LIMIT, "gauss radius too large");
+
+  const frs_batch& B = c->hb;
+  const int T = B.n_tints, NI = B.n_islands, NR = B.n_reps, N = B.n_reads;
+  const i64 L = B.n_samples;
+  cudaStream_t st = c->stream;
+  c->launch_count = 0;
+  for (int i = 0; i < c->n_stages; ++i) { c->stages[i].used = false; c->stages[i].launches = 0; }
+
+  // parameter tables
+  const int lw = prm->gauss_radius, rr = prm->refine_radius;
+  size_t ptab = (size_t)prm->thr_table_len + (2 * lw + 1) + (2 * rr + 1);
+  ENS(b_params, ptab * 8);
+  double* d_tbl = c->b_params.as<double>();
+  double* d_gw = d_tbl + prm->thr_table_len;
+  double* d_rw = d_gw + (2 * lw + 1);
+  CK(cudaMemcpyAsync(d_tbl, prm->thr_table, (size_t)prm->thr_table_len * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_gw, prm->gauss_w, (size_t)(2 * lw + 1) * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_rw, prm->refine_w, (size_t)(2 * rr + 1) * 8, cudaMemcpyHostToDevice, st));
+
+  ENS(b_counters, 64 * 8);
+  ENS(b_stats, 8 * 8);
+  ENS(b_err, 16);
+  CK(cudaMemsetAsync(c->b_counters.p, 0, 64 * 8, st));
+  CK(cudaMemsetAsync(c->b_stats.p, 0, 8 * 8, st));
+  CK(cudaMemsetAsync(c->b_err.p, 0, 16, st));
+  int* d_err = c->b_err.as<int>();
+
+  const int* d_tint_island_off = c->b_tint_island_off.as<int>();
+  const int* d_tint_rep_off = c->b_tint_rep_off.as<int>();
+  const int* d_island_sample_off = c->b_island_sample_off.as<int>();
+  const int* d_island_tint = c->b_island_tint.as<int>();
+
+  // ================= phase 1: signal -> smoothed signal -> candidates, threshold =================
+  stage_begin(c, "signal");
+  ENS(b_yraw, L * 4);
+  CK(cudaMemsetAsync(c->b_yraw.p, 0, L * 4, st));
+  k_signal<<<c->n_sig_work, SIG_THREADS, SIG_BINS * 4, st>>>(c->b_sig_work.as<SigWork>(), c->b_rep_iv_off.as<int>(),
+                                                             c->b_rep_weight.as<int>(), c->b_rep_fs.as<int>(),
+                                                             c->b_rep_fe.as<int>(), prm->ignore_ends, c->b_yraw.as<int>());
+  LAUNCHED();
+
+  stage_begin(c, "gauss");
+  ENS(b_y, L * 8);
+  {
+    size_t sm = (size_t)((2 * lw + 1) + TILE_SAMPLES + 2 * lw) * 8;
+    if (sm > 48 * 1024) CK(cudaFuncSetAttribute(k_gauss, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_gauss<<<c->n_tiles, GAUSS_THREADS, sm, st>>>(c->b_tiles.as<TileWork>(), d_island_sample_off, c->b_yraw.as<int>(),
+                                                   d_gw, lw, c->b_y.as<double>());
+    LAUNCHED();
+  }
+
+  stage_begin(c, "candidates");
+  ENS(b_sflag, L);
+  CK(cudaMemsetAsync(c->b_sflag.p, 0, L, st));
+  k_peaks<<<c->n_tiles, GAUSS_THREADS, 0, st>>>(c->b_tiles.as<TileWork>(), d_island_sample_off, c->b_y.as<double>(),
+                                                c->b_sflag.as<u8>());
+  LAUNCHED();
+  ENS(b_cand_flat, (L / 2 + 2 * NI + 16) * 4);  // peaks are >= 2 apart, plus both ends of every island
+  { int r = compact<u8>(c, c->b_sflag.as<u8>(), L, c->b_cand_flat.as<int>(), 0); if (r) return r; }
+
+  stage_begin(c, "threshold");
+  ENS(b_thr, (size_t)T * 8);
+  ENS(b_vbuf, L * 8);
+  {
+    size_t nl = (size_t)L / 64 + 2 * (size_t)T + 8;
+    ENS(b_leaf_off, nl * 4);
+    ENS(b_leaf_len, nl * 4);
+    ENS(b_leaf_sum, nl * 8);
+  }
+  k_threshold<<<T, THR_THREADS, 0, st>>>(d_tint_island_off, d_island_sample_off, c->b_y.as<double>(), prm->vf,
+                                         c->b_vbuf.as<double>(), c->b_leaf_off.as<int>(), c->b_leaf_len.as<int>(),
+                                         c->b_leaf_sum.as<double>(), c->b_thr.as<double>());
+  LAUNCHED();
+  stage_end(c);
+
+  { int r = read_counters(c, 1); if (r) return r; }   // sync: number of candidates
+  const i64 K = c->h_pin[0];
+  c->n_cand = K;
+
+  // ================= phase 2: fixed candidates, subproblems, coverage, DP =================
+  stage_begin(c, "fixed");
+  ENS(b_cand_island, K * 4);
+  ENS(b_island_cand_off, (size_t)(NI + 1) * 4);
+  k_cand_meta<<<cdiv(K + 1, 256), 256, 0, st>>>(c->b_cand_flat.as<int>(), (int)K, d_island_sample_off, NI,
+                                                c->b_cand_island.as<int>(), c->b_island_cand_off.as<int>());
+  LAUNCHED();
+  ENS(b_fixed0, K);
+  ENS(b_fixed1, K);
+  k_fixed_a<<<cdiv(K, 256), 256, 0, st>>>((int)K, c->b_cand_flat.as<int>(), c->b_cand_island.as<int>(),
+                                          c->b_island_cand_off.as<int>(), d_island_tint, c->b_y.as<double>(),
+                                          c->b_thr.as<double>(), c->b_fixed0.as<u8>(), c->b_fixed1.as<u8>());
+  LAUNCHED();
+  k_fixed_b<<<cdiv(K, 256), 256, 0, st>>>((int)K, c->b_cand_flat.as<int>(), c->b_cand_island.as<int>(),
+                                          c->b_island_cand_off.as<int>(), c->b_y.as<double>(), prm->mps,
+                                          c->b_fixed0.as<u8>(), c->b_fixed1.as<u8>(), d_err);
+  LAUNCHED();
+  ENS(b_fixed_list, K * 4);
+  { int r = compact<u8>(c, c->b_fixed1.as<u8>(), K, c->b_fixed_list.as<int>(), 1); if (r) return r; }
+  { int r = read_counters(c, 2); if (r) return r; }   // sync: number of fixed candidates
+  const i64 NF = c->h_pin[1];
+  c->n_fixed = NF;
+
+  stage_begin(c, "subproblems");
+  ENS(b_sub_flag, NF);
+  ENS(b_sub_fidx, NF * 4);
+  k_sub_flag<<<cdiv(NF, 256), 256, 0, st>>>((int)NF, c->b_fixed_list.as<int>(), c->b_cand_island.as<int>(),
+                                            c->b_sub_flag.as<u8>());
+  LAUNCHED();
+  { int r = compact<u8>(c, c->b_sub_flag.as<u8>(), NF, c->b_sub_fidx.as<int>(), 2); if (r) return r; }
+  // coverage block offsets per tint (rows = candidates of the tint, stride Rp)
+  ENS(b_tint_cand_off, (size_t)(T + 1) * 4);
+  ENS(b_cov_sz, (size_t)(T + 1) * 8);
+  ENS(b_tint_cov_off, (size_t)(T + 1) * 8);
+  k_tint_cov_sizes<<<cdiv(T + 1, 256), 256, 0, st>>>(T, d_tint_island_off, c->b_island_cand_off.as<int>(), d_tint_rep_off,
+                                                     c->b_tint_cand_off.as<int>(), c->b_cov_sz.as<i64>());
+  LAUNCHED();
+  { int r = scan_exclusive<i64, i64>(c, c->b_cov_sz.as<i64>(), T, c->b_tint_cov_off.as<i64>()); if (r) return r; }
+  CK(cudaMemcpyAsync(c->b_counters.as<i64>() + 3, c->b_tint_cov_off.as<i64>() + T, 8, cudaMemcpyDeviceToDevice, st));
+  { int r = read_counters(c, 4); if (r) return r; }   // sync: number of subproblems, coverage size
+  const i64 NSUB = c->h_pin[2];
+  const i64 COV = c->h_pin[3];
+  c->n_sub = NSUB;
+  c->cov_elems = COV;
+
+  const int slab_words = 256;  // 8192 read reps per CTA of the DP-table kernel
+  i64 n_pairs = 0, n_triples = 0, n_work = 0;
+  int max_n = 0;
+  if (NSUB > 0) {
+    ENS(b_sub_start, NSUB * 4);
+    ENS(b_sub_n, NSUB * 4);
+    ENS(b_sub_tint, NSUB * 4);
+    ENS(b_sz_pair, NSUB * 4);
+    ENS(b_sz_triple, NSUB * 4);
+    ENS(b_sz_work, NSUB * 4);
+    ENS(b_sub_pair_off, (NSUB + 1) * 8);
+    ENS(b_sub_triple_off, (NSUB + 1) * 8);
+    ENS(b_sub_work_off, (NSUB + 1) * 4);
+    k_sub_sizes<<<cdiv(NSUB, 256), 256, 0, st>>>((int)NSUB, c->b_sub_fidx.as<int>(), c->b_fixed_list.as<int>(),
+                                                 c->b_cand_island.as<int>(), d_island_tint, d_tint_rep_off, slab_words,
+                                                 c->b_sub_start.as<int>(), c->b_sub_n.as<int>(), c->b_sub_tint.as<int>(),
+                                                 c->b_sz_pair.as<int>(), c->b_sz_triple.as<int>(), c->b_sz_work.as<int>(),
+                                                 c->b_stats.as<i64>());
+    LAUNCHED();
+    { int r = scan_exclusive<int, i64>(c, c->b_sz_pair.as<int>(), NSUB, c->b_sub_pair_off.as<i64>()); if (r) return r; }
+    { int r = scan_exclusive<int, i64>(c, c->b_sz_triple.as<int>(), NSUB, c->b_sub_triple_off.as<i64>()); if (r) return r; }
+    { int r = scan_exclusive<int, int>(c, c->b_sz_work.as<int>(), NSUB, c->b_sub_work_off.as<int>()); if (r) return r; }
+    CK(cudaMemcpyAsync(c->b_counters.as<i64>() + 4, c->b_sub_pair_off.as<i64>() + NSUB, 8, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(c->b_counters.as<i64>() + 5, c->b_sub_triple_off.as<i64>() + NSUB, 8, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(c->b_counters.as<i64>() + 6, c->b_stats.as<i64>(), 24, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemsetAsync(c->b_counters.as<i64>() + 9, 0, 8, st));
+    CK(cudaMemcpyAsync(c->b_counters.as<i64>() + 9, c->b_sub_work_off.as<int>() + NSUB, 4, cudaMemcpyDeviceToDevice, st));
+    { int r = read_counters(c, 10); if (r) return r; }   // sync: table sizes
+    n_pairs = c->h_pin[4];
+    n_triples = c->h_pin[5];
+    max_n = (int)(c->h_pin[8] & 0xffffffff);
+    n_work = c->h_pin[9];
+  }
+  c->n_pairs = n_pairs;
+  c->n_triples = n_triples;
+  { int r = check_dev_err(c); if (r) return r; }
+
+  stage_begin(c, "coverage");
+  ENS(b_P, COV * 4);
+  if (NSUB > 0) {
+    k_coverage<<<c->n_cov_tiles, COV_THREADS, 0, st>>>(c->b_cov_tiles.as<RepTile>(), d_tint_rep_off,
+                                                       c->b_tint_cand_off.as<int>(), c->b_tint_cov_off.as<i64>(),
+                                                       c->b_rep_iv_off.as<int>(), c->b_rep_fs.as<int>(),
+                                                       c->b_rep_fe.as<int>(), c->b_cand_flat.as<int>(), c->b_P.as<u32>());
+    LAUNCHED();
+  }
+
+  ENS(b_dpfinal, K);
+  CK(cudaMemcpyAsync(c->b_dpfinal.p, c->b_fixed1.p, K, cudaMemcpyDeviceToDevice, st));
+  if (NSUB > 0) {
+    stage_begin(c, "dp_tables");
+    ENS(b_ins, n_pairs * 4);
+    ENS(b_out, n_triples * 4);
+    CK(cudaMemsetAsync(c->b_ins.p, 0, n_pairs * 4, st));
+    CK(cudaMemsetAsync(c->b_out.p, 0, n_triples * 4, st));
+    int wc = DPT_MAXW;
+    while (wc > 1 && dpt_smem_bytes(max_n, wc) > 200 * 1024) wc >>= 1;
+    size_t sm = dpt_smem_bytes(max_n, wc);
+    if (sm > 227 * 1024)
+      return fail(c, FRS_ERR_LIMIT, "subproblem with %d candidates exceeds the DP kernel's shared-memory budget "
+                                    "(max_problem_size too large for this build)", max_n);
+    DptArgs A;
+    A.sub_start = c->b_sub_start.as<int>(); A.sub_n = c->b_sub_n.as<int>(); A.sub_tint = c->b_sub_tint.as<int>();
+    A.sub_work_off = c->b_sub_work_off.as<int>(); A.sub_pair_off = c->b_sub_pair_off.as<i64>();
+    A.sub_triple_off = c->b_sub_triple_off.as<i64>(); A.n_sub = (int)NSUB;
+    A.tint_rep_off = d_tint_rep_off; A.tint_cand_off = c->b_tint_cand_off.as<int>();
+    A.tint_cov_off = c->b_tint_cov_off.as<i64>(); A.rep_weight = c->b_rep_weight.as<int>();
+    A.cand_flat = c->b_cand_flat.as<int>(); A.P = c->b_P.as<u32>();
+    A.thr_table = d_tbl; A.thr_table_len = prm->thr_table_len; A.tp = prm->tp;
+    A.slab_words = slab_words; A.max_n = max_n; A.ins = c->b_ins.as<int>(); A.out = c->b_out.as<int>();
+    k_dp_tables<<<(unsigned)n_work, DPT_THREADS, sm, st>>>(A, wc);
+    LAUNCHED();
+
+    stage_begin(c, "dp_solve");
+    DpsArgs S;
+    S.sub_start = A.sub_start; S.sub_n = A.sub_n; S.sub_pair_off = A.sub_pair_off; S.sub_triple_off = A.sub_triple_off;
+    S.cand_flat = A.cand_flat; S.ins = A.ins; S.out = A.out; S.lo = prm->lo; S.max_n = max_n;
+    S.final_flag = c->b_dpfinal.as<u8>(); S.err = d_err;
+    size_t sm2 = (size_t)max_n * max_n * 4 + (size_t)max_n * 4 + (size_t)max_n * max_n * 2 + 16;
+    if (sm2 > 200 * 1024) return fail(c, FRS_ERR_LIMIT, "subproblem with %d candidates exceeds the DP solver's budget", max_n);
+    k_dp_solve<<<(unsigned)NSUB, DPS_THREADS, sm2, st>>>(S);
+    LAUNCHED();
+  }
+
+  // ================= phase 3: refine, final positions, digits =================
+  stage_begin(c, "refine");
+  ENS(b_pf_list, K * 4);
+  { int r = compact<u8>(c, c->b_dpfinal.as<u8>(), K, c->b_pf_list.as<int>(), 10); if (r) return r; }
+  { int r = read_counters(c, 11); if (r) return r; }  // sync: number of pre-refine finals
+  const i64 NPF = c->h_pin[10];
+  CK(cudaMemsetAsync(c->b_sflag.p, 0, L, st));
+  k_mark_final<<<cdiv(NPF, 256), 256, 0, st>>>((int)NPF, c->b_pf_list.as<int>(), c->b_cand_flat.as<int>(),
+                                               c->b_sflag.as<u8>());
+  LAUNCHED();
+  ENS(b_gbuf, L * 8);
+  ENS(b_pstate, L);
+  k_refine<<<(unsigned)NPF, REF_THREADS, 0, st>>>((int)NPF, c->b_pf_list.as<int>(), c->b_cand_flat.as<int>(),
+                                                  c->b_cand_island.as<int>(), c->b_yraw.as<int>(), d_rw, rr, prm->sigma,
+                                                  c->b_gbuf.as<double>(), c->b_pstate.as<u8>(), c->b_sflag.as<u8>());
+  LAUNCHED();
+
+  stage_begin(c, "finals");
+  ENS(b_final_flat, (L / 2 + 2 * NI + 16) * 4);
+  { int r = compact<u8>(c, c->b_sflag.as<u8>(), L, c->b_final_flat.as<int>(), 11); if (r) return r; }
+  { int r = read_counters(c, 12); if (r) return r; }  // sync: number of final positions
+  const i64 NFIN = c->h_pin[11];
+  ENS(b_final_pos, NFIN * 4);
+  ENS(b_final_island, NFIN * 4);
+  ENS(b_tint_final_off, (size_t)(T + 1) * 4);
+  k_final_meta<<<cdiv(NFIN + 1, 256), 256, 0, st>>>((int)NFIN, c->b_final_flat.as<int>(), d_island_sample_off,
+                                                    c->b_island_start.as<int>(), d_island_tint, d_tint_island_off, NI, T,
+                                                    c->b_final_pos.as<int>(), c->b_final_island.as<int>(),
+                                                    c->b_tint_final_off.as<int>());
+  LAUNCHED();
+  ENS(b_dig_sz, (size_t)(T + 1) * 8);
+  ENS(b_tint_digit_off, (size_t)(T + 1) * 8);
+  k_digit_sizes<<<cdiv(T, 256), 256, 0, st>>>(T, d_tint_rep_off, c->b_tint_final_off.as<int>(), c->b_dig_sz.as<i64>());
+  LAUNCHED();
+  { int r = scan_exclusive<i64, i64>(c, c->b_dig_sz.as<i64>(), T, c->b_tint_digit_off.as<i64>()); if (r) return r; }
+  CK(cudaMemcpyAsync(c->b_counters.as<i64>() + 12, c->b_tint_digit_off.as<i64>() + T, 8, cudaMemcpyDeviceToDevice, st));
+  ENS(b_seg_ty, NFIN * 4);
+  ENS(b_seg_tn, NFIN * 4);
+  k_seg_cuts<<<cdiv(NFIN, 256), 256, 0, st>>>((int)NFIN, c->b_final_flat.as<int>(), c->b_final_island.as<int>(), d_tbl,
+                                              prm->thr_table_len, prm->tp, c->b_seg_ty.as<int>(), c->b_seg_tn.as<int>());
+  LAUNCHED();
+  { int r = read_counters(c, 13); if (r) return r; }  // sync: digit bytes
+  const i64 NDIG = c->h_pin[12];
+
+  stage_begin(c, "digits");
+  ENS(b_digits, NDIG);
+  k_digits<<<c->n_dig_tiles, DIG_THREADS, 0, st>>>(c->b_dig_tiles.as<RepTile>(), 64, d_tint_rep_off,
+                                                   c->b_tint_final_off.as<int>(), c->b_tint_digit_off.as<i64>(),
+                                                   c->b_rep_iv_off.as<int>(), c->b_rep_fs.as<int>(), c->b_rep_fe.as<int>(),
+                                                   c->b_final_flat.as<int>(), c->b_seg_ty.as<int>(), c->b_seg_tn.as<int>(),
+                                                   c->b_digits.as<u8>(), d_err);
+  LAUNCHED();
+
+  stage_begin(c, "runs");
+  ENS(b_run_cnt, (size_t)NR * 4);
+  ENS(b_run_off, (size_t)(NR + 1) * 4);
+  k_run_count<<<cdiv((i64)NR * 32, 256), 256, 0, st>>>(NR, c->b_rep_tint.as<int>(), d_tint_rep_off,
+                                                       c->b_tint_final_off.as<int>(), c->b_tint_digit_off.as<i64>(),
+                                                       c->b_digits.as<u8>(), c->b_run_cnt.as<int>());
+  LAUNCHED();
+  { int r = scan_exclusive<int, int>(c, c->b_run_cnt.as<int>(), NR, c->b_run_off.as<int>()); if (r) return r; }
+  CK(cudaMemsetAsync(c->b_counters.as<i64>() + 13, 0, 16, st));
+  CK(cudaMemcpyAsync(c->b_counters.as<i64>() + 13, c->b_run_off.as<int>() + NR, 4, cudaMemcpyDeviceToDevice, st));
+  ENS(b_gap_cnt, (size_t)N * 4);
+  ENS(b_read_gap_off, (size_t)(N + 1) * 4);
+  k_gap_count<<<cdiv(N, 256), 256, 0, st>>>(N, c->b_read_rep.as<int>(), c->b_run_off.as<int>(), c->b_gap_cnt.as<int>());
+  LAUNCHED();
+  { int r = scan_exclusive<int, int>(c, c->b_gap_cnt.as<int>(), N, c->b_read_gap_off.as<int>()); if (r) return r; }
+  CK(cudaMemcpyAsync(c->b_counters.as<i64>() + 14, c->b_read_gap_off.as<int>() + N, 4, cudaMemcpyDeviceToDevice, st));
+  { int r = read_counters(c, 15); if (r) return r; }  // sync: number of runs / gap records
+  const i64 NRUN = c->h_pin[13];
+  const i64 NGAP = c->h_pin[14];
+  ENS(b_runs, NRUN * 8);
+  k_run_fill<<<cdiv((i64)NR * 32, 256), 256, 0, st>>>(NR, c->b_rep_tint.as<int>(), d_tint_rep_off,
+                                                      c->b_tint_final_off.as<int>(), c->b_tint_digit_off.as<i64>(),
+                                                      c->b_digits.as<u8>(), c->b_run_off.as<int>(), c->b_runs.as<int2>());
+  LAUNCHED();
+
+  stage_begin(c, "gaps");
+  ENS(b_read_head, (size_t)N * 32);
+  ENS(b_gap_rec, NGAP * 12);
+  {
+    GapArgs G;
+    G.n_reads = N; G.read_rep = c->b_read_rep.as<int>(); G.read_strand = c->b_read_strand.as<u8>();
+    G.read_len = c->b_read_len.as<int>(); G.read_iv_off = c->b_read_iv_off.as<int>();
+    G.read_seq_off = c->b_read_seq_off.as<i64>(); G.read_tint = c->b_read_tint.as<int>();
+    G.riv_ts = c->b_riv_ts.as<int>(); G.riv_te = c->b_riv_te.as<int>(); G.riv_qs = c->b_riv_qs.as<int>();
+    G.riv_qe = c->b_riv_qe.as<int>(); G.riv_cig_off = c->b_riv_cig_off.as<int>(); G.cigar = c->b_cigar.as<u32>();
+    G.seq_a = c->b_seq_a.as<u32>(); G.seq_t = c->b_seq_t.as<u32>(); G.run_off = c->b_run_off.as<int>();
+    G.runs = c->b_runs.as<int2>(); G.tint_final_off = c->b_tint_final_off.as<int>();
+    G.final_pos = c->b_final_pos.as<int>(); G.read_gap_off = c->b_read_gap_off.as<int>();
+    G.read_head = c->b_read_head.as<int>(); G.gap_rec = c->b_gap_rec.as<int>(); G.err = d_err;
+    if (N > 0) { k_gaps<<<cdiv(N, 128), 128, 0, st>>>(G); LAUNCHED(); }
+  }
+  stage_end(c);
+  { int r = check_dev_err(c); if (r) return r; }
+  CK(cudaGetLastError());
+
+  c->sizes.n_final = NFIN;
+  c->sizes.n_digit_bytes = NDIG;
+  c->sizes.n_gap_records = NGAP;
+  c->sizes.n_candidates = K;
+  c->sizes.n_subproblems = NSUB;
+  c->sizes.dp_cells = NSUB > 0 ? c->h_pin[6] : 0;
+  c->sizes.dp_read_cells = NSUB > 0 ? c->h_pin[7] : 0;
+  c->sizes.max_subproblem = max_n;
+  c->sizes.pad = 0;
+  if (sizes_out) *sizes_out = c->sizes;
+  c->ran = true;
+  return 0;
+}
+
+int frs_segment_batch(frs_context* c, const frs_batch* batch, const frs_params* prm, frs_result_sizes* sizes) {
+  int r = frs_upload(c, batch);
+  if (r) return r;
+  return frs_run(c, prm, sizes);
+}
+
+#define D2H(dst, buf, bytes)                                                                              \
+  do {                                                                                                    \
+    if ((dst) && (bytes) > 0) CK(cudaMemcpyAsync(dst, c->buf.p, (size_t)(bytes), cudaMemcpyDeviceToHost, c->stream)); \
+  } while (0)
+
+int frs_download(frs_context* c, const frs_result* o) {
+  if (!c || !o) return fail(c, FRS_ERR_ARG, "frs_download: NULL argument");
+  if (!c->ran) return fail(c, FRS_ERR_STATE, "frs_download: no results (call frs_run first)");
+  CK(cudaSetDevice(c->device));
+  const int T = c->hb.n_tints, N = c->hb.n_reads;
+  D2H(o->tint_final_off, b_tint_final_off, (size_t)(T + 1) * 4);
+  D2H(o->final_pos, b_final_pos, c->sizes.n_final * 4);
+  D2H(o->tint_digit_off, b_tint_digit_off, (size_t)(T + 1) * 8);
+  D2H(o->digits, b_digits, c->sizes.n_digit_bytes);
+  D2H(o->read_head, b_read_head, (size_t)N * 32);
+  D2H(o->read_gap_off, b_read_gap_off, (size_t)(N + 1) * 4);
+  D2H(o->gap_rec, b_gap_rec, c->sizes.n_gap_records * 12);
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int frs_get_intermediate(frs_context* c, int which, void* dst, size_t cap, size_t* bytes) {
+  if (!c || !bytes) return fail(c, FRS_ERR_ARG, "frs_get_intermediate: NULL argument");
+  if (!c->ran) return fail(c, FRS_ERR_STATE, "frs_get_intermediate: nothing has run");
+  CK(cudaSetDevice(c->device));
+  const void* src = nullptr;
+  size_t sz = 0;
+  const i64 L = c->hb.n_samples, K = c->n_cand, NS = c->n_sub;
+  switch (which) {
+    case FRS_TAP_Y_RAW: src = c->b_yraw.p; sz = L * 4; break;
+    case FRS_TAP_Y: src = c->b_y.p; sz = L * 8; break;
+    case FRS_TAP_THR: src = c->b_thr.p; sz = (size_t)c->hb.n_tints * 8; break;
+    case FRS_TAP_CAND: src = c->b_cand_flat.p; sz = K * 4; break;
+    case FRS_TAP_FIXED: src = c->b_fixed1.p; sz = K; break;
+    case FRS_TAP_DP_FINAL: src = c->b_dpfinal.p; sz = K; break;
+    case FRS_TAP_SUB_START: src = c->b_sub_start.p; sz = NS * 4; break;
+    case FRS_TAP_SUB_N: src = c->b_sub_n.p; sz = NS * 4; break;
+    case FRS_TAP_COVERAGE: src = c->b_P.p; sz = c->cov_elems * 4; break;
+    case FRS_TAP_INS: src = c->b_ins.p; sz = c->n_pairs * 4; break;
+    case FRS_TAP_OUT: src = c->b_out.p; sz = c->n_triples * 4; break;
+    case FRS_TAP_COV_OFF: src = c->b_tint_cov_off.p; sz = (size_t)(c->hb.n_tints + 1) * 8; break;
+    case FRS_TAP_SUB_PAIR_OFF: src = c->b_sub_pair_off.p; sz = NS ? (NS + 1) * 8 : 0; break;
+    case FRS_TAP_SUB_TRIPLE_OFF: src = c->b_sub_triple_off.p; sz = NS ? (NS + 1) * 8 : 0; break;
+    default: return fail(c, FRS_ERR_ARG, "frs_get_intermediate: unknown tap %d", which);
+  }
+  *bytes = sz;
+  size_t n = sz < cap ? sz : cap;
+  if (dst && n > 0) {
+    CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
+}  // extern "C"
+

@@ -1,0 +1,418 @@
+// kernels_finish.cuh -- refine, final positions, digit matrix, 1-runs, gaps / poly-A.
+// Reference steps: refine_segmentation (freddie_segment.py:249-266), digits (:808-838),
+// get_unaligned_gaps_and_polyA (:370-472) with get_interval_start/end (:307-349),
+// forward_thread_cigar (:289-304), find_longest_poly (:352-367).
+#pragma once
+#include "common.cuh"
+
+// mark the pre-refine finals (candidates kept by fixed | DP) in the per-sample flag array
+__global__ void k_mark_final(int n, const int* __restrict__ pf_list, const int* __restrict__ cand_flat,
+                             u8* __restrict__ sflag) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) sflag[cand_flat[pf_list[e]]] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K9 refine: one CTA per pre-refine segment (a, b) of an island (:249-266).
+//   v = raw[a:b] with 20 samples zeroed at both ends; skip if b-a <= 40 or sum(v) < 20;
+//   g = Gaussian(v), radius int(sigma+.5), zero outside (mode='constant'), same pair order as K2;
+//   peaks = strict local maxima of g (plateau midpoint), min-distance 20 suppression by descending
+//   height (ties: the later peak first = stable ascending argsort walked from the end);
+//   keep peak i iff the sequential sum of g[round(i-sigma) : round(i+sigma+1)] (python slice) >= 20.
+// g and the peak states live in global scratch indexed by flat sample (segments are disjoint).
+// ---------------------------------------------------------------------------------------------
+#define REF_THREADS 128
+#define REF_SKIP 20
+
+__global__ void __launch_bounds__(REF_THREADS) k_refine(int n_pf, const int* __restrict__ pf_list,
+                                                       const int* __restrict__ cand_flat,
+                                                       const int* __restrict__ cand_island,
+                                                       const int* __restrict__ y_raw, const double* __restrict__ rw,
+                                                       int rad, double sigma, double* __restrict__ gbuf,
+                                                       u8* __restrict__ pstate, u8* __restrict__ sflag) {
+  __shared__ int sm_red[REF_THREADS / 32];
+  __shared__ int sm_flag;
+  const int e = blockIdx.x;
+  if (e + 1 >= n_pf) return;
+  const int qa = pf_list[e], qb = pf_list[e + 1];
+  if (cand_island[qa] != cand_island[qb]) return;
+  const int a = cand_flat[qa], b = cand_flat[qb];
+  const int len = b - a;
+  if (len <= 2 * REF_SKIP) return;
+  const int tid = threadIdx.x;
+  // sum of the inner raw signal (integers)
+  long long s = 0;
+  for (int x = REF_SKIP + tid; x < len - REF_SKIP; x += REF_THREADS) s += y_raw[a + x];
+  int si = (int)min(s, (long long)20);  // non-negative terms: only "total < 20" matters, so clamp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) si += __shfl_xor_sync(0xffffffffu, si, o);
+  if ((tid & 31) == 0) sm_red[tid >> 5] = si;
+  __syncthreads();
+  long long tot = 0;
+  for (int w = 0; w < REF_THREADS / 32; ++w) tot += sm_red[w];
+  if (tot < 20) return;
+  // g = constant-mode Gaussian of v
+  double* g = gbuf + a;
+  u8* ps = pstate + a;
+  for (int x = tid; x < len; x += REF_THREADS) {
+    auto v = [&](int i) -> double {
+      return (i >= REF_SKIP && i < len - REF_SKIP) ? (double)y_raw[a + i] : 0.0;
+    };
+    double acc = __dmul_rn(v(x), rw[rad]);
+    for (int jj = -rad; jj < 0; ++jj) acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(v(x + jj), v(x - jj)), rw[rad + jj]));
+    g[x] = acc;
+    ps[x] = 0;
+  }
+  __syncthreads();
+  // peaks (1 = undecided)
+  for (int x = 1 + tid; x < len - 1; x += REF_THREADS) {
+    double vx = g[x];
+    if (g[x - 1] < vx) {
+      int ia = x + 1;
+      while (ia < len - 1 && g[ia] == vx) ++ia;
+      if (g[ia] < vx) ps[(x + ia - 1) >> 1] = 1;
+    }
+  }
+  __syncthreads();
+  // min-distance suppression in rounds: an undecided peak with no higher-priority undecided peak
+  // within distance < 20 is kept (2); undecided peaks next to a kept one are removed (3)
+  for (int round = 0; round < len; ++round) {
+    if (tid == 0) sm_flag = 0;
+    __syncthreads();
+    for (int x = tid; x < len; x += REF_THREADS) {
+      if (ps[x] != 1) continue;
+      bool top = true;
+      double hx = g[x];
+      for (int d = 1; d < REF_SKIP && top; ++d) {
+        int l = x - d, r = x + d;
+        if (l >= 0 && ps[l] == 1 && g[l] > hx) top = false;              // earlier peak wins only if strictly higher
+        if (r < len && ps[r] == 1 && g[r] >= hx) top = false;            // later peak wins ties
+      }
+      if (top) ps[x] = 4;  // provisional keep (not yet visible as "kept" to this round's readers)
+    }
+    __syncthreads();
+    for (int x = tid; x < len; x += REF_THREADS) {
+      if (ps[x] != 1) continue;
+      bool rm = false;
+      for (int d = 1; d < REF_SKIP && !rm; ++d) {
+        int l = x - d, r = x + d;
+        if ((l >= 0 && ps[l] == 4) || (r < len && ps[r] == 4)) rm = true;
+      }
+      if (rm) ps[x] = 3;
+    }
+    __syncthreads();
+    for (int x = tid; x < len; x += REF_THREADS) {
+      if (ps[x] == 4) ps[x] = 2;
+      else if (ps[x] == 1) sm_flag = 1;
+    }
+    __syncthreads();
+    if (!sm_flag) break;
+    __syncthreads();
+  }
+  // window test on kept peaks (python slice semantics, sequential left-to-right sum)
+  for (int x = tid; x < len; x += REF_THREADS) {
+    if (ps[x] != 2) continue;
+    long long lo_i = (long long)rint(__dsub_rn((double)x, sigma));
+    long long hi_i = (long long)rint(__dadd_rn(__dadd_rn((double)x, sigma), 1.0));
+    if (lo_i < 0) { lo_i += len; if (lo_i < 0) lo_i = 0; }
+    if (hi_i < 0) { hi_i += len; if (hi_i < 0) hi_i = 0; }
+    if (lo_i > len) lo_i = len;
+    if (hi_i > len) hi_i = len;
+    double sum = 0.0;
+    for (long long i = lo_i; i < hi_i; ++i) sum = __dadd_rn(sum, g[i]);
+    if (!(sum < 20.0)) sflag[a + x] = 1;
+  }
+}
+
+// after compaction of the per-sample final flags: positions + per-tint offsets + island of each final
+__global__ void k_final_meta(int n_final, const int* __restrict__ final_flat, const int* __restrict__ island_sample_off,
+                             const int* __restrict__ island_start, const int* __restrict__ island_tint,
+                             const int* __restrict__ tint_island_off, int n_islands, int n_tints,
+                             int* __restrict__ final_pos, int* __restrict__ final_island,
+                             int* __restrict__ tint_final_off) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_final) {
+    if (e == n_final) tint_final_off[n_tints] = n_final;
+    return;
+  }
+  int f = final_flat[e];
+  int isl = upper_row(island_sample_off, n_islands, f);
+  final_island[e] = isl;
+  final_pos[e] = island_start[isl] + (f - island_sample_off[isl]);
+  int t = island_tint[isl];
+  if (f == island_sample_off[isl] && isl == tint_island_off[t]) tint_final_off[t] = e;
+}
+
+// per tint: digit block size = n_reps * (n_final - 1)
+__global__ void k_digit_sizes(int n_tints, const int* __restrict__ tint_rep_off, const int* __restrict__ tint_final_off,
+                              i64* __restrict__ sz) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tints) return;
+  i64 S = tint_final_off[t + 1] - tint_final_off[t] - 1;
+  sz[t] = S * (tint_rep_off[t + 1] - tint_rep_off[t]);
+}
+
+// per final e (segment e -> e+1): integer cuts of the segment, or a separator marker
+__global__ void k_seg_cuts(int n_final, const int* __restrict__ final_flat, const int* __restrict__ final_island,
+                           const double* __restrict__ tbl, int tbl_len, double tp, int* __restrict__ seg_ty,
+                           int* __restrict__ seg_tn) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_final) return;
+  int ty = 0x7fffffff, tn = -2;  // tn == -2 marks "no segment" (island separator or tint end)
+  if (e + 1 < n_final && final_island[e] == final_island[e + 1])
+    length_cuts(final_flat[e + 1] - final_flat[e] + 1, tbl, tbl_len, tp, ty, tn);
+  seg_ty[e] = ty;
+  seg_tn[e] = tn;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K10 digits: one warp per read rep, lanes over segments; ASCII digits, rep-major rows (:815-838).
+// cov(segment) = P(f_{t+1}) - P(f_t) with P(x) = samples of the rep strictly before flat x.
+// ---------------------------------------------------------------------------------------------
+#define DIG_THREADS 256
+__global__ void __launch_bounds__(DIG_THREADS) k_digits(const RepTile* __restrict__ tiles, int reps_per_tile,
+                                                       const int* __restrict__ tint_rep_off,
+                                                       const int* __restrict__ tint_final_off,
+                                                       const i64* __restrict__ tint_digit_off,
+                                                       const int* __restrict__ rep_iv_off,
+                                                       const int* __restrict__ iv_fs, const int* __restrict__ iv_fe,
+                                                       const int* __restrict__ final_flat,
+                                                       const int* __restrict__ seg_ty, const int* __restrict__ seg_tn,
+                                                       u8* __restrict__ digits, int* __restrict__ err) {
+  const RepTile tl = tiles[blockIdx.x];
+  const int r0 = tint_rep_off[tl.tint];
+  const int R = tint_rep_off[tl.tint + 1] - r0;
+  const int f0 = tint_final_off[tl.tint];
+  const int S = tint_final_off[tl.tint + 1] - f0 - 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r_hi = min(R, tl.rep_lo + reps_per_tile);
+  for (int r = tl.rep_lo + warp; r < r_hi; r += DIG_THREADS / 32) {
+    const int a = rep_iv_off[r0 + r], b = rep_iv_off[r0 + r + 1];
+    u8* row = digits + tint_digit_off[tl.tint] + (i64)r * S;
+    for (int s = lane; s < S; s += 32) {
+      const int tn = seg_tn[f0 + s];
+      u8 d = '0';
+      if (tn != -2) {
+        const int fa = final_flat[f0 + s], fb = final_flat[f0 + s + 1];
+        int cov = 0;
+        for (int k = a; k < b; ++k) {
+          int fs = iv_fs[k], len = iv_fe[k] - fs + 1;
+          int hi = min(max(fb - fs, 0), len);
+          int lo = min(max(fa - fs, 0), len);
+          cov += hi - lo;
+        }
+        if (cov > fb - fa + 1) dev_fail(err, DEVERR_RATIO_RANGE, r0 + r);
+        d = (cov >= seg_ty[f0 + s]) ? '1' : ((cov <= tn) ? '0' : '2');
+      }
+      row[s] = d;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1-runs per rep (shared by all reads of the rep): count, then fill after a scan.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_run_count(int n_reps, const int* __restrict__ rep_tint, const int* __restrict__ tint_rep_off,
+                            const int* __restrict__ tint_final_off, const i64* __restrict__ tint_digit_off,
+                            const u8* __restrict__ digits, int* __restrict__ run_cnt) {
+  int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (r >= n_reps) return;
+  int t = rep_tint[r];
+  int S = tint_final_off[t + 1] - tint_final_off[t] - 1;
+  const u8* row = digits + tint_digit_off[t] + (i64)(r - tint_rep_off[t]) * S;
+  int cnt = 0;
+  for (int s = lane; s < S; s += 32) cnt += (row[s] == '1' && (s == 0 || row[s - 1] != '1')) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) run_cnt[r] = cnt;
+}
+
+__global__ void k_run_fill(int n_reps, const int* __restrict__ rep_tint, const int* __restrict__ tint_rep_off,
+                           const int* __restrict__ tint_final_off, const i64* __restrict__ tint_digit_off,
+                           const u8* __restrict__ digits, const int* __restrict__ run_off, int2* __restrict__ runs) {
+  int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (r >= n_reps) return;
+  int t = rep_tint[r];
+  int S = tint_final_off[t + 1] - tint_final_off[t] - 1;
+  const u8* row = digits + tint_digit_off[t] + (i64)(r - tint_rep_off[t]) * S;
+  int base = run_off[r];
+  for (int s0 = 0; s0 < S; s0 += 32) {
+    int s = s0 + lane;
+    bool st = s < S && row[s] == '1' && (s == 0 || row[s - 1] != '1');
+    unsigned m = __ballot_sync(0xffffffffu, st);
+    if (st) {
+      int idx = base + __popc(m & ((1u << lane) - 1u));
+      int e = s;
+      while (e + 1 < S && row[e + 1] == '1') ++e;
+      runs[idx] = make_int2(s, e);
+    }
+    base += __popc(m);
+  }
+}
+
+__global__ void k_gap_count(int n_reads, const int* __restrict__ read_rep, const int* __restrict__ run_off,
+                            int* __restrict__ gap_cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_reads) return;
+  int r = read_rep[i];
+  int c = run_off[r + 1] - run_off[r];
+  gap_cnt[i] = c > 0 ? c - 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K11 gaps / poly-A: one thread per read (:370-472).
+// ---------------------------------------------------------------------------------------------
+struct GapArgs {
+  int n_reads;
+  const int* read_rep; const u8* read_strand; const int* read_len; const int* read_iv_off;
+  const i64* read_seq_off; const int* read_tint;
+  const int* riv_ts; const int* riv_te; const int* riv_qs; const int* riv_qe; const int* riv_cig_off;
+  const u32* cigar; const u32* seq_a; const u32* seq_t;
+  const int* run_off; const int2* runs;
+  const int* tint_final_off; const int* final_pos;
+  const int* read_gap_off;
+  int* read_head; int* gap_rec; int* err;
+};
+
+// forward_thread_cigar (:289-304): every op length, insertions included, is clipped by the remaining
+// target distance.  Returns false if the CIGAR is exhausted before reaching t_goal.
+__device__ __forceinline__ bool thread_cigar(const u32* __restrict__ cig, int c0, int c1, int t_goal, int t_pos,
+                                             int q_pos, int& q_out) {
+  int k = c0;
+  while (t_pos < t_goal) {
+    if (k >= c1) return false;
+    u32 op = cig[k++];
+    int c = (int)(op >> 4);
+    int ty = (int)(op & 15u);
+    c = min(c, t_goal - t_pos);
+    if (ty == 0) { t_pos += c; q_pos += c; }
+    else if (ty == 2) t_pos += c;
+    else if (ty == 1) q_pos += c;
+  }
+  q_out = q_pos;
+  return t_pos == t_goal;
+}
+
+// get_interval_start (:307-326)
+__device__ bool interval_start(const GapArgs& A, int i0, int i1, int p, int& q, int& slack) {
+  for (int k = i0; k < i1; ++k) {
+    int ts = A.riv_ts[k], te = A.riv_te[k];
+    if (te < p) continue;
+    if (p < ts) { q = A.riv_qs[k]; slack = p - ts; return true; }
+    slack = 0;
+    if (!thread_cigar(A.cigar, A.riv_cig_off[k], A.riv_cig_off[k + 1], p, ts, A.riv_qs[k], q)) return false;
+    return q >= A.riv_qs[k] && q <= A.riv_qe[k];
+  }
+  return false;
+}
+// get_interval_end (:329-349)
+__device__ bool interval_end(const GapArgs& A, int i0, int i1, int p, int& q, int& slack) {
+  for (int k = i1 - 1; k >= i0; --k) {
+    int ts = A.riv_ts[k], te = A.riv_te[k];
+    if (ts > p) continue;
+    if (te < p) { q = A.riv_qe[k]; slack = te - p; return true; }
+    slack = 0;
+    if (!thread_cigar(A.cigar, A.riv_cig_off[k], A.riv_cig_off[k + 1], p, ts, A.riv_qs[k], q)) return false;
+    return q >= 0 && q <= A.riv_qe[k];
+  }
+  return false;
+}
+
+// One scan of find_longest_poly (:352-367) over a clip of n bases whose scan position t maps to read
+// index (first + t*step) in the plane `pl`; candidates with len >= 20 and purity >= 0.85 compete on
+// purity, the FIRST maximum wins (A runs are offered before T runs, :392-408).
+struct PolyBest { double p; int i0; int len; int kind; };
+
+__device__ void poly_scan(const u32* __restrict__ pl, int first, int step, int n, int kind, PolyBest& best) {
+  if (n <= 0) return;
+  int sc = 0;
+  int run_i0 = -1, run_best = 0, run_best_i = 0;
+  int prefix = 0;       // matches in [0, t)
+  int pre_i0 = 0;       // matches in [0, run_i0)
+  int pre_best = 0;     // matches in [0, run_best_i]
+  auto close = [&]() {
+    if (run_i0 < 0) return;
+    int len = run_best_i + 1 - run_i0;
+    if (len >= 20) {
+      double p = __ddiv_rn((double)(pre_best - pre_i0), (double)len);
+      if (p >= 0.85 && (best.kind == 0 || p > best.p)) { best.p = p; best.i0 = run_i0; best.len = len; best.kind = kind; }
+    }
+    run_i0 = -1;
+  };
+  for (int t = 0; t < n; ++t) {
+    int idx = first + t * step;
+    int m = (int)((pl[idx >> 5] >> (idx & 31)) & 1u);
+    if (t == 0) sc = m;  // scores[0] = match_score or 0 (:355-358)
+    else sc = max(0, sc + (m ? 1 : -2));
+    if (sc > 0) {
+      if (run_i0 < 0) { run_i0 = t; run_best = 0; pre_i0 = prefix; }
+      if (sc >= run_best) { run_best = sc; run_best_i = t; pre_best = prefix + m; }
+    } else {
+      close();
+    }
+    prefix += m;
+  }
+  close();
+}
+
+__global__ void k_gaps(GapArgs A) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n_reads) return;
+  int* head = A.read_head + (i64)i * 8;
+  for (int k = 0; k < 8; ++k) head[k] = 0;
+  const int rep = A.read_rep[i];
+  const int ra = A.run_off[rep], rb = A.run_off[rep + 1];
+  if (ra == rb) return;  // no '1' digit: empty gaps (:372)
+  const int t = A.read_tint[i];
+  const int* fpos = A.final_pos + A.tint_final_off[t];  // segs[s] = (fpos[s], fpos[s+1])
+  const int i0 = A.read_iv_off[i], i1 = A.read_iv_off[i + 1];
+  const int L = A.read_len[i];
+  int q_ssc, q_esc, slack;
+  if (!interval_start(A, i0, i1, fpos[A.runs[ra].x], q_ssc, slack)) { dev_fail(A.err, DEVERR_THREAD_CIGAR, i); return; }
+  if (!interval_end(A, i0, i1, fpos[A.runs[rb - 1].y + 1], q_esc, slack)) { dev_fail(A.err, DEVERR_THREAD_CIGAR, i); return; }
+  if (!(0 <= q_ssc && q_ssc <= q_esc && q_esc <= L)) { dev_fail(A.err, DEVERR_Q_RANGE, i); return; }
+  const bool minus = A.read_strand[i] != 0;
+  const u32* pa = A.seq_a + A.read_seq_off[i];
+  const u32* pt = A.seq_t + A.read_seq_off[i];
+  // start clip: q_ssc bases; '+': seq[t] vs ch; '-': seq[L-1-t] vs complement(ch)  (:392-401)
+  PolyBest sb; sb.kind = 0; sb.p = 0; sb.i0 = 0; sb.len = 0;
+  poly_scan(minus ? pt : pa, minus ? L - 1 : 0, minus ? -1 : 1, q_ssc, 1, sb);
+  poly_scan(minus ? pa : pt, minus ? L - 1 : 0, minus ? -1 : 1, q_ssc, 2, sb);
+  int flags = 1;
+  if (sb.kind) {
+    int gap = q_ssc - sb.i0 - sb.len;
+    if (!(0 <= gap && gap < q_ssc)) { dev_fail(A.err, DEVERR_POLY_RANGE, i); return; }
+    flags |= sb.kind << 8;
+    head[1] = sb.len; head[2] = gap; head[3] = sb.i0;
+  } else {
+    head[3] = q_ssc;
+  }
+  // end clip: L-q_esc bases; '+': seq[q_esc+t]; '-': seq[L-1-q_esc-t]  (:422-431)
+  PolyBest eb; eb.kind = 0; eb.p = 0; eb.i0 = 0; eb.len = 0;
+  poly_scan(minus ? pt : pa, minus ? L - 1 - q_esc : q_esc, minus ? -1 : 1, L - q_esc, 1, eb);
+  poly_scan(minus ? pa : pt, minus ? L - 1 - q_esc : q_esc, minus ? -1 : 1, L - q_esc, 2, eb);
+  if (eb.kind) {
+    int esc = L - q_esc - eb.i0;
+    if (!(eb.i0 >= 0 && eb.i0 < L - q_esc && esc > 0)) { dev_fail(A.err, DEVERR_POLY_RANGE, i); return; }
+    flags |= eb.kind << 16;
+    head[4] = eb.len; head[5] = eb.i0; head[6] = esc;
+  } else {
+    head[6] = L - q_esc;
+  }
+  head[0] = flags;
+  // unaligned gaps between consecutive 1-runs (:455-471)
+  int* rec = A.gap_rec + (i64)A.read_gap_off[i] * 3;
+  for (int k = ra; k + 1 < rb; ++k) {
+    int l1 = A.runs[k].y, f2 = A.runs[k + 1].x;
+    int qa, sa, qb, sb2;
+    if (!interval_end(A, i0, i1, fpos[l1 + 1], qa, sa)) { dev_fail(A.err, DEVERR_THREAD_CIGAR, i); return; }
+    if (!interval_start(A, i0, i1, fpos[f2], qb, sb2)) { dev_fail(A.err, DEVERR_THREAD_CIGAR, i); return; }
+    if (!(0 < qa && qa <= qb && qb < L)) { dev_fail(A.err, DEVERR_GAP_RANGE, i); return; }
+    int size = max(0, qb - qa + sa + sb2);
+    if (!(size < L)) { dev_fail(A.err, DEVERR_GAP_RANGE, i); return; }
+    rec[0] = l1; rec[1] = f2; rec[2] = size;
+    rec += 3;
+  }
+}

@@ -1,0 +1,82 @@
+"""Native host I/O: SPLIT parser and SEGMENT formatter of ``libfreddie_b200.so`` (csrc/host_io.cpp).
+
+Replaces the reference's regex parsing (read_split / read_sequence, freddie_segment.py:121-185) and
+its row formatting (:715-731) with multi-threaded C++ that reads the SPLIT files straight into the
+packed batch and writes the SEGMENT files straight from the result arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence, Tuple
+
+from . import _lib
+from .engine import Engine, SegmentParams
+
+
+def available() -> bool:
+    return hasattr(_lib.load(), "frs_parse_tints")
+
+
+def _paths(split_dir: str, outdir: str, chunk: Sequence[Tuple[str, int]]):
+    sp = [("{}/{}/split_{}_{}.tsv".format(split_dir, c, c, t)).encode() for c, t in chunk]
+    rp = [("{}/{}/reads_{}_{}.tsv".format(split_dir, c, c, t)).encode() for c, t in chunk]
+    op = [("{}/{}/segment_{}_{}.tsv".format(outdir, c, c, t)).encode() for c, t in chunk]
+    lp = [("{}/{}/segment_{}_{}.log".format(outdir, c, c, t)).encode() for c, t in chunk]
+    return sp, rp, op, lp
+
+
+class ParsedBatch:
+    """A batch parsed by the native parser; owns the C++ object."""
+
+    def __init__(self, split_paths: List[bytes], reads_paths: List[bytes], threads: int):
+        self.lib = _lib.load()
+        n = len(split_paths)
+        self.handle = C.c_void_p()
+        err = C.create_string_buffer(1024)
+        a = (C.c_char_p * n)(*split_paths)
+        b = (C.c_char_p * n)(*reads_paths)
+        rc = self.lib.frs_parse_tints(a, b, n, threads, C.byref(self.handle), err, len(err))
+        if rc != 0:
+            msg = err.value.decode(errors="replace")
+            if msg.startswith("AssertionError"):
+                raise AssertionError(msg)
+            raise _lib.FrsError(rc, msg)
+        self.struct = _lib.FrsBatch()
+        self.lib.frs_parsed_batch(self.handle, C.byref(self.struct))
+        self.n_tints = self.struct.n_tints
+        self.n_reads = self.struct.n_reads
+
+    def as_struct(self):
+        return self.struct
+
+    def format(self, res, out_paths: List[bytes], log_paths: List[bytes], threads: int):
+        n = len(out_paths)
+        err = C.create_string_buffer(1024)
+        r = res.as_struct()
+        rc = self.lib.frs_format_tints(self.handle, C.byref(r), (C.c_char_p * n)(*out_paths),
+                                       (C.c_char_p * n)(*log_paths), threads, err, len(err))
+        if rc != 0:
+            raise _lib.FrsError(rc, err.value.decode(errors="replace"))
+
+    def close(self):
+        if self.handle:
+            self.lib.frs_parsed_free(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def run_batch_native(eng: Engine, prm: SegmentParams, split_dir: str, outdir: str,
+                     chunk: Sequence[Tuple[str, int]], threads: int):
+    sp, rp, op, lp = _paths(split_dir, outdir, chunk)
+    pb = ParsedBatch(sp, rp, threads)
+    try:
+        res = eng.segment_batch(pb, prm)
+        pb.format(res, op, lp, threads)
+        return pb.n_reads, int(res.sizes["dp_cells"])
+    finally:
+        pb.close()

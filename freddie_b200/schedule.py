@@ -1,0 +1,60 @@
+"""Tint scheduling: cost estimates, LPT bin-packing across GPUs, memory-bounded batches.
+
+The reference's only parallelism is ``Pool.imap_unordered`` over tints (freddie_segment.py:871-876);
+tints never interact, so they are sharded across GPUs with no exchange step.
+"""
+from __future__ import annotations
+
+import os
+from typing import Iterable, List, Sequence, Tuple
+
+
+def estimate_reads_from_bytes(split_bytes: int) -> float:
+    """A split row is ~60 B of fixed fields plus ~25 B per interval."""
+    return max(1.0, split_bytes / 220.0)
+
+
+def estimate_cost(n_reads: float) -> float:
+    """Relative cost of a tint: streaming steps are linear in the reads; the DP tables grow with
+    candidates x reads, and the candidate count itself grows with the read count before saturating."""
+    k = min(n_reads, 40000.0) / 40.0 + 20.0  # rough candidate count
+    return n_reads * (1.0 + k / 50.0)
+
+
+def estimate_cost_from_files(split_dir: str, contig: str, tint_id: int) -> Tuple[float, float]:
+    """(cost, estimated reads) from the split file size alone -- no parsing."""
+    p = "{}/{}/split_{}_{}.tsv".format(split_dir, contig, contig, tint_id)
+    try:
+        b = os.path.getsize(p)
+    except OSError:
+        b = 0
+    n = estimate_reads_from_bytes(b)
+    return estimate_cost(n), n
+
+
+def lpt_partition(costs: Sequence[Tuple[float, float]], n_bins: int) -> List[List[int]]:
+    """Longest-processing-time-first: items by decreasing cost, each to the least-loaded bin.
+    Deterministic (ties broken by index)."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i][0], i))
+    load = [0.0] * n_bins
+    bins: List[List[int]] = [[] for _ in range(n_bins)]
+    for i in order:
+        b = min(range(n_bins), key=lambda j: (load[j], j))
+        bins[b].append(i)
+        load[b] += costs[i][0]
+    return bins
+
+
+def batches(jobs: Sequence, costs: Sequence[Tuple[float, float]], batch_reads: int) -> Iterable[List]:
+    """Consecutive jobs grouped so that the estimated reads of a batch stay under ``batch_reads``
+    (a single larger tint forms its own batch)."""
+    cur: List = []
+    acc = 0.0
+    for job, (_, n) in zip(jobs, costs):
+        if cur and acc + n > batch_reads:
+            yield cur
+            cur, acc = [], 0.0
+        cur.append(job)
+        acc += n
+    if cur:
+        yield cur

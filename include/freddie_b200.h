@@ -1,0 +1,198 @@
+/*
+ * freddie_b200.h -- C ABI of the B200-native segment stage (libfreddie_b200.so)
+ *
+ * The reference (vpc-ccg/freddie, py/freddie_segment.py) has no FFI: its boundary is the stage's CLI
+ * plus the in-process seam  segment(tint, sigma, smoothed_threshold, threshold_rate, variance_factor,
+ * max_problem_size, min_read_support_outside, ignore_ends)  (freddie_segment.py:738-747) that
+ * run_segment() (:681-735) calls once per tint.  This header is what a ctypes binding of that seam
+ * binds to: the Python host packs a batch of tints into flat arrays (frs_batch), one call runs every
+ * step of segment() for the whole batch on one GPU, and the results come back as flat arrays
+ * (frs_result) from which the SEGMENT rows (:715-731) are formatted.  INTEGRATION.md shows the stub.
+ *
+ * Conventions: every function returns 0 on success, <0 on error (message via frs_last_error).  The
+ * caller owns every host buffer; the library keeps no host pointer after a call returns.  One context
+ * per GPU, used by one host thread at a time; all device work is ordered on the context's stream.
+ * No torch types, no C++ types.  There is NO CPU fallback: without a CUDA device frs_create fails.
+ */
+#ifndef FREDDIE_B200_H
+#define FREDDIE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRS_ABI_VERSION 1
+
+/* error codes */
+#define FRS_OK 0
+#define FRS_ERR_CUDA (-1)        /* CUDA runtime failure */
+#define FRS_ERR_ARG (-2)         /* malformed batch / parameter (the reference would assert) */
+#define FRS_ERR_ASSERT (-3)      /* a data-dependent assert of the reference fired on the device */
+#define FRS_ERR_LIMIT (-4)       /* a documented size limit of this build was exceeded */
+#define FRS_ERR_STATE (-5)       /* calls out of order */
+#define FRS_ERR_IO (-6)          /* host file I/O (parser / formatter) */
+
+typedef struct frs_context frs_context;
+
+/* Flags of parse_args() (freddie_segment.py:53-110) plus the host-computed tables.
+ * thr_table      = smooth_threshold(tp) (:277-286), thr_table_len entries.
+ * gauss_w        = scipy's normalised kernel for truncate=4.0, 2*gauss_radius+1 doubles (:755).
+ * refine_w       = same for truncate=1.0 (refine_segmentation, :260-261).
+ * Both kernels are computed by numpy on the host so their bits match scipy's. */
+typedef struct {
+  double sigma;
+  double tp;
+  double vf;
+  int32_t mps;
+  int32_t lo;
+  int32_t ignore_ends;
+  int32_t thr_table_len;
+  const double* thr_table;
+  const double* gauss_w;
+  const double* refine_w;
+  int32_t gauss_radius;
+  int32_t refine_radius;
+} frs_params;
+
+/* A packed batch of tints (what read_split + read_sequence build, :121-185, as CSR arrays).
+ * "sample" = one position of an island, islands iterated s..e inclusive (:652-659); samples of all
+ * islands of all tints are concatenated ("flat" index).  Interval ends (te) are flat indices of the
+ * INCLUSIVE sample the reference uses (:205,:666-673). */
+typedef struct {
+  int32_t n_tints, n_islands, n_reps, n_rep_ivs, n_reads, n_read_ivs, n_cigar_ops, n_samples;
+  int64_t n_seq_words;
+  /* tints */
+  const int32_t* tint_island_off; /* [n_tints+1] */
+  const int32_t* tint_rep_off;    /* [n_tints+1] */
+  const int32_t* tint_read_off;   /* [n_tints+1] */
+  /* islands */
+  const int32_t* island_start;      /* [n_islands] genomic s */
+  const int32_t* island_sample_off; /* [n_islands+1] */
+  /* read reps (:165-170), any order inside a tint */
+  const int32_t* rep_iv_off; /* [n_reps+1] */
+  const int32_t* rep_weight; /* [n_reps] number of reads of the rep */
+  const int32_t* rep_iv_fs;  /* [n_rep_ivs] flat sample of ts */
+  const int32_t* rep_iv_fe;  /* [n_rep_ivs] flat sample of te */
+  /* reads, file order */
+  const int32_t* read_rep;     /* [n_reads] batch-global rep id */
+  const uint8_t* read_strand;  /* [n_reads] 0 '+', 1 '-' */
+  const int32_t* read_len;     /* [n_reads] len(seq) */
+  const int32_t* read_iv_off;  /* [n_reads+1] */
+  const int64_t* read_seq_off; /* [n_reads+1] word offsets into the bit-planes */
+  const int32_t* riv_ts;       /* [n_read_ivs] genomic target start */
+  const int32_t* riv_te;       /* [n_read_ivs] genomic target end */
+  const int32_t* riv_qs;       /* [n_read_ivs] query start */
+  const int32_t* riv_qe;       /* [n_read_ivs] query end */
+  const int32_t* riv_cig_off;  /* [n_read_ivs+1] */
+  const uint32_t* cigar;       /* [n_cigar_ops] (len << 4) | op, op: 0 M/X/=, 1 I, 2 D, 3 other */
+  const uint32_t* seq_is_a;    /* [n_seq_words] bit b of word w of a read = (seq[32w+b]=='A') */
+  const uint32_t* seq_is_t;    /* [n_seq_words] same for 'T' */
+} frs_batch;
+
+/* Sizes of the variable-length results of the batch that was just run. */
+typedef struct {
+  int64_t n_final;       /* total final positions */
+  int64_t n_digit_bytes; /* sum over tints of n_reps(t) * n_segs(t) */
+  int64_t n_gap_records; /* total "a-b:n" records */
+  int64_t n_candidates;  /* statistics */
+  int64_t n_subproblems;
+  int64_t dp_cells;      /* sum over subproblems of C(n,3)  (BASELINE metric "DP cell updates") */
+  int64_t dp_read_cells; /* sum of C(n,3) * n_reps(tint) */
+  int32_t max_subproblem;
+  int32_t pad;
+} frs_result_sizes;
+
+/* Caller-allocated result buffers (sizes from frs_result_sizes and the batch). */
+typedef struct {
+  int32_t* tint_final_off; /* [n_tints+1] */
+  int32_t* final_pos;      /* [n_final] genomic positions = tint['final_positions'] (:806) */
+  int64_t* tint_digit_off; /* [n_tints+1] byte offset of the tint's digit block */
+  uint8_t* digits;         /* [n_digit_bytes] ASCII '0'/'1'/'2'; row r_local of tint t starts at
+                              tint_digit_off[t] + r_local * (n_final(t)-1)   (:815-838) */
+  int32_t* read_head;      /* [n_reads*8] fixed part of every read's gaps field, see FRS_HEAD_* */
+  int32_t* read_gap_off;   /* [n_reads+1] */
+  int32_t* gap_rec;        /* [n_gap_records*3] (l1, f2, size) -> "{l1}-{f2}:{size}" (:455-471) */
+} frs_result;
+
+/* read_head layout (8 x int32 per read) */
+#define FRS_HEAD_FLAGS 0 /* bit0: read has a '1' digit (else the gaps field is empty, :372);
+                            bits 8-9: start poly kind (0 none, 1 'A', 2 'T'); bits 16-17: end poly kind */
+#define FRS_HEAD_S_LEN 1 /* "S{A|T}_{s_len}:{s_gap}" + "SSC:{ssc}"  or just "SSC:{ssc}" (:407-420) */
+#define FRS_HEAD_S_GAP 2
+#define FRS_HEAD_SSC 3
+#define FRS_HEAD_E_LEN 4 /* "E{A|T}_{e_len}:{e_gap}" + "ESC:{esc}"  or just "ESC:{esc}" (:438-454) */
+#define FRS_HEAD_E_GAP 5
+#define FRS_HEAD_ESC 6
+#define FRS_HEAD_RESERVED 7
+
+/* ---- context ---- */
+int frs_abi_version(void);
+int frs_device_count(void);
+int frs_create(int device, frs_context** out);
+void frs_destroy(frs_context* ctx);
+const char* frs_last_error(const frs_context* ctx); /* ctx may be NULL: last global error */
+void* frs_stream(frs_context* ctx);                 /* cudaStream_t of the context */
+
+/* ---- the hot path (replaces segment(), freddie_segment.py:738-844, for a batch of tints) ---- */
+/* H2D copy of the batch (async on the context stream; host arrays may be pinned or pageable). */
+int frs_upload(frs_context* ctx, const frs_batch* batch);
+/* Runs every kernel of the pipeline on the uploaded batch; may be called repeatedly. */
+int frs_run(frs_context* ctx, const frs_params* prm, frs_result_sizes* sizes);
+/* D2H copy of the results into caller buffers; synchronises the stream. */
+int frs_download(frs_context* ctx, const frs_result* out);
+/* upload + run + (caller allocates between) is the usual sequence; this convenience call does
+ * upload+run and leaves the download to the caller once it has sized its buffers. */
+int frs_segment_batch(frs_context* ctx, const frs_batch* batch, const frs_params* prm,
+                      frs_result_sizes* sizes);
+
+/* ---- debug taps for per-step parity tests (values of the LAST frs_run) ---- */
+enum {
+  FRS_TAP_Y_RAW = 1,      /* int32 [n_samples]   process_splicing_data (:648-678) */
+  FRS_TAP_Y = 2,          /* f64   [n_samples]   gaussian_filter1d (:755) */
+  FRS_TAP_THR = 3,        /* f64   [n_tints]     variance threshold (:757-759) */
+  FRS_TAP_CAND = 4,       /* int32 [n_candidates] flat sample index of each candidate (:615-621) */
+  FRS_TAP_FIXED = 5,      /* u8    [n_candidates] fixed flags after break_large_problems (:776-788) */
+  FRS_TAP_DP_FINAL = 6,   /* u8    [n_candidates] fixed | chosen by the DP (:793-801) */
+  FRS_TAP_SUB_START = 7,  /* int32 [n_subproblems] first candidate rank of each subproblem */
+  FRS_TAP_SUB_N = 8,      /* int32 [n_subproblems] size n */
+  FRS_TAP_COVERAGE = 9,   /* u32   cumulative coverage rows, see DESIGN.md */
+  FRS_TAP_INS = 10,       /* int32 ins tables */
+  FRS_TAP_OUT = 11,       /* int32 out tables */
+  FRS_TAP_COV_OFF = 12,   /* int64 [n_tints+1] element offset of each tint's coverage block */
+  FRS_TAP_SUB_PAIR_OFF = 13,   /* int64 [n_subproblems+1] */
+  FRS_TAP_SUB_TRIPLE_OFF = 14, /* int64 [n_subproblems+1] */
+};
+/* Copies min(cap_bytes, size) bytes of the tap to dst (host) and stores the full size in *bytes. */
+int frs_get_intermediate(frs_context* ctx, int which, void* dst, size_t cap_bytes, size_t* bytes);
+
+/* ---- per-kernel device timing of the last frs_run (CUDA events on the context stream) ---- */
+#define FRS_MAX_STAGES 32
+int frs_set_profiling(frs_context* ctx, int enabled);
+/* names[i] points to a static string; ms[i] is the summed duration of the stage's launches;
+ * launches[i] the number of kernel launches in it.  Returns the number of stages (<= FRS_MAX_STAGES). */
+int frs_get_timings(frs_context* ctx, const char** names, float* ms, int* launches);
+/* total kernel launches issued by the last frs_run */
+int frs_last_launch_count(frs_context* ctx);
+
+/* ---- host side: native SPLIT parser and SEGMENT formatter (read_split/read_sequence :121-185,
+ *      output :715-731).  See host_io.cpp. ---- */
+typedef struct frs_parsed frs_parsed;
+/* Parses the tints named by (split_paths[i], reads_paths[i]) with n_threads host threads into one
+ * packed batch owned by the returned object. */
+int frs_parse_tints(const char* const* split_paths, const char* const* reads_paths, int n, int n_threads,
+                    frs_parsed** out, char* err, size_t err_cap);
+/* Fills *batch with pointers into the parsed object (valid until frs_parsed_free). */
+int frs_parsed_batch(const frs_parsed* p, frs_batch* batch);
+void frs_parsed_free(frs_parsed* p);
+/* Writes segment_<contig>_<id>.tsv (+ empty .log) for every tint of the parsed batch into
+ * out_paths[i] (tsv) / log_paths[i]. */
+int frs_format_tints(const frs_parsed* p, const frs_result* res, const char* const* out_paths,
+                     const char* const* log_paths, int n_threads, char* err, size_t err_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FREDDIE_B200_H */
