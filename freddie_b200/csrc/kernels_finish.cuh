@@ -85,10 +85,11 @@ __global__ void __launch_bounds__(REF_THREADS) k_refine(int n_pf, const int* __r
       double hx = g[x];
       for (int d = 1; d < REF_SKIP && top; ++d) {
         int l = x - d, r = x + d;
-        if (l >= 0 && ps[l] == 1 && g[l] > hx) top = false;              // earlier peak wins only if strictly higher
-        if (r < len && ps[r] == 1 && g[r] >= hx) top = false;            // later peak wins ties
+        // state 4 = marked "keep" earlier in this same round by another thread: still a competitor
+        if (l >= 0 && (ps[l] == 1 || ps[l] == 4) && g[l] > hx) top = false;    // earlier peak wins only if strictly higher
+        if (r < len && (ps[r] == 1 || ps[r] == 4) && g[r] >= hx) top = false;  // later peak wins ties
       }
-      if (top) ps[x] = 4;  // provisional keep (not yet visible as "kept" to this round's readers)
+      if (top) ps[x] = 4;  // provisional keep
     }
     __syncthreads();
     for (int x = tid; x < len; x += REF_THREADS) {

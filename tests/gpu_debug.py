@@ -97,6 +97,19 @@ def check_set(eng, name):
         d = first_diff(g, o)
         print("   %-9s %s" % (label, "ok" if d is None else "MISMATCH " + d))
         bad += d is not None
+    # final positions
+    fo = res.arrays["tint_final_off"]
+    for t, (ot, it) in enumerate(zip(otints, inters)):
+        g = res.arrays["final_pos"][fo[t]:fo[t + 1]].tolist()
+        o = ot["final_positions"]
+        if g != o:
+            sg, so = set(g), set(o)
+            extra = set()
+            for a, (s0, e0) in enumerate(ot["intervals"]):
+                extra |= {s0 + x for x in it["refine"][a]}
+            print("   tint %d finals: gpu-only %s  oracle-only %s (oracle-only that are refine extras: %s)" % (
+                t, sorted(sg - so)[:10], sorted(so - sg)[:10], sorted((so - sg) & extra)[:10]))
+            bad += 1
     # end to end text
     n_bad_t = 0
     for t, ot in enumerate(otints):
