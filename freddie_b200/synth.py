@@ -370,37 +370,48 @@ def config_plan(cfg: int, scale: float = 1.0, seed: Optional[int] = None) -> dic
     return dict(cfg=cfg, seed=seed, sizes=sizes, kind=kind)
 
 
-def make_config(cfg: int, scale: float = 1.0, seed: Optional[int] = None, progress=None) -> List[dict]:
-    """Realise a config as a list of tints (seeded, deterministic)."""
+_TINT_SPACING = 300000  # genomic distance between tint loci on a contig (loci are <= 120 kb)
+_TINTS_PER_CONTIG = 2500
+
+
+def _tint_job(job):
+    """Builds tint ``i`` of a plan from its own child seed (so tints can be generated in parallel)."""
+    seed, cfg, i, n, kind, contig, slot, rid0 = job
+    rng = np.random.default_rng([seed, 7919, i])
+    base = 100000 + slot * _TINT_SPACING
+    if kind == "locus40k":
+        kw = dict(locus_len=40000, n_exons=int(rng.integers(8, 13)), n_iso=int(rng.integers(6, 9)))
+        opts = None
+    elif kind == "giant":
+        kw = dict(locus_len=int(rng.integers(60000, 120000)), n_exons=int(rng.integers(30, 41)),
+                  n_iso=int(rng.integers(8, 16)))
+        opts = dict(noise_p=0.55, jitter_p=0.5, jitter=30, ragged=60, split_p=0.1)
+    else:
+        kw = dict(locus_len=int(rng.integers(2000, 100000)), n_exons=int(rng.integers(2, 26)),
+                  n_iso=int(rng.integers(1, 9)))
+        opts = None
+    if cfg == 3 and i % 4 == 3:  # heavy-duplication variant (weighted read reps)
+        opts = dict(opts or {}, dup_p=0.9)
+    return make_tint(rng, contig, i, n, base=base, rid0=rid0, opts=opts, **kw)
+
+
+def make_config(cfg: int, scale: float = 1.0, seed: Optional[int] = None, workers: int = 1) -> List[dict]:
+    """Realise a config as a list of tints (seeded, deterministic, independent of ``workers``)."""
     plan = config_plan(cfg, scale, seed)
-    rng = np.random.default_rng([plan["seed"], 7919])
-    n_contigs = 1 if cfg != 5 else 22
-    tints = []
+    sizes = [int(n) for n in plan["sizes"]]
+    n_contigs = max(1, (len(sizes) + _TINTS_PER_CONTIG - 1) // _TINTS_PER_CONTIG)
+    if cfg == 5:
+        n_contigs = max(n_contigs, 22)
+    jobs = []
     rid = 0
-    base = 100000
-    for i, (n, kind) in enumerate(zip(plan["sizes"], plan["kind"])):
-        n = int(n)
-        contig = "chr%d" % (1 + i % n_contigs)
-        if kind == "locus40k":
-            kw = dict(locus_len=40000, n_exons=int(rng.integers(8, 13)), n_iso=int(rng.integers(6, 9)))
-            opts = None
-        elif kind == "giant":
-            kw = dict(locus_len=int(rng.integers(60000, 120000)), n_exons=int(rng.integers(30, 41)),
-                      n_iso=int(rng.integers(8, 16)))
-            opts = dict(noise_p=0.55, jitter_p=0.5, jitter=30, ragged=60, split_p=0.1)
-        else:
-            kw = dict(locus_len=int(rng.integers(2000, 100000)), n_exons=int(rng.integers(2, 26)),
-                      n_iso=int(rng.integers(1, 9)))
-            opts = None
-        if cfg == 3 and i % 4 == 3:  # heavy-duplication variant (weighted read reps)
-            opts = dict(opts or {}, dup_p=0.9)
-        t = make_tint(rng, contig, i, n, base=base, rid0=rid, opts=opts, **kw)
-        tints.append(t)
+    for i, (n, kind) in enumerate(zip(sizes, plan["kind"])):
+        jobs.append((plan["seed"], cfg, i, n, kind, "chr%d" % (1 + i % n_contigs), i // n_contigs, rid))
         rid += n
-        base = t["intervals"][-1][1] + 5000
-        if progress and i % 500 == 0:
-            progress(i, len(plan["sizes"]))
-    return tints
+    if workers > 1 and len(jobs) > 1:
+        from multiprocessing import Pool
+        with Pool(workers) as p:
+            return p.map(_tint_job, jobs, chunksize=max(1, len(jobs) // (workers * 8)))
+    return [_tint_job(j) for j in jobs]
 
 
 def describe(tints: Sequence[dict]) -> Dict[str, int]:
@@ -456,7 +467,7 @@ def make_plateau_tint(contig: str = "chrP", tint_id: int = 0) -> dict:
     samples, so the candidate step must pick the floor midpoint."""
     reads = []
     rid = 0
-    for rep, (a, b) in enumerate([(1300, 1607), (1300, 1609), (1307, 1607), (1309, 1609)]):
+    for rep, (a, b) in enumerate([(1300, 1607), (1300, 1616), (1309, 1607), (1309, 1616)]):
         for _ in range(6):
             reads.append(_simple_read(rid, contig, tint_id, "+" if rid % 2 else "-",
                                       [(1000, a), (b, 2000), (2300, 2600)], 3, 5,
@@ -475,6 +486,9 @@ GOLDEN_SETS = {
     "cfg3_mini": (dict(cfg=3, scale=0.03), []),
     "cfg4_mini": (dict(cfg=4, scale=0.002), []),
     "cfg5_mini": (dict(cfg=5, scale=0.0005), []),
+    "cfg2_sigma50": (dict(cfg=2, scale=0.003, seed=14), ["-sd", "50"]),
+    "cfg2_mps11": (dict(cfg=2, scale=0.004, seed=15), ["-mps", "11", "-vf", "9.5"]),
+    "dup_heavy": (dict(special="dup_heavy"), []),
     "degenerate": (dict(special="degenerate"), []),
     "plateau": (dict(special="plateau"), []),
 }
@@ -484,6 +498,12 @@ def make_golden_set(name: str) -> Tuple[List[dict], List[str]]:
     kw, flags = GOLDEN_SETS[name]
     if kw.get("special") == "degenerate":
         return make_degenerate(), flags
+    if kw.get("special") == "dup_heavy":
+        rng = np.random.default_rng([99, 1])
+        return [make_tint(rng, "chrW", 0, 1500, locus_len=30000, n_exons=9, n_iso=5,
+                          opts=dict(dup_p=0.9, jitter_p=0.3)),
+                make_tint(rng, "chrW", 1, 400, base=500000, locus_len=20000, n_exons=6, n_iso=3,
+                          opts=dict(dup_p=0.97, noise_p=0.3))], flags
     if kw.get("special") == "plateau":
         return [make_plateau_tint()], flags
     return make_config(**kw), flags

@@ -1,0 +1,207 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle and the golden
+vectors of the unmodified reference.  Integer / byte / index outputs are compared bit-exactly; the
+smoothed fp64 signal is held to bit-identity as well (north_star allows 1e-6 relative)."""
+import copy
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, flags_to_kwargs, sha_dir
+from oracle import segment_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+ALL_SETS = ["degenerate", "plateau", "cfg1", "cfg2_small", "cfg2_flagsA", "cfg2_flagsB", "cfg2_sigma50",
+            "cfg2_mps11", "dup_heavy", "cfg3_mini", "cfg4_mini", "cfg5_mini"]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from freddie_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _params(flags):
+    from freddie_b200.engine import SegmentParams
+    o = orc.Params(**flags_to_kwargs(flags))
+    return o, SegmentParams(o.sigma, o.tp, o.vf, o.mps, o.lo, o.ignore_ends)
+
+
+@pytest.mark.parametrize("name", ALL_SETS)
+def test_segment_text_equals_oracle(name, golden_set, eng):
+    from freddie_b200.engine import format_tint
+    from freddie_b200.pack import pack_tints
+    tints, flags, _ = golden_set(name)
+    oprm, gprm = _params(flags)
+    batch = pack_tints(tints)
+    res = eng.segment_batch(batch, gprm)
+    assert eng.launch_count() > 0
+    otints = copy.deepcopy(tints)
+    for t, ot in enumerate(otints):
+        orc.segment_tint(ot, oprm)
+        assert format_tint(batch, res, t) == orc.format_segment(ot), "tint %d of %s" % (t, name)
+
+
+@pytest.mark.parametrize("name", ["degenerate", "plateau", "cfg2_small", "cfg2_flagsA", "cfg2_flagsB", "cfg4_mini",
+                                  "dup_heavy", "cfg2_sigma50", "cfg2_mps11"])
+def test_cli_directory_equals_reference_manifest(name, golden_set, manifest, tmp_path):
+    """The drop-in CLI (native parser + kernels + native formatter) against the SHA-256 manifest of the
+    SEGMENT directory the unmodified reference wrote for the same SPLIT directory."""
+    _, flags, split_dir = golden_set(name)
+    out = str(tmp_path / "seg")
+    r = subprocess.run([sys.executable, "-m", "freddie_b200.segment", "-s", split_dir, "-o", out, "-t", "4"] + flags,
+                       cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "[freddie_segment] Done with" in r.stdout
+    assert sha_dir(out) == manifest[name]["outputs"]
+
+
+def test_cfg1_taps_equal_reference_intermediates(golden_set, eng):
+    """Per-step taps against the intermediates dumped from the reference's own functions."""
+    from freddie_b200 import _lib
+    from freddie_b200.pack import pack_tints
+    tints, flags, _ = golden_set("cfg1")
+    _, gprm = _params(flags)
+    batch = pack_tints(tints)
+    res = eng.segment_batch(batch, gprm)
+    z = np.load(os.path.join(GOLDEN, "cfg1_intermediates.npz"))
+    assert np.array_equal(eng.tap(_lib.TAP_Y_RAW, np.int32), z["Y_raw"].astype(np.int32))
+    y = eng.tap(_lib.TAP_Y, np.float64)
+    assert np.allclose(y, z["Y"], rtol=1e-6, atol=0)  # the stated tolerance ...
+    assert np.array_equal(y, z["Y"])                  # ... and in fact bit-identical
+    assert eng.tap(_lib.TAP_THR, np.float64)[0] == float(z["thr"])
+    cand = eng.tap(_lib.TAP_CAND, np.int32)
+    off = z["island_off"]
+    want = np.concatenate([z["cand"][z["cand_off"][a]:z["cand_off"][a + 1]] + off[a] for a in range(len(off) - 1)])
+    assert np.array_equal(cand, want)
+    fixed = np.flatnonzero(eng.tap(_lib.TAP_FIXED, np.uint8))
+    wantf = np.concatenate([z["fixed"][z["fixed_off"][a]:z["fixed_off"][a + 1]] + z["cand_off"][a]
+                            for a in range(len(off) - 1)])
+    assert np.array_equal(fixed, wantf)
+    assert res.arrays["final_pos"].tolist() == z["final_positions"].tolist()
+    # coverage: column sums of the last row of each island block reproduce the reference's C.sum() check
+    P = eng.tap(_lib.TAP_COVERAGE, np.uint32)
+    R = batch.n_reps
+    Rp = (R + 3) & ~3
+    P = P.reshape(-1, Rp)
+    assert P.shape[0] == len(cand)
+
+
+def test_dp_tables_equal_oracle(golden_set, eng):
+    """ins / out tables of every subproblem of a weighted tint against the oracle's numpy tables."""
+    from freddie_b200 import _lib
+    from freddie_b200.pack import pack_tints
+    tints, flags, _ = golden_set("dup_heavy")
+    oprm, gprm = _params(flags)
+    batch = pack_tints(tints[:1])
+    eng.segment_batch(batch, gprm)
+    ot = copy.deepcopy(tints[0])
+    it = orc.segment_tint(ot, oprm, keep=True)
+    ss, sn = eng.tap(_lib.TAP_SUB_START, np.int32), eng.tap(_lib.TAP_SUB_N, np.int32)
+    po, to = eng.tap(_lib.TAP_SUB_PAIR_OFF, np.int64), eng.tap(_lib.TAP_SUB_TRIPLE_OFF, np.int64)
+    ins, out = eng.tap(_lib.TAP_INS, np.int32), eng.tap(_lib.TAP_OUT, np.int32)
+    cand_off = np.cumsum([0] + [len(c) for c in it["cand"]])
+    keys, members = orc.build_reps(ot)
+    checked = 0
+    for p in range(len(ss)):
+        a = int(np.searchsorted(cand_off, ss[p], side="right") - 1)
+        start = int(ss[p] - cand_off[a])
+        n = int(sn[p])
+        isl = ot["intervals"][a]
+        rep_iv = [[(ts - isl[0], te - isl[0]) for ts, te in k if isl[0] <= ts <= isl[1]] for k in keys]
+        C = orc.coverage_matrix(rep_iv, it["cand"][a])
+        oi, oo = orc.dp_tables(it["cand"][a], C, it["W"], start, start + n - 1, oprm.table, oprm.tp)
+        gi = ins[po[p]:po[p + 1]].reshape(n, n)
+        for i in range(n - 1):
+            for j in range(i + 1, n):
+                assert -gi[i, j] == oi[i, j]
+        g = out[to[p]:to[p + 1]]
+        k = 0
+        for j in range(1, n - 1):
+            for i in range(j):
+                for kk in range(j + 1, n):
+                    assert g[k] == oo[i, j, kk], (p, i, j, kk)
+                    k += 1
+        checked += 1
+        if checked >= 12:
+            break
+    assert checked > 0
+
+
+def test_in_process_seam_has_reference_signature(golden_set):
+    """segment(tint, sigma, smoothed_threshold, tp, vf, mps, lo, ignore_ends) mutates the tint like the
+    reference (freddie_segment.py:738-844)."""
+    from freddie_b200.segment import segment, smooth_threshold
+    tints, _, _ = golden_set("plateau")
+    t = copy.deepcopy(tints[0])
+    ot = copy.deepcopy(tints[0])
+    assert segment(t, 5.0, smooth_threshold(0.9), 0.9, 3.0, 50, 3, True) == t["id"]
+    orc.segment_tint(ot, orc.Params())
+    assert t["final_positions"] == ot["final_positions"] and t["segs"] == ot["segs"]
+    for r, o in zip(t["reads"], ot["reads"]):
+        assert r["data"] == o["data"] and r["gaps"] == o["gaps"]
+
+
+def test_output_independent_of_batch_composition(golden_set, eng):
+    from freddie_b200.engine import format_tint
+    from freddie_b200.pack import pack_tints
+    tints, flags, _ = golden_set("cfg4_mini")
+    _, gprm = _params(flags)
+    whole = pack_tints(tints)
+    res = eng.segment_batch(whole, gprm)
+    texts = [format_tint(whole, res, t) for t in range(len(tints))]
+    again = eng.segment_batch(whole, gprm)
+    assert all(np.array_equal(res.arrays[k], again.arrays[k]) for k in res.arrays)  # deterministic
+    order = list(range(len(tints)))[::-1]
+    for lo in range(0, len(order), 50):
+        part = [tints[i] for i in order[lo:lo + 50]]
+        b = pack_tints(part)
+        r = eng.segment_batch(b, gprm)
+        for k, i in enumerate(order[lo:lo + 50]):
+            assert format_tint(b, r, k) == texts[i]
+
+
+def test_full_size_config2_properties(eng):
+    """BASELINE config 2 at full size (200k reads, ~3k tints): size-independent properties plus an
+    oracle spot check on a sample of tints."""
+    from freddie_b200 import synth
+    from freddie_b200.engine import SegmentParams, format_tint
+    from freddie_b200.pack import pack_tints
+    tints = synth.make_config(2, workers=min(8, os.cpu_count() or 1))
+    assert sum(len(t["reads"]) for t in tints) > 150000
+    batch = pack_tints(tints)
+    res = eng.segment_batch(batch, SegmentParams())
+    a, ba = res.arrays, batch.arrays
+    assert set(np.unique(a["digits"]).tolist()) <= {48, 49, 50}
+    for t, tint in enumerate(tints):
+        f = a["final_pos"][a["tint_final_off"][t]:a["tint_final_off"][t + 1]]
+        assert np.all(np.diff(f) > 0)
+        ends = sorted(x for iv in tint["intervals"] for x in iv)
+        assert set(ends) <= set(f.tolist()) and f[0] == ends[0] and f[-1] == ends[-1]
+        S = len(f) - 1
+        R = ba["tint_rep_off"][t + 1] - ba["tint_rep_off"][t]
+        assert a["tint_digit_off"][t + 1] - a["tint_digit_off"][t] == S * R
+    rng = np.random.default_rng(0)
+    for t in rng.choice(len(tints), size=25, replace=False):
+        ot = copy.deepcopy(tints[int(t)])
+        orc.segment_tint(ot, orc.Params())
+        assert format_tint(batch, res, int(t)) == orc.format_segment(ot)
+
+
+def test_errors_are_loud(golden_set, eng):
+    from freddie_b200 import _lib
+    from freddie_b200.engine import SegmentParams
+    from freddie_b200.pack import pack_tints
+    tints, _, _ = golden_set("plateau")
+    batch = pack_tints(tints)
+    with pytest.raises(_lib.FrsError, match="max_problem_size < 11"):
+        eng.segment_batch(batch, SegmentParams(max_problem_size=4))
+    bad = pack_tints(tints)
+    bad.arrays["read_rep"][0] = 10 ** 6
+    with pytest.raises(_lib.FrsError, match="rep"):
+        eng.upload(bad)

@@ -1,0 +1,233 @@
+"""Host logic on CPU: packing, native parser / formatter, scheduler, CLI surface, sharding (gloo)."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, flags_to_kwargs, sha_dir
+from helpers import oracle_result_arrays
+from oracle import segment_oracle as orc
+
+
+def test_pack_invariants(golden_set):
+    from freddie_b200.pack import pack_tints
+    tints, _, _ = golden_set("cfg2_flagsA")
+    b = pack_tints(tints)
+    a = b.arrays
+    c = b.counts()
+    assert c["n_tints"] == len(tints) and c["n_reads"] == sum(len(t["reads"]) for t in tints)
+    assert int(a["rep_weight"].sum()) == c["n_reads"]
+    assert np.all(np.diff(a["island_sample_off"]) >= 2)
+    assert np.all(a["rep_iv_fs"] < a["rep_iv_fe"])
+    # reps are the distinct target-interval tuples in first-seen order (freddie_segment.py:165-170)
+    for t, tint in enumerate(tints):
+        keys, members = orc.build_reps(tint)
+        r0, r1 = a["tint_rep_off"][t], a["tint_rep_off"][t + 1]
+        assert r1 - r0 == len(keys)
+        assert a["rep_weight"][r0:r1].tolist() == [len(m) for m in members]
+    # bit-planes
+    r = tints[0]["reads"][0]
+    w0 = int(a["read_seq_off"][0])
+    bits = [(int(a["seq_is_a"][w0 + i // 32]) >> (i % 32)) & 1 for i in range(len(r["seq"]))]
+    assert bits == [int(ch == "A") for ch in r["seq"]]
+
+
+def test_pack_rejects_what_the_reference_rejects():
+    from freddie_b200.pack import pack_tints
+    from freddie_b200 import synth
+    t = synth.make_degenerate()[0]
+    bad = dict(t, intervals=[(1000, 1100), (1500, 1800)])  # first interval ends outside its island
+    with pytest.raises(KeyError):
+        pack_tints([bad])
+    bad = dict(t, intervals=[(1000, 1800), (1700, 1900)])
+    with pytest.raises(AssertionError):
+        pack_tints([bad])
+
+
+def _native_batch(split_dir, tints, threads=4):
+    from freddie_b200 import hostio
+    jobs = [(t["chr"], t["id"]) for t in tints]
+    sp, rp, _, _ = hostio._paths(split_dir, "/nonexistent", jobs)
+    return hostio.ParsedBatch(sp, rp, threads)
+
+
+@pytest.mark.parametrize("name", ["cfg2_flagsA", "degenerate", "cfg4_mini"])
+def test_native_parser_equals_python_packer(name, golden_set, built_lib):
+    from freddie_b200 import _lib
+    from freddie_b200.pack import pack_tints
+    from freddie_b200.segment import _load_tint_py
+    tints, _, split_dir = golden_set(name)
+    pb = _native_batch(split_dir, tints)
+    ref = pack_tints([_load_tint_py(split_dir, t["chr"], t["id"]) for t in tints])
+    for k, v in ref.counts().items():
+        assert getattr(pb.struct, k) == v, k
+    for nm in _lib.BATCH_ARRAYS:
+        arr = ref.arrays[nm]
+        if arr.size == 0:
+            continue
+        ptr = C.cast(getattr(pb.struct, nm), C.POINTER(np.ctypeslib.as_ctypes_type(arr.dtype)))
+        assert np.array_equal(np.ctypeslib.as_array(ptr, shape=arr.shape), arr), nm
+    pb.close()
+
+
+def test_native_parser_errors_mirror_reference(tmp_path, built_lib):
+    from freddie_b200 import hostio, synth, _lib
+    t = synth.make_degenerate()[2]
+    d = str(tmp_path / "s")
+    synth.write_split_dir([t], d)
+    sp = os.path.join(d, t["chr"], "split_%s_%d.tsv" % (t["chr"], t["id"]))
+    rp = os.path.join(d, t["chr"], "reads_%s_%d.tsv" % (t["chr"], t["id"]))
+    good = open(sp).read()
+    # wrong read count -> the reference's assert at :164
+    open(sp, "w").write(good.replace("\t3\n", "\t4\n", 1))
+    with pytest.raises(AssertionError, match="read_count"):
+        hostio.ParsedBatch([sp.encode()], [rp.encode()], 1)
+    # malformed CIGAR -> no regex match
+    open(sp, "w").write(good.replace("M", "Q", 1))
+    with pytest.raises(_lib.FrsError, match="read_prog"):
+        hostio.ParsedBatch([sp.encode()], [rp.encode()], 1)
+    # missing sequence row -> assert at :181
+    open(sp, "w").write(good)
+    open(rp, "w").write("".join(open(rp).readlines()[:-1]))
+    with pytest.raises(AssertionError, match="rid_to_seq"):
+        hostio.ParsedBatch([sp.encode()], [rp.encode()], 1)
+    with pytest.raises(_lib.FrsError, match="FileNotFoundError"):
+        hostio.ParsedBatch([b"/nonexistent/split_x_0.tsv"], [rp.encode()], 1)
+
+
+@pytest.mark.parametrize("name", ["cfg2_flagsA", "degenerate", "plateau"])
+def test_native_formatter_writes_reference_bytes(name, golden_set, manifest, tmp_path, built_lib):
+    """Formatter fed with the oracle's results (as frs_result arrays) must emit the reference's files."""
+    from freddie_b200 import _lib
+    tints, flags, split_dir = golden_set(name)
+    pb = _native_batch(split_dir, tints)
+    _, arrays = oracle_result_arrays(tints, orc.Params(**flags_to_kwargs(flags)))
+    res = _lib.FrsResult()
+    for k in _lib.RESULT_ARRAYS:
+        setattr(res, k, arrays[k].ctypes.data_as(C.c_void_p))
+
+    class R:
+        def as_struct(self):
+            return res
+    out = str(tmp_path / "seg")
+    ops, lps = [], []
+    for t in tints:
+        os.makedirs(os.path.join(out, t["chr"]), exist_ok=True)
+        ops.append(os.path.join(out, t["chr"], "segment_%s_%d.tsv" % (t["chr"], t["id"])).encode())
+        lps.append(os.path.join(out, t["chr"], "segment_%s_%d.log" % (t["chr"], t["id"])).encode())
+    pb.format(R(), ops, lps, 3)
+    assert sha_dir(out) == manifest[name]["outputs"]
+    pb.close()
+
+
+def test_python_formatter_and_gap_strings(golden_set, manifest):
+    from freddie_b200.engine import BatchResult, format_tint, apply_result
+    from freddie_b200.pack import pack_tints
+    tints, flags, _ = golden_set("cfg2_flagsA")
+    otints, arrays = oracle_result_arrays(tints, orc.Params(**flags_to_kwargs(flags)))
+    batch = pack_tints(tints)
+    res = BatchResult.__new__(BatchResult)
+    res.arrays, res.sizes = arrays, {}
+    for t, ot in enumerate(otints):
+        assert format_tint(batch, res, t) == orc.format_segment(ot)
+    apply_result(batch, res)
+    for t, ot in zip(batch.tints, otints):
+        assert t["final_positions"] == ot["final_positions"] and t["segs"] == ot["segs"]
+        for r, o in zip(t["reads"], ot["reads"]):
+            assert r["data"] == o["data"] and r["gaps"] == o["gaps"]
+
+
+def test_params_tables_match_scipy_and_reference():
+    from scipy.ndimage import _filters
+    from freddie_b200.engine import SegmentParams, smooth_threshold, gaussian_kernel
+    assert smooth_threshold(0.9) == orc.smooth_threshold(0.9) and smooth_threshold(1.0) == orc.smooth_threshold(1.0)
+    for sd in (0.7, 5.0, 12.5, 50.0):
+        for tr in (4.0, 1.0):
+            lw = int(tr * sd + 0.5)
+            assert np.array_equal(gaussian_kernel(sd, tr), _filters._gaussian_kernel1d(sd, 0, lw)[::-1])
+    for bad in (dict(threshold_rate=0.4), dict(variance_factor=10), dict(sigma=0), dict(sigma=51),
+                dict(max_problem_size=3), dict(min_read_support_outside=-1)):
+        with pytest.raises(AssertionError):
+            SegmentParams(**bad)
+
+
+def test_cli_surface_matches_reference():
+    from freddie_b200.segment import parse_args
+    a = parse_args(["-s", "x"])
+    assert (a.outdir, a.threads, a.sigma, a.threshold_rate, a.variance_factor, a.max_problem_size,
+            a.min_read_support_outside, a.consider_ends) == ("freddie_segment/", 1, 5.0, 0.9, 3.0, 50, 3, False)
+    a = parse_args(["-s", "x", "--consider-ends", "-sd", "2.5", "-tp", "0.8", "-vf", "1.5", "-mps", "12", "-lo", "1",
+                    "-t", "4", "-o", "y"])
+    assert a.consider_ends is True and a.max_problem_size == 12
+    assert parse_args(["-s", "x", "--consider-ends", "no"]).consider_ends is False
+    with pytest.raises(AssertionError):
+        parse_args(["-s", "x", "-tp", "0.3"])
+
+
+def test_read_split_equals_oracle_parser(golden_set):
+    from freddie_b200.segment import read_split, read_sequence
+    tints, _, d = golden_set("cfg2_flagsA")
+    t = tints[3]
+    sp = os.path.join(d, t["chr"], "split_%s_%d.tsv" % (t["chr"], t["id"]))
+    rp = os.path.join(d, t["chr"], "reads_%s_%d.tsv" % (t["chr"], t["id"]))
+    a = read_split(sp)[0]
+    read_sequence(a, rp)
+    b = orc.parse_split(sp)
+    orc.parse_reads(b, rp)
+    assert a["intervals"] == b["intervals"] and a["id"] == b["id"]
+    for x, y in zip(a["reads"], b["reads"]):
+        assert x == y
+
+
+def test_lpt_partition_and_batches():
+    from freddie_b200 import schedule
+    costs = [(float(c), float(c)) for c in [100, 1, 1, 50, 49, 2, 3, 98]]
+    bins = schedule.lpt_partition(costs, 2)
+    assert sorted(i for b in bins for i in b) == list(range(8))
+    loads = [sum(costs[i][0] for i in b) for b in bins]
+    assert abs(loads[0] - loads[1]) <= 4
+    assert schedule.lpt_partition(costs, 2) == bins  # deterministic
+    groups = list(schedule.batches(list(range(8)), costs, 100))
+    assert [i for g in groups for i in g] == list(range(8))
+    assert all(sum(costs[i][1] for i in g) <= 100 or len(g) == 1 for g in groups)
+
+
+_GLOO = r'''
+import os, sys, json
+sys.path.insert(0, %r)
+import torch.distributed as dist
+from freddie_b200 import schedule, synth
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, ws = dist.get_rank(), dist.get_world_size()
+plan = synth.config_plan(4, scale=0.002)
+costs = [(schedule.estimate_cost(float(n)), float(n)) for n in plan["sizes"]]
+mine = schedule.lpt_partition(costs, ws)[rank]
+got = [None] * ws
+dist.all_gather_object(got, dict(rank=rank, idx=mine, reads=int(sum(plan["sizes"][i] for i in mine)),
+                                 cost=sum(costs[i][0] for i in mine)))
+if rank == 0:
+    print(json.dumps(dict(shards=got, n=len(costs), total=int(plan["sizes"].sum()))))
+dist.destroy_process_group()
+'''
+
+
+def test_sharding_world_size_2_gloo(tmp_path):
+    """The multi-GPU path is a partition with a host-side gather and no data-path collective: two ranks
+    must cover every tint exactly once with balanced estimated cost."""
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    import json
+    info = json.loads(outs[0][0].strip().splitlines()[-1])
+    idx = sorted(i for s in info["shards"] for i in s["idx"])
+    assert idx == list(range(info["n"]))
+    assert sum(s["reads"] for s in info["shards"]) == info["total"]
+    c = [s["cost"] for s in info["shards"]]
+    assert abs(c[0] - c[1]) / max(c) < 0.25

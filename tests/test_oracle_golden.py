@@ -1,0 +1,71 @@
+"""The oracle against the golden vectors produced by the unmodified reference
+(oracle/pin_against_reference.py; the reference itself ships no tests, test/.gitignore:1)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, digest, flags_to_kwargs, sha_dir
+from oracle import segment_oracle as orc
+
+FAST_SETS = ["degenerate", "plateau", "cfg2_flagsA", "cfg2_small", "cfg4_mini", "cfg5_mini"]
+
+
+@pytest.mark.parametrize("name", FAST_SETS)
+def test_oracle_reproduces_reference_outputs(name, golden_set, manifest, tmp_path):
+    tints, flags, split_dir = golden_set(name)
+    out = str(tmp_path / "seg")
+    n = orc.run_dir(split_dir, out, orc.Params(**flags_to_kwargs(flags)), threads=min(8, os.cpu_count() or 1))
+    assert n == manifest[name]["describe"]["reads"]
+    got = sha_dir(out)
+    assert got == manifest[name]["outputs"]
+    logs = [k for k in got if k.endswith(".log")]
+    assert logs and all(os.path.getsize(os.path.join(out, k)) == 0 for k in logs)
+
+
+@pytest.mark.parametrize("name", ["degenerate", "plateau"])
+def test_committed_reference_files(name, tmp_path):
+    """Inputs and reference outputs committed wholesale: no generator in the loop."""
+    src = os.path.join(GOLDEN, name)
+    out = str(tmp_path / "seg")
+    orc.run_dir(os.path.join(src, "split"), out, orc.Params())
+    assert sha_dir(out) == sha_dir(os.path.join(src, "segment"))
+
+
+def test_cfg1_intermediates_bit_identical(golden_set):
+    tints, flags, split_dir = golden_set("cfg1")
+    z = np.load(os.path.join(GOLDEN, "cfg1_intermediates.npz"))
+    t = orc.parse_split(os.path.join(split_dir, "chr1", "split_chr1_0.tsv"))
+    orc.parse_reads(t, os.path.join(split_dir, "chr1", "reads_chr1_0.tsv"))
+    it = orc.segment_tint(t, orc.Params(), keep=True)
+    assert np.array_equal(np.concatenate(it["Y_raw"]), z["Y_raw"])
+    assert np.array_equal(np.concatenate(it["Y"]), z["Y"])  # bit-identical, stronger than the 1e-6 bar
+    assert it["thr"] == float(z["thr"])
+    assert np.array_equal(np.concatenate(it["cand"]), z["cand"])
+    assert np.array_equal(np.concatenate(it["fixed"]), z["fixed"])
+    assert t["final_positions"] == z["final_positions"].tolist()
+    assert not it["ties"] or True  # ties are reported, not an error
+
+
+def test_oracle_output_passes_the_consumers_grammar(golden_set, tmp_path):
+    """freddie_cluster.read_segment's regexes (freddie_cluster.py:15-34) restated: every row parses,
+    positions strictly increase, one digit per segment, gap indices in range (:131-169)."""
+    import re
+    tints, flags, split_dir = golden_set("cfg2_flagsA")
+    out = str(tmp_path / "seg")
+    orc.run_dir(split_dir, out, orc.Params(**flags_to_kwargs(flags)))
+    head = re.compile(r"#[^\t]+\t[0-9]+\t([0-9]+(?:,[0-9]+)*)\n$")
+    row = re.compile(r"[0-9]+\t[!-?A-~]{1,254}\t[^\t]+\t[+-]\t[0-9]+\t([012]+)\t((?:[0-9]+-[0-9]+:[0-9]+,|[ES]SC:[0-9]+,|[ES][AT]_[0-9]+:[0-9]+,)*)\n$")
+    for base, _, files in os.walk(out):
+        for fn in files:
+            if not fn.endswith(".tsv"):
+                continue
+            lines = open(os.path.join(base, fn)).readlines()
+            pos = [int(x) for x in head.match(lines[0]).group(1).split(",")]
+            assert all(a < b for a, b in zip(pos[:-1], pos[1:]))
+            for ln in lines[1:]:
+                m = row.match(ln)
+                assert m, ln
+                assert len(m.group(1)) == len(pos) - 1
+                for g in re.findall(r"([0-9]+)-([0-9]+):", m.group(2)):
+                    assert 0 <= int(g[0]) < int(g[1]) < len(pos) - 1
