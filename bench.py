@@ -1,0 +1,339 @@
+#!/usr/bin/env python3
+"""Benchmark of the segment stage hot path (contract: see the task's bench.py section).
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU arm (oracle port on host cores)
+
+A *step* = one pass of the whole hot path (signal -> ... -> gaps) over one batch of synthetic SPLIT
+data.  Workload at every N: BASELINE.json configs[1] -- "synthetic chromosome-scale SPLIT: 200k reads
+across ~3k tints" -- per GPU (weak scaling: rank r segments its own seeded realisation; tints never
+interact, so there is no data-path collective, only the timing reduction).
+
+value  = reads/s with the packed batch already resident in HBM (K x frs_run, CUDA events).
+e2e    = reads/s through the C ABI with pinned HOST buffers: frs_upload + frs_run + frs_download.
+roofline = dominant kernel of the step, algorithmic bytes / CUDA-event time.
+cpu_baseline = the oracle port (numpy restatement of the reference, NOT the product) on all host
+cores over a bounded sample of the same workload (rank 0, N = 1 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "reads/sec through freddie_segment"
+UNIT = "reads/s"
+WORKLOADS = {
+    "cfg2": "BASELINE configs[1]: synthetic chromosome-scale SPLIT, 200k reads across ~3k tints (seeded, per GPU)",
+    "cfg3": "BASELINE configs[2]: DP-dominated giant tints (scaled by --scale), per GPU",
+}
+
+
+# ------------------------------------------------------------------------------------------------
+def rank_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def make_workload(workload: str, scale: float, seed: int, workers: int):
+    from freddie_b200 import synth
+    cfg = {"cfg2": 2, "cfg3": 3}[workload]
+    return synth.make_config(cfg, scale=scale, seed=seed, workers=workers)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def algorithmic_bytes(counts: dict, sizes: dict, cov_elems: int) -> dict:
+    """Per-stage ALGORITHMIC bytes of one step (DESIGN.md 'Bytes per unit')."""
+    L, I, R, N = counts["n_samples"], counts["n_rep_ivs"], counts["n_reps"], counts["n_reads"]
+    Ir, K = counts["n_read_ivs"], sizes["n_candidates"]
+    dig = sizes["n_digit_bytes"]
+    return {
+        "signal": 8 * I + 8 * L,
+        "gauss": 16 * L,
+        "candidates": 8 * L,
+        "threshold": 8 * L,
+        "coverage": 8 * I + 4 * cov_elems,
+        "dp_tables": 4 * cov_elems + 4 * R,
+        "refine": 8 * L,
+        "digits": 8 * I + dig,
+        "gaps": 16 * Ir + 4 * N + 4 * counts["n_seq_words"] * 2,
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+def oracle_rate(tints, threads: int, target_reads: int):
+    """Oracle (CPU port of the reference algorithm) on a bounded, size-stratified sample of tints."""
+    from multiprocessing import Pool
+    order = sorted(range(len(tints)), key=lambda i: len(tints[i]["reads"]))
+    stride = max(1, int(len(order) * (sum(len(t["reads"]) for t in tints) / len(tints)) / max(target_reads, 1)))
+    pick = order[stride // 2::stride]
+    sample = [tints[i] for i in pick]
+    n = sum(len(t["reads"]) for t in sample)
+    t0 = time.perf_counter()
+    with Pool(threads) as p:
+        res = p.map(_oracle_one, sample, chunksize=1)
+    dt = time.perf_counter() - t0
+    cells = sum(r[1] for r in res)
+    return n / dt, cells / dt, dict(tints=len(sample), reads=n, seconds=round(dt, 2), dp_cells=cells)
+
+
+def _oracle_one(tint):
+    from oracle import segment_oracle as orc
+    st = {}
+    orc.segment_tint(tint, orc.Params(), stats=st)
+    return len(tint["reads"]), st.get("cells", 0)
+
+
+def run_reference_arm(args):
+    rank, _, world = rank_env()
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    tints = make_workload(args.workload, args.scale, 2, min(cores, 16))
+    total_steps = args.steps + args.warmup
+    budget = 150.0 / max(total_steps, 1)  # seconds of CPU work per step
+    rate_guess = 300.0 * cores
+    rates, cell_rates, sample = [], [], None
+    for s in range(total_steps):
+        target = int(min(sum(len(t["reads"]) for t in tints), max(500, rate_guess * budget)))
+        r, c, sample = oracle_rate(tints, cores, target)
+        rate_guess = r
+        if s >= args.warmup:
+            rates.append(r)
+            cell_rates.append(c)
+    v = float(np.mean(rates))
+    line = dict(
+        impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+        ms_per_step=None, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32+f64",
+        data="synthetic", config=dict(workload=WORKLOADS[args.workload], scale=args.scale),
+        cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port",
+                          sample="oracle/segment_oracle.py (numpy restatement of freddie_segment.py; the reference "
+                                 "tree is not present on the GPU box) on a size-stratified sample per step: %s" % sample),
+        e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+        dp_cells_per_sec=float(np.mean(cell_rates)),
+    )
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_cuda_arm(args):
+    import torch
+    rank, local_rank, world = rank_env()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    from freddie_b200.engine import Engine, SegmentParams
+    from freddie_b200.pack import pack_tints
+
+    cores = os.cpu_count() or 1
+    t0 = time.time()
+    tints = make_workload(args.workload, args.scale, 2 + 1000 * rank, max(1, min(16, cores // world)))
+    batch = pack_tints(tints).pin()
+    t_gen = time.time() - t0
+    n_reads = batch.n_reads
+    prm = SegmentParams()
+    eng = Engine(local_rank)
+    stream = torch.cuda.ExternalStream(eng.lib.frs_stream(eng.ctx), device=torch.device("cuda", local_rank))
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush.zero_()
+
+    # ---- warm-up: full end-to-end steps (also sizes every device buffer) ----
+    res = None
+    for _ in range(max(args.warmup, 1)):
+        res = eng.segment_batch(batch, prm, pinned=True)
+    sizes = res.sizes
+    d2h = int(sum(v.nbytes for v in res.arrays.values()))
+    h2d = batch.nbytes()
+
+    # ---- timed: K x frs_run on the resident batch ----
+    eng.upload(batch)
+    eng.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    stage_ms, stage_launch = {}, {}
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    sampler.start()
+    launches = 0
+    for k in range(args.steps):
+        flush_l2()
+        ev[k][0].record(stream)
+        eng.run(prm)
+        ev[k][1].record(stream)
+        launches += eng.launch_count()
+        for name, ms, ln in eng.timings():
+            stage_ms[name] = stage_ms.get(name, 0.0) + ms
+            stage_launch[name] = ln
+    barrier()
+    clocks = sampler.stop()
+    t_dev = sum(a.elapsed_time(b) for a, b in ev) / 1e3
+    eng.set_profiling(False)
+
+    # ---- timed: K x (upload + run + download) with pinned host buffers ----
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    w0 = time.perf_counter()
+    for k in range(args.steps):
+        flush_l2()
+        ev2[k][0].record(stream)
+        eng.upload(batch)
+        eng.run(prm)
+        _download_into(eng, res)
+        ev2[k][1].record(stream)
+    barrier()
+    t_e2e_wall = time.perf_counter() - w0
+    t_e2e = sum(a.elapsed_time(b) for a, b in ev2) / 1e3
+
+    # ---- reduce over ranks: max time, sum of units ----
+    tot_reads, tot_cells = n_reads, int(sizes["dp_cells"])
+    dp_ms = stage_ms.get("dp_tables", 0.0) + stage_ms.get("dp_solve", 0.0)
+    if world > 1:
+        t = torch.tensor([t_dev, t_e2e, dp_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e, dp_ms = [float(x) for x in t.tolist()]
+        u = torch.tensor([n_reads, tot_cells, launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+        tot_reads, tot_cells, launches = [int(x) for x in u.tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = tot_reads * args.steps / t_dev
+    e2e_v = tot_reads * args.steps / t_e2e
+    counts = batch.counts()
+    cov_elems = int(eng.tap(12, np.int64)[-1])  # FRS_TAP_COV_OFF: last entry = total coverage elements
+    alg = algorithmic_bytes(counts, sizes, cov_elems)
+    peak, peak_src = peaks()
+    dom = max((k for k in stage_ms if k in alg), key=lambda k: stage_ms[k])
+    dom_ms = stage_ms[dom] / args.steps
+    ach = alg[dom] / (dom_ms * 1e-3) / 1e9
+    stages = {k: dict(ms=round(v / args.steps, 4), launches=stage_launch[k],
+                      alg_GBps=(round(alg[k] / (v / args.steps * 1e-3) / 1e9, 1) if k in alg and v > 0 else None))
+              for k, v in stage_ms.items()}
+    line = dict(
+        metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=t_dev / args.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+        dtype="int32+f64", data="synthetic",
+        config=dict(workload=WORKLOADS[args.workload], scale=args.scale, reads_per_gpu=n_reads, tints_per_gpu=len(tints),
+                    l2="flushed between timed steps (256 MiB memset)", params="defaults (sd=5 tp=0.9 vf=3 mps=50 lo=3)"),
+        e2e=dict(value=e2e_v, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                 wall_value=tot_reads * args.steps / t_e2e_wall),
+        gpu_launches=launches,
+        clocks=clocks,
+        roofline=dict(bound="hbm", kernel=dom, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None,
+                      peak_source=peak_src, alg_bytes_per_launch=alg[dom], ms_per_launch=dom_ms),
+        dp_cells_per_sec=tot_cells * args.steps / max(dp_ms * 1e-3, 1e-12),
+        dp_read_cells_per_sec=int(sizes["dp_read_cells"]) * args.steps * world / max(dp_ms * 1e-3, 1e-12),
+        dp=dict(cells=int(sizes["dp_cells"]), subproblems=int(sizes["n_subproblems"]),
+                max_n=int(sizes["max_subproblem"]), candidates=int(sizes["n_candidates"])),
+        stages=stages,
+        setup_seconds=round(t_gen, 1),
+    )
+    if world == 1 and not args.no_cpu_baseline:
+        r, c, sample = oracle_rate(tints, cores, int(os.environ.get("FRS_CPU_SAMPLE_READS", 300 * cores * 15)))
+        line["cpu_baseline"] = dict(value=r, unit=UNIT, cores=cores, kind="port", dp_cells_per_sec=c,
+                                    sample="oracle/segment_oracle.py over a size-stratified sample of the same "
+                                           "workload: %s" % sample)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _download_into(eng, res):
+    """frs_download into the already allocated pinned result buffers of the warm-up step."""
+    import ctypes as C
+    r = res.as_struct()
+    eng._check(eng.lib.frs_download(eng.ctx, C.byref(r)))
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_cuda_arm(args)
+
+
+if __name__ == "__main__":
+    main()

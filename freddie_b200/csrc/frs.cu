@@ -415,16 +415,16 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
   const int* d_island_tint = c->b_island_tint.as<int>();
 
   // ================= phase 1: signal -> smoothed signal -> candidates, threshold =================
-  stage_begin(c, "signal");
   ENS(b_yraw, L * 4);
   CK(cudaMemsetAsync(c->b_yraw.p, 0, L * 4, st));
+  stage_begin(c, "signal");
   k_signal<<<c->n_sig_work, SIG_THREADS, SIG_BINS * 4, st>>>(c->b_sig_work.as<SigWork>(), c->b_rep_iv_off.as<int>(),
                                                              c->b_rep_weight.as<int>(), c->b_rep_fs.as<int>(),
                                                              c->b_rep_fe.as<int>(), prm->ignore_ends, c->b_yraw.as<int>());
   LAUNCHED();
 
-  stage_begin(c, "gauss");
   ENS(b_y, L * 8);
+  stage_begin(c, "gauss");
   {
     size_t sm = (size_t)((2 * lw + 1) + TILE_SAMPLES + 2 * lw) * 8;
     if (sm > 48 * 1024) CK(cudaFuncSetAttribute(k_gauss, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -543,8 +543,8 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
   c->n_triples = n_triples;
   { int r = check_dev_err(c); if (r) return r; }
 
-  stage_begin(c, "coverage");
   ENS(b_P, COV * 4);
+  stage_begin(c, "coverage");
   if (NSUB > 0) {
     k_coverage<<<c->n_cov_tiles, COV_THREADS, 0, st>>>(c->b_cov_tiles.as<RepTile>(), d_tint_rep_off,
                                                        c->b_tint_cand_off.as<int>(), c->b_tint_cov_off.as<i64>(),
@@ -556,11 +556,12 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
   ENS(b_dpfinal, K);
   CK(cudaMemcpyAsync(c->b_dpfinal.p, c->b_fixed1.p, K, cudaMemcpyDeviceToDevice, st));
   if (NSUB > 0) {
-    stage_begin(c, "dp_tables");
+    stage_end(c);
     ENS(b_ins, n_pairs * 4);
     ENS(b_out, n_triples * 4);
     CK(cudaMemsetAsync(c->b_ins.p, 0, n_pairs * 4, st));
     CK(cudaMemsetAsync(c->b_out.p, 0, n_triples * 4, st));
+    stage_begin(c, "dp_tables");
     int wc = DPT_MAXW;
     while (wc > 1 && dpt_smem_bytes(max_n, wc) > 200 * 1024) wc >>= 1;
     size_t sm = dpt_smem_bytes(max_n, wc);
@@ -634,8 +635,8 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
   { int r = read_counters(c, 13); if (r) return r; }  // sync: digit bytes
   const i64 NDIG = c->h_pin[12];
 
-  stage_begin(c, "digits");
   ENS(b_digits, NDIG);
+  stage_begin(c, "digits");
   k_digits<<<c->n_dig_tiles, DIG_THREADS, 0, st>>>(c->b_dig_tiles.as<RepTile>(), 64, d_tint_rep_off,
                                                    c->b_tint_final_off.as<int>(), c->b_tint_digit_off.as<i64>(),
                                                    c->b_rep_iv_off.as<int>(), c->b_rep_fs.as<int>(), c->b_rep_fe.as<int>(),
@@ -668,9 +669,9 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
                                                       c->b_digits.as<u8>(), c->b_run_off.as<int>(), c->b_runs.as<int2>());
   LAUNCHED();
 
-  stage_begin(c, "gaps");
   ENS(b_read_head, (size_t)N * 32);
   ENS(b_gap_rec, NGAP * 12);
+  stage_begin(c, "gaps");
   {
     GapArgs G;
     G.n_reads = N; G.read_rep = c->b_read_rep.as<int>(); G.read_strand = c->b_read_strand.as<u8>();
