@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(DPT_THREADS, 1) k_dp_tables(DptArgs A, int wc)
         }
       }
     }
-    // the next iteration's first __syncthreads orders this triple phase before the next mask phase
+    __syncthreads();  // the next chunk rewrites the weight planes and the masks: wait for every warp's triple phase
   }
 }
 
