@@ -395,6 +395,54 @@ def _tint_job(job):
     return make_tint(rng, contig, i, n, base=base, rid0=rid0, opts=opts, **kw)
 
 
+def config_jobs(cfg: int, scale: float = 1.0, seed: Optional[int] = None) -> list:
+    """Per-tint generation jobs of a config (each tint has its own child seed)."""
+    plan = config_plan(cfg, scale, seed)
+    sizes = [int(n) for n in plan["sizes"]]
+    n_contigs = max(1, (len(sizes) + _TINTS_PER_CONTIG - 1) // _TINTS_PER_CONTIG)
+    if cfg == 5:
+        n_contigs = max(n_contigs, 22)
+    jobs = []
+    rid = 0
+    for i, (n, kind) in enumerate(zip(sizes, plan["kind"])):
+        jobs.append((plan["seed"], cfg, i, n, kind, "chr%d" % (1 + i % n_contigs), i // n_contigs, rid))
+        rid += n
+    return jobs
+
+
+def iter_config(cfg: int, scale: float = 1.0, seed: Optional[int] = None, workers: int = 1, chunk_reads: int = 200000):
+    """Streams a config as lists of tints of about ``chunk_reads`` reads (same tints, same order as
+    ``make_config``), so that whole-transcriptome configs never have to sit in host memory at once."""
+    jobs = config_jobs(cfg, scale, seed)
+    pool = None
+    if workers > 1 and len(jobs) > 1:
+        from multiprocessing import Pool
+        pool = Pool(workers)
+    try:
+        i = 0
+        while i < len(jobs):
+            j, acc = i, 0
+            while j < len(jobs) and (j == i or acc + jobs[j][3] <= chunk_reads):
+                acc += jobs[j][3]
+                j += 1
+            part = jobs[i:j]
+            # largest tints first inside the chunk so the pool stays busy
+            if pool is not None and len(part) > 1:
+                order = sorted(range(len(part)), key=lambda k: -part[k][3])
+                res = pool.map(_tint_job, [part[k] for k in order], chunksize=1 if len(part) < 64 else 8)
+                out = [None] * len(part)
+                for k, r in zip(order, res):
+                    out[k] = r
+                yield out
+            else:
+                yield [_tint_job(x) for x in part]
+            i = j
+    finally:
+        if pool is not None:
+            pool.close()
+            pool.join()
+
+
 def make_config(cfg: int, scale: float = 1.0, seed: Optional[int] = None, workers: int = 1) -> List[dict]:
     """Realise a config as a list of tints (seeded, deterministic, independent of ``workers``)."""
     plan = config_plan(cfg, scale, seed)
