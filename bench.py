@@ -115,7 +115,7 @@ def algorithmic_bytes(counts: dict, sizes: dict, cov_elems: int) -> dict:
         "candidates": 8 * L,
         "threshold": 8 * L,
         "coverage": 8 * I + 4 * cov_elems,
-        "dp_tables": 4 * cov_elems + 4 * R,
+        "dp": 4 * cov_elems + 4 * R,
         "refine": 8 * L,
         "digits": 8 * I + dig,
         "gaps": 16 * Ir + 4 * N + 4 * counts["n_seq_words"] * 2,
@@ -257,7 +257,7 @@ def run_cuda_arm(args):
 
     # ---- reduce over ranks: max time, sum of units ----
     tot_reads, tot_cells = n_reads, int(sizes["dp_cells"])
-    dp_ms = stage_ms.get("dp_tables", 0.0) + stage_ms.get("dp_solve", 0.0)
+    dp_ms = stage_ms.get("dp", 0.0) + stage_ms.get("dp_solve", 0.0)
     if world > 1:
         t = torch.tensor([t_dev, t_e2e, dp_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

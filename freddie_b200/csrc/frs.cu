@@ -51,14 +51,16 @@ struct frs_context {
   DBuf b_params;  // thr table | gauss w | refine w
   DBuf b_yraw, b_y, b_sflag, b_bsum, b_cand_flat, b_cand_island, b_island_cand_off, b_tint_cand_off, b_thr, b_vbuf,
       b_leaf_off, b_leaf_len, b_leaf_sum, b_fixed0, b_fixed1, b_fixed_list, b_sub_flag, b_sub_fidx, b_sub_start,
-      b_sub_n, b_sub_tint, b_sz_pair, b_sz_triple, b_sz_work, b_sub_pair_off, b_sub_triple_off, b_sub_work_off,
-      b_cov_sz, b_tint_cov_off, b_P, b_ins, b_out, b_dpfinal, b_pf_list, b_gbuf, b_pstate, b_final_flat,
+      b_sub_n, b_sub_tint, b_sub_info, b_sub_slabs, b_sz_tab, b_sub_tab_off, b_plan, b_work, b_split_list, b_cursor,
+      b_cov_sz, b_tint_cov_off, b_P, b_tab, b_dpfinal, b_pf_list, b_gbuf, b_pstate, b_final_flat,
       b_final_pos, b_final_island, b_tint_final_off, b_dig_sz, b_tint_digit_off, b_seg_ty, b_seg_tn, b_digits,
       b_run_cnt, b_run_off, b_runs, b_gap_cnt, b_read_gap_off, b_read_head, b_gap_rec, b_counters, b_stats, b_err;
   i64* h_pin = nullptr;  // pinned scratch for small D2H reads
   // results of the last run
   frs_result_sizes sizes;
-  i64 n_cand = 0, n_fixed = 0, n_sub = 0, cov_elems = 0, n_pairs = 0, n_triples = 0;
+  i64 n_cand = 0, n_fixed = 0, n_sub = 0, cov_elems = 0, tab_elems = 0;
+  // options (frs_set_option)
+  int opt_slab_words = 64, opt_keep_tables = 0;
   // timing
   Stage stages[FRS_MAX_STAGES];
   int n_stages = 0, cur_stage = -1, launch_count = 0;
@@ -216,7 +218,10 @@ int frs_create(int device, frs_context** out) {
     return r;
   }
   cudaFuncSetAttribute(k_signal, cudaFuncAttributeMaxDynamicSharedMemorySize, SIG_BINS * 4);
-  cudaFuncSetAttribute(k_dp_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(k_dp<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(k_dp<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(k_dp<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(k_dp<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(k_dp_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   *out = c;
   return 0;
@@ -246,6 +251,21 @@ int frs_set_profiling(frs_context* c, int enabled) {
 }
 
 int frs_last_launch_count(frs_context* c) { return c ? c->launch_count : 0; }
+
+int frs_set_option(frs_context* c, int key, long long value) {
+  if (!c) return FRS_ERR_ARG;
+  switch (key) {
+    case FRS_OPT_SLAB_WORDS:
+      if (value < 1 || value > (1 << 20)) return fail(c, FRS_ERR_ARG, "frs_set_option: slab words out of range");
+      c->opt_slab_words = (int)value;
+      return 0;
+    case FRS_OPT_KEEP_DP_TABLES:
+      c->opt_keep_tables = value != 0;
+      return 0;
+    default:
+      return fail(c, FRS_ERR_ARG, "frs_set_option: unknown key %d", key);
+  }
+}
 
 int frs_get_timings(frs_context* c, const char** names, float* ms, int* launches) {
   if (!c) return 0;
@@ -506,41 +526,42 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
   c->n_sub = NSUB;
   c->cov_elems = COV;
 
-  const int slab_words = 256;  // 8192 read reps per CTA of the DP-table kernel
-  i64 n_pairs = 0, n_triples = 0, n_work = 0;
+  const int slab_words = c->opt_slab_words;
+  const int keep = c->opt_keep_tables;
+  i64 tab_total = 0, n_split = 0, dp_cells = 0, dp_read_cells = 0, cls_cnt[DP_CLASSES] = {0, 0, 0, 0, 0};
+  int cls_maxn[DP_CLASSES] = {0, 0, 0, 0, 0};
   int max_n = 0;
   if (NSUB > 0) {
     ENS(b_sub_start, NSUB * 4);
     ENS(b_sub_n, NSUB * 4);
     ENS(b_sub_tint, NSUB * 4);
-    ENS(b_sz_pair, NSUB * 4);
-    ENS(b_sz_triple, NSUB * 4);
-    ENS(b_sz_work, NSUB * 4);
-    ENS(b_sub_pair_off, (NSUB + 1) * 8);
-    ENS(b_sub_triple_off, (NSUB + 1) * 8);
-    ENS(b_sub_work_off, (NSUB + 1) * 4);
-    k_sub_sizes<<<cdiv(NSUB, 256), 256, 0, st>>>((int)NSUB, c->b_sub_fidx.as<int>(), c->b_fixed_list.as<int>(),
-                                                 c->b_cand_island.as<int>(), d_island_tint, d_tint_rep_off, slab_words,
-                                                 c->b_sub_start.as<int>(), c->b_sub_n.as<int>(), c->b_sub_tint.as<int>(),
-                                                 c->b_sz_pair.as<int>(), c->b_sz_triple.as<int>(), c->b_sz_work.as<int>(),
-                                                 c->b_stats.as<i64>());
+    ENS(b_sub_info, NSUB * 4);
+    ENS(b_sub_slabs, NSUB * 4);
+    ENS(b_sz_tab, NSUB * 4);
+    ENS(b_sub_tab_off, (NSUB + 1) * 8);
+    ENS(b_plan, PLAN_SLOTS * 8);
+    CK(cudaMemsetAsync(c->b_plan.p, 0, PLAN_SLOTS * 8, st));
+    k_sub_plan<<<cdiv(NSUB, 256), 256, 0, st>>>((int)NSUB, c->b_sub_fidx.as<int>(), c->b_fixed_list.as<int>(),
+                                                c->b_cand_island.as<int>(), d_island_tint, d_tint_rep_off, slab_words, keep,
+                                                c->b_sub_start.as<int>(), c->b_sub_n.as<int>(), c->b_sub_tint.as<int>(),
+                                                c->b_sub_info.as<int>(), c->b_sub_slabs.as<int>(), c->b_sz_tab.as<int>(),
+                                                c->b_plan.as<i64>());
     LAUNCHED();
-    { int r = scan_exclusive<int, i64>(c, c->b_sz_pair.as<int>(), NSUB, c->b_sub_pair_off.as<i64>()); if (r) return r; }
-    { int r = scan_exclusive<int, i64>(c, c->b_sz_triple.as<int>(), NSUB, c->b_sub_triple_off.as<i64>()); if (r) return r; }
-    { int r = scan_exclusive<int, int>(c, c->b_sz_work.as<int>(), NSUB, c->b_sub_work_off.as<int>()); if (r) return r; }
-    CK(cudaMemcpyAsync(c->b_counters.as<i64>() + 4, c->b_sub_pair_off.as<i64>() + NSUB, 8, cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemcpyAsync(c->b_counters.as<i64>() + 5, c->b_sub_triple_off.as<i64>() + NSUB, 8, cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemcpyAsync(c->b_counters.as<i64>() + 6, c->b_stats.as<i64>(), 24, cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemsetAsync(c->b_counters.as<i64>() + 9, 0, 8, st));
-    CK(cudaMemcpyAsync(c->b_counters.as<i64>() + 9, c->b_sub_work_off.as<int>() + NSUB, 4, cudaMemcpyDeviceToDevice, st));
-    { int r = read_counters(c, 10); if (r) return r; }   // sync: table sizes
-    n_pairs = c->h_pin[4];
-    n_triples = c->h_pin[5];
-    max_n = (int)(c->h_pin[8] & 0xffffffff);
-    n_work = c->h_pin[9];
+    { int r = scan_exclusive<int, i64>(c, c->b_sz_tab.as<int>(), NSUB, c->b_sub_tab_off.as<i64>()); if (r) return r; }
+    CK(cudaMemcpyAsync(c->b_counters.as<i64>() + 4, c->b_sub_tab_off.as<i64>() + NSUB, 8, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(c->b_counters.as<i64>() + 16, c->b_plan.p, PLAN_SLOTS * 8, cudaMemcpyDeviceToDevice, st));
+    { int r = read_counters(c, 32); if (r) return r; }   // sync: work-list and table sizes
+    tab_total = c->h_pin[4];
+    for (int k = 0; k < DP_CLASSES; ++k) {
+      cls_cnt[k] = c->h_pin[16 + PLAN_WORK + k];
+      cls_maxn[k] = (int)c->h_pin[16 + PLAN_MAXN + k];
+    }
+    n_split = c->h_pin[16 + PLAN_SPLIT];
+    dp_cells = c->h_pin[16 + PLAN_CELLS];
+    dp_read_cells = c->h_pin[16 + PLAN_RCELLS];
+    max_n = (int)c->h_pin[16 + PLAN_MAXALL];
   }
-  c->n_pairs = n_pairs;
-  c->n_triples = n_triples;
+  c->tab_elems = tab_total;
   { int r = check_dev_err(c); if (r) return r; }
 
   ENS(b_P, COV * 4);
@@ -556,39 +577,57 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
   ENS(b_dpfinal, K);
   CK(cudaMemcpyAsync(c->b_dpfinal.p, c->b_fixed1.p, K, cudaMemcpyDeviceToDevice, st));
   if (NSUB > 0) {
-    stage_end(c);
-    ENS(b_ins, n_pairs * 4);
-    ENS(b_out, n_triples * 4);
-    CK(cudaMemsetAsync(c->b_ins.p, 0, n_pairs * 4, st));
-    CK(cudaMemsetAsync(c->b_out.p, 0, n_triples * 4, st));
-    stage_begin(c, "dp_tables");
-    int wc = DPT_MAXW;
-    while (wc > 1 && dpt_smem_bytes(max_n, wc) > 200 * 1024) wc >>= 1;
-    size_t sm = dpt_smem_bytes(max_n, wc);
-    if (sm > 227 * 1024)
-      return fail(c, FRS_ERR_LIMIT, "subproblem with %d candidates exceeds the DP kernel's shared-memory budget "
-                                    "(max_problem_size too large for this build)", max_n);
-    DptArgs A;
+    stage_begin(c, "dp_plan");
+    i64 n_work = 0;
+    DpBases bases;
+    for (int k = 0; k < DP_CLASSES; ++k) { bases.base[k] = (int)n_work; n_work += cls_cnt[k]; }
+    if (n_work > 0x7fffffff) return fail(c, FRS_ERR_LIMIT, "too many DP work items in one batch (%lld)", (long long)n_work);
+    ENS(b_work, n_work * 8);
+    ENS(b_split_list, n_split * 4);
+    ENS(b_cursor, 8 * 4);
+    CK(cudaMemsetAsync(c->b_cursor.p, 0, 8 * 4, st));
+    k_sub_fill<<<cdiv(NSUB, 256), 256, 0, st>>>((int)NSUB, c->b_sub_info.as<int>(), c->b_sub_slabs.as<int>(), bases,
+                                                c->b_cursor.as<int>(), c->b_work.as<DpWork>(), c->b_split_list.as<int>());
+    LAUNCHED();
+    ENS(b_tab, tab_total * 4);
+    if (tab_total > 0) CK(cudaMemsetAsync(c->b_tab.p, 0, tab_total * 4, st));
+    stage_begin(c, "dp");
+    DpArgs A;
     A.sub_start = c->b_sub_start.as<int>(); A.sub_n = c->b_sub_n.as<int>(); A.sub_tint = c->b_sub_tint.as<int>();
-    A.sub_work_off = c->b_sub_work_off.as<int>(); A.sub_pair_off = c->b_sub_pair_off.as<i64>();
-    A.sub_triple_off = c->b_sub_triple_off.as<i64>(); A.n_sub = (int)NSUB;
+    A.sub_info = c->b_sub_info.as<int>(); A.sub_tab_off = c->b_sub_tab_off.as<i64>();
     A.tint_rep_off = d_tint_rep_off; A.tint_cand_off = c->b_tint_cand_off.as<int>();
     A.tint_cov_off = c->b_tint_cov_off.as<i64>(); A.rep_weight = c->b_rep_weight.as<int>();
     A.cand_flat = c->b_cand_flat.as<int>(); A.P = c->b_P.as<u32>();
     A.thr_table = d_tbl; A.thr_table_len = prm->thr_table_len; A.tp = prm->tp;
-    A.slab_words = slab_words; A.max_n = max_n; A.ins = c->b_ins.as<int>(); A.out = c->b_out.as<int>();
-    k_dp_tables<<<(unsigned)n_work, DPT_THREADS, sm, st>>>(A, wc);
-    LAUNCHED();
-
-    stage_begin(c, "dp_solve");
-    DpsArgs S;
-    S.sub_start = A.sub_start; S.sub_n = A.sub_n; S.sub_pair_off = A.sub_pair_off; S.sub_triple_off = A.sub_triple_off;
-    S.cand_flat = A.cand_flat; S.ins = A.ins; S.out = A.out; S.lo = prm->lo; S.max_n = max_n;
-    S.final_flag = c->b_dpfinal.as<u8>(); S.err = d_err;
-    size_t sm2 = (size_t)max_n * max_n * 4 + (size_t)max_n * 4 + (size_t)max_n * max_n * 2 + 16;
-    if (sm2 > 200 * 1024) return fail(c, FRS_ERR_LIMIT, "subproblem with %d candidates exceeds the DP solver's budget", max_n);
-    k_dp_solve<<<(unsigned)NSUB, DPS_THREADS, sm2, st>>>(S);
-    LAUNCHED();
+    A.slab_words = slab_words; A.lo = prm->lo; A.keep_tables = keep;
+    A.tab = c->b_tab.as<int>(); A.final_flag = c->b_dpfinal.as<u8>(); A.err = d_err;
+    const int SMEM_BUDGET = 200 * 1024;
+    for (int k = 0; k < DP_CLASSES; ++k) {
+      if (cls_cnt[k] == 0) continue;
+      const int M = cls_maxn[k], on_chip = k < 4 ? 1 : 0;
+      int wc = (k <= 2) ? 4 : DPT_MAXW;
+      while (wc > 1 && dp_smem_layout(M, wc, on_chip).total > SMEM_BUDGET) wc >>= 1;
+      const size_t sm = (size_t)dp_smem_layout(M, wc, on_chip).total;
+      if (sm > 227 * 1024)
+        return fail(c, FRS_ERR_LIMIT, "subproblem with %d candidates exceeds the DP kernel's shared-memory budget "
+                                      "(max_problem_size too large for this build)", M);
+      const DpWork* wl = c->b_work.as<DpWork>() + bases.base[k];
+      const unsigned g = (unsigned)cls_cnt[k];
+      switch (k) {
+        case 0: k_dp<64><<<g, 64, sm, st>>>(A, wl, M, wc, on_chip); break;
+        case 1: k_dp<128><<<g, 128, sm, st>>>(A, wl, M, wc, on_chip); break;
+        case 2: k_dp<256><<<g, 256, sm, st>>>(A, wl, M, wc, on_chip); break;
+        default: k_dp<512><<<g, 512, sm, st>>>(A, wl, M, wc, on_chip); break;
+      }
+      LAUNCHED();
+    }
+    if (n_split > 0) {
+      stage_begin(c, "dp_solve");
+      size_t sm2 = dps_smem_bytes(max_n);
+      if (sm2 > 200 * 1024) return fail(c, FRS_ERR_LIMIT, "subproblem with %d candidates exceeds the DP solver's budget", max_n);
+      k_dp_solve<<<(unsigned)n_split, DPS_THREADS, sm2, st>>>(A, c->b_split_list.as<int>(), max_n);
+      LAUNCHED();
+    }
   }
 
   // ================= phase 3: refine, final positions, digits =================
@@ -694,8 +733,8 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
   c->sizes.n_gap_records = NGAP;
   c->sizes.n_candidates = K;
   c->sizes.n_subproblems = NSUB;
-  c->sizes.dp_cells = NSUB > 0 ? c->h_pin[6] : 0;
-  c->sizes.dp_read_cells = NSUB > 0 ? c->h_pin[7] : 0;
+  c->sizes.dp_cells = dp_cells;
+  c->sizes.dp_read_cells = dp_read_cells;
   c->sizes.max_subproblem = max_n;
   c->sizes.pad = 0;
   if (sizes_out) *sizes_out = c->sizes;
@@ -747,11 +786,9 @@ int frs_get_intermediate(frs_context* c, int which, void* dst, size_t cap, size_
     case FRS_TAP_SUB_START: src = c->b_sub_start.p; sz = NS * 4; break;
     case FRS_TAP_SUB_N: src = c->b_sub_n.p; sz = NS * 4; break;
     case FRS_TAP_COVERAGE: src = c->b_P.p; sz = c->cov_elems * 4; break;
-    case FRS_TAP_INS: src = c->b_ins.p; sz = c->n_pairs * 4; break;
-    case FRS_TAP_OUT: src = c->b_out.p; sz = c->n_triples * 4; break;
+    case FRS_TAP_DP_TABLES: src = c->b_tab.p; sz = c->tab_elems * 4; break;
     case FRS_TAP_COV_OFF: src = c->b_tint_cov_off.p; sz = (size_t)(c->hb.n_tints + 1) * 8; break;
-    case FRS_TAP_SUB_PAIR_OFF: src = c->b_sub_pair_off.p; sz = NS ? (NS + 1) * 8 : 0; break;
-    case FRS_TAP_SUB_TRIPLE_OFF: src = c->b_sub_triple_off.p; sz = NS ? (NS + 1) * 8 : 0; break;
+    case FRS_TAP_SUB_TAB_OFF: src = c->b_sub_tab_off.p; sz = NS ? (NS + 1) * 8 : 0; break;
     default: return fail(c, FRS_ERR_ARG, "frs_get_intermediate: unknown tap %d", which);
   }
   *bytes = sz;

@@ -127,50 +127,121 @@ __global__ void k_sub_flag(int n_fixed, const int* __restrict__ fixed_list, cons
   flag[f] = v;
 }
 
-// per subproblem sizes for the offset scans.  slab_words: words of 32 reps handled by one CTA.
-__global__ void k_sub_sizes(int n_sub, const int* __restrict__ sub_fidx, const int* __restrict__ fixed_list,
-                            const int* __restrict__ cand_island, const int* __restrict__ island_tint,
-                            const int* __restrict__ tint_rep_off, int slab_words, int* __restrict__ sub_start,
-                            int* __restrict__ sub_n, int* __restrict__ sub_tint, int* __restrict__ sz_pair,
-                            int* __restrict__ sz_triple, int* __restrict__ sz_work, i64* __restrict__ stats) {
+// ---------------------------------------------------------------------------------------------
+// Subproblem plan.  Every subproblem gets a size class (by its candidate count n) and a mode:
+//   fused : all read reps of the tint fit one slab (words <= slab_words) and n <= DP_SMEM_MAX_N.
+//           ONE CTA builds ins/out in shared memory and solves the DP in place -- the tables
+//           never touch HBM ("one CTA per tint-sized problem").
+//   split : giant tints.  The reps are cut into slabs of slab_words x 32; every (subproblem, slab)
+//           is a CTA that accumulates its partial tables in shared memory and adds them to the
+//           global tables with RED once per slab ("multi-CTA cooperative mode"); k_dp_solve then
+//           runs on the summed tables.
+// Classes: n <= 8 / 16 / 32 / DP_SMEM_MAX_N share a kernel body with different CTA sizes and
+// shared-memory carve-ups; class 4 (n > DP_SMEM_MAX_N, only reachable with a large -mps) keeps its
+// out table in global memory and is always split.
+// ---------------------------------------------------------------------------------------------
+#define DP_CLASSES 5
+#define DP_SMEM_MAX_N 56
+// counter slots (i64) written by k_sub_plan
+#define PLAN_WORK 0     // [5] work items per class
+#define PLAN_MAXN 5     // [5] largest n per class
+#define PLAN_SPLIT 10   // subproblems that need k_dp_solve
+#define PLAN_CELLS 11   // sum C(n,3)
+#define PLAN_RCELLS 12  // sum C(n,3) * R
+#define PLAN_MAXALL 13  // largest n
+#define PLAN_SLOTS 16
+
+struct DpWork { int sub; int slab; };
+
+__host__ __device__ inline int dp_class_of(int n) {
+  return n <= 8 ? 0 : n <= 16 ? 1 : n <= 32 ? 2 : n <= DP_SMEM_MAX_N ? 3 : 4;
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_max_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// sub_info[p] = class | fused << 8 | slabs << 16 ... slabs can exceed 16 bits for absurd sizes, so it
+// has its own array.  sz_tab[p] = int32 elements of the subproblem's global table block
+// (pair-indexed ins [n(n-1)/2] followed by out [C(n,3)]), 0 when the tables stay on chip.
+__global__ void k_sub_plan(int n_sub, const int* __restrict__ sub_fidx, const int* __restrict__ fixed_list,
+                           const int* __restrict__ cand_island, const int* __restrict__ island_tint,
+                           const int* __restrict__ tint_rep_off, int slab_words, int keep_tables,
+                           int* __restrict__ sub_start, int* __restrict__ sub_n, int* __restrict__ sub_tint,
+                           int* __restrict__ sub_info, int* __restrict__ sub_slabs, int* __restrict__ sz_tab,
+                           i64* __restrict__ plan) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int cls = -1, slabs = 0, n = 0, split = 0;
+  long long t3 = 0, rc = 0;
+  if (p < n_sub) {
+    int f = sub_fidx[p];
+    int a = fixed_list[f], b = fixed_list[f + 1];
+    n = b - a + 1;
+    int t = island_tint[cand_island[a]];
+    int R = tint_rep_off[t + 1] - tint_rep_off[t];
+    int words = (R + 31) >> 5;
+    cls = dp_class_of(n);
+    int fused = (cls < 4 && words <= slab_words) ? 1 : 0;
+    slabs = fused ? 1 : (words + slab_words - 1) / slab_words;
+    split = !fused;
+    t3 = (long long)n * (n - 1) * (n - 2) / 6;
+    rc = t3 * R;
+    sub_start[p] = a;
+    sub_n[p] = n;
+    sub_tint[p] = t;
+    sub_info[p] = cls | (fused << 8);
+    sub_slabs[p] = slabs;
+    sz_tab[p] = (fused && !keep_tables) ? 0 : (int)(n * (n - 1) / 2 + t3);
+  }
+  // warp-aggregated statistics
+#pragma unroll
+  for (int c = 0; c < DP_CLASSES; ++c) {
+    long long s = warp_sum_ll(cls == c ? slabs : 0);
+    int m = warp_max_i(cls == c ? n : 0);
+    if (lane == 0 && s) {
+      atomicAdd((unsigned long long*)&plan[PLAN_WORK + c], (unsigned long long)s);
+      atomicMax((long long*)&plan[PLAN_MAXN + c], (long long)m);
+    }
+  }
+  long long s_split = warp_sum_ll(split), s_t3 = warp_sum_ll(t3), s_rc = warp_sum_ll(rc);
+  int m_all = warp_max_i(n);
+  if (lane == 0) {
+    if (s_split) atomicAdd((unsigned long long*)&plan[PLAN_SPLIT], (unsigned long long)s_split);
+    if (s_t3) atomicAdd((unsigned long long*)&plan[PLAN_CELLS], (unsigned long long)s_t3);
+    if (s_rc) atomicAdd((unsigned long long*)&plan[PLAN_RCELLS], (unsigned long long)s_rc);
+    atomicMax((long long*)&plan[PLAN_MAXALL], (long long)m_all);
+  }
+}
+
+// work lists: class c owns work[base[c] .. base[c] + count[c]); cursor[c] starts at 0.  The order of
+// the items inside a class is arbitrary (atomics) -- results do not depend on it (integer sums).
+struct DpBases { int base[DP_CLASSES]; };
+__global__ void k_sub_fill(int n_sub, const int* __restrict__ sub_info, const int* __restrict__ sub_slabs,
+                           DpBases bases, int* __restrict__ cursor, DpWork* __restrict__ work,
+                           int* __restrict__ split_list) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_sub) return;
-  int f = sub_fidx[p];
-  int a = fixed_list[f], b = fixed_list[f + 1];
-  int n = b - a + 1;
-  int t = island_tint[cand_island[a]];
-  int R = tint_rep_off[t + 1] - tint_rep_off[t];
-  int words = (R + 31) >> 5;
-  sub_start[p] = a;
-  sub_n[p] = n;
-  sub_tint[p] = t;
-  sz_pair[p] = n * n;
-  i64 t3 = (i64)n * (n - 1) * (n - 2) / 6;
-  sz_triple[p] = (int)t3;
-  sz_work[p] = (words + slab_words - 1) / slab_words;
-  atomicAdd((unsigned long long*)&stats[0], (unsigned long long)t3);
-  atomicAdd((unsigned long long*)&stats[1], (unsigned long long)(t3 * R));
-  atomicMax((int*)&stats[2], n);
+  const int info = sub_info[p];
+  const int cls = info & 0xff, slabs = sub_slabs[p];
+  int off = bases.base[cls] + atomicAdd(&cursor[cls], slabs);
+  for (int s = 0; s < slabs; ++s) work[off + s] = DpWork{p, s};
+  if (!((info >> 8) & 1)) split_list[atomicAdd(&cursor[DP_CLASSES], 1)] = p;
 }
 
 // ---------------------------------------------------------------------------------------------
-// K7 DP tables.  One CTA = (subproblem, slab of read-rep words).  Per chunk of Wc words:
-//   1. TMA bulk copies stage the n coverage rows x 32*Wc reps of the chunk into shared memory;
-//   2. mask phase: a warp owns a row i, a lane owns a rep; for every j>i the lanes compare
-//      cov = P[j]-P[i] with the pair's integer cuts and __ballot_sync packs the yea / nay bits of
-//      32 reps into one word each; ambiguous counts (ins, :500-506) are accumulated on the fly;
-//   3. triple phase: out(i,j,k) = sum_w W . [(yea_ij & nay_jk) | (nay_ij & yea_jk)]  (:509-528) as
-//      weighted popcounts over the packed words; a warp owns the middle candidate j, its lanes the
-//      left candidate i, the loop runs over k with broadcast shared-memory loads.
-// Weights: bit-planes of W per word (plane b = reps whose weight has bit b), so weight-1 data costs
-// one AND + POPC.  Non-zero partial sums are added to the global tables with RED.
-// out layout per subproblem: [j][i][k-j-1], j = 1..n-2, i < j < k  -> exactly C(n,3) entries.
+// index helpers.  pairs (i<j): row-major upper triangle.  triples: [j][i][k-j-1], j = 1..n-2,
+// i < j < k  -> exactly C(n,3) entries.
 // ---------------------------------------------------------------------------------------------
-#define DPT_THREADS 512
-#define DPT_MAXW 8
-
-__device__ __forceinline__ int pair_index(int i, int j, int n) { return i * (2 * n - i - 1) / 2 + (j - i - 1); }
-__device__ __forceinline__ int triple_mid_off(int j, int n) {
+__host__ __device__ __forceinline__ int pair_index(int i, int j, int n) { return i * (2 * n - i - 1) / 2 + (j - i - 1); }
+__host__ __device__ __forceinline__ int triple_mid_off(int j, int n) {
   // sum_{j'=1}^{j-1} j' (n-1-j')
   int m = j - 1;
   return (n - 1) * m * (m + 1) / 2 - m * (m + 1) * (2 * m + 1) / 6;
@@ -204,222 +275,35 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, u32 byt
                : "memory");
 }
 
-struct DptArgs {
-  const int* sub_start; const int* sub_n; const int* sub_tint; const int* sub_work_off;
-  const i64* sub_pair_off; const i64* sub_triple_off;
-  int n_sub;
-  const int* tint_rep_off; const int* tint_cand_off; const i64* tint_cov_off;
-  const int* rep_weight; const int* cand_flat; const u32* P;
-  const double* thr_table; int thr_table_len; double tp;
-  int slab_words; int max_n;
-  int* ins; int* out;
-};
-
-// shared-memory carve-up for a given (n_max, Wc)
-__host__ __device__ inline size_t dpt_smem_bytes(int n, int wc) {
-  size_t p2 = (size_t)n * (n - 1) / 2;
-  size_t b = 0;
-  b += 16;                             // mbarrier
-  b += (size_t)n * 4;                  // cf
-  b += p2 * 8;                         // ty, tn
-  b += (size_t)n * 32 * wc * 4;        // coverage tile
-  b += p2 * wc * 8;                    // yea/nay words (uint2)
-  b += (size_t)wc * 32 * 4 + wc * 4;   // weight planes + plane counts
-  return (b + 15) & ~(size_t)15;
-}
-
-__global__ void __launch_bounds__(DPT_THREADS, 1) k_dp_tables(DptArgs A, int wc) {
-  extern __shared__ __align__(16) unsigned char dsm[];
-  // work item -> (subproblem, slab)
-  const int p = upper_row(A.sub_work_off, A.n_sub, (int)blockIdx.x);
-  const int slab = blockIdx.x - A.sub_work_off[p];
-  const int n = A.sub_n[p];
-  const int qs = A.sub_start[p];
-  const int t = A.sub_tint[p];
-  const int r0 = A.tint_rep_off[t];
-  const int R = A.tint_rep_off[t + 1] - r0;
-  const int Rp = (R + 3) & ~3;
-  const int words = (R + 31) >> 5;
-  const int w_lo = slab * A.slab_words;
-  const int w_hi = min(words, w_lo + A.slab_words);
-  const int p2 = n * (n - 1) / 2;
-  const int CW = 32 * wc;
-  // carve shared memory (sized for max_n by the host)
-  unsigned long long* bar = (unsigned long long*)dsm;
-  u32* tile = (u32*)(dsm + 16);                      // [n][CW]   (16-byte aligned rows)
-  uint2* ynm = (uint2*)(tile + (size_t)A.max_n * CW); // [p2][wc]  x = yea, y = nay
-  int* cf = (int*)(ynm + (size_t)(A.max_n * (A.max_n - 1) / 2) * wc);
-  int* ty = cf + A.max_n;
-  int* tn = ty + (A.max_n * (A.max_n - 1) / 2);
-  u32* planes = (u32*)(tn + (A.max_n * (A.max_n - 1) / 2));  // [wc][32]
-  int* nplanes = (int*)(planes + wc * 32);                   // [wc]
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int NW = DPT_THREADS / 32;
-  const u32* Prow0 = A.P + A.tint_cov_off[t] + (i64)(qs - A.tint_cand_off[t]) * Rp;
-
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int i = tid; i < n; i += DPT_THREADS) cf[i] = A.cand_flat[qs + i];
-  __syncthreads();
-  // first chunk's TMA can fly while the cuts are computed
-  u32 phase = 0;
-  auto issue = [&](int w0) {
-    int col0 = w0 * 32;
-    int cols = min(CW, Rp - col0);
-    u32 bytes = (u32)cols * 4u;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(bar, bytes * (u32)n);
-    for (int i = 0; i < n; ++i) tma_bulk_g2s(tile + (size_t)i * CW, Prow0 + (i64)i * Rp + col0, bytes, bar);
-  };
-  if (tid == 0 && w_lo < w_hi) issue(w_lo);
-  for (int e = tid; e < p2; e += DPT_THREADS) {
-    // decode pair e -> (i, j): rows are short, a linear walk is fine (done once per CTA)
-    int i = 0, rem = e;
-    while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
-    int j = i + 1 + rem;
-    int a, b;
-    length_cuts(cf[j] - cf[i] + 1, A.thr_table, A.thr_table_len, A.tp, a, b);
-    ty[e] = a;
-    tn[e] = b;
-  }
-  int* ins_g = A.ins + A.sub_pair_off[p];
-  int* out_g = A.out + A.sub_triple_off[p];
-
-  for (int w0 = w_lo; w0 < w_hi; w0 += wc) {
-    const int nw = min(wc, w_hi - w0);
-    // weight planes of the chunk
-    for (int w = warp; w < nw; w += NW) {
-      int rep = (w0 + w) * 32 + lane;
-      int wt = (rep < R) ? A.rep_weight[r0 + rep] : 0;
-      int mx = wt;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      int np = 32 - __clz(mx);
-      for (int b = 0; b < np; ++b) {
-        u32 m = __ballot_sync(0xffffffffu, (wt >> b) & 1);
-        if (lane == 0) planes[w * 32 + b] = m;
-      }
-      if (lane == 0) nplanes[w] = np;
-    }
-    __syncthreads();  // cuts + planes visible; previous chunk's triple phase done
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    // ---- mask phase: rows i paired from both ends for balance ----
-    const int nrows = n - 1;                 // rows i = 0..n-2
-    const int nrp = (nrows + 1) / 2;         // row a is processed together with row nrows-1-a
-    for (int a = warp; a < nrp; a += NW) {
-#pragma unroll 1
-      for (int side = 0; side < 2; ++side) {
-        const int i = side ? (nrows - 1 - a) : a;
-        if (side && i == a) break;
-        const u32* rowi = tile + (size_t)i * CW;
-        const int ebase = pair_index(i, i + 1, n);
-        for (int j = i + 1; j < n; ++j) {
-          const int e = ebase + (j - i - 1);
-          const int cy = ty[e], cn = tn[e];
-          const u32* rowj = tile + (size_t)j * CW;
-          int amb = 0;
-          for (int w = 0; w < nw; ++w) {
-            const int rep = (w0 + w) * 32 + lane;
-            const bool valid = rep < R;
-            const int cov = (int)(rowj[w * 32 + lane] - rowi[w * 32 + lane]);
-            const u32 by = __ballot_sync(0xffffffffu, valid && cov >= cy);
-            const u32 bn = __ballot_sync(0xffffffffu, valid && cov <= cn);
-            if (lane == 0) {
-              ynm[(size_t)e * wc + w] = make_uint2(by, bn);
-              const int left = R - (w0 + w) * 32;
-              const u32 vm = (left >= 32) ? 0xffffffffu : ((1u << left) - 1u);
-              const u32 am = vm & ~(by | bn);
-              if (am) {
-                const int np = nplanes[w];
-                for (int b = 0; b < np; ++b) amb += __popc(am & planes[w * 32 + b]) << b;
-              }
-            }
-          }
-          if (lane == 0 && amb) atomicAdd(&ins_g[i * n + j], amb);
-        }
-      }
-    }
-    __syncthreads();  // masks complete, tile free
-    if (tid == 0 && w0 + wc < w_hi) issue(w0 + wc);
-    // ---- triple phase ----
-    for (int j = 1 + warp; j <= n - 2; j += NW) {
-      const int cols = n - 1 - j;
-      int* outj = out_g + triple_mid_off(j, n);
-      for (int i = lane; i < j; i += 32) {
-        const uint2* yn_ij = ynm + (size_t)pair_index(i, j, n) * wc;
-        uint2 rij[DPT_MAXW];
-#pragma unroll
-        for (int w = 0; w < DPT_MAXW; ++w) rij[w] = (w < nw) ? yn_ij[w] : make_uint2(0u, 0u);
-        const uint2* yn_jk = ynm + (size_t)pair_index(j, j + 1, n) * wc;
-        for (int k = j + 1; k < n; ++k, yn_jk += wc) {
-          int acc = 0;
-#pragma unroll
-          for (int w = 0; w < DPT_MAXW; ++w) {
-            if (w < nw) {
-              uint2 jk = yn_jk[w];
-              u32 m = (rij[w].x & jk.y) | (rij[w].y & jk.x);
-              if (m) {
-                int np = nplanes[w];
-                for (int b = 0; b < np; ++b) acc += __popc(m & planes[w * 32 + b]) << b;
-              }
-            }
-          }
-          if (acc) atomicAdd(&outj[i * cols + (k - j - 1)], acc);
-        }
-      }
-    }
-    __syncthreads();  // the next chunk rewrites the weight planes and the masks: wait for every warp's triple phase
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
-// K8 DP solve (one CTA per subproblem).  G(j,k) = best continuation after committing segment (j,k):
+// K8 DP solve (block-cooperative device function; tables in shared OR global memory).
+//   G(j,k) = best continuation after committing segment (j,k):
 //   G(j,E) = ins(j,E);  G(j,k) = max_{k'>k} D(j,k,k')  (ascending k', first maximum wins)
 //   D(i,j,k) = ins(i,j) + out(i,j,k) + G(j,k)  if both segments span >= 5 samples, out >= lo and
 //              G(j,k) is finite, else -inf                                   (:532-558)
 // Top level (:560-566): lexicographic (j,k), strict improvement over ins(0,E).  Backtrace (:592-594)
-// marks the chosen candidates.
+// marks the chosen candidates.  amb = pair-indexed POSITIVE ambiguous counts: ins(i,j) = -amb[pair(i,j)].
 // ---------------------------------------------------------------------------------------------
-#define DPS_THREADS 128
-
-struct DpsArgs {
-  const int* sub_start; const int* sub_n; const i64* sub_pair_off; const i64* sub_triple_off;
-  const int* cand_flat; const int* ins; const int* out; int lo; int max_n;
-  u8* final_flag; int* err;
-};
-
-__global__ void __launch_bounds__(DPS_THREADS) k_dp_solve(DpsArgs A) {
-  extern __shared__ int ssm[];
-  const int p = blockIdx.x;
-  const int n = A.sub_n[p], qs = A.sub_start[p], E = n - 1;
-  int* G = ssm;                          // [n][n]
-  int* cf = G + A.max_n * A.max_n;       // [n]
-  short* arg = (short*)(cf + A.max_n);   // [n][n]
-  __shared__ int best_v[DPS_THREADS / 32];
-  __shared__ int best_e[DPS_THREADS / 32];
-  const int* ins = A.ins + A.sub_pair_off[p];  // positive ambiguous counts; ins(i,j) = -ins[i*n+j]
-  const int* out = A.out + A.sub_triple_off[p];
-  const int tid = threadIdx.x;
-  for (int i = tid; i < n; i += DPS_THREADS) cf[i] = A.cand_flat[qs + i];
-  for (int e = tid; e < n * n; e += DPS_THREADS) { G[e] = FRS_NEG_INF; arg[e] = -1; }
+#define DPS_MAX_WARPS 16
+__device__ void dp_solve_block(const int n, const int* __restrict__ cf, const int* amb, const int* out, const int lo,
+                               int* G /*[n*n]*/, short* arg /*[n*n]*/, int* red /*[2*DPS_MAX_WARPS]*/,
+                               u8* __restrict__ final_flag /* + qs */, int* __restrict__ err, int p) {
+  const int tid = threadIdx.x, nt = blockDim.x, E = n - 1;
+  for (int e = tid; e < n * n; e += nt) { G[e] = FRS_NEG_INF; arg[e] = -1; }
   __syncthreads();
-  for (int j = tid; j < E; j += DPS_THREADS) G[j * n + E] = -ins[j * n + E];
+  for (int j = tid; j < E; j += nt) G[j * n + E] = -amb[pair_index(j, E, n)];
   __syncthreads();
   for (int j = E - 2; j >= 0; --j) {
     // all k in (j, E) are independent given rows k > j
-    for (int k = j + 1 + tid; k < E; k += DPS_THREADS) {
+    for (int k = j + 1 + tid; k < E; k += nt) {
       int best = FRS_NEG_INF, bk = -1;
       if (cf[k] - cf[j] >= 5) {
-        const int base = -ins[j * n + k];
+        const int base = -amb[pair_index(j, k, n)];
         const int* o = out + triple_mid_off(k, n) + j * (n - 1 - k);
         for (int k2 = k + 1; k2 <= E; ++k2) {
           if (cf[k2] - cf[k] < 5) continue;
           int ov = o[k2 - k - 1];
-          if (ov < A.lo) continue;
+          if (ov < lo) continue;
           int g = G[k * n + k2];
           if (g == FRS_NEG_INF) continue;
           int d = base + ov + g;
@@ -433,15 +317,15 @@ __global__ void __launch_bounds__(DPS_THREADS) k_dp_solve(DpsArgs A) {
   }
   // top level: D(0,j,k) over 1 <= j < k <= E, first maximum in lexicographic order
   int my_best = FRS_NEG_INF, my_e = 0x7fffffff;
-  for (int e = tid; e < n * n; e += DPS_THREADS) {
+  for (int e = tid; e < n * n; e += nt) {
     int j = e / n, k = e - j * n;
     if (j < 1 || k <= j) continue;
     if (cf[j] - cf[0] < 5 || cf[k] - cf[j] < 5) continue;
-    int ov = out[triple_mid_off(j, n) + 0 * (n - 1 - j) + (k - j - 1)];
-    if (ov < A.lo) continue;
+    int ov = out[triple_mid_off(j, n) + (k - j - 1)];
+    if (ov < lo) continue;
     int g = G[j * n + k];
     if (g == FRS_NEG_INF) continue;
-    int d = -ins[0 * n + j] + ov + g;
+    int d = -amb[pair_index(0, j, n)] + ov + g;
     if (d > my_best || (d == my_best && e < my_e)) { my_best = d; my_e = e; }
   }
 #pragma unroll
@@ -450,24 +334,290 @@ __global__ void __launch_bounds__(DPS_THREADS) k_dp_solve(DpsArgs A) {
     int oe = __shfl_xor_sync(0xffffffffu, my_e, o);
     if (ov > my_best || (ov == my_best && oe < my_e)) { my_best = ov; my_e = oe; }
   }
-  if ((tid & 31) == 0) { best_v[tid >> 5] = my_best; best_e[tid >> 5] = my_e; }
+  if ((tid & 31) == 0) { red[tid >> 5] = my_best; red[DPS_MAX_WARPS + (tid >> 5)] = my_e; }
   __syncthreads();
   if (tid == 0) {
-    for (int w = 1; w < DPS_THREADS / 32; ++w)
-      if (best_v[w] > my_best || (best_v[w] == my_best && best_e[w] < my_e)) { my_best = best_v[w]; my_e = best_e[w]; }
-    int none = -ins[0 * n + E];
+    for (int w = 1; w < (nt >> 5); ++w) {
+      int bv = red[w], be = red[DPS_MAX_WARPS + w];
+      if (bv > my_best || (bv == my_best && be < my_e)) { my_best = bv; my_e = be; }
+    }
+    int none = -amb[pair_index(0, E, n)];
     if (my_best != FRS_NEG_INF && my_best > none) {
       int j = my_e / n, k = my_e - j * n;
-      A.final_flag[qs + j] = 1;
-      A.final_flag[qs + k] = 1;
+      final_flag[j] = 1;
+      final_flag[k] = 1;
       int guard = 0;
       while (k != E) {
         int k2 = arg[j * n + k];
-        if (k2 <= k || ++guard > n) { dev_fail(A.err, DEVERR_BACKTRACE, p); break; }
-        A.final_flag[qs + k2] = 1;
+        if (k2 <= k || ++guard > n) { dev_fail(err, DEVERR_BACKTRACE, p); break; }
+        final_flag[k2] = 1;
         j = k;
         k = k2;
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7 DP tables (+ fused solve).  One CTA = (subproblem, slab of read-rep words).  Per chunk of wc words:
+//   1. TMA bulk copies stage the n coverage rows x 32*wc reps of the chunk into shared memory
+//      (the next chunk's copies fly during the triple phase of the current one);
+//   2. mask phase: a warp owns a row i, a lane owns a rep; for every j>i the lanes compare
+//      cov = P[j]-P[i] with the pair's integer cuts and __ballot_sync packs the yea / nay bits of
+//      32 reps into one word each (:488-497);
+//   3. ins pass: amb(i,j) = sum_w W . ~(yea|nay)   (:500-506), one thread per pair;
+//   4. triple phase: out(i,j,k) = sum_w W . [(yea_ij & nay_jk) | (nay_ij & yea_jk)]  (:509-528) as
+//      weighted popcounts over the packed words; a warp owns the middle candidate j, its lanes the
+//      left candidate i, the loop runs over k with broadcast shared-memory loads.
+// Weights: bit-planes of W per word (plane b = reps whose weight has bit b); a word whose reps all
+// have weight 1 costs one POPC.  Partial sums accumulate in shared memory over the chunks of the slab.
+// ---------------------------------------------------------------------------------------------
+#define DPT_MAXW 8
+
+struct DpArgs {
+  const int* sub_start; const int* sub_n; const int* sub_tint; const int* sub_info; const i64* sub_tab_off;
+  const int* tint_rep_off; const int* tint_cand_off; const i64* tint_cov_off;
+  const int* rep_weight; const int* cand_flat; const u32* P;
+  const double* thr_table; int thr_table_len; double tp;
+  int slab_words; int lo; int keep_tables;
+  int* tab;        // global tables of the split / kept subproblems
+  u8* final_flag;  // [n_cand]
+  int* err;
+};
+
+// shared-memory carve-up of k_dp for (M = largest n of the launch, wc, out table on chip?)
+struct DpSmem {
+  int tile, ynm, cf, ty, tn, planes, nplanes, vmask, amb, out, G, arg, red, total;
+};
+__host__ __device__ inline DpSmem dp_smem_layout(int M, int wc, int out_on_chip) {
+  DpSmem s;
+  int p2 = M * (M - 1) / 2;
+  int c3 = M * (M - 1) * (M - 2) / 6;
+  int o = 16;  // mbarrier
+  s.tile = o; o += M * 32 * wc * 4;
+  s.ynm = o; o += p2 * wc * 8;
+  s.cf = o; o += M * 4;
+  s.ty = o; o += p2 * 4;
+  s.tn = o; o += p2 * 4;
+  s.planes = o; o += wc * 32 * 4;
+  s.nplanes = o; o += wc * 4;
+  s.vmask = o; o += wc * 4;
+  s.amb = o; o += out_on_chip ? p2 * 4 : 0;
+  s.out = o; o += out_on_chip ? c3 * 4 : 0;
+  s.G = o; o += out_on_chip ? M * M * 4 : 0;
+  s.arg = o; o += out_on_chip ? M * M * 2 : 0;
+  o = (o + 3) & ~3;
+  s.red = o; o += 2 * DPS_MAX_WARPS * 4;
+  s.total = (o + 15) & ~15;
+  return s;
+}
+
+__device__ __forceinline__ int wpopc(u32 m, const u32* __restrict__ pl, int np) {
+  if (np <= 1) return __popc(m);  // every rep of the word has weight 1 (m only holds valid reps)
+  int acc = 0;
+  for (int b = 0; b < np; ++b) acc += __popc(m & pl[b]) << b;
+  return acc;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_dp(DpArgs A, const DpWork* __restrict__ work, int M, int wc,
+                                                int out_on_chip) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  const DpWork wk = work[blockIdx.x];
+  const int p = wk.sub;
+  const int n = A.sub_n[p];
+  const int qs = A.sub_start[p];
+  const int t = A.sub_tint[p];
+  const bool fused = (A.sub_info[p] >> 8) & 1;
+  const int r0 = A.tint_rep_off[t];
+  const int R = A.tint_rep_off[t + 1] - r0;
+  const int Rp = (R + 3) & ~3;
+  const int words = (R + 31) >> 5;
+  const int w_lo = fused ? 0 : wk.slab * A.slab_words;
+  const int w_hi = fused ? words : min(words, w_lo + A.slab_words);
+  const int p2 = n * (n - 1) / 2;
+  const int c3 = n * (n - 1) * (n - 2) / 6;
+  const int CW = 32 * wc;
+  const DpSmem L = dp_smem_layout(M, wc, out_on_chip);
+  unsigned long long* bar = (unsigned long long*)dsm;
+  u32* tile = (u32*)(dsm + L.tile);      // [n][CW]   (16-byte aligned rows)
+  uint2* ynm = (uint2*)(dsm + L.ynm);    // [p2][wc]  x = yea, y = nay
+  int* cf = (int*)(dsm + L.cf);
+  int* ty = (int*)(dsm + L.ty);
+  int* tn = (int*)(dsm + L.tn);
+  u32* planes = (u32*)(dsm + L.planes);  // [wc][32]
+  int* nplanes = (int*)(dsm + L.nplanes);
+  u32* vmask = (u32*)(dsm + L.vmask);
+  int* amb_s = (int*)(dsm + L.amb);      // [p2]
+  int* out_s = (int*)(dsm + L.out);      // [c3]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = THREADS / 32;
+  const u32* Prow0 = A.P + A.tint_cov_off[t] + (i64)(qs - A.tint_cand_off[t]) * Rp;
+  int* tab_g = A.tab + A.sub_tab_off[p];  // only dereferenced when the subproblem owns a block
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < n; i += THREADS) cf[i] = A.cand_flat[qs + i];
+  if (out_on_chip) {
+    for (int e = tid; e < p2; e += THREADS) amb_s[e] = 0;
+    for (int e = tid; e < c3; e += THREADS) out_s[e] = 0;
+  }
+  __syncthreads();
+  // first chunk's TMA can fly while the cuts are computed
+  u32 phase = 0;
+  auto issue = [&](int w0) {
+    int col0 = w0 * 32;
+    int cols = min(CW, Rp - col0);
+    u32 bytes = (u32)cols * 4u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(bar, bytes * (u32)n);
+    for (int i = 0; i < n; ++i) tma_bulk_g2s(tile + (size_t)i * CW, Prow0 + (i64)i * Rp + col0, bytes, bar);
+  };
+  if (tid == 0 && w_lo < w_hi) issue(w_lo);
+  for (int e = tid; e < p2; e += THREADS) {
+    // decode pair e -> (i, j): rows are short, a linear walk is fine (done once per CTA)
+    int i = 0, rem = e;
+    while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
+    int j = i + 1 + rem;
+    int a, b;
+    length_cuts(cf[j] - cf[i] + 1, A.thr_table, A.thr_table_len, A.tp, a, b);
+    ty[e] = a;
+    tn[e] = b;
+  }
+
+  for (int w0 = w_lo; w0 < w_hi; w0 += wc) {
+    const int nw = min(wc, w_hi - w0);
+    // weight planes + valid-rep mask of the chunk's words
+    for (int w = warp; w < nw; w += NW) {
+      int rep = (w0 + w) * 32 + lane;
+      int wt = (rep < R) ? A.rep_weight[r0 + rep] : 0;
+      int mx = warp_max_i(wt);
+      int np = 32 - __clz(mx);
+      for (int b = 0; b < np; ++b) {
+        u32 m = __ballot_sync(0xffffffffu, (wt >> b) & 1);
+        if (lane == 0) planes[w * 32 + b] = m;
+      }
+      u32 vm = __ballot_sync(0xffffffffu, rep < R);
+      if (lane == 0) { nplanes[w] = np; vmask[w] = vm; }
+    }
+    __syncthreads();  // cuts + planes visible; previous chunk's triple phase done
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    // ---- mask phase: rows i paired from both ends for balance ----
+    {
+      u32 vl = 0;  // bit w: this lane's rep of word w is a real rep
+      for (int w = 0; w < nw; ++w) vl |= ((vmask[w] >> lane) & 1u) << w;
+      const int nrows = n - 1;          // rows i = 0..n-2
+      const int nrp = (nrows + 1) / 2;  // row a is processed together with row nrows-1-a
+      for (int a = warp; a < nrp; a += NW) {
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {
+          const int i = side ? (nrows - 1 - a) : a;
+          if (side && i == a) break;
+          const u32* rowi = tile + (size_t)i * CW + lane;
+          u32 ri[DPT_MAXW];
+#pragma unroll
+          for (int w = 0; w < DPT_MAXW; ++w) ri[w] = (w < nw) ? rowi[w * 32] : 0u;
+          const int ebase = pair_index(i, i + 1, n);
+          for (int j = i + 1; j < n; ++j) {
+            const int e = ebase + (j - i - 1);
+            const int cy = ty[e], cn = tn[e];
+            const u32* rowj = tile + (size_t)j * CW + lane;
+            u32 my_y = 0, my_n = 0;
+#pragma unroll
+            for (int w = 0; w < DPT_MAXW; ++w) {
+              if (w < nw) {
+                const bool valid = (vl >> w) & 1u;
+                const int cov = (int)(rowj[w * 32] - ri[w]);
+                const u32 by = __ballot_sync(0xffffffffu, valid && cov >= cy);
+                const u32 bn = __ballot_sync(0xffffffffu, valid && cov <= cn);
+                if (lane == w) { my_y = by; my_n = bn; }
+              }
+            }
+            if (lane < nw) ynm[(size_t)e * wc + lane] = make_uint2(my_y, my_n);
+          }
+        }
+      }
+    }
+    __syncthreads();  // masks complete, tile free
+    if (tid == 0 && w0 + wc < w_hi) issue(w0 + wc);
+    // ---- ins pass: ambiguous reps per pair ----
+    for (int e = tid; e < p2; e += THREADS) {
+      int acc = 0;
+      for (int w = 0; w < nw; ++w) {
+        const uint2 yn = ynm[(size_t)e * wc + w];
+        const u32 am = vmask[w] & ~(yn.x | yn.y);
+        if (am) acc += wpopc(am, planes + w * 32, nplanes[w]);
+      }
+      if (acc) {
+        if (out_on_chip) amb_s[e] += acc;
+        else atomicAdd(&tab_g[e], acc);
+      }
+    }
+    // ---- triple phase ----
+    for (int j = 1 + warp; j <= n - 2; j += NW) {
+      const int cols = n - 1 - j;
+      const int joff = triple_mid_off(j, n);
+      for (int i = lane; i < j; i += 32) {
+        const uint2* yn_ij = ynm + (size_t)pair_index(i, j, n) * wc;
+        uint2 rij[DPT_MAXW];
+#pragma unroll
+        for (int w = 0; w < DPT_MAXW; ++w) rij[w] = (w < nw) ? yn_ij[w] : make_uint2(0u, 0u);
+        const uint2* yn_jk = ynm + (size_t)pair_index(j, j + 1, n) * wc;
+        const int obase = joff + i * cols;
+        for (int k = j + 1; k < n; ++k, yn_jk += wc) {
+          int acc = 0;
+#pragma unroll
+          for (int w = 0; w < DPT_MAXW; ++w) {
+            if (w < nw) {
+              const uint2 jk = yn_jk[w];
+              const u32 m = (rij[w].x & jk.y) | (rij[w].y & jk.x);
+              if (m) acc += wpopc(m, planes + w * 32, nplanes[w]);
+            }
+          }
+          if (acc) {
+            if (out_on_chip) out_s[obase + (k - j - 1)] += acc;
+            else atomicAdd(&tab_g[p2 + obase + (k - j - 1)], acc);
+          }
+        }
+      }
+    }
+    __syncthreads();  // the next chunk rewrites the weight planes and the masks
+  }
+
+  if (!out_on_chip) return;  // class 4: tables are already in global memory
+  if (!fused) {
+    // split mode: add this slab's partial tables to the global ones
+    for (int e = tid; e < p2; e += THREADS) { int v = amb_s[e]; if (v) atomicAdd(&tab_g[e], v); }
+    for (int e = tid; e < c3; e += THREADS) { int v = out_s[e]; if (v) atomicAdd(&tab_g[p2 + e], v); }
+    return;
+  }
+  if (A.keep_tables) {
+    for (int e = tid; e < p2; e += THREADS) tab_g[e] = amb_s[e];
+    for (int e = tid; e < c3; e += THREADS) tab_g[p2 + e] = out_s[e];
+  }
+  dp_solve_block(n, cf, amb_s, out_s, A.lo, (int*)(dsm + L.G), (short*)(dsm + L.arg), (int*)(dsm + L.red),
+                 A.final_flag + qs, A.err, p);
+}
+
+// K8 for split subproblems: tables summed in global memory by the slab CTAs of k_dp.
+#define DPS_THREADS 128
+__global__ void __launch_bounds__(DPS_THREADS) k_dp_solve(DpArgs A, const int* __restrict__ split_list, int max_n) {
+  extern __shared__ __align__(16) int ssm[];
+  const int p = split_list[blockIdx.x];
+  const int n = A.sub_n[p], qs = A.sub_start[p];
+  int* G = ssm;                         // [n][n]
+  int* cf = G + max_n * max_n;          // [n]
+  int* red = cf + max_n;                // [2*DPS_MAX_WARPS]
+  short* arg = (short*)(red + 2 * DPS_MAX_WARPS);  // [n][n]
+  const int* tab = A.tab + A.sub_tab_off[p];
+  for (int i = threadIdx.x; i < n; i += DPS_THREADS) cf[i] = A.cand_flat[qs + i];
+  __syncthreads();
+  dp_solve_block(n, cf, tab, tab + n * (n - 1) / 2, A.lo, G, arg, red, A.final_flag + qs, A.err, p);
+}
+__host__ inline size_t dps_smem_bytes(int max_n) {
+  return (size_t)max_n * max_n * 4 + (size_t)max_n * 4 + 2 * DPS_MAX_WARPS * 4 + (size_t)max_n * max_n * 2 + 16;
 }

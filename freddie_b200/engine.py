@@ -169,6 +169,9 @@ class Engine:
         n = self.lib.frs_get_timings(self.ctx, names, ms, ln)
         return [(names[i].decode(), float(ms[i]), int(ln[i])) for i in range(n)]
 
+    def set_option(self, key: int, value: int):
+        self._check(self.lib.frs_set_option(self.ctx, int(key), int(value)))
+
     def launch_count(self) -> int:
         return int(self.lib.frs_last_launch_count(self.ctx))
 

@@ -159,14 +159,23 @@ enum {
   FRS_TAP_SUB_START = 7,  /* int32 [n_subproblems] first candidate rank of each subproblem */
   FRS_TAP_SUB_N = 8,      /* int32 [n_subproblems] size n */
   FRS_TAP_COVERAGE = 9,   /* u32   cumulative coverage rows, see DESIGN.md */
-  FRS_TAP_INS = 10,       /* int32 ins tables */
-  FRS_TAP_OUT = 11,       /* int32 out tables */
+  FRS_TAP_DP_TABLES = 10, /* int32 per-subproblem blocks: pair-indexed ambiguous counts (= -ins, :500-506),
+                             n(n-1)/2 entries, then out (:509-528) as [j][i][k-j-1], C(n,3) entries.  Blocks
+                             exist for subproblems of giant tints (summed over their rep slabs) and, with
+                             FRS_OPT_KEEP_DP_TABLES, for every subproblem */
   FRS_TAP_COV_OFF = 12,   /* int64 [n_tints+1] element offset of each tint's coverage block */
-  FRS_TAP_SUB_PAIR_OFF = 13,   /* int64 [n_subproblems+1] */
-  FRS_TAP_SUB_TRIPLE_OFF = 14, /* int64 [n_subproblems+1] */
+  FRS_TAP_SUB_TAB_OFF = 13, /* int64 [n_subproblems+1] element offset of each subproblem's table block */
 };
 /* Copies min(cap_bytes, size) bytes of the tap to dst (host) and stores the full size in *bytes. */
 int frs_get_intermediate(frs_context* ctx, int which, void* dst, size_t cap_bytes, size_t* bytes);
+
+/* ---- tuning / test options ---- */
+enum {
+  FRS_OPT_SLAB_WORDS = 1,     /* read reps per DP CTA, in words of 32 (default 64): tints with more reps are
+                                 processed by several CTAs per subproblem (multi-CTA mode) */
+  FRS_OPT_KEEP_DP_TABLES = 2, /* also store the on-chip ins/out tables of small tints for FRS_TAP_DP_TABLES */
+};
+int frs_set_option(frs_context* ctx, int key, long long value);
 
 /* ---- per-kernel device timing of the last frs_run (CUDA events on the context stream) ---- */
 #define FRS_MAX_STAGES 32

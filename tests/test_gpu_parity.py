@@ -92,19 +92,13 @@ def test_cfg1_taps_equal_reference_intermediates(golden_set, eng):
     assert P.shape[0] == len(cand)
 
 
-def test_dp_tables_equal_oracle(golden_set, eng):
-    """ins / out tables of every subproblem of a weighted tint against the oracle's numpy tables."""
+def _check_dp_tables(eng, tint, oprm, limit=12):
+    """ins / out blocks of the last run (one tint) against the oracle's numpy tables."""
     from freddie_b200 import _lib
-    from freddie_b200.pack import pack_tints
-    tints, flags, _ = golden_set("dup_heavy")
-    oprm, gprm = _params(flags)
-    batch = pack_tints(tints[:1])
-    eng.segment_batch(batch, gprm)
-    ot = copy.deepcopy(tints[0])
+    ot = copy.deepcopy(tint)
     it = orc.segment_tint(ot, oprm, keep=True)
     ss, sn = eng.tap(_lib.TAP_SUB_START, np.int32), eng.tap(_lib.TAP_SUB_N, np.int32)
-    po, to = eng.tap(_lib.TAP_SUB_PAIR_OFF, np.int64), eng.tap(_lib.TAP_SUB_TRIPLE_OFF, np.int64)
-    ins, out = eng.tap(_lib.TAP_INS, np.int32), eng.tap(_lib.TAP_OUT, np.int32)
+    off, tab = eng.tap(_lib.TAP_SUB_TAB_OFF, np.int64), eng.tap(_lib.TAP_DP_TABLES, np.int32)
     cand_off = np.cumsum([0] + [len(c) for c in it["cand"]])
     keys, members = orc.build_reps(ot)
     checked = 0
@@ -112,25 +106,67 @@ def test_dp_tables_equal_oracle(golden_set, eng):
         a = int(np.searchsorted(cand_off, ss[p], side="right") - 1)
         start = int(ss[p] - cand_off[a])
         n = int(sn[p])
+        assert off[p + 1] - off[p] == n * (n - 1) // 2 + n * (n - 1) * (n - 2) // 6
         isl = ot["intervals"][a]
         rep_iv = [[(ts - isl[0], te - isl[0]) for ts, te in k if isl[0] <= ts <= isl[1]] for k in keys]
         C = orc.coverage_matrix(rep_iv, it["cand"][a])
         oi, oo = orc.dp_tables(it["cand"][a], C, it["W"], start, start + n - 1, oprm.table, oprm.tp)
-        gi = ins[po[p]:po[p + 1]].reshape(n, n)
+        blk = tab[off[p]:off[p + 1]]
+        k = 0
         for i in range(n - 1):
             for j in range(i + 1, n):
-                assert -gi[i, j] == oi[i, j]
-        g = out[to[p]:to[p + 1]]
-        k = 0
+                assert -blk[k] == oi[i, j], (p, i, j)
+                k += 1
         for j in range(1, n - 1):
             for i in range(j):
                 for kk in range(j + 1, n):
-                    assert g[k] == oo[i, j, kk], (p, i, j, kk)
+                    assert blk[k] == oo[i, j, kk], (p, i, j, kk)
                     k += 1
         checked += 1
-        if checked >= 12:
+        if checked >= limit:
             break
     assert checked > 0
+
+
+def test_dp_tables_equal_oracle(golden_set, eng):
+    """ins / out tables of every subproblem of a weighted tint against the oracle's numpy tables: once
+    from the on-chip tables of the one-CTA mode, once summed over rep slabs by the multi-CTA mode."""
+    from freddie_b200 import _lib
+    from freddie_b200.pack import pack_tints
+    tints, flags, _ = golden_set("dup_heavy")
+    oprm, gprm = _params(flags)
+    batch = pack_tints(tints[:1])
+    try:
+        eng.set_option(_lib.OPT_KEEP_DP_TABLES, 1)
+        eng.segment_batch(batch, gprm)
+        _check_dp_tables(eng, tints[0], oprm)
+        eng.set_option(_lib.OPT_KEEP_DP_TABLES, 0)
+        eng.set_option(_lib.OPT_SLAB_WORDS, 2)
+        eng.segment_batch(batch, gprm)
+        _check_dp_tables(eng, tints[0], oprm)
+    finally:
+        eng.set_option(_lib.OPT_KEEP_DP_TABLES, 0)
+        eng.set_option(_lib.OPT_SLAB_WORDS, 64)
+
+
+@pytest.mark.parametrize("name", ["dup_heavy", "cfg3_mini", "cfg4_mini", "cfg2_flagsB"])
+def test_multi_cta_mode_equals_one_cta_mode(name, golden_set, eng):
+    """Giant-tint path on small data: with 32-rep slabs every tint above 32 reps runs its subproblems as
+    several CTAs + k_dp_solve; all results must equal the default (one CTA per subproblem) run."""
+    from freddie_b200 import _lib
+    from freddie_b200.pack import pack_tints
+    tints, flags, _ = golden_set(name)
+    _, gprm = _params(flags)
+    batch = pack_tints(tints)
+    want = eng.segment_batch(batch, gprm)
+    try:
+        for words in (1, 3):
+            eng.set_option(_lib.OPT_SLAB_WORDS, words)
+            got = eng.segment_batch(batch, gprm)
+            for k in want.arrays:
+                assert np.array_equal(want.arrays[k], got.arrays[k]), (name, words, k)
+    finally:
+        eng.set_option(_lib.OPT_SLAB_WORDS, 64)
 
 
 def test_in_process_seam_has_reference_signature(golden_set):
