@@ -18,6 +18,8 @@
 
 static thread_local char g_err[512] = "";
 
+#define FRS_SIDE_STREAMS 4
+
 struct DBuf {
   void* p = nullptr;
   size_t cap = 0;
@@ -34,6 +36,8 @@ struct Stage {
 struct frs_context {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side[FRS_SIDE_STREAMS] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[FRS_SIDE_STREAMS] = {};
   char err[512] = "";
   bool uploaded = false, ran = false;
   bool profiling = false;
@@ -217,8 +221,14 @@ int frs_create(int device, frs_context** out) {
     delete c;
     return r;
   }
+  for (int i = 0; i < FRS_SIDE_STREAMS; ++i) {
+    cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
+  }
+  cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+  cudaFuncSetAttribute(k_dp_warp<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DPW_WARPS * sizeof(DpWarpSmem<8>)));
+  cudaFuncSetAttribute(k_dp_warp<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DPW_WARPS * sizeof(DpWarpSmem<16>)));
   cudaFuncSetAttribute(k_signal, cudaFuncAttributeMaxDynamicSharedMemorySize, SIG_BINS * 4);
-  cudaFuncSetAttribute(k_dp<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(k_dp<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(k_dp<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(k_dp<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -238,6 +248,11 @@ void frs_destroy(frs_context* c) {
     cudaEventDestroy(c->stages[i].ev1);
   }
   if (c->h_pin) cudaFreeHost(c->h_pin);
+  for (int i = 0; i < FRS_SIDE_STREAMS; ++i) {
+    if (c->side[i]) cudaStreamDestroy(c->side[i]);
+    if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+  }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -528,8 +543,8 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
 
   const int slab_words = c->opt_slab_words;
   const int keep = c->opt_keep_tables;
-  i64 tab_total = 0, n_split = 0, dp_cells = 0, dp_read_cells = 0, cls_cnt[DP_CLASSES] = {0, 0, 0, 0, 0};
-  int cls_maxn[DP_CLASSES] = {0, 0, 0, 0, 0};
+  i64 tab_total = 0, n_split = 0, dp_cells = 0, dp_read_cells = 0, cls_cnt[DP_CLASSES] = {0, 0, 0, 0, 0, 0};
+  int cls_maxn[DP_CLASSES] = {0, 0, 0, 0, 0, 0};
   int max_n = 0;
   if (NSUB > 0) {
     ENS(b_sub_start, NSUB * 4);
@@ -599,28 +614,42 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
     A.tint_cov_off = c->b_tint_cov_off.as<i64>(); A.rep_weight = c->b_rep_weight.as<int>();
     A.cand_flat = c->b_cand_flat.as<int>(); A.P = c->b_P.as<u32>();
     A.thr_table = d_tbl; A.thr_table_len = prm->thr_table_len; A.tp = prm->tp;
-    A.slab_words = slab_words; A.lo = prm->lo; A.keep_tables = keep;
+    A.lo = prm->lo; A.keep_tables = keep;
     A.tab = c->b_tab.as<int>(); A.final_flag = c->b_dpfinal.as<u8>(); A.err = d_err;
     const int SMEM_BUDGET = 200 * 1024;
-    for (int k = 0; k < DP_CLASSES; ++k) {
+    // the classes are independent: launch them on side streams so that the few long CTAs of the large
+    // classes overlap the many short ones (fork / join with events on the context stream)
+    CK(cudaEventRecord(c->ev_fork, st));
+    int side = 0;
+    for (int k = DP_CLASSES - 1; k >= 0; --k) {  // longest-running classes first
       if (cls_cnt[k] == 0) continue;
-      const int M = cls_maxn[k], on_chip = k < 4 ? 1 : 0;
-      int wc = (k <= 2) ? 4 : DPT_MAXW;
-      while (wc > 1 && dp_smem_layout(M, wc, on_chip).total > SMEM_BUDGET) wc >>= 1;
-      const size_t sm = (size_t)dp_smem_layout(M, wc, on_chip).total;
-      if (sm > 227 * 1024)
-        return fail(c, FRS_ERR_LIMIT, "subproblem with %d candidates exceeds the DP kernel's shared-memory budget "
-                                      "(max_problem_size too large for this build)", M);
+      cudaStream_t ks = c->side[side % FRS_SIDE_STREAMS];
+      CK(cudaStreamWaitEvent(ks, c->ev_fork, 0));
       const DpWork* wl = c->b_work.as<DpWork>() + bases.base[k];
-      const unsigned g = (unsigned)cls_cnt[k];
-      switch (k) {
-        case 0: k_dp<64><<<g, 64, sm, st>>>(A, wl, M, wc, on_chip); break;
-        case 1: k_dp<128><<<g, 128, sm, st>>>(A, wl, M, wc, on_chip); break;
-        case 2: k_dp<256><<<g, 256, sm, st>>>(A, wl, M, wc, on_chip); break;
-        default: k_dp<512><<<g, 512, sm, st>>>(A, wl, M, wc, on_chip); break;
+      if (k <= 1) {
+        const unsigned g = (unsigned)((cls_cnt[k] + DPW_WARPS - 1) / DPW_WARPS);
+        if (k == 0) k_dp_warp<8><<<g, DPW_WARPS * 32, DPW_WARPS * sizeof(DpWarpSmem<8>), ks>>>(A, wl, (int)cls_cnt[k]);
+        else k_dp_warp<16><<<g, DPW_WARPS * 32, DPW_WARPS * sizeof(DpWarpSmem<16>), ks>>>(A, wl, (int)cls_cnt[k]);
+      } else {
+        const int M = cls_maxn[k], on_chip = k < 5 ? 1 : 0;
+        int wc = (k <= 3) ? 4 : DPT_MAXW;
+        while (wc > 1 && dp_smem_layout(M, wc, on_chip).total > SMEM_BUDGET) wc >>= 1;
+        const size_t sm = (size_t)dp_smem_layout(M, wc, on_chip).total;
+        if (sm > 227 * 1024)
+          return fail(c, FRS_ERR_LIMIT, "subproblem with %d candidates exceeds the DP kernel's shared-memory budget "
+                                        "(max_problem_size too large for this build)", M);
+        const unsigned g = (unsigned)cls_cnt[k];
+        switch (k) {
+          case 2: k_dp<128><<<g, 128, sm, ks>>>(A, wl, M, wc, on_chip); break;
+          case 3: k_dp<256><<<g, 256, sm, ks>>>(A, wl, M, wc, on_chip); break;
+          default: k_dp<512><<<g, 512, sm, ks>>>(A, wl, M, wc, on_chip); break;
+        }
       }
       LAUNCHED();
+      CK(cudaEventRecord(c->ev_join[side % FRS_SIDE_STREAMS], ks));
+      ++side;
     }
+    for (int k = 0; k < side && k < FRS_SIDE_STREAMS; ++k) CK(cudaStreamWaitEvent(st, c->ev_join[k], 0));
     if (n_split > 0) {
       stage_begin(c, "dp_solve");
       size_t sm2 = dps_smem_bytes(max_n);

@@ -140,21 +140,36 @@ __global__ void k_sub_flag(int n_fixed, const int* __restrict__ fixed_list, cons
 // shared-memory carve-ups; class 4 (n > DP_SMEM_MAX_N, only reachable with a large -mps) keeps its
 // out table in global memory and is always split.
 // ---------------------------------------------------------------------------------------------
-#define DP_CLASSES 5
+#define DP_CLASSES 6
 #define DP_SMEM_MAX_N 56
+#define DP_WARP_MAX_WORDS 16
 // counter slots (i64) written by k_sub_plan
-#define PLAN_WORK 0     // [5] work items per class
-#define PLAN_MAXN 5     // [5] largest n per class
-#define PLAN_SPLIT 10   // subproblems that need k_dp_solve
-#define PLAN_CELLS 11   // sum C(n,3)
-#define PLAN_RCELLS 12  // sum C(n,3) * R
-#define PLAN_MAXALL 13  // largest n
+#define PLAN_WORK 0     // [6] work items per class
+#define PLAN_MAXN 6     // [6] largest n per class
+#define PLAN_SPLIT 12   // subproblems that need k_dp_solve
+#define PLAN_CELLS 13   // sum C(n,3)
+#define PLAN_RCELLS 14  // sum C(n,3) * R
+#define PLAN_MAXALL 15  // largest n
 #define PLAN_SLOTS 16
 
 struct DpWork { int sub; int slab; };
 
-__host__ __device__ inline int dp_class_of(int n) {
-  return n <= 8 ? 0 : n <= 16 ? 1 : n <= 32 ? 2 : n <= DP_SMEM_MAX_N ? 3 : 4;
+// classes: 0 / 1 = one WARP per subproblem (n <= 8 / 16, tint of at most 512 reps);
+//          2 / 3 / 4 = one CTA of 128 / 256 / 512 threads per (subproblem, slab), n <= 16 / 32 / 56;
+//          5 = n > 56 (only reachable with a large -mps): out table in global memory, always split.
+__host__ __device__ inline int dp_class_of(int n, int words, int fused) {
+  if (fused && n <= 16 && words <= DP_WARP_MAX_WORDS) return n <= 8 ? 0 : 1;
+  return n <= 16 ? 2 : n <= 32 ? 3 : n <= DP_SMEM_MAX_N ? 4 : 5;
+}
+
+// read-rep words per CTA of a subproblem: bounded work per CTA (~ n^3 x words) so that a few large
+// subproblems of a mid-size tint do not become the tail of the launch, at least ~8 slabs for tints
+// well above that bound, and at most `cap` words (giant tints: fewer, fatter CTAs -> fewer REDs).
+__host__ __device__ inline int dp_slab_words(int n, int words, int cap) {
+  int lat = (1 << 20) / (n * n * n);
+  lat = max(4, min(64, lat)) & ~3;
+  int spread = (((words + 7) / 8) + 3) & ~3;
+  return max(1, min(cap, max(lat, spread)));
 }
 
 __device__ __forceinline__ long long warp_sum_ll(long long v) {
@@ -168,12 +183,12 @@ __device__ __forceinline__ int warp_max_i(int v) {
   return v;
 }
 
-// sub_info[p] = class | fused << 8 | slabs << 16 ... slabs can exceed 16 bits for absurd sizes, so it
-// has its own array.  sz_tab[p] = int32 elements of the subproblem's global table block
-// (pair-indexed ins [n(n-1)/2] followed by out [C(n,3)]), 0 when the tables stay on chip.
+// sub_info[p] = class | fused << 8 | slab_words << 16;  sub_slabs[p] = CTAs of the subproblem.
+// sz_tab[p] = int32 elements of the subproblem's global table block (pair-indexed ins [n(n-1)/2]
+// followed by out [C(n,3)]), 0 when the tables stay on chip.
 __global__ void k_sub_plan(int n_sub, const int* __restrict__ sub_fidx, const int* __restrict__ fixed_list,
                            const int* __restrict__ cand_island, const int* __restrict__ island_tint,
-                           const int* __restrict__ tint_rep_off, int slab_words, int keep_tables,
+                           const int* __restrict__ tint_rep_off, int slab_cap, int keep_tables,
                            int* __restrict__ sub_start, int* __restrict__ sub_n, int* __restrict__ sub_tint,
                            int* __restrict__ sub_info, int* __restrict__ sub_slabs, int* __restrict__ sz_tab,
                            i64* __restrict__ plan) {
@@ -188,16 +203,17 @@ __global__ void k_sub_plan(int n_sub, const int* __restrict__ sub_fidx, const in
     int t = island_tint[cand_island[a]];
     int R = tint_rep_off[t + 1] - tint_rep_off[t];
     int words = (R + 31) >> 5;
-    cls = dp_class_of(n);
-    int fused = (cls < 4 && words <= slab_words) ? 1 : 0;
-    slabs = fused ? 1 : (words + slab_words - 1) / slab_words;
+    int sw = dp_slab_words(n, words, slab_cap);
+    int fused = (n <= DP_SMEM_MAX_N && words <= sw) ? 1 : 0;
+    cls = dp_class_of(n, words, fused);
+    slabs = fused ? 1 : (words + sw - 1) / sw;
     split = !fused;
     t3 = (long long)n * (n - 1) * (n - 2) / 6;
     rc = t3 * R;
     sub_start[p] = a;
     sub_n[p] = n;
     sub_tint[p] = t;
-    sub_info[p] = cls | (fused << 8);
+    sub_info[p] = cls | (fused << 8) | (sw << 16);
     sub_slabs[p] = slabs;
     sz_tab[p] = (fused && !keep_tables) ? 0 : (int)(n * (n - 1) / 2 + t3);
   }
@@ -285,14 +301,22 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, u32 byt
 // marks the chosen candidates.  amb = pair-indexed POSITIVE ambiguous counts: ins(i,j) = -amb[pair(i,j)].
 // ---------------------------------------------------------------------------------------------
 #define DPS_MAX_WARPS 16
-__device__ void dp_solve_block(const int n, const int* __restrict__ cf, const int* amb, const int* out, const int lo,
-                               int* G /*[n*n]*/, short* arg /*[n*n]*/, int* red /*[2*DPS_MAX_WARPS]*/,
-                               u8* __restrict__ final_flag /* + qs */, int* __restrict__ err, int p) {
-  const int tid = threadIdx.x, nt = blockDim.x, E = n - 1;
+template <bool WARP>
+__device__ __forceinline__ void dp_sync() {
+  if (WARP) __syncwarp(); else __syncthreads();
+}
+// WARP = true: executed by one warp (lanes), else by the whole CTA.
+template <bool WARP>
+__device__ void dp_solve(const int n, const int* cf, const int* amb, const int* out, const int lo,
+                         int* G /*[n*n]*/, short* arg /*[n*n]*/, int* red /*[2*DPS_MAX_WARPS], CTA mode only*/,
+                         u8* __restrict__ final_flag /* + qs */, int* __restrict__ err, int p) {
+  const int tid = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+  const int nt = WARP ? 32 : (int)blockDim.x;
+  const int E = n - 1;
   for (int e = tid; e < n * n; e += nt) { G[e] = FRS_NEG_INF; arg[e] = -1; }
-  __syncthreads();
+  dp_sync<WARP>();
   for (int j = tid; j < E; j += nt) G[j * n + E] = -amb[pair_index(j, E, n)];
-  __syncthreads();
+  dp_sync<WARP>();
   for (int j = E - 2; j >= 0; --j) {
     // all k in (j, E) are independent given rows k > j
     for (int k = j + 1 + tid; k < E; k += nt) {
@@ -313,7 +337,7 @@ __device__ void dp_solve_block(const int n, const int* __restrict__ cf, const in
       G[j * n + k] = best;
       arg[j * n + k] = (short)bk;
     }
-    __syncthreads();
+    dp_sync<WARP>();
   }
   // top level: D(0,j,k) over 1 <= j < k <= E, first maximum in lexicographic order
   int my_best = FRS_NEG_INF, my_e = 0x7fffffff;
@@ -334,12 +358,16 @@ __device__ void dp_solve_block(const int n, const int* __restrict__ cf, const in
     int oe = __shfl_xor_sync(0xffffffffu, my_e, o);
     if (ov > my_best || (ov == my_best && oe < my_e)) { my_best = ov; my_e = oe; }
   }
-  if ((tid & 31) == 0) { red[tid >> 5] = my_best; red[DPS_MAX_WARPS + (tid >> 5)] = my_e; }
-  __syncthreads();
+  if (!WARP) {
+    if ((tid & 31) == 0) { red[tid >> 5] = my_best; red[DPS_MAX_WARPS + (tid >> 5)] = my_e; }
+    __syncthreads();
+  }
   if (tid == 0) {
-    for (int w = 1; w < (nt >> 5); ++w) {
-      int bv = red[w], be = red[DPS_MAX_WARPS + w];
-      if (bv > my_best || (bv == my_best && be < my_e)) { my_best = bv; my_e = be; }
+    if (!WARP) {
+      for (int w = 1; w < (nt >> 5); ++w) {
+        int bv = red[w], be = red[DPS_MAX_WARPS + w];
+        if (bv > my_best || (bv == my_best && be < my_e)) { my_best = bv; my_e = be; }
+      }
     }
     int none = -amb[pair_index(0, E, n)];
     if (my_best != FRS_NEG_INF && my_best > none) {
@@ -379,7 +407,7 @@ struct DpArgs {
   const int* tint_rep_off; const int* tint_cand_off; const i64* tint_cov_off;
   const int* rep_weight; const int* cand_flat; const u32* P;
   const double* thr_table; int thr_table_len; double tp;
-  int slab_words; int lo; int keep_tables;
+  int lo; int keep_tables;
   int* tab;        // global tables of the split / kept subproblems
   u8* final_flag;  // [n_cand]
   int* err;
@@ -433,8 +461,9 @@ __global__ void __launch_bounds__(THREADS) k_dp(DpArgs A, const DpWork* __restri
   const int R = A.tint_rep_off[t + 1] - r0;
   const int Rp = (R + 3) & ~3;
   const int words = (R + 31) >> 5;
-  const int w_lo = fused ? 0 : wk.slab * A.slab_words;
-  const int w_hi = fused ? words : min(words, w_lo + A.slab_words);
+  const int sw = A.sub_info[p] >> 16;  // read-rep words per CTA of this subproblem
+  const int w_lo = fused ? 0 : wk.slab * sw;
+  const int w_hi = fused ? words : min(words, w_lo + sw);
   const int p2 = n * (n - 1) / 2;
   const int c3 = n * (n - 1) * (n - 2) / 6;
   const int CW = 32 * wc;
@@ -599,8 +628,118 @@ __global__ void __launch_bounds__(THREADS) k_dp(DpArgs A, const DpWork* __restri
     for (int e = tid; e < p2; e += THREADS) tab_g[e] = amb_s[e];
     for (int e = tid; e < c3; e += THREADS) tab_g[p2 + e] = out_s[e];
   }
-  dp_solve_block(n, cf, amb_s, out_s, A.lo, (int*)(dsm + L.G), (short*)(dsm + L.arg), (int*)(dsm + L.red),
+  dp_solve<false>(n, cf, amb_s, out_s, A.lo, (int*)(dsm + L.G), (short*)(dsm + L.arg), (int*)(dsm + L.red),
                  A.final_flag + qs, A.err, p);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7+K8 for the many small subproblems of typical tints: ONE WARP per subproblem (n <= MAXN, at most
+// DP_WARP_MAX_WORDS x 32 read reps), eight subproblems per CTA, warp-synchronous only.  Per word of
+// 32 reps: lanes = reps load the n coverage rows (coalesced), every pair's yea/nay word is a pair of
+// ballots, ambiguous counts and the out table accumulate in the warp's shared-memory slice, then the
+// warp solves the DP in place.  No table ever leaves the SM.
+// ---------------------------------------------------------------------------------------------
+#define DPW_WARPS 8
+template <int MAXN>
+struct DpWarpSmem {
+  static constexpr int P2 = MAXN * (MAXN - 1) / 2;
+  static constexpr int C3 = MAXN * (MAXN - 1) * (MAXN - 2) / 6;
+  u32 tile[MAXN][32];
+  uint2 yn[P2];
+  int ty[P2], tn[P2], amb[P2];
+  int out[C3];
+  int G[MAXN * MAXN];
+  short arg[MAXN * MAXN];
+  int cf[MAXN];
+  u32 planes[32];
+};
+
+template <int MAXN>
+__global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWork* __restrict__ work, int n_work) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int item = blockIdx.x * DPW_WARPS + warp;
+  if (item >= n_work) return;
+  DpWarpSmem<MAXN>& S = reinterpret_cast<DpWarpSmem<MAXN>*>(dsm)[warp];
+  const int p = work[item].sub;
+  const int n = A.sub_n[p];
+  const int qs = A.sub_start[p];
+  const int t = A.sub_tint[p];
+  const int r0 = A.tint_rep_off[t];
+  const int R = A.tint_rep_off[t + 1] - r0;
+  const int Rp = (R + 3) & ~3;
+  const int words = (R + 31) >> 5;
+  const int p2 = n * (n - 1) / 2;
+  const int c3 = n * (n - 1) * (n - 2) / 6;
+  const u32* Prow0 = A.P + A.tint_cov_off[t] + (i64)(qs - A.tint_cand_off[t]) * Rp;
+  if (lane < n) S.cf[lane] = A.cand_flat[qs + lane];
+  __syncwarp();
+  for (int e = lane; e < p2; e += 32) {
+    int i = 0, rem = e;
+    while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
+    int j = i + 1 + rem;
+    int a, b;
+    length_cuts(S.cf[j] - S.cf[i] + 1, A.thr_table, A.thr_table_len, A.tp, a, b);
+    S.ty[e] = a;
+    S.tn[e] = b;
+    S.amb[e] = 0;
+  }
+  for (int e = lane; e < c3; e += 32) S.out[e] = 0;
+  const int npair_ij = (n - 2) * (n - 1) / 2;  // (j, i) with 1 <= j <= n-2, i < j
+  for (int w = 0; w < words; ++w) {
+    const int rep = w * 32 + lane;
+    const bool valid = rep < R;
+    const int wt = valid ? A.rep_weight[r0 + rep] : 0;
+    const int np = 32 - __clz(warp_max_i(wt));
+    const u32 vm = __ballot_sync(0xffffffffu, valid);
+    __syncwarp();  // previous word's readers are done with tile / yn / planes
+    if (np > 1)
+      for (int b = 0; b < np; ++b) {
+        u32 m = __ballot_sync(0xffffffffu, (wt >> b) & 1);
+        if (lane == 0) S.planes[b] = m;
+      }
+    for (int i = 0; i < n; ++i) S.tile[i][lane] = valid ? Prow0[(i64)i * Rp + rep] : 0u;
+    __syncwarp();
+    // masks
+    int e = 0;
+    for (int i = 0; i < n - 1; ++i) {
+      const u32 ri = S.tile[i][lane];
+      for (int j = i + 1; j < n; ++j, ++e) {
+        const int cov = (int)(S.tile[j][lane] - ri);
+        const u32 by = __ballot_sync(0xffffffffu, valid && cov >= S.ty[e]);
+        const u32 bn = __ballot_sync(0xffffffffu, valid && cov <= S.tn[e]);
+        if (lane == (e & 31)) S.yn[e] = make_uint2(by, bn);
+      }
+    }
+    __syncwarp();
+    // ambiguous counts
+    for (int q = lane; q < p2; q += 32) {
+      const uint2 yn = S.yn[q];
+      const u32 am = vm & ~(yn.x | yn.y);
+      if (am) S.amb[q] += wpopc(am, S.planes, np);
+    }
+    // triples: lanes over (j, i), loop over k
+    for (int q = lane; q < npair_ij; q += 32) {
+      int j = 1, rem = q;
+      while (rem >= j) { rem -= j; ++j; }
+      const int i = rem;
+      const uint2 ij = S.yn[pair_index(i, j, n)];
+      const uint2* jk = S.yn + pair_index(j, j + 1, n);
+      int* o = S.out + triple_mid_off(j, n) + i * (n - 1 - j);
+      for (int k = j + 1; k < n; ++k, ++jk, ++o) {
+        const uint2 v = *jk;
+        const u32 m = (ij.x & v.y) | (ij.y & v.x);
+        if (m) *o += wpopc(m, S.planes, np);
+      }
+    }
+  }
+  __syncwarp();
+  if (A.keep_tables) {
+    int* tab_g = A.tab + A.sub_tab_off[p];
+    for (int e = lane; e < p2; e += 32) tab_g[e] = S.amb[e];
+    for (int e = lane; e < c3; e += 32) tab_g[p2 + e] = S.out[e];
+  }
+  dp_solve<true>(n, S.cf, S.amb, S.out, A.lo, S.G, S.arg, nullptr, A.final_flag + qs, A.err, p);
 }
 
 // K8 for split subproblems: tables summed in global memory by the slab CTAs of k_dp.
@@ -616,7 +755,7 @@ __global__ void __launch_bounds__(DPS_THREADS) k_dp_solve(DpArgs A, const int* _
   const int* tab = A.tab + A.sub_tab_off[p];
   for (int i = threadIdx.x; i < n; i += DPS_THREADS) cf[i] = A.cand_flat[qs + i];
   __syncthreads();
-  dp_solve_block(n, cf, tab, tab + n * (n - 1) / 2, A.lo, G, arg, red, A.final_flag + qs, A.err, p);
+  dp_solve<false>(n, cf, tab, tab + n * (n - 1) / 2, A.lo, G, arg, red, A.final_flag + qs, A.err, p);
 }
 __host__ inline size_t dps_smem_bytes(int max_n) {
   return (size_t)max_n * max_n * 4 + (size_t)max_n * 4 + 2 * DPS_MAX_WARPS * 4 + (size_t)max_n * max_n * 2 + 16;
