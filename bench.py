@@ -118,7 +118,7 @@ def algorithmic_bytes(counts: dict, sizes: dict, cov_elems: int) -> dict:
         "dp": 4 * cov_elems + 4 * R,
         "refine": 8 * L,
         "digits": 8 * I + dig,
-        "gaps": 16 * Ir + 4 * N + 4 * counts["n_seq_words"] * 2,
+        "gaps": 16 * Ir + 4 * N,
     }
 
 

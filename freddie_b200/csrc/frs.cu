@@ -58,7 +58,7 @@ struct frs_context {
       b_sub_n, b_sub_tint, b_sub_info, b_sub_slabs, b_sz_tab, b_sub_tab_off, b_plan, b_work, b_split_list, b_cursor,
       b_cov_sz, b_tint_cov_off, b_P, b_tab, b_dpfinal, b_pf_list, b_gbuf, b_pstate, b_final_flat,
       b_final_pos, b_final_island, b_tint_final_off, b_dig_sz, b_tint_digit_off, b_seg_ty, b_seg_tn, b_digits,
-      b_run_cnt, b_run_off, b_runs, b_gap_cnt, b_read_gap_off, b_read_head, b_gap_rec, b_counters, b_stats, b_err;
+      b_run_cnt, b_run_off, b_runs, b_gap_cnt, b_task_n, b_task_order, b_task_res, b_poly_cls, b_read_gap_off, b_read_head, b_gap_rec, b_counters, b_stats, b_err;
   i64* h_pin = nullptr;  // pinned scratch for small D2H reads
   // results of the last run
   frs_result_sizes sizes;
@@ -232,7 +232,7 @@ int frs_create(int device, frs_context** out) {
   cudaFuncSetAttribute(k_dp<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(k_dp<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(k_dp<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(k_dp_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_dp_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   *out = c;
   return 0;
 }
@@ -461,7 +461,7 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
   ENS(b_y, L * 8);
   stage_begin(c, "gauss");
   {
-    size_t sm = (size_t)((2 * lw + 1) + TILE_SAMPLES + 2 * lw) * 8;
+    size_t sm = gauss_smem_bytes(lw);
     if (sm > 48 * 1024) CK(cudaFuncSetAttribute(k_gauss, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k_gauss<<<c->n_tiles, GAUSS_THREADS, sm, st>>>(c->b_tiles.as<TileWork>(), d_island_sample_off, c->b_yraw.as<int>(),
                                                    d_gw, lw, c->b_y.as<double>());
@@ -652,9 +652,10 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
     for (int k = 0; k < side && k < FRS_SIDE_STREAMS; ++k) CK(cudaStreamWaitEvent(st, c->ev_join[k], 0));
     if (n_split > 0) {
       stage_begin(c, "dp_solve");
-      size_t sm2 = dps_smem_bytes(max_n);
-      if (sm2 > 200 * 1024) return fail(c, FRS_ERR_LIMIT, "subproblem with %d candidates exceeds the DP solver's budget", max_n);
-      k_dp_solve<<<(unsigned)n_split, DPS_THREADS, sm2, st>>>(A, c->b_split_list.as<int>(), max_n);
+      const int stage_n = max_n < DP_SMEM_MAX_N ? max_n : DP_SMEM_MAX_N;
+      size_t sm2 = dps_smem_bytes(max_n, stage_n);
+      if (sm2 > 220 * 1024) return fail(c, FRS_ERR_LIMIT, "subproblem with %d candidates exceeds the DP solver's budget", max_n);
+      k_dp_solve<<<(unsigned)n_split, DPS_THREADS, sm2, st>>>(A, c->b_split_list.as<int>(), max_n, stage_n);
       LAUNCHED();
     }
   }
@@ -751,7 +752,22 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
     G.runs = c->b_runs.as<int2>(); G.tint_final_off = c->b_tint_final_off.as<int>();
     G.final_pos = c->b_final_pos.as<int>(); G.read_gap_off = c->b_read_gap_off.as<int>();
     G.read_head = c->b_read_head.as<int>(); G.gap_rec = c->b_gap_rec.as<int>(); G.err = d_err;
-    if (N > 0) { k_gaps<<<cdiv(N, 128), 128, 0, st>>>(G); LAUNCHED(); }
+    ENS(b_task_n, (size_t)N * 16);
+    ENS(b_task_order, (size_t)N * 16);
+    ENS(b_task_res, (size_t)N * 4 * sizeof(PolyRes));
+    ENS(b_poly_cls, (2 * POLY_CLASSES + 1) * 4);
+    G.task_n = c->b_task_n.as<int>(); G.cls_count = c->b_poly_cls.as<int>();
+    G.task_order = c->b_task_order.as<int>(); G.task_res = c->b_task_res.as<PolyRes>();
+    if (N > 0) {
+      CK(cudaMemsetAsync(c->b_poly_cls.p, 0, (2 * POLY_CLASSES + 1) * 4, st));
+      k_gap_prep<<<cdiv(N, 128), 128, 0, st>>>(G); LAUNCHED();
+      if (NGAP > 0) { k_gap_sizes<<<cdiv(NGAP, 128), 128, 0, st>>>(G, (int)NGAP); LAUNCHED(); }
+      stage_begin(c, "poly");
+      k_poly_bases<<<1, 32, 0, st>>>(G.cls_count); LAUNCHED();
+      k_poly_scatter<<<cdiv((i64)N * 4, 256), 256, 0, st>>>(N * 4, G.task_n, G.cls_count, G.task_order); LAUNCHED();
+      k_poly_scan<<<cdiv((i64)N * 4, 128), 128, 0, st>>>(G); LAUNCHED();
+      k_gap_finish<<<cdiv(N, 128), 128, 0, st>>>(G); LAUNCHED();
+    }
   }
   stage_end(c);
   { int r = check_dev_err(c); if (r) return r; }

@@ -305,26 +305,29 @@ template <bool WARP>
 __device__ __forceinline__ void dp_sync() {
   if (WARP) __syncwarp(); else __syncthreads();
 }
-// WARP = true: executed by one warp (lanes), else by the whole CTA.
-template <bool WARP>
+// WARP = true: executed by one warp (lanes), else by the whole CTA.  For a fixed j every (k, k2) is
+// independent: groups of SUB lanes own a k, the lanes of a group stride over k2 (ascending, strict >
+// keeps the first maximum per lane) and a shuffle reduction picks the maximum with the smallest k2.
+template <bool WARP, int SUB>
 __device__ void dp_solve(const int n, const int* cf, const int* amb, const int* out, const int lo,
                          int* G /*[n*n]*/, short* arg /*[n*n]*/, int* red /*[2*DPS_MAX_WARPS], CTA mode only*/,
                          u8* __restrict__ final_flag /* + qs */, int* __restrict__ err, int p) {
   const int tid = WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
   const int nt = WARP ? 32 : (int)blockDim.x;
   const int E = n - 1;
+  const int grp = tid / SUB, gl = tid % SUB, ngrp = nt / SUB;
   for (int e = tid; e < n * n; e += nt) { G[e] = FRS_NEG_INF; arg[e] = -1; }
   dp_sync<WARP>();
   for (int j = tid; j < E; j += nt) G[j * n + E] = -amb[pair_index(j, E, n)];
   dp_sync<WARP>();
   for (int j = E - 2; j >= 0; --j) {
-    // all k in (j, E) are independent given rows k > j
-    for (int k = j + 1 + tid; k < E; k += nt) {
-      int best = FRS_NEG_INF, bk = -1;
-      if (cf[k] - cf[j] >= 5) {
+    for (int kk = j + 1; kk < E; kk += ngrp) {  // uniform trip count: the shuffles below need every lane
+      const int k = kk + grp;
+      int best = FRS_NEG_INF, bk = 0x7fff;
+      if (k < E && cf[k] - cf[j] >= 5) {
         const int base = -amb[pair_index(j, k, n)];
         const int* o = out + triple_mid_off(k, n) + j * (n - 1 - k);
-        for (int k2 = k + 1; k2 <= E; ++k2) {
+        for (int k2 = k + 1 + gl; k2 <= E; k2 += SUB) {
           if (cf[k2] - cf[k] < 5) continue;
           int ov = o[k2 - k - 1];
           if (ov < lo) continue;
@@ -334,8 +337,16 @@ __device__ void dp_solve(const int n, const int* cf, const int* amb, const int* 
           if (d > best) { best = d; bk = k2; }
         }
       }
-      G[j * n + k] = best;
-      arg[j * n + k] = (short)bk;
+#pragma unroll
+      for (int s = SUB / 2; s > 0; s >>= 1) {
+        int ob = __shfl_xor_sync(0xffffffffu, best, s);
+        int ok = __shfl_xor_sync(0xffffffffu, bk, s);
+        if (ob > best || (ob == best && ok < bk)) { best = ob; bk = ok; }
+      }
+      if (gl == 0 && k < E) {
+        G[j * n + k] = best;
+        arg[j * n + k] = (short)(best == FRS_NEG_INF ? -1 : bk);
+      }
     }
     dp_sync<WARP>();
   }
@@ -628,7 +639,7 @@ __global__ void __launch_bounds__(THREADS) k_dp(DpArgs A, const DpWork* __restri
     for (int e = tid; e < p2; e += THREADS) tab_g[e] = amb_s[e];
     for (int e = tid; e < c3; e += THREADS) tab_g[p2 + e] = out_s[e];
   }
-  dp_solve<false>(n, cf, amb_s, out_s, A.lo, (int*)(dsm + L.G), (short*)(dsm + L.arg), (int*)(dsm + L.red),
+  dp_solve<false, (THREADS == 128 ? 16 : 32)>(n, cf, amb_s, out_s, A.lo, (int*)(dsm + L.G), (short*)(dsm + L.arg), (int*)(dsm + L.red),
                  A.final_flag + qs, A.err, p);
 }
 
@@ -739,12 +750,14 @@ __global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWo
     for (int e = lane; e < p2; e += 32) tab_g[e] = S.amb[e];
     for (int e = lane; e < c3; e += 32) tab_g[p2 + e] = S.out[e];
   }
-  dp_solve<true>(n, S.cf, S.amb, S.out, A.lo, S.G, S.arg, nullptr, A.final_flag + qs, A.err, p);
+  dp_solve<true, (MAXN <= 8 ? 8 : 16)>(n, S.cf, S.amb, S.out, A.lo, S.G, S.arg, nullptr, A.final_flag + qs, A.err, p);
 }
 
-// K8 for split subproblems: tables summed in global memory by the slab CTAs of k_dp.
-#define DPS_THREADS 128
-__global__ void __launch_bounds__(DPS_THREADS) k_dp_solve(DpArgs A, const int* __restrict__ split_list, int max_n) {
+// K8 for split subproblems: tables summed in global memory by the slab CTAs of k_dp; staged into
+// shared memory when they fit (n <= DP_SMEM_MAX_N), the sweep is latency-bound on table reads.
+#define DPS_THREADS 256
+__global__ void __launch_bounds__(DPS_THREADS) k_dp_solve(DpArgs A, const int* __restrict__ split_list, int max_n,
+                                                          int stage_max_n) {
   extern __shared__ __align__(16) int ssm[];
   const int p = split_list[blockIdx.x];
   const int n = A.sub_n[p], qs = A.sub_start[p];
@@ -752,11 +765,21 @@ __global__ void __launch_bounds__(DPS_THREADS) k_dp_solve(DpArgs A, const int* _
   int* cf = G + max_n * max_n;          // [n]
   int* red = cf + max_n;                // [2*DPS_MAX_WARPS]
   short* arg = (short*)(red + 2 * DPS_MAX_WARPS);  // [n][n]
+  int* stab = (int*)(arg + ((max_n * max_n + 1) & ~1));
   const int* tab = A.tab + A.sub_tab_off[p];
+  const int p2 = n * (n - 1) / 2;
   for (int i = threadIdx.x; i < n; i += DPS_THREADS) cf[i] = A.cand_flat[qs + i];
+  if (n <= stage_max_n) {
+    const int tot = p2 + n * (n - 1) * (n - 2) / 6;
+    for (int e = threadIdx.x; e < tot; e += DPS_THREADS) stab[e] = tab[e];
+    tab = stab;
+  }
   __syncthreads();
-  dp_solve<false>(n, cf, tab, tab + n * (n - 1) / 2, A.lo, G, arg, red, A.final_flag + qs, A.err, p);
+  dp_solve<false, 32>(n, cf, tab, tab + p2, A.lo, G, arg, red, A.final_flag + qs, A.err, p);
 }
-__host__ inline size_t dps_smem_bytes(int max_n) {
-  return (size_t)max_n * max_n * 4 + (size_t)max_n * 4 + 2 * DPS_MAX_WARPS * 4 + (size_t)max_n * max_n * 2 + 16;
+__host__ inline size_t dps_smem_bytes(int max_n, int stage_max_n) {
+  size_t b = (size_t)max_n * max_n * 4 + (size_t)max_n * 4 + 2 * DPS_MAX_WARPS * 4 + (size_t)((max_n * max_n + 1) & ~1) * 2;
+  size_t m = stage_max_n;
+  b += (m * (m - 1) / 2 + m * (m - 1) * (m - 2) / 6) * 4;
+  return b + 16;
 }

@@ -263,8 +263,27 @@ __global__ void k_gap_count(int n_reads, const int* __restrict__ read_rep, const
 }
 
 // ---------------------------------------------------------------------------------------------
-// K11 gaps / poly-A: one thread per read (:370-472).
+// find_longest_poly (:352-367) as independent scan TASKS.  A read has up to four: (start | end clip)
+// x (A | T).  Scan position t of a clip of n bases maps to read index first + t*step in the bit-plane
+// of the (possibly complemented) target base.  Score recurrence sc_t = max(0, sc_{t-1} + (+1 | -2)),
+// sc_{-1} = 0 (the reference's special case for t = 0 gives the same value).  For each maximal run
+// of positive scores: i* = LAST index of the run's maximum, len = i*+1-i0; inside a run the score is
+// matches - 2*mismatches, so matches = (peak + 2*len)/3 exactly and purity p = matches/len.  A run
+// counts if len >= 20 and p >= 0.85; the FIRST maximum of p wins.  Clips shorter than 20 bases cannot
+// hold such a run and get no task.
+// The scans are serial recurrences of very different lengths (0 .. whole read), so a thread per read
+// leaves ~5 of 32 lanes busy.  Instead every task is a thread and the tasks are bucketed by length
+// class (4 classes per octave, longest first), which keeps the lanes of a warp in step.
 // ---------------------------------------------------------------------------------------------
+#define POLY_CLASSES 96
+struct PolyRes { double p; int i0; int len; };  // len == 0: no qualifying run
+
+__device__ __forceinline__ int poly_class_dev(int n) {
+  // n >= 20.  class grows with n: octave * 4 + the next two mantissa bits
+  int o = 31 - __clz(n);
+  return min(POLY_CLASSES - 1, o * 4 + ((n >> (o - 2)) & 3));
+}
+
 struct GapArgs {
   int n_reads;
   const int* read_rep; const u8* read_strand; const int* read_len; const int* read_iv_off;
@@ -275,6 +294,11 @@ struct GapArgs {
   const int* tint_final_off; const int* final_pos;
   const int* read_gap_off;
   int* read_head; int* gap_rec; int* err;
+  // poly tasks: slot = read*4 + (0 start-A, 1 start-T, 2 end-A, 3 end-T)
+  int* task_n;        // [4N] clip length of the slot's scan, 0 = no task
+  int* cls_count;     // [POLY_CLASSES] (+ [POLY_CLASSES] cursors, + 1 total) zeroed before k_gap_prep
+  int* task_order;    // [4N] slots, longest class first
+  PolyRes* task_res;  // [4N]
 };
 
 // forward_thread_cigar (:289-304): every op length, insertions included, is clipped by the remaining
@@ -296,124 +320,212 @@ __device__ __forceinline__ bool thread_cigar(const u32* __restrict__ cig, int c0
   return t_pos == t_goal;
 }
 
-// get_interval_start (:307-326)
+// get_interval_start (:307-326): first interval with t_end >= p.  Intervals are ordered and disjoint
+// (asserted at parse time, :158-161), so the linear search of the reference is a binary search.
 __device__ bool interval_start(const GapArgs& A, int i0, int i1, int p, int& q, int& slack) {
-  for (int k = i0; k < i1; ++k) {
-    int ts = A.riv_ts[k], te = A.riv_te[k];
-    if (te < p) continue;
-    if (p < ts) { q = A.riv_qs[k]; slack = p - ts; return true; }
-    slack = 0;
-    if (!thread_cigar(A.cigar, A.riv_cig_off[k], A.riv_cig_off[k + 1], p, ts, A.riv_qs[k], q)) return false;
-    return q >= A.riv_qs[k] && q <= A.riv_qe[k];
+  int lo = i0, hi = i1;  // first k in [i0, i1) with te[k] >= p
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (A.riv_te[mid] < p) lo = mid + 1; else hi = mid;
   }
-  return false;
+  if (lo >= i1) return false;
+  const int k = lo, ts = A.riv_ts[k];
+  if (p < ts) { q = A.riv_qs[k]; slack = p - ts; return true; }
+  slack = 0;
+  if (!thread_cigar(A.cigar, A.riv_cig_off[k], A.riv_cig_off[k + 1], p, ts, A.riv_qs[k], q)) return false;
+  return q >= A.riv_qs[k] && q <= A.riv_qe[k];
 }
-// get_interval_end (:329-349)
+// get_interval_end (:329-349): last interval with t_start <= p
 __device__ bool interval_end(const GapArgs& A, int i0, int i1, int p, int& q, int& slack) {
-  for (int k = i1 - 1; k >= i0; --k) {
-    int ts = A.riv_ts[k], te = A.riv_te[k];
-    if (ts > p) continue;
-    if (te < p) { q = A.riv_qe[k]; slack = te - p; return true; }
-    slack = 0;
-    if (!thread_cigar(A.cigar, A.riv_cig_off[k], A.riv_cig_off[k + 1], p, ts, A.riv_qs[k], q)) return false;
-    return q >= 0 && q <= A.riv_qe[k];
+  int lo = i0, hi = i1;  // first k with ts[k] > p
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (A.riv_ts[mid] <= p) lo = mid + 1; else hi = mid;
   }
-  return false;
+  if (lo <= i0) return false;
+  const int k = lo - 1, ts = A.riv_ts[k], te = A.riv_te[k];
+  if (te < p) { q = A.riv_qe[k]; slack = te - p; return true; }
+  slack = 0;
+  if (!thread_cigar(A.cigar, A.riv_cig_off[k], A.riv_cig_off[k + 1], p, ts, A.riv_qs[k], q)) return false;
+  return q >= 0 && q <= A.riv_qe[k];
 }
 
-// One scan of find_longest_poly (:352-367) over a clip of n bases whose scan position t maps to read
-// index (first + t*step) in the plane `pl`; candidates with len >= 20 and purity >= 0.85 compete on
-// purity, the FIRST maximum wins (A runs are offered before T runs, :392-408).
-struct PolyBest { double p; int i0; int len; int kind; };
-
-__device__ void poly_scan(const u32* __restrict__ pl, int first, int step, int n, int kind, PolyBest& best) {
-  if (n <= 0) return;
-  int sc = 0;
-  int run_i0 = -1, run_best = 0, run_best_i = 0;
-  int prefix = 0;       // matches in [0, t)
-  int pre_i0 = 0;       // matches in [0, run_i0)
-  int pre_best = 0;     // matches in [0, run_best_i]
-  auto close = [&]() {
-    if (run_i0 < 0) return;
-    int len = run_best_i + 1 - run_i0;
-    if (len >= 20) {
-      double p = __ddiv_rn((double)(pre_best - pre_i0), (double)len);
-      if (p >= 0.85 && (best.kind == 0 || p > best.p)) { best.p = p; best.i0 = run_i0; best.len = len; best.kind = kind; }
+// K11a: per read, everything of get_unaligned_gaps_and_polyA (:370-472) except the poly scans:
+// clip bounds by CIGAR threading, unaligned gaps between consecutive 1-runs, and the scan tasks.
+// head[3] = q_ssc and head[6] = q_esc are provisional; k_gap_finish rewrites them.
+__global__ void __launch_bounds__(128) k_gap_prep(GapArgs A) {
+  __shared__ int sh_cnt[POLY_CLASSES];
+  for (int k = threadIdx.x; k < POLY_CLASSES; k += blockDim.x) sh_cnt[k] = 0;
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < A.n_reads) {
+    int* head = A.read_head + (i64)i * 8;
+    for (int k = 0; k < 8; ++k) head[k] = 0;
+    int* tn = A.task_n + (i64)i * 4;
+    tn[0] = tn[1] = tn[2] = tn[3] = 0;
+    const int rep = A.read_rep[i];
+    const int ra = A.run_off[rep], rb = A.run_off[rep + 1];
+    if (ra != rb) {  // else: no '1' digit, empty gaps (:372)
+      const int t = A.read_tint[i];
+      const int* fpos = A.final_pos + A.tint_final_off[t];  // segs[s] = (fpos[s], fpos[s+1])
+      const int i0 = A.read_iv_off[i], i1 = A.read_iv_off[i + 1];
+      const int L = A.read_len[i];
+      int q_ssc = 0, q_esc = 0, slack;
+      bool ok = true;
+      if (!interval_start(A, i0, i1, fpos[A.runs[ra].x], q_ssc, slack)) { dev_fail(A.err, DEVERR_THREAD_CIGAR, i); ok = false; }
+      if (ok && !interval_end(A, i0, i1, fpos[A.runs[rb - 1].y + 1], q_esc, slack)) { dev_fail(A.err, DEVERR_THREAD_CIGAR, i); ok = false; }
+      if (ok && !(0 <= q_ssc && q_ssc <= q_esc && q_esc <= L)) { dev_fail(A.err, DEVERR_Q_RANGE, i); ok = false; }
+      if (ok) {
+        head[0] = 1;
+        head[3] = q_ssc;
+        head[6] = q_esc;
+        const int ns = q_ssc, ne = L - q_esc;
+        if (ns >= 20) { tn[0] = tn[1] = ns; atomicAdd(&sh_cnt[poly_class_dev(ns)], 2); }
+        if (ne >= 20) { tn[2] = tn[3] = ne; atomicAdd(&sh_cnt[poly_class_dev(ne)], 2); }
+        // unaligned gaps between consecutive 1-runs (:455-471): (l1, f2, owner); k_gap_sizes fills the size
+        int* rec = A.gap_rec + (i64)A.read_gap_off[i] * 3;
+        for (int k = ra; k + 1 < rb; ++k, rec += 3) { rec[0] = A.runs[k].y; rec[1] = A.runs[k + 1].x; rec[2] = i; }
+      }
     }
-    run_i0 = -1;
-  };
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < POLY_CLASSES; k += blockDim.x)
+    if (sh_cnt[k]) atomicAdd(&A.cls_count[k], sh_cnt[k]);
+}
+
+// K11a': one thread per unaligned-gap record: "{l1}-{f2}:{size}" (:455-471)
+__global__ void k_gap_sizes(GapArgs A, int n_gaps) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_gaps) return;
+  int* rec = A.gap_rec + (i64)g * 3;
+  const int l1 = rec[0], f2 = rec[1], i = rec[2];
+  const int* fpos = A.final_pos + A.tint_final_off[A.read_tint[i]];
+  const int i0 = A.read_iv_off[i], i1 = A.read_iv_off[i + 1];
+  const int L = A.read_len[i];
+  int qa, sa, qb, sb;
+  if (!interval_end(A, i0, i1, fpos[l1 + 1], qa, sa)) { dev_fail(A.err, DEVERR_THREAD_CIGAR, i); return; }
+  if (!interval_start(A, i0, i1, fpos[f2], qb, sb)) { dev_fail(A.err, DEVERR_THREAD_CIGAR, i); return; }
+  if (!(0 < qa && qa <= qb && qb < L)) { dev_fail(A.err, DEVERR_GAP_RANGE, i); return; }
+  int size = max(0, qb - qa + sa + sb);
+  if (!(size < L)) { dev_fail(A.err, DEVERR_GAP_RANGE, i); return; }
+  rec[2] = size;
+}
+
+// one warp: class bases, LONGEST class first; cls_count[c] becomes the base, cursors start at 0
+__global__ void k_poly_bases(int* __restrict__ cls_count) {
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int c = POLY_CLASSES - 1; c >= 0; --c) { int v = cls_count[c]; cls_count[c] = acc; acc += v; }
+    cls_count[2 * POLY_CLASSES] = acc;  // total tasks
+  }
+}
+
+__global__ void k_poly_scatter(int n_slots, const int* __restrict__ task_n, int* __restrict__ cls_count,
+                               int* __restrict__ order) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  int n = task_n[s];
+  if (n < 20) return;
+  int c = poly_class_dev(n);
+  // warp-aggregate the cursor bump of lanes that share a class
+  unsigned peers = __match_any_sync(__activemask(), c);
+  int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(&cls_count[POLY_CLASSES + c], __popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  order[cls_count[c] + base + __popc(peers & ((1u << lane) - 1u))] = s;
+}
+
+// K11b: one thread per scan task
+__global__ void __launch_bounds__(128) k_poly_scan(GapArgs A) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= A.cls_count[2 * POLY_CLASSES]) return;
+  const int slot = A.task_order[e];
+  const int i = slot >> 2, which = slot & 3;
+  const int n = A.task_n[slot];
+  const int L = A.read_len[i];
+  const bool minus = A.read_strand[i] != 0;
+  const bool want_a = (which & 1) == 0;
+  // '+': seq[..] == ch; '-': reversed read, complemented target base (:392-401, :422-431)
+  const u32* pl = ((want_a != minus) ? A.seq_a : A.seq_t) + A.read_seq_off[i];
+  const int step = minus ? -1 : 1;
+  int idx;
+  if (which < 2) idx = minus ? L - 1 : 0;                 // start clip: q_ssc bases
+  else { const int q_esc = L - n; idx = minus ? L - 1 - q_esc : q_esc; }  // end clip: L - q_esc bases
+  PolyRes best; best.p = 0.0; best.i0 = 0; best.len = 0;
+  int sc = 0, run_i0 = 0, run_best = 0, run_best_i = 0;
+  // words are consumed in scan order; the next one is requested a whole word ahead of its use
+  const int wlast = (idx + step * (n - 1)) >> 5;  // last word the scan touches
+  int wi = idx >> 5;
+  u32 w = pl[wi];
+  u32 wnext = (wi != wlast) ? pl[wi + step] : 0u;
   for (int t = 0; t < n; ++t) {
-    int idx = first + t * step;
-    int m = (int)((pl[idx >> 5] >> (idx & 31)) & 1u);
-    if (t == 0) sc = m;  // scores[0] = match_score or 0 (:355-358)
-    else sc = max(0, sc + (m ? 1 : -2));
-    if (sc > 0) {
-      if (run_i0 < 0) { run_i0 = t; run_best = 0; pre_i0 = prefix; }
-      if (sc >= run_best) { run_best = sc; run_best_i = t; pre_best = prefix + m; }
-    } else {
-      close();
+    const int b = idx & 31;
+    const int m = (int)((w >> b) & 1u);
+    const int nsc = max(0, sc + (m ? 1 : -2));
+    if (nsc > 0) {
+      if (sc == 0) { run_i0 = t; run_best = 0; }
+      if (nsc >= run_best) { run_best = nsc; run_best_i = t; }
+    } else if (sc > 0) {  // the run [run_i0 .. t-1] closes
+      const int len = run_best_i + 1 - run_i0;
+      if (len >= 20) {
+        const double p = __ddiv_rn((double)((run_best + 2 * len) / 3), (double)len);
+        if (p >= 0.85 && (best.len == 0 || p > best.p)) { best.p = p; best.i0 = run_i0; best.len = len; }
+      }
     }
-    prefix += m;
+    sc = nsc;
+    idx += step;
+    if ((step > 0) ? (b == 31) : (b == 0)) {
+      w = wnext;
+      wi += step;
+      wnext = (wi != wlast && t + 1 < n) ? pl[wi + step] : 0u;
+    }
   }
-  close();
+  if (sc > 0) {
+    const int len = run_best_i + 1 - run_i0;
+    if (len >= 20) {
+      const double p = __ddiv_rn((double)((run_best + 2 * len) / 3), (double)len);
+      if (p >= 0.85 && (best.len == 0 || p > best.p)) { best.p = p; best.i0 = run_i0; best.len = len; }
+    }
+  }
+  A.task_res[slot] = best;
 }
 
-__global__ void k_gaps(GapArgs A) {
+// K11c: per read, pick the poly candidates (A offered before T, first maximum of p wins, :392-408)
+// and write the final head fields (:407-420, :438-454).
+__global__ void k_gap_finish(GapArgs A) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n_reads) return;
   int* head = A.read_head + (i64)i * 8;
-  for (int k = 0; k < 8; ++k) head[k] = 0;
-  const int rep = A.read_rep[i];
-  const int ra = A.run_off[rep], rb = A.run_off[rep + 1];
-  if (ra == rb) return;  // no '1' digit: empty gaps (:372)
-  const int t = A.read_tint[i];
-  const int* fpos = A.final_pos + A.tint_final_off[t];  // segs[s] = (fpos[s], fpos[s+1])
-  const int i0 = A.read_iv_off[i], i1 = A.read_iv_off[i + 1];
+  if (!(head[0] & 1)) return;
   const int L = A.read_len[i];
-  int q_ssc, q_esc, slack;
-  if (!interval_start(A, i0, i1, fpos[A.runs[ra].x], q_ssc, slack)) { dev_fail(A.err, DEVERR_THREAD_CIGAR, i); return; }
-  if (!interval_end(A, i0, i1, fpos[A.runs[rb - 1].y + 1], q_esc, slack)) { dev_fail(A.err, DEVERR_THREAD_CIGAR, i); return; }
-  if (!(0 <= q_ssc && q_ssc <= q_esc && q_esc <= L)) { dev_fail(A.err, DEVERR_Q_RANGE, i); return; }
-  const bool minus = A.read_strand[i] != 0;
-  const u32* pa = A.seq_a + A.read_seq_off[i];
-  const u32* pt = A.seq_t + A.read_seq_off[i];
-  // start clip: q_ssc bases; '+': seq[t] vs ch; '-': seq[L-1-t] vs complement(ch)  (:392-401)
-  PolyBest sb; sb.kind = 0; sb.p = 0; sb.i0 = 0; sb.len = 0;
-  poly_scan(minus ? pt : pa, minus ? L - 1 : 0, minus ? -1 : 1, q_ssc, 1, sb);
-  poly_scan(minus ? pa : pt, minus ? L - 1 : 0, minus ? -1 : 1, q_ssc, 2, sb);
+  const int q_ssc = head[3], q_esc = head[6];
+  const int* tn = A.task_n + (i64)i * 4;
+  const PolyRes* rs = A.task_res + (i64)i * 4;
   int flags = 1;
-  if (sb.kind) {
-    int gap = q_ssc - sb.i0 - sb.len;
-    if (!(0 <= gap && gap < q_ssc)) { dev_fail(A.err, DEVERR_POLY_RANGE, i); return; }
-    flags |= sb.kind << 8;
-    head[1] = sb.len; head[2] = gap; head[3] = sb.i0;
-  } else {
-    head[3] = q_ssc;
+  {
+    int kind = 0; PolyRes b; b.p = 0; b.i0 = 0; b.len = 0;
+    if (tn[0] >= 20 && rs[0].len > 0) { b = rs[0]; kind = 1; }
+    if (tn[1] >= 20 && rs[1].len > 0 && (kind == 0 || rs[1].p > b.p)) { b = rs[1]; kind = 2; }
+    if (kind) {
+      int gap = q_ssc - b.i0 - b.len;
+      if (!(0 <= gap && gap < q_ssc)) { dev_fail(A.err, DEVERR_POLY_RANGE, i); return; }
+      flags |= kind << 8;
+      head[1] = b.len; head[2] = gap; head[3] = b.i0;
+    }
   }
-  // end clip: L-q_esc bases; '+': seq[q_esc+t]; '-': seq[L-1-q_esc-t]  (:422-431)
-  PolyBest eb; eb.kind = 0; eb.p = 0; eb.i0 = 0; eb.len = 0;
-  poly_scan(minus ? pt : pa, minus ? L - 1 - q_esc : q_esc, minus ? -1 : 1, L - q_esc, 1, eb);
-  poly_scan(minus ? pa : pt, minus ? L - 1 - q_esc : q_esc, minus ? -1 : 1, L - q_esc, 2, eb);
-  if (eb.kind) {
-    int esc = L - q_esc - eb.i0;
-    if (!(eb.i0 >= 0 && eb.i0 < L - q_esc && esc > 0)) { dev_fail(A.err, DEVERR_POLY_RANGE, i); return; }
-    flags |= eb.kind << 16;
-    head[4] = eb.len; head[5] = eb.i0; head[6] = esc;
-  } else {
-    head[6] = L - q_esc;
+  {
+    int kind = 0; PolyRes b; b.p = 0; b.i0 = 0; b.len = 0;
+    if (tn[2] >= 20 && rs[2].len > 0) { b = rs[2]; kind = 1; }
+    if (tn[3] >= 20 && rs[3].len > 0 && (kind == 0 || rs[3].p > b.p)) { b = rs[3]; kind = 2; }
+    if (kind) {
+      int esc = L - q_esc - b.i0;
+      if (!(b.i0 >= 0 && b.i0 < L - q_esc && esc > 0)) { dev_fail(A.err, DEVERR_POLY_RANGE, i); return; }
+      flags |= kind << 16;
+      head[4] = b.len; head[5] = b.i0; head[6] = esc;
+    } else {
+      head[6] = L - q_esc;
+    }
   }
   head[0] = flags;
-  // unaligned gaps between consecutive 1-runs (:455-471)
-  int* rec = A.gap_rec + (i64)A.read_gap_off[i] * 3;
-  for (int k = ra; k + 1 < rb; ++k) {
-    int l1 = A.runs[k].y, f2 = A.runs[k + 1].x;
-    int qa, sa, qb, sb2;
-    if (!interval_end(A, i0, i1, fpos[l1 + 1], qa, sa)) { dev_fail(A.err, DEVERR_THREAD_CIGAR, i); return; }
-    if (!interval_start(A, i0, i1, fpos[f2], qb, sb2)) { dev_fail(A.err, DEVERR_THREAD_CIGAR, i); return; }
-    if (!(0 < qa && qa <= qb && qb < L)) { dev_fail(A.err, DEVERR_GAP_RANGE, i); return; }
-    int size = max(0, qb - qa + sa + sb2);
-    if (!(size < L)) { dev_fail(A.err, DEVERR_GAP_RANGE, i); return; }
-    rec[0] = l1; rec[1] = f2; rec[2] = size;
-    rec += 3;
-  }
 }

@@ -74,10 +74,25 @@ __global__ void __launch_bounds__(SIG_THREADS) k_signal(const SigWork* __restric
 // for jj=-lw..-1: acc = acc + (y[l+jj] + y[l-jj]) * w[c+jj], each op rounded separately (no FMA).
 // Reflect extension 'd c b a | a b c d | d c b a', valid when the island is shorter than lw.
 // ---------------------------------------------------------------------------------------------
-#define TILE_SAMPLES 2048
-#define GAUSS_THREADS 256
+#define TILE_SAMPLES 1024
+#define GAUSS_THREADS 128
+#define GAUSS_OPT 8  // consecutive outputs per thread (register sliding window)
+#define GAUSS_DB 4   // tap distances per register block
 
 struct TileWork { int island; int lo; };  // lo = island-local first sample of the tile
+
+// Taps are evaluated outermost pair first, like scipy.  The radius is padded to a multiple of
+// GAUSS_DB with zero weights: those pairs come first and add (a+b)*0 = +0 to a non-negative
+// accumulator, which leaves every bit unchanged.  Thread t owns outputs 8t..8t+7; for a block of 4
+// distances it needs 11 + 11 consecutive inputs, so a tap pair costs ~0.7 shared-memory loads instead
+// of 3.  The tile is stored with a skew of one double per 8 so that the stride-8 accesses of a warp
+// are bank-conflict free.
+__host__ __device__ __forceinline__ int gauss_pad_radius(int lw) { return (lw + GAUSS_DB - 1) / GAUSS_DB * GAUSS_DB; }
+__host__ __device__ __forceinline__ int gauss_skew(int q) { return q + (q >> 3); }
+__host__ __device__ inline size_t gauss_smem_bytes(int lw) {
+  int lwp = gauss_pad_radius(lw);
+  return (size_t)(lwp + 1 + gauss_skew(TILE_SAMPLES + 2 * lwp) + 2) * 8;
+}
 
 __global__ void __launch_bounds__(GAUSS_THREADS) k_gauss(const TileWork* __restrict__ tiles,
                                                         const int* __restrict__ island_sample_off,
@@ -85,28 +100,60 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_gauss(const TileWork* __restr
                                                         const double* __restrict__ gw, int lw,
                                                         double* __restrict__ y) {
   extern __shared__ double gsm[];
-  double* wv = gsm;                  // 2*lw+1 (only [0..lw] used)
-  double* ext = gsm + (2 * lw + 1);  // TILE_SAMPLES + 2*lw
+  const int lwp = gauss_pad_radius(lw);
+  double* wd = gsm;              // wd[d] = weight of the pair at distance d (0 for the padding)
+  double* ext = gsm + lwp + 1;   // skewed tile + halo
   const TileWork tw = tiles[blockIdx.x];
   const int f0 = island_sample_off[tw.island];
   const int n = island_sample_off[tw.island + 1] - f0;
   const int cnt = min(TILE_SAMPLES, n - tw.lo);
-  for (int i = threadIdx.x; i < 2 * lw + 1; i += GAUSS_THREADS) wv[i] = gw[i];
-  const int n2 = 2 * n;
-  for (int s = threadIdx.x; s < cnt + 2 * lw; s += GAUSS_THREADS) {
-    int idx = tw.lo - lw + s;
-    int j = idx % n2;
-    if (j < 0) j += n2;
-    if (j >= n) j = n2 - 1 - j;
-    ext[s] = (double)y_raw[f0 + j];
+  for (int d = threadIdx.x; d <= lwp; d += GAUSS_THREADS) wd[d] = (d <= lw) ? gw[lw - d] : 0.0;
+  const int span = cnt + 2 * lwp;
+  const int first = tw.lo - lwp;
+  if (first >= 0 && first + span <= n) {  // interior tile: no reflection
+    const int* src = y_raw + f0 + first;
+    for (int s = threadIdx.x; s < span; s += GAUSS_THREADS) ext[gauss_skew(s)] = (double)src[s];
+  } else {
+    const int n2 = 2 * n;
+    for (int s = threadIdx.x; s < span; s += GAUSS_THREADS) {
+      int j = (first + s) % n2;
+      if (j < 0) j += n2;
+      if (j >= n) j = n2 - 1 - j;
+      ext[gauss_skew(s)] = (double)y_raw[f0 + j];
+    }
   }
   __syncthreads();
-  for (int x = threadIdx.x; x < cnt; x += GAUSS_THREADS) {
-    const double* c = ext + x + lw;
-    double acc = __dmul_rn(c[0], wv[lw]);
-    for (int jj = -lw; jj < 0; ++jj)
-      acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(c[jj], c[-jj]), wv[lw + jj]));
-    y[f0 + tw.lo + x] = acc;
+  const int x0 = threadIdx.x * GAUSS_OPT;
+  if (x0 >= cnt) return;
+  // logical index of output i's centre: lwp + x0 + i ; all offsets below are warp-uniform + 8*t
+  auto at = [&](int off) -> double { return ext[x0 + threadIdx.x + off + (off >> 3)]; };  // skew(8t+off) = 9t+off+(off>>3)
+  double acc[GAUSS_OPT];
+  const double w0 = wd[0];
+#pragma unroll
+  for (int i = 0; i < GAUSS_OPT; ++i) acc[i] = __dmul_rn(at(lwp + i), w0);
+  for (int d0 = lwp; d0 >= GAUSS_DB; d0 -= GAUSS_DB) {
+    double bl[GAUSS_OPT + GAUSS_DB - 1], br[GAUSS_OPT + GAUSS_DB - 1];
+#pragma unroll
+    for (int m = 0; m < GAUSS_OPT + GAUSS_DB - 1; ++m) {
+      bl[m] = at(lwp - d0 + m);                   // input  x0 + m - d0
+      br[m] = at(lwp + d0 - (GAUSS_DB - 1) + m);  // input  x0 + m + d0 - (DB-1)
+    }
+#pragma unroll
+    for (int sft = 0; sft < GAUSS_DB; ++sft) {
+      const double w = wd[d0 - sft];
+#pragma unroll
+      for (int i = 0; i < GAUSS_OPT; ++i)
+        acc[i] = __dadd_rn(acc[i], __dmul_rn(__dadd_rn(bl[i + sft], br[i - sft + GAUSS_DB - 1]), w));
+    }
+  }
+  double* dst = y + f0 + tw.lo + x0;
+  if (x0 + GAUSS_OPT <= cnt && ((((size_t)dst) & 15) == 0)) {
+#pragma unroll
+    for (int i = 0; i < GAUSS_OPT; i += 2) *reinterpret_cast<double2*>(dst + i) = make_double2(acc[i], acc[i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < GAUSS_OPT; ++i)
+      if (x0 + i < cnt) dst[i] = acc[i];
   }
 }
 
@@ -158,23 +205,31 @@ __global__ void k_cand_meta(const int* __restrict__ cand_flat, int n_cand, const
 // ---------------------------------------------------------------------------------------------
 #define THR_THREADS 256
 
-__device__ double pw_leaf(const double* a, int n) {
+// SQ: sum of (a[i]-mean)^2 instead of a[i] (numpy evaluates x = a - mean, then x*x, then the same tree)
+template <bool SQ>
+__device__ __forceinline__ double pw_term(double v, double mean) {
+  if (!SQ) return v;
+  double d = __dsub_rn(v, mean);
+  return __dmul_rn(d, d);
+}
+template <bool SQ>
+__device__ double pw_leaf(const double* a, int n, double mean) {
   if (n < 8) {
     double res = 0.0;
-    for (int i = 0; i < n; ++i) res = __dadd_rn(res, a[i]);
+    for (int i = 0; i < n; ++i) res = __dadd_rn(res, pw_term<SQ>(a[i], mean));
     return res;
   }
   double r[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) r[k] = a[k];
+  for (int k = 0; k < 8; ++k) r[k] = pw_term<SQ>(a[k], mean);
   int i = 8;
   for (; i < n - (n % 8); i += 8) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], a[i + k]);
+    for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], pw_term<SQ>(a[i + k], mean));
   }
   double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
                          __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-  for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+  for (; i < n; ++i) res = __dadd_rn(res, pw_term<SQ>(a[i], mean));
   return res;
 }
 
@@ -240,15 +295,24 @@ __global__ void __launch_bounds__(THR_THREADS) k_threshold(const int* __restrict
   const int t = blockIdx.x;
   const int s0 = island_sample_off[tint_island_off[t]];
   const int s1 = island_sample_off[tint_island_off[t + 1]];
-  // ordered compaction of positives into vbuf[s0 ...]
+  // ordered compaction of positives into vbuf[s0 ...]: 8 consecutive samples per thread, one block
+  // scan per 2048 samples
   int base = 0;
-  for (int off = s0; off < s1; off += THR_THREADS) {
-    int i = off + threadIdx.x;
-    double v = (i < s1) ? y[i] : 0.0;
-    int p = (i < s1 && v > 0.0) ? 1 : 0;
+  for (int off = s0; off < s1; off += THR_THREADS * 8) {
+    const int i0 = off + threadIdx.x * 8;
+    double v[8];
+    int p = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k] = (i0 + k < s1) ? y[i0 + k] : 0.0;
+      p += (v[k] > 0.0) ? 1 : 0;
+    }
     int tot;
     int ex = block_exclusive_scan<int>(p, &tot, sm_scan);
-    if (p) vbuf[s0 + base + ex] = v;
+    double* dst = vbuf + s0 + base + ex;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (v[k] > 0.0) *dst++ = v[k];
     base += tot;
   }
   const int n = base;
@@ -266,17 +330,12 @@ __global__ void __launch_bounds__(THR_THREADS) k_threshold(const int* __restrict
   if (threadIdx.x == 0) sm_nl = pw_leaves(n, lo, ll);
   __syncthreads();
   const int nl = sm_nl;
-  for (int k = threadIdx.x; k < nl; k += THR_THREADS) ls[k] = pw_leaf(v + lo[k], ll[k]);
+  for (int k = threadIdx.x; k < nl; k += THR_THREADS) ls[k] = pw_leaf<false>(v + lo[k], ll[k], 0.0);
   __syncthreads();
   if (threadIdx.x == 0) sm_mean = __ddiv_rn(pw_combine(n, ls), (double)n);
   __syncthreads();
   const double mean = sm_mean;
-  for (int i = threadIdx.x; i < n; i += THR_THREADS) {
-    double d = __dsub_rn(v[i], mean);
-    v[i] = __dmul_rn(d, d);
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < nl; k += THR_THREADS) ls[k] = pw_leaf(v + lo[k], ll[k]);
+  for (int k = threadIdx.x; k < nl; k += THR_THREADS) ls[k] = pw_leaf<true>(v + lo[k], ll[k], mean);
   __syncthreads();
   if (threadIdx.x == 0) {
     double var = __ddiv_rn(pw_combine(n, ls), (double)n);
