@@ -64,7 +64,7 @@ struct frs_context {
   frs_result_sizes sizes;
   i64 n_cand = 0, n_fixed = 0, n_sub = 0, cov_elems = 0, tab_elems = 0;
   // options (frs_set_option)
-  int opt_slab_words = 64, opt_keep_tables = 0;
+  int opt_slab_words = 64, opt_keep_tables = 0, opt_poly_long_class = POLY_LONG_CLASS;
   // timing
   Stage stages[FRS_MAX_STAGES];
   int n_stages = 0, cur_stage = -1, launch_count = 0;
@@ -276,6 +276,10 @@ int frs_set_option(frs_context* c, int key, long long value) {
       return 0;
     case FRS_OPT_KEEP_DP_TABLES:
       c->opt_keep_tables = value != 0;
+      return 0;
+    case FRS_OPT_POLY_LONG_CLASS:
+      if (value < 1 || value >= POLY_CLASSES) return fail(c, FRS_ERR_ARG, "frs_set_option: poly class out of range");
+      c->opt_poly_long_class = (int)value;
       return 0;
     default:
       return fail(c, FRS_ERR_ARG, "frs_set_option: unknown key %d", key);
@@ -758,6 +762,7 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
     ENS(b_poly_cls, (2 * POLY_CLASSES + 1) * 4);
     G.task_n = c->b_task_n.as<int>(); G.cls_count = c->b_poly_cls.as<int>();
     G.task_order = c->b_task_order.as<int>(); G.task_res = c->b_task_res.as<PolyRes>();
+    G.long_class = c->opt_poly_long_class;
     if (N > 0) {
       CK(cudaMemsetAsync(c->b_poly_cls.p, 0, (2 * POLY_CLASSES + 1) * 4, st));
       k_gap_prep<<<cdiv(N, 128), 128, 0, st>>>(G); LAUNCHED();
@@ -765,7 +770,13 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
       stage_begin(c, "poly");
       k_poly_bases<<<1, 32, 0, st>>>(G.cls_count); LAUNCHED();
       k_poly_scatter<<<cdiv((i64)N * 4, 256), 256, 0, st>>>(N * 4, G.task_n, G.cls_count, G.task_order); LAUNCHED();
+      // long clips (one warp each) run beside the short ones (one thread each)
+      CK(cudaEventRecord(c->ev_fork, st));
+      CK(cudaStreamWaitEvent(c->side[0], c->ev_fork, 0));
+      k_poly_long<<<148 * 4, 128, 0, c->side[0]>>>(G); LAUNCHED();
+      CK(cudaEventRecord(c->ev_join[0], c->side[0]));
       k_poly_scan<<<cdiv((i64)N * 4, 128), 128, 0, st>>>(G); LAUNCHED();
+      CK(cudaStreamWaitEvent(st, c->ev_join[0], 0));
       k_gap_finish<<<cdiv(N, 128), 128, 0, st>>>(G); LAUNCHED();
     }
   }

@@ -276,6 +276,8 @@ __global__ void k_gap_count(int n_reads, const int* __restrict__ read_rep, const
 // class (4 classes per octave, longest first), which keeps the lanes of a warp in step.
 // ---------------------------------------------------------------------------------------------
 #define POLY_CLASSES 96
+#define POLY_LONG_CLASS 40  // poly_class(1024): longer clips are scanned by a whole warp (k_poly_long)
+#define POLY_C 64            // bases per lane and window in k_poly_long
 struct PolyRes { double p; int i0; int len; };  // len == 0: no qualifying run
 
 __device__ __forceinline__ int poly_class_dev(int n) {
@@ -299,6 +301,7 @@ struct GapArgs {
   int* cls_count;     // [POLY_CLASSES] (+ [POLY_CLASSES] cursors, + 1 total) zeroed before k_gap_prep
   int* task_order;    // [4N] slots, longest class first
   PolyRes* task_res;  // [4N]
+  int long_class;     // tasks of classes >= long_class go to k_poly_long (default POLY_LONG_CLASS)
 };
 
 // forward_thread_cigar (:289-304): every op length, insertions included, is clipped by the remaining
@@ -436,9 +439,10 @@ __global__ void k_poly_scatter(int n_slots, const int* __restrict__ task_n, int*
   order[cls_count[c] + base + __popc(peers & ((1u << lane) - 1u))] = s;
 }
 
-// K11b: one thread per scan task
+// K11b: one thread per scan task (clips shorter than 1024 bases)
 __global__ void __launch_bounds__(128) k_poly_scan(GapArgs A) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  // tasks of the long classes (front of the order) belong to k_poly_long
+  const int e = A.cls_count[A.long_class - 1] + blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= A.cls_count[2 * POLY_CLASSES]) return;
   const int slot = A.task_order[e];
   const int i = slot >> 2, which = slot & 3;
@@ -489,6 +493,127 @@ __global__ void __launch_bounds__(128) k_poly_scan(GapArgs A) {
     }
   }
   A.task_res[slot] = best;
+}
+
+// K11b': one WARP per long scan task (n >= 1024): the serial recurrence is cut into 64-base chunks, one
+// per lane.  A chunk acts on the incoming score as f(x) = max(x + a, b) (a = sum of its deltas, b = its
+// final score after the last reset); these maps compose associatively, so a warp scan gives every lane
+// its exact incoming score.  Each lane then rescans its chunk with absolute scores and reports: the
+// piece of a run continuing from the left (its maximum, last argmax, whether it closes), the best run
+// that lies inside the chunk, and the run still open at its right end.  The warp merges the 32 reports
+// in position order, which reproduces the serial scan exactly (first maximum of p, last index of a
+// run's maximum).  ~1 instruction per base per warp instead of ~10 per base on one thread.
+
+__device__ __forceinline__ unsigned long long poly_fetch64(const u32* __restrict__ pl, int nwords, int idx0, int step,
+                                                           int cnt) {
+  // bit k (k < cnt) of the result = plane bit at read index idx0 + k*step
+  int j0 = step > 0 ? idx0 : idx0 - 63;  // lowest index of the ascending 64-bit window
+  int shl = 0;
+  if (j0 < 0) { shl = -j0; j0 = 0; }
+  const int wq = j0 >> 5, sh = j0 & 31;
+  const u32 w0 = wq < nwords ? pl[wq] : 0u;
+  const u32 w1 = wq + 1 < nwords ? pl[wq + 1] : 0u;
+  const u32 w2 = (sh && wq + 2 < nwords) ? pl[wq + 2] : 0u;
+  unsigned long long asc = ((((unsigned long long)w1) << 32) | w0) >> sh;
+  if (sh) asc |= ((unsigned long long)w2) << (64 - sh);
+  asc <<= shl;
+  unsigned long long x = step > 0 ? asc : __brevll(asc);
+  if (cnt < 64) x &= ((1ull << cnt) - 1ull);
+  return x;
+}
+
+__device__ __forceinline__ void poly_offer(PolyRes& best, int i0, int pk, int pk_t) {
+  const int len = pk_t + 1 - i0;
+  if (len >= 20) {
+    const double p = __ddiv_rn((double)((pk + 2 * len) / 3), (double)len);
+    if (p >= 0.85 && (best.len == 0 || p > best.p)) { best.p = p; best.i0 = i0; best.len = len; }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_poly_long(GapArgs A) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_long = A.cls_count[A.long_class - 1];
+  for (int e = gw; e < n_long; e += nwarps) {
+    const int slot = A.task_order[e];
+    const int i = slot >> 2, which = slot & 3;
+    const int n = A.task_n[slot];
+    const int L = A.read_len[i];
+    const bool minus = A.read_strand[i] != 0;
+    const bool want_a = (which & 1) == 0;
+    const u32* pl = ((want_a != minus) ? A.seq_a : A.seq_t) + A.read_seq_off[i];
+    const int nwords = (L + 31) >> 5;
+    const int step = minus ? -1 : 1;
+    int idx_start;
+    if (which < 2) idx_start = minus ? L - 1 : 0;
+    else { const int q_esc = L - n; idx_start = minus ? L - 1 - q_esc : q_esc; }
+    bool open = false;
+    int r_i0 = 0, r_best = 0, r_best_t = 0, sc_carry = 0;
+    PolyRes best; best.p = 0.0; best.i0 = 0; best.len = 0;
+    for (int W0 = 0; W0 < n; W0 += 32 * POLY_C) {
+      const int t0 = W0 + lane * POLY_C;
+      const int cnt = max(0, min(POLY_C, n - t0));
+      const unsigned long long bits = cnt > 0 ? poly_fetch64(pl, nwords, idx_start + t0 * step, step, cnt) : 0ull;
+      // pass 1: the chunk as a map x -> max(x + fa, fb)
+      int fa = 0, fb = 0;
+      {
+        int s = 0, mn = 0x3fffffff;
+        for (int k = 0; k < cnt; ++k) {
+          s += ((bits >> k) & 1ull) ? 1 : -2;
+          mn = min(mn, s);
+        }
+        if (cnt > 0) { fa = s; fb = s - mn; }
+      }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {  // inclusive scan of map composition (earlier chunk applied first)
+        const int pa = __shfl_up_sync(FULL, fa, o), pb = __shfl_up_sync(FULL, fb, o);
+        if (lane >= o) { fb = max(pb + fa, fb); fa = pa + fa; }
+      }
+      int ea = __shfl_up_sync(FULL, fa, 1), eb = __shfl_up_sync(FULL, fb, 1);
+      const int sc_in = lane == 0 ? sc_carry : max(sc_carry + ea, eb);
+      const int sc_out_w = max(sc_carry + __shfl_sync(FULL, fa, 31), __shfl_sync(FULL, fb, 31));
+      // pass 2: rescan with absolute scores
+      int head_max = 0, head_max_t = 0, head_closed = 0;
+      PolyRes loc; loc.p = 0.0; loc.i0 = 0; loc.len = 0;
+      int cur_i0 = -1, cur_best = 0, cur_best_t = 0, sc = sc_in;
+      for (int k = 0; k < cnt; ++k) {
+        const int t = t0 + k;
+        const int nsc = max(0, sc + (((bits >> k) & 1ull) ? 1 : -2));
+        if (nsc > 0) {
+          if (sc == 0) { cur_i0 = t; cur_best = 0; }
+          if (nsc >= cur_best) { cur_best = nsc; cur_best_t = t; }
+        } else if (sc > 0) {
+          if (cur_i0 < 0) { head_closed = 1; head_max = cur_best; head_max_t = cur_best_t; }
+          else poly_offer(loc, cur_i0, cur_best, cur_best_t);
+        }
+        sc = nsc;
+      }
+      const int tail_open = (cnt > 0 && sc > 0) ? 1 : 0;
+      const int tail_i0 = cur_i0;
+      if (tail_open && cur_i0 < 0) { head_max = cur_best; head_max_t = cur_best_t; }  // run spans the whole chunk
+      // merge the 32 reports in position order (every lane computes the same state)
+      for (int l = 0; l < 32; ++l) {
+        const int c_l = __shfl_sync(FULL, cnt, l);
+        const int hm = __shfl_sync(FULL, head_max, l), hmt = __shfl_sync(FULL, head_max_t, l);
+        const int hc = __shfl_sync(FULL, head_closed, l);
+        const double lp = __shfl_sync(FULL, loc.p, l);
+        const int li0 = __shfl_sync(FULL, loc.i0, l), ll = __shfl_sync(FULL, loc.len, l);
+        const int to = __shfl_sync(FULL, tail_open, l), ti0 = __shfl_sync(FULL, tail_i0, l);
+        const int tm = __shfl_sync(FULL, cur_best, l), tmt = __shfl_sync(FULL, cur_best_t, l);
+        if (c_l == 0) continue;
+        if (open) {
+          if (hm >= r_best) { r_best = hm; r_best_t = hmt; }
+          if (hc) { poly_offer(best, r_i0, r_best, r_best_t); open = false; }
+        }
+        if (ll > 0 && (best.len == 0 || lp > best.p)) { best.p = lp; best.i0 = li0; best.len = ll; }
+        if (to && ti0 >= 0) { open = true; r_i0 = ti0; r_best = tm; r_best_t = tmt; }
+      }
+      sc_carry = sc_out_w;
+    }
+    if (open) poly_offer(best, r_i0, r_best, r_best_t);
+    if (lane == 0) A.task_res[slot] = best;
+  }
 }
 
 // K11c: per read, pick the poly candidates (A offered before T, first maximum of p wins, :392-408)

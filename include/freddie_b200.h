@@ -174,6 +174,8 @@ enum {
   FRS_OPT_SLAB_WORDS = 1,     /* read reps per DP CTA, in words of 32 (default 64): tints with more reps are
                                  processed by several CTAs per subproblem (multi-CTA mode) */
   FRS_OPT_KEEP_DP_TABLES = 2, /* also store the on-chip ins/out tables of small tints for FRS_TAP_DP_TABLES */
+  FRS_OPT_POLY_LONG_CLASS = 3, /* length class (4 per octave: 40 = 1024 bases, default) from which a poly-A/T
+                                 clip scan is done by a whole warp instead of one thread; 1 = every scan */
 };
 int frs_set_option(frs_context* ctx, int key, long long value);
 

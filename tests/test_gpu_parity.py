@@ -169,6 +169,27 @@ def test_multi_cta_mode_equals_one_cta_mode(name, golden_set, eng):
         eng.set_option(_lib.OPT_SLAB_WORDS, 64)
 
 
+@pytest.mark.parametrize("name", ["cfg1", "degenerate", "cfg2_small", "cfg5_mini"])
+def test_warp_poly_scan_equals_thread_scan(name, golden_set, eng):
+    """find_longest_poly as a chunked warp scan (used for clips >= 1024 bases) must give the results of
+    the serial per-thread scan on every clip: force every scan task through it."""
+    from freddie_b200 import _lib
+    from freddie_b200.pack import pack_tints
+    tints, flags, _ = golden_set(name)
+    _, gprm = _params(flags)
+    batch = pack_tints(tints)
+    try:
+        eng.set_option(_lib.OPT_POLY_LONG_CLASS, 95)   # every scan by a single thread
+        want = eng.segment_batch(batch, gprm)
+        eng.set_option(_lib.OPT_POLY_LONG_CLASS, 1)    # every scan by a warp
+        got = eng.segment_batch(batch, gprm)
+    finally:
+        eng.set_option(_lib.OPT_POLY_LONG_CLASS, 40)
+    assert (want.arrays["read_head"].reshape(-1, 8)[:, 0] >> 8).any()  # the set does contain poly-A/T hits
+    for k in want.arrays:
+        assert np.array_equal(want.arrays[k], got.arrays[k]), (name, k)
+
+
 def test_in_process_seam_has_reference_signature(golden_set):
     """segment(tint, sigma, smoothed_threshold, tp, vf, mps, lo, ignore_ends) mutates the tint like the
     reference (freddie_segment.py:738-844)."""
