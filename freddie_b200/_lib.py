@@ -17,7 +17,8 @@ FRS_MAX_STAGES = 32
 # taps (frs_get_intermediate)
 TAP_Y_RAW, TAP_Y, TAP_THR, TAP_CAND, TAP_FIXED, TAP_DP_FINAL, TAP_SUB_START, TAP_SUB_N = 1, 2, 3, 4, 5, 6, 7, 8
 TAP_COVERAGE, TAP_DP_TABLES, TAP_COV_OFF, TAP_SUB_TAB_OFF = 9, 10, 12, 13
-OPT_SLAB_WORDS, OPT_KEEP_DP_TABLES, OPT_POLY_LONG_CLASS = 1, 2, 3
+OPT_SLAB_WORDS, OPT_KEEP_DP_TABLES, OPT_POLY_LONG_CLASS, OPT_LAZY_SEQ = 1, 2, 3, 4
+STAT_NAMES = ["h2d_upload", "h2d_run", "d2h_run", "clip_words", "seq_words"]
 
 _p = C.c_void_p
 
@@ -99,6 +100,8 @@ def load():
     lib.frs_get_timings.argtypes = [_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_int)]
     lib.frs_last_launch_count.argtypes = [_p]
     lib.frs_set_option.argtypes = [_p, C.c_int, C.c_longlong]
+    lib.frs_get_stats.argtypes = [_p, C.POINTER(C.c_longlong), C.c_int]
+    lib.frs_get_stats.restype = C.c_int
     for fn in ("frs_create", "frs_upload", "frs_run", "frs_download", "frs_segment_batch", "frs_get_intermediate",
                "frs_set_profiling", "frs_get_timings", "frs_last_launch_count", "frs_set_option"):
         getattr(lib, fn).restype = C.c_int
@@ -122,6 +125,6 @@ def load():
 EXPORTED = [
     "frs_abi_version", "frs_device_count", "frs_create", "frs_destroy", "frs_last_error", "frs_stream",
     "frs_upload", "frs_run", "frs_download", "frs_segment_batch", "frs_get_intermediate", "frs_set_profiling",
-    "frs_get_timings", "frs_last_launch_count", "frs_set_option", "frs_parse_tints", "frs_parsed_batch", "frs_parsed_free",
+    "frs_get_timings", "frs_last_launch_count", "frs_set_option", "frs_get_stats", "frs_parse_tints", "frs_parsed_batch", "frs_parsed_free",
     "frs_format_tints",
 ]

@@ -58,13 +58,23 @@ struct frs_context {
       b_sub_n, b_sub_tint, b_sub_info, b_sub_slabs, b_sz_tab, b_sub_tab_off, b_plan, b_work, b_split_list, b_cursor,
       b_cov_sz, b_tint_cov_off, b_P, b_tab, b_dpfinal, b_pf_list, b_gbuf, b_pstate, b_final_flat,
       b_final_pos, b_final_island, b_tint_final_off, b_dig_sz, b_tint_digit_off, b_seg_ty, b_seg_tn, b_digits,
-      b_run_cnt, b_run_off, b_runs, b_gap_cnt, b_task_n, b_task_order, b_task_res, b_poly_cls, b_read_gap_off, b_read_head, b_gap_rec, b_counters, b_stats, b_err;
+      b_run_cnt, b_run_off, b_runs, b_gap_cnt, b_clip_n, b_clip_off, b_task_order, b_task_res, b_poly_cls, b_read_gap_off, b_read_head, b_gap_rec, b_counters, b_stats, b_err;
   i64* h_pin = nullptr;  // pinned scratch for small D2H reads
   // results of the last run
   frs_result_sizes sizes;
   i64 n_cand = 0, n_fixed = 0, n_sub = 0, cov_elems = 0, tab_elems = 0;
   // options (frs_set_option)
-  int opt_slab_words = 64, opt_keep_tables = 0, opt_poly_long_class = POLY_LONG_CLASS;
+  int opt_slab_words = 64, opt_keep_tables = 0, opt_poly_long_class = POLY_LONG_CLASS, opt_lazy_seq = 1;
+  // lazy sequence mode: host copies of the small per-read tables, pinned staging for the clip words
+  bool seq_resident = false;
+  std::vector<int> h_read_len;
+  std::vector<u8> h_read_strand;
+  std::vector<i64> h_read_seq_off;
+  const u32* h_seq_a = nullptr;  // caller's planes (valid until frs_run returns, see the header)
+  const u32* h_seq_t = nullptr;
+  void* h_stage = nullptr;       // pinned: clip_n (D2H), clip_off + gathered words (H2D)
+  size_t h_stage_cap = 0;
+  i64 st_h2d_upload = 0, st_h2d_run = 0, st_d2h_run = 0, st_poly_tasks = 0, st_clip_words = 0;
   // timing
   Stage stages[FRS_MAX_STAGES];
   int n_stages = 0, cur_stage = -1, launch_count = 0;
@@ -189,6 +199,79 @@ static int check_dev_err(frs_context* c) {
   return 0;
 }
 
+// Lazy sequence mode: after k_gap_prep the clip lengths are known.  Bring them to the host, gather the
+// plane words each clip needs from the caller's (host) bit-planes into pinned staging, and send only
+// those to the device -- a few per cent of the reads' bases instead of all of them.
+static int fetch_clip_words(frs_context* c, int N) {
+  cudaStream_t st = c->stream;
+  const size_t n_clip = (size_t)N * 2;
+  // staging layout: [clip_n: 2N int][clip_off: 2N i64][words A][words T]; worst case = whole planes
+  const size_t head = n_clip * 4 + n_clip * 8 + 64;
+  if (c->h_stage_cap < head) {
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr;
+    c->h_stage_cap = 0;
+    size_t want = head + (64u << 20);
+    CK(cudaMallocHost(&c->h_stage, want));
+    c->h_stage_cap = want;
+  }
+  int* h_n = (int*)c->h_stage;
+  CK(cudaMemcpyAsync(h_n, c->b_clip_n.p, n_clip * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  c->st_d2h_run += (i64)n_clip * 4;
+  // word counts -> offsets (serial scan: 2N adds), then a parallel gather
+  std::vector<i64> off(n_clip + 1);
+  i64 total = 0;
+  for (size_t k = 0; k < n_clip; ++k) {
+    off[k] = total;
+    const int n = h_n[k];
+    if (n >= 20) {
+      const int i = (int)(k >> 1);
+      total += clip_geometry(c->h_read_len[i], n, (k & 1) == 0, c->h_read_strand[i] != 0).n_words;
+    }
+  }
+  off[n_clip] = total;
+  const size_t need = head + (size_t)total * 8 + 64;
+  if (c->h_stage_cap < need) {  // grow (contents are re-derived below)
+    std::vector<int> keep(h_n, h_n + n_clip);
+    CK(cudaFreeHost(c->h_stage));
+    c->h_stage = nullptr;
+    c->h_stage_cap = 0;
+    size_t want = need + need / 4;
+    CK(cudaMallocHost(&c->h_stage, want));
+    c->h_stage_cap = want;
+    h_n = (int*)c->h_stage;
+    memcpy(h_n, keep.data(), n_clip * 4);
+  }
+  i64* h_off = (i64*)((char*)c->h_stage + ((n_clip * 4 + 15) & ~(size_t)15));
+  u32* h_wa = (u32*)((char*)h_off + ((n_clip * 8 + 15) & ~(size_t)15));
+  u32* h_wt = h_wa + total;
+  const u32* pa = c->h_seq_a;
+  const u32* pt = c->h_seq_t;
+#pragma omp parallel for schedule(static, 4096)
+  for (long long k = 0; k < (long long)n_clip; ++k) {
+    h_off[k] = off[k];
+    const int n = h_n[k];
+    if (n < 20) continue;
+    const int i = (int)(k >> 1);
+    const ClipGeo g = clip_geometry(c->h_read_len[i], n, (k & 1) == 0, c->h_read_strand[i] != 0);
+    const i64 src = c->h_read_seq_off[i] + g.w_first;
+    memcpy(h_wa + off[k], pa + src, (size_t)g.n_words * 4);
+    memcpy(h_wt + off[k], pt + src, (size_t)g.n_words * 4);
+  }
+  int r;
+  if ((r = ensure(c, c->b_seq_a, (size_t)total * 4))) return r;
+  if ((r = ensure(c, c->b_seq_t, (size_t)total * 4))) return r;
+  CK(cudaMemcpyAsync(c->b_clip_off.p, h_off, n_clip * 8, cudaMemcpyHostToDevice, st));
+  if (total > 0) {
+    CK(cudaMemcpyAsync(c->b_seq_a.p, h_wa, (size_t)total * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->b_seq_t.p, h_wt, (size_t)total * 4, cudaMemcpyHostToDevice, st));
+  }
+  c->st_h2d_run += (i64)n_clip * 8 + total * 8;
+  c->st_clip_words = total;
+  return 0;
+}
+
 // C ABI ----------------------------------------------------------------------------------------
 extern "C" {
 
@@ -248,6 +331,7 @@ void frs_destroy(frs_context* c) {
     cudaEventDestroy(c->stages[i].ev1);
   }
   if (c->h_pin) cudaFreeHost(c->h_pin);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
   for (int i = 0; i < FRS_SIDE_STREAMS; ++i) {
     if (c->side[i]) cudaStreamDestroy(c->side[i]);
     if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
@@ -267,6 +351,14 @@ int frs_set_profiling(frs_context* c, int enabled) {
 
 int frs_last_launch_count(frs_context* c) { return c ? c->launch_count : 0; }
 
+int frs_get_stats(frs_context* c, long long* out, int n) {
+  if (!c || !out) return FRS_ERR_ARG;
+  const long long v[FRS_N_STATS] = {c->st_h2d_upload, c->st_h2d_run, c->st_d2h_run, c->st_clip_words,
+                                    (long long)c->hb.n_seq_words};
+  for (int i = 0; i < n && i < FRS_N_STATS; ++i) out[i] = v[i];
+  return FRS_N_STATS;
+}
+
 int frs_set_option(frs_context* c, int key, long long value) {
   if (!c) return FRS_ERR_ARG;
   switch (key) {
@@ -276,6 +368,9 @@ int frs_set_option(frs_context* c, int key, long long value) {
       return 0;
     case FRS_OPT_KEEP_DP_TABLES:
       c->opt_keep_tables = value != 0;
+      return 0;
+    case FRS_OPT_LAZY_SEQ:
+      c->opt_lazy_seq = value != 0;
       return 0;
     case FRS_OPT_POLY_LONG_CLASS:
       if (value < 1 || value >= POLY_CLASSES) return fail(c, FRS_ERR_ARG, "frs_set_option: poly class out of range");
@@ -307,6 +402,7 @@ int frs_get_timings(frs_context* c, const char** names, float* ms, int* launches
   do {                                                                                            \
     ENS(buf, bytes);                                                                              \
     if ((bytes) > 0) CK(cudaMemcpyAsync(c->buf.p, src, (size_t)(bytes), cudaMemcpyHostToDevice, c->stream)); \
+    c->st_h2d_upload += (i64)(bytes);                                                             \
   } while (0)
 
 int frs_upload(frs_context* c, const frs_batch* b) {
@@ -369,6 +465,7 @@ int frs_upload(frs_context* c, const frs_batch* b) {
   c->n_cov_tiles = (int)cov_tiles.size();
   c->n_dig_tiles = (int)dig_tiles.size();
   // ---- copies ----
+  c->st_h2d_upload = 0;
   H2D(b_tint_island_off, b->tint_island_off, (size_t)(T + 1) * 4);
   H2D(b_tint_rep_off, b->tint_rep_off, (size_t)(T + 1) * 4);
   H2D(b_tint_read_off, b->tint_read_off, (size_t)(T + 1) * 4);
@@ -389,8 +486,19 @@ int frs_upload(frs_context* c, const frs_batch* b) {
   H2D(b_riv_qe, b->riv_qe, (size_t)b->n_read_ivs * 4);
   H2D(b_riv_cig_off, b->riv_cig_off, (size_t)(b->n_read_ivs + 1) * 4);
   H2D(b_cigar, b->cigar, (size_t)b->n_cigar_ops * 4);
-  H2D(b_seq_a, b->seq_is_a, (size_t)b->n_seq_words * 4);
-  H2D(b_seq_t, b->seq_is_t, (size_t)b->n_seq_words * 4);
+  c->seq_resident = !c->opt_lazy_seq;
+  if (c->seq_resident) {
+    H2D(b_seq_a, b->seq_is_a, (size_t)b->n_seq_words * 4);
+    H2D(b_seq_t, b->seq_is_t, (size_t)b->n_seq_words * 4);
+  } else {
+    // the poly-A/T scans only look at the clips of a read, and those are known after segmentation:
+    // frs_run fetches just the clip words from the caller's planes (k_gap_prep -> host gather -> H2D)
+    c->h_seq_a = b->seq_is_a;
+    c->h_seq_t = b->seq_is_t;
+    c->h_read_len.assign(b->read_len, b->read_len + N);
+    c->h_read_strand.assign(b->read_strand, b->read_strand + N);
+    c->h_read_seq_off.assign(b->read_seq_off, b->read_seq_off + N + 1);
+  }
   // the derived tables live in pageable vectors: stage synchronously before they go out of scope
   H2D(b_island_tint, island_tint.data(), (size_t)NI * 4);
   H2D(b_rep_tint, rep_tint.data(), (size_t)NR * 4);
@@ -756,20 +864,30 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
     G.runs = c->b_runs.as<int2>(); G.tint_final_off = c->b_tint_final_off.as<int>();
     G.final_pos = c->b_final_pos.as<int>(); G.read_gap_off = c->b_read_gap_off.as<int>();
     G.read_head = c->b_read_head.as<int>(); G.gap_rec = c->b_gap_rec.as<int>(); G.err = d_err;
-    ENS(b_task_n, (size_t)N * 16);
+    ENS(b_clip_n, (size_t)N * 8);
+    ENS(b_clip_off, (size_t)N * 16);
     ENS(b_task_order, (size_t)N * 16);
     ENS(b_task_res, (size_t)N * 4 * sizeof(PolyRes));
     ENS(b_poly_cls, (2 * POLY_CLASSES + 1) * 4);
-    G.task_n = c->b_task_n.as<int>(); G.cls_count = c->b_poly_cls.as<int>();
+    G.clip_n = c->b_clip_n.as<int>(); G.clip_off = c->b_clip_off.as<i64>(); G.seq_resident = c->seq_resident ? 1 : 0;
+    G.cls_count = c->b_poly_cls.as<int>();
     G.task_order = c->b_task_order.as<int>(); G.task_res = c->b_task_res.as<PolyRes>();
     G.long_class = c->opt_poly_long_class;
+    c->st_h2d_run = c->st_d2h_run = c->st_clip_words = 0;
     if (N > 0) {
       CK(cudaMemsetAsync(c->b_poly_cls.p, 0, (2 * POLY_CLASSES + 1) * 4, st));
       k_gap_prep<<<cdiv(N, 128), 128, 0, st>>>(G); LAUNCHED();
       if (NGAP > 0) { k_gap_sizes<<<cdiv(NGAP, 128), 128, 0, st>>>(G, (int)NGAP); LAUNCHED(); }
+      if (!c->seq_resident) {
+        stage_begin(c, "clip_fetch");
+        int r = fetch_clip_words(c, N);
+        if (r) return r;
+        G.seq_a = c->b_seq_a.as<u32>();
+        G.seq_t = c->b_seq_t.as<u32>();
+      }
       stage_begin(c, "poly");
       k_poly_bases<<<1, 32, 0, st>>>(G.cls_count); LAUNCHED();
-      k_poly_scatter<<<cdiv((i64)N * 4, 256), 256, 0, st>>>(N * 4, G.task_n, G.cls_count, G.task_order); LAUNCHED();
+      k_poly_scatter<<<cdiv((i64)N * 4, 256), 256, 0, st>>>(N * 4, G.clip_n, G.cls_count, G.task_order); LAUNCHED();
       // long clips (one warp each) run beside the short ones (one thread each)
       CK(cudaEventRecord(c->ev_fork, st));
       CK(cudaStreamWaitEvent(c->side[0], c->ev_fork, 0));

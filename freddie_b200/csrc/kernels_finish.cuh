@@ -297,7 +297,10 @@ struct GapArgs {
   const int* read_gap_off;
   int* read_head; int* gap_rec; int* err;
   // poly tasks: slot = read*4 + (0 start-A, 1 start-T, 2 end-A, 3 end-T)
-  int* task_n;        // [4N] clip length of the slot's scan, 0 = no task
+  int* clip_n;        // [2N] bases of the read's start (2i) / end (2i+1) clip, 0 = nothing to scan (< 20)
+  i64* clip_off;      // [2N] word offset of the clip's plane words inside seq_a / seq_t (see clip_geometry)
+  int seq_resident;   // 1: seq_a/seq_t hold the whole reads (clip_off written by k_gap_prep);
+                      // 0: they hold only the clip words, gathered by the host after k_gap_prep
   int* cls_count;     // [POLY_CLASSES] (+ [POLY_CLASSES] cursors, + 1 total) zeroed before k_gap_prep
   int* task_order;    // [4N] slots, longest class first
   PolyRes* task_res;  // [4N]
@@ -353,6 +356,22 @@ __device__ bool interval_end(const GapArgs& A, int i0, int i1, int p, int& q, in
   return q >= 0 && q <= A.riv_qe[k];
 }
 
+// A clip of n bases of a read of L bases covers the read's first n bases (start clip on '+', end clip
+// on '-') or its last n (start clip on '-', end clip on '+'), because '-' reads are scanned from the
+// other end (:393-401, :423-431).  Only the 32-bit plane words that overlap that range are needed:
+// first word w_first, n_words words; scan position t reads bit (idx0 + t*step) RELATIVE to w_first.
+struct ClipGeo { int w_first, n_words, idx0, step; };
+__host__ __device__ __forceinline__ ClipGeo clip_geometry(int L, int n, bool is_start, bool minus) {
+  ClipGeo g;
+  const bool at_begin = (is_start != minus);
+  g.step = minus ? -1 : 1;
+  g.w_first = at_begin ? 0 : ((L - n) >> 5);
+  g.n_words = at_begin ? ((n + 31) >> 5) : (((L + 31) >> 5) - g.w_first);
+  const int abs0 = is_start ? (minus ? L - 1 : 0) : (minus ? n - 1 : L - n);
+  g.idx0 = abs0 - (g.w_first << 5);
+  return g;
+}
+
 // K11a: per read, everything of get_unaligned_gaps_and_polyA (:370-472) except the poly scans:
 // clip bounds by CIGAR threading, unaligned gaps between consecutive 1-runs, and the scan tasks.
 // head[3] = q_ssc and head[6] = q_esc are provisional; k_gap_finish rewrites them.
@@ -364,8 +383,8 @@ __global__ void __launch_bounds__(128) k_gap_prep(GapArgs A) {
   if (i < A.n_reads) {
     int* head = A.read_head + (i64)i * 8;
     for (int k = 0; k < 8; ++k) head[k] = 0;
-    int* tn = A.task_n + (i64)i * 4;
-    tn[0] = tn[1] = tn[2] = tn[3] = 0;
+    int* cn = A.clip_n + (i64)i * 2;
+    cn[0] = cn[1] = 0;
     const int rep = A.read_rep[i];
     const int ra = A.run_off[rep], rb = A.run_off[rep + 1];
     if (ra != rb) {  // else: no '1' digit, empty gaps (:372)
@@ -383,8 +402,17 @@ __global__ void __launch_bounds__(128) k_gap_prep(GapArgs A) {
         head[3] = q_ssc;
         head[6] = q_esc;
         const int ns = q_ssc, ne = L - q_esc;
-        if (ns >= 20) { tn[0] = tn[1] = ns; atomicAdd(&sh_cnt[poly_class_dev(ns)], 2); }
-        if (ne >= 20) { tn[2] = tn[3] = ne; atomicAdd(&sh_cnt[poly_class_dev(ne)], 2); }
+        const bool minus = A.read_strand[i] != 0;
+        if (ns >= 20) {
+          cn[0] = ns;
+          atomicAdd(&sh_cnt[poly_class_dev(ns)], 2);
+          if (A.seq_resident) A.clip_off[2 * (i64)i] = A.read_seq_off[i] + clip_geometry(L, ns, true, minus).w_first;
+        }
+        if (ne >= 20) {
+          cn[1] = ne;
+          atomicAdd(&sh_cnt[poly_class_dev(ne)], 2);
+          if (A.seq_resident) A.clip_off[2 * (i64)i + 1] = A.read_seq_off[i] + clip_geometry(L, ne, false, minus).w_first;
+        }
         // unaligned gaps between consecutive 1-runs (:455-471): (l1, f2, owner); k_gap_sizes fills the size
         int* rec = A.gap_rec + (i64)A.read_gap_off[i] * 3;
         for (int k = ra; k + 1 < rb; ++k, rec += 3) { rec[0] = A.runs[k].y; rec[1] = A.runs[k + 1].x; rec[2] = i; }
@@ -423,11 +451,11 @@ __global__ void k_poly_bases(int* __restrict__ cls_count) {
   }
 }
 
-__global__ void k_poly_scatter(int n_slots, const int* __restrict__ task_n, int* __restrict__ cls_count,
+__global__ void k_poly_scatter(int n_slots, const int* __restrict__ clip_n, int* __restrict__ cls_count,
                                int* __restrict__ order) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_slots) return;
-  int n = task_n[s];
+  int n = clip_n[s >> 1];
   if (n < 20) return;
   int c = poly_class_dev(n);
   // warp-aggregate the cursor bump of lanes that share a class
@@ -446,16 +474,15 @@ __global__ void __launch_bounds__(128) k_poly_scan(GapArgs A) {
   if (e >= A.cls_count[2 * POLY_CLASSES]) return;
   const int slot = A.task_order[e];
   const int i = slot >> 2, which = slot & 3;
-  const int n = A.task_n[slot];
-  const int L = A.read_len[i];
+  const int clip = slot >> 1;
+  const int n = A.clip_n[clip];
   const bool minus = A.read_strand[i] != 0;
   const bool want_a = (which & 1) == 0;
   // '+': seq[..] == ch; '-': reversed read, complemented target base (:392-401, :422-431)
-  const u32* pl = ((want_a != minus) ? A.seq_a : A.seq_t) + A.read_seq_off[i];
-  const int step = minus ? -1 : 1;
-  int idx;
-  if (which < 2) idx = minus ? L - 1 : 0;                 // start clip: q_ssc bases
-  else { const int q_esc = L - n; idx = minus ? L - 1 - q_esc : q_esc; }  // end clip: L - q_esc bases
+  const u32* pl = ((want_a != minus) ? A.seq_a : A.seq_t) + A.clip_off[clip];
+  const ClipGeo geo = clip_geometry(A.read_len[i], n, which < 2, minus);
+  const int step = geo.step;
+  int idx = geo.idx0;
   PolyRes best; best.p = 0.0; best.i0 = 0; best.len = 0;
   int sc = 0, run_i0 = 0, run_best = 0, run_best_i = 0;
   // words are consumed in scan order; the next one is requested a whole word ahead of its use
@@ -538,16 +565,13 @@ __global__ void __launch_bounds__(128) k_poly_long(GapArgs A) {
   for (int e = gw; e < n_long; e += nwarps) {
     const int slot = A.task_order[e];
     const int i = slot >> 2, which = slot & 3;
-    const int n = A.task_n[slot];
-    const int L = A.read_len[i];
+    const int clip = slot >> 1;
+    const int n = A.clip_n[clip];
     const bool minus = A.read_strand[i] != 0;
     const bool want_a = (which & 1) == 0;
-    const u32* pl = ((want_a != minus) ? A.seq_a : A.seq_t) + A.read_seq_off[i];
-    const int nwords = (L + 31) >> 5;
-    const int step = minus ? -1 : 1;
-    int idx_start;
-    if (which < 2) idx_start = minus ? L - 1 : 0;
-    else { const int q_esc = L - n; idx_start = minus ? L - 1 - q_esc : q_esc; }
+    const u32* pl = ((want_a != minus) ? A.seq_a : A.seq_t) + A.clip_off[clip];
+    const ClipGeo geo = clip_geometry(A.read_len[i], n, which < 2, minus);
+    const int nwords = geo.n_words, step = geo.step, idx_start = geo.idx0;
     bool open = false;
     int r_i0 = 0, r_best = 0, r_best_t = 0, sc_carry = 0;
     PolyRes best; best.p = 0.0; best.i0 = 0; best.len = 0;
@@ -625,13 +649,13 @@ __global__ void k_gap_finish(GapArgs A) {
   if (!(head[0] & 1)) return;
   const int L = A.read_len[i];
   const int q_ssc = head[3], q_esc = head[6];
-  const int* tn = A.task_n + (i64)i * 4;
+  const int* cn = A.clip_n + (i64)i * 2;
   const PolyRes* rs = A.task_res + (i64)i * 4;
   int flags = 1;
   {
     int kind = 0; PolyRes b; b.p = 0; b.i0 = 0; b.len = 0;
-    if (tn[0] >= 20 && rs[0].len > 0) { b = rs[0]; kind = 1; }
-    if (tn[1] >= 20 && rs[1].len > 0 && (kind == 0 || rs[1].p > b.p)) { b = rs[1]; kind = 2; }
+    if (cn[0] >= 20 && rs[0].len > 0) { b = rs[0]; kind = 1; }
+    if (cn[0] >= 20 && rs[1].len > 0 && (kind == 0 || rs[1].p > b.p)) { b = rs[1]; kind = 2; }
     if (kind) {
       int gap = q_ssc - b.i0 - b.len;
       if (!(0 <= gap && gap < q_ssc)) { dev_fail(A.err, DEVERR_POLY_RANGE, i); return; }
@@ -641,8 +665,8 @@ __global__ void k_gap_finish(GapArgs A) {
   }
   {
     int kind = 0; PolyRes b; b.p = 0; b.i0 = 0; b.len = 0;
-    if (tn[2] >= 20 && rs[2].len > 0) { b = rs[2]; kind = 1; }
-    if (tn[3] >= 20 && rs[3].len > 0 && (kind == 0 || rs[3].p > b.p)) { b = rs[3]; kind = 2; }
+    if (cn[1] >= 20 && rs[2].len > 0) { b = rs[2]; kind = 1; }
+    if (cn[1] >= 20 && rs[3].len > 0 && (kind == 0 || rs[3].p > b.p)) { b = rs[3]; kind = 2; }
     if (kind) {
       int esc = L - q_esc - b.i0;
       if (!(b.i0 >= 0 && b.i0 < L - q_esc && esc > 0)) { dev_fail(A.err, DEVERR_POLY_RANGE, i); return; }

@@ -172,6 +172,12 @@ class Engine:
     def set_option(self, key: int, value: int):
         self._check(self.lib.frs_set_option(self.ctx, int(key), int(value)))
 
+    def stats(self) -> Dict[str, int]:
+        """Transfer statistics of the last upload / run (``frs_get_stats``)."""
+        buf = (C.c_longlong * len(_lib.STAT_NAMES))()
+        self.lib.frs_get_stats(self.ctx, buf, len(_lib.STAT_NAMES))
+        return {k: int(buf[i]) for i, k in enumerate(_lib.STAT_NAMES)}
+
     def launch_count(self) -> int:
         return int(self.lib.frs_last_launch_count(self.ctx))
 

@@ -137,7 +137,8 @@ const char* frs_last_error(const frs_context* ctx); /* ctx may be NULL: last glo
 void* frs_stream(frs_context* ctx);                 /* cudaStream_t of the context */
 
 /* ---- the hot path (replaces segment(), freddie_segment.py:738-844, for a batch of tints) ---- */
-/* H2D copy of the batch (async on the context stream; host arrays may be pinned or pageable). */
+/* H2D copy of the batch (async on the context stream; host arrays may be pinned or pageable).  With
+ * FRS_OPT_LAZY_SEQ (default) the two sequence bit-planes are not copied here, see the option. */
 int frs_upload(frs_context* ctx, const frs_batch* batch);
 /* Runs every kernel of the pipeline on the uploaded batch; may be called repeatedly. */
 int frs_run(frs_context* ctx, const frs_params* prm, frs_result_sizes* sizes);
@@ -176,8 +177,19 @@ enum {
   FRS_OPT_KEEP_DP_TABLES = 2, /* also store the on-chip ins/out tables of small tints for FRS_TAP_DP_TABLES */
   FRS_OPT_POLY_LONG_CLASS = 3, /* length class (4 per octave: 40 = 1024 bases, default) from which a poly-A/T
                                  clip scan is done by a whole warp instead of one thread; 1 = every scan */
+  FRS_OPT_LAZY_SEQ = 4,       /* 1 (default): frs_upload does NOT copy the sequence bit-planes; frs_run reads the
+                                 clip lengths back after segmentation, gathers only the plane words of the
+                                 soft-clips from the caller's seq_is_a / seq_is_t and uploads those.  The two
+                                 host arrays must then stay valid until frs_run returns.
+                                 0: frs_upload copies both planes whole (inputs fully resident in HBM). */
 };
 int frs_set_option(frs_context* ctx, int key, long long value);
+
+/* transfer statistics of the last frs_upload / frs_run; returns the number of statistics */
+#define FRS_N_STATS 5
+enum { FRS_STAT_H2D_UPLOAD = 0, FRS_STAT_H2D_RUN = 1, FRS_STAT_D2H_RUN = 2, FRS_STAT_CLIP_WORDS = 3,
+       FRS_STAT_SEQ_WORDS = 4 };
+int frs_get_stats(frs_context* ctx, long long* out, int n);
 
 /* ---- per-kernel device timing of the last frs_run (CUDA events on the context stream) ---- */
 #define FRS_MAX_STAGES 32

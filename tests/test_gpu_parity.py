@@ -190,6 +190,28 @@ def test_warp_poly_scan_equals_thread_scan(name, golden_set, eng):
         assert np.array_equal(want.arrays[k], got.arrays[k]), (name, k)
 
 
+@pytest.mark.parametrize("name", ["cfg1", "degenerate", "cfg2_small", "cfg4_mini"])
+def test_lazy_clip_upload_equals_resident_planes(name, golden_set, eng):
+    """Default mode uploads only the soft-clip words of the sequence bit-planes (gathered by the host
+    after segmentation); with the planes fully resident the results must be identical."""
+    from freddie_b200 import _lib
+    from freddie_b200.pack import pack_tints
+    tints, flags, _ = golden_set(name)
+    _, gprm = _params(flags)
+    batch = pack_tints(tints)
+    lazy = eng.segment_batch(batch, gprm)
+    st = eng.stats()
+    assert st["clip_words"] <= st["seq_words"] and st["h2d_run"] >= 8 * st["clip_words"]
+    try:
+        eng.set_option(_lib.OPT_LAZY_SEQ, 0)
+        full = eng.segment_batch(batch, gprm)
+        assert eng.stats()["h2d_run"] == 0
+    finally:
+        eng.set_option(_lib.OPT_LAZY_SEQ, 1)
+    for k in lazy.arrays:
+        assert np.array_equal(lazy.arrays[k], full.arrays[k]), (name, k)
+
+
 def test_in_process_seam_has_reference_signature(golden_set):
     """segment(tint, sigma, smoothed_threshold, tp, vf, mps, lo, ignore_ends) mutates the tint like the
     reference (freddie_segment.py:738-844)."""
