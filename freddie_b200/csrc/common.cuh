@@ -183,3 +183,15 @@ __device__ __forceinline__ int upper_row64(const i64* __restrict__ off, int n, i
   }
   return lo;
 }
+
+// tint of every island / read rep / read (binary search in the tint offset tables)
+__global__ void k_owner_tables(int T, int n_islands, int n_reps, int n_reads, const int* __restrict__ tint_island_off,
+                               const int* __restrict__ tint_rep_off, const int* __restrict__ tint_read_off,
+                               int* __restrict__ island_tint, int* __restrict__ rep_tint, int* __restrict__ read_tint) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n_islands) { island_tint[e] = upper_row(tint_island_off, T, (int)e); return; }
+  e -= n_islands;
+  if (e < n_reps) { rep_tint[e] = upper_row(tint_rep_off, T, (int)e); return; }
+  e -= n_reps;
+  if (e < n_reads) read_tint[e] = upper_row(tint_read_off, T, (int)e);
+}

@@ -58,7 +58,7 @@ struct frs_context {
       b_sub_n, b_sub_tint, b_sub_info, b_sub_slabs, b_sz_tab, b_sub_tab_off, b_plan, b_work, b_split_list, b_cursor,
       b_cov_sz, b_tint_cov_off, b_P, b_tab, b_dpfinal, b_pf_list, b_gbuf, b_pstate, b_final_flat,
       b_final_pos, b_final_island, b_tint_final_off, b_dig_sz, b_tint_digit_off, b_seg_ty, b_seg_tn, b_digits,
-      b_run_cnt, b_run_off, b_runs, b_gap_cnt, b_clip_n, b_clip_off, b_task_order, b_task_res, b_poly_cls, b_read_gap_off, b_read_head, b_gap_rec, b_counters, b_stats, b_err;
+      b_run_cnt, b_run_off, b_runs, b_gap_cnt, b_clip_n, b_clip_words, b_clip_off, b_task_order, b_task_res, b_poly_cls, b_read_gap_off, b_read_head, b_gap_rec, b_counters, b_stats, b_err;
   i64* h_pin = nullptr;  // pinned scratch for small D2H reads
   // results of the last run
   frs_result_sizes sizes;
@@ -205,69 +205,60 @@ static int check_dev_err(frs_context* c) {
 static int fetch_clip_words(frs_context* c, int N) {
   cudaStream_t st = c->stream;
   const size_t n_clip = (size_t)N * 2;
-  // staging layout: [clip_n: 2N int][clip_off: 2N i64][words A][words T]; worst case = whole planes
-  const size_t head = n_clip * 4 + n_clip * 8 + 64;
-  if (c->h_stage_cap < head) {
-    if (c->h_stage) cudaFreeHost(c->h_stage);
+  // device: exclusive scan of the per-clip word counts -> compact offsets (total at [2N])
+  { int r = scan_exclusive<int, i64>(c, c->b_clip_words.as<int>(), (i64)n_clip, c->b_clip_off.as<i64>()); if (r) return r; }
+  // staging layout: [clip_n: 2N int][clip_off: 2N+1 i64][words A][words T]
+  const size_t o_off = (n_clip * 4 + 15) & ~(size_t)15;
+  const size_t o_words = o_off + (((n_clip + 1) * 8 + 15) & ~(size_t)15);
+  auto grow = [&](size_t need) -> int {
+    if (c->h_stage_cap >= need) return 0;
+    if (c->h_stage) CK(cudaFreeHost(c->h_stage));
     c->h_stage = nullptr;
     c->h_stage_cap = 0;
-    size_t want = head + (64u << 20);
+    size_t want = need + need / 4 + (16u << 20);
     CK(cudaMallocHost(&c->h_stage, want));
     c->h_stage_cap = want;
-  }
-  int* h_n = (int*)c->h_stage;
-  CK(cudaMemcpyAsync(h_n, c->b_clip_n.p, n_clip * 4, cudaMemcpyDeviceToHost, st));
+    return 0;
+  };
+  { int r = grow(o_words + 64); if (r) return r; }
+  CK(cudaMemcpyAsync((char*)c->h_stage, c->b_clip_n.p, n_clip * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync((char*)c->h_stage + o_off, c->b_clip_off.p, (n_clip + 1) * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  c->st_d2h_run += (i64)n_clip * 4;
-  // word counts -> offsets (serial scan: 2N adds), then a parallel gather
-  std::vector<i64> off(n_clip + 1);
-  i64 total = 0;
-  for (size_t k = 0; k < n_clip; ++k) {
-    off[k] = total;
-    const int n = h_n[k];
-    if (n >= 20) {
-      const int i = (int)(k >> 1);
-      total += clip_geometry(c->h_read_len[i], n, (k & 1) == 0, c->h_read_strand[i] != 0).n_words;
-    }
+  c->st_d2h_run += (i64)n_clip * 4 + (i64)(n_clip + 1) * 8;
+  const i64 total = ((const i64*)((char*)c->h_stage + o_off))[n_clip];
+  if (c->h_stage_cap < o_words + (size_t)total * 8 + 64) {  // grow, keeping the two tables
+    std::vector<char> keep((char*)c->h_stage, (char*)c->h_stage + o_words);
+    int r = grow(o_words + (size_t)total * 8 + 64);
+    if (r) return r;
+    memcpy(c->h_stage, keep.data(), o_words);
   }
-  off[n_clip] = total;
-  const size_t need = head + (size_t)total * 8 + 64;
-  if (c->h_stage_cap < need) {  // grow (contents are re-derived below)
-    std::vector<int> keep(h_n, h_n + n_clip);
-    CK(cudaFreeHost(c->h_stage));
-    c->h_stage = nullptr;
-    c->h_stage_cap = 0;
-    size_t want = need + need / 4;
-    CK(cudaMallocHost(&c->h_stage, want));
-    c->h_stage_cap = want;
-    h_n = (int*)c->h_stage;
-    memcpy(h_n, keep.data(), n_clip * 4);
-  }
-  i64* h_off = (i64*)((char*)c->h_stage + ((n_clip * 4 + 15) & ~(size_t)15));
-  u32* h_wa = (u32*)((char*)h_off + ((n_clip * 8 + 15) & ~(size_t)15));
+  const int* h_n = (const int*)c->h_stage;
+  const i64* h_off = (const i64*)((char*)c->h_stage + o_off);
+  u32* h_wa = (u32*)((char*)c->h_stage + o_words);
   u32* h_wt = h_wa + total;
   const u32* pa = c->h_seq_a;
   const u32* pt = c->h_seq_t;
-#pragma omp parallel for schedule(static, 4096)
+  const int* rl = c->h_read_len.data();
+  const u8* rs = c->h_read_strand.data();
+  const i64* so = c->h_read_seq_off.data();
+#pragma omp parallel for schedule(static, 2048)
   for (long long k = 0; k < (long long)n_clip; ++k) {
-    h_off[k] = off[k];
     const int n = h_n[k];
     if (n < 20) continue;
     const int i = (int)(k >> 1);
-    const ClipGeo g = clip_geometry(c->h_read_len[i], n, (k & 1) == 0, c->h_read_strand[i] != 0);
-    const i64 src = c->h_read_seq_off[i] + g.w_first;
-    memcpy(h_wa + off[k], pa + src, (size_t)g.n_words * 4);
-    memcpy(h_wt + off[k], pt + src, (size_t)g.n_words * 4);
+    const ClipGeo g = clip_geometry(rl[i], n, (k & 1) == 0, rs[i] != 0);
+    const i64 src = so[i] + g.w_first;
+    memcpy(h_wa + h_off[k], pa + src, (size_t)g.n_words * 4);
+    memcpy(h_wt + h_off[k], pt + src, (size_t)g.n_words * 4);
   }
   int r;
   if ((r = ensure(c, c->b_seq_a, (size_t)total * 4))) return r;
   if ((r = ensure(c, c->b_seq_t, (size_t)total * 4))) return r;
-  CK(cudaMemcpyAsync(c->b_clip_off.p, h_off, n_clip * 8, cudaMemcpyHostToDevice, st));
   if (total > 0) {
     CK(cudaMemcpyAsync(c->b_seq_a.p, h_wa, (size_t)total * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->b_seq_t.p, h_wt, (size_t)total * 4, cudaMemcpyHostToDevice, st));
   }
-  c->st_h2d_run += (i64)n_clip * 8 + total * 8;
+  c->st_h2d_run += total * 8;
   c->st_clip_words = total;
   return 0;
 }
@@ -432,20 +423,20 @@ int frs_upload(frs_context* c, const frs_batch* b) {
   c->h_tint_read_off.assign(b->tint_read_off, b->tint_read_off + T + 1);
   c->h_island_sample_off.assign(b->island_sample_off, b->island_sample_off + NI + 1);
   // ---- derived host tables ----
-  std::vector<int> island_tint(NI), rep_tint(NR), read_tint(N);
   std::vector<SigWork> sig;
   std::vector<TileWork> tiles;
   std::vector<RepTile> cov_tiles, dig_tiles;
   const int DIG_REPS = 64;
   for (int t = 0; t < T; ++t) {
     for (int i = b->tint_island_off[t]; i < b->tint_island_off[t + 1]; ++i) {
-      island_tint[i] = t;
       int n = b->island_sample_off[i + 1] - b->island_sample_off[i];
       for (int lo = 0; lo < n; lo += TILE_SAMPLES) tiles.push_back(TileWork{i, lo});
     }
     int r0 = b->tint_rep_off[t], r1 = b->tint_rep_off[t + 1];
-    for (int r = r0; r < r1; ++r) rep_tint[r] = t;
-    for (int r = b->tint_read_off[t]; r < b->tint_read_off[t + 1]; ++r) read_tint[r] = t;
+    for (int r = b->tint_read_off[t]; r < b->tint_read_off[t + 1]; ++r) {
+      const int rep = b->read_rep[r];
+      if (rep < r0 || rep >= r1) return fail(c, FRS_ERR_ARG, "frs_upload: read %d points at rep %d of another tint", r, rep);
+    }
     int s0 = b->island_sample_off[b->tint_island_off[t]], s1 = b->island_sample_off[b->tint_island_off[t + 1]];
     int single = (r1 - r0) <= SIG_REPS;
     for (int w = s0; w < s1; w += SIG_BINS)
@@ -454,11 +445,6 @@ int frs_upload(frs_context* c, const frs_batch* b) {
     int R = r1 - r0, Rp = (R + 3) & ~3;
     for (int r = 0; r < Rp; r += COV_THREADS) cov_tiles.push_back(RepTile{t, r});
     for (int r = 0; r < R; r += DIG_REPS) dig_tiles.push_back(RepTile{t, r});
-  }
-  for (int r = 0; r < N; ++r) {
-    int rep = b->read_rep[r];
-    if (rep < 0 || rep >= NR || rep_tint[rep] != read_tint[r])
-      return fail(c, FRS_ERR_ARG, "frs_upload: read %d points at rep %d of another tint", r, rep);
   }
   c->n_sig_work = (int)sig.size();
   c->n_tiles = (int)tiles.size();
@@ -500,9 +486,13 @@ int frs_upload(frs_context* c, const frs_batch* b) {
     c->h_read_seq_off.assign(b->read_seq_off, b->read_seq_off + N + 1);
   }
   // the derived tables live in pageable vectors: stage synchronously before they go out of scope
-  H2D(b_island_tint, island_tint.data(), (size_t)NI * 4);
-  H2D(b_rep_tint, rep_tint.data(), (size_t)NR * 4);
-  H2D(b_read_tint, read_tint.data(), (size_t)N * 4);
+  // owner tables (tint of every island / rep / read) are derived on the device
+  ENS(b_island_tint, (size_t)NI * 4);
+  ENS(b_rep_tint, (size_t)NR * 4);
+  ENS(b_read_tint, (size_t)N * 4);
+  k_owner_tables<<<cdiv((i64)NI + NR + N, 256), 256, 0, c->stream>>>(
+      T, NI, NR, N, c->b_tint_island_off.as<int>(), c->b_tint_rep_off.as<int>(), c->b_tint_read_off.as<int>(),
+      c->b_island_tint.as<int>(), c->b_rep_tint.as<int>(), c->b_read_tint.as<int>());
   H2D(b_sig_work, sig.data(), sig.size() * sizeof(SigWork));
   H2D(b_tiles, tiles.data(), tiles.size() * sizeof(TileWork));
   H2D(b_cov_tiles, cov_tiles.data(), cov_tiles.size() * sizeof(RepTile));
@@ -865,11 +855,12 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
     G.final_pos = c->b_final_pos.as<int>(); G.read_gap_off = c->b_read_gap_off.as<int>();
     G.read_head = c->b_read_head.as<int>(); G.gap_rec = c->b_gap_rec.as<int>(); G.err = d_err;
     ENS(b_clip_n, (size_t)N * 8);
-    ENS(b_clip_off, (size_t)N * 16);
+    ENS(b_clip_words, (size_t)N * 8);
+    ENS(b_clip_off, (size_t)N * 16 + 8);
     ENS(b_task_order, (size_t)N * 16);
     ENS(b_task_res, (size_t)N * 4 * sizeof(PolyRes));
     ENS(b_poly_cls, (2 * POLY_CLASSES + 1) * 4);
-    G.clip_n = c->b_clip_n.as<int>(); G.clip_off = c->b_clip_off.as<i64>(); G.seq_resident = c->seq_resident ? 1 : 0;
+    G.clip_n = c->b_clip_n.as<int>(); G.clip_words = c->b_clip_words.as<int>(); G.clip_off = c->b_clip_off.as<i64>(); G.seq_resident = c->seq_resident ? 1 : 0;
     G.cls_count = c->b_poly_cls.as<int>();
     G.task_order = c->b_task_order.as<int>(); G.task_res = c->b_task_res.as<PolyRes>();
     G.long_class = c->opt_poly_long_class;

@@ -298,7 +298,8 @@ struct GapArgs {
   int* read_head; int* gap_rec; int* err;
   // poly tasks: slot = read*4 + (0 start-A, 1 start-T, 2 end-A, 3 end-T)
   int* clip_n;        // [2N] bases of the read's start (2i) / end (2i+1) clip, 0 = nothing to scan (< 20)
-  i64* clip_off;      // [2N] word offset of the clip's plane words inside seq_a / seq_t (see clip_geometry)
+  int* clip_words;    // [2N] plane words the clip needs (lazy mode: scanned into clip_off)
+  i64* clip_off;      // [2N+1] word offset of the clip's plane words inside seq_a / seq_t (see clip_geometry)
   int seq_resident;   // 1: seq_a/seq_t hold the whole reads (clip_off written by k_gap_prep);
                       // 0: they hold only the clip words, gathered by the host after k_gap_prep
   int* cls_count;     // [POLY_CLASSES] (+ [POLY_CLASSES] cursors, + 1 total) zeroed before k_gap_prep
@@ -384,7 +385,9 @@ __global__ void __launch_bounds__(128) k_gap_prep(GapArgs A) {
     int* head = A.read_head + (i64)i * 8;
     for (int k = 0; k < 8; ++k) head[k] = 0;
     int* cn = A.clip_n + (i64)i * 2;
+    int* cw = A.clip_words + (i64)i * 2;
     cn[0] = cn[1] = 0;
+    cw[0] = cw[1] = 0;
     const int rep = A.read_rep[i];
     const int ra = A.run_off[rep], rb = A.run_off[rep + 1];
     if (ra != rb) {  // else: no '1' digit, empty gaps (:372)
@@ -406,12 +409,16 @@ __global__ void __launch_bounds__(128) k_gap_prep(GapArgs A) {
         if (ns >= 20) {
           cn[0] = ns;
           atomicAdd(&sh_cnt[poly_class_dev(ns)], 2);
-          if (A.seq_resident) A.clip_off[2 * (i64)i] = A.read_seq_off[i] + clip_geometry(L, ns, true, minus).w_first;
+          const ClipGeo g = clip_geometry(L, ns, true, minus);
+          cw[0] = g.n_words;
+          if (A.seq_resident) A.clip_off[2 * (i64)i] = A.read_seq_off[i] + g.w_first;
         }
         if (ne >= 20) {
           cn[1] = ne;
           atomicAdd(&sh_cnt[poly_class_dev(ne)], 2);
-          if (A.seq_resident) A.clip_off[2 * (i64)i + 1] = A.read_seq_off[i] + clip_geometry(L, ne, false, minus).w_first;
+          const ClipGeo g = clip_geometry(L, ne, false, minus);
+          cw[1] = g.n_words;
+          if (A.seq_resident) A.clip_off[2 * (i64)i + 1] = A.read_seq_off[i] + g.w_first;
         }
         // unaligned gaps between consecutive 1-runs (:455-471): (l1, f2, owner); k_gap_sizes fills the size
         int* rec = A.gap_rec + (i64)A.read_gap_off[i] * 3;
