@@ -426,7 +426,7 @@ int frs_upload(frs_context* c, const frs_batch* b) {
   std::vector<SigWork> sig;
   std::vector<TileWork> tiles;
   std::vector<RepTile> cov_tiles, dig_tiles;
-  const int DIG_REPS = 64;
+  const int DIG_REPS = DIG_THREADS;
   for (int t = 0; t < T; ++t) {
     for (int i = b->tint_island_off[t]; i < b->tint_island_off[t + 1]; ++i) {
       int n = b->island_sample_off[i + 1] - b->island_sample_off[i];
@@ -808,20 +808,16 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
 
   ENS(b_digits, NDIG);
   stage_begin(c, "digits");
-  k_digits<<<c->n_dig_tiles, DIG_THREADS, 0, st>>>(c->b_dig_tiles.as<RepTile>(), 64, d_tint_rep_off,
+  ENS(b_run_cnt, (size_t)NR * 4);
+  ENS(b_run_off, (size_t)(NR + 1) * 4);
+  k_digits<<<c->n_dig_tiles, DIG_THREADS, 0, st>>>(c->b_dig_tiles.as<RepTile>(), d_tint_rep_off,
                                                    c->b_tint_final_off.as<int>(), c->b_tint_digit_off.as<i64>(),
                                                    c->b_rep_iv_off.as<int>(), c->b_rep_fs.as<int>(), c->b_rep_fe.as<int>(),
                                                    c->b_final_flat.as<int>(), c->b_seg_ty.as<int>(), c->b_seg_tn.as<int>(),
-                                                   c->b_digits.as<u8>(), d_err);
+                                                   c->b_digits.as<u8>(), c->b_run_cnt.as<int>(), d_err);
   LAUNCHED();
 
   stage_begin(c, "runs");
-  ENS(b_run_cnt, (size_t)NR * 4);
-  ENS(b_run_off, (size_t)(NR + 1) * 4);
-  k_run_count<<<cdiv((i64)NR * 32, 256), 256, 0, st>>>(NR, c->b_rep_tint.as<int>(), d_tint_rep_off,
-                                                       c->b_tint_final_off.as<int>(), c->b_tint_digit_off.as<i64>(),
-                                                       c->b_digits.as<u8>(), c->b_run_cnt.as<int>());
-  LAUNCHED();
   { int r = scan_exclusive<int, int>(c, c->b_run_cnt.as<int>(), NR, c->b_run_off.as<int>()); if (r) return r; }
   CK(cudaMemsetAsync(c->b_counters.as<i64>() + 13, 0, 16, st));
   CK(cudaMemcpyAsync(c->b_counters.as<i64>() + 13, c->b_run_off.as<int>() + NR, 4, cudaMemcpyDeviceToDevice, st));

@@ -253,14 +253,19 @@ __global__ void k_sub_fill(int n_sub, const int* __restrict__ sub_info, const in
 }
 
 // ---------------------------------------------------------------------------------------------
-// index helpers.  pairs (i<j): row-major upper triangle.  triples: [j][i][k-j-1], j = 1..n-2,
-// i < j < k  -> exactly C(n,3) entries.
+// index helpers.  pairs (i<j): row-major upper triangle.  triples (i<j<k): [j][k-j-1][i], j = 1..n-2
+// -> exactly C(n,3) entries; the left candidate i is the fastest index because the lanes of the triple
+// phase run over i (conflict-free shared-memory accumulation).
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ int pair_index(int i, int j, int n) { return i * (2 * n - i - 1) / 2 + (j - i - 1); }
 __host__ __device__ __forceinline__ int triple_mid_off(int j, int n) {
   // sum_{j'=1}^{j-1} j' (n-1-j')
   int m = j - 1;
   return (n - 1) * m * (m + 1) / 2 - m * (m + 1) * (2 * m + 1) / 6;
+}
+
+__host__ __device__ __forceinline__ int triple_index(int i, int j, int k, int n) {
+  return triple_mid_off(j, n) + (k - j - 1) * j + i;
 }
 
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
@@ -326,10 +331,10 @@ __device__ void dp_solve(const int n, const int* cf, const int* amb, const int* 
       int best = FRS_NEG_INF, bk = 0x7fff;
       if (k < E && cf[k] - cf[j] >= 5) {
         const int base = -amb[pair_index(j, k, n)];
-        const int* o = out + triple_mid_off(k, n) + j * (n - 1 - k);
+        const int* o = out + triple_mid_off(k, n) + j;  // out(j, k, k2) = o[(k2-k-1)*k]
         for (int k2 = k + 1 + gl; k2 <= E; k2 += SUB) {
           if (cf[k2] - cf[k] < 5) continue;
-          int ov = o[k2 - k - 1];
+          int ov = o[(k2 - k - 1) * k];
           if (ov < lo) continue;
           int g = G[k * n + k2];
           if (g == FRS_NEG_INF) continue;
@@ -356,7 +361,7 @@ __device__ void dp_solve(const int n, const int* cf, const int* amb, const int* 
     int j = e / n, k = e - j * n;
     if (j < 1 || k <= j) continue;
     if (cf[j] - cf[0] < 5 || cf[k] - cf[j] < 5) continue;
-    int ov = out[triple_mid_off(j, n) + (k - j - 1)];
+    int ov = out[triple_index(0, j, k, n)];
     if (ov < lo) continue;
     int g = G[j * n + k];
     if (g == FRS_NEG_INF) continue;
@@ -458,8 +463,92 @@ __device__ __forceinline__ int wpopc(u32 m, const u32* __restrict__ pl, int np) 
   return acc;
 }
 
+// mask phase of one chunk: yea / nay words of every pair (i<j) for the nw words staged in `tile`.
+template <int THREADS, bool MASKED>
+__device__ __forceinline__ void dp_mask_phase(const int n, const int nw, const int wc, const int CW,
+                                              const u32* __restrict__ tile, const int* __restrict__ ty,
+                                              const int* __restrict__ tn, uint2* __restrict__ ynm,
+                                              const u32* __restrict__ vmask) {
+  constexpr int NW = THREADS / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  u32 vl = 0xffffffffu;  // bit w: this lane's rep of word w is a real rep
+  if (MASKED) {
+    vl = 0;
+    for (int w = 0; w < nw; ++w) vl |= ((vmask[w] >> lane) & 1u) << w;
+  }
+  const int nrows = n - 1;          // rows i = 0..n-2
+  const int nrp = (nrows + 1) / 2;  // row a is processed together with row nrows-1-a
+  for (int a = warp; a < nrp; a += NW) {
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+      const int i = side ? (nrows - 1 - a) : a;
+      if (side && i == a) break;
+      const u32* rowi = tile + (size_t)i * CW + lane;
+      u32 ri[DPT_MAXW];
+#pragma unroll
+      for (int w = 0; w < DPT_MAXW; ++w) ri[w] = (w < nw) ? rowi[w * 32] : 0u;
+      const int ebase = pair_index(i, i + 1, n);
+      for (int j = i + 1; j < n; ++j) {
+        const int e = ebase + (j - i - 1);
+        const int cy = ty[e], cn = tn[e];
+        const u32* rowj = tile + (size_t)j * CW + lane;
+        uint2* dst = ynm + (size_t)e * wc;
+#pragma unroll
+        for (int w = 0; w < DPT_MAXW; ++w) {
+          if (w < nw) {
+            const int cov = (int)(rowj[w * 32] - ri[w]);
+            bool py = cov >= cy, pn = cov <= cn;
+            if (MASKED) { const bool valid = (vl >> w) & 1u; py = py && valid; pn = pn && valid; }
+            const u32 by = __ballot_sync(0xffffffffu, py);
+            const u32 bn = __ballot_sync(0xffffffffu, pn);
+            if (lane == 0) dst[w] = make_uint2(by, bn);
+          }
+        }
+      }
+    }
+  }
+}
+
+// triple phase of one chunk: out(i,j,k) += sum_w W . [(yea_ij & nay_jk) | (nay_ij & yea_jk)].  The
+// (j, i) pairs are flattened over the threads (a warp holds consecutive i of one or two j, so the
+// yn_jk loads are broadcasts and the accumulation is conflict-free); the loop runs over k.
+template <int THREADS, bool W1>
+__device__ __forceinline__ void dp_triple_phase(const int n, const int nw, const int wc, const uint2* __restrict__ ynm,
+                                                const u32* __restrict__ planes, const int* __restrict__ nplanes,
+                                                const int out_on_chip, int* __restrict__ dst) {
+  const int U = (n - 1) * (n - 2) / 2;  // units (j, i): q = j(j-1)/2 + i, 1 <= j <= n-2, i < j
+  for (int q = threadIdx.x; q < U; q += THREADS) {
+    int j = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)q)) * 0.5f);
+    while (j * (j - 1) / 2 > q) --j;
+    while ((j + 1) * j / 2 <= q) ++j;
+    const int i = q - j * (j - 1) / 2;
+    const uint2* yn_ij = ynm + (size_t)pair_index(i, j, n) * wc;
+    uint2 rij[DPT_MAXW];
+#pragma unroll
+    for (int w = 0; w < DPT_MAXW; ++w) rij[w] = (w < nw) ? yn_ij[w] : make_uint2(0u, 0u);
+    const uint2* yn_jk = ynm + (size_t)pair_index(j, j + 1, n) * wc;
+    int o = triple_mid_off(j, n) + i;
+    for (int k = j + 1; k < n; ++k, yn_jk += wc, o += j) {
+      int acc = 0;
+#pragma unroll
+      for (int w = 0; w < DPT_MAXW; ++w) {
+        if (w < nw) {
+          const uint2 jk = yn_jk[w];
+          const u32 m = (rij[w].x & jk.y) | (rij[w].y & jk.x);
+          if (W1) acc += __popc(m);
+          else if (m) acc += wpopc(m, planes + w * 32, nplanes[w]);
+        }
+      }
+      if (acc) {
+        if (out_on_chip) dst[o] += acc;
+        else atomicAdd(&dst[o], acc);
+      }
+    }
+  }
+}
+
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_dp(DpArgs A, const DpWork* __restrict__ work, int M, int wc,
+__global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 ? 3 : 1)) k_dp(DpArgs A, const DpWork* __restrict__ work, int M, int wc,
                                                 int out_on_chip) {
   extern __shared__ __align__(16) unsigned char dsm[];
   const DpWork wk = work[blockIdx.x];
@@ -546,42 +635,11 @@ __global__ void __launch_bounds__(THREADS) k_dp(DpArgs A, const DpWork* __restri
     __syncthreads();  // cuts + planes visible; previous chunk's triple phase done
     mbar_wait(bar, phase);
     phase ^= 1;
-    // ---- mask phase: rows i paired from both ends for balance ----
-    {
-      u32 vl = 0;  // bit w: this lane's rep of word w is a real rep
-      for (int w = 0; w < nw; ++w) vl |= ((vmask[w] >> lane) & 1u) << w;
-      const int nrows = n - 1;          // rows i = 0..n-2
-      const int nrp = (nrows + 1) / 2;  // row a is processed together with row nrows-1-a
-      for (int a = warp; a < nrp; a += NW) {
-#pragma unroll 1
-        for (int side = 0; side < 2; ++side) {
-          const int i = side ? (nrows - 1 - a) : a;
-          if (side && i == a) break;
-          const u32* rowi = tile + (size_t)i * CW + lane;
-          u32 ri[DPT_MAXW];
-#pragma unroll
-          for (int w = 0; w < DPT_MAXW; ++w) ri[w] = (w < nw) ? rowi[w * 32] : 0u;
-          const int ebase = pair_index(i, i + 1, n);
-          for (int j = i + 1; j < n; ++j) {
-            const int e = ebase + (j - i - 1);
-            const int cy = ty[e], cn = tn[e];
-            const u32* rowj = tile + (size_t)j * CW + lane;
-            u32 my_y = 0, my_n = 0;
-#pragma unroll
-            for (int w = 0; w < DPT_MAXW; ++w) {
-              if (w < nw) {
-                const bool valid = (vl >> w) & 1u;
-                const int cov = (int)(rowj[w * 32] - ri[w]);
-                const u32 by = __ballot_sync(0xffffffffu, valid && cov >= cy);
-                const u32 bn = __ballot_sync(0xffffffffu, valid && cov <= cn);
-                if (lane == w) { my_y = by; my_n = bn; }
-              }
-            }
-            if (lane < nw) ynm[(size_t)e * wc + lane] = make_uint2(my_y, my_n);
-          }
-        }
-      }
-    }
+    // ---- mask phase: rows i paired from both ends for balance.  Only the last word of a tint can
+    // hold lanes without a rep; every other chunk skips the masking ----
+    const bool tail_chunk = (w0 + nw == words) && (R & 31);
+    if (tail_chunk) dp_mask_phase<THREADS, true>(n, nw, wc, CW, tile, ty, tn, ynm, vmask);
+    else dp_mask_phase<THREADS, false>(n, nw, wc, CW, tile, ty, tn, ynm, vmask);
     __syncthreads();  // masks complete, tile free
     if (tid == 0 && w0 + wc < w_hi) issue(w0 + wc);
     // ---- ins pass: ambiguous reps per pair ----
@@ -598,32 +656,12 @@ __global__ void __launch_bounds__(THREADS) k_dp(DpArgs A, const DpWork* __restri
       }
     }
     // ---- triple phase ----
-    for (int j = 1 + warp; j <= n - 2; j += NW) {
-      const int cols = n - 1 - j;
-      const int joff = triple_mid_off(j, n);
-      for (int i = lane; i < j; i += 32) {
-        const uint2* yn_ij = ynm + (size_t)pair_index(i, j, n) * wc;
-        uint2 rij[DPT_MAXW];
-#pragma unroll
-        for (int w = 0; w < DPT_MAXW; ++w) rij[w] = (w < nw) ? yn_ij[w] : make_uint2(0u, 0u);
-        const uint2* yn_jk = ynm + (size_t)pair_index(j, j + 1, n) * wc;
-        const int obase = joff + i * cols;
-        for (int k = j + 1; k < n; ++k, yn_jk += wc) {
-          int acc = 0;
-#pragma unroll
-          for (int w = 0; w < DPT_MAXW; ++w) {
-            if (w < nw) {
-              const uint2 jk = yn_jk[w];
-              const u32 m = (rij[w].x & jk.y) | (rij[w].y & jk.x);
-              if (m) acc += wpopc(m, planes + w * 32, nplanes[w]);
-            }
-          }
-          if (acc) {
-            if (out_on_chip) out_s[obase + (k - j - 1)] += acc;
-            else atomicAdd(&tab_g[p2 + obase + (k - j - 1)], acc);
-          }
-        }
-      }
+    {
+      bool w1 = true;  // every word of the chunk has unit weights only
+      for (int w = 0; w < nw; ++w) w1 = w1 && nplanes[w] <= 1;
+      int* dst = out_on_chip ? out_s : (tab_g + p2);
+      if (w1) dp_triple_phase<THREADS, true>(n, nw, wc, ynm, planes, nplanes, out_on_chip, dst);
+      else dp_triple_phase<THREADS, false>(n, nw, wc, ynm, planes, nplanes, out_on_chip, dst);
     }
     __syncthreads();  // the next chunk rewrites the weight planes and the masks
   }
@@ -736,8 +774,8 @@ __global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWo
       const int i = rem;
       const uint2 ij = S.yn[pair_index(i, j, n)];
       const uint2* jk = S.yn + pair_index(j, j + 1, n);
-      int* o = S.out + triple_mid_off(j, n) + i * (n - 1 - j);
-      for (int k = j + 1; k < n; ++k, ++jk, ++o) {
+      int* o = S.out + triple_mid_off(j, n) + i;
+      for (int k = j + 1; k < n; ++k, ++jk, o += j) {
         const uint2 v = *jk;
         const u32 m = (ij.x & v.y) | (ij.y & v.x);
         if (m) *o += wpopc(m, S.planes, np);

@@ -167,11 +167,15 @@ __global__ void k_seg_cuts(int n_final, const int* __restrict__ final_flat, cons
 }
 
 // ---------------------------------------------------------------------------------------------
-// K10 digits: one warp per read rep, lanes over segments; ASCII digits, rep-major rows (:815-838).
-// cov(segment) = P(f_{t+1}) - P(f_t) with P(x) = samples of the rep strictly before flat x.
+// K10 digits (:808-838).  One thread per read rep walks the tint's final positions and its own
+// (ordered) intervals with two pointers: P(x) = samples of the rep strictly before flat x, and the
+// coverage of segment s is P(f_{s+1}) - P(f_s).  32 segments at a time go through a shared-memory
+// transpose so that the ASCII digit rows (rep-major, what the formatter copies) are written as
+// contiguous 32-byte pieces.  The same walk counts the rep's runs of '1' digits.
 // ---------------------------------------------------------------------------------------------
-#define DIG_THREADS 256
-__global__ void __launch_bounds__(DIG_THREADS) k_digits(const RepTile* __restrict__ tiles, int reps_per_tile,
+#define DIG_THREADS 128
+#define DIG_SEGS 32
+__global__ void __launch_bounds__(DIG_THREADS) k_digits(const RepTile* __restrict__ tiles,
                                                        const int* __restrict__ tint_rep_off,
                                                        const int* __restrict__ tint_final_off,
                                                        const i64* __restrict__ tint_digit_off,
@@ -179,56 +183,70 @@ __global__ void __launch_bounds__(DIG_THREADS) k_digits(const RepTile* __restric
                                                        const int* __restrict__ iv_fs, const int* __restrict__ iv_fe,
                                                        const int* __restrict__ final_flat,
                                                        const int* __restrict__ seg_ty, const int* __restrict__ seg_tn,
-                                                       u8* __restrict__ digits, int* __restrict__ err) {
+                                                       u8* __restrict__ digits, int* __restrict__ run_cnt,
+                                                       int* __restrict__ err) {
+  __shared__ u8 tile[DIG_THREADS][DIG_SEGS + 1];
   const RepTile tl = tiles[blockIdx.x];
   const int r0 = tint_rep_off[tl.tint];
   const int R = tint_rep_off[tl.tint + 1] - r0;
   const int f0 = tint_final_off[tl.tint];
   const int S = tint_final_off[tl.tint + 1] - f0 - 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int r_hi = min(R, tl.rep_lo + reps_per_tile);
-  for (int r = tl.rep_lo + warp; r < r_hi; r += DIG_THREADS / 32) {
-    const int a = rep_iv_off[r0 + r], b = rep_iv_off[r0 + r + 1];
-    u8* row = digits + tint_digit_off[tl.tint] + (i64)r * S;
-    for (int s = lane; s < S; s += 32) {
-      const int tn = seg_tn[f0 + s];
-      u8 d = '0';
-      if (tn != -2) {
-        const int fa = final_flat[f0 + s], fb = final_flat[f0 + s + 1];
-        int cov = 0;
-        for (int k = a; k < b; ++k) {
-          int fs = iv_fs[k], len = iv_fe[k] - fs + 1;
-          int hi = min(max(fb - fs, 0), len);
-          int lo = min(max(fa - fs, 0), len);
-          cov += hi - lo;
-        }
-        if (cov > fb - fa + 1) dev_fail(err, DEVERR_RATIO_RANGE, r0 + r);
-        d = (cov >= seg_ty[f0 + s]) ? '1' : ((cov <= tn) ? '0' : '2');
-      }
-      row[s] = d;
+  const int r = tl.rep_lo + threadIdx.x;
+  const bool have = r < R;
+  int a = 0, b = 0;
+  if (have) { a = rep_iv_off[r0 + r]; b = rep_iv_off[r0 + r + 1]; }
+  int fs = (a < b) ? iv_fs[a] : 0x7fffffff;
+  int fe = (a < b) ? iv_fe[a] : 0x7fffffff;
+  u32 acc = 0;
+  auto P = [&](int x) -> u32 {  // x is non-decreasing over the calls
+    while (a < b && fe < x) {
+      acc += (u32)(fe - fs + 1);
+      ++a;
+      fs = (a < b) ? iv_fs[a] : 0x7fffffff;
+      fe = (a < b) ? iv_fe[a] : 0x7fffffff;
     }
+    return acc + ((a < b && x > fs) ? (u32)(x - fs) : 0u);
+  };
+  u32 p_prev = (have && S > 0) ? P(final_flat[f0]) : 0u;
+  int runs = 0;
+  bool prev1 = false;
+  u8* out0 = digits + tint_digit_off[tl.tint];
+  for (int s0 = 0; s0 < S; s0 += DIG_SEGS) {
+    const int ns = min(DIG_SEGS, S - s0);
+    if (have) {
+      for (int k = 0; k < ns; ++k) {
+        const int s = s0 + k;
+        const int fb = final_flat[f0 + s + 1];
+        const u32 p_next = P(fb);
+        const int tn = seg_tn[f0 + s];
+        u8 d = '0';
+        if (tn != -2) {
+          const int cov = (int)(p_next - p_prev);
+          if (cov > fb - final_flat[f0 + s] + 1) dev_fail(err, DEVERR_RATIO_RANGE, r0 + r);
+          d = (cov >= seg_ty[f0 + s]) ? '1' : ((cov <= tn) ? '0' : '2');
+        }
+        p_prev = p_next;
+        const bool is1 = d == '1';
+        runs += (is1 && !prev1) ? 1 : 0;
+        prev1 = is1;
+        tile[threadIdx.x][k] = d;
+      }
+    }
+    __syncthreads();
+    // rows of this warp's 32 reps, 32 contiguous bytes each
+    for (int rr = 0; rr < 32; ++rr) {
+      const int row = tl.rep_lo + warp * 32 + rr;
+      if (row >= R) break;
+      if (lane < ns) out0[(i64)row * S + s0 + lane] = tile[warp * 32 + rr][lane];
+    }
+    __syncthreads();
   }
+  if (have) run_cnt[r0 + r] = runs;
 }
 
-// ---------------------------------------------------------------------------------------------
-// 1-runs per rep (shared by all reads of the rep): count, then fill after a scan.
-// ---------------------------------------------------------------------------------------------
-__global__ void k_run_count(int n_reps, const int* __restrict__ rep_tint, const int* __restrict__ tint_rep_off,
-                            const int* __restrict__ tint_final_off, const i64* __restrict__ tint_digit_off,
-                            const u8* __restrict__ digits, int* __restrict__ run_cnt) {
-  int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (r >= n_reps) return;
-  int t = rep_tint[r];
-  int S = tint_final_off[t + 1] - tint_final_off[t] - 1;
-  const u8* row = digits + tint_digit_off[t] + (i64)(r - tint_rep_off[t]) * S;
-  int cnt = 0;
-  for (int s = lane; s < S; s += 32) cnt += (row[s] == '1' && (s == 0 || row[s - 1] != '1')) ? 1 : 0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if (lane == 0) run_cnt[r] = cnt;
-}
-
+// 1-runs per rep (shared by all reads of the rep): one warp per rep, 32 segments per step, starts and
+// ends found with ballots -- the k-th start and the k-th end of a row belong to the same run.
 __global__ void k_run_fill(int n_reps, const int* __restrict__ rep_tint, const int* __restrict__ tint_rep_off,
                            const int* __restrict__ tint_final_off, const i64* __restrict__ tint_digit_off,
                            const u8* __restrict__ digits, const int* __restrict__ run_off, int2* __restrict__ runs) {
@@ -238,18 +256,24 @@ __global__ void k_run_fill(int n_reps, const int* __restrict__ rep_tint, const i
   int t = rep_tint[r];
   int S = tint_final_off[t + 1] - tint_final_off[t] - 1;
   const u8* row = digits + tint_digit_off[t] + (i64)(r - tint_rep_off[t]) * S;
-  int base = run_off[r];
+  int* out = (int*)(runs + run_off[r]);
+  if (run_off[r + 1] == run_off[r]) return;
+  int base_s = 0, base_e = 0;
+  bool carry1 = false;  // digit before this chunk is '1'
   for (int s0 = 0; s0 < S; s0 += 32) {
-    int s = s0 + lane;
-    bool st = s < S && row[s] == '1' && (s == 0 || row[s - 1] != '1');
-    unsigned m = __ballot_sync(0xffffffffu, st);
-    if (st) {
-      int idx = base + __popc(m & ((1u << lane) - 1u));
-      int e = s;
-      while (e + 1 < S && row[e + 1] == '1') ++e;
-      runs[idx] = make_int2(s, e);
-    }
-    base += __popc(m);
+    const int s = s0 + lane;
+    const bool is1 = s < S && row[s] == '1';
+    const unsigned m1 = __ballot_sync(0xffffffffu, is1);
+    const bool after1 = (s0 + 32 < S) && row[s0 + 32] == '1';  // same address for the whole warp
+    const unsigned prevm = (m1 << 1) | (carry1 ? 1u : 0u);
+    const unsigned nextm = (m1 >> 1) | (after1 ? 0x80000000u : 0u);
+    const unsigned ms = m1 & ~prevm, me = m1 & ~nextm;
+    const unsigned lt = (1u << lane) - 1u;
+    if ((ms >> lane) & 1u) out[2 * (base_s + __popc(ms & lt))] = s;
+    if ((me >> lane) & 1u) out[2 * (base_e + __popc(me & lt)) + 1] = s;
+    base_s += __popc(ms);
+    base_e += __popc(me);
+    carry1 = (m1 >> 31) & 1u;
   }
 }
 

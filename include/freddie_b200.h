@@ -161,7 +161,7 @@ enum {
   FRS_TAP_SUB_N = 8,      /* int32 [n_subproblems] size n */
   FRS_TAP_COVERAGE = 9,   /* u32   cumulative coverage rows, see DESIGN.md */
   FRS_TAP_DP_TABLES = 10, /* int32 per-subproblem blocks: pair-indexed ambiguous counts (= -ins, :500-506),
-                             n(n-1)/2 entries, then out (:509-528) as [j][i][k-j-1], C(n,3) entries.  Blocks
+                             n(n-1)/2 entries, then out (:509-528) as [j][k-j-1][i], C(n,3) entries.  Blocks
                              exist for subproblems of giant tints (summed over their rep slabs) and, with
                              FRS_OPT_KEEP_DP_TABLES, for every subproblem */
   FRS_TAP_COV_OFF = 12,   /* int64 [n_tints+1] element offset of each tint's coverage block */

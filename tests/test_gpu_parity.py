@@ -117,9 +117,9 @@ def _check_dp_tables(eng, tint, oprm, limit=12):
             for j in range(i + 1, n):
                 assert -blk[k] == oi[i, j], (p, i, j)
                 k += 1
-        for j in range(1, n - 1):
-            for i in range(j):
-                for kk in range(j + 1, n):
+        for j in range(1, n - 1):          # out layout: [j][k-j-1][i]
+            for kk in range(j + 1, n):
+                for i in range(j):
                     assert blk[k] == oo[i, j, kk], (p, i, j, kk)
                     k += 1
         checked += 1
