@@ -19,6 +19,9 @@
 static thread_local char g_err[512] = "";
 
 #define FRS_SIDE_STREAMS 4
+#ifndef DP_BIG_THREADS
+#define DP_BIG_THREADS 1024  // CTA size of the DP kernel for subproblems with more than 32 candidates
+#endif
 
 struct DBuf {
   void* p = nullptr;
@@ -303,9 +306,9 @@ int frs_create(int device, frs_context** out) {
   cudaFuncSetAttribute(k_dp_warp<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DPW_WARPS * sizeof(DpWarpSmem<8>)));
   cudaFuncSetAttribute(k_dp_warp<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DPW_WARPS * sizeof(DpWarpSmem<16>)));
   cudaFuncSetAttribute(k_signal, cudaFuncAttributeMaxDynamicSharedMemorySize, SIG_BINS * 4);
-  cudaFuncSetAttribute(k_dp<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(k_dp<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(k_dp<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(k_dp<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256);
+  cudaFuncSetAttribute(k_dp<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256);
+  cudaFuncSetAttribute(k_dp<DP_BIG_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256);
   cudaFuncSetAttribute(k_dp_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   *out = c;
   return 0;
@@ -737,14 +740,14 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
         int wc = (k <= 3) ? 4 : DPT_MAXW;
         while (wc > 1 && dp_smem_layout(M, wc, on_chip).total > SMEM_BUDGET) wc >>= 1;
         const size_t sm = (size_t)dp_smem_layout(M, wc, on_chip).total;
-        if (sm > 227 * 1024)
+        if (sm > 227 * 1024 - 256)
           return fail(c, FRS_ERR_LIMIT, "subproblem with %d candidates exceeds the DP kernel's shared-memory budget "
                                         "(max_problem_size too large for this build)", M);
         const unsigned g = (unsigned)cls_cnt[k];
         switch (k) {
           case 2: k_dp<128><<<g, 128, sm, ks>>>(A, wl, M, wc, on_chip); break;
           case 3: k_dp<256><<<g, 256, sm, ks>>>(A, wl, M, wc, on_chip); break;
-          default: k_dp<512><<<g, 512, sm, ks>>>(A, wl, M, wc, on_chip); break;
+          default: k_dp<DP_BIG_THREADS><<<g, DP_BIG_THREADS, sm, ks>>>(A, wl, M, wc, on_chip); break;
         }
       }
       LAUNCHED();

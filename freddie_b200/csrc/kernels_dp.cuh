@@ -305,7 +305,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, u32 byt
 // Top level (:560-566): lexicographic (j,k), strict improvement over ins(0,E).  Backtrace (:592-594)
 // marks the chosen candidates.  amb = pair-indexed POSITIVE ambiguous counts: ins(i,j) = -amb[pair(i,j)].
 // ---------------------------------------------------------------------------------------------
-#define DPS_MAX_WARPS 16
+#define DPS_MAX_WARPS 32
 template <bool WARP>
 __device__ __forceinline__ void dp_sync() {
   if (WARP) __syncwarp(); else __syncthreads();
@@ -416,7 +416,9 @@ __device__ void dp_solve(const int n, const int* cf, const int* amb, const int* 
 // Weights: bit-planes of W per word (plane b = reps whose weight has bit b); a word whose reps all
 // have weight 1 costs one POPC.  Partial sums accumulate in shared memory over the chunks of the slab.
 // ---------------------------------------------------------------------------------------------
-#define DPT_MAXW 8
+#define DPT_MAXW 4
+#define DP_MASK_J 8   // pairs (i, j0..j0+7) per mask-phase unit
+#define DP_TRI_K 16   // right candidates k per triple-phase unit
 
 struct DpArgs {
   const int* sub_start; const int* sub_n; const int* sub_tint; const int* sub_info; const i64* sub_tab_off;
@@ -431,7 +433,7 @@ struct DpArgs {
 
 // shared-memory carve-up of k_dp for (M = largest n of the launch, wc, out table on chip?)
 struct DpSmem {
-  int tile, ynm, cf, ty, tn, planes, nplanes, vmask, amb, out, G, arg, red, total;
+  int tile, ynm, cf, ty, tn, planes, nplanes, vmask, munit, cumu, amb, out, G, arg, red, total;
 };
 __host__ __device__ inline DpSmem dp_smem_layout(int M, int wc, int out_on_chip) {
   DpSmem s;
@@ -446,6 +448,8 @@ __host__ __device__ inline DpSmem dp_smem_layout(int M, int wc, int out_on_chip)
   s.planes = o; o += wc * 32 * 4;
   s.nplanes = o; o += wc * 4;
   s.vmask = o; o += wc * 4;
+  s.munit = o; o += (p2 / DP_MASK_J + M + 1) * 4;  // mask-phase units (row i, first j), ushort2
+  s.cumu = o; o += (M + 1) * 4;                    // triple-phase units: prefix of j * ceil((n-1-j)/DP_TRI_K)
   s.amb = o; o += out_on_chip ? p2 * 4 : 0;
   s.out = o; o += out_on_chip ? c3 * 4 : 0;
   s.G = o; o += out_on_chip ? M * M * 4 : 0;
@@ -468,7 +472,8 @@ template <int THREADS, bool MASKED>
 __device__ __forceinline__ void dp_mask_phase(const int n, const int nw, const int wc, const int CW,
                                               const u32* __restrict__ tile, const int* __restrict__ ty,
                                               const int* __restrict__ tn, uint2* __restrict__ ynm,
-                                              const u32* __restrict__ vmask) {
+                                              const u32* __restrict__ vmask, const ushort2* __restrict__ munit,
+                                              const int n_munit) {
   constexpr int NW = THREADS / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   u32 vl = 0xffffffffu;  // bit w: this lane's rep of word w is a real rep
@@ -476,33 +481,28 @@ __device__ __forceinline__ void dp_mask_phase(const int n, const int nw, const i
     vl = 0;
     for (int w = 0; w < nw; ++w) vl |= ((vmask[w] >> lane) & 1u) << w;
   }
-  const int nrows = n - 1;          // rows i = 0..n-2
-  const int nrp = (nrows + 1) / 2;  // row a is processed together with row nrows-1-a
-  for (int a = warp; a < nrp; a += NW) {
-#pragma unroll 1
-    for (int side = 0; side < 2; ++side) {
-      const int i = side ? (nrows - 1 - a) : a;
-      if (side && i == a) break;
-      const u32* rowi = tile + (size_t)i * CW + lane;
-      u32 ri[DPT_MAXW];
+  // units = (row i, block of DP_MASK_J consecutive j): equal cost, dealt round-robin to the warps
+  for (int u = warp; u < n_munit; u += NW) {
+    const ushort2 un = munit[u];
+    const int i = un.x, j0 = un.y, j1 = min(n, j0 + DP_MASK_J);
+    const u32* rowi = tile + (size_t)i * CW + lane;
+    u32 ri[DPT_MAXW];
 #pragma unroll
-      for (int w = 0; w < DPT_MAXW; ++w) ri[w] = (w < nw) ? rowi[w * 32] : 0u;
-      const int ebase = pair_index(i, i + 1, n);
-      for (int j = i + 1; j < n; ++j) {
-        const int e = ebase + (j - i - 1);
-        const int cy = ty[e], cn = tn[e];
-        const u32* rowj = tile + (size_t)j * CW + lane;
-        uint2* dst = ynm + (size_t)e * wc;
+    for (int w = 0; w < DPT_MAXW; ++w) ri[w] = (w < nw) ? rowi[w * 32] : 0u;
+    int e = pair_index(i, j0, n);
+    for (int j = j0; j < j1; ++j, ++e) {
+      const int cy = ty[e], cn = tn[e];
+      const u32* rowj = tile + (size_t)j * CW + lane;
+      uint2* dst = ynm + (size_t)e * wc;
 #pragma unroll
-        for (int w = 0; w < DPT_MAXW; ++w) {
-          if (w < nw) {
-            const int cov = (int)(rowj[w * 32] - ri[w]);
-            bool py = cov >= cy, pn = cov <= cn;
-            if (MASKED) { const bool valid = (vl >> w) & 1u; py = py && valid; pn = pn && valid; }
-            const u32 by = __ballot_sync(0xffffffffu, py);
-            const u32 bn = __ballot_sync(0xffffffffu, pn);
-            if (lane == 0) dst[w] = make_uint2(by, bn);
-          }
+      for (int w = 0; w < DPT_MAXW; ++w) {
+        if (w < nw) {
+          const int cov = (int)(rowj[w * 32] - ri[w]);
+          bool py = cov >= cy, pn = cov <= cn;
+          if (MASKED) { const bool valid = (vl >> w) & 1u; py = py && valid; pn = pn && valid; }
+          const u32 by = __ballot_sync(0xffffffffu, py);
+          const u32 bn = __ballot_sync(0xffffffffu, pn);
+          if (lane == 0) dst[w] = make_uint2(by, bn);
         }
       }
     }
@@ -515,20 +515,27 @@ __device__ __forceinline__ void dp_mask_phase(const int n, const int nw, const i
 template <int THREADS, bool W1>
 __device__ __forceinline__ void dp_triple_phase(const int n, const int nw, const int wc, const uint2* __restrict__ ynm,
                                                 const u32* __restrict__ planes, const int* __restrict__ nplanes,
-                                                const int out_on_chip, int* __restrict__ dst) {
-  const int U = (n - 1) * (n - 2) / 2;  // units (j, i): q = j(j-1)/2 + i, 1 <= j <= n-2, i < j
+                                                const int* __restrict__ cumu, const int out_on_chip,
+                                                int* __restrict__ dst) {
+  // units (j, block of DP_TRI_K right candidates, i), i fastest: cumu[j] = first unit of middle j
+  const int U = cumu[n - 1];
   for (int q = threadIdx.x; q < U; q += THREADS) {
-    int j = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)q)) * 0.5f);
-    while (j * (j - 1) / 2 > q) --j;
-    while ((j + 1) * j / 2 <= q) ++j;
-    const int i = q - j * (j - 1) / 2;
+    int lo = 1, hi = n - 1;  // largest j in [1, n-2] with cumu[j] <= q
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (cumu[mid] <= q) lo = mid; else hi = mid;
+    }
+    const int j = lo;
+    const int rem = q - cumu[j];
+    const int kb = rem / j, i = rem - kb * j;
+    const int k0 = j + 1 + kb * DP_TRI_K, k1 = min(n, k0 + DP_TRI_K);
     const uint2* yn_ij = ynm + (size_t)pair_index(i, j, n) * wc;
     uint2 rij[DPT_MAXW];
 #pragma unroll
     for (int w = 0; w < DPT_MAXW; ++w) rij[w] = (w < nw) ? yn_ij[w] : make_uint2(0u, 0u);
-    const uint2* yn_jk = ynm + (size_t)pair_index(j, j + 1, n) * wc;
-    int o = triple_mid_off(j, n) + i;
-    for (int k = j + 1; k < n; ++k, yn_jk += wc, o += j) {
+    const uint2* yn_jk = ynm + (size_t)pair_index(j, k0, n) * wc;
+    int o = triple_mid_off(j, n) + (k0 - j - 1) * j + i;
+    for (int k = k0; k < k1; ++k, yn_jk += wc, o += j) {
       int acc = 0;
 #pragma unroll
       for (int w = 0; w < DPT_MAXW; ++w) {
@@ -577,6 +584,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 
   u32* planes = (u32*)(dsm + L.planes);  // [wc][32]
   int* nplanes = (int*)(dsm + L.nplanes);
   u32* vmask = (u32*)(dsm + L.vmask);
+  ushort2* munit = (ushort2*)(dsm + L.munit);
+  int* cumu = (int*)(dsm + L.cumu);
+  __shared__ int s_n_munit;
   int* amb_s = (int*)(dsm + L.amb);      // [p2]
   int* out_s = (int*)(dsm + L.out);      // [c3]
 
@@ -590,6 +600,18 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < n; i += THREADS) cf[i] = A.cand_flat[qs + i];
+  if (tid == 32 % THREADS) {  // unit tables of the two phases (a few hundred entries)
+    int u = 0;
+    for (int i = 0; i < n - 1; ++i)
+      for (int j0 = i + 1; j0 < n; j0 += DP_MASK_J) munit[u++] = make_ushort2((unsigned short)i, (unsigned short)j0);
+    s_n_munit = u;
+    int acc = 0;
+    cumu[0] = 0;
+    for (int j = 1; j <= n - 1; ++j) {
+      cumu[j] = acc;
+      acc += j * ((n - 1 - j + DP_TRI_K - 1) / DP_TRI_K);
+    }
+  }
   if (out_on_chip) {
     for (int e = tid; e < p2; e += THREADS) amb_s[e] = 0;
     for (int e = tid; e < c3; e += THREADS) out_s[e] = 0;
@@ -638,8 +660,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 
     // ---- mask phase: rows i paired from both ends for balance.  Only the last word of a tint can
     // hold lanes without a rep; every other chunk skips the masking ----
     const bool tail_chunk = (w0 + nw == words) && (R & 31);
-    if (tail_chunk) dp_mask_phase<THREADS, true>(n, nw, wc, CW, tile, ty, tn, ynm, vmask);
-    else dp_mask_phase<THREADS, false>(n, nw, wc, CW, tile, ty, tn, ynm, vmask);
+    if (tail_chunk) dp_mask_phase<THREADS, true>(n, nw, wc, CW, tile, ty, tn, ynm, vmask, munit, s_n_munit);
+    else dp_mask_phase<THREADS, false>(n, nw, wc, CW, tile, ty, tn, ynm, vmask, munit, s_n_munit);
     __syncthreads();  // masks complete, tile free
     if (tid == 0 && w0 + wc < w_hi) issue(w0 + wc);
     // ---- ins pass: ambiguous reps per pair ----
@@ -660,8 +682,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 
       bool w1 = true;  // every word of the chunk has unit weights only
       for (int w = 0; w < nw; ++w) w1 = w1 && nplanes[w] <= 1;
       int* dst = out_on_chip ? out_s : (tab_g + p2);
-      if (w1) dp_triple_phase<THREADS, true>(n, nw, wc, ynm, planes, nplanes, out_on_chip, dst);
-      else dp_triple_phase<THREADS, false>(n, nw, wc, ynm, planes, nplanes, out_on_chip, dst);
+      if (w1) dp_triple_phase<THREADS, true>(n, nw, wc, ynm, planes, nplanes, cumu, out_on_chip, dst);
+      else dp_triple_phase<THREADS, false>(n, nw, wc, ynm, planes, nplanes, cumu, out_on_chip, dst);
     }
     __syncthreads();  // the next chunk rewrites the weight planes and the masks
   }
