@@ -179,8 +179,13 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------------
 def run_cuda_arm(args):
-    import torch
     rank, local_rank, world = rank_env()
+    cores = os.cpu_count() or 1
+    # torchrun pins OMP_NUM_THREADS=1 in its children; the library's host gather (clip words) and the
+    # native parser use OpenMP, so give every rank its share of the cores
+    os.environ["OMP_NUM_THREADS"] = str(max(1, cores // max(world, 1)))
+    os.environ["NCCL_DEBUG"] = os.environ.get("FRS_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+    import torch
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -188,7 +193,6 @@ def run_cuda_arm(args):
     from freddie_b200.engine import Engine, SegmentParams
     from freddie_b200.pack import pack_tints
 
-    cores = os.cpu_count() or 1
     t0 = time.time()
     tints = make_workload(args.workload, args.scale, 2 + 1000 * rank, max(1, min(16, cores // world)))
     batch = pack_tints(tints).pin()
@@ -307,8 +311,15 @@ def run_cuda_arm(args):
     dom_ms = stage_ms[dom] / args.steps
     ach = alg[dom] / (dom_ms * 1e-3) / 1e9
     stages = {k: dict(ms=round(v / args.steps, 4), launches=stage_launch[k],
-                      alg_GBps=(round(alg[k] / (v / args.steps * 1e-3) / 1e9, 1) if k in alg and v > 0 else None))
+                      alg_GBps=(round(alg[k] / (v / args.steps * 1e-3) / 1e9, 1) if k in alg and v > 0 else None),
+                      hbm_frac=(round(alg[k] / (v / args.steps * 1e-3) / 1e9 / peak, 4) if k in alg and v > 0 else None))
               for k, v in stage_ms.items()}
+    stream_ms = sum(v for k, v in stage_ms.items() if k in alg and k != "dp") / args.steps
+    stream_bytes = sum(b for k, b in alg.items() if k != "dp" and k in stage_ms)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp) and args.workload == "cfg2" and args.scale == 1.0:
+        traffic = json.load(open(tp)).get(dom)
     line = dict(
         metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=t_dev / args.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -321,8 +332,15 @@ def run_cuda_arm(args):
                  clip_words_per_step=st["clip_words"], seq_words_in_batch=st["seq_words"]),
         gpu_launches=launches,
         clocks=clocks,
-        roofline=dict(bound="hbm", kernel=dom, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None,
-                      peak_source=peak_src, alg_bytes_per_launch=alg[dom], ms_per_launch=dom_ms),
+        roofline=dict(bound="hbm", kernel=dom, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic,
+                      peak_source=peak_src, alg_bytes_per_launch=alg[dom], ms_per_launch=dom_ms,
+                      note=("the DP stage is VOTE/LOP3/POPC issue-bound, not HBM-bound: its only HBM traffic is the "
+                            "coverage tile (read once via TMA); see profiles/ for issue-slot utilisation"
+                            if dom == "dp" else None),
+                      streaming_stages=dict(achieved=round(stream_bytes / (stream_ms * 1e-3) / 1e9, 1),
+                                            frac=round(stream_bytes / (stream_ms * 1e-3) / 1e9 / peak, 4),
+                                            ms=round(stream_ms, 4), alg_bytes=stream_bytes,
+                                            what="all HBM-streaming stages together (every stage but dp)")),
         dp_cells_per_sec=tot_cells * args.steps / max(dp_ms * 1e-3, 1e-12),
         dp_read_cells_per_sec=int(sizes["dp_read_cells"]) * args.steps * world / max(dp_ms * 1e-3, 1e-12),
         dp=dict(cells=int(sizes["dp_cells"]), subproblems=int(sizes["n_subproblems"]),

@@ -59,7 +59,7 @@ struct frs_context {
   DBuf b_yraw, b_y, b_sflag, b_bsum, b_cand_flat, b_cand_island, b_island_cand_off, b_tint_cand_off, b_thr, b_vbuf,
       b_leaf_off, b_leaf_len, b_leaf_sum, b_fixed0, b_fixed1, b_fixed_list, b_sub_flag, b_sub_fidx, b_sub_start,
       b_sub_n, b_sub_tint, b_sub_info, b_sub_slabs, b_sz_tab, b_sub_tab_off, b_plan, b_work, b_split_list, b_cursor,
-      b_cov_sz, b_tint_cov_off, b_P, b_tab, b_dpfinal, b_pf_list, b_gbuf, b_pstate, b_final_flat,
+      b_cov_sz, b_tint_cov_off, b_P, b_tab, b_dpfinal, b_ref_list, b_ref_list2, b_gbuf, b_pstate, b_final_flat,
       b_final_pos, b_final_island, b_tint_final_off, b_dig_sz, b_tint_digit_off, b_seg_ty, b_seg_tn, b_digits,
       b_run_cnt, b_run_off, b_runs, b_gap_cnt, b_clip_n, b_clip_words, b_clip_off, b_task_order, b_task_res, b_poly_cls, b_read_gap_off, b_read_head, b_gap_rec, b_counters, b_stats, b_err;
   i64* h_pin = nullptr;  // pinned scratch for small D2H reads
@@ -618,19 +618,25 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
                                           c->b_island_cand_off.as<int>(), c->b_y.as<double>(), prm->mps,
                                           c->b_fixed0.as<u8>(), c->b_fixed1.as<u8>(), d_err);
   LAUNCHED();
-  ENS(b_fixed_list, K * 4);
-  { int r = compact<u8>(c, c->b_fixed1.as<u8>(), K, c->b_fixed_list.as<int>(), 1); if (r) return r; }
-  { int r = read_counters(c, 2); if (r) return r; }   // sync: number of fixed candidates
-  const i64 NF = c->h_pin[1];
-  c->n_fixed = NF;
-
   stage_begin(c, "subproblems");
-  ENS(b_sub_flag, NF);
-  ENS(b_sub_fidx, NF * 4);
-  k_sub_flag<<<cdiv(NF, 256), 256, 0, st>>>((int)NF, c->b_fixed_list.as<int>(), c->b_cand_island.as<int>(),
-                                            c->b_sub_flag.as<u8>());
+  // every subproblem has an interior candidate of its own: at most K/2 of them
+  const i64 NSUB_MAX = K / 2 + 1;
+  ENS(b_sub_start, NSUB_MAX * 4);
+  ENS(b_sub_n, NSUB_MAX * 4);
+  ENS(b_sub_tint, NSUB_MAX * 4);
+  ENS(b_sub_info, NSUB_MAX * 4);
+  ENS(b_sub_slabs, NSUB_MAX * 4);
+  ENS(b_sub_tab_off, NSUB_MAX * 8);
+  ENS(b_plan, PLAN_SLOTS * 8);
+  CK(cudaMemsetAsync(c->b_plan.p, 0, PLAN_SLOTS * 8, st));
+  const int slab_words = c->opt_slab_words;
+  const int keep = c->opt_keep_tables;
+  k_sub_build<<<cdiv(K, 256), 256, 0, st>>>((int)K, c->b_fixed1.as<u8>(), c->b_cand_island.as<int>(),
+                                            c->b_island_cand_off.as<int>(), d_island_tint, d_tint_rep_off, slab_words, keep,
+                                            c->b_sub_start.as<int>(), c->b_sub_n.as<int>(), c->b_sub_tint.as<int>(),
+                                            c->b_sub_info.as<int>(), c->b_sub_slabs.as<int>(), c->b_sub_tab_off.as<i64>(),
+                                            c->b_plan.as<i64>());
   LAUNCHED();
-  { int r = compact<u8>(c, c->b_sub_flag.as<u8>(), NF, c->b_sub_fidx.as<int>(), 2); if (r) return r; }
   // coverage block offsets per tint (rows = candidates of the tint, stride Rp)
   ENS(b_tint_cand_off, (size_t)(T + 1) * 4);
   ENS(b_cov_sz, (size_t)(T + 1) * 8);
@@ -640,49 +646,26 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
   LAUNCHED();
   { int r = scan_exclusive<i64, i64>(c, c->b_cov_sz.as<i64>(), T, c->b_tint_cov_off.as<i64>()); if (r) return r; }
   CK(cudaMemcpyAsync(c->b_counters.as<i64>() + 3, c->b_tint_cov_off.as<i64>() + T, 8, cudaMemcpyDeviceToDevice, st));
-  { int r = read_counters(c, 4); if (r) return r; }   // sync: number of subproblems, coverage size
-  const i64 NSUB = c->h_pin[2];
+  CK(cudaMemcpyAsync(c->b_counters.as<i64>() + 16, c->b_plan.p, PLAN_SLOTS * 8, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(c->b_counters.as<i64>() + 5, d_err, 8, cudaMemcpyDeviceToDevice, st));
+  { int r = read_counters(c, 16 + PLAN_SLOTS); if (r) return r; }   // the ONE sync of this phase: plan, sizes, asserts
+  {
+    const int* he = (const int*)(c->h_pin + 5);
+    if (he[0]) return fail(c, FRS_ERR_ASSERT, "AssertionError: %s [item %d]", deverr_text(he[0]), he[1]);
+  }
+  const i64 NSUB = c->h_pin[16 + PLAN_NSUB];
   const i64 COV = c->h_pin[3];
   c->n_sub = NSUB;
   c->cov_elems = COV;
-
-  const int slab_words = c->opt_slab_words;
-  const int keep = c->opt_keep_tables;
-  i64 tab_total = 0, n_split = 0, dp_cells = 0, dp_read_cells = 0, cls_cnt[DP_CLASSES] = {0, 0, 0, 0, 0, 0};
-  int cls_maxn[DP_CLASSES] = {0, 0, 0, 0, 0, 0};
-  int max_n = 0;
-  if (NSUB > 0) {
-    ENS(b_sub_start, NSUB * 4);
-    ENS(b_sub_n, NSUB * 4);
-    ENS(b_sub_tint, NSUB * 4);
-    ENS(b_sub_info, NSUB * 4);
-    ENS(b_sub_slabs, NSUB * 4);
-    ENS(b_sz_tab, NSUB * 4);
-    ENS(b_sub_tab_off, (NSUB + 1) * 8);
-    ENS(b_plan, PLAN_SLOTS * 8);
-    CK(cudaMemsetAsync(c->b_plan.p, 0, PLAN_SLOTS * 8, st));
-    k_sub_plan<<<cdiv(NSUB, 256), 256, 0, st>>>((int)NSUB, c->b_sub_fidx.as<int>(), c->b_fixed_list.as<int>(),
-                                                c->b_cand_island.as<int>(), d_island_tint, d_tint_rep_off, slab_words, keep,
-                                                c->b_sub_start.as<int>(), c->b_sub_n.as<int>(), c->b_sub_tint.as<int>(),
-                                                c->b_sub_info.as<int>(), c->b_sub_slabs.as<int>(), c->b_sz_tab.as<int>(),
-                                                c->b_plan.as<i64>());
-    LAUNCHED();
-    { int r = scan_exclusive<int, i64>(c, c->b_sz_tab.as<int>(), NSUB, c->b_sub_tab_off.as<i64>()); if (r) return r; }
-    CK(cudaMemcpyAsync(c->b_counters.as<i64>() + 4, c->b_sub_tab_off.as<i64>() + NSUB, 8, cudaMemcpyDeviceToDevice, st));
-    CK(cudaMemcpyAsync(c->b_counters.as<i64>() + 16, c->b_plan.p, PLAN_SLOTS * 8, cudaMemcpyDeviceToDevice, st));
-    { int r = read_counters(c, 32); if (r) return r; }   // sync: work-list and table sizes
-    tab_total = c->h_pin[4];
-    for (int k = 0; k < DP_CLASSES; ++k) {
-      cls_cnt[k] = c->h_pin[16 + PLAN_WORK + k];
-      cls_maxn[k] = (int)c->h_pin[16 + PLAN_MAXN + k];
-    }
-    n_split = c->h_pin[16 + PLAN_SPLIT];
-    dp_cells = c->h_pin[16 + PLAN_CELLS];
-    dp_read_cells = c->h_pin[16 + PLAN_RCELLS];
-    max_n = (int)c->h_pin[16 + PLAN_MAXALL];
+  i64 tab_total = c->h_pin[16 + PLAN_TAB], n_split = c->h_pin[16 + PLAN_SPLIT], dp_cells = c->h_pin[16 + PLAN_CELLS],
+      dp_read_cells = c->h_pin[16 + PLAN_RCELLS], cls_cnt[DP_CLASSES];
+  int cls_maxn[DP_CLASSES];
+  for (int k = 0; k < DP_CLASSES; ++k) {
+    cls_cnt[k] = c->h_pin[16 + PLAN_WORK + k];
+    cls_maxn[k] = (int)c->h_pin[16 + PLAN_MAXN + k];
   }
+  const int max_n = (int)c->h_pin[16 + PLAN_MAXALL];
   c->tab_elems = tab_total;
-  { int r = check_dev_err(c); if (r) return r; }
 
   ENS(b_P, COV * 4);
   stage_begin(c, "coverage");
@@ -767,33 +750,39 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
 
   // ================= phase 3: refine, final positions, digits =================
   stage_begin(c, "refine");
-  ENS(b_pf_list, K * 4);
-  { int r = compact<u8>(c, c->b_dpfinal.as<u8>(), K, c->b_pf_list.as<int>(), 10); if (r) return r; }
-  { int r = read_counters(c, 11); if (r) return r; }  // sync: number of pre-refine finals
-  const i64 NPF = c->h_pin[10];
+  ENS(b_ref_list, K * 8 + 16);
   CK(cudaMemsetAsync(c->b_sflag.p, 0, L, st));
-  k_mark_final<<<cdiv(NPF, 256), 256, 0, st>>>((int)NPF, c->b_pf_list.as<int>(), c->b_cand_flat.as<int>(),
-                                               c->b_sflag.as<u8>());
+  CK(cudaMemsetAsync(c->b_counters.as<i64>() + 10, 0, 8, st));
+  int* d_ref_cnt = (int*)(c->b_counters.as<i64>() + 10);
+  k_final_mark<<<cdiv(K, 256), 256, 0, st>>>((int)K, c->b_dpfinal.as<u8>(), c->b_cand_flat.as<int>(),
+                                             c->b_cand_island.as<int>(), c->b_island_cand_off.as<int>(),
+                                             c->b_sflag.as<u8>(), c->b_ref_list.as<int2>(), d_ref_cnt);
+  LAUNCHED();
+  ENS(b_ref_list2, K * 8 + 16);
+  CK(cudaMemsetAsync(c->b_counters.as<i64>() + 9, 0, 8, st));
+  int* d_ref_cnt2 = (int*)(c->b_counters.as<i64>() + 9);
+  k_refine_filter<<<148 * 8, 256, 0, st>>>(c->b_ref_list.as<int2>(), d_ref_cnt, c->b_yraw.as<int>(),
+                                           c->b_ref_list2.as<int2>(), d_ref_cnt2);
   LAUNCHED();
   ENS(b_gbuf, L * 8);
   ENS(b_pstate, L);
-  k_refine<<<(unsigned)NPF, REF_THREADS, 0, st>>>((int)NPF, c->b_pf_list.as<int>(), c->b_cand_flat.as<int>(),
-                                                  c->b_cand_island.as<int>(), c->b_yraw.as<int>(), d_rw, rr, prm->sigma,
-                                                  c->b_gbuf.as<double>(), c->b_pstate.as<u8>(), c->b_sflag.as<u8>());
+  k_refine<<<148 * 8, REF_THREADS, 0, st>>>(c->b_ref_list2.as<int2>(), d_ref_cnt2, c->b_yraw.as<int>(), d_rw, rr, prm->sigma,
+                                            c->b_gbuf.as<double>(), c->b_pstate.as<u8>(), c->b_sflag.as<u8>());
   LAUNCHED();
 
   stage_begin(c, "finals");
+  // refine adds peaks at least 20 samples apart inside segments longer than 40
+  const i64 NFIN_MAX = K + L / 20 + 16;
   ENS(b_final_flat, (L / 2 + 2 * NI + 16) * 4);
   { int r = compact<u8>(c, c->b_sflag.as<u8>(), L, c->b_final_flat.as<int>(), 11); if (r) return r; }
-  { int r = read_counters(c, 12); if (r) return r; }  // sync: number of final positions
-  const i64 NFIN = c->h_pin[11];
-  ENS(b_final_pos, NFIN * 4);
-  ENS(b_final_island, NFIN * 4);
+  const i64* d_nfin = c->b_counters.as<i64>() + 11;
+  ENS(b_final_pos, NFIN_MAX * 4);
+  ENS(b_final_island, NFIN_MAX * 4);
   ENS(b_tint_final_off, (size_t)(T + 1) * 4);
-  k_final_meta<<<cdiv(NFIN + 1, 256), 256, 0, st>>>((int)NFIN, c->b_final_flat.as<int>(), d_island_sample_off,
-                                                    c->b_island_start.as<int>(), d_island_tint, d_tint_island_off, NI, T,
-                                                    c->b_final_pos.as<int>(), c->b_final_island.as<int>(),
-                                                    c->b_tint_final_off.as<int>());
+  k_final_meta<<<148 * 4, 256, 0, st>>>(d_nfin, c->b_final_flat.as<int>(), d_island_sample_off,
+                                        c->b_island_start.as<int>(), d_island_tint, d_tint_island_off, NI, T,
+                                        c->b_final_pos.as<int>(), c->b_final_island.as<int>(),
+                                        c->b_tint_final_off.as<int>());
   LAUNCHED();
   ENS(b_dig_sz, (size_t)(T + 1) * 8);
   ENS(b_tint_digit_off, (size_t)(T + 1) * 8);
@@ -801,13 +790,15 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
   LAUNCHED();
   { int r = scan_exclusive<i64, i64>(c, c->b_dig_sz.as<i64>(), T, c->b_tint_digit_off.as<i64>()); if (r) return r; }
   CK(cudaMemcpyAsync(c->b_counters.as<i64>() + 12, c->b_tint_digit_off.as<i64>() + T, 8, cudaMemcpyDeviceToDevice, st));
-  ENS(b_seg_ty, NFIN * 4);
-  ENS(b_seg_tn, NFIN * 4);
-  k_seg_cuts<<<cdiv(NFIN, 256), 256, 0, st>>>((int)NFIN, c->b_final_flat.as<int>(), c->b_final_island.as<int>(), d_tbl,
-                                              prm->thr_table_len, prm->tp, c->b_seg_ty.as<int>(), c->b_seg_tn.as<int>());
+  ENS(b_seg_ty, NFIN_MAX * 4);
+  ENS(b_seg_tn, NFIN_MAX * 4);
+  k_seg_cuts<<<148 * 4, 256, 0, st>>>(d_nfin, c->b_final_flat.as<int>(), c->b_final_island.as<int>(), d_tbl,
+                                      prm->thr_table_len, prm->tp, c->b_seg_ty.as<int>(), c->b_seg_tn.as<int>());
   LAUNCHED();
-  { int r = read_counters(c, 13); if (r) return r; }  // sync: digit bytes
+  { int r = read_counters(c, 13); if (r) return r; }  // sync: final positions, digit bytes
+  const i64 NFIN = c->h_pin[11];
   const i64 NDIG = c->h_pin[12];
+  if (NFIN > NFIN_MAX) return fail(c, FRS_ERR_LIMIT, "internal: more final positions than the refine bound allows");
 
   ENS(b_digits, NDIG);
   stage_begin(c, "digits");
@@ -952,7 +943,7 @@ int frs_get_intermediate(frs_context* c, int which, void* dst, size_t cap, size_
     case FRS_TAP_COVERAGE: src = c->b_P.p; sz = c->cov_elems * 4; break;
     case FRS_TAP_DP_TABLES: src = c->b_tab.p; sz = c->tab_elems * 4; break;
     case FRS_TAP_COV_OFF: src = c->b_tint_cov_off.p; sz = (size_t)(c->hb.n_tints + 1) * 8; break;
-    case FRS_TAP_SUB_TAB_OFF: src = c->b_sub_tab_off.p; sz = NS ? (NS + 1) * 8 : 0; break;
+    case FRS_TAP_SUB_TAB_OFF: src = c->b_sub_tab_off.p; sz = NS * 8; break;
     default: return fail(c, FRS_ERR_ARG, "frs_get_intermediate: unknown tap %d", which);
   }
   *bytes = sz;

@@ -113,20 +113,6 @@ __global__ void k_fixed_b(int n_cand, const int* __restrict__ cand_flat, const i
   }
 }
 
-// subproblems: consecutive fixed candidates (a, b) of one island with at least one interior
-// candidate.  flag over the fixed list, then compaction gives the subproblem list.
-__global__ void k_sub_flag(int n_fixed, const int* __restrict__ fixed_list, const int* __restrict__ cand_island,
-                           u8* __restrict__ flag) {
-  int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= n_fixed) return;
-  u8 v = 0;
-  if (f + 1 < n_fixed) {
-    int a = fixed_list[f], b = fixed_list[f + 1];
-    v = (cand_island[a] == cand_island[b] && b - a >= 2) ? 1 : 0;
-  }
-  flag[f] = v;
-}
-
 // ---------------------------------------------------------------------------------------------
 // Subproblem plan.  Every subproblem gets a size class (by its candidate count n) and a mode:
 //   fused : all read reps of the tint fit one slab (words <= slab_words) and n <= DP_SMEM_MAX_N.
@@ -150,7 +136,9 @@ __global__ void k_sub_flag(int n_fixed, const int* __restrict__ fixed_list, cons
 #define PLAN_CELLS 13   // sum C(n,3)
 #define PLAN_RCELLS 14  // sum C(n,3) * R
 #define PLAN_MAXALL 15  // largest n
-#define PLAN_SLOTS 16
+#define PLAN_NSUB 16    // number of subproblems
+#define PLAN_TAB 17     // int32 elements of the global DP tables
+#define PLAN_SLOTS 20
 
 struct DpWork { int sub; int slab; };
 
@@ -183,48 +171,71 @@ __device__ __forceinline__ int warp_max_i(int v) {
   return v;
 }
 
+// Subproblems = consecutive fixed candidates (a, b) of one island with at least one interior
+// candidate (:571-596).  One thread per candidate: a fixed candidate looks for the next fixed one
+// (at most ~mps steps after break_large_problems) and, if there is an interior, appends the
+// subproblem to the list (slot from a warp-aggregated atomic: the ORDER of the list is arbitrary, the
+// results do not depend on it).  Per subproblem: class, slab size, CTA count, table block.
 // sub_info[p] = class | fused << 8 | slab_words << 16;  sub_slabs[p] = CTAs of the subproblem.
-// sz_tab[p] = int32 elements of the subproblem's global table block (pair-indexed ins [n(n-1)/2]
-// followed by out [C(n,3)]), 0 when the tables stay on chip.
-__global__ void k_sub_plan(int n_sub, const int* __restrict__ sub_fidx, const int* __restrict__ fixed_list,
-                           const int* __restrict__ cand_island, const int* __restrict__ island_tint,
-                           const int* __restrict__ tint_rep_off, int slab_cap, int keep_tables,
-                           int* __restrict__ sub_start, int* __restrict__ sub_n, int* __restrict__ sub_tint,
-                           int* __restrict__ sub_info, int* __restrict__ sub_slabs, int* __restrict__ sz_tab,
-                           i64* __restrict__ plan) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
+// sub_tab_off[p] = first int32 of the subproblem's global table block (pair-indexed ins [n(n-1)/2]
+// followed by out [C(n,3)]); only subproblems whose tables leave the chip own one.
+__global__ void k_sub_build(int n_cand, const u8* __restrict__ fixed, const int* __restrict__ cand_island,
+                            const int* __restrict__ island_cand_off, const int* __restrict__ island_tint,
+                            const int* __restrict__ tint_rep_off, int slab_cap, int keep_tables,
+                            int* __restrict__ sub_start, int* __restrict__ sub_n, int* __restrict__ sub_tint,
+                            int* __restrict__ sub_info, int* __restrict__ sub_slabs, i64* __restrict__ sub_tab_off,
+                            i64* __restrict__ plan) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  int cls = -1, slabs = 0, n = 0, split = 0;
-  long long t3 = 0, rc = 0;
-  if (p < n_sub) {
-    int f = sub_fidx[p];
-    int a = fixed_list[f], b = fixed_list[f + 1];
-    n = b - a + 1;
-    int t = island_tint[cand_island[a]];
-    int R = tint_rep_off[t + 1] - tint_rep_off[t];
-    int words = (R + 31) >> 5;
-    int sw = dp_slab_words(n, words, slab_cap);
-    int fused = (n <= DP_SMEM_MAX_N && words <= sw) ? 1 : 0;
-    cls = dp_class_of(n, words, fused);
-    slabs = fused ? 1 : (words + sw - 1) / sw;
-    split = !fused;
-    t3 = (long long)n * (n - 1) * (n - 2) / 6;
-    rc = t3 * R;
-    sub_start[p] = a;
+  int cls = -1, slabs = 0, n = 0, split = 0, info = 0, t = 0;
+  long long t3 = 0, rc = 0, sz = 0;
+  bool has = false;
+  if (q < n_cand && fixed[q]) {
+    const int isl = cand_island[q];
+    const int c1 = island_cand_off[isl + 1];
+    if (q < c1 - 1) {
+      int e = q + 1;
+      while (!fixed[e]) ++e;  // the island's last candidate is fixed
+      if (e - q >= 2) {
+        has = true;
+        n = e - q + 1;
+        t = island_tint[isl];
+        const int R = tint_rep_off[t + 1] - tint_rep_off[t];
+        const int words = (R + 31) >> 5;
+        const int sw = dp_slab_words(n, words, slab_cap);
+        const int fused = (n <= DP_SMEM_MAX_N && words <= sw) ? 1 : 0;
+        cls = dp_class_of(n, words, fused);
+        slabs = fused ? 1 : (words + sw - 1) / sw;
+        split = !fused;
+        t3 = (long long)n * (n - 1) * (n - 2) / 6;
+        rc = t3 * R;
+        info = cls | (fused << 8) | (sw << 16);
+        sz = (fused && !keep_tables) ? 0 : (long long)n * (n - 1) / 2 + t3;
+      }
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, has);
+  if (m == 0) return;
+  int base = 0;
+  if (lane == __ffs(m) - 1) base = (int)atomicAdd((unsigned long long*)&plan[PLAN_NSUB], (unsigned long long)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (has) {
+    const int p = base + __popc(m & ((1u << lane) - 1u));
+    sub_start[p] = q;
     sub_n[p] = n;
     sub_tint[p] = t;
-    sub_info[p] = cls | (fused << 8) | (sw << 16);
+    sub_info[p] = info;
     sub_slabs[p] = slabs;
-    sz_tab[p] = (fused && !keep_tables) ? 0 : (int)(n * (n - 1) / 2 + t3);
+    sub_tab_off[p] = sz ? (i64)atomicAdd((unsigned long long*)&plan[PLAN_TAB], (unsigned long long)sz) : 0;
   }
   // warp-aggregated statistics
 #pragma unroll
   for (int c = 0; c < DP_CLASSES; ++c) {
     long long s = warp_sum_ll(cls == c ? slabs : 0);
-    int m = warp_max_i(cls == c ? n : 0);
+    int mx = warp_max_i(cls == c ? n : 0);
     if (lane == 0 && s) {
       atomicAdd((unsigned long long*)&plan[PLAN_WORK + c], (unsigned long long)s);
-      atomicMax((long long*)&plan[PLAN_MAXN + c], (long long)m);
+      atomicMax((long long*)&plan[PLAN_MAXN + c], (long long)mx);
     }
   }
   long long s_split = warp_sum_ll(split), s_t3 = warp_sum_ll(t3), s_rc = warp_sum_ll(rc);

@@ -5,11 +5,22 @@
 #pragma once
 #include "common.cuh"
 
-// mark the pre-refine finals (candidates kept by fixed | DP) in the per-sample flag array
-__global__ void k_mark_final(int n, const int* __restrict__ pf_list, const int* __restrict__ cand_flat,
-                             u8* __restrict__ sflag) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < n) sflag[cand_flat[pf_list[e]]] = 1;
+// Pre-refine finals = candidates kept by fixed | DP.  One thread per candidate: mark its sample in the
+// per-sample flag array and, if the segment up to the next final of the island is longer than 40
+// samples (:252), append it to the refine work list (arbitrary order).
+__global__ void k_final_mark(int n_cand, const u8* __restrict__ dpfinal, const int* __restrict__ cand_flat,
+                             const int* __restrict__ cand_island, const int* __restrict__ island_cand_off,
+                             u8* __restrict__ sflag, int2* __restrict__ ref_list, int* __restrict__ ref_cnt) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_cand || !dpfinal[q]) return;
+  const int a = cand_flat[q];
+  sflag[a] = 1;
+  const int c1 = island_cand_off[cand_island[q] + 1];
+  if (q >= c1 - 1) return;
+  int e = q + 1;
+  while (!dpfinal[e]) ++e;  // the island's last candidate is final
+  const int b = cand_flat[e];
+  if (b - a > 2 * 20) ref_list[atomicAdd(ref_cnt, 1)] = make_int2(a, b);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -24,21 +35,30 @@ __global__ void k_mark_final(int n, const int* __restrict__ pf_list, const int* 
 #define REF_THREADS 128
 #define REF_SKIP 20
 
-__global__ void __launch_bounds__(REF_THREADS) k_refine(int n_pf, const int* __restrict__ pf_list,
-                                                       const int* __restrict__ cand_flat,
-                                                       const int* __restrict__ cand_island,
-                                                       const int* __restrict__ y_raw, const double* __restrict__ rw,
-                                                       int rad, double sigma, double* __restrict__ gbuf,
-                                                       u8* __restrict__ pstate, u8* __restrict__ sflag) {
-  __shared__ int sm_red[REF_THREADS / 32];
-  __shared__ int sm_flag;
-  const int e = blockIdx.x;
-  if (e + 1 >= n_pf) return;
-  const int qa = pf_list[e], qb = pf_list[e + 1];
-  if (cand_island[qa] != cand_island[qb]) return;
-  const int a = cand_flat[qa], b = cand_flat[qb];
+// refine, stage A: one warp per candidate segment sums the inner raw signal (:256-257: skip if the sum
+// is below 20).  Splice sites are sparse, so almost every segment stops here; the survivors go to the
+// list of stage B (one CTA per segment).
+__global__ void k_refine_filter(const int2* __restrict__ in_list, const int* __restrict__ in_cnt,
+                                const int* __restrict__ y_raw, int2* __restrict__ out_list, int* __restrict__ out_cnt) {
+  const int lane = threadIdx.x & 31;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  const int n = *in_cnt;
+  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n; e += nw) {
+    const int2 seg = in_list[e];
+    long long s = 0;
+    for (int x = seg.x + REF_SKIP + lane; x < seg.y - REF_SKIP; x += 32) s += y_raw[x];
+    int si = (int)min(s, (long long)20);  // non-negative terms: only "total < 20" matters
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) si += __shfl_xor_sync(0xffffffffu, si, o);
+    if (lane == 0 && si >= 20) out_list[atomicAdd(out_cnt, 1)] = seg;
+  }
+}
+
+__device__ void k_refine_segment(const int a, const int b, const int* __restrict__ y_raw,
+                                 const double* __restrict__ rw, int rad, double sigma, double* __restrict__ gbuf,
+                                 u8* __restrict__ pstate, u8* __restrict__ sflag, int* sm_red, int* sm_flag_p) {
   const int len = b - a;
-  if (len <= 2 * REF_SKIP) return;
+#define sm_flag (*sm_flag_p)
   const int tid = threadIdx.x;
   // sum of the inner raw signal (integers)
   long long s = 0;
@@ -124,24 +144,37 @@ __global__ void __launch_bounds__(REF_THREADS) k_refine(int n_pf, const int* __r
     if (!(sum < 20.0)) sflag[a + x] = 1;
   }
 }
+#undef sm_flag
+
+__global__ void __launch_bounds__(REF_THREADS) k_refine(const int2* __restrict__ ref_list, const int* __restrict__ ref_cnt,
+                                                       const int* __restrict__ y_raw, const double* __restrict__ rw,
+                                                       int rad, double sigma, double* __restrict__ gbuf,
+                                                       u8* __restrict__ pstate, u8* __restrict__ sflag) {
+  __shared__ int sm_red[REF_THREADS / 32];
+  __shared__ int sm_flag;
+  const int n_work = *ref_cnt;
+  for (int e = blockIdx.x; e < n_work; e += gridDim.x) {
+    k_refine_segment(ref_list[e].x, ref_list[e].y, y_raw, rw, rad, sigma, gbuf, pstate, sflag, sm_red, &sm_flag);
+    __syncthreads();
+  }
+}
 
 // after compaction of the per-sample final flags: positions + per-tint offsets + island of each final
-__global__ void k_final_meta(int n_final, const int* __restrict__ final_flat, const int* __restrict__ island_sample_off,
-                             const int* __restrict__ island_start, const int* __restrict__ island_tint,
-                             const int* __restrict__ tint_island_off, int n_islands, int n_tints,
-                             int* __restrict__ final_pos, int* __restrict__ final_island,
+__global__ void k_final_meta(const i64* __restrict__ n_final_p, const int* __restrict__ final_flat,
+                             const int* __restrict__ island_sample_off, const int* __restrict__ island_start,
+                             const int* __restrict__ island_tint, const int* __restrict__ tint_island_off, int n_islands,
+                             int n_tints, int* __restrict__ final_pos, int* __restrict__ final_island,
                              int* __restrict__ tint_final_off) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_final) {
-    if (e == n_final) tint_final_off[n_tints] = n_final;
-    return;
+  const int n_final = (int)*n_final_p;  // device-side count: no host round trip before this launch
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e <= n_final; e += gridDim.x * blockDim.x) {
+    if (e == n_final) { tint_final_off[n_tints] = n_final; break; }
+    int f = final_flat[e];
+    int isl = upper_row(island_sample_off, n_islands, f);
+    final_island[e] = isl;
+    final_pos[e] = island_start[isl] + (f - island_sample_off[isl]);
+    int t = island_tint[isl];
+    if (f == island_sample_off[isl] && isl == tint_island_off[t]) tint_final_off[t] = e;
   }
-  int f = final_flat[e];
-  int isl = upper_row(island_sample_off, n_islands, f);
-  final_island[e] = isl;
-  final_pos[e] = island_start[isl] + (f - island_sample_off[isl]);
-  int t = island_tint[isl];
-  if (f == island_sample_off[isl] && isl == tint_island_off[t]) tint_final_off[t] = e;
 }
 
 // per tint: digit block size = n_reps * (n_final - 1)
@@ -154,16 +187,17 @@ __global__ void k_digit_sizes(int n_tints, const int* __restrict__ tint_rep_off,
 }
 
 // per final e (segment e -> e+1): integer cuts of the segment, or a separator marker
-__global__ void k_seg_cuts(int n_final, const int* __restrict__ final_flat, const int* __restrict__ final_island,
-                           const double* __restrict__ tbl, int tbl_len, double tp, int* __restrict__ seg_ty,
-                           int* __restrict__ seg_tn) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_final) return;
-  int ty = 0x7fffffff, tn = -2;  // tn == -2 marks "no segment" (island separator or tint end)
-  if (e + 1 < n_final && final_island[e] == final_island[e + 1])
-    length_cuts(final_flat[e + 1] - final_flat[e] + 1, tbl, tbl_len, tp, ty, tn);
-  seg_ty[e] = ty;
-  seg_tn[e] = tn;
+__global__ void k_seg_cuts(const i64* __restrict__ n_final_p, const int* __restrict__ final_flat,
+                           const int* __restrict__ final_island, const double* __restrict__ tbl, int tbl_len, double tp,
+                           int* __restrict__ seg_ty, int* __restrict__ seg_tn) {
+  const int n_final = (int)*n_final_p;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_final; e += gridDim.x * blockDim.x) {
+    int ty = 0x7fffffff, tn = -2;  // tn == -2 marks "no segment" (island separator or tint end)
+    if (e + 1 < n_final && final_island[e] == final_island[e + 1])
+      length_cuts(final_flat[e + 1] - final_flat[e] + 1, tbl, tbl_len, tp, ty, tn);
+    seg_ty[e] = ty;
+    seg_tn[e] = tn;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

