@@ -248,7 +248,7 @@ def run_cuda_arm(args):
     # pinned host memory, runs, and downloads the results into pinned host memory.  Two library
     # contexts (two host threads) take alternate steps so that the copies of one step overlap the
     # kernels of the other, exactly as the CLI driver runs consecutive batches. ----
-    n_lanes = 2
+    n_lanes = int(os.environ.get("FRS_E2E_LANES", "3"))
     lanes = []
     for _ in range(n_lanes):
         e2 = Engine(local_rank)
@@ -327,7 +327,7 @@ def run_cuda_arm(args):
         config=dict(workload=WORKLOADS[args.workload], scale=args.scale, reads_per_gpu=n_reads, tints_per_gpu=len(tints),
                     l2="flushed between timed steps (256 MiB memset)", params="defaults (sd=5 tp=0.9 vf=3 mps=50 lo=3)"),
         e2e=dict(value=e2e_v, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                 timing="wall clock around K steps, synchronize on both sides; 2 contexts take alternate steps",
+                 timing="wall clock around K steps, synchronize on both sides; %d contexts take alternate steps" % n_lanes,
                  serial_value=tot_reads * args.steps / t_e2e_serial,
                  clip_words_per_step=st["clip_words"], seq_words_in_batch=st["seq_words"]),
         gpu_launches=launches,

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -54,7 +55,7 @@ struct frs_context {
       b_rep_iv_off, b_rep_weight, b_rep_fs, b_rep_fe, b_rep_tint, b_read_rep, b_read_strand, b_read_len,
       b_read_iv_off, b_read_seq_off, b_read_tint, b_riv_ts, b_riv_te, b_riv_qs, b_riv_qe, b_riv_cig_off, b_cigar,
       b_seq_a, b_seq_t;
-  DBuf b_sig_work, b_tiles, b_cov_tiles, b_dig_tiles;
+  DBuf b_sig_work, b_tiles, b_cov_tiles, b_dig_tiles, b_tint_order;
   DBuf b_params;  // thr table | gauss w | refine w
   DBuf b_yraw, b_y, b_sflag, b_bsum, b_cand_flat, b_cand_island, b_island_cand_off, b_tint_cand_off, b_thr, b_vbuf,
       b_leaf_off, b_leaf_len, b_leaf_sum, b_fixed0, b_fixed1, b_fixed_list, b_sub_flag, b_sub_fidx, b_sub_start,
@@ -449,6 +450,16 @@ int frs_upload(frs_context* c, const frs_batch* b) {
     for (int r = 0; r < Rp; r += COV_THREADS) cov_tiles.push_back(RepTile{t, r});
     for (int r = 0; r < R; r += DIG_REPS) dig_tiles.push_back(RepTile{t, r});
   }
+  // tints by decreasing sample count (per-tint CTAs: start the long ones first)
+  std::vector<int> tint_order(T);
+  for (int t = 0; t < T; ++t) tint_order[t] = t;
+  {
+    const int* io = b->tint_island_off;
+    const int* so = b->island_sample_off;
+    std::stable_sort(tint_order.begin(), tint_order.end(), [&](int x, int y) {
+      return so[io[x + 1]] - so[io[x]] > so[io[y + 1]] - so[io[y]];
+    });
+  }
   c->n_sig_work = (int)sig.size();
   c->n_tiles = (int)tiles.size();
   c->n_cov_tiles = (int)cov_tiles.size();
@@ -496,6 +507,7 @@ int frs_upload(frs_context* c, const frs_batch* b) {
   k_owner_tables<<<cdiv((i64)NI + NR + N, 256), 256, 0, c->stream>>>(
       T, NI, NR, N, c->b_tint_island_off.as<int>(), c->b_tint_rep_off.as<int>(), c->b_tint_read_off.as<int>(),
       c->b_island_tint.as<int>(), c->b_rep_tint.as<int>(), c->b_read_tint.as<int>());
+  H2D(b_tint_order, tint_order.data(), (size_t)T * 4);
   H2D(b_sig_work, sig.data(), sig.size() * sizeof(SigWork));
   H2D(b_tiles, tiles.data(), tiles.size() * sizeof(TileWork));
   H2D(b_cov_tiles, cov_tiles.data(), cov_tiles.size() * sizeof(RepTile));
@@ -591,7 +603,7 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
     ENS(b_leaf_len, nl * 4);
     ENS(b_leaf_sum, nl * 8);
   }
-  k_threshold<<<T, THR_THREADS, 0, st>>>(d_tint_island_off, d_island_sample_off, c->b_y.as<double>(), prm->vf,
+  k_threshold<<<T, THR_THREADS, 0, st>>>(c->b_tint_order.as<int>(), d_tint_island_off, d_island_sample_off, c->b_y.as<double>(), prm->vf,
                                          c->b_vbuf.as<double>(), c->b_leaf_off.as<int>(), c->b_leaf_len.as<int>(),
                                          c->b_leaf_sum.as<double>(), c->b_thr.as<double>());
   LAUNCHED();

@@ -283,7 +283,8 @@ __device__ double pw_combine(int n, const double* leaf_sum) {
   return ret;
 }
 
-__global__ void __launch_bounds__(THR_THREADS) k_threshold(const int* __restrict__ tint_island_off,
+__global__ void __launch_bounds__(THR_THREADS) k_threshold(const int* __restrict__ tint_order,
+                                                          const int* __restrict__ tint_island_off,
                                                           const int* __restrict__ island_sample_off,
                                                           const double* __restrict__ y, double vf,
                                                           double* __restrict__ vbuf, int* __restrict__ leaf_off,
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(THR_THREADS) k_threshold(const int* __restrict
   __shared__ int sm_scan[40];
   __shared__ int sm_nl;
   __shared__ double sm_mean;
-  const int t = blockIdx.x;
+  const int t = tint_order[blockIdx.x];  // largest tints first: the longest CTA must not start last
   const int s0 = island_sample_off[tint_island_off[t]];
   const int s1 = island_sample_off[tint_island_off[t + 1]];
   // ordered compaction of positives into vbuf[s0 ...]: 8 consecutive samples per thread, one block
