@@ -27,7 +27,10 @@ FULL = [
 
 
 def full(path):
-    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
+    if path.endswith(".csv"):  # already exported on the GPU box: ncu -i x.ncu-rep --page raw --csv > x.csv
+        txt = open(path).read()
+    else:
+        txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units = rows[0], rows[1]
     for r in rows[2:]:
