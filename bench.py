@@ -111,9 +111,9 @@ def algorithmic_bytes(counts: dict, sizes: dict, cov_elems: int) -> dict:
     dig = sizes["n_digit_bytes"]
     return {
         "signal": 8 * I + 8 * L,
-        "gauss": 16 * L,
-        "candidates": 8 * L,
-        "threshold": 8 * L,
+        # k_phase1 fuses the Gaussian (a4: 16 L), the candidate peaks (a6: 8 L) and the ordered
+        # compaction of the positive samples for the variance threshold (a5: 8 L) into one pass
+        "smooth": 32 * L,
         "coverage": 8 * I + 4 * cov_elems,
         "dp": 4 * cov_elems + 4 * R,
         "refine": 8 * L,

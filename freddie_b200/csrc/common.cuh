@@ -146,23 +146,63 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const TIn* __restri
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = (TOut)bsum[gridDim.x];
 }
 
-// idx_out[rank] = i for every i with flags[i] != 0 (ascending)
-template <typename TIn>
-__global__ void __launch_bounds__(SCAN_THREADS) k_compact(const TIn* __restrict__ flags, i64 n,
-                                                         const i64* __restrict__ bsum, int* __restrict__ idx_out) {
+// short arrays (per-tint tables): one CTA, one launch.  out[i] = exclusive prefix, out[n] = total
+#define SCAN_SMALL_MAX 65536
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(1024) k_scan_small(const TIn* __restrict__ in, int n, TOut* __restrict__ out) {
   __shared__ i64 sm[40];
-  i64 base = (i64)blockIdx.x * SCAN_TILE + (i64)threadIdx.x * SCAN_ITEMS;
-  int f[SCAN_ITEMS];
+  const int per = (n + 1023) / 1024;
+  const int i0 = min(n, (int)threadIdx.x * per), i1 = min(n, i0 + per);
   i64 s = 0;
-#pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; ++k) {
-    f[k] = (base + k < n) ? (flags[base + k] != 0) : 0;
-    s += f[k];
+  for (int i = i0; i < i1; ++i) s += (i64)in[i];
+  i64 tot;
+  i64 ex = block_exclusive_scan<i64>(s, &tot, sm);
+  for (int i = i0; i < i1; ++i) {
+    const i64 v = (i64)in[i];
+    out[i] = (TOut)ex;
+    ex += v;
   }
-  i64 ex = block_exclusive_scan<i64>(s, (i64*)nullptr, sm) + bsum[blockIdx.x];
-#pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; ++k) {
-    if (f[k]) idx_out[ex++] = (int)(base + k);
+  if (threadIdx.x == 0) out[n] = (TOut)tot;
+}
+
+// byte-flag compaction, idx_out[rank] = i for every i with flags[i] != 0 (ascending): 16 flags per
+// thread from one 16-byte load
+#define FLAG_ITEMS 16
+#define FLAG_TILE (SCAN_THREADS * FLAG_ITEMS)
+__device__ __forceinline__ uint4 flag_load16(const u8* __restrict__ flags, i64 base, i64 n) {
+  if (base + FLAG_ITEMS <= n) return *reinterpret_cast<const uint4*>(flags + base);  // base is a multiple of 16
+  u32 w[4] = {0u, 0u, 0u, 0u};
+  for (int k = 0; k < FLAG_ITEMS; ++k)
+    if (base + k < n && flags[base + k]) w[k >> 2] |= 1u << ((k & 3) * 8);
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ u32 flag_bits16(uint4 v) {  // bit k = flag k != 0
+  auto nzb = [](u32 x) -> u32 {  // 4 bytes -> 4 bits
+    u32 m = (x | (x >> 4)) & 0x0f0f0f0fu;
+    m = (m | (m >> 2)) & 0x03030303u;
+    m = (m | (m >> 1)) & 0x01010101u;
+    return (m | (m >> 7) | (m >> 14) | (m >> 21)) & 0xfu;
+  };
+  return nzb(v.x) | (nzb(v.y) << 4) | (nzb(v.z) << 8) | (nzb(v.w) << 12);
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_flag_sums(const u8* __restrict__ flags, i64 n, i64* __restrict__ bsum) {
+  __shared__ int sm[40];
+  const i64 base = (i64)blockIdx.x * FLAG_TILE + (i64)threadIdx.x * FLAG_ITEMS;
+  const int s = (base < n) ? __popc(flag_bits16(flag_load16(flags, base, n))) : 0;
+  int tot;
+  block_exclusive_scan<int>(s, &tot, sm);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_flag_compact(const u8* __restrict__ flags, i64 n,
+                                                              const i64* __restrict__ bsum, int* __restrict__ idx_out) {
+  __shared__ int sm[40];
+  const i64 base = (i64)blockIdx.x * FLAG_TILE + (i64)threadIdx.x * FLAG_ITEMS;
+  u32 bits = (base < n) ? flag_bits16(flag_load16(flags, base, n)) : 0u;
+  i64 ex = (i64)block_exclusive_scan<int>(__popc(bits), (int*)nullptr, sm) + bsum[blockIdx.x];
+  while (bits) {
+    const int k = __ffs(bits) - 1;
+    bits &= bits - 1;
+    idx_out[ex++] = (int)(base + k);
   }
 }
 

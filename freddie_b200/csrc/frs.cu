@@ -58,11 +58,11 @@ struct frs_context {
   DBuf b_sig_work, b_tiles, b_cov_tiles, b_dig_tiles, b_tint_order;
   DBuf b_params;  // thr table | gauss w | refine w
   DBuf b_yraw, b_y, b_sflag, b_bsum, b_cand_flat, b_cand_island, b_island_cand_off, b_tint_cand_off, b_thr, b_vbuf,
-      b_leaf_off, b_leaf_len, b_leaf_sum, b_fixed0, b_fixed1, b_fixed_list, b_sub_flag, b_sub_fidx, b_sub_start,
+      b_leaf_off, b_leaf_len, b_leaf_sum, b_tint_pos_off, b_tile_state, b_fixed0, b_fixed1, b_fixed_list, b_sub_flag, b_sub_fidx, b_sub_start,
       b_sub_n, b_sub_tint, b_sub_info, b_sub_slabs, b_sz_tab, b_sub_tab_off, b_plan, b_work, b_split_list, b_cursor,
       b_cov_sz, b_tint_cov_off, b_P, b_tab, b_dpfinal, b_ref_list, b_ref_list2, b_gbuf, b_pstate, b_final_flat,
       b_final_pos, b_final_island, b_tint_final_off, b_dig_sz, b_tint_digit_off, b_seg_ty, b_seg_tn, b_digits,
-      b_run_cnt, b_run_off, b_runs, b_gap_cnt, b_clip_n, b_clip_words, b_clip_off, b_task_order, b_task_res, b_poly_cls, b_read_gap_off, b_read_head, b_gap_rec, b_counters, b_stats, b_err;
+      b_run_cnt, b_run_off, b_runs, b_gap_cnt, b_clip_n, b_clip_words, b_clip_off, b_task_order, b_task_res, b_poly_cls, b_poly_flag, b_read_gap_off, b_read_head, b_gap_rec, b_counters, b_stats, b_err;
   i64* h_pin = nullptr;  // pinned scratch for small D2H reads
   // results of the last run
   frs_result_sizes sizes;
@@ -78,7 +78,7 @@ struct frs_context {
   const u32* h_seq_t = nullptr;
   void* h_stage = nullptr;       // pinned: clip_n (D2H), clip_off + gathered words (H2D)
   size_t h_stage_cap = 0;
-  i64 st_h2d_upload = 0, st_h2d_run = 0, st_d2h_run = 0, st_poly_tasks = 0, st_clip_words = 0;
+  i64 st_h2d_upload = 0, st_h2d_run = 0, st_d2h_run = 0, st_poly_tasks = 0, st_poly_long = 0, st_clip_words = 0;
   // timing
   Stage stages[FRS_MAX_STAGES];
   int n_stages = 0, cur_stage = -1, launch_count = 0;
@@ -157,6 +157,10 @@ static inline int cdiv(i64 a, i64 b) { return (int)((a + b - 1) / b); }
 // device-wide helpers ------------------------------------------------------------------------
 template <typename TIn, typename TOut>
 static int scan_exclusive(frs_context* c, const TIn* in, i64 n, TOut* out) {
+  if (n <= SCAN_SMALL_MAX && (const void*)in != (const void*)out) {
+    k_scan_small<TIn, TOut><<<1, 1024, 0, c->stream>>>(in, (int)n, out); LAUNCHED();
+    return 0;
+  }
   int nb = cdiv(n > 0 ? n : 1, SCAN_TILE);
   ENS(b_bsum, (size_t)(nb + 1) * 8);
   i64* bs = c->b_bsum.as<i64>();
@@ -165,15 +169,14 @@ static int scan_exclusive(frs_context* c, const TIn* in, i64 n, TOut* out) {
   k_scan_apply<TIn, TOut><<<nb, SCAN_THREADS, 0, c->stream>>>(in, n, bs, out); LAUNCHED();
   return 0;
 }
-// compaction; the count ends up in bsum[nb] and is copied to counters[slot]
-template <typename TIn>
-static int compact(frs_context* c, const TIn* flags, i64 n, int* idx_out, int counter_slot) {
-  int nb = cdiv(n > 0 ? n : 1, SCAN_TILE);
+// compaction of byte flags; the count ends up in bsum[nb] and is copied to counters[slot]
+static int compact_flags(frs_context* c, const u8* flags, i64 n, int* idx_out, int counter_slot) {
+  int nb = cdiv(n > 0 ? n : 1, FLAG_TILE);
   ENS(b_bsum, (size_t)(nb + 1) * 8);
   i64* bs = c->b_bsum.as<i64>();
-  k_scan_block_sums<TIn><<<nb, SCAN_THREADS, 0, c->stream>>>(flags, n, bs); LAUNCHED();
+  k_flag_sums<<<nb, SCAN_THREADS, 0, c->stream>>>(flags, n, bs); LAUNCHED();
   k_scan_bsums<<<1, 1024, 0, c->stream>>>(bs, nb); LAUNCHED();
-  k_compact<TIn><<<nb, SCAN_THREADS, 0, c->stream>>>(flags, n, bs, idx_out); LAUNCHED();
+  k_flag_compact<<<nb, SCAN_THREADS, 0, c->stream>>>(flags, n, bs, idx_out); LAUNCHED();
   CK(cudaMemcpyAsync(c->b_counters.as<i64>() + counter_slot, bs + nb, 8, cudaMemcpyDeviceToDevice, c->stream));
   return 0;
 }
@@ -196,9 +199,11 @@ static const char* deverr_text(int code) {
   }
 }
 static int check_dev_err(frs_context* c) {
-  int h[2];
-  CK(cudaMemcpyAsync(h, c->b_err.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  int* h = (int*)(c->h_pin + 60);  // pinned scratch: [code, item, poly tasks, long poly tasks]
+  CK(cudaMemcpyAsync(h, c->b_err.p, 16, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  c->st_poly_tasks = h[2];
+  c->st_poly_long = h[3];
   if (h[0]) return fail(c, FRS_ERR_ASSERT, "AssertionError: %s [item %d]", deverr_text(h[0]), h[1]);
   return 0;
 }
@@ -349,7 +354,7 @@ int frs_last_launch_count(frs_context* c) { return c ? c->launch_count : 0; }
 int frs_get_stats(frs_context* c, long long* out, int n) {
   if (!c || !out) return FRS_ERR_ARG;
   const long long v[FRS_N_STATS] = {c->st_h2d_upload, c->st_h2d_run, c->st_d2h_run, c->st_clip_words,
-                                    (long long)c->hb.n_seq_words};
+                                    (long long)c->hb.n_seq_words, c->st_poly_tasks, c->st_poly_long};
   for (int i = 0; i < n && i < FRS_N_STATS; ++i) out[i] = v[i];
   return FRS_N_STATS;
 }
@@ -576,36 +581,43 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
   LAUNCHED();
 
   ENS(b_y, L * 8);
-  stage_begin(c, "gauss");
+  stage_begin(c, "smooth");
+  ENS(b_sflag, L);
+  ENS(b_cand_flat, (L / 2 + 2 * NI + 16) * 4);  // peaks are >= 2 apart, plus both ends of every island
+  ENS(b_vbuf, L * 8);
+  ENS(b_tint_pos_off, (size_t)(T + 1) * 4);
+  const size_t n_groups = (size_t)c->n_tiles / TILE_GROUP + 1;
+  ENS(b_tile_state, n_groups * 8 + (size_t)c->n_tiles * (2 * TILE_WORDS * 4 + 4) + 64);
   {
-    size_t sm = gauss_smem_bytes(lw);
-    if (sm > 48 * 1024) CK(cudaFuncSetAttribute(k_gauss, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_gauss<<<c->n_tiles, GAUSS_THREADS, sm, st>>>(c->b_tiles.as<TileWork>(), d_island_sample_off, c->b_yraw.as<int>(),
-                                                   d_gw, lw, c->b_y.as<double>());
+    // group totals | per tile: candidate / positive ballot words, packed counts
+    unsigned long long* d_gsum = c->b_tile_state.as<unsigned long long>();
+    u32* d_cmask = (u32*)(d_gsum + n_groups);
+    u32* d_pmask = d_cmask + (size_t)c->n_tiles * TILE_WORDS;
+    u32* d_tcnt = d_pmask + (size_t)c->n_tiles * TILE_WORDS;
+    CK(cudaMemsetAsync(d_gsum, 0, n_groups * 8, st));
+    const size_t sm = (size_t)p1_smem_layout(lw).total;
+    if (sm > 48 * 1024) CK(cudaFuncSetAttribute(k_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_smooth<<<c->n_tiles, GAUSS_THREADS, sm, st>>>(c->b_tiles.as<TileWork>(), d_island_sample_off, c->b_yraw.as<int>(),
+                                                    d_gw, lw, c->b_y.as<double>(), d_cmask, d_pmask, d_tcnt, d_gsum);
+    LAUNCHED();
+    k_tile_lists<<<c->n_tiles, GAUSS_THREADS, 0, st>>>(c->b_tiles.as<TileWork>(), c->n_tiles, d_island_sample_off,
+                                                       d_island_tint, d_tint_island_off, T, d_cmask, d_pmask, d_tcnt,
+                                                       d_gsum, c->b_y.as<double>(), c->b_cand_flat.as<int>(),
+                                                       c->b_vbuf.as<double>(), c->b_tint_pos_off.as<int>(),
+                                                       c->b_counters.as<i64>());
     LAUNCHED();
   }
 
-  stage_begin(c, "candidates");
-  ENS(b_sflag, L);
-  CK(cudaMemsetAsync(c->b_sflag.p, 0, L, st));
-  k_peaks<<<c->n_tiles, GAUSS_THREADS, 0, st>>>(c->b_tiles.as<TileWork>(), d_island_sample_off, c->b_y.as<double>(),
-                                                c->b_sflag.as<u8>());
-  LAUNCHED();
-  ENS(b_cand_flat, (L / 2 + 2 * NI + 16) * 4);  // peaks are >= 2 apart, plus both ends of every island
-  { int r = compact<u8>(c, c->b_sflag.as<u8>(), L, c->b_cand_flat.as<int>(), 0); if (r) return r; }
-
   stage_begin(c, "threshold");
   ENS(b_thr, (size_t)T * 8);
-  ENS(b_vbuf, L * 8);
   {
-    size_t nl = (size_t)L / 64 + 2 * (size_t)T + 8;
-    ENS(b_leaf_off, nl * 4);
-    ENS(b_leaf_len, nl * 4);
-    ENS(b_leaf_sum, nl * 8);
+    size_t nh = (size_t)L / 8 + 64 * (size_t)T + 64;  // heap scratch of the giant tints (see k_threshold)
+    ENS(b_leaf_len, nh * 4);
+    ENS(b_leaf_sum, nh * 8);
   }
-  k_threshold<<<T, THR_THREADS, 0, st>>>(c->b_tint_order.as<int>(), d_tint_island_off, d_island_sample_off, c->b_y.as<double>(), prm->vf,
-                                         c->b_vbuf.as<double>(), c->b_leaf_off.as<int>(), c->b_leaf_len.as<int>(),
-                                         c->b_leaf_sum.as<double>(), c->b_thr.as<double>());
+  k_threshold<<<T, THR_THREADS, 0, st>>>(c->b_tint_order.as<int>(), d_tint_island_off, d_island_sample_off,
+                                         c->b_tint_pos_off.as<int>(), prm->vf, c->b_vbuf.as<double>(),
+                                         c->b_leaf_len.as<int>(), c->b_leaf_sum.as<double>(), c->b_thr.as<double>());
   LAUNCHED();
   stage_end(c);
 
@@ -682,7 +694,7 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
   ENS(b_P, COV * 4);
   stage_begin(c, "coverage");
   if (NSUB > 0) {
-    k_coverage<<<c->n_cov_tiles, COV_THREADS, 0, st>>>(c->b_cov_tiles.as<RepTile>(), d_tint_rep_off,
+    k_coverage<<<dim3((unsigned)c->n_cov_tiles, COV_CHUNKS), COV_THREADS, 0, st>>>(c->b_cov_tiles.as<RepTile>(), d_tint_rep_off,
                                                        c->b_tint_cand_off.as<int>(), c->b_tint_cov_off.as<i64>(),
                                                        c->b_rep_iv_off.as<int>(), c->b_rep_fs.as<int>(),
                                                        c->b_rep_fe.as<int>(), c->b_cand_flat.as<int>(), c->b_P.as<u32>());
@@ -786,7 +798,7 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
   // refine adds peaks at least 20 samples apart inside segments longer than 40
   const i64 NFIN_MAX = K + L / 20 + 16;
   ENS(b_final_flat, (L / 2 + 2 * NI + 16) * 4);
-  { int r = compact<u8>(c, c->b_sflag.as<u8>(), L, c->b_final_flat.as<int>(), 11); if (r) return r; }
+  { int r = compact_flags(c, c->b_sflag.as<u8>(), L, c->b_final_flat.as<int>(), 11); if (r) return r; }
   const i64* d_nfin = c->b_counters.as<i64>() + 11;
   ENS(b_final_pos, NFIN_MAX * 4);
   ENS(b_final_island, NFIN_MAX * 4);
@@ -816,7 +828,8 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
   stage_begin(c, "digits");
   ENS(b_run_cnt, (size_t)NR * 4);
   ENS(b_run_off, (size_t)(NR + 1) * 4);
-  k_digits<<<c->n_dig_tiles, DIG_THREADS, 0, st>>>(c->b_dig_tiles.as<RepTile>(), d_tint_rep_off,
+  CK(cudaMemsetAsync(c->b_run_cnt.p, 0, (size_t)NR * 4, st));
+  k_digits<<<dim3((unsigned)c->n_dig_tiles, DIG_CHUNKS), DIG_THREADS, 0, st>>>(c->b_dig_tiles.as<RepTile>(), d_tint_rep_off,
                                                    c->b_tint_final_off.as<int>(), c->b_tint_digit_off.as<i64>(),
                                                    c->b_rep_iv_off.as<int>(), c->b_rep_fs.as<int>(), c->b_rep_fe.as<int>(),
                                                    c->b_final_flat.as<int>(), c->b_seg_ty.as<int>(), c->b_seg_tn.as<int>(),
@@ -879,8 +892,11 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
         G.seq_t = c->b_seq_t.as<u32>();
       }
       stage_begin(c, "poly");
-      k_poly_bases<<<1, 32, 0, st>>>(G.cls_count); LAUNCHED();
-      k_poly_scatter<<<cdiv((i64)N * 4, 256), 256, 0, st>>>(N * 4, G.clip_n, G.cls_count, G.task_order); LAUNCHED();
+      ENS(b_poly_flag, (size_t)N * 4);
+      k_poly_filter<<<cdiv((i64)N * 4, 128), 128, 0, st>>>(G, c->b_poly_flag.as<u8>()); LAUNCHED();
+      k_poly_bases<<<1, 32, 0, st>>>(G.cls_count, G.long_class, d_err + 2); LAUNCHED();
+      k_poly_scatter<<<cdiv((i64)N * 4, 256), 256, 0, st>>>(N * 4, G.clip_n, c->b_poly_flag.as<u8>(), G.cls_count,
+                                                             G.task_order); LAUNCHED();
       // long clips (one warp each) run beside the short ones (one thread each)
       CK(cudaEventRecord(c->ev_fork, st));
       CK(cudaStreamWaitEvent(c->side[0], c->ev_fork, 0));

@@ -10,9 +10,13 @@
 // multiple of 4 so that row segments can be fetched with 16-byte TMA bulk copies).  Inside an
 // island  P[j]-P[i]  equals the reference's  C[j]-C[i]  (:493): earlier islands add the same
 // constant to both rows.  One thread per rep walks the candidates and its (sorted) intervals with
-// two pointers; a warp writes 128 contiguous bytes of one row per step.
+// two pointers; a warp writes 128 contiguous bytes of one row per step.  The candidate rows of a tint
+// are cut into up to COV_CHUNKS chunks (grid.y) so that the serial walk of a thread is bounded by
+// Kt / COV_CHUNKS candidates (+ its own few intervals, re-walked from the first one per chunk).
 // ---------------------------------------------------------------------------------------------
 #define COV_THREADS 128
+#define COV_CHUNKS 8
+#define COV_MIN_CHUNK 32
 struct RepTile { int tint; int rep_lo; };  // rep_lo: tint-local first rep of the tile
 
 __global__ void __launch_bounds__(COV_THREADS) k_coverage(const RepTile* __restrict__ tiles,
@@ -29,9 +33,12 @@ __global__ void __launch_bounds__(COV_THREADS) k_coverage(const RepTile* __restr
   const int r = tl.rep_lo + threadIdx.x;
   if (r >= Rp) return;
   const int q0 = tint_cand_off[tl.tint], q1 = tint_cand_off[tl.tint + 1];
+  const int chunk = max(COV_MIN_CHUNK, (q1 - q0 + COV_CHUNKS - 1) / COV_CHUNKS);
+  const int qa = q0 + (int)blockIdx.y * chunk, qb = min(q1, qa + chunk);
+  if (qa >= q1) return;
   u32* out = P + tint_cov_off[tl.tint] + r;
   if (r >= R) {  // padding columns
-    for (int q = q0; q < q1; ++q) out[(i64)(q - q0) * Rp] = 0u;
+    for (int q = qa; q < qb; ++q) out[(i64)(q - q0) * Rp] = 0u;
     return;
   }
   int a = rep_iv_off[r0 + r];
@@ -39,7 +46,7 @@ __global__ void __launch_bounds__(COV_THREADS) k_coverage(const RepTile* __restr
   u32 acc = 0;
   int fs = (a < b) ? iv_fs[a] : 0x7fffffff;
   int fe = (a < b) ? iv_fe[a] : 0x7fffffff;
-  for (int q = q0; q < q1; ++q) {
+  for (int q = qa; q < qb; ++q) {
     const int cf = cand_flat[q];
     while (a < b && fe < cf) {  // interval entirely before the candidate (te is an inclusive sample)
       acc += (u32)(fe - fs + 1);
@@ -157,6 +164,7 @@ __host__ __device__ inline int dp_slab_words(int n, int words, int cap) {
   int lat = (1 << 20) / (n * n * n);
   lat = max(4, min(64, lat)) & ~3;
   int spread = (((words + 7) / 8) + 3) & ~3;
+  if (words <= 256) cap = min(cap, 16);  // mid-size tints: more, shorter CTAs (swept on B200); giant tints keep fat slabs
   return max(1, min(cap, max(lat, spread)));
 }
 

@@ -209,6 +209,8 @@ __global__ void k_seg_cuts(const i64* __restrict__ n_final_p, const int* __restr
 // ---------------------------------------------------------------------------------------------
 #define DIG_THREADS 128
 #define DIG_SEGS 32
+#define DIG_CHUNKS 8      // grid.y: the segments of a tint are cut into chunks (bounded serial walk per thread)
+#define DIG_MIN_CHUNK 64  // segments, a multiple of DIG_SEGS
 __global__ void __launch_bounds__(DIG_THREADS) k_digits(const RepTile* __restrict__ tiles,
                                                        const int* __restrict__ tint_rep_off,
                                                        const int* __restrict__ tint_final_off,
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(DIG_THREADS) k_digits(const RepTile* __restric
                                                        const int* __restrict__ iv_fs, const int* __restrict__ iv_fe,
                                                        const int* __restrict__ final_flat,
                                                        const int* __restrict__ seg_ty, const int* __restrict__ seg_tn,
-                                                       u8* __restrict__ digits, int* __restrict__ run_cnt,
+                                                       u8* __restrict__ digits, int* __restrict__ run_cnt /* zeroed */,
                                                        int* __restrict__ err) {
   __shared__ u8 tile[DIG_THREADS][DIG_SEGS + 1];
   const RepTile tl = tiles[blockIdx.x];
@@ -225,6 +227,9 @@ __global__ void __launch_bounds__(DIG_THREADS) k_digits(const RepTile* __restric
   const int R = tint_rep_off[tl.tint + 1] - r0;
   const int f0 = tint_final_off[tl.tint];
   const int S = tint_final_off[tl.tint + 1] - f0 - 1;
+  const int chunk = max(DIG_MIN_CHUNK, ((S + DIG_CHUNKS - 1) / DIG_CHUNKS + DIG_SEGS - 1) / DIG_SEGS * DIG_SEGS);
+  const int sa = (int)blockIdx.y * chunk, sb = min(S, sa + chunk);
+  if (sa >= S) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = tl.rep_lo + threadIdx.x;
   const bool have = r < R;
@@ -242,24 +247,34 @@ __global__ void __launch_bounds__(DIG_THREADS) k_digits(const RepTile* __restric
     }
     return acc + ((a < b && x > fs) ? (u32)(x - fs) : 0u);
   };
-  u32 p_prev = (have && S > 0) ? P(final_flat[f0]) : 0u;
-  int runs = 0;
+  auto digit = [&](int s, u32 p_lo, u32 p_hi) -> u8 {
+    const int tn = seg_tn[f0 + s];
+    if (tn == -2) return '0';  // island separator
+    const int cov = (int)(p_hi - p_lo);
+    if (cov > final_flat[f0 + s + 1] - final_flat[f0 + s] + 1) dev_fail(err, DEVERR_RATIO_RANGE, r0 + r);
+    return (cov >= seg_ty[f0 + s]) ? '1' : ((cov <= tn) ? '0' : '2');
+  };
+  // the digit before the chunk decides whether the chunk's first '1' starts a run
   bool prev1 = false;
+  u32 p_prev = 0u;
+  if (have) {
+    if (sa > 0) {
+      const u32 p0 = P(final_flat[f0 + sa - 1]);
+      p_prev = P(final_flat[f0 + sa]);
+      prev1 = digit(sa - 1, p0, p_prev) == '1';
+    } else {
+      p_prev = P(final_flat[f0]);
+    }
+  }
+  int runs = 0;
   u8* out0 = digits + tint_digit_off[tl.tint];
-  for (int s0 = 0; s0 < S; s0 += DIG_SEGS) {
-    const int ns = min(DIG_SEGS, S - s0);
+  for (int s0 = sa; s0 < sb; s0 += DIG_SEGS) {
+    const int ns = min(DIG_SEGS, sb - s0);
     if (have) {
       for (int k = 0; k < ns; ++k) {
         const int s = s0 + k;
-        const int fb = final_flat[f0 + s + 1];
-        const u32 p_next = P(fb);
-        const int tn = seg_tn[f0 + s];
-        u8 d = '0';
-        if (tn != -2) {
-          const int cov = (int)(p_next - p_prev);
-          if (cov > fb - final_flat[f0 + s] + 1) dev_fail(err, DEVERR_RATIO_RANGE, r0 + r);
-          d = (cov >= seg_ty[f0 + s]) ? '1' : ((cov <= tn) ? '0' : '2');
-        }
+        const u32 p_next = P(final_flat[f0 + s + 1]);
+        const u8 d = digit(s, p_prev, p_next);
         p_prev = p_next;
         const bool is1 = d == '1';
         runs += (is1 && !prev1) ? 1 : 0;
@@ -276,7 +291,7 @@ __global__ void __launch_bounds__(DIG_THREADS) k_digits(const RepTile* __restric
     }
     __syncthreads();
   }
-  if (have) run_cnt[r0 + r] = runs;
+  if (have && runs) atomicAdd(&run_cnt[r0 + r], runs);
 }
 
 // 1-runs per rep (shared by all reads of the rep): one warp per rep, 32 segments per step, starts and
@@ -334,7 +349,7 @@ __global__ void k_gap_count(int n_reads, const int* __restrict__ read_rep, const
 // class (4 classes per octave, longest first), which keeps the lanes of a warp in step.
 // ---------------------------------------------------------------------------------------------
 #define POLY_CLASSES 96
-#define POLY_LONG_CLASS 40  // poly_class(1024): longer clips are scanned by a whole warp (k_poly_long)
+#define POLY_LONG_CLASS 36  // poly_class(512): longer clips are scanned by a whole warp (k_poly_long); swept on B200
 #define POLY_C 64            // bases per lane and window in k_poly_long
 struct PolyRes { double p; int i0; int len; };  // len == 0: no qualifying run
 
@@ -360,7 +375,7 @@ struct GapArgs {
   i64* clip_off;      // [2N+1] word offset of the clip's plane words inside seq_a / seq_t (see clip_geometry)
   int seq_resident;   // 1: seq_a/seq_t hold the whole reads (clip_off written by k_gap_prep);
                       // 0: they hold only the clip words, gathered by the host after k_gap_prep
-  int* cls_count;     // [POLY_CLASSES] (+ [POLY_CLASSES] cursors, + 1 total) zeroed before k_gap_prep
+  int* cls_count;     // [POLY_CLASSES] (+ [POLY_CLASSES] cursors, + 1 total) zeroed before k_poly_filter
   int* task_order;    // [4N] slots, longest class first
   PolyRes* task_res;  // [4N]
   int long_class;     // tasks of classes >= long_class go to k_poly_long (default POLY_LONG_CLASS)
@@ -435,9 +450,6 @@ __host__ __device__ __forceinline__ ClipGeo clip_geometry(int L, int n, bool is_
 // clip bounds by CIGAR threading, unaligned gaps between consecutive 1-runs, and the scan tasks.
 // head[3] = q_ssc and head[6] = q_esc are provisional; k_gap_finish rewrites them.
 __global__ void __launch_bounds__(128) k_gap_prep(GapArgs A) {
-  __shared__ int sh_cnt[POLY_CLASSES];
-  for (int k = threadIdx.x; k < POLY_CLASSES; k += blockDim.x) sh_cnt[k] = 0;
-  __syncthreads();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < A.n_reads) {
     int* head = A.read_head + (i64)i * 8;
@@ -466,14 +478,12 @@ __global__ void __launch_bounds__(128) k_gap_prep(GapArgs A) {
         const bool minus = A.read_strand[i] != 0;
         if (ns >= 20) {
           cn[0] = ns;
-          atomicAdd(&sh_cnt[poly_class_dev(ns)], 2);
           const ClipGeo g = clip_geometry(L, ns, true, minus);
           cw[0] = g.n_words;
           if (A.seq_resident) A.clip_off[2 * (i64)i] = A.read_seq_off[i] + g.w_first;
         }
         if (ne >= 20) {
           cn[1] = ne;
-          atomicAdd(&sh_cnt[poly_class_dev(ne)], 2);
           const ClipGeo g = clip_geometry(L, ne, false, minus);
           cw[1] = g.n_words;
           if (A.seq_resident) A.clip_off[2 * (i64)i + 1] = A.read_seq_off[i] + g.w_first;
@@ -484,9 +494,6 @@ __global__ void __launch_bounds__(128) k_gap_prep(GapArgs A) {
       }
     }
   }
-  __syncthreads();
-  for (int k = threadIdx.x; k < POLY_CLASSES; k += blockDim.x)
-    if (sh_cnt[k]) atomicAdd(&A.cls_count[k], sh_cnt[k]);
 }
 
 // K11a': one thread per unaligned-gap record: "{l1}-{f2}:{size}" (:455-471)
@@ -507,22 +514,68 @@ __global__ void k_gap_sizes(GapArgs A, int n_gaps) {
   rec[2] = size;
 }
 
+// Scan-task filter, one thread per slot.  A run that find_longest_poly keeps has len >= 20 and at most
+// 0.15*len mismatches, i.e. at most 0.15*len + 1 stretches of matches holding >= 0.85*len matches, so
+// one stretch has >= ceil(0.85*len / (0.15*len + 1)) >= 5 consecutive matches.  A clip whose plane has
+// no 5 consecutive set bits therefore yields "no run" without being scanned (exact; ~90 % of the
+// clips of random sequence).  The test is word-parallel: v & v>>1 & v>>2 & v>>3 & v>>4 over the
+// plane words, carried across word boundaries.  Survivors are counted per length class.
+__global__ void __launch_bounds__(128) k_poly_filter(GapArgs A, u8* __restrict__ pass_flag) {
+  __shared__ int sh_cnt[POLY_CLASSES];
+  for (int k = threadIdx.x; k < POLY_CLASSES; k += blockDim.x) sh_cnt[k] = 0;
+  __syncthreads();
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot < A.n_reads * 4) {
+    const int i = slot >> 2, which = slot & 3, clip = slot >> 1;
+    const int n = A.clip_n[clip];
+    bool pass = false;
+    if (n >= 20) {
+      const bool minus = A.read_strand[i] != 0;
+      const bool want_a = (which & 1) == 0;
+      const u32* pl = ((want_a != minus) ? A.seq_a : A.seq_t) + A.clip_off[clip];
+      const ClipGeo geo = clip_geometry(A.read_len[i], n, which < 2, minus);
+      const int last = geo.idx0 + geo.step * (n - 1);
+      const int b_lo = min(geo.idx0, last), b_hi = max(geo.idx0, last);  // clip bits, relative to the first word
+      const int w_lo = b_lo >> 5, w_hi = b_hi >> 5;
+      u32 prev = 0u;
+      for (int w = w_lo; w <= w_hi + 1 && !pass; ++w) {
+        u32 cur = 0u;
+        if (w <= w_hi) {
+          cur = pl[w];
+          if (w == w_lo) cur &= 0xffffffffu << (b_lo & 31);
+          if (w == w_hi && (b_hi & 31) != 31) cur &= 0xffffffffu >> (31 - (b_hi & 31));
+        }
+        const unsigned long long v = ((unsigned long long)cur << 32) | prev;
+        const unsigned long long r = v & (v >> 1) & (v >> 2) & (v >> 3) & (v >> 4);
+        pass = (u32)r != 0u;  // stretches that start in `prev` (and may end in `cur`)
+        prev = cur;
+      }
+      if (pass) atomicAdd(&sh_cnt[poly_class_dev(n)], 1);
+      else { PolyRes none; none.p = 0.0; none.i0 = 0; none.len = 0; A.task_res[slot] = none; }
+    }
+    pass_flag[slot] = pass ? 1 : 0;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < POLY_CLASSES; k += blockDim.x)
+    if (sh_cnt[k]) atomicAdd(&A.cls_count[k], sh_cnt[k]);
+}
+
 // one warp: class bases, LONGEST class first; cls_count[c] becomes the base, cursors start at 0
-__global__ void k_poly_bases(int* __restrict__ cls_count) {
+__global__ void k_poly_bases(int* __restrict__ cls_count, int long_class, int* __restrict__ stat /* [2] */) {
   if (threadIdx.x == 0) {
     int acc = 0;
     for (int c = POLY_CLASSES - 1; c >= 0; --c) { int v = cls_count[c]; cls_count[c] = acc; acc += v; }
     cls_count[2 * POLY_CLASSES] = acc;  // total tasks
+    stat[0] = acc;                       // scan tasks that survived the filter
+    stat[1] = cls_count[long_class - 1]; // of which warp-scanned (long clips)
   }
 }
 
-__global__ void k_poly_scatter(int n_slots, const int* __restrict__ clip_n, int* __restrict__ cls_count,
-                               int* __restrict__ order) {
+__global__ void k_poly_scatter(int n_slots, const int* __restrict__ clip_n, const u8* __restrict__ pass_flag,
+                               int* __restrict__ cls_count, int* __restrict__ order) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_slots) return;
-  int n = clip_n[s >> 1];
-  if (n < 20) return;
-  int c = poly_class_dev(n);
+  if (s >= n_slots || !pass_flag[s]) return;
+  int c = poly_class_dev(clip_n[s >> 1]);
   // warp-aggregate the cursor bump of lanes that share a class
   unsigned peers = __match_any_sync(__activemask(), c);
   int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;

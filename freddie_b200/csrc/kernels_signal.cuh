@@ -50,14 +50,25 @@ __global__ void __launch_bounds__(SIG_THREADS) k_signal(const SigWork* __restric
     int mmax = m;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
-    for (int k = 0; k < mmax; ++k) {
-      bool have = k < m;
-      int fs = have ? iv_fs[a + k] : -1;
-      int fe = have ? iv_fe[a + k] : -1;
-      bool use_s = have && !(ignore_ends && k == 0) && fs >= wk.win_lo && fs < wk.win_hi;
-      bool use_e = have && !(ignore_ends && k == m - 1) && fe >= wk.win_lo && fe < wk.win_hi;
-      hist_add(hist, fs - wk.win_lo, w, use_s);
-      hist_add(hist, fe - wk.win_lo, w, use_e);
+    for (int k0 = 0; k0 < mmax; k0 += 4) {  // four intervals' loads in flight per round trip
+      int fs4[4], fe4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool have = k0 + u < m;
+        fs4[u] = have ? iv_fs[a + k0 + u] : -1;
+        fe4[u] = have ? iv_fe[a + k0 + u] : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + u;
+        if (k >= mmax) break;  // warp-uniform
+        const bool have = k < m;
+        const int fs = fs4[u], fe = fe4[u];
+        bool use_s = have && !(ignore_ends && k == 0) && fs >= wk.win_lo && fs < wk.win_hi;
+        bool use_e = have && !(ignore_ends && k == m - 1) && fe >= wk.win_lo && fe < wk.win_hi;
+        hist_add(hist, fs - wk.win_lo, w, use_s);
+        hist_add(hist, fe - wk.win_lo, w, use_e);
+      }
     }
   }
   __syncthreads();
@@ -69,116 +80,266 @@ __global__ void __launch_bounds__(SIG_THREADS) k_signal(const SigWork* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2 Gaussian: shared-memory tiled fp64 stencil over one island tile.
-// Evaluation order of scipy's correlate1d symmetric branch:  acc = y[l]*w[c];
-// for jj=-lw..-1: acc = acc + (y[l+jj] + y[l-jj]) * w[c+jj], each op rounded separately (no FMA).
-// Reflect extension 'd c b a | a b c d | d c b a', valid when the island is shorter than lw.
+// K2 + K4 + first half of K3 in one pass over the signal (k_smooth), one CTA per island tile:
+//   1. fp64 Gaussian of the tile, evaluation order of scipy's correlate1d symmetric branch:
+//      acc = y[l]*w[c];  for jj=-lw..-1: acc = acc + (y[l+jj] + y[l-jj]) * w[c+jj], each op rounded
+//      separately (no FMA).  Reflect extension 'd c b a | a b c d | d c b a', also valid when the
+//      island is shorter than lw.  The raw signal is SPARSE (splice sites): a pair whose two inputs
+//      are zero adds (0+0)*w = +0 to a non-negative accumulator and changes no bit, so every output
+//      only visits the pairs that have a non-zero input, outermost first, found with a bit mask of
+//      the non-zero staged samples (~3 pairs instead of 20 at sigma = 5).
+//   2. candidates of the tile: strict local maxima with plateau -> floor midpoint, island ends never
+//      peaks, plus the first and last sample of every island (scipy _local_maxima_1d;
+//      candidates_from_peaks :615-621), decided per OWNING sample so that tiles never write into
+//      each other:  m is a peak  <=>  y[m] > 0, the maximal plateau [a, b] of value y[m] around m has
+//      1 <= a, b <= n-2, y[a-1] < y[m] > y[b+1], and m == (a+b)>>1.
+//   3. per 32 samples one ballot word of candidates and one of positive samples (the input of the
+//      variance threshold, :757-759), plus the two counts of the tile.
+// k_tile_lists then writes the ordered candidate list and the ordered positive samples from the
+// masks (its offsets come from a two-level sum of the tile counts, no device-wide scan).  HBM traffic
+// of the two: 4 B read + 8 B written per sample, 1/4 B of masks, and the positive samples once more.
 // ---------------------------------------------------------------------------------------------
 #define TILE_SAMPLES 1024
 #define GAUSS_THREADS 128
-#define GAUSS_OPT 8  // consecutive outputs per thread (register sliding window)
-#define GAUSS_DB 4   // tap distances per register block
+#define TILE_WORDS (TILE_SAMPLES / 32)
+#define TILE_GROUP 1024  // tiles per group of the two-level count prefix
 
 struct TileWork { int island; int lo; };  // lo = island-local first sample of the tile
 
-// Taps are evaluated outermost pair first, like scipy.  The radius is padded to a multiple of
-// GAUSS_DB with zero weights: those pairs come first and add (a+b)*0 = +0 to a non-negative
-// accumulator, which leaves every bit unchanged.  Thread t owns outputs 8t..8t+7; for a block of 4
-// distances it needs 11 + 11 consecutive inputs, so a tap pair costs ~0.7 shared-memory loads instead
-// of 3.  The tile is stored with a skew of one double per 8 so that the stride-8 accesses of a warp
-// are bank-conflict free.
-__host__ __device__ __forceinline__ int gauss_pad_radius(int lw) { return (lw + GAUSS_DB - 1) / GAUSS_DB * GAUSS_DB; }
-__host__ __device__ __forceinline__ int gauss_skew(int q) { return q + (q >> 3); }
-__host__ __device__ inline size_t gauss_smem_bytes(int lw) {
-  int lwp = gauss_pad_radius(lw);
-  return (size_t)(lwp + 1 + gauss_skew(TILE_SAMPLES + 2 * lwp) + 2) * 8;
+// staged window: logical index s = island sample lo - lw - 1 + s (one extra sample on both sides: the
+// neighbours of the tile's first and last output); centre of tile sample x = lw + 1 + x
+struct P1Smem { int wd, ext, yout, nz, red, total; };
+__host__ __device__ inline P1Smem p1_smem_layout(int lw) {
+  const int span = TILE_SAMPLES + 2 * lw + 2;
+  P1Smem s;
+  int o = 0;
+  s.wd = o; o += (lw + 1) * 8;
+  s.ext = o; o += (span + 2) * 8;
+  s.yout = o; o += (TILE_SAMPLES + 2) * 8;
+  s.nz = o; o += ((span + 127) / 128 * 4 + 2) * 4;
+  s.red = o; o += 16 * 4;
+  s.total = (o + 15) & ~15;
+  return s;
 }
 
-__global__ void __launch_bounds__(GAUSS_THREADS) k_gauss(const TileWork* __restrict__ tiles,
-                                                        const int* __restrict__ island_sample_off,
-                                                        const int* __restrict__ y_raw,
-                                                        const double* __restrict__ gw, int lw,
-                                                        double* __restrict__ y) {
-  extern __shared__ double gsm[];
-  const int lwp = gauss_pad_radius(lw);
-  double* wd = gsm;              // wd[d] = weight of the pair at distance d (0 for the padding)
-  double* ext = gsm + lwp + 1;   // skewed tile + halo
+__device__ __forceinline__ u32 nz_bit(const u32* nz, int s) { return (nz[s >> 5] >> (s & 31)) & 1u; }
+// 32 mask bits starting at bit position s (s >= 0)
+__device__ __forceinline__ u32 nz_word(const u32* nz, int s) {
+  const int w = s >> 5, b = s & 31;
+  return b ? __funnelshift_r(nz[w], nz[w + 1], b) : nz[w];
+}
+
+// y of the sample whose staged centre index is c.  wd[d] = weight of the pair at distance d.
+__device__ __forceinline__ double gauss_sparse(const double* ext, const u32* nz, const double* wd, int lw, int c) {
+  double acc = __dmul_rn(ext[c], wd[0]);
+  if (lw == 0) return acc;
+  if (lw <= 32) {
+    // bit (d-1) of m: the pair at distance d has a non-zero input
+    const u32 keep = lw == 32 ? 0xffffffffu : ((1u << lw) - 1u);
+    const u32 right = nz_word(nz, c + 1) & keep;                     // bit d-1 = sample c+d
+    const u32 left = __brev(nz_word(nz, c - lw)) >> (32 - lw);       // bit lw-d -> bit d-1 = sample c-d
+    u32 m = right | (left & keep);
+    while (m) {
+      const int d = 32 - __clz(m);  // outermost remaining pair first
+      m &= ~(1u << (d - 1));
+      acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(ext[c - d], ext[c + d]), wd[d]));
+    }
+  } else {
+    for (int d = lw; d >= 1; --d)
+      if (nz_bit(nz, c - d) | nz_bit(nz, c + d))
+        acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(ext[c - d], ext[c + d]), wd[d]));
+  }
+  return acc;
+}
+
+// y at island-local sample x straight from the raw signal in global memory (plateaus that leave the
+// tile: rare).  Same operation order; zero pairs are not skipped, which gives the same bits.
+__device__ double gauss_global(const int* __restrict__ yr, int n, int x, const double* wd, int lw) {
+  const int n2 = 2 * n;
+  auto g = [&](int i) -> double {
+    int j = i % n2;
+    if (j < 0) j += n2;
+    if (j >= n) j = n2 - 1 - j;
+    return (double)yr[j];
+  };
+  double acc = __dmul_rn(g(x), wd[0]);
+  for (int d = lw; d >= 1; --d) acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(g(x - d), g(x + d)), wd[d]));
+  return acc;
+}
+
+__global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __restrict__ tiles,
+                                                         const int* __restrict__ island_sample_off,
+                                                         const int* __restrict__ y_raw,
+                                                         const double* __restrict__ gw, int lw,
+                                                         double* __restrict__ y, u32* __restrict__ cmask,
+                                                         u32* __restrict__ pmask, u32* __restrict__ tile_cnt,
+                                                         unsigned long long* __restrict__ group_sum /* zeroed */) {
+  extern __shared__ __align__(16) unsigned char p1sm[];
+  const P1Smem Lo = p1_smem_layout(lw);
+  double* wd = (double*)(p1sm + Lo.wd);
+  double* ext = (double*)(p1sm + Lo.ext);    // raw tile + halo as doubles
+  double* yout = (double*)(p1sm + Lo.yout);  // yout[1 + x] = y of tile sample x; [0], [cnt+1] = neighbours
+  u32* nz = (u32*)(p1sm + Lo.nz);            // bit s: staged sample s is non-zero
+  int* red = (int*)(p1sm + Lo.red);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const TileWork tw = tiles[blockIdx.x];
   const int f0 = island_sample_off[tw.island];
   const int n = island_sample_off[tw.island + 1] - f0;
   const int cnt = min(TILE_SAMPLES, n - tw.lo);
-  for (int d = threadIdx.x; d <= lwp; d += GAUSS_THREADS) wd[d] = (d <= lw) ? gw[lw - d] : 0.0;
-  const int span = cnt + 2 * lwp;
-  const int first = tw.lo - lwp;
-  if (first >= 0 && first + span <= n) {  // interior tile: no reflection
-    const int* src = y_raw + f0 + first;
-    for (int s = threadIdx.x; s < span; s += GAUSS_THREADS) ext[gauss_skew(s)] = (double)src[s];
-  } else {
-    const int n2 = 2 * n;
-    for (int s = threadIdx.x; s < span; s += GAUSS_THREADS) {
-      int j = (first + s) % n2;
-      if (j < 0) j += n2;
-      if (j >= n) j = n2 - 1 - j;
-      ext[gauss_skew(s)] = (double)y_raw[f0 + j];
+  const int* yr = y_raw + f0;
+  for (int d = tid; d <= lw; d += GAUSS_THREADS) wd[d] = gw[lw - d];
+  const int span = cnt + 2 * lw + 2;
+  const int first = tw.lo - lw - 1;
+  const int span_r = (span + GAUSS_THREADS - 1) / GAUSS_THREADS * GAUSS_THREADS;
+  const bool interior = first >= 0 && first + span <= n;
+  const int n2 = 2 * n;
+  for (int s = tid; s < span_r; s += GAUSS_THREADS) {  // whole warps: the ballot needs every lane
+    int v = 0;
+    if (s < span) {
+      int j = first + s;
+      if (!interior) {
+        j %= n2;
+        if (j < 0) j += n2;
+        if (j >= n) j = n2 - 1 - j;
+      }
+      v = yr[j];
+      ext[s] = (double)v;
     }
+    const u32 m = __ballot_sync(0xffffffffu, v != 0);
+    if (lane == 0) nz[s >> 5] = m;
+  }
+  if (tid < 2) nz[(span_r >> 5) + tid] = 0u;
+  __syncthreads();
+  // ---- Gaussian: a warp owns 256 consecutive samples, 32 per step (coalesced 256-byte stores) ----
+  for (int it = 0; it < TILE_WORDS / 4; ++it) {
+    const int xb = warp * (TILE_SAMPLES / 4) + it * 32;
+    if (xb >= cnt) break;
+    const int x = xb + lane;
+    // inputs of this step: staged samples [xb + 1, xb + 32 + 2*lw]
+    bool any = false;
+    for (int s = xb + 1; s < xb + 33 + 2 * lw; s += 32) {
+      u32 m = nz_word(nz, s);
+      const int rem = xb + 33 + 2 * lw - s;
+      if (rem < 32) m &= (1u << rem) - 1u;
+      any = any || (m != 0u);
+    }
+    double v = 0.0;
+    if (any && x < cnt) v = gauss_sparse(ext, nz, wd, lw, lw + 1 + x);
+    if (x < cnt) {
+      y[f0 + tw.lo + x] = v;
+      yout[1 + x] = v;
+    }
+  }
+  if (tid == GAUSS_THREADS - 2) yout[0] = gauss_sparse(ext, nz, wd, lw, lw);              // sample lo - 1
+  if (tid == GAUSS_THREADS - 1) yout[cnt + 1] = gauss_sparse(ext, nz, wd, lw, lw + 1 + cnt);  // sample lo + cnt
+  __syncthreads();
+  // ---- candidates and positives ----
+  auto Y = [&](int X) -> double {  // island-local sample, 0 <= X < n
+    const int x = X - tw.lo;
+    return (x >= -1 && x <= cnt) ? yout[1 + x] : gauss_global(yr, n, X, wd, lw);
+  };
+  int nc = 0, np = 0;
+  u32* cm_out = cmask + (size_t)blockIdx.x * TILE_WORDS;
+  u32* pm_out = pmask + (size_t)blockIdx.x * TILE_WORDS;
+  for (int it = 0; it < TILE_WORDS / 4; ++it) {
+    const int wi = warp * (TILE_WORDS / 4) + it;
+    const int x = wi * 32 + lane, X = tw.lo + x;
+    bool is_c = false, is_p = false;
+    if (x < cnt) {
+      const double v = yout[1 + x];
+      is_p = v > 0.0;
+      is_c = (X == 0 || X == n - 1);
+      if (!is_c && is_p) {
+        const double l = yout[x], r = yout[x + 2];
+        if (l < v && r < v) is_c = true;
+        else if (!(l > v) && !(r > v)) {  // a neighbour equals v: walk the plateau
+          int a = X, b = X;
+          while (a - 1 >= 0 && Y(a - 1) == v) --a;
+          while (b + 1 <= n - 1 && Y(b + 1) == v) ++b;
+          if (a >= 1 && b <= n - 2 && Y(a - 1) < v && Y(b + 1) < v && X == ((a + b) >> 1)) is_c = true;
+        }
+      }
+    }
+    const u32 cm = __ballot_sync(0xffffffffu, is_c), pm = __ballot_sync(0xffffffffu, is_p);
+    if (lane == 0) { cm_out[wi] = cm; pm_out[wi] = pm; }
+    nc += __popc(cm);
+    np += __popc(pm);
+  }
+  if (lane == 0) red[warp] = nc | (np << 16);
+  __syncthreads();
+  if (tid == 0) {
+    const u32 v = (u32)(red[0] + red[1] + red[2] + red[3]);  // candidates | positives << 16
+    tile_cnt[blockIdx.x] = v;
+    // totals of every group of TILE_GROUP consecutive tiles: positives << 32 | candidates
+    atomicAdd(&group_sum[blockIdx.x / TILE_GROUP], ((unsigned long long)(v >> 16) << 32) | (unsigned long long)(v & 0xffffu));
+  }
+}
+
+// Ordered candidate list and ordered positive samples of one tile from its ballot words.  The tile's
+// offsets into the two lists = totals of the tile groups before its group (k_smooth's atomics) + counts
+// of the earlier tiles of its own group: at most (n_tiles / TILE_GROUP + TILE_GROUP) cached loads per
+// CTA instead of a device-wide scan.  Also: per-tint offsets of the positive list and the totals.
+__global__ void __launch_bounds__(GAUSS_THREADS) k_tile_lists(const TileWork* __restrict__ tiles, int n_tiles,
+                                                             const int* __restrict__ island_sample_off,
+                                                             const int* __restrict__ island_tint,
+                                                             const int* __restrict__ tint_island_off, int n_tints,
+                                                             const u32* __restrict__ cmask, const u32* __restrict__ pmask,
+                                                             const u32* __restrict__ tile_cnt,
+                                                             const unsigned long long* __restrict__ group_sum,
+                                                             const double* __restrict__ y, int* __restrict__ cand_flat,
+                                                             double* __restrict__ vbuf, int* __restrict__ tint_pos_off,
+                                                             i64* __restrict__ n_cand_out) {
+  __shared__ int pre_c[TILE_WORDS], pre_p[TILE_WORDS];
+  __shared__ unsigned long long red[GAUSS_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x;
+  const u32* cm_in = cmask + (size_t)tile * TILE_WORDS;
+  const u32* pm_in = pmask + (size_t)tile * TILE_WORDS;
+  // ---- (candidates, positives) before this tile ----
+  unsigned long long s = 0;
+  const int g = tile / TILE_GROUP;
+  for (int k = tid; k < g; k += GAUSS_THREADS) s += group_sum[k];
+  for (int k = g * TILE_GROUP + tid; k < tile; k += GAUSS_THREADS) {
+    const u32 v = tile_cnt[k];
+    s += ((unsigned long long)(v >> 16) << 32) | (unsigned long long)(v & 0xffffu);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) red[warp] = s;
+  if (warp == 0) {
+    int c = __popc(cm_in[lane]), p = __popc(pm_in[lane]);
+    const int c0 = c, p0 = p;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, c, o), b = __shfl_up_sync(0xffffffffu, p, o);
+      if (lane >= o) { c += a; p += b; }
+    }
+    pre_c[lane] = c - c0;
+    pre_p[lane] = p - p0;
   }
   __syncthreads();
-  const int x0 = threadIdx.x * GAUSS_OPT;
-  if (x0 >= cnt) return;
-  // logical index of output i's centre: lwp + x0 + i ; all offsets below are warp-uniform + 8*t
-  auto at = [&](int off) -> double { return ext[x0 + threadIdx.x + off + (off >> 3)]; };  // skew(8t+off) = 9t+off+(off>>3)
-  double acc[GAUSS_OPT];
-  const double w0 = wd[0];
-#pragma unroll
-  for (int i = 0; i < GAUSS_OPT; ++i) acc[i] = __dmul_rn(at(lwp + i), w0);
-  for (int d0 = lwp; d0 >= GAUSS_DB; d0 -= GAUSS_DB) {
-    double bl[GAUSS_OPT + GAUSS_DB - 1], br[GAUSS_OPT + GAUSS_DB - 1];
-#pragma unroll
-    for (int m = 0; m < GAUSS_OPT + GAUSS_DB - 1; ++m) {
-      bl[m] = at(lwp - d0 + m);                   // input  x0 + m - d0
-      br[m] = at(lwp + d0 - (GAUSS_DB - 1) + m);  // input  x0 + m + d0 - (DB-1)
+  const unsigned long long before = red[0] + red[1] + red[2] + red[3];
+  const int off_c = (int)(before & 0xffffffffull), off_p = (int)(before >> 32);
+  const TileWork tw = tiles[tile];
+  if (tid == 0) {
+    if (tw.lo == 0) {
+      const int t = island_tint[tw.island];
+      if (tw.island == tint_island_off[t]) tint_pos_off[t] = off_p;
     }
-#pragma unroll
-    for (int sft = 0; sft < GAUSS_DB; ++sft) {
-      const double w = wd[d0 - sft];
-#pragma unroll
-      for (int i = 0; i < GAUSS_OPT; ++i)
-        acc[i] = __dadd_rn(acc[i], __dmul_rn(__dadd_rn(bl[i + sft], br[i - sft + GAUSS_DB - 1]), w));
+    if (tile == n_tiles - 1) {
+      const u32 v = tile_cnt[tile];
+      tint_pos_off[n_tints] = off_p + (int)(v >> 16);
+      *n_cand_out = (i64)off_c + (i64)(v & 0xffffu);
     }
   }
-  double* dst = y + f0 + tw.lo + x0;
-  if (x0 + GAUSS_OPT <= cnt && ((((size_t)dst) & 15) == 0)) {
-#pragma unroll
-    for (int i = 0; i < GAUSS_OPT; i += 2) *reinterpret_cast<double2*>(dst + i) = make_double2(acc[i], acc[i + 1]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < GAUSS_OPT; ++i)
-      if (x0 + i < cnt) dst[i] = acc[i];
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K4 candidates: strict local maxima with plateau -> floor midpoint, ends never peaks, plus the
-// first and last sample of every island (scipy _local_maxima_1d; candidates_from_peaks :615-621).
-// Writes byte flags; the ordered list comes from the generic compaction.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GAUSS_THREADS) k_peaks(const TileWork* __restrict__ tiles,
-                                                        const int* __restrict__ island_sample_off,
-                                                        const double* __restrict__ y, u8* __restrict__ flag) {
-  const TileWork tw = tiles[blockIdx.x];
-  const int f0 = island_sample_off[tw.island];
-  const int n = island_sample_off[tw.island + 1] - f0;
-  const int cnt = min(TILE_SAMPLES, n - tw.lo);
-  const double* yi = y + f0;
-  for (int t = threadIdx.x; t < cnt; t += GAUSS_THREADS) {
-    int x = tw.lo + t;
-    if (x == 0 || x == n - 1) { flag[f0 + x] = 1; continue; }
-    double v = yi[x];
-    if (yi[x - 1] < v) {
-      int ia = x + 1;
-      while (ia < n - 1 && yi[ia] == v) ++ia;
-      if (yi[ia] < v) flag[f0 + ((x + ia - 1) >> 1)] = 1;
-    }
+  const int fbase = island_sample_off[tw.island] + tw.lo;
+  const u32 lt = (1u << lane) - 1u;
+  for (int it = 0; it < TILE_WORDS / 4; ++it) {
+    const int wi = warp * (TILE_WORDS / 4) + it;
+    const u32 cm = cm_in[wi], pm = pm_in[wi];
+    const int f = fbase + wi * 32 + lane;
+    if ((cm >> lane) & 1u) cand_flat[off_c + pre_c[wi] + __popc(cm & lt)] = f;
+    if ((pm >> lane) & 1u) vbuf[off_p + pre_p[wi] + __popc(pm & lt)] = y[f];
   }
 }
 
@@ -197,11 +358,12 @@ __global__ void k_cand_meta(const int* __restrict__ cand_flat, int n_cand, const
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3 variance threshold (one CTA per tint): ordered compaction of the positive smoothed samples,
-// then numpy's pairwise summation tree (DOUBLE_pairwise_sum) for mean and variance:
+// K3 variance threshold (one CTA per tint) over the tint's slice of the compacted positive samples
+// (written in sample order by k_phase1): numpy's pairwise summation tree (DOUBLE_pairwise_sum) for
+// mean and variance:
 //   n < 8: sequential; n <= 128: eight strided accumulators, combined ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)),
 //   remainder added sequentially; else split at n/2 rounded down to a multiple of 8.
-// Leaves (<=128 elements) are summed in parallel, the tree is combined in numpy's order by thread 0.
+// Leaves (<=128 elements) are summed in parallel by groups of 8 lanes, inner nodes level by level.
 // ---------------------------------------------------------------------------------------------
 #define THR_THREADS 256
 
@@ -212,134 +374,106 @@ __device__ __forceinline__ double pw_term(double v, double mean) {
   double d = __dsub_rn(v, mean);
   return __dmul_rn(d, d);
 }
+// one leaf by a group of 8 lanes: lane k owns numpy's accumulator r[k] (coalesced 64-byte reads), the
+// combine ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) is three shuffle steps, the remainder is added by lane 0
 template <bool SQ>
-__device__ double pw_leaf(const double* a, int n, double mean) {
-  if (n < 8) {
-    double res = 0.0;
-    for (int i = 0; i < n; ++i) res = __dadd_rn(res, pw_term<SQ>(a[i], mean));
-    return res;
+__device__ __forceinline__ double pw_leaf8(const double* __restrict__ a, int n, double mean, int sub) {
+  // every lane of the warp reaches the shuffles, whatever its group's n
+  const int n8 = n - (n % 8);
+  double r = 0.0;
+  if (n >= 8) {
+    r = pw_term<SQ>(a[sub], mean);
+    for (int i = 8; i < n8; i += 8) r = __dadd_rn(r, pw_term<SQ>(a[i + sub], mean));
   }
-  double r[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) r[k] = pw_term<SQ>(a[k], mean);
-  int i = 8;
-  for (; i < n - (n % 8); i += 8) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], pw_term<SQ>(a[i + k], mean));
-  }
-  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-  for (; i < n; ++i) res = __dadd_rn(res, pw_term<SQ>(a[i], mean));
-  return res;
-}
-
-// thread 0: enumerate leaves of the pairwise tree in order
-__device__ int pw_leaves(int n, int* leaf_off, int* leaf_len) {
-  int stack_off[40], stack_len[40];
-  int sp = 0, nl = 0;
-  stack_off[0] = 0; stack_len[0] = n; sp = 1;
-  while (sp > 0) {
-    --sp;
-    int o = stack_off[sp], l = stack_len[sp];
-    if (l <= 128) { leaf_off[nl] = o; leaf_len[nl] = l; ++nl; continue; }
-    int n2 = l / 2;
-    n2 -= n2 % 8;
-    // right pushed first so that the left half is expanded first (in-order leaves)
-    stack_off[sp] = o + n2; stack_len[sp] = l - n2; ++sp;
-    stack_off[sp] = o; stack_len[sp] = n2; ++sp;
-  }
-  return nl;
-}
-
-// thread 0: combine leaf sums following the recursion  pw(l) = pw(left) + pw(right)
-__device__ double pw_combine(int n, const double* leaf_sum) {
-  // iterative post-order: frames hold (len, state, left value)
-  int f_len[40];
-  int f_state[40];
-  double f_left[40];
-  int sp = 0, next_leaf = 0;
-  double ret = 0.0;
-  f_len[0] = n; f_state[0] = 0; sp = 1;
-  while (sp > 0) {
-    int t = sp - 1;
-    int l = f_len[t];
-    if (f_state[t] == 0) {
-      if (l <= 128) { ret = leaf_sum[next_leaf++]; --sp; continue; }
-      int n2 = l / 2;
-      n2 -= n2 % 8;
-      f_state[t] = 1;
-      f_len[sp] = n2; f_state[sp] = 0; ++sp;
-    } else if (f_state[t] == 1) {
-      f_left[t] = ret;
-      int n2 = l / 2;
-      n2 -= n2 % 8;
-      f_state[t] = 2;
-      f_len[sp] = l - n2; f_state[sp] = 0; ++sp;
+  r = __dadd_rn(r, __shfl_down_sync(0xffffffffu, r, 1));
+  r = __dadd_rn(r, __shfl_down_sync(0xffffffffu, r, 2));
+  r = __dadd_rn(r, __shfl_down_sync(0xffffffffu, r, 4));
+  if (sub == 0) {
+    if (n < 8) {
+      r = 0.0;
+      for (int i = 0; i < n; ++i) r = __dadd_rn(r, pw_term<SQ>(a[i], mean));
     } else {
-      ret = __dadd_rn(f_left[t], ret);
-      --sp;
+      for (int i = n8; i < n; ++i) r = __dadd_rn(r, pw_term<SQ>(a[i], mean));
     }
   }
-  return ret;
+  return r;  // valid on sub == 0
+}
+
+// The pairwise tree as an implicit heap (root 1, children 2i / 2i+1): a node of length l splits at
+// n2 = l/2 - (l/2)%8 while l > 128, so all leaves sit at the last two or three levels and the heap of a
+// tint with n positives has at most ~n/14 slots.  Every slot finds its (offset, length) by walking
+// down from the root (<= 24 steps); leaves are summed by groups of 8 lanes, inner nodes level by
+// level from the bottom -- no serial pass over the leaves.
+#define THR_HEAP_SMEM 2048  // heap slots held in shared memory (n <= ~28 k positives); else global scratch
+__device__ __forceinline__ bool pw_node(int n, int idx, int& off, int& len) {
+  // idx >= 1.  false if the slot is not a node of the tree (an ancestor is already a leaf)
+  int o = 0, l = n;
+  const int depth = 31 - __clz(idx);
+  for (int b = depth - 1; b >= 0; --b) {
+    if (l <= 128) return false;
+    int n2 = l / 2;
+    n2 -= n2 % 8;
+    if ((idx >> b) & 1) { o += n2; l -= n2; } else { l = n2; }
+  }
+  off = o;
+  len = l;
+  return true;
+}
+
+template <bool SQ>
+__device__ __forceinline__ double pw_tree(const double* __restrict__ v, int n, double mean, int levels, int* h_len,
+                                          double* h_val) {
+  // 1. leaves (groups of 8 lanes; whole warps run the shuffles)
+  const int slots = 1 << levels;
+  const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;
+  for (int i0 = 0; i0 < slots; i0 += THR_THREADS / 8) {
+    const int idx = i0 + grp;
+    int off = 0, len = 0;
+    const bool node = idx >= 1 && idx < slots && pw_node(n, idx, off, len);
+    const bool leaf = node && len <= 128;
+    const double r = pw_leaf8<SQ>(v + (leaf ? off : 0), leaf ? len : 0, mean, sub);
+    if (sub == 0 && idx < slots) {
+      h_len[idx] = node ? len : 0;
+      if (leaf) h_val[idx] = r;
+    }
+  }
+  __syncthreads();
+  // 2. inner nodes, bottom level first
+  for (int d = levels - 2; d >= 0; --d) {
+    for (int idx = (1 << d) + threadIdx.x; idx < (2 << d); idx += THR_THREADS)
+      if (h_len[idx] > 128) h_val[idx] = __dadd_rn(h_val[2 * idx], h_val[2 * idx + 1]);
+    __syncthreads();
+  }
+  return h_val[1];
 }
 
 __global__ void __launch_bounds__(THR_THREADS) k_threshold(const int* __restrict__ tint_order,
                                                           const int* __restrict__ tint_island_off,
                                                           const int* __restrict__ island_sample_off,
-                                                          const double* __restrict__ y, double vf,
-                                                          double* __restrict__ vbuf, int* __restrict__ leaf_off,
-                                                          int* __restrict__ leaf_len, double* __restrict__ leaf_sum,
-                                                          double* __restrict__ thr) {
-  __shared__ int sm_scan[40];
-  __shared__ int sm_nl;
-  __shared__ double sm_mean;
+                                                          const int* __restrict__ tint_pos_off, double vf,
+                                                          const double* __restrict__ vbuf, int* __restrict__ heap_len,
+                                                          double* __restrict__ heap_val, double* __restrict__ thr) {
+  __shared__ int s_len[THR_HEAP_SMEM];
+  __shared__ double s_val[THR_HEAP_SMEM];
   const int t = tint_order[blockIdx.x];  // largest tints first: the longest CTA must not start last
   const int s0 = island_sample_off[tint_island_off[t]];
-  const int s1 = island_sample_off[tint_island_off[t + 1]];
-  // ordered compaction of positives into vbuf[s0 ...]: 8 consecutive samples per thread, one block
-  // scan per 2048 samples
-  int base = 0;
-  for (int off = s0; off < s1; off += THR_THREADS * 8) {
-    const int i0 = off + threadIdx.x * 8;
-    double v[8];
-    int p = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      v[k] = (i0 + k < s1) ? y[i0 + k] : 0.0;
-      p += (v[k] > 0.0) ? 1 : 0;
-    }
-    int tot;
-    int ex = block_exclusive_scan<int>(p, &tot, sm_scan);
-    double* dst = vbuf + s0 + base + ex;
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (v[k] > 0.0) *dst++ = v[k];
-    base += tot;
-  }
-  const int n = base;
+  const int n = tint_pos_off[t + 1] - tint_pos_off[t];
   if (n == 0) {
     if (threadIdx.x == 0) thr[t] = __longlong_as_double(0x7ff8000000000000LL);  // NaN (:757-759, empty mean)
     return;
   }
-  // per-tint leaf scratch: leaves have > 64 elements once n > 128, so n/64 + 2 slots suffice
-  const int lbase = s0 / 64 + 2 * t;
-  int* lo = leaf_off + lbase;
-  int* ll = leaf_len + lbase;
-  double* ls = leaf_sum + lbase;
-  double* v = vbuf + s0;
+  // depth of the tree: the right child (l - n2 >= l/2) is the longer one, up to 15 elements longer
+  // than half; one spare level covers paths that alternate sides
+  int levels = 1;
+  for (int l = n; l > 128; ++levels) { int n2 = l / 2; n2 -= n2 % 8; l -= n2; }
+  levels += 1;
+  const bool small = (1 << levels) <= THR_HEAP_SMEM;
+  // global heap scratch of tint t: slots [s0/8 + 64 t, ...), at most n/14 + 4 of them (see THR_HEAP_ELEMS)
+  int* h_len = small ? s_len : heap_len + (s0 / 8 + 64 * t);
+  double* h_val = small ? s_val : heap_val + (s0 / 8 + 64 * t);
+  const double* v = vbuf + tint_pos_off[t];
+  const double mean = __ddiv_rn(pw_tree<false>(v, n, 0.0, levels, h_len, h_val), (double)n);
   __syncthreads();
-  if (threadIdx.x == 0) sm_nl = pw_leaves(n, lo, ll);
-  __syncthreads();
-  const int nl = sm_nl;
-  for (int k = threadIdx.x; k < nl; k += THR_THREADS) ls[k] = pw_leaf<false>(v + lo[k], ll[k], 0.0);
-  __syncthreads();
-  if (threadIdx.x == 0) sm_mean = __ddiv_rn(pw_combine(n, ls), (double)n);
-  __syncthreads();
-  const double mean = sm_mean;
-  for (int k = threadIdx.x; k < nl; k += THR_THREADS) ls[k] = pw_leaf<true>(v + lo[k], ll[k], mean);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double var = __ddiv_rn(pw_combine(n, ls), (double)n);
-    thr[t] = __dadd_rn(mean, __dmul_rn(vf, __dsqrt_rn(var)));
-  }
+  const double var = __ddiv_rn(pw_tree<true>(v, n, mean, levels, h_len, h_val), (double)n);
+  if (threadIdx.x == 0) thr[t] = __dadd_rn(mean, __dmul_rn(vf, __dsqrt_rn(var)));
 }

@@ -410,10 +410,15 @@ def config_jobs(cfg: int, scale: float = 1.0, seed: Optional[int] = None) -> lis
     return jobs
 
 
-def iter_config(cfg: int, scale: float = 1.0, seed: Optional[int] = None, workers: int = 1, chunk_reads: int = 200000):
+def iter_config(cfg: int, scale: float = 1.0, seed: Optional[int] = None, workers: int = 1, chunk_reads: int = 200000,
+                limit: Optional[int] = None):
     """Streams a config as lists of tints of about ``chunk_reads`` reads (same tints, same order as
-    ``make_config``), so that whole-transcriptome configs never have to sit in host memory at once."""
+    ``make_config``), so that whole-transcriptome configs never have to sit in host memory at once.
+    ``limit``: only the first ``limit`` tints (every tint has its own child seed, so a prefix of a
+    config is byte-identical to the same tints of the full config)."""
     jobs = config_jobs(cfg, scale, seed)
+    if limit is not None:
+        jobs = jobs[:limit]
     pool = None
     if workers > 1 and len(jobs) > 1:
         from multiprocessing import Pool

@@ -176,7 +176,7 @@ enum {
   FRS_OPT_SLAB_WORDS = 1,     /* read reps per DP CTA, in words of 32 (default 64): tints with more reps are
                                  processed by several CTAs per subproblem (multi-CTA mode) */
   FRS_OPT_KEEP_DP_TABLES = 2, /* also store the on-chip ins/out tables of small tints for FRS_TAP_DP_TABLES */
-  FRS_OPT_POLY_LONG_CLASS = 3, /* length class (4 per octave: 40 = 1024 bases, default) from which a poly-A/T
+  FRS_OPT_POLY_LONG_CLASS = 3, /* length class (4 per octave: 36 = 512 bases, default) from which a poly-A/T
                                  clip scan is done by a whole warp instead of one thread; 1 = every scan */
   FRS_OPT_LAZY_SEQ = 4,       /* 1 (default): frs_upload does NOT copy the sequence bit-planes; frs_run reads the
                                  clip lengths back after segmentation, gathers only the plane words of the
@@ -187,9 +187,10 @@ enum {
 int frs_set_option(frs_context* ctx, int key, long long value);
 
 /* transfer statistics of the last frs_upload / frs_run; returns the number of statistics */
-#define FRS_N_STATS 5
+#define FRS_N_STATS 7
 enum { FRS_STAT_H2D_UPLOAD = 0, FRS_STAT_H2D_RUN = 1, FRS_STAT_D2H_RUN = 2, FRS_STAT_CLIP_WORDS = 3,
-       FRS_STAT_SEQ_WORDS = 4 };
+       FRS_STAT_SEQ_WORDS = 4, FRS_STAT_POLY_TASKS = 5 /* poly-A/T scan tasks that survived the 5-stretch filter */,
+       FRS_STAT_POLY_LONG_TASKS = 6 /* of which scanned by a whole warp */ };
 int frs_get_stats(frs_context* ctx, long long* out, int n);
 
 /* ---- per-kernel device timing of the last frs_run (CUDA events on the context stream) ---- */

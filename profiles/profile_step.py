@@ -42,3 +42,4 @@ for _ in range(steps):
 torch.cuda.synchronize()
 rt.cudaProfilerStop()
 print("profiled %d step(s): %d reads, %d launches per step" % (steps, batch.n_reads, eng.launch_count()))
+print("stats", eng.stats())
