@@ -14,7 +14,7 @@ TEST INFRASTRUCTURE (authoring container only: needs ``/root/reference``).  For 
 The GPU-side check (``tests/full_config_check.py``) regenerates the same SPLIT directory on the GPU
 box, runs the drop-in CLI and compares every file hash with this manifest.
 
-Usage:  python oracle/pin_full_configs.py --cfg 3 [--work /tmp/frs_full] [--threads 8] [--impl reference|oracle]
+Usage:  python oracle/pin_full_configs.py --cfg 3 [--tints 4] [--work /tmp/frs_full] [--threads 8] [--impl reference|oracle]
 """
 import argparse
 import hashlib
@@ -43,11 +43,12 @@ def sha_file(p):
     return h.hexdigest()
 
 
-def write_config(cfg, split_dir, workers, scale=1.0):
-    """Streams the config to ``split_dir``; returns ({(contig, id): n_reads}, describe dict)."""
+def write_config(cfg, split_dir, workers, scale=1.0, limit=None, chunk_reads=200000):
+    """Streams the config (or its first ``limit`` tints) to ``split_dir``; returns
+    ({(contig, id): n_reads}, describe dict)."""
     tints_meta = {}
     tot = dict(tints=0, reads=0, intervals=0, positions=0, islands=0)
-    for part in synth.iter_config(cfg, scale=scale, workers=workers):
+    for part in synth.iter_config(cfg, scale=scale, workers=workers, limit=limit, chunk_reads=chunk_reads):
         synth.write_split_dir(part, split_dir)
         d = synth.describe(part)
         for k in tot:
@@ -91,6 +92,9 @@ def main():
     ap.add_argument("--threads", type=int, default=os.cpu_count())
     ap.add_argument("--impl", default="reference", choices=["reference", "oracle"])
     ap.add_argument("--keep", action="store_true")
+    ap.add_argument("--tints", type=int, default=None, help="pin only the first k tints of the config (cfg3: one "
+                    "100 k-read tint costs the reference tens of minutes)")
+    ap.add_argument("--chunk-reads", type=int, default=200000)
     a = ap.parse_args()
     name = "cfg%d" % a.cfg
     sd = os.path.join(a.work, name, "split")
@@ -98,7 +102,7 @@ def main():
     for d in (sd, od):
         shutil.rmtree(d, ignore_errors=True)
     t0 = time.time()
-    meta, desc = write_config(a.cfg, sd, a.threads)
+    meta, desc = write_config(a.cfg, sd, a.threads, limit=a.tints, chunk_reads=a.chunk_reads)
     keys = sorted(meta)
     t_gen = time.time() - t0
     print("%s: generated %s in %.0fs" % (name, desc, t_gen), flush=True)
@@ -116,7 +120,7 @@ def main():
     assert n_files == 2 * len(keys), (n_files, len(keys))
     gold = os.path.join(ROOT, "tests", "golden", "full")
     os.makedirs(gold, exist_ok=True)
-    man = dict(config=name, impl=a.impl, describe=desc, threads=a.threads, seconds=round(t_ref, 1),
+    man = dict(config=name, impl=a.impl, tints_pinned=len(keys), describe=desc, threads=a.threads, seconds=round(t_ref, 1),
                reads_per_sec=round(desc["reads"] / t_ref, 1), input_digest=digest(m_in), output_digest=digest(m_out),
                n_reads={k: meta[tuple([k.split("/")[0], int(k.split("/")[1])])] for k in m_in},
                inputs=m_in, outputs=m_out)

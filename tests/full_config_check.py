@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--batch-reads", type=int, default=400000)
     ap.add_argument("--keep", action="store_true")
     ap.add_argument("--tints", type=int, default=None, help="only the first k tints of the config")
+    ap.add_argument("--chunk-reads", type=int, default=200000, help="reads generated per pool round")
     a = ap.parse_args()
     name = "cfg%d" % a.cfg
     with open(os.path.join(ROOT, "tests", "golden", "full", name + ".json")) as fh:
@@ -60,7 +61,7 @@ def main():
     t0 = time.time()
     n_reads = 0
     made = set()
-    for part in synth.iter_config(a.cfg, workers=a.threads, limit=a.tints):
+    for part in synth.iter_config(a.cfg, workers=a.threads, limit=a.tints, chunk_reads=a.chunk_reads):
         synth.write_split_dir(part, sd)
         n_reads += sum(len(t["reads"]) for t in part)
         made.update("%s/%d" % (t["chr"], t["id"]) for t in part)
