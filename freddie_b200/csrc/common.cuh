@@ -235,3 +235,28 @@ __global__ void k_owner_tables(int T, int n_islands, int n_reps, int n_reads, co
   e -= n_reps;
   if (e < n_reads) read_tint[e] = upper_row(tint_read_off, T, (int)e);
 }
+
+// Genomic target coordinates of every read's intervals from its rep's flat-sample intervals: a read's
+// target intervals ARE its rep's (the dedupe key of read_split, freddie_segment.py:165-170), so a caller
+// may leave frs_batch.riv_ts / riv_te NULL and save their host-to-device copy.  One thread per read.
+__global__ void k_derive_riv(int n_reads, int n_islands, const int* __restrict__ read_rep, const int* __restrict__ read_iv_off,
+                             const int* __restrict__ rep_iv_off, const int* __restrict__ rep_fs, const int* __restrict__ rep_fe,
+                             const int* __restrict__ island_sample_off, const int* __restrict__ island_start,
+                             int* __restrict__ riv_ts, int* __restrict__ riv_te) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_reads) return;
+  const int k0 = read_iv_off[r], k1 = read_iv_off[r + 1];
+  int q = rep_iv_off[read_rep[r]];
+  int isl = -1, lo = 0, hi = -1, base = 0;
+  for (int k = k0; k < k1; ++k, ++q) {
+    const int fs = rep_fs[q], fe = rep_fe[q];
+    if (fs < lo || fs > hi) {  // intervals of a read are sorted: most stay in or move to a later island
+      isl = upper_row(island_sample_off, n_islands, fs);
+      lo = island_sample_off[isl];
+      hi = island_sample_off[isl + 1] - 1;
+      base = island_start[isl] - lo;
+    }
+    riv_ts[k] = fs + base;
+    riv_te[k] = fe + base;
+  }
+}

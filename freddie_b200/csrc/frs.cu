@@ -445,6 +445,8 @@ int frs_upload(frs_context* c, const frs_batch* b) {
     for (int r = b->tint_read_off[t]; r < b->tint_read_off[t + 1]; ++r) {
       const int rep = b->read_rep[r];
       if (rep < r0 || rep >= r1) return fail(c, FRS_ERR_ARG, "frs_upload: read %d points at rep %d of another tint", r, rep);
+      if (b->read_iv_off[r + 1] - b->read_iv_off[r] != b->rep_iv_off[rep + 1] - b->rep_iv_off[rep])
+        return fail(c, FRS_ERR_ARG, "frs_upload: read %d and its rep %d differ in their number of intervals", r, rep);
     }
     int s0 = b->island_sample_off[b->tint_island_off[t]], s1 = b->island_sample_off[b->tint_island_off[t + 1]];
     int single = (r1 - r0) <= SIG_REPS;
@@ -485,8 +487,14 @@ int frs_upload(frs_context* c, const frs_batch* b) {
   H2D(b_read_len, b->read_len, (size_t)N * 4);
   H2D(b_read_iv_off, b->read_iv_off, (size_t)(N + 1) * 4);
   H2D(b_read_seq_off, b->read_seq_off, (size_t)(N + 1) * 8);
-  H2D(b_riv_ts, b->riv_ts, (size_t)b->n_read_ivs * 4);
-  H2D(b_riv_te, b->riv_te, (size_t)b->n_read_ivs * 4);
+  const bool derive_riv = !b->riv_ts || !b->riv_te;  // NULL: derived on the device from the rep intervals
+  if (derive_riv) {
+    ENS(b_riv_ts, (size_t)b->n_read_ivs * 4);
+    ENS(b_riv_te, (size_t)b->n_read_ivs * 4);
+  } else {
+    H2D(b_riv_ts, b->riv_ts, (size_t)b->n_read_ivs * 4);
+    H2D(b_riv_te, b->riv_te, (size_t)b->n_read_ivs * 4);
+  }
   H2D(b_riv_qs, b->riv_qs, (size_t)b->n_read_ivs * 4);
   H2D(b_riv_qe, b->riv_qe, (size_t)b->n_read_ivs * 4);
   H2D(b_riv_cig_off, b->riv_cig_off, (size_t)(b->n_read_ivs + 1) * 4);
@@ -512,6 +520,11 @@ int frs_upload(frs_context* c, const frs_batch* b) {
   k_owner_tables<<<cdiv((i64)NI + NR + N, 256), 256, 0, c->stream>>>(
       T, NI, NR, N, c->b_tint_island_off.as<int>(), c->b_tint_rep_off.as<int>(), c->b_tint_read_off.as<int>(),
       c->b_island_tint.as<int>(), c->b_rep_tint.as<int>(), c->b_read_tint.as<int>());
+  if (derive_riv && N > 0)
+    k_derive_riv<<<cdiv(N, 256), 256, 0, c->stream>>>(N, NI, c->b_read_rep.as<int>(), c->b_read_iv_off.as<int>(),
+                                                      c->b_rep_iv_off.as<int>(), c->b_rep_fs.as<int>(), c->b_rep_fe.as<int>(),
+                                                      c->b_island_sample_off.as<int>(), c->b_island_start.as<int>(),
+                                                      c->b_riv_ts.as<int>(), c->b_riv_te.as<int>());
   H2D(b_tint_order, tint_order.data(), (size_t)T * 4);
   H2D(b_sig_work, sig.data(), sig.size() * sizeof(SigWork));
   H2D(b_tiles, tiles.data(), tiles.size() * sizeof(TileWork));
@@ -728,7 +741,7 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
     A.thr_table = d_tbl; A.thr_table_len = prm->thr_table_len; A.tp = prm->tp;
     A.lo = prm->lo; A.keep_tables = keep;
     A.tab = c->b_tab.as<int>(); A.final_flag = c->b_dpfinal.as<u8>(); A.err = d_err;
-    const int SMEM_BUDGET = 200 * 1024;
+    const int SMEM_BUDGET = 226 * 1024;  // of the 227 KB a CTA can opt in to: room for 4-word chunks up to n = 55
     // the classes are independent: launch them on side streams so that the few long CTAs of the large
     // classes overlap the many short ones (fork / join with events on the context stream)
     CK(cudaEventRecord(c->ev_fork, st));

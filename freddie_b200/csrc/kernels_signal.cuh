@@ -196,11 +196,17 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __rest
   for (int s = tid; s < span_r; s += GAUSS_THREADS) {  // whole warps: the ballot needs every lane
     int v = 0;
     if (s < span) {
-      int j = first + s;
+      const int j0 = first + s;
+      int j = j0;
       if (!interior) {
-        j %= n2;
-        if (j < 0) j += n2;
-        if (j >= n) j = n2 - 1 - j;
+        // scipy's reflect (d c b a | a b c d | d c b a): one fold covers every island longer than the halo
+        if (j0 < 0) j = -1 - j0;
+        else if (j0 >= n) j = n2 - 1 - j0;
+        if ((unsigned)j >= (unsigned)n) {  // island shorter than the halo: general period-2n fold
+          j = j0 % n2;
+          if (j < 0) j += n2;
+          if (j >= n) j = n2 - 1 - j;
+        }
       }
       v = yr[j];
       ext[s] = (double)v;
@@ -211,20 +217,20 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __rest
   if (tid < 2) nz[(span_r >> 5) + tid] = 0u;
   __syncthreads();
   // ---- Gaussian: a warp owns 256 consecutive samples, 32 per step (coalesced 256-byte stores) ----
+  u32 live = 0;  // bit it: step `it` of this warp has a non-zero input near its window (else its y is all 0)
   for (int it = 0; it < TILE_WORDS / 4; ++it) {
     const int xb = warp * (TILE_SAMPLES / 4) + it * 32;
     if (xb >= cnt) break;
     const int x = xb + lane;
-    // inputs of this step: staged samples [xb + 1, xb + 32 + 2*lw]
-    bool any = false;
-    for (int s = xb + 1; s < xb + 33 + 2 * lw; s += 32) {
-      u32 m = nz_word(nz, s);
-      const int rem = xb + 33 + 2 * lw - s;
-      if (rem < 32) m &= (1u << rem) - 1u;
-      any = any || (m != 0u);
-    }
+    // inputs of this step: staged samples [xb + 1, xb + 32 + 2*lw]; testing the whole mask words that
+    // hold them is conservative (a false positive only runs the sparse filter over zeros: same bits)
+    u32 any = 0;
+    for (int w = (xb + 1) >> 5; w <= (xb + 32 + 2 * lw) >> 5; ++w) any |= nz[w];
     double v = 0.0;
-    if (any && x < cnt) v = gauss_sparse(ext, nz, wd, lw, lw + 1 + x);
+    if (any) {
+      live |= 1u << it;
+      if (x < cnt) v = gauss_sparse(ext, nz, wd, lw, lw + 1 + x);
+    }
     if (x < cnt) {
       y[f0 + tw.lo + x] = v;
       yout[1 + x] = v;
@@ -245,10 +251,10 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __rest
     const int wi = warp * (TILE_WORDS / 4) + it;
     const int x = wi * 32 + lane, X = tw.lo + x;
     bool is_c = false, is_p = false;
-    if (x < cnt) {
+    if (x < cnt) is_c = (X == 0 || X == n - 1);
+    if (((live >> it) & 1u) && x < cnt) {  // the same warp smoothed these samples: a dead step is all zeros
       const double v = yout[1 + x];
       is_p = v > 0.0;
-      is_c = (X == 0 || X == n - 1);
       if (!is_c && is_p) {
         const double l = yout[x], r = yout[x + 2];
         if (l < v && r < v) is_c = true;

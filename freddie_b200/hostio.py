@@ -43,11 +43,16 @@ class ParsedBatch:
             raise _lib.FrsError(rc, msg)
         self.struct = _lib.FrsBatch()
         self.lib.frs_parsed_batch(self.handle, C.byref(self.struct))
+        # a read's target intervals are its rep's: the library derives them on the device (no copy)
+        self.lean = _lib.FrsBatch()
+        C.memmove(C.byref(self.lean), C.byref(self.struct), C.sizeof(_lib.FrsBatch))
+        self.lean.riv_ts = None
+        self.lean.riv_te = None
         self.n_tints = self.struct.n_tints
         self.n_reads = self.struct.n_reads
 
     def as_struct(self):
-        return self.struct
+        return self.lean
 
     def format(self, res, out_paths: List[bytes], log_paths: List[bytes], threads: int):
         n = len(out_paths)

@@ -37,6 +37,8 @@ class PackedBatch:
         self.n_tints = len(arrays["tint_island_off"]) - 1
         self.n_reads = len(arrays["read_rep"])
         self.n_reps = len(arrays["rep_weight"])
+        # a read's target intervals are its rep's: do not ship them twice (frs_batch.riv_ts / riv_te NULL)
+        self.derive_riv = True
 
     def counts(self) -> Dict[str, int]:
         a = self.arrays
@@ -51,6 +53,9 @@ class PackedBatch:
         for k, v in self.counts().items():
             setattr(b, k, v)
         for name in _lib.BATCH_ARRAYS:
+            if self.derive_riv and name in ("riv_ts", "riv_te"):
+                setattr(b, name, None)  # the library derives them from the rep intervals (no copy)
+                continue
             arr = self.arrays[name]
             assert arr.dtype == _DTYPES[name] and arr.flags["C_CONTIGUOUS"], name
             setattr(b, name, arr.ctypes.data_as(C.c_void_p))

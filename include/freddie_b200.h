@@ -82,8 +82,8 @@ typedef struct {
   const int32_t* read_len;     /* [n_reads] len(seq) */
   const int32_t* read_iv_off;  /* [n_reads+1] */
   const int64_t* read_seq_off; /* [n_reads+1] word offsets into the bit-planes */
-  const int32_t* riv_ts;       /* [n_read_ivs] genomic target start */
-  const int32_t* riv_te;       /* [n_read_ivs] genomic target end */
+  const int32_t* riv_ts;       /* [n_read_ivs] genomic target start; riv_ts / riv_te may be NULL: a read's target */
+  const int32_t* riv_te;       /* [n_read_ivs] genomic target end     intervals are its rep's (:165-170), derived on the device */
   const int32_t* riv_qs;       /* [n_read_ivs] query start */
   const int32_t* riv_qe;       /* [n_read_ivs] query end */
   const int32_t* riv_cig_off;  /* [n_read_ivs+1] */

@@ -23,7 +23,8 @@ tints = synth.make_config(2, scale=float(os.environ.get("SCALE", "1")), seed=2, 
 batch = pack_tints(tints).pin()
 prm = SegmentParams()
 lanes = []
-for _ in range(4):
+N_LANES = int(os.environ.get('LANES_MAX', '8'))
+for _ in range(N_LANES):
     e = Engine(0)
     r = None
     for _ in range(3):
@@ -54,9 +55,9 @@ def lane_work(idx, steps):
         e2._check(e2.lib.frs_download(e2.ctx, C.byref(rs)))
 
 
-for n_used in (1, 2, 3, 4):
+for n_used in [n for n in (1, 2, 3, 4, 6, 8) if n <= N_LANES]:
     for rep in range(2):
-        steps = 12
+        steps = 24
         per = [steps // n_used + (1 if i < steps % n_used else 0) for i in range(n_used)]
         ths = [threading.Thread(target=lane_work, args=(i, per[i])) for i in range(n_used)]
         torch.cuda.synchronize()

@@ -212,6 +212,27 @@ def test_lazy_clip_upload_equals_resident_planes(name, golden_set, eng):
         assert np.array_equal(lazy.arrays[k], full.arrays[k]), (name, k)
 
 
+@pytest.mark.parametrize("name", ["cfg1", "degenerate", "dup_heavy", "cfg3_mini", "cfg5_mini"])
+def test_derived_read_intervals_equal_uploaded_ones(name, golden_set, eng):
+    """frs_batch.riv_ts / riv_te NULL (default of the Python packer): the genomic target intervals of
+    every read are derived on the device from its rep's flat-sample intervals (freddie_segment.py:165-170:
+    the rep key IS the tuple of target intervals).  Results must equal those with the arrays uploaded,
+    and the transfer must shrink by exactly the two arrays."""
+    from freddie_b200.pack import pack_tints
+    tints, flags, _ = golden_set(name)
+    _, gprm = _params(flags)
+    batch = pack_tints(tints)
+    assert batch.derive_riv
+    lean = eng.segment_batch(batch, gprm)
+    h_lean = eng.stats()["h2d_upload"]
+    batch.derive_riv = False
+    full = eng.segment_batch(batch, gprm)
+    h_full = eng.stats()["h2d_upload"]
+    assert h_full - h_lean == 8 * batch.counts()["n_read_ivs"]
+    for k in lean.arrays:
+        assert np.array_equal(lean.arrays[k], full.arrays[k]), (name, k)
+
+
 def test_in_process_seam_has_reference_signature(golden_set):
     """segment(tint, sigma, smoothed_threshold, tp, vf, mps, lo, ignore_ends) mutates the tint like the
     reference (freddie_segment.py:738-844)."""
