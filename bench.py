@@ -245,10 +245,11 @@ def run_cuda_arm(args):
     eng.set_profiling(False)
 
     # ---- timed: end to end through the C ABI with HOST buffers.  Every step uploads its inputs from
-    # pinned host memory, runs, and downloads the results into pinned host memory.  Two library
-    # contexts (two host threads) take alternate steps so that the copies of one step overlap the
-    # kernels of the other, exactly as the CLI driver runs consecutive batches. ----
-    n_lanes = int(os.environ.get("FRS_E2E_LANES", "3"))
+    # pinned host memory, runs, and downloads the results into pinned host memory.  Several library
+    # contexts (one host thread each, up to 6: tests/e2e_probe.py shows the rate levelling off there)
+    # take alternate steps so that the copies and host round trips of one step overlap the kernels of
+    # the others, exactly as the CLI driver runs consecutive batches. ----
+    n_lanes = max(1, min(int(os.environ.get("FRS_E2E_LANES", "6")), args.steps))
     lanes = []
     for _ in range(n_lanes):
         e2 = Engine(local_rank)

@@ -450,9 +450,15 @@ int frs_upload(frs_context* c, const frs_batch* b) {
     }
     int s0 = b->island_sample_off[b->tint_island_off[t]], s1 = b->island_sample_off[b->tint_island_off[t + 1]];
     int single = (r1 - r0) <= SIG_REPS;
-    for (int w = s0; w < s1; w += SIG_BINS)
-      for (int r = r0; r < r1; r += SIG_REPS)
-        sig.push_back(SigWork{t, w, w + SIG_BINS < s1 ? w + SIG_BINS : s1, r, r + SIG_REPS < r1 ? r + SIG_REPS : r1, single});
+    const i64 n_endpoints = 2 * (i64)(b->rep_iv_off[r1] - b->rep_iv_off[r0]);
+    if (n_endpoints < (i64)(s1 - s0)) {  // sparse tint: endpoints go straight to the global signal
+      for (int r = r0; r < r1; r += SIG_DIRECT_REPS)
+        sig.push_back(SigWork{t, s0, s1, r, r + SIG_DIRECT_REPS < r1 ? r + SIG_DIRECT_REPS : r1, 2});
+    } else {
+      for (int w = s0; w < s1; w += SIG_BINS)
+        for (int r = r0; r < r1; r += SIG_REPS)
+          sig.push_back(SigWork{t, w, w + SIG_BINS < s1 ? w + SIG_BINS : s1, r, r + SIG_REPS < r1 ? r + SIG_REPS : r1, single});
+    }
     int R = r1 - r0, Rp = (R + 3) & ~3;
     for (int r = 0; r < Rp; r += COV_THREADS) cov_tiles.push_back(RepTile{t, r});
     for (int r = 0; r < R; r += DIG_REPS) dig_tiles.push_back(RepTile{t, r});

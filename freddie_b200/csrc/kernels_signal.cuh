@@ -15,6 +15,12 @@
 #define SIG_REPS 2048
 #define SIG_THREADS 256
 
+#define SIG_DIRECT_REPS 512  // reps per CTA in direct mode
+
+// single: 0 = histogram, RED flush (the tint has several rep chunks); 1 = histogram, plain store;
+// 2 = DIRECT: the tint has fewer endpoints than samples (typical tints: ~0.1 per sample), so zeroing
+// and flushing a 16 k-bin histogram per window costs more than the endpoints themselves -- the CTA
+// adds its endpoints straight to the zeroed global signal (same warp aggregation, one RED per site).
 struct SigWork { int tint; int win_lo; int win_hi; int rep_lo; int rep_hi; int single; };
 
 __device__ __forceinline__ void hist_add(int* hist, int bin, int w, bool active) {
@@ -37,8 +43,12 @@ __global__ void __launch_bounds__(SIG_THREADS) k_signal(const SigWork* __restric
   extern __shared__ int hist[];  // SIG_BINS ints (dynamic: above the 48 KB static limit)
   const SigWork wk = work[blockIdx.x];
   const int nb = wk.win_hi - wk.win_lo;
-  for (int b = threadIdx.x; b < nb; b += SIG_THREADS) hist[b] = 0;
-  __syncthreads();
+  const bool direct = wk.single == 2;
+  int* const yg = y_raw + wk.win_lo;
+  if (!direct) {
+    for (int b = threadIdx.x; b < nb; b += SIG_THREADS) hist[b] = 0;
+    __syncthreads();
+  }
   // one lane per rep, intervals walked in lock step so that lanes hit the same splice site together
   const int n_rep = wk.rep_hi - wk.rep_lo;
   const int n_round = (n_rep + SIG_THREADS - 1) / SIG_THREADS;
@@ -66,11 +76,17 @@ __global__ void __launch_bounds__(SIG_THREADS) k_signal(const SigWork* __restric
         const int fs = fs4[u], fe = fe4[u];
         bool use_s = have && !(ignore_ends && k == 0) && fs >= wk.win_lo && fs < wk.win_hi;
         bool use_e = have && !(ignore_ends && k == m - 1) && fe >= wk.win_lo && fe < wk.win_hi;
-        hist_add(hist, fs - wk.win_lo, w, use_s);
-        hist_add(hist, fe - wk.win_lo, w, use_e);
+        if (direct) {  // CTA-uniform; kept apart so that the histogram path compiles to shared-memory atomics
+          hist_add(yg, fs - wk.win_lo, w, use_s);
+          hist_add(yg, fe - wk.win_lo, w, use_e);
+        } else {
+          hist_add(hist, fs - wk.win_lo, w, use_s);
+          hist_add(hist, fe - wk.win_lo, w, use_e);
+        }
       }
     }
   }
+  if (direct) return;
   __syncthreads();
   for (int b = threadIdx.x; b < nb; b += SIG_THREADS) {
     int v = hist[b];

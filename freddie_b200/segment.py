@@ -67,7 +67,7 @@ def parse_args(argv=None):
                         help="Minimum reads support for splice site to support a breakpoint")
     # additive flags of the B200 implementation
     parser.add_argument("--gpus", type=int, default=0, help="GPUs to use (0 = all visible)")
-    parser.add_argument("--batch-reads", type=int, default=400000, help="Upper bound of reads per GPU batch")
+    parser.add_argument("--batch-reads", type=int, default=131072, help="Upper bound of reads per GPU batch")
     args = parser.parse_args(argv)
     assert 1 >= args.threshold_rate >= 0.5
     assert 10 > args.variance_factor > 0
@@ -137,16 +137,17 @@ def read_sequence(tint: dict, reads_tsv: str) -> None:
 # ------------------------------------------------------------------------------------------------
 # engines (one per GPU, created lazily)
 # ------------------------------------------------------------------------------------------------
-_ENGINES: Dict[int, Engine] = {}
+_ENGINES: Dict[tuple, Engine] = {}
 _ENGINES_LOCK = threading.Lock()
 
 
-def get_engine(device: int = 0) -> Engine:
+def get_engine(device: int = 0, lane: int = 0) -> Engine:
+    """One library context per (GPU, lane); a lane is one host thread of the directory driver."""
     with _ENGINES_LOCK:
-        e = _ENGINES.get(device)
+        e = _ENGINES.get((device, lane))
         if e is None:
             e = Engine(device)
-            _ENGINES[device] = e
+            _ENGINES[(device, lane)] = e
         return e
 
 
@@ -209,9 +210,12 @@ def _load_tint_py(split_dir, contig, tint_id):
 
 
 def run_directory(split_dir: str, outdir: str, prm: SegmentParams, threads: int = 1, gpus: int = 0,
-                  batch_reads: int = 400000, native: Optional[bool] = None, progress: bool = True) -> dict:
+                  batch_reads: int = 131072, native: Optional[bool] = None, progress: bool = True,
+                  lanes: int = 2) -> dict:
     """Segments every tint of a SPLIT directory; returns counters.  Output is independent of
-    ``threads``, ``gpus`` and batch composition."""
+    ``threads``, ``gpus``, ``lanes`` and batch composition.  Every GPU is fed by ``lanes`` host threads
+    (one library context each) that take the GPU's batches in turn, so that parsing and formatting of
+    one batch overlap the copies and kernels of another."""
     from . import hostio
     lib = _engine._lib.load()
     n_dev = lib.frs_device_count()
@@ -241,10 +245,22 @@ def run_directory(split_dir: str, outdir: str, prm: SegmentParams, threads: int 
             stats["reads"] += n_reads
             stats["dp_cells"] += cells
 
-    def worker(dev, idxs):
+    feeds = [iter(schedule.batches([jobs[i] for i in shards[d]], [costs[i] for i in shards[d]], batch_reads))
+             for d in range(n_gpus)]
+    feed_locks = [threading.Lock() for _ in range(n_gpus)]
+
+    def next_chunks(dev):
+        while not errors:
+            with feed_locks[dev]:
+                chunk = next(feeds[dev], None)
+            if chunk is None:
+                return
+            yield chunk
+
+    def worker(dev, lane):
         try:
-            eng = get_engine(dev)
-            for chunk in schedule.batches([jobs[i] for i in idxs], [costs[i] for i in idxs], batch_reads):
+            eng = get_engine(dev, lane)
+            for chunk in next_chunks(dev):
                 if native:
                     n_reads, cells = hostio.run_batch_native(eng, prm, split_dir, outdir, chunk, threads)
                 else:
@@ -260,7 +276,7 @@ def run_directory(split_dir: str, outdir: str, prm: SegmentParams, threads: int 
         except BaseException as e:  # propagate like the reference: the whole run aborts
             errors.append(e)
 
-    ths = [threading.Thread(target=worker, args=(d, shards[d])) for d in range(n_gpus)]
+    ths = [threading.Thread(target=worker, args=(d, k)) for d in range(n_gpus) for k in range(max(1, lanes))]
     for t in ths:
         t.start()
     for t in ths:

@@ -46,7 +46,7 @@ def main():
     ap.add_argument("--work", default="/tmp/frs_full")
     ap.add_argument("--threads", type=int, default=os.cpu_count())
     ap.add_argument("--gpus", type=int, default=0)
-    ap.add_argument("--batch-reads", type=int, default=400000)
+    ap.add_argument("--batch-reads", type=int, default=131072)
     ap.add_argument("--keep", action="store_true")
     ap.add_argument("--tints", type=int, default=None, help="only the first k tints of the config")
     ap.add_argument("--chunk-reads", type=int, default=200000, help="reads generated per pool round")
