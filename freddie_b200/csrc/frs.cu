@@ -19,7 +19,7 @@
 
 static thread_local char g_err[512] = "";
 
-#define FRS_SIDE_STREAMS 4
+#define FRS_SIDE_STREAMS 6  // 0..3: CTA classes of the DP (2..5) and its solver, high priority; 4..5: warp classes
 #ifndef DP_BIG_THREADS
 #define DP_BIG_THREADS 1024  // CTA size of the DP kernel for subproblems with more than 32 candidates
 #endif
@@ -48,7 +48,7 @@ struct frs_context {
   // host copy of the batch sizes and small offset arrays
   frs_batch hb;  // pointers here are DEVICE pointers after upload
   std::vector<int> h_tint_island_off, h_tint_rep_off, h_tint_read_off, h_island_sample_off;
-  int n_sig_work = 0, n_tiles = 0, n_cov_tiles = 0, n_dig_tiles = 0;
+  int n_sig_work = 0, n_sig_direct = 0, n_tiles = 0, n_cov_tiles = 0, n_dig_tiles = 0;
   // device buffers (grow-only)
   std::vector<DBuf*> all;
   DBuf b_tint_island_off, b_tint_rep_off, b_tint_read_off, b_island_start, b_island_sample_off, b_island_tint,
@@ -304,8 +304,11 @@ int frs_create(int device, frs_context** out) {
     delete c;
     return r;
   }
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   for (int i = 0; i < FRS_SIDE_STREAMS; ++i) {
-    cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking);
+    // the chain "large DP classes -> solver of the split subproblems" is the critical path of the stage
+    cudaStreamCreateWithPriority(&c->side[i], cudaStreamNonBlocking, i < 4 ? prio_hi : prio_lo);
     cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
   }
   cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
@@ -433,6 +436,7 @@ int frs_upload(frs_context* c, const frs_batch* b) {
   c->h_island_sample_off.assign(b->island_sample_off, b->island_sample_off + NI + 1);
   // ---- derived host tables ----
   std::vector<SigWork> sig;
+  std::vector<std::pair<int, int>> direct_runs;  // rep ranges of the sparse tints (k_signal direct mode)
   std::vector<TileWork> tiles;
   std::vector<RepTile> cov_tiles, dig_tiles;
   const int DIG_REPS = DIG_THREADS;
@@ -452,8 +456,9 @@ int frs_upload(frs_context* c, const frs_batch* b) {
     int single = (r1 - r0) <= SIG_REPS;
     const i64 n_endpoints = 2 * (i64)(b->rep_iv_off[r1] - b->rep_iv_off[r0]);
     if (n_endpoints < (i64)(s1 - s0)) {  // sparse tint: endpoints go straight to the global signal
-      for (int r = r0; r < r1; r += SIG_DIRECT_REPS)
-        sig.push_back(SigWork{t, s0, s1, r, r + SIG_DIRECT_REPS < r1 ? r + SIG_DIRECT_REPS : r1, 2});
+      // flat samples and reps need no tint: runs of consecutive sparse tints share full CTAs
+      if (!direct_runs.empty() && direct_runs.back().second == r0) direct_runs.back().second = r1;
+      else direct_runs.push_back(std::make_pair(r0, r1));
     } else {
       for (int w = s0; w < s1; w += SIG_BINS)
         for (int r = r0; r < r1; r += SIG_REPS)
@@ -473,7 +478,11 @@ int frs_upload(frs_context* c, const frs_batch* b) {
       return so[io[x + 1]] - so[io[x]] > so[io[y + 1]] - so[io[y]];
     });
   }
-  c->n_sig_work = (int)sig.size();
+  c->n_sig_work = (int)sig.size();  // histogram items first, then the direct ones
+  for (const auto& run : direct_runs)
+    for (int r = run.first; r < run.second; r += SIG_DIRECT_REPS)
+      sig.push_back(SigWork{-1, 0, b->n_samples, r, r + SIG_DIRECT_REPS < run.second ? r + SIG_DIRECT_REPS : run.second, 2});
+  c->n_sig_direct = (int)sig.size() - c->n_sig_work;
   c->n_tiles = (int)tiles.size();
   c->n_cov_tiles = (int)cov_tiles.size();
   c->n_dig_tiles = (int)dig_tiles.size();
@@ -594,10 +603,18 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
   ENS(b_yraw, L * 4);
   CK(cudaMemsetAsync(c->b_yraw.p, 0, L * 4, st));
   stage_begin(c, "signal");
-  k_signal<<<c->n_sig_work, SIG_THREADS, SIG_BINS * 4, st>>>(c->b_sig_work.as<SigWork>(), c->b_rep_iv_off.as<int>(),
-                                                             c->b_rep_weight.as<int>(), c->b_rep_fs.as<int>(),
-                                                             c->b_rep_fe.as<int>(), prm->ignore_ends, c->b_yraw.as<int>());
-  LAUNCHED();
+  if (c->n_sig_work > 0) {
+    k_signal<<<c->n_sig_work, SIG_THREADS, SIG_BINS * 4, st>>>(c->b_sig_work.as<SigWork>(), c->b_rep_iv_off.as<int>(),
+                                                               c->b_rep_weight.as<int>(), c->b_rep_fs.as<int>(),
+                                                               c->b_rep_fe.as<int>(), prm->ignore_ends, c->b_yraw.as<int>());
+    LAUNCHED();
+  }
+  if (c->n_sig_direct > 0) {  // no histogram: no shared memory, full occupancy
+    k_signal<<<c->n_sig_direct, SIG_THREADS, 0, st>>>(c->b_sig_work.as<SigWork>() + c->n_sig_work, c->b_rep_iv_off.as<int>(),
+                                                      c->b_rep_weight.as<int>(), c->b_rep_fs.as<int>(),
+                                                      c->b_rep_fe.as<int>(), prm->ignore_ends, c->b_yraw.as<int>());
+    LAUNCHED();
+  }
 
   ENS(b_y, L * 8);
   stage_begin(c, "smooth");
@@ -751,10 +768,11 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
     // the classes are independent: launch them on side streams so that the few long CTAs of the large
     // classes overlap the many short ones (fork / join with events on the context stream)
     CK(cudaEventRecord(c->ev_fork, st));
-    int side = 0;
+    bool used[FRS_SIDE_STREAMS] = {};
     for (int k = DP_CLASSES - 1; k >= 0; --k) {  // longest-running classes first
       if (cls_cnt[k] == 0) continue;
-      cudaStream_t ks = c->side[side % FRS_SIDE_STREAMS];
+      const int sidx = k >= 2 ? k - 2 : 4 + k;  // a stream per class
+      cudaStream_t ks = c->side[sidx];
       CK(cudaStreamWaitEvent(ks, c->ev_fork, 0));
       const DpWork* wl = c->b_work.as<DpWork>() + bases.base[k];
       if (k <= 1) {
@@ -777,18 +795,26 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
         }
       }
       LAUNCHED();
-      CK(cudaEventRecord(c->ev_join[side % FRS_SIDE_STREAMS], ks));
-      ++side;
+      CK(cudaEventRecord(c->ev_join[sidx], ks));
+      used[sidx] = true;
     }
-    for (int k = 0; k < side && k < FRS_SIDE_STREAMS; ++k) CK(cudaStreamWaitEvent(st, c->ev_join[k], 0));
     if (n_split > 0) {
-      stage_begin(c, "dp_solve");
+      // only CTA classes (streams 0..3) have split subproblems: their solver starts as soon as those are
+      // done and runs beside the warp classes
+      cudaStream_t ss = c->side[0];
+      if (!used[0]) CK(cudaStreamWaitEvent(ss, c->ev_fork, 0));
+      for (int k = 1; k < 4; ++k)
+        if (used[k]) CK(cudaStreamWaitEvent(ss, c->ev_join[k], 0));
       const int stage_n = max_n < DP_SMEM_MAX_N ? max_n : DP_SMEM_MAX_N;
       size_t sm2 = dps_smem_bytes(max_n, stage_n);
       if (sm2 > 220 * 1024) return fail(c, FRS_ERR_LIMIT, "subproblem with %d candidates exceeds the DP solver's budget", max_n);
-      k_dp_solve<<<(unsigned)n_split, DPS_THREADS, sm2, st>>>(A, c->b_split_list.as<int>(), max_n, stage_n);
+      k_dp_solve<<<(unsigned)n_split, DPS_THREADS, sm2, ss>>>(A, c->b_split_list.as<int>(), max_n, stage_n);
       LAUNCHED();
+      CK(cudaEventRecord(c->ev_join[0], ss));
+      used[0] = true;
     }
+    for (int k = 0; k < FRS_SIDE_STREAMS; ++k)
+      if (used[k]) CK(cudaStreamWaitEvent(st, c->ev_join[k], 0));
   }
 
   // ================= phase 3: refine, final positions, digits =================

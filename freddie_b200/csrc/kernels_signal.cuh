@@ -15,7 +15,7 @@
 #define SIG_REPS 2048
 #define SIG_THREADS 256
 
-#define SIG_DIRECT_REPS 512  // reps per CTA in direct mode
+#define SIG_DIRECT_REPS 256  // reps per CTA in direct mode (one per thread)
 
 // single: 0 = histogram, RED flush (the tint has several rep chunks); 1 = histogram, plain store;
 // 2 = DIRECT: the tint has fewer endpoints than samples (typical tints: ~0.1 per sample), so zeroing
