@@ -443,7 +443,7 @@ int frs_upload(frs_context* c, const frs_batch* b) {
   for (int t = 0; t < T; ++t) {
     for (int i = b->tint_island_off[t]; i < b->tint_island_off[t + 1]; ++i) {
       int n = b->island_sample_off[i + 1] - b->island_sample_off[i];
-      for (int lo = 0; lo < n; lo += TILE_SAMPLES) tiles.push_back(TileWork{i, lo});
+      for (int lo = 0; lo < n; lo += TILE_SAMPLES) tiles.push_back(TileWork{i, lo, b->island_sample_off[i], n});
     }
     int r0 = b->tint_rep_off[t], r1 = b->tint_rep_off[t + 1];
     for (int r = b->tint_read_off[t]; r < b->tint_read_off[t + 1]; ++r) {
@@ -455,7 +455,7 @@ int frs_upload(frs_context* c, const frs_batch* b) {
     int s0 = b->island_sample_off[b->tint_island_off[t]], s1 = b->island_sample_off[b->tint_island_off[t + 1]];
     int single = (r1 - r0) <= SIG_REPS;
     const i64 n_endpoints = 2 * (i64)(b->rep_iv_off[r1] - b->rep_iv_off[r0]);
-    if (n_endpoints < (i64)(s1 - s0)) {  // sparse tint: endpoints go straight to the global signal
+    if (n_endpoints < 8 * (i64)(s1 - s0)) {  // sparse tint: endpoints go straight to the global signal
       // flat samples and reps need no tint: runs of consecutive sparse tints share full CTAs
       if (!direct_runs.empty() && direct_runs.back().second == r0) direct_runs.back().second = r1;
       else direct_runs.push_back(std::make_pair(r0, r1));
@@ -636,6 +636,7 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
     k_smooth<<<c->n_tiles, GAUSS_THREADS, sm, st>>>(c->b_tiles.as<TileWork>(), d_island_sample_off, c->b_yraw.as<int>(),
                                                     d_gw, lw, c->b_y.as<double>(), d_cmask, d_pmask, d_tcnt, d_gsum);
     LAUNCHED();
+    stage_begin(c, "lists");
     k_tile_lists<<<c->n_tiles, GAUSS_THREADS, 0, st>>>(c->b_tiles.as<TileWork>(), c->n_tiles, d_island_sample_off,
                                                        d_island_tint, d_tint_island_off, T, d_cmask, d_pmask, d_tcnt,
                                                        d_gsum, c->b_y.as<double>(), c->b_cand_flat.as<int>(),

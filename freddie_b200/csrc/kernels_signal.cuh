@@ -18,9 +18,10 @@
 #define SIG_DIRECT_REPS 256  // reps per CTA in direct mode (one per thread)
 
 // single: 0 = histogram, RED flush (the tint has several rep chunks); 1 = histogram, plain store;
-// 2 = DIRECT: the tint has fewer endpoints than samples (typical tints: ~0.1 per sample), so zeroing
-// and flushing a 16 k-bin histogram per window costs more than the endpoints themselves -- the CTA
-// adds its endpoints straight to the zeroed global signal (same warp aggregation, one RED per site).
+// 2 = DIRECT: the tints have fewer than 8 endpoints per sample (typical tints: ~0.1), so zeroing and
+// flushing a 16 k-bin histogram per window costs more than the endpoints themselves -- the CTA adds the
+// endpoints of 256 reps (any tints: flat samples need no tint) straight to the zeroed global signal,
+// with the same warp aggregation (one RED per distinct site and warp).  Launched without shared memory.
 struct SigWork { int tint; int win_lo; int win_hi; int rep_lo; int rep_hi; int single; };
 
 __device__ __forceinline__ void hist_add(int* hist, int bin, int w, bool active) {
@@ -120,7 +121,9 @@ __global__ void __launch_bounds__(SIG_THREADS) k_signal(const SigWork* __restric
 #define TILE_WORDS (TILE_SAMPLES / 32)
 #define TILE_GROUP 1024  // tiles per group of the two-level count prefix
 
-struct TileWork { int island; int lo; };  // lo = island-local first sample of the tile
+// lo = island-local first sample of the tile; f0 / n = first flat sample / length of the island (copied
+// here so that a CTA learns its geometry from ONE 16-byte load instead of a chain of two)
+struct __align__(16) TileWork { int island; int lo; int f0; int n; };
 
 // staged window: logical index s = island sample lo - lw - 1 + s (one extra sample on both sides: the
 // neighbours of the tile's first and last output); centre of tile sample x = lw + 1 + x
@@ -199,8 +202,8 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __rest
   int* red = (int*)(p1sm + Lo.red);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const TileWork tw = tiles[blockIdx.x];
-  const int f0 = island_sample_off[tw.island];
-  const int n = island_sample_off[tw.island + 1] - f0;
+  const int f0 = tw.f0;
+  const int n = tw.n;
   const int cnt = min(TILE_SAMPLES, n - tw.lo);
   const int* yr = y_raw + f0;
   for (int d = tid; d <= lw; d += GAUSS_THREADS) wd[d] = gw[lw - d];
@@ -232,6 +235,14 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __rest
   }
   if (tid < 2) nz[(span_r >> 5) + tid] = 0u;
   __syncthreads();
+  // bit w of wm: mask word w of the staged window has a non-zero sample (at most 50 words at sigma = 50)
+  unsigned long long wm;
+  {
+    const int n_nz = (span_r >> 5) + 2;
+    const u32 lo32 = __ballot_sync(0xffffffffu, lane < n_nz && nz[lane] != 0u);
+    const u32 hi32 = __ballot_sync(0xffffffffu, 32 + lane < n_nz && nz[32 + lane] != 0u);
+    wm = ((unsigned long long)hi32 << 32) | lo32;
+  }
   // ---- Gaussian: a warp owns 256 consecutive samples, 32 per step (coalesced 256-byte stores) ----
   u32 live = 0;  // bit it: step `it` of this warp has a non-zero input near its window (else its y is all 0)
   for (int it = 0; it < TILE_WORDS / 4; ++it) {
@@ -240,8 +251,8 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __rest
     const int x = xb + lane;
     // inputs of this step: staged samples [xb + 1, xb + 32 + 2*lw]; testing the whole mask words that
     // hold them is conservative (a false positive only runs the sparse filter over zeros: same bits)
-    u32 any = 0;
-    for (int w = (xb + 1) >> 5; w <= (xb + 32 + 2 * lw) >> 5; ++w) any |= nz[w];
+    const int w_a = (xb + 1) >> 5, w_b = (xb + 32 + 2 * lw) >> 5;  // w_b - w_a <= 14
+    const bool any = ((wm >> w_a) & ((2ull << (w_b - w_a)) - 1ull)) != 0ull;
     double v = 0.0;
     if (any) {
       live |= 1u << it;
@@ -354,7 +365,7 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_tile_lists(const TileWork* __
       *n_cand_out = (i64)off_c + (i64)(v & 0xffffu);
     }
   }
-  const int fbase = island_sample_off[tw.island] + tw.lo;
+  const int fbase = tw.f0 + tw.lo;
   const u32 lt = (1u << lane) - 1u;
   for (int it = 0; it < TILE_WORDS / 4; ++it) {
     const int wi = warp * (TILE_WORDS / 4) + it;
