@@ -159,7 +159,7 @@ def run_reference_arm(args):
     total_steps = args.steps + args.warmup
     budget = 150.0 / max(total_steps, 1)  # seconds of CPU work per step
     rate_guess = 300.0 * cores
-    rates, cell_rates, sample = [], [], None
+    rates, cell_rates, secs, sample = [], [], [], None
     for s in range(total_steps):
         target = int(min(sum(len(t["reads"]) for t in tints), max(500, rate_guess * budget)))
         r, c, sample = oracle_rate(tints, cores, target)
@@ -167,11 +167,13 @@ def run_reference_arm(args):
         if s >= args.warmup:
             rates.append(r)
             cell_rates.append(c)
+            secs.append(sample["seconds"])
     v = float(np.mean(rates))
     line = dict(
         impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-        ms_per_step=None, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32+f64",
-        data="synthetic", config=dict(workload=WORKLOADS[args.workload], scale=args.scale),
+        ms_per_step=float(np.mean(secs)) * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32+f64",
+        data="synthetic", config=dict(workload=WORKLOADS[args.workload], scale=args.scale,
+                                      step="one bounded, size-stratified sample of the workload (see cpu_baseline.sample)"),
         cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port",
                           sample="oracle/segment_oracle.py (numpy restatement of freddie_segment.py; the reference "
                                  "tree is not present on the GPU box) on a size-stratified sample per step: %s" % sample),
@@ -188,7 +190,11 @@ def run_cuda_arm(args):
     # torchrun pins OMP_NUM_THREADS=1 in its children; the library's host gather (clip words) and the
     # native parser use OpenMP, so give every rank its share of the cores
     os.environ["OMP_NUM_THREADS"] = str(max(1, cores // max(world, 1)))
-    os.environ["NCCL_DEBUG"] = os.environ.get("FRS_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+    # keep stdout to the ONE JSON line: NCCL prints its version banner there at NCCL_DEBUG >= VERSION
+    if "FRS_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["FRS_NCCL_DEBUG"]
+    else:
+        os.environ.pop("NCCL_DEBUG", None)
     import torch
     if world > 1:
         import torch.distributed as dist
@@ -298,9 +304,9 @@ def run_cuda_arm(args):
         t = torch.tensor([t_dev, t_e2e, dp_ms, t_e2e_serial], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev, t_e2e, dp_ms, t_e2e_serial = [float(x) for x in t.tolist()]
-        u = torch.tensor([n_reads, tot_cells, launches], device="cuda", dtype=torch.int64)
+        u = torch.tensor([n_reads, tot_cells, launches, h2d, d2h], device="cuda", dtype=torch.int64)
         dist.all_reduce(u, op=dist.ReduceOp.SUM)
-        tot_reads, tot_cells, launches = [int(x) for x in u.tolist()]
+        tot_reads, tot_cells, launches, h2d, d2h = [int(x) for x in u.tolist()]  # whole-job totals
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
