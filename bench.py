@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "reads/sec through freddie_segment"
 UNIT = "reads/s"
-KERNEL_OF = {"signal": "k_signal", "smooth": "k_smooth", "coverage": "k_coverage",
+KERNEL_OF = {"signal": "k_signal", "smooth": "k_smooth", "lists": "k_tile_lists", "coverage": "k_coverage",
              "refine": "k_refine_filter+k_refine", "digits": "k_digits", "gaps": "k_gap_prep+k_gap_sizes", "dp": "k_dp*"}
 WORKLOADS = {
     "cfg2": "BASELINE configs[1]: synthetic chromosome-scale SPLIT, 200k reads across ~3k tints (seeded, per GPU)",
@@ -113,9 +113,11 @@ def algorithmic_bytes(counts: dict, sizes: dict, cov_elems: int) -> dict:
     dig = sizes["n_digit_bytes"]
     return {
         "signal": 8 * I + 8 * L,
-        # k_smooth does the Gaussian (a4: 16 L), the candidate peaks (a6: 8 L) and the ordered gather of
-        # the positive samples the variance threshold reads (a5: 8 L) in ONE pass over the signal
-        "smooth": 32 * L,
+        # k_smooth fuses the Gaussian (a4: 16 L) and the candidate peaks (a6: 8 L) into one pass;
+        # k_tile_lists writes the candidate list and gathers the positive samples the variance
+        # threshold reads (a5: 8 L)
+        "smooth": 24 * L,
+        "lists": 8 * L,
         "coverage": 8 * I + 4 * cov_elems,
         "dp": 4 * cov_elems + 4 * R,
         "refine": 8 * L,

@@ -22,7 +22,6 @@ enum {
   DEVERR_POLY_RANGE = 7,        // freddie_segment.py:410,441,450
   DEVERR_BACKTRACE = 8,         // internal: DP backtrace ran off the table
   DEVERR_ISLAND = 9,            // freddie_segment.py:668  interval ends in different islands
-  DEVERR_LOOKBACK = 10,         // internal: k_smooth's look-back never saw a predecessor tile
 };
 
 __device__ __forceinline__ void dev_fail(int* err, int code, int where) {

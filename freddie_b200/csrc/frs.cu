@@ -195,7 +195,6 @@ static const char* deverr_text(int code) {
     case DEVERR_GAP_RANGE: return "assert on unaligned gap coordinates (freddie_segment.py:462/466)";
     case DEVERR_POLY_RANGE: return "assert on poly-A/T coordinates (freddie_segment.py:410/441/450)";
     case DEVERR_BACKTRACE: return "internal: DP backtrace left the table";
-    case DEVERR_LOOKBACK: return "internal: k_smooth's look-back never saw a predecessor tile";
     default: return "unknown device assert";
   }
 }
@@ -623,17 +622,26 @@ int frs_run(frs_context* c, const frs_params* prm, frs_result_sizes* sizes_out) 
   ENS(b_cand_flat, (L / 2 + 2 * NI + 16) * 4);  // peaks are >= 2 apart, plus both ends of every island
   ENS(b_vbuf, L * 8);
   ENS(b_tint_pos_off, (size_t)(T + 1) * 4);
-  ENS(b_tile_state, (size_t)c->n_tiles * 8 + 64);
+  const size_t n_groups = (size_t)c->n_tiles / TILE_GROUP + 1;
+  ENS(b_tile_state, n_groups * 8 + (size_t)c->n_tiles * (2 * TILE_WORDS * 4 + 4) + 64);
   {
-    // one pass: Gaussian + candidate peaks + ordered lists (decoupled look-back over the tile counts)
-    unsigned long long* d_state = c->b_tile_state.as<unsigned long long>();
-    CK(cudaMemsetAsync(d_state, 0, (size_t)c->n_tiles * 8, st));
+    // group totals | per tile: candidate / positive ballot words, packed counts
+    unsigned long long* d_gsum = c->b_tile_state.as<unsigned long long>();
+    u32* d_cmask = (u32*)(d_gsum + n_groups);
+    u32* d_pmask = d_cmask + (size_t)c->n_tiles * TILE_WORDS;
+    u32* d_tcnt = d_pmask + (size_t)c->n_tiles * TILE_WORDS;
+    CK(cudaMemsetAsync(d_gsum, 0, n_groups * 8, st));
     const size_t sm = (size_t)p1_smem_layout(lw).total;
     if (sm > 48 * 1024) CK(cudaFuncSetAttribute(k_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_smooth<<<c->n_tiles, GAUSS_THREADS, sm, st>>>(c->b_tiles.as<TileWork>(), c->n_tiles, d_island_tint, d_tint_island_off, T,
-                                                    c->b_yraw.as<int>(), d_gw, lw, c->b_y.as<double>(), d_state,
-                                                    c->b_cand_flat.as<int>(), c->b_vbuf.as<double>(),
-                                                    c->b_tint_pos_off.as<int>(), c->b_counters.as<i64>(), d_err);
+    k_smooth<<<c->n_tiles, GAUSS_THREADS, sm, st>>>(c->b_tiles.as<TileWork>(), d_island_sample_off, c->b_yraw.as<int>(),
+                                                    d_gw, lw, c->b_y.as<double>(), d_cmask, d_pmask, d_tcnt, d_gsum);
+    LAUNCHED();
+    stage_begin(c, "lists");
+    k_tile_lists<<<c->n_tiles, GAUSS_THREADS, 0, st>>>(c->b_tiles.as<TileWork>(), c->n_tiles, d_island_sample_off,
+                                                       d_island_tint, d_tint_island_off, T, d_cmask, d_pmask, d_tcnt,
+                                                       d_gsum, c->b_y.as<double>(), c->b_cand_flat.as<int>(),
+                                                       c->b_vbuf.as<double>(), c->b_tint_pos_off.as<int>(),
+                                                       c->b_counters.as<i64>());
     LAUNCHED();
   }
 

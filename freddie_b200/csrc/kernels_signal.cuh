@@ -186,23 +186,13 @@ __device__ double gauss_global(const int* __restrict__ yr, int n, int x, const d
   return acc;
 }
 
-// tile_state[b] (zeroed before the launch): bits 0..30 candidates, 31..61 positive samples, 62..63 flag
-// (0 = not yet, 1 = this tile's own counts, 2 = inclusive prefix up to and including this tile)
-#define TS_FLAG_AGG (1ull << 62)
-#define TS_FLAG_INCL (2ull << 62)
-#define TS_VALUE_MASK ((1ull << 62) - 1ull)
-#define TS_FIELD_MASK 0x7fffffffull
-
-__global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __restrict__ tiles, int n_tiles,
-                                                         const int* __restrict__ island_tint,
-                                                         const int* __restrict__ tint_island_off, int n_tints,
+__global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __restrict__ tiles,
+                                                         const int* __restrict__ island_sample_off,
                                                          const int* __restrict__ y_raw,
                                                          const double* __restrict__ gw, int lw,
-                                                         double* __restrict__ y,
-                                                         unsigned long long* __restrict__ tile_state /* zeroed */,
-                                                         int* __restrict__ cand_flat, double* __restrict__ vbuf,
-                                                         int* __restrict__ tint_pos_off, i64* __restrict__ n_cand_out,
-                                                         int* __restrict__ err) {
+                                                         double* __restrict__ y, u32* __restrict__ cmask,
+                                                         u32* __restrict__ pmask, u32* __restrict__ tile_cnt,
+                                                         unsigned long long* __restrict__ group_sum /* zeroed */) {
   extern __shared__ __align__(16) unsigned char p1sm[];
   const P1Smem Lo = p1_smem_layout(lw);
   double* wd = (double*)(p1sm + Lo.wd);
@@ -282,8 +272,8 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __rest
     return (x >= -1 && x <= cnt) ? yout[1 + x] : gauss_global(yr, n, X, wd, lw);
   };
   int nc = 0, np = 0;
-  u32 cmw[TILE_WORDS / 4], pmw[TILE_WORDS / 4];  // this warp's ballot words (lane-uniform)
-#pragma unroll
+  u32* cm_out = cmask + (size_t)blockIdx.x * TILE_WORDS;
+  u32* pm_out = pmask + (size_t)blockIdx.x * TILE_WORDS;
   for (int it = 0; it < TILE_WORDS / 4; ++it) {
     const int wi = warp * (TILE_WORDS / 4) + it;
     const int x = wi * 32 + lane, X = tw.lo + x;
@@ -303,84 +293,21 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __rest
         }
       }
     }
-    cmw[it] = __ballot_sync(0xffffffffu, is_c);
-    pmw[it] = __ballot_sync(0xffffffffu, is_p);
-    nc += __popc(cmw[it]);
-    np += __popc(pmw[it]);
+    const u32 cm = __ballot_sync(0xffffffffu, is_c), pm = __ballot_sync(0xffffffffu, is_p);
+    if (lane == 0) { cm_out[wi] = cm; pm_out[wi] = pm; }
+    nc += __popc(cm);
+    np += __popc(pm);
   }
-  if (lane == 0) red[warp] = nc | (np << 16);  // at most 256 each
+  if (lane == 0) red[warp] = nc | (np << 16);
   __syncthreads();
-  int wc_off = 0, wp_off = 0, tot_c = 0, tot_p = 0;
-#pragma unroll
-  for (int w2 = 0; w2 < GAUSS_THREADS / 32; ++w2) {
-    const int v = red[w2];
-    if (w2 < warp) { wc_off += v & 0xffff; wp_off += v >> 16; }
-    tot_c += v & 0xffff;
-    tot_p += v >> 16;
-  }
-  // ---- single-pass ordered compaction: decoupled look-back over the tiles before this one.  Tiles are
-  // dispatched in blockIdx order, so every predecessor is resident or done; a predecessor publishes its
-  // own counts before it looks back itself, so nobody waits on a chain.  The spin is bounded: a broken
-  // assumption becomes a loud error, not a hang. ----
-  unsigned long long* s_excl = (unsigned long long*)(red + 8);
-  const int b_tile = blockIdx.x;
-  if (warp == 0) {
-    const unsigned long long own = (unsigned long long)tot_c | ((unsigned long long)tot_p << 31);
-    unsigned long long excl = 0ull;
-    if (b_tile == 0) {
-      if (lane == 0) atomicExch(&tile_state[0], own | TS_FLAG_INCL);
-    } else {
-      if (lane == 0) atomicExch(&tile_state[b_tile], own | TS_FLAG_AGG);
-      for (int j = b_tile - 1;; j -= 32) {
-        const int idx = j - lane;
-        unsigned long long v = TS_FLAG_INCL;  // before tile 0: an empty inclusive prefix
-        if (idx >= 0) {
-          const volatile unsigned long long* src = tile_state + idx;
-          int spins = 0;
-          while (((v = *src) >> 62) == 0ull) {
-            if (++spins > (1 << 22)) { dev_fail(err, DEVERR_LOOKBACK, b_tile); v = TS_FLAG_INCL; break; }
-            __nanosleep(64);
-          }
-        }
-        const u32 incl = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
-        const int stop = incl ? (__ffs(incl) - 1) : 31;  // nearest predecessor with a full prefix
-        unsigned long long part = lane <= stop ? (v & TS_VALUE_MASK) : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        excl += part;
-        if (incl) break;
-      }
-      if (lane == 0) atomicExch(&tile_state[b_tile], ((excl + own) & TS_VALUE_MASK) | TS_FLAG_INCL);
-    }
-    if (lane == 0) *s_excl = excl;
-  }
-  __syncthreads();
-  const unsigned long long excl = *s_excl;
-  const int base_c = (int)(excl & TS_FIELD_MASK), base_p = (int)((excl >> 31) & TS_FIELD_MASK);
-  int oc = base_c + wc_off, op = base_p + wp_off;
-  const u32 lt = (1u << lane) - 1u;
-#pragma unroll
-  for (int it = 0; it < TILE_WORDS / 4; ++it) {
-    const u32 cm = cmw[it], pm = pmw[it];
-    const int x = (warp * (TILE_WORDS / 4) + it) * 32 + lane;
-    if ((cm >> lane) & 1u) cand_flat[oc + __popc(cm & lt)] = f0 + tw.lo + x;
-    if ((pm >> lane) & 1u) vbuf[op + __popc(pm & lt)] = yout[1 + x];
-    oc += __popc(cm);
-    op += __popc(pm);
-  }
   if (tid == 0) {
-    if (tw.lo == 0) {  // first tile of an island: is it the first island of its tint?
-      const int t = island_tint[tw.island];
-      if (tw.island == tint_island_off[t]) tint_pos_off[t] = base_p;
-    }
-    if (b_tile == n_tiles - 1) {
-      tint_pos_off[n_tints] = base_p + tot_p;
-      *n_cand_out = (i64)base_c + (i64)tot_c;
-    }
+    const u32 v = (u32)(red[0] + red[1] + red[2] + red[3]);  // candidates | positives << 16
+    tile_cnt[blockIdx.x] = v;
+    // totals of every group of TILE_GROUP consecutive tiles: positives << 32 | candidates
+    atomicAdd(&group_sum[blockIdx.x / TILE_GROUP], ((unsigned long long)(v >> 16) << 32) | (unsigned long long)(v & 0xffffu));
   }
 }
 
-#if 0  // superseded by the single-pass compaction inside k_smooth (kept for reference of the two-pass scheme)
 // Ordered candidate list and ordered positive samples of one tile from its ballot words.  The tile's
 // offsets into the two lists = totals of the tile groups before its group (k_smooth's atomics) + counts
 // of the earlier tiles of its own group: at most (n_tiles / TILE_GROUP + TILE_GROUP) cached loads per
@@ -448,8 +375,6 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_tile_lists(const TileWork* __
     if ((pm >> lane) & 1u) vbuf[off_p + pre_p[wi] + __popc(pm & lt)] = y[f];
   }
 }
-
-#endif
 
 // after compaction: per candidate rank q -> island id, and the island / tint offset tables
 __global__ void k_cand_meta(const int* __restrict__ cand_flat, int n_cand, const int* __restrict__ island_sample_off,

@@ -12,7 +12,7 @@ import json
 import sys
 
 STAGE = [  # first match wins
-    ("k_signal", "signal"), ("k_smooth", "smooth"), ("k_tile_lists", "smooth"), ("k_threshold", "threshold"),
+    ("k_signal", "signal"), ("k_smooth", "smooth"), ("k_tile_lists", "lists"), ("k_threshold", "threshold"),
     ("k_cand_meta", "fixed"), ("k_fixed", "fixed"), ("k_sub_build", "subproblems"), ("k_tint_cov", "subproblems"),
     ("k_coverage", "coverage"), ("k_sub_fill", "dp_plan"), ("k_dp_solve", "dp_solve"), ("k_dp", "dp"),
     ("k_final_mark", "refine"), ("k_refine", "refine"), ("k_flag_", "finals"), ("k_final_meta", "finals"), ("k_digit_sizes", "finals"),
