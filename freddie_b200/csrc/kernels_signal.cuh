@@ -133,7 +133,7 @@ __host__ __device__ inline P1Smem p1_smem_layout(int lw) {
   P1Smem s;
   int o = 0;
   s.wd = o; o += (lw + 1) * 8;
-  s.ext = o; o += (span + 2) * 8;
+  s.ext = o; o += ((span + 2) * 4 + 7) & ~7;
   s.yout = o; o += (TILE_SAMPLES + 2) * 8;
   s.nz = o; o += ((span + 127) / 128 * 4 + 2) * 4;
   s.red = o; o += 16 * 4;
@@ -149,8 +149,10 @@ __device__ __forceinline__ u32 nz_word(const u32* nz, int s) {
 }
 
 // y of the sample whose staged centre index is c.  wd[d] = weight of the pair at distance d.
-__device__ __forceinline__ double gauss_sparse(const double* ext, const u32* nz, const double* wd, int lw, int c) {
-  double acc = __dmul_rn(ext[c], wd[0]);
+// The staged samples are the raw int32 counts: (double)a + (double)b == (double)(a + b) exactly for counts,
+// so a pair costs one conversion, and the tile takes half the shared memory of doubles (16 CTAs per SM).
+__device__ __forceinline__ double gauss_sparse(const int* ext, const u32* nz, const double* wd, int lw, int c) {
+  double acc = __dmul_rn((double)ext[c], wd[0]);
   if (lw == 0) return acc;
   if (lw <= 32) {
     // bit (d-1) of m: the pair at distance d has a non-zero input
@@ -161,12 +163,12 @@ __device__ __forceinline__ double gauss_sparse(const double* ext, const u32* nz,
     while (m) {
       const int d = 32 - __clz(m);  // outermost remaining pair first
       m &= ~(1u << (d - 1));
-      acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(ext[c - d], ext[c + d]), wd[d]));
+      acc = __dadd_rn(acc, __dmul_rn((double)(ext[c - d] + ext[c + d]), wd[d]));
     }
   } else {
     for (int d = lw; d >= 1; --d)
       if (nz_bit(nz, c - d) | nz_bit(nz, c + d))
-        acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(ext[c - d], ext[c + d]), wd[d]));
+        acc = __dadd_rn(acc, __dmul_rn((double)(ext[c - d] + ext[c + d]), wd[d]));
   }
   return acc;
 }
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __rest
   extern __shared__ __align__(16) unsigned char p1sm[];
   const P1Smem Lo = p1_smem_layout(lw);
   double* wd = (double*)(p1sm + Lo.wd);
-  double* ext = (double*)(p1sm + Lo.ext);    // raw tile + halo as doubles
+  int* ext = (int*)(p1sm + Lo.ext);          // raw tile + halo (int32 counts)
   double* yout = (double*)(p1sm + Lo.yout);  // yout[1 + x] = y of tile sample x; [0], [cnt+1] = neighbours
   u32* nz = (u32*)(p1sm + Lo.nz);            // bit s: staged sample s is non-zero
   int* red = (int*)(p1sm + Lo.red);
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __rest
         }
       }
       v = yr[j];
-      ext[s] = (double)v;
+      ext[s] = v;
     }
     const u32 m = __ballot_sync(0xffffffffu, v != 0);
     if (lane == 0) nz[s >> 5] = m;
