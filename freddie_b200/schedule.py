@@ -6,7 +6,8 @@ tints never interact, so they are sharded across GPUs with no exchange step (SUR
 from __future__ import annotations
 
 import os
-from typing import Iterable, List, Sequence, Tuple
+import threading
+from typing import Iterable, List, Optional, Sequence, Tuple
 
 
 def estimate_reads_from_bytes(split_bytes: int) -> float:
@@ -58,3 +59,29 @@ def batches(jobs: Sequence, costs: Sequence[Tuple[float, float]], batch_reads: i
         acc += n
     if cur:
         yield cur
+
+
+class BatchFeed:
+    """The batches of one GPU, handed out to that GPU's lanes (host threads) one at a time: every batch
+    goes to exactly one lane, in order, and ``stop()`` (an error in any lane) ends the feed for all."""
+
+    def __init__(self, jobs: Sequence, costs: Sequence[Tuple[float, float]], batch_reads: int):
+        self._it = iter(batches(jobs, costs, batch_reads))
+        self._lock = threading.Lock()
+        self._stopped = False
+
+    def stop(self) -> None:
+        self._stopped = True
+
+    def next(self) -> Optional[List]:
+        with self._lock:
+            if self._stopped:
+                return None
+            return next(self._it, None)
+
+    def __iter__(self):
+        while True:
+            chunk = self.next()
+            if chunk is None:
+                return
+            yield chunk

@@ -245,22 +245,13 @@ def run_directory(split_dir: str, outdir: str, prm: SegmentParams, threads: int 
             stats["reads"] += n_reads
             stats["dp_cells"] += cells
 
-    feeds = [iter(schedule.batches([jobs[i] for i in shards[d]], [costs[i] for i in shards[d]], batch_reads))
+    feeds = [schedule.BatchFeed([jobs[i] for i in shards[d]], [costs[i] for i in shards[d]], batch_reads)
              for d in range(n_gpus)]
-    feed_locks = [threading.Lock() for _ in range(n_gpus)]
-
-    def next_chunks(dev):
-        while not errors:
-            with feed_locks[dev]:
-                chunk = next(feeds[dev], None)
-            if chunk is None:
-                return
-            yield chunk
 
     def worker(dev, lane):
         try:
             eng = get_engine(dev, lane)
-            for chunk in next_chunks(dev):
+            for chunk in feeds[dev]:
                 if native:
                     n_reads, cells = hostio.run_batch_native(eng, prm, split_dir, outdir, chunk, threads)
                 else:
@@ -275,6 +266,8 @@ def run_directory(split_dir: str, outdir: str, prm: SegmentParams, threads: int 
                 tick(len(chunk), n_reads, cells)
         except BaseException as e:  # propagate like the reference: the whole run aborts
             errors.append(e)
+            for f in feeds:
+                f.stop()
 
     ths = [threading.Thread(target=worker, args=(d, k)) for d in range(n_gpus) for k in range(max(1, lanes))]
     for t in ths:

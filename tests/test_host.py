@@ -231,3 +231,55 @@ def test_sharding_world_size_2_gloo(tmp_path):
     assert sum(s["reads"] for s in info["shards"]) == info["total"]
     c = [s["cost"] for s in info["shards"]]
     assert abs(c[0] - c[1]) / max(c) < 0.25
+
+
+def test_batch_feed_hands_every_batch_to_exactly_one_lane():
+    """The CLI driver's lanes (host threads of one GPU) drain a shared feed: no batch twice, none lost,
+    and stop() -- an error in any lane -- ends the feed for everybody (the reference aborts the whole
+    run on an exception, freddie_segment.py:871-885)."""
+    import threading
+    from freddie_b200 import schedule
+    jobs = [("chr1", i) for i in range(1000)]
+    costs = [(1.0, 37.0 + (i % 11)) for i in range(1000)]
+    want = list(schedule.batches(jobs, costs, 500))
+    feed = schedule.BatchFeed(jobs, costs, 500)
+    got, lock = [], threading.Lock()
+
+    def lane():
+        for chunk in feed:
+            with lock:
+                got.append(chunk)
+
+    ths = [threading.Thread(target=lane) for _ in range(4)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert sorted(got) == sorted(want) and sum(len(c) for c in got) == len(jobs)
+    feed = schedule.BatchFeed(jobs, costs, 500)
+    assert feed.next() == want[0]
+    feed.stop()
+    assert feed.next() is None and list(feed) == []
+
+
+def test_packed_batch_ships_read_intervals_once(golden_set):
+    """frs_batch.riv_ts / riv_te are NULL by default (a read's target intervals are its rep's,
+    freddie_segment.py:165-170, and the library derives them on the device); with derive_riv off the
+    arrays are passed.  The rep intervals really do determine them (what k_derive_riv computes)."""
+    from freddie_b200.pack import pack_tints
+    tints, _, _ = golden_set("cfg2_small")
+    b = pack_tints(tints)
+    s = b.as_struct()
+    assert b.derive_riv and not s.riv_ts and not s.riv_te and s.riv_qs and s.rep_iv_fs
+    b.derive_riv = False
+    s = b.as_struct()
+    assert s.riv_ts and s.riv_te
+    a = b.arrays
+    iso, ist = a["island_sample_off"], a["island_start"]
+    for r in range(0, b.n_reads, 7):
+        k0, k1 = a["read_iv_off"][r], a["read_iv_off"][r + 1]
+        q0 = a["rep_iv_off"][a["read_rep"][r]]
+        fs, fe = a["rep_iv_fs"][q0:q0 + k1 - k0], a["rep_iv_fe"][q0:q0 + k1 - k0]
+        isl = np.searchsorted(iso, fs, side="right") - 1
+        assert np.array_equal(ist[isl] + fs - iso[isl], a["riv_ts"][k0:k1])
+        assert np.array_equal(ist[isl] + fe - iso[isl], a["riv_te"][k0:k1])
