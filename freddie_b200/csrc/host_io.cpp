@@ -6,10 +6,15 @@
 // any of its asserts (:136-140, :158-164, :181, :666-668), aborts the batch with a message naming it.
 // Tints are parsed in parallel (one file pair per task) and concatenated into one packed batch.
 #include <errno.h>
+#include <fcntl.h>
+#include <immintrin.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -20,7 +25,26 @@
 
 #include "../../include/freddie_b200.h"
 
+#include <chrono>
+
 namespace {
+
+// FRS_HOST_PROFILE=1: thread-seconds per parser phase on stderr after every frs_parse_tints
+struct HostProf {
+  std::atomic<long long> ns[6];
+  bool on;
+  HostProf() : on(getenv("FRS_HOST_PROFILE") != nullptr) { for (auto& x : ns) x = 0; }
+};
+HostProf g_prof;
+struct ProfScope {
+  int k;
+  std::chrono::steady_clock::time_point t0;
+  explicit ProfScope(int k_) : k(k_) { if (g_prof.on) t0 = std::chrono::steady_clock::now(); }
+  ~ProfScope() {
+    if (g_prof.on) g_prof.ns[k] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+  }
+};
+enum { PROF_LOAD = 0, PROF_SPLIT = 1, PROF_READS_LINES = 2, PROF_PLANES = 3, PROF_CONCAT = 4 };
 
 struct ReadMeta {
   int64_t rid;
@@ -47,23 +71,88 @@ struct TintData {
   std::string error;
 };
 
+// A whole input file, read-only.  Small files (the typical tint) are read into a buffer the thread
+// keeps and reuses: no page faults, no process-wide mmap lock with thousands of files in flight on all
+// threads.  Large files (giant tints) are mapped from the page cache instead of copied.  The parsers
+// only look at [p, p + n) -- nothing relies on a terminator.
 struct FileBuf {
   char* p = nullptr;
   size_t n = 0;
-  ~FileBuf() { free(p); }
-  bool load(const char* path, std::string& err) {
-    FILE* f = fopen(path, "rb");
-    if (!f) { err = std::string("FileNotFoundError: ") + path + ": " + strerror(errno); return false; }
-    fseek(f, 0, SEEK_END);
-    long sz = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    p = (char*)malloc((size_t)sz + 1);
-    n = sz > 0 ? fread(p, 1, (size_t)sz, f) : 0;
-    p[n] = 0;
-    fclose(f);
+  bool mapped = false;
+  static constexpr size_t SMALL = 8u << 20;
+  ~FileBuf() {
+    if (mapped) munmap(p, n);
+  }
+  static std::vector<char>& scratch(int which) {
+    static thread_local std::vector<char> buf[2];
+    return buf[which];
+  }
+  // `which`: 0 = split file, 1 = reads file (both may be alive in one thread at the same time)
+  bool load(const char* path, std::string& err, int which) {
+    ProfScope ps(PROF_LOAD);
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) { err = std::string("FileNotFoundError: ") + path + ": " + strerror(errno); return false; }
+    struct stat st;
+    if (fstat(fd, &st) != 0) { err = std::string("OSError: ") + path + ": " + strerror(errno); close(fd); return false; }
+    n = (size_t)st.st_size;
+    if (n > SMALL) {
+      void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+      if (m != MAP_FAILED) {
+        p = (char*)m;
+        mapped = true;
+        madvise(p, n, MADV_SEQUENTIAL);
+        close(fd);
+        return true;
+      }
+    }
+    std::vector<char>& buf = scratch(which);
+    if (buf.size() < n + 1) buf.resize(n + 1);
+    p = buf.data();
+    size_t got = 0;
+    while (got < n) {
+      ssize_t r = read(fd, p + got, n - got);
+      if (r < 0 && errno == EINTR) continue;
+      if (r <= 0) break;
+      got += (size_t)r;
+    }
+    n = got;
+    close(fd);
     return true;
   }
 };
+
+// isA / isT bit-planes of one read: bit k of word w = (seq[32 w + k] == 'A' / 'T'), exact upper-case
+// compare like the reference's  base == 'A'  (freddie_segment.py:352-367).
+static void planes_scalar(const char* b, uint32_t L, uint32_t* pa, uint32_t* pt) {
+  const uint32_t nw = (L + 31) / 32;
+  for (uint32_t w = 0; w < nw; ++w) {
+    const uint32_t n = std::min<uint32_t>(32, L - w * 32);
+    const char* c = b + (size_t)w * 32;
+    uint32_t ma = 0, mt = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+      ma |= (uint32_t)(c[k] == 'A') << k;
+      mt |= (uint32_t)(c[k] == 'T') << k;
+    }
+    pa[w] = ma;
+    pt[w] = mt;
+  }
+}
+// 32 bases per step: byte compare + movemask IS the plane word
+__attribute__((target("avx2"))) static void planes_avx2(const char* b, uint32_t L, uint32_t* pa, uint32_t* pt) {
+  const __m256i vA = _mm256_set1_epi8('A'), vT = _mm256_set1_epi8('T');
+  const uint32_t full = L / 32;
+  for (uint32_t w = 0; w < full; ++w) {
+    const __m256i v = _mm256_loadu_si256((const __m256i*)(b + (size_t)w * 32));
+    pa[w] = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, vA));
+    pt[w] = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, vT));
+  }
+  if (L % 32) planes_scalar(b + (size_t)full * 32, L % 32, pa + full, pt + full);
+}
+static void seq_planes(const char* b, uint32_t L, uint32_t* pa, uint32_t* pt) {
+  static const bool have_avx2 = __builtin_cpu_supports("avx2");
+  if (have_avx2) planes_avx2(b, L, pa, pt);
+  else planes_scalar(b, L, pa, pt);
+}
 
 inline bool is_digit(char c) { return c >= '0' && c <= '9'; }
 inline bool chr_first(unsigned char c) {
@@ -117,11 +206,39 @@ std::string line_snip(const char* s, const char* e) {
 
 bool parse_split_file(const char* path, TintData& T) {
   FileBuf fb;
-  if (!fb.load(path, T.error)) return false;
+  if (!fb.load(path, T.error, 0)) return false;
+  ProfScope ps(PROF_SPLIT);
   const char* s = fb.p;
   const char* end = fb.p + fb.n;
   bool have_header = false;
-  std::unordered_map<std::vector<int32_t>, int32_t, KeyHash> rep_index;
+  // read-rep dedupe (:165-170): open-addressing table of rep ids; a rep's key is compared against the
+  // target intervals of its first read (no per-rep key allocation)
+  std::vector<int32_t> rep_slot;       // -1 = empty, else rep id
+  std::vector<int32_t> rep_first_iv;   // rep -> first interval index (into riv_ts / riv_te) of its first read
+  size_t rep_mask = 0;
+  auto rep_table_init = [&](size_t n_reads) {
+    size_t cap = 64;
+    while (cap < 2 * n_reads + 2) cap <<= 1;
+    rep_slot.assign(cap, -1);
+    rep_mask = cap - 1;
+  };
+  auto rep_table_grow = [&]() {
+    std::vector<int32_t> old;
+    old.swap(rep_slot);
+    rep_slot.assign(old.size() * 2, -1);
+    rep_mask = rep_slot.size() - 1;
+    for (int32_t r : old) {
+      if (r < 0) continue;
+      uint64_t h = 1469598103934665603ull;
+      for (int32_t k = T.rep_iv_off[(size_t)r], f = rep_first_iv[(size_t)r]; k < T.rep_iv_off[(size_t)r + 1]; ++k, ++f) {
+        h ^= (uint32_t)T.riv_ts[(size_t)f]; h *= 1099511628211ull;
+        h ^= (uint32_t)T.riv_te[(size_t)f]; h *= 1099511628211ull;
+      }
+      size_t p = (size_t)h & rep_mask;
+      while (rep_slot[p] >= 0) p = (p + 1) & rep_mask;
+      rep_slot[p] = r;
+    }
+  };
   std::vector<int32_t> key;
   while (s < end) {
     const char* nl = (const char*)memchr(s, '\n', (size_t)(end - s));
@@ -160,6 +277,7 @@ bool parse_split_file(const char* path, TintData& T) {
         T.read_count = cnt;
         T.isl_s = is;
         T.isl_e = ie;
+        rep_table_init((size_t)std::max<int64_t>(cnt, 0) < (size_t)(fb.n / 16 + 16) ? (size_t)std::max<int64_t>(cnt, 0) : fb.n / 16 + 16);
         T.isl_off.assign(1, 0);
         int64_t off = 0;
         for (size_t i = 0; i < is.size(); ++i) {
@@ -249,11 +367,27 @@ bool parse_split_file(const char* path, TintData& T) {
         T.read_strand.push_back(m.strand == '+' ? 0 : 1);
         T.meta.push_back(m);
         // read rep (first-seen order, :165-170)
-        auto it = rep_index.find(key);
-        int32_t rep;
-        if (it == rep_index.end()) {
+        uint64_t kh = 1469598103934665603ull;
+        for (int32_t v : key) { kh ^= (uint32_t)v; kh *= 1099511628211ull; }
+        if ((T.rep_w.size() + 1) * 2 > rep_slot.size()) rep_table_grow();
+        size_t pos = (size_t)kh & rep_mask;
+        int32_t rep = -1;
+        const size_t n_key_iv = key.size() / 2;
+        while (rep_slot[pos] >= 0) {
+          const int32_t r = rep_slot[pos];
+          if ((size_t)(T.rep_iv_off[(size_t)r + 1] - T.rep_iv_off[(size_t)r]) == n_key_iv) {
+            const int32_t f = rep_first_iv[(size_t)r];
+            bool same = true;
+            for (size_t k = 0; k < n_key_iv && same; ++k)
+              same = T.riv_ts[(size_t)f + k] == key[2 * k] && T.riv_te[(size_t)f + k] == key[2 * k + 1];
+            if (same) { rep = r; break; }
+          }
+          pos = (pos + 1) & rep_mask;
+        }
+        if (rep < 0) {
           rep = (int32_t)T.rep_w.size();
-          rep_index.emplace(key, rep);
+          rep_slot[pos] = rep;
+          rep_first_iv.push_back((int32_t)iv0);
           T.rep_w.push_back(0);
           for (size_t k = 0; k < key.size(); k += 2) {
             int32_t ts = key[k], te = key[k + 1];
@@ -271,8 +405,6 @@ bool parse_split_file(const char* path, TintData& T) {
             T.rep_fe.push_back(T.isl_off[a] + (te - T.isl_s[a]));
           }
           T.rep_iv_off.push_back((int32_t)T.rep_fs.size());
-        } else {
-          rep = it->second;
         }
         T.rep_w[rep] += 1;
         T.read_rep.push_back(rep);
@@ -292,11 +424,13 @@ bool parse_split_file(const char* path, TintData& T) {
 // read_sequence (:174-185): cols 0 and 3 of every line; later duplicates of a rid win
 bool parse_reads_file(const char* path, TintData& T) {
   FileBuf fb;
-  if (!fb.load(path, T.error)) return false;
+  if (!fb.load(path, T.error, 1)) return false;
   std::unordered_map<int64_t, std::pair<const char*, uint32_t>> seqs;
   seqs.reserve(T.meta.size() * 2);
   const char* s = fb.p;
   const char* end = fb.p + fb.n;
+  {
+  ProfScope ps_lines(PROF_READS_LINES);
   while (s < end) {
     const char* nl = (const char*)memchr(s, '\n', (size_t)(end - s));
     const char* e = nl ? nl : end;
@@ -317,8 +451,10 @@ bool parse_reads_file(const char* path, TintData& T) {
     seqs[rid] = std::make_pair(f3, (uint32_t)(f3e - f3));
     s = next;
   }
+  }
   if (seqs.size() != T.meta.size()) { T.error = "AssertionError: assert len(rid_to_seq) == len(tint['reads']) (freddie_segment.py:181)"; return false; }
   // bit-planes
+  ProfScope ps_planes(PROF_PLANES);
   size_t words = 0;
   T.read_len.reserve(T.meta.size());
   for (const ReadMeta& m : T.meta) {
@@ -330,26 +466,13 @@ bool parse_reads_file(const char* path, TintData& T) {
     words += (L + 31) / 32;
     T.read_seq_off.push_back((int64_t)words);
   }
-  T.seq_a.assign(words, 0u);
-  T.seq_t.assign(words, 0u);
+  T.seq_a.resize(words);
+  T.seq_t.resize(words);
   size_t w0 = 0;
   for (const ReadMeta& m : T.meta) {
-    auto& sq = seqs[m.rid];
-    const char* b = sq.first;
-    uint32_t L = sq.second;
-    uint32_t nw = (L + 31) / 32;
-    for (uint32_t w = 0; w < nw; ++w) {
-      uint32_t n = std::min<uint32_t>(32, L - w * 32);
-      const char* c = b + (size_t)w * 32;
-      uint32_t ma = 0, mt = 0;
-      for (uint32_t k = 0; k < n; ++k) {
-        ma |= (uint32_t)(c[k] == 'A') << k;
-        mt |= (uint32_t)(c[k] == 'T') << k;
-      }
-      T.seq_a[w0 + w] = ma;
-      T.seq_t[w0 + w] = mt;
-    }
-    w0 += nw;
+    const auto& sq = seqs[m.rid];
+    seq_planes(sq.first, sq.second, T.seq_a.data() + w0, T.seq_t.data() + w0);
+    w0 += (sq.second + 31) / 32;
   }
   return true;
 }
@@ -384,6 +507,19 @@ void append_shift(std::vector<T>& dst, const std::vector<T>& src, T shift, size_
 
 }  // namespace
 
+// uninitialised storage for the large concatenated arrays (a std::vector would zero-fill ~400 MB
+// single-threaded before the parallel copy overwrites every element)
+template <typename T>
+struct RawBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~RawBuf() { free(p); }
+  void resize(size_t m) { free(p); p = (T*)malloc((m ? m : 1) * sizeof(T)); n = m; }
+  T* data() { return p; }
+  const T* data() const { return p; }
+  size_t size() const { return n; }
+};
+
 struct frs_parsed {
   std::vector<TintData> tints;
   // concatenated batch
@@ -391,7 +527,7 @@ struct frs_parsed {
       rep_weight, rep_iv_fs, rep_iv_fe, read_rep, read_len, read_iv_off, riv_ts, riv_te, riv_qs, riv_qe, riv_cig_off;
   std::vector<uint8_t> read_strand;
   std::vector<int64_t> read_seq_off;
-  std::vector<uint32_t> cigar, seq_a, seq_t;
+  RawBuf<uint32_t> cigar, seq_a, seq_t;
 };
 
 extern "C" {
@@ -422,14 +558,7 @@ int frs_parse_tints(const char* const* split_paths, const char* const* reads_pat
       return io ? FRS_ERR_IO : FRS_ERR_ARG;
     }
   // concatenate
-  P->tint_island_off.push_back(0);
-  P->tint_rep_off.push_back(0);
-  P->tint_read_off.push_back(0);
-  P->island_sample_off.push_back(0);
-  P->rep_iv_off.push_back(0);
-  P->read_iv_off.push_back(0);
-  P->riv_cig_off.push_back(0);
-  P->read_seq_off.push_back(0);
+  ProfScope* ps_cat = new ProfScope(PROF_CONCAT);
   int64_t smp = 0, reps = 0, rivs = 0, rep_ivs = 0, cig = 0, reads = 0, isl = 0, words = 0;
   for (TintData& T : P->tints) {
     smp += T.isl_off.back();
@@ -446,37 +575,96 @@ int frs_parse_tints(const char* const* split_paths, const char* const* reads_pat
     delete P;
     return FRS_ERR_LIMIT;
   }
-  P->seq_a.reserve((size_t)words);
-  P->seq_t.reserve((size_t)words);
-  for (TintData& T : P->tints) {
-    int32_t smp0 = P->island_sample_off.back();
-    int32_t rep0 = (int32_t)P->rep_weight.size();
-    P->island_start.insert(P->island_start.end(), T.isl_s.begin(), T.isl_s.end());
-    append_shift(P->island_sample_off, T.isl_off, smp0, 1);
-    append_shift(P->rep_iv_off, T.rep_iv_off, P->rep_iv_off.back(), 1);
-    P->rep_weight.insert(P->rep_weight.end(), T.rep_w.begin(), T.rep_w.end());
-    append_shift(P->rep_iv_fs, T.rep_fs, smp0);
-    append_shift(P->rep_iv_fe, T.rep_fe, smp0);
-    append_shift(P->read_rep, T.read_rep, rep0);
-    P->read_strand.insert(P->read_strand.end(), T.read_strand.begin(), T.read_strand.end());
-    P->read_len.insert(P->read_len.end(), T.read_len.begin(), T.read_len.end());
-    append_shift(P->read_iv_off, T.read_iv_off, P->read_iv_off.back(), 1);
-    append_shift(P->read_seq_off, T.read_seq_off, P->read_seq_off.back(), 1);
-    P->riv_ts.insert(P->riv_ts.end(), T.riv_ts.begin(), T.riv_ts.end());
-    P->riv_te.insert(P->riv_te.end(), T.riv_te.begin(), T.riv_te.end());
-    P->riv_qs.insert(P->riv_qs.end(), T.riv_qs.begin(), T.riv_qs.end());
-    P->riv_qe.insert(P->riv_qe.end(), T.riv_qe.begin(), T.riv_qe.end());
-    append_shift(P->riv_cig_off, T.riv_cig_off, P->riv_cig_off.back(), 1);
-    P->cigar.insert(P->cigar.end(), T.cigar.begin(), T.cigar.end());
-    P->seq_a.insert(P->seq_a.end(), T.seq_a.begin(), T.seq_a.end());
-    P->seq_t.insert(P->seq_t.end(), T.seq_t.begin(), T.seq_t.end());
-    P->tint_island_off.push_back((int32_t)P->island_start.size());
-    P->tint_rep_off.push_back((int32_t)P->rep_weight.size());
-    P->tint_read_off.push_back((int32_t)P->read_rep.size());
+  // every tint's slice of every array is known from the prefix sums: size once, copy in parallel
+  const size_t NT = P->tints.size();
+  struct Base { int64_t smp, reps, rep_ivs, rivs, cig, reads, isl, words; };
+  std::vector<Base> base(NT + 1);
+  {
+    Base a{0, 0, 0, 0, 0, 0, 0, 0};
+    for (size_t t = 0; t < NT; ++t) {
+      const TintData& T = P->tints[t];
+      base[t] = a;
+      a.smp += T.isl_off.back();
+      a.reps += (int64_t)T.rep_w.size();
+      a.rep_ivs += (int64_t)T.rep_fs.size();
+      a.rivs += (int64_t)T.riv_ts.size();
+      a.cig += (int64_t)T.cigar.size();
+      a.reads += (int64_t)T.meta.size();
+      a.isl += (int64_t)T.isl_s.size();
+      a.words += (int64_t)T.seq_a.size();
+    }
+    base[NT] = a;
+  }
+  P->tint_island_off.resize(NT + 1);
+  P->tint_rep_off.resize(NT + 1);
+  P->tint_read_off.resize(NT + 1);
+  P->island_start.resize((size_t)isl);
+  P->island_sample_off.resize((size_t)isl + 1);
+  P->rep_iv_off.resize((size_t)reps + 1);
+  P->rep_weight.resize((size_t)reps);
+  P->rep_iv_fs.resize((size_t)rep_ivs);
+  P->rep_iv_fe.resize((size_t)rep_ivs);
+  P->read_rep.resize((size_t)reads);
+  P->read_strand.resize((size_t)reads);
+  P->read_len.resize((size_t)reads);
+  P->read_iv_off.resize((size_t)reads + 1);
+  P->read_seq_off.resize((size_t)reads + 1);
+  P->riv_ts.resize((size_t)rivs);
+  P->riv_te.resize((size_t)rivs);
+  P->riv_qs.resize((size_t)rivs);
+  P->riv_qe.resize((size_t)rivs);
+  P->riv_cig_off.resize((size_t)rivs + 1);
+  P->cigar.resize((size_t)cig);
+  P->seq_a.resize((size_t)words);
+  P->seq_t.resize((size_t)words);
+  P->tint_island_off[NT] = (int32_t)isl;
+  P->tint_rep_off[NT] = (int32_t)reps;
+  P->tint_read_off[NT] = (int32_t)reads;
+  P->island_sample_off[0] = 0;
+  P->rep_iv_off[0] = 0;
+  P->read_iv_off[0] = 0;
+  P->riv_cig_off[0] = 0;
+  P->read_seq_off[0] = 0;
+  parallel_for((int)NT, n_threads, [&](int ti) {
+    TintData& T = P->tints[(size_t)ti];
+    const Base& b = base[(size_t)ti];
+    auto put = [](auto& dst, int64_t at, const auto& src, size_t skip, auto shift) {
+      for (size_t i = skip; i < src.size(); ++i) dst[(size_t)at + i - skip] = (decltype(shift))(src[i] + shift);
+    };
+    P->tint_island_off[(size_t)ti] = (int32_t)b.isl;
+    P->tint_rep_off[(size_t)ti] = (int32_t)b.reps;
+    P->tint_read_off[(size_t)ti] = (int32_t)b.reads;
+    put(P->island_start, b.isl, T.isl_s, 0, (int32_t)0);
+    put(P->island_sample_off, b.isl + 1, T.isl_off, 1, (int32_t)b.smp);
+    put(P->rep_iv_off, b.reps + 1, T.rep_iv_off, 1, (int32_t)b.rep_ivs);
+    put(P->rep_weight, b.reps, T.rep_w, 0, (int32_t)0);
+    put(P->rep_iv_fs, b.rep_ivs, T.rep_fs, 0, (int32_t)b.smp);
+    put(P->rep_iv_fe, b.rep_ivs, T.rep_fe, 0, (int32_t)b.smp);
+    put(P->read_rep, b.reads, T.read_rep, 0, (int32_t)b.reps);
+    put(P->read_strand, b.reads, T.read_strand, 0, (uint8_t)0);
+    put(P->read_len, b.reads, T.read_len, 0, (int32_t)0);
+    put(P->read_iv_off, b.reads + 1, T.read_iv_off, 1, (int32_t)b.rivs);
+    put(P->read_seq_off, b.reads + 1, T.read_seq_off, 1, (int64_t)b.words);
+    put(P->riv_ts, b.rivs, T.riv_ts, 0, (int32_t)0);
+    put(P->riv_te, b.rivs, T.riv_te, 0, (int32_t)0);
+    put(P->riv_qs, b.rivs, T.riv_qs, 0, (int32_t)0);
+    put(P->riv_qe, b.rivs, T.riv_qe, 0, (int32_t)0);
+    put(P->riv_cig_off, b.rivs + 1, T.riv_cig_off, 1, (int32_t)b.cig);
+    if (!T.cigar.empty()) memcpy(P->cigar.data() + b.cig, T.cigar.data(), T.cigar.size() * 4);
+    if (!T.seq_a.empty()) {
+      memcpy(P->seq_a.data() + b.words, T.seq_a.data(), T.seq_a.size() * 4);
+      memcpy(P->seq_t.data() + b.words, T.seq_t.data(), T.seq_t.size() * 4);
+    }
     // per-tint copies of the big arrays are no longer needed
     std::vector<uint32_t>().swap(T.seq_a);
     std::vector<uint32_t>().swap(T.seq_t);
     std::vector<uint32_t>().swap(T.cigar);
+  });
+  delete ps_cat;
+  if (g_prof.on) {
+    fprintf(stderr, "[frs host profile] thread-seconds: load %.3f  split rows %.3f  reads lines %.3f  bit-planes %.3f  concat %.3f\n",
+            g_prof.ns[0] * 1e-9, (g_prof.ns[1]) * 1e-9, g_prof.ns[2] * 1e-9, g_prof.ns[3] * 1e-9, g_prof.ns[4] * 1e-9);
+    for (auto& x : g_prof.ns) x = 0;
   }
   *out = P;
   return 0;
