@@ -7,6 +7,9 @@ packed batch and writes the SEGMENT files straight from the result arrays.
 from __future__ import annotations
 
 import ctypes as C
+import os
+import sys
+import time
 from typing import List, Sequence, Tuple
 
 from . import _lib
@@ -77,11 +80,19 @@ class ParsedBatch:
 
 def run_batch_native(eng: Engine, prm: SegmentParams, split_dir: str, outdir: str,
                      chunk: Sequence[Tuple[str, int]], threads: int):
+    prof = os.environ.get("FRS_CLI_PROFILE")
+    t0 = time.perf_counter()
     sp, rp, op, lp = _paths(split_dir, outdir, chunk)
     pb = ParsedBatch(sp, rp, threads)
+    t1 = time.perf_counter()
     try:
         res = eng.segment_batch(pb, prm)
+        t2 = time.perf_counter()
         pb.format(res, op, lp, threads)
+        t3 = time.perf_counter()
+        if prof:
+            sys.stderr.write("[frs cli profile] batch of %d tints / %d reads: parse %.3f s  upload+kernels+download %.3f s  "
+                             "format+write %.3f s\n" % (len(chunk), pb.n_reads, t1 - t0, t2 - t1, t3 - t2))
         return pb.n_reads, int(res.sizes["dp_cells"])
     finally:
         pb.close()

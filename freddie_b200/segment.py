@@ -20,6 +20,7 @@ import os
 import re
 import sys
 import threading
+import time
 from math import ceil
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -250,7 +251,11 @@ def run_directory(split_dir: str, outdir: str, prm: SegmentParams, threads: int 
 
     def worker(dev, lane):
         try:
+            t_eng = time.perf_counter()
             eng = get_engine(dev, lane)
+            if os.environ.get("FRS_CLI_PROFILE"):
+                sys.stderr.write("[frs cli profile] context of GPU %d lane %d ready after %.3f s\n"
+                                 % (dev, lane, time.perf_counter() - t_eng))
             for chunk in feeds[dev]:
                 if native:
                     n_reads, cells = hostio.run_batch_native(eng, prm, split_dir, outdir, chunk, threads)
