@@ -204,216 +204,309 @@ std::string line_snip(const char* s, const char* e) {
   return std::string(s, n);
 }
 
-bool parse_split_file(const char* path, TintData& T) {
+// ---- tint header:  #<chr>\t<id>\t<s>-<e>(,<s>-<e>)*\t<count>   (tint_prog, :22) ----
+bool parse_header_line(const char* s, const char* e, const char* path, bool have_header, TintData& T) {
+  const char* q = s + 1;
+  const char* c0 = q;
+  int64_t id, cnt;
+  std::vector<int32_t> is, ie;
+  if (!parse_chr(q, e)) goto bad_header;
+  {
+    std::string chr(c0, (size_t)(q - c0));
+    if (!expect(q, e, '\t') || !parse_uint(q, e, id) || !expect(q, e, '\t')) goto bad_header;
+    for (;;) {
+      int32_t a, b;
+      if (!parse_i32(q, e, a) || !expect(q, e, '-') || !parse_i32(q, e, b)) goto bad_header;
+      is.push_back(a);
+      ie.push_back(b);
+      if (q < e && *q == ',') { ++q; continue; }
+      break;
+    }
+    if (!expect(q, e, '\t') || !parse_uint(q, e, cnt) || q != e) goto bad_header;
+    if (have_header) {
+      if (id == T.id) T.error = "AssertionError: Transcriptional interval with id " + std::to_string(id) + " is repeated!";
+      else T.error = std::string("AssertionError: assert len(tints) == 1 (freddie_segment.py:699): ") + path;
+      return false;
+    }
+    for (size_t i = 0; i + 1 < is.size(); ++i)
+      if (!(ie[i] < is[i + 1])) { T.error = "AssertionError: tint intervals overlap or are unordered (freddie_segment.py:138)"; return false; }
+    for (size_t i = 0; i < is.size(); ++i)
+      if (!(is[i] < ie[i])) { T.error = "AssertionError: empty tint interval (freddie_segment.py:140)"; return false; }
+    T.chr = chr;
+    T.id = id;
+    T.read_count = cnt;
+    T.isl_s = is;
+    T.isl_e = ie;
+    T.isl_off.assign(1, 0);
+    int64_t off = 0;
+    for (size_t i = 0; i < is.size(); ++i) {
+      off += (int64_t)ie[i] - is[i] + 1;
+      if (off > INT32_MAX) { T.error = "tint spans more than 2^31 samples"; return false; }
+      T.isl_off.push_back((int32_t)off);
+    }
+  }
+  return true;
+bad_header:
+  T.error = std::string("AttributeError: tint header does not match tint_prog (freddie_segment.py:22): ") + line_snip(s, e);
+  return false;
+}
+
+// ---- read row:  <rid>\t<name>\t<chr>\t<strand>\t<tint>\t<iv>(\t<iv>)*   (read_prog, :28) ----
+// Appends the row to C (meta, text, intervals, CIGARs); the read-rep dedupe is a separate step
+// (RepTable::add_read) so that the rows of a giant tint can be parsed by several threads.
+bool parse_read_row(const char* s, const char* e, bool have_header, int64_t tint_id, TintData& C) {
+  const char* q = s;
+  ReadMeta m;
+  if (!parse_uint(q, e, m.rid) || !expect(q, e, '\t')) goto bad_read;
+  {
+    const char* n0 = q;
+    while (q < e && name_char((unsigned char)*q)) ++q;
+    size_t nlen = (size_t)(q - n0);
+    if (nlen < 1 || nlen > 254 || !expect(q, e, '\t')) goto bad_read;
+    const char* c0 = q;
+    if (!parse_chr(q, e)) goto bad_read;
+    size_t clen = (size_t)(q - c0);
+    if (!expect(q, e, '\t')) goto bad_read;
+    if (q >= e || (*q != '+' && *q != '-')) goto bad_read;
+    m.strand = *q++;
+    if (!expect(q, e, '\t') || !parse_uint(q, e, m.tint) || !expect(q, e, '\t')) goto bad_read;
+    if (!have_header || m.tint != tint_id) { C.error = "KeyError: read row refers to tint " + std::to_string(m.tint) + " (freddie_segment.py:162)"; return false; }
+    m.name_off = (uint32_t)C.text.size();
+    m.name_len = (uint32_t)nlen;
+    C.text.append(n0, nlen);
+    m.chr_off = (uint32_t)C.text.size();
+    m.chr_len = (uint32_t)clen;
+    C.text.append(c0, clen);
+    size_t iv0 = C.riv_ts.size();
+    for (;;) {
+      int32_t ts, te, qs, qe;
+      if (!parse_i32(q, e, ts) || !expect(q, e, '-') || !parse_i32(q, e, te) || !expect(q, e, ':') ||
+          !parse_i32(q, e, qs) || !expect(q, e, '-') || !parse_i32(q, e, qe) || !expect(q, e, ':'))
+        goto bad_read;
+      int nops = 0;
+      while (q < e && is_digit(*q)) {
+        int64_t c;
+        if (!parse_uint(q, e, c) || q >= e) goto bad_read;
+        uint32_t op;
+        switch (*q) {
+          case 'M': case 'X': case '=': op = 0; break;
+          case 'I': op = 1; break;
+          case 'D': op = 2; break;
+          case 'N': case 'S': case 'H': case 'P': op = 3; break;
+          default: goto bad_read;
+        }
+        ++q;
+        if (c >= (1ll << 28)) { C.error = "CIGAR operation longer than 2^28"; return false; }
+        C.cigar.push_back(((uint32_t)c << 4) | op);
+        ++nops;
+      }
+      if (nops == 0) goto bad_read;
+      C.riv_ts.push_back(ts);
+      C.riv_te.push_back(te);
+      C.riv_qs.push_back(qs);
+      C.riv_qe.push_back(qe);
+      C.riv_cig_off.push_back((int32_t)C.cigar.size());
+      if (q < e && *q == '\t') { ++q; continue; }
+      break;
+    }
+    if (q != e) goto bad_read;
+    size_t iv1 = C.riv_ts.size();
+    for (size_t k = iv0; k + 1 < iv1; ++k)
+      if (!(C.riv_te[k] <= C.riv_ts[k + 1] && C.riv_qe[k] <= C.riv_qs[k + 1])) {
+        C.error = "AssertionError: read intervals out of order (freddie_segment.py:158)";
+        return false;
+      }
+    for (size_t k = iv0; k < iv1; ++k)
+      if (!(C.riv_ts[k] < C.riv_te[k] && C.riv_qs[k] < C.riv_qe[k])) {
+        C.error = "AssertionError: empty read interval (freddie_segment.py:160)";
+        return false;
+      }
+    C.read_iv_off.push_back((int32_t)iv1);
+    C.read_strand.push_back(m.strand == '+' ? 0 : 1);
+    C.meta.push_back(m);
+  }
+  return true;
+bad_read:
+  C.error = std::string("AttributeError: read row does not match read_prog (freddie_segment.py:28): ") + line_snip(s, e);
+  return false;
+}
+
+// read-rep dedupe (:165-170): reps are the distinct tuples of target intervals in first-seen order.
+// Open-addressing table of rep ids; a rep's key is compared against the target intervals of its first
+// read (no per-rep key allocation).
+struct RepTable {
+  std::vector<int32_t> slot;       // -1 = empty, else rep id
+  std::vector<int32_t> first_iv;   // rep -> first interval index (into riv_ts / riv_te) of its first read
+  size_t mask = 0;
+  static uint64_t hash_ivs(const TintData& T, size_t f, size_t n) {
+    uint64_t h = 1469598103934665603ull;
+    for (size_t k = 0; k < n; ++k) {
+      h ^= (uint32_t)T.riv_ts[f + k]; h *= 1099511628211ull;
+      h ^= (uint32_t)T.riv_te[f + k]; h *= 1099511628211ull;
+    }
+    return h;
+  }
+  void init(size_t n_reads) {
+    size_t cap = 64;
+    while (cap < 2 * n_reads + 2) cap <<= 1;
+    slot.assign(cap, -1);
+    mask = cap - 1;
+  }
+  void grow(const TintData& T) {
+    std::vector<int32_t> old;
+    old.swap(slot);
+    slot.assign(old.size() * 2, -1);
+    mask = slot.size() - 1;
+    for (int32_t r : old) {
+      if (r < 0) continue;
+      size_t p = (size_t)hash_ivs(T, (size_t)first_iv[(size_t)r], (size_t)(T.rep_iv_off[(size_t)r + 1] - T.rep_iv_off[(size_t)r])) & mask;
+      while (slot[p] >= 0) p = (p + 1) & mask;
+      slot[p] = r;
+    }
+  }
+  // read `k` of T (its intervals are in place): find or create its rep
+  bool add_read(TintData& T, size_t k) {
+    if (slot.empty()) init(64);
+    const size_t iv0 = (size_t)T.read_iv_off[k], n_iv = (size_t)T.read_iv_off[k + 1] - iv0;
+    if ((T.rep_w.size() + 1) * 2 > slot.size()) grow(T);
+    size_t pos = (size_t)hash_ivs(T, iv0, n_iv) & mask;
+    int32_t rep = -1;
+    while (slot[pos] >= 0) {
+      const int32_t r = slot[pos];
+      if ((size_t)(T.rep_iv_off[(size_t)r + 1] - T.rep_iv_off[(size_t)r]) == n_iv) {
+        const size_t f = (size_t)first_iv[(size_t)r];
+        bool same = true;
+        for (size_t i = 0; i < n_iv && same; ++i)
+          same = T.riv_ts[f + i] == T.riv_ts[iv0 + i] && T.riv_te[f + i] == T.riv_te[iv0 + i];
+        if (same) { rep = r; break; }
+      }
+      pos = (pos + 1) & mask;
+    }
+    if (rep < 0) {
+      rep = (int32_t)T.rep_w.size();
+      slot[pos] = rep;
+      first_iv.push_back((int32_t)iv0);
+      T.rep_w.push_back(0);
+      for (size_t i = 0; i < n_iv; ++i) {
+        const int32_t ts = T.riv_ts[iv0 + i], te = T.riv_te[iv0 + i];
+        // island of ts: last island with start <= ts
+        size_t a = (size_t)(std::upper_bound(T.isl_s.begin(), T.isl_s.end(), ts) - T.isl_s.begin());
+        if (a == 0 || ts > T.isl_e[a - 1]) { T.error = "KeyError: " + std::to_string(ts) + " (freddie_segment.py:666)"; return false; }
+        --a;
+        if (te > T.isl_e[a]) {
+          size_t b = (size_t)(std::upper_bound(T.isl_s.begin(), T.isl_s.end(), te) - T.isl_s.begin());
+          if (b == 0 || te > T.isl_e[b - 1]) T.error = "KeyError: " + std::to_string(te) + " (freddie_segment.py:667)";
+          else T.error = "AssertionError: assert Y_idx_s == Y_idx_e (freddie_segment.py:668)";
+          return false;
+        }
+        T.rep_fs.push_back(T.isl_off[a] + (ts - T.isl_s[a]));
+        T.rep_fe.push_back(T.isl_off[a] + (te - T.isl_s[a]));
+      }
+      T.rep_iv_off.push_back((int32_t)T.rep_fs.size());
+    }
+    T.rep_w[(size_t)rep] += 1;
+    T.read_rep.push_back(rep);
+    return true;
+  }
+};
+
+template <typename F>
+void parallel_for(int n, int n_threads, F f);
+
+size_t big_file_bytes() {  // files above this are parsed by all threads together (giant tints)
+  const char* e = getenv("FRS_PARSE_BIG_BYTES");  // read per batch: tests force the chunked path with 1
+  return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)(32u << 20);
+}
+
+// One split file.  inner_threads > 1 (giant tint): the rows after the header are cut into chunks at
+// line ends, parsed in parallel into private TintData blocks, appended in order, then deduped in row
+// order -- same arrays, same first error as the sequential walk.
+bool parse_split_file(const char* path, TintData& T, int inner_threads) {
   FileBuf fb;
   if (!fb.load(path, T.error, 0)) return false;
   ProfScope ps(PROF_SPLIT);
   const char* s = fb.p;
   const char* end = fb.p + fb.n;
   bool have_header = false;
-  // read-rep dedupe (:165-170): open-addressing table of rep ids; a rep's key is compared against the
-  // target intervals of its first read (no per-rep key allocation)
-  std::vector<int32_t> rep_slot;       // -1 = empty, else rep id
-  std::vector<int32_t> rep_first_iv;   // rep -> first interval index (into riv_ts / riv_te) of its first read
-  size_t rep_mask = 0;
-  auto rep_table_init = [&](size_t n_reads) {
-    size_t cap = 64;
-    while (cap < 2 * n_reads + 2) cap <<= 1;
-    rep_slot.assign(cap, -1);
-    rep_mask = cap - 1;
+  RepTable reps;
+  auto no_newline = [&](const char* at) {
+    T.error = std::string("AttributeError: line without newline does not match (") + path + "): " + line_snip(at, end);
+    return false;
   };
-  auto rep_table_grow = [&]() {
-    std::vector<int32_t> old;
-    old.swap(rep_slot);
-    rep_slot.assign(old.size() * 2, -1);
-    rep_mask = rep_slot.size() - 1;
-    for (int32_t r : old) {
-      if (r < 0) continue;
-      uint64_t h = 1469598103934665603ull;
-      for (int32_t k = T.rep_iv_off[(size_t)r], f = rep_first_iv[(size_t)r]; k < T.rep_iv_off[(size_t)r + 1]; ++k, ++f) {
-        h ^= (uint32_t)T.riv_ts[(size_t)f]; h *= 1099511628211ull;
-        h ^= (uint32_t)T.riv_te[(size_t)f]; h *= 1099511628211ull;
-      }
-      size_t p = (size_t)h & rep_mask;
-      while (rep_slot[p] >= 0) p = (p + 1) & rep_mask;
-      rep_slot[p] = r;
-    }
-  };
-  std::vector<int32_t> key;
-  while (s < end) {
+  // ---- parallel path ----
+  if (inner_threads > 1 && fb.n > 0 && *s == '#') {
     const char* nl = (const char*)memchr(s, '\n', (size_t)(end - s));
-    if (!nl) { T.error = std::string("AttributeError: line without newline does not match (") + path + "): " + line_snip(s, end); return false; }
-    const char* e = nl;  // line content is [s, e)
-    if (*s == '#') {
-      // #<chr>\t<id>\t<s>-<e>(,<s>-<e>)*\t<count>
-      const char* q = s + 1;
-      const char* c0 = q;
-      int64_t id, cnt;
-      if (!parse_chr(q, e)) goto bad_header;
-      {
-        std::string chr(c0, (size_t)(q - c0));
-        if (!expect(q, e, '\t') || !parse_uint(q, e, id) || !expect(q, e, '\t')) goto bad_header;
-        std::vector<int32_t> is, ie;
-        for (;;) {
-          int32_t a, b;
-          if (!parse_i32(q, e, a) || !expect(q, e, '-') || !parse_i32(q, e, b)) goto bad_header;
-          is.push_back(a);
-          ie.push_back(b);
-          if (q < e && *q == ',') { ++q; continue; }
-          break;
-        }
-        if (!expect(q, e, '\t') || !parse_uint(q, e, cnt) || q != e) goto bad_header;
-        if (have_header) {
-          if (id == T.id) T.error = "AssertionError: Transcriptional interval with id " + std::to_string(id) + " is repeated!";
-          else T.error = std::string("AssertionError: assert len(tints) == 1 (freddie_segment.py:699): ") + path;
-          return false;
-        }
-        for (size_t i = 0; i + 1 < is.size(); ++i)
-          if (!(ie[i] < is[i + 1])) { T.error = "AssertionError: tint intervals overlap or are unordered (freddie_segment.py:138)"; return false; }
-        for (size_t i = 0; i < is.size(); ++i)
-          if (!(is[i] < ie[i])) { T.error = "AssertionError: empty tint interval (freddie_segment.py:140)"; return false; }
-        T.chr = chr;
-        T.id = id;
-        T.read_count = cnt;
-        T.isl_s = is;
-        T.isl_e = ie;
-        rep_table_init((size_t)std::max<int64_t>(cnt, 0) < (size_t)(fb.n / 16 + 16) ? (size_t)std::max<int64_t>(cnt, 0) : fb.n / 16 + 16);
-        T.isl_off.assign(1, 0);
-        int64_t off = 0;
-        for (size_t i = 0; i < is.size(); ++i) {
-          off += (int64_t)ie[i] - is[i] + 1;
-          if (off > INT32_MAX) { T.error = "tint spans more than 2^31 samples"; return false; }
-          T.isl_off.push_back((int32_t)off);
-        }
+    if (!nl) return no_newline(s);
+    if (!parse_header_line(s, nl, path, false, T)) return false;
+    have_header = true;
+    s = nl + 1;
+    const int K = inner_threads * 4;
+    std::vector<const char*> cut((size_t)K + 1, end);
+    cut[0] = s;
+    for (int k = 1; k < K; ++k) {
+      const char* c = s + (size_t)((end - s) / K) * (size_t)k;
+      if (c < cut[(size_t)k - 1]) c = cut[(size_t)k - 1];
+      const char* n2 = c < end ? (const char*)memchr(c, '\n', (size_t)(end - c)) : nullptr;
+      cut[(size_t)k] = n2 ? n2 + 1 : end;
+    }
+    std::vector<TintData> part((size_t)K);
+    std::vector<int> bad_kind((size_t)K, 0);  // 1 = row error (part.error), 2 = header line inside, 3 = no newline
+    std::vector<const char*> bad_at((size_t)K, nullptr);
+    parallel_for(K, inner_threads, [&](int k) {
+      TintData& C = part[(size_t)k];
+      const char* p = cut[(size_t)k];
+      const char* pe = cut[(size_t)k + 1];
+      while (p < pe) {
+        const char* n2 = (const char*)memchr(p, '\n', (size_t)(pe - p));
+        if (!n2) { bad_kind[(size_t)k] = 3; bad_at[(size_t)k] = p; return; }
+        if (*p == '#') { bad_kind[(size_t)k] = 2; bad_at[(size_t)k] = p; return; }
+        if (!parse_read_row(p, n2, true, T.id, C)) { bad_kind[(size_t)k] = 1; return; }
+        p = n2 + 1;
+      }
+    });
+    // append in order, dedupe in row order; the first error in row order wins
+    for (int k = 0; k < K; ++k) {
+      TintData& C = part[(size_t)k];
+      const size_t r0 = T.meta.size();
+      const uint32_t text0 = (uint32_t)T.text.size();
+      const int32_t iv0 = (int32_t)T.riv_ts.size(), cig0 = (int32_t)T.cigar.size();
+      T.text += C.text;
+      for (ReadMeta m : C.meta) { m.name_off += text0; m.chr_off += text0; T.meta.push_back(m); }
+      T.riv_ts.insert(T.riv_ts.end(), C.riv_ts.begin(), C.riv_ts.end());
+      T.riv_te.insert(T.riv_te.end(), C.riv_te.begin(), C.riv_te.end());
+      T.riv_qs.insert(T.riv_qs.end(), C.riv_qs.begin(), C.riv_qs.end());
+      T.riv_qe.insert(T.riv_qe.end(), C.riv_qe.begin(), C.riv_qe.end());
+      for (size_t i = 1; i < C.riv_cig_off.size(); ++i) T.riv_cig_off.push_back(C.riv_cig_off[i] + cig0);
+      T.cigar.insert(T.cigar.end(), C.cigar.begin(), C.cigar.end());
+      for (size_t i = 1; i < C.read_iv_off.size(); ++i) T.read_iv_off.push_back(C.read_iv_off[i] + iv0);
+      T.read_strand.insert(T.read_strand.end(), C.read_strand.begin(), C.read_strand.end());
+      for (size_t r = r0; r < T.meta.size(); ++r)
+        if (!reps.add_read(T, r)) return false;
+      if (bad_kind[(size_t)k] == 1) { T.error = C.error; return false; }
+      if (bad_kind[(size_t)k] == 2) {
+        const char* at = bad_at[(size_t)k];
+        const char* n2 = (const char*)memchr(at, '\n', (size_t)(end - at));
+        parse_header_line(at, n2 ? n2 : end, path, true, T);  // sets the "repeated" / "len(tints) == 1" error
+        if (T.error.empty()) T.error = std::string("AssertionError: assert len(tints) == 1 (freddie_segment.py:699): ") + path;
+        return false;
+      }
+      if (bad_kind[(size_t)k] == 3) return no_newline(bad_at[(size_t)k]);
+      C = TintData();
+    }
+  } else {
+    // ---- sequential walk ----
+    while (s < end) {
+      const char* nl = (const char*)memchr(s, '\n', (size_t)(end - s));
+      if (!nl) return no_newline(s);
+      if (*s == '#') {
+        if (!parse_header_line(s, nl, path, have_header, T)) return false;
         have_header = true;
+        reps.init((size_t)std::min<int64_t>(std::max<int64_t>(T.read_count, 0), (int64_t)(fb.n / 16 + 16)));
+      } else {
+        if (!parse_read_row(s, nl, have_header, T.id, T)) return false;
+        if (!reps.add_read(T, T.meta.size() - 1)) return false;
       }
       s = nl + 1;
-      continue;
-    bad_header:
-      T.error = std::string("AttributeError: tint header does not match tint_prog (freddie_segment.py:22): ") + line_snip(s, e);
-      return false;
-    } else {
-      // <rid>\t<name>\t<chr>\t<strand>\t<tint>\t<iv>(\t<iv>)*
-      const char* q = s;
-      ReadMeta m;
-      if (!parse_uint(q, e, m.rid) || !expect(q, e, '\t')) goto bad_read;
-      {
-        const char* n0 = q;
-        while (q < e && name_char((unsigned char)*q)) ++q;
-        size_t nlen = (size_t)(q - n0);
-        if (nlen < 1 || nlen > 254 || !expect(q, e, '\t')) goto bad_read;
-        const char* c0 = q;
-        if (!parse_chr(q, e)) goto bad_read;
-        size_t clen = (size_t)(q - c0);
-        if (!expect(q, e, '\t')) goto bad_read;
-        if (q >= e || (*q != '+' && *q != '-')) goto bad_read;
-        m.strand = *q++;
-        if (!expect(q, e, '\t') || !parse_uint(q, e, m.tint) || !expect(q, e, '\t')) goto bad_read;
-        if (!have_header || m.tint != T.id) { T.error = "KeyError: read row refers to tint " + std::to_string(m.tint) + " (freddie_segment.py:162)"; return false; }
-        m.name_off = (uint32_t)T.text.size();
-        m.name_len = (uint32_t)nlen;
-        T.text.append(n0, nlen);
-        m.chr_off = (uint32_t)T.text.size();
-        m.chr_len = (uint32_t)clen;
-        T.text.append(c0, clen);
-        key.clear();
-        size_t iv0 = T.riv_ts.size();
-        for (;;) {
-          int32_t ts, te, qs, qe;
-          if (!parse_i32(q, e, ts) || !expect(q, e, '-') || !parse_i32(q, e, te) || !expect(q, e, ':') ||
-              !parse_i32(q, e, qs) || !expect(q, e, '-') || !parse_i32(q, e, qe) || !expect(q, e, ':'))
-            goto bad_read;
-          int nops = 0;
-          while (q < e && is_digit(*q)) {
-            int64_t c;
-            if (!parse_uint(q, e, c) || q >= e) goto bad_read;
-            uint32_t op;
-            switch (*q) {
-              case 'M': case 'X': case '=': op = 0; break;
-              case 'I': op = 1; break;
-              case 'D': op = 2; break;
-              case 'N': case 'S': case 'H': case 'P': op = 3; break;
-              default: goto bad_read;
-            }
-            ++q;
-            if (c >= (1ll << 28)) { T.error = "CIGAR operation longer than 2^28"; return false; }
-            T.cigar.push_back(((uint32_t)c << 4) | op);
-            ++nops;
-          }
-          if (nops == 0) goto bad_read;
-          T.riv_ts.push_back(ts);
-          T.riv_te.push_back(te);
-          T.riv_qs.push_back(qs);
-          T.riv_qe.push_back(qe);
-          T.riv_cig_off.push_back((int32_t)T.cigar.size());
-          key.push_back(ts);
-          key.push_back(te);
-          if (q < e && *q == '\t') { ++q; continue; }
-          break;
-        }
-        if (q != e) goto bad_read;
-        size_t iv1 = T.riv_ts.size();
-        for (size_t k = iv0; k + 1 < iv1; ++k)
-          if (!(T.riv_te[k] <= T.riv_ts[k + 1] && T.riv_qe[k] <= T.riv_qs[k + 1])) {
-            T.error = "AssertionError: read intervals out of order (freddie_segment.py:158)";
-            return false;
-          }
-        for (size_t k = iv0; k < iv1; ++k)
-          if (!(T.riv_ts[k] < T.riv_te[k] && T.riv_qs[k] < T.riv_qe[k])) {
-            T.error = "AssertionError: empty read interval (freddie_segment.py:160)";
-            return false;
-          }
-        T.read_iv_off.push_back((int32_t)iv1);
-        T.read_strand.push_back(m.strand == '+' ? 0 : 1);
-        T.meta.push_back(m);
-        // read rep (first-seen order, :165-170)
-        uint64_t kh = 1469598103934665603ull;
-        for (int32_t v : key) { kh ^= (uint32_t)v; kh *= 1099511628211ull; }
-        if ((T.rep_w.size() + 1) * 2 > rep_slot.size()) rep_table_grow();
-        size_t pos = (size_t)kh & rep_mask;
-        int32_t rep = -1;
-        const size_t n_key_iv = key.size() / 2;
-        while (rep_slot[pos] >= 0) {
-          const int32_t r = rep_slot[pos];
-          if ((size_t)(T.rep_iv_off[(size_t)r + 1] - T.rep_iv_off[(size_t)r]) == n_key_iv) {
-            const int32_t f = rep_first_iv[(size_t)r];
-            bool same = true;
-            for (size_t k = 0; k < n_key_iv && same; ++k)
-              same = T.riv_ts[(size_t)f + k] == key[2 * k] && T.riv_te[(size_t)f + k] == key[2 * k + 1];
-            if (same) { rep = r; break; }
-          }
-          pos = (pos + 1) & rep_mask;
-        }
-        if (rep < 0) {
-          rep = (int32_t)T.rep_w.size();
-          rep_slot[pos] = rep;
-          rep_first_iv.push_back((int32_t)iv0);
-          T.rep_w.push_back(0);
-          for (size_t k = 0; k < key.size(); k += 2) {
-            int32_t ts = key[k], te = key[k + 1];
-            // island of ts: last island with start <= ts
-            size_t a = (size_t)(std::upper_bound(T.isl_s.begin(), T.isl_s.end(), ts) - T.isl_s.begin());
-            if (a == 0 || ts > T.isl_e[a - 1]) { T.error = "KeyError: " + std::to_string(ts) + " (freddie_segment.py:666)"; return false; }
-            --a;
-            if (te > T.isl_e[a]) {
-              size_t b = (size_t)(std::upper_bound(T.isl_s.begin(), T.isl_s.end(), te) - T.isl_s.begin());
-              if (b == 0 || te > T.isl_e[b - 1]) T.error = "KeyError: " + std::to_string(te) + " (freddie_segment.py:667)";
-              else T.error = "AssertionError: assert Y_idx_s == Y_idx_e (freddie_segment.py:668)";
-              return false;
-            }
-            T.rep_fs.push_back(T.isl_off[a] + (ts - T.isl_s[a]));
-            T.rep_fe.push_back(T.isl_off[a] + (te - T.isl_s[a]));
-          }
-          T.rep_iv_off.push_back((int32_t)T.rep_fs.size());
-        }
-        T.rep_w[rep] += 1;
-        T.read_rep.push_back(rep);
-      }
-      s = nl + 1;
-      continue;
-    bad_read:
-      T.error = std::string("AttributeError: read row does not match read_prog (freddie_segment.py:28): ") + line_snip(s, e);
-      return false;
     }
   }
   if (!have_header) { T.error = std::string("AssertionError: assert len(tints) == 1 (freddie_segment.py:699): ") + path; return false; }
@@ -422,7 +515,7 @@ bool parse_split_file(const char* path, TintData& T) {
 }
 
 // read_sequence (:174-185): cols 0 and 3 of every line; later duplicates of a rid win
-bool parse_reads_file(const char* path, TintData& T) {
+bool parse_reads_file(const char* path, TintData& T, int inner_threads) {
   FileBuf fb;
   if (!fb.load(path, T.error, 1)) return false;
   std::unordered_map<int64_t, std::pair<const char*, uint32_t>> seqs;
@@ -468,12 +561,16 @@ bool parse_reads_file(const char* path, TintData& T) {
   }
   T.seq_a.resize(words);
   T.seq_t.resize(words);
-  size_t w0 = 0;
-  for (const ReadMeta& m : T.meta) {
-    const auto& sq = seqs[m.rid];
-    seq_planes(sq.first, sq.second, T.seq_a.data() + w0, T.seq_t.data() + w0);
-    w0 += (sq.second + 31) / 32;
-  }
+  const size_t n_reads = T.meta.size();
+  const int blocks = inner_threads > 1 ? inner_threads * 8 : 1;
+  parallel_for(blocks, inner_threads, [&](int bk) {
+    const size_t k0 = n_reads * (size_t)bk / (size_t)blocks, k1 = n_reads * ((size_t)bk + 1) / (size_t)blocks;
+    for (size_t k = k0; k < k1; ++k) {
+      const auto& sq = seqs.find(T.meta[k].rid)->second;
+      const size_t w0 = (size_t)T.read_seq_off[k];
+      seq_planes(sq.first, sq.second, T.seq_a.data() + w0, T.seq_t.data() + w0);
+    }
+  });
   return true;
 }
 
@@ -542,13 +639,24 @@ int frs_parse_tints(const char* const* split_paths, const char* const* reads_pat
   frs_parsed* P = new frs_parsed();
   P->tints.resize((size_t)n);
   std::atomic<int> failed(-1);
-  parallel_for(n, n_threads, [&](int i) {
+  // giant tints (files above big_file_bytes()) one after the other with all threads inside the file,
+  // then the many small tints one per task
+  std::vector<int> small, big;
+  for (int i = 0; i < n; ++i) {
+    struct stat st1, st2;
+    const size_t b1 = stat(split_paths[i], &st1) == 0 ? (size_t)st1.st_size : 0;
+    const size_t b2 = stat(reads_paths[i], &st2) == 0 ? (size_t)st2.st_size : 0;
+    ((n_threads > 1 && std::max(b1, b2) > big_file_bytes()) ? big : small).push_back(i);
+  }
+  auto one = [&](int i, int inner) {
     TintData& T = P->tints[(size_t)i];
-    if (!parse_split_file(split_paths[i], T) || !parse_reads_file(reads_paths[i], T)) {
+    if (!parse_split_file(split_paths[i], T, inner) || !parse_reads_file(reads_paths[i], T, inner)) {
       int exp = -1;
       failed.compare_exchange_strong(exp, i);
     }
-  });
+  };
+  for (int i : big) one(i, n_threads);
+  parallel_for((int)small.size(), n_threads, [&](int k) { one(small[(size_t)k], 1); });
   // deterministic error: the first failing tint in input order
   for (int i = 0; i < n; ++i)
     if (!P->tints[(size_t)i].error.empty()) {

@@ -98,6 +98,70 @@ def test_native_parser_errors_mirror_reference(tmp_path, built_lib):
         hostio.ParsedBatch([b"/nonexistent/split_x_0.tsv"], [rp.encode()], 1)
 
 
+@pytest.mark.parametrize("name", ["cfg1", "cfg2_flagsA", "degenerate", "dup_heavy", "cfg3_mini"])
+def test_native_parser_chunked_path_equals_sequential(name, golden_set, built_lib, monkeypatch):
+    """Giant tints are parsed by all threads inside one file (rows cut into chunks at line ends, appended
+    and deduped in row order).  FRS_PARSE_BIG_BYTES=1 forces that path on the golden sets: every array
+    must equal the sequential parse, and the first error in row order must be the same one."""
+    from freddie_b200 import _lib, hostio
+    tints, _, split_dir = golden_set(name)
+    seq = _native_batch(split_dir, tints)
+    monkeypatch.setenv("FRS_PARSE_BIG_BYTES", "1")
+    sp = [("%s/%s/split_%s_%d.tsv" % (split_dir, t["chr"], t["chr"], t["id"])).encode() for t in tints]
+    rp = [("%s/%s/reads_%s_%d.tsv" % (split_dir, t["chr"], t["chr"], t["id"])).encode() for t in tints]
+    par = hostio.ParsedBatch(sp, rp, 4)
+    for k in _lib.BATCH_COUNTS + ["n_seq_words"]:
+        assert getattr(par.struct, k) == getattr(seq.struct, k), k
+    sizes = dict(tint_island_off="n_tints+1", tint_rep_off="n_tints+1", tint_read_off="n_tints+1", island_start="n_islands",
+                 island_sample_off="n_islands+1", rep_iv_off="n_reps+1", rep_weight="n_reps", rep_iv_fs="n_rep_ivs",
+                 rep_iv_fe="n_rep_ivs", read_rep="n_reads", read_strand="n_reads", read_len="n_reads",
+                 read_iv_off="n_reads+1", read_seq_off="n_reads+1", riv_ts="n_read_ivs", riv_te="n_read_ivs",
+                 riv_qs="n_read_ivs", riv_qe="n_read_ivs", riv_cig_off="n_read_ivs+1", cigar="n_cigar_ops",
+                 seq_is_a="n_seq_words", seq_is_t="n_seq_words")
+    dt = dict(read_strand=C.c_uint8, read_seq_off=C.c_int64, cigar=C.c_uint32, seq_is_a=C.c_uint32, seq_is_t=C.c_uint32)
+    for nm, expr in sizes.items():
+        base, _, plus = expr.partition("+")
+        n = int(getattr(seq.struct, base)) + (1 if plus else 0)
+        if n == 0:
+            continue
+        ct = dt.get(nm, C.c_int32)
+        a = np.ctypeslib.as_array(C.cast(getattr(seq.struct, nm), C.POINTER(ct)), shape=(n,))
+        b = np.ctypeslib.as_array(C.cast(getattr(par.struct, nm), C.POINTER(ct)), shape=(n,))
+        assert np.array_equal(a, b), nm
+    seq.close()
+    par.close()
+
+
+def test_native_parser_chunked_path_reports_the_first_error_in_row_order(tmp_path, built_lib, monkeypatch):
+    from freddie_b200 import hostio, synth, _lib
+    t = synth.make_config(2, scale=0.002, seed=77)[0]
+    d = str(tmp_path / "s")
+    synth.write_split_dir([t], d)
+    sp = os.path.join(d, t["chr"], "split_%s_%d.tsv" % (t["chr"], t["id"]))
+    rp = os.path.join(d, t["chr"], "reads_%s_%d.tsv" % (t["chr"], t["id"]))
+    lines = open(sp).read().split("\n")
+    assert len(lines) > 12
+    # an interval outside every island early (KeyError at dedupe, :666) and a malformed row later (read_prog)
+    f = lines[3].split("\t")
+    f[5] = "1-2:" + f[5].split(":", 1)[1]
+    early = "\t".join(f)
+    late = lines[-3].replace("M", "Q", 1)
+    for big in ("1", None):
+        if big:
+            monkeypatch.setenv("FRS_PARSE_BIG_BYTES", big)
+        else:
+            monkeypatch.delenv("FRS_PARSE_BIG_BYTES", raising=False)
+        open(sp, "w").write("\n".join(lines[:3] + [early] + lines[4:-3] + [late] + lines[-2:]))
+        with pytest.raises(_lib.FrsError, match="KeyError: 1 "):
+            hostio.ParsedBatch([sp.encode()], [rp.encode()], 4)
+        open(sp, "w").write("\n".join(lines[:-3] + [late] + lines[-2:]))
+        with pytest.raises(_lib.FrsError, match="read_prog"):
+            hostio.ParsedBatch([sp.encode()], [rp.encode()], 4)
+        open(sp, "w").write("\n".join(lines[:6] + [lines[0]] + lines[6:]))
+        with pytest.raises(AssertionError, match="repeated"):
+            hostio.ParsedBatch([sp.encode()], [rp.encode()], 4)
+
+
 @pytest.mark.parametrize("name", ["cfg2_flagsA", "degenerate", "plateau"])
 def test_native_formatter_writes_reference_bytes(name, golden_set, manifest, tmp_path, built_lib):
     """Formatter fed with the oracle's results (as frs_result arrays) must emit the reference's files."""
