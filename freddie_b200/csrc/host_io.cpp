@@ -464,25 +464,69 @@ bool parse_split_file(const char* path, TintData& T, int inner_threads) {
         p = n2 + 1;
       }
     });
-    // append in order, dedupe in row order; the first error in row order wins
-    for (int k = 0; k < K; ++k) {
+    // rows up to the first failing chunk (inclusive: its complete rows precede the failing one) are put
+    // in place in parallel, then deduped in row order; the first error in row order wins
+    int k_end = K;
+    for (int k = 0; k < K; ++k)
+      if (bad_kind[(size_t)k]) { k_end = k + 1; break; }
+    struct Off { size_t reads, text, ivs, cig; };
+    std::vector<Off> off((size_t)k_end + 1);
+    {
+      Off a{0, 0, 0, 0};
+      for (int k = 0; k < k_end; ++k) {
+        off[(size_t)k] = a;
+        const TintData& C = part[(size_t)k];
+        a.reads += C.meta.size();
+        a.text += C.text.size();
+        a.ivs += C.read_iv_off.back();  // complete rows only (a failing row may have left a partial tail)
+        a.cig += C.meta.empty() ? 0 : (size_t)C.riv_cig_off[(size_t)C.read_iv_off.back()];
+      }
+      off[(size_t)k_end] = a;
+      if (a.ivs > (size_t)INT32_MAX || a.cig > (size_t)INT32_MAX || a.text > (size_t)UINT32_MAX) {
+        T.error = "tint too large for 32-bit offsets";
+        return false;
+      }
+      T.meta.resize(a.reads);
+      T.text.resize(a.text);
+      T.riv_ts.resize(a.ivs);
+      T.riv_te.resize(a.ivs);
+      T.riv_qs.resize(a.ivs);
+      T.riv_qe.resize(a.ivs);
+      T.riv_cig_off.resize(a.ivs + 1);
+      T.cigar.resize(a.cig);
+      T.read_iv_off.resize(a.reads + 1);
+      T.read_strand.resize(a.reads);
+    }
+    parallel_for(k_end, inner_threads, [&](int k) {
       TintData& C = part[(size_t)k];
-      const size_t r0 = T.meta.size();
-      const uint32_t text0 = (uint32_t)T.text.size();
-      const int32_t iv0 = (int32_t)T.riv_ts.size(), cig0 = (int32_t)T.cigar.size();
-      T.text += C.text;
-      for (ReadMeta m : C.meta) { m.name_off += text0; m.chr_off += text0; T.meta.push_back(m); }
-      T.riv_ts.insert(T.riv_ts.end(), C.riv_ts.begin(), C.riv_ts.end());
-      T.riv_te.insert(T.riv_te.end(), C.riv_te.begin(), C.riv_te.end());
-      T.riv_qs.insert(T.riv_qs.end(), C.riv_qs.begin(), C.riv_qs.end());
-      T.riv_qe.insert(T.riv_qe.end(), C.riv_qe.begin(), C.riv_qe.end());
-      for (size_t i = 1; i < C.riv_cig_off.size(); ++i) T.riv_cig_off.push_back(C.riv_cig_off[i] + cig0);
-      T.cigar.insert(T.cigar.end(), C.cigar.begin(), C.cigar.end());
-      for (size_t i = 1; i < C.read_iv_off.size(); ++i) T.read_iv_off.push_back(C.read_iv_off[i] + iv0);
-      T.read_strand.insert(T.read_strand.end(), C.read_strand.begin(), C.read_strand.end());
-      for (size_t r = r0; r < T.meta.size(); ++r)
-        if (!reps.add_read(T, r)) return false;
-      if (bad_kind[(size_t)k] == 1) { T.error = C.error; return false; }
+      const Off& o = off[(size_t)k];
+      const size_t n_r = C.meta.size(), n_iv = (size_t)C.read_iv_off.back();
+      const size_t n_cig = n_r ? (size_t)C.riv_cig_off[n_iv] : 0;
+      memcpy(&T.text[o.text], C.text.data(), C.text.size());
+      for (size_t r = 0; r < n_r; ++r) {
+        ReadMeta m = C.meta[r];
+        m.name_off += (uint32_t)o.text;
+        m.chr_off += (uint32_t)o.text;
+        T.meta[o.reads + r] = m;
+        T.read_iv_off[o.reads + r + 1] = C.read_iv_off[r + 1] + (int32_t)o.ivs;
+        T.read_strand[o.reads + r] = C.read_strand[r];
+      }
+      if (n_iv) {
+        memcpy(&T.riv_ts[o.ivs], C.riv_ts.data(), n_iv * 4);
+        memcpy(&T.riv_te[o.ivs], C.riv_te.data(), n_iv * 4);
+        memcpy(&T.riv_qs[o.ivs], C.riv_qs.data(), n_iv * 4);
+        memcpy(&T.riv_qe[o.ivs], C.riv_qe.data(), n_iv * 4);
+        for (size_t i = 1; i <= n_iv; ++i) T.riv_cig_off[o.ivs + i] = C.riv_cig_off[i] + (int32_t)o.cig;
+      }
+      if (n_cig) memcpy(&T.cigar[o.cig], C.cigar.data(), n_cig * 4);
+      if (!bad_kind[(size_t)k]) C = TintData();
+    });
+    reps.init(T.meta.size());
+    for (size_t r = 0; r < T.meta.size(); ++r)
+      if (!reps.add_read(T, r)) return false;
+    if (k_end > 0 && bad_kind[(size_t)k_end - 1]) {
+      const int k = k_end - 1;
+      if (bad_kind[(size_t)k] == 1) { T.error = part[(size_t)k].error; return false; }
       if (bad_kind[(size_t)k] == 2) {
         const char* at = bad_at[(size_t)k];
         const char* n2 = (const char*)memchr(at, '\n', (size_t)(end - at));
@@ -490,8 +534,7 @@ bool parse_split_file(const char* path, TintData& T, int inner_threads) {
         if (T.error.empty()) T.error = std::string("AssertionError: assert len(tints) == 1 (freddie_segment.py:699): ") + path;
         return false;
       }
-      if (bad_kind[(size_t)k] == 3) return no_newline(bad_at[(size_t)k]);
-      C = TintData();
+      return no_newline(bad_at[(size_t)k]);
     }
   } else {
     // ---- sequential walk ----
@@ -523,27 +566,70 @@ bool parse_reads_file(const char* path, TintData& T, int inner_threads) {
   const char* s = fb.p;
   const char* end = fb.p + fb.n;
   {
-  ProfScope ps_lines(PROF_READS_LINES);
-  while (s < end) {
-    const char* nl = (const char*)memchr(s, '\n', (size_t)(end - s));
-    const char* e = nl ? nl : end;
-    const char* next = nl ? nl + 1 : end;
-    // rstrip(): trailing whitespace
-    while (e > s && (e[-1] == ' ' || e[-1] == '\t' || e[-1] == '\r' || e[-1] == '\n' || e[-1] == '\v' || e[-1] == '\f')) --e;
-    // int(line[0]) tolerates surrounding blanks and a sign; split rows only hold digits
-    const char* q = s;
-    int64_t rid;
-    if (!parse_uint(q, e, rid) || (q < e && *q != '\t')) { T.error = std::string("ValueError: invalid read id in ") + path; return false; }
-    int tabs = 0;
-    const char* f3 = nullptr;
-    for (const char* c = s; c < e; ++c)
-      if (*c == '\t') { if (++tabs == 3) { f3 = c + 1; break; } }
-    if (!f3) { T.error = std::string("IndexError: list index out of range (freddie_segment.py:179): ") + path; return false; }
-    const char* f3e = (const char*)memchr(f3, '\t', (size_t)(e - f3));
-    if (!f3e) f3e = e;
-    seqs[rid] = std::make_pair(f3, (uint32_t)(f3e - f3));
-    s = next;
-  }
+    ProfScope ps_lines(PROF_READS_LINES);
+    // one line -> (rid, sequence); returns 0 ok, 1 ValueError, 2 IndexError
+    struct Row { int64_t rid; const char* seq; uint32_t len; };
+    auto parse_line = [](const char* ls, const char* e, Row& row) -> int {
+      // rstrip(): trailing whitespace
+      while (e > ls && (e[-1] == ' ' || e[-1] == '\t' || e[-1] == '\r' || e[-1] == '\n' || e[-1] == '\v' || e[-1] == '\f')) --e;
+      // int(line[0]) tolerates surrounding blanks and a sign; split rows only hold digits
+      const char* q = ls;
+      if (!parse_uint(q, e, row.rid) || (q < e && *q != '\t')) return 1;
+      int tabs = 0;
+      const char* f3 = nullptr;
+      for (const char* c = ls; c < e; ++c)
+        if (*c == '\t') { if (++tabs == 3) { f3 = c + 1; break; } }
+      if (!f3) return 2;
+      const char* f3e = (const char*)memchr(f3, '\t', (size_t)(e - f3));
+      if (!f3e) f3e = e;
+      row.seq = f3;
+      row.len = (uint32_t)(f3e - f3);
+      return 0;
+    };
+    auto fail_line = [&](int code) {
+      if (code == 1) T.error = std::string("ValueError: invalid read id in ") + path;
+      else T.error = std::string("IndexError: list index out of range (freddie_segment.py:179): ") + path;
+      return false;
+    };
+    if (inner_threads > 1) {
+      // giant tint: line chunks in parallel, rows entered in file order (later duplicates of a rid win)
+      const int K = inner_threads * 4;
+      std::vector<const char*> cut((size_t)K + 1, end);
+      cut[0] = s;
+      for (int k = 1; k < K; ++k) {
+        const char* c = s + (size_t)((end - s) / K) * (size_t)k;
+        if (c < cut[(size_t)k - 1]) c = cut[(size_t)k - 1];
+        const char* n2 = c < end ? (const char*)memchr(c, '\n', (size_t)(end - c)) : nullptr;
+        cut[(size_t)k] = n2 ? n2 + 1 : end;
+      }
+      std::vector<std::vector<Row>> rows((size_t)K);
+      std::vector<int> bad((size_t)K, 0);
+      parallel_for(K, inner_threads, [&](int k) {
+        const char* p = cut[(size_t)k];
+        const char* pe = cut[(size_t)k + 1];
+        while (p < pe) {
+          const char* n2 = (const char*)memchr(p, '\n', (size_t)(pe - p));
+          Row row;
+          const int rc = parse_line(p, n2 ? n2 : pe, row);
+          if (rc) { bad[(size_t)k] = rc; return; }
+          rows[(size_t)k].push_back(row);
+          p = n2 ? n2 + 1 : pe;
+        }
+      });
+      for (int k = 0; k < K; ++k) {
+        for (const Row& r : rows[(size_t)k]) seqs[r.rid] = std::make_pair(r.seq, r.len);
+        if (bad[(size_t)k]) return fail_line(bad[(size_t)k]);
+      }
+    } else {
+      while (s < end) {
+        const char* nl = (const char*)memchr(s, '\n', (size_t)(end - s));
+        Row row;
+        const int rc = parse_line(s, nl ? nl : end, row);
+        if (rc) return fail_line(rc);
+        seqs[row.rid] = std::make_pair(row.seq, row.len);
+        s = nl ? nl + 1 : end;
+      }
+    }
   }
   if (seqs.size() != T.meta.size()) { T.error = "AssertionError: assert len(rid_to_seq) == len(tint['reads']) (freddie_segment.py:181)"; return false; }
   // bit-planes
@@ -610,8 +696,22 @@ template <typename T>
 struct RawBuf {
   T* p = nullptr;
   size_t n = 0;
-  ~RawBuf() { free(p); }
-  void resize(size_t m) { free(p); p = (T*)malloc((m ? m : 1) * sizeof(T)); n = m; }
+  std::vector<T> own;  // adopt(): the storage of a tint's own vector (single-tint batches: no copy)
+  bool borrowed = false;
+  ~RawBuf() { if (!borrowed) free(p); }
+  void resize(size_t m) {
+    if (!borrowed) free(p);
+    borrowed = false;
+    p = (T*)malloc((m ? m : 1) * sizeof(T));
+    n = m;
+  }
+  void adopt(std::vector<T>&& v) {
+    if (!borrowed) free(p);
+    own = std::move(v);
+    p = own.data();
+    n = own.size();
+    borrowed = true;
+  }
   T* data() { return p; }
   const T* data() const { return p; }
   size_t size() const { return n; }
@@ -683,8 +783,43 @@ int frs_parse_tints(const char* const* split_paths, const char* const* reads_pat
     delete P;
     return FRS_ERR_LIMIT;
   }
-  // every tint's slice of every array is known from the prefix sums: size once, copy in parallel
   const size_t NT = P->tints.size();
+  if (NT == 1) {
+    // a giant tint is a batch of its own: its arrays ARE the batch (all shifts are zero) -- move them
+    TintData& T = P->tints[0];
+    P->tint_island_off = {0, (int32_t)isl};
+    P->tint_rep_off = {0, (int32_t)reps};
+    P->tint_read_off = {0, (int32_t)reads};
+    P->island_start = std::move(T.isl_s);
+    P->island_sample_off = std::move(T.isl_off);
+    P->rep_iv_off = std::move(T.rep_iv_off);
+    P->rep_weight = std::move(T.rep_w);
+    P->rep_iv_fs = std::move(T.rep_fs);
+    P->rep_iv_fe = std::move(T.rep_fe);
+    P->read_rep = std::move(T.read_rep);
+    P->read_strand = std::move(T.read_strand);
+    P->read_len = std::move(T.read_len);
+    P->read_iv_off = std::move(T.read_iv_off);
+    P->read_seq_off = std::move(T.read_seq_off);
+    P->riv_ts = std::move(T.riv_ts);
+    P->riv_te = std::move(T.riv_te);
+    P->riv_qs = std::move(T.riv_qs);
+    P->riv_qe = std::move(T.riv_qe);
+    P->riv_cig_off = std::move(T.riv_cig_off);
+    P->cigar.adopt(std::move(T.cigar));
+    P->seq_a.adopt(std::move(T.seq_a));
+    P->seq_t.adopt(std::move(T.seq_t));
+    delete ps_cat;
+    ps_cat = nullptr;
+    if (g_prof.on) {
+      fprintf(stderr, "[frs host profile] thread-seconds: load %.3f  split rows %.3f  reads lines %.3f  bit-planes %.3f  concat %.3f (moved)\n",
+              g_prof.ns[0] * 1e-9, (g_prof.ns[1]) * 1e-9, g_prof.ns[2] * 1e-9, g_prof.ns[3] * 1e-9, g_prof.ns[4] * 1e-9);
+      for (auto& x : g_prof.ns) x = 0;
+    }
+    *out = P;
+    return 0;
+  }
+  // every tint's slice of every array is known from the prefix sums: size once, copy in parallel
   struct Base { int64_t smp, reps, rep_ivs, rivs, cig, reads, isl, words; };
   std::vector<Base> base(NT + 1);
   {

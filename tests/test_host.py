@@ -54,7 +54,7 @@ def _native_batch(split_dir, tints, threads=4):
     return hostio.ParsedBatch(sp, rp, threads)
 
 
-@pytest.mark.parametrize("name", ["cfg2_flagsA", "degenerate", "cfg4_mini"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2_flagsA", "degenerate", "cfg4_mini"])  # cfg1: single-tint batch (arrays moved)
 def test_native_parser_equals_python_packer(name, golden_set, built_lib):
     from freddie_b200 import _lib
     from freddie_b200.pack import pack_tints
