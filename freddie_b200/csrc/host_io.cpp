@@ -413,6 +413,11 @@ struct RepTable {
 template <typename F>
 void parallel_for(int n, int n_threads, F f);
 
+size_t format_big_rows() {  // tints with more reads are formatted by all threads together
+  const char* e = getenv("FRS_FORMAT_BIG_ROWS");  // tests force the chunked path with 0
+  return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)20000;
+}
+
 size_t big_file_bytes() {  // files above this are parsed by all threads together (giant tints)
   const char* e = getenv("FRS_PARSE_BIG_BYTES");  // read per batch: tests force the chunked path with 1
   return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)(32u << 20);
@@ -960,28 +965,17 @@ int frs_format_tints(const frs_parsed* P, const frs_result* R, const char* const
   if (!P || !R || !out_paths) return FRS_ERR_ARG;
   const int n = (int)P->tints.size();
   std::vector<std::string> errors((size_t)n);
-  parallel_for(n, n_threads, [&](int t) {
+  // rows [k0, k1) of tint t, appended to o
+  auto format_rows = [&](int t, size_t k0, size_t k1, std::string& o) {
     const TintData& T = P->tints[(size_t)t];
     const int32_t f0 = R->tint_final_off[t], f1 = R->tint_final_off[t + 1];
     const int64_t S = f1 - f0 - 1;
     const int64_t d0 = R->tint_digit_off[t];
     const int32_t rep0 = P->tint_rep_off[(size_t)t];
     const int32_t r0 = P->tint_read_off[(size_t)t];
-    std::string o;
-    o.reserve((size_t)(T.meta.size() * (size_t)(S + 96) + (size_t)(f1 - f0) * 11 + 64));
     char num[32];
-    o.push_back('#');
-    o += T.chr;
-    o.push_back('\t');
-    o.append(num, (size_t)snprintf(num, sizeof num, "%lld", (long long)T.id));
-    o.push_back('\t');
-    for (int32_t f = f0; f < f1; ++f) {
-      if (f > f0) o.push_back(',');
-      o.append(num, (size_t)snprintf(num, sizeof num, "%d", R->final_pos[f]));
-    }
-    o.push_back('\n');
     std::vector<std::string> gaps;
-    for (size_t k = 0; k < T.meta.size(); ++k) {
+    for (size_t k = k0; k < k1; ++k) {
       const ReadMeta& m = T.meta[k];
       const int64_t i = (int64_t)r0 + (int64_t)k;
       o.append(num, (size_t)snprintf(num, sizeof num, "%lld", (long long)m.rid));
@@ -1019,16 +1013,51 @@ int frs_format_tints(const frs_parsed* P, const frs_result* R, const char* const
       }
       o.push_back('\n');
     }
+  };
+  // one tint: header + rows (in `inner` chunks formatted by `inner` threads for giant tints) -> file
+  auto format_tint = [&](int t, int inner) {
+    const TintData& T = P->tints[(size_t)t];
+    const int32_t f0 = R->tint_final_off[t], f1 = R->tint_final_off[t + 1];
+    const int64_t S = f1 - f0 - 1;
+    const size_t n_rows = T.meta.size();
+    const int K = inner > 1 ? inner * 2 : 1;
+    std::vector<std::string> part((size_t)K);
+    parallel_for(K, inner, [&](int c) {
+      const size_t k0 = n_rows * (size_t)c / (size_t)K, k1 = n_rows * ((size_t)c + 1) / (size_t)K;
+      std::string& o = part[(size_t)c];
+      o.reserve((size_t)((k1 - k0) * (size_t)(S + 96) + (c == 0 ? (size_t)(f1 - f0) * 11 + 64 : 0)));
+      if (c == 0) {
+        char num[32];
+        o.push_back('#');
+        o += T.chr;
+        o.push_back('\t');
+        o.append(num, (size_t)snprintf(num, sizeof num, "%lld", (long long)T.id));
+        o.push_back('\t');
+        for (int32_t f = f0; f < f1; ++f) {
+          if (f > f0) o.push_back(',');
+          o.append(num, (size_t)snprintf(num, sizeof num, "%d", R->final_pos[f]));
+        }
+        o.push_back('\n');
+      }
+      format_rows(t, k0, k1, o);
+    });
     FILE* f = fopen(out_paths[t], "wb");
     if (!f) { errors[(size_t)t] = std::string("cannot open ") + out_paths[t] + ": " + strerror(errno); return; }
-    if (fwrite(o.data(), 1, o.size(), f) != o.size()) errors[(size_t)t] = std::string("short write to ") + out_paths[t];
+    for (const std::string& o : part)
+      if (fwrite(o.data(), 1, o.size(), f) != o.size()) { errors[(size_t)t] = std::string("short write to ") + out_paths[t]; break; }
     fclose(f);
     if (log_paths && log_paths[t]) {
       FILE* l = fopen(log_paths[t], "wb");  // the reference leaves an empty .log per tint (:695,:734)
       if (l) fclose(l);
       else errors[(size_t)t] = std::string("cannot open ") + log_paths[t];
     }
-  });
+  };
+  // giant tints one after the other with all threads inside, the rest one tint per task
+  std::vector<int> small, big;
+  for (int t = 0; t < n; ++t)
+    ((n_threads > 1 && P->tints[(size_t)t].meta.size() > format_big_rows()) ? big : small).push_back(t);
+  for (int t : big) format_tint(t, n_threads);
+  parallel_for((int)small.size(), n_threads, [&](int k) { format_tint(small[(size_t)k], 1); });
   for (int t = 0; t < n; ++t)
     if (!errors[(size_t)t].empty()) {
       if (err) snprintf(err, err_cap, "%s", errors[(size_t)t].c_str());

@@ -162,10 +162,14 @@ def test_native_parser_chunked_path_reports_the_first_error_in_row_order(tmp_pat
             hostio.ParsedBatch([sp.encode()], [rp.encode()], 4)
 
 
+@pytest.mark.parametrize("chunked", [False, True])
 @pytest.mark.parametrize("name", ["cfg2_flagsA", "degenerate", "plateau"])
-def test_native_formatter_writes_reference_bytes(name, golden_set, manifest, tmp_path, built_lib):
-    """Formatter fed with the oracle's results (as frs_result arrays) must emit the reference's files."""
+def test_native_formatter_writes_reference_bytes(name, chunked, golden_set, manifest, tmp_path, built_lib, monkeypatch):
+    """Formatter fed with the oracle's results (as frs_result arrays) must emit the reference's files;
+    `chunked` forces the path of giant tints (rows formatted in chunks by all threads) on every tint."""
     from freddie_b200 import _lib
+    if chunked:
+        monkeypatch.setenv("FRS_FORMAT_BIG_ROWS", "0")
     tints, flags, split_dir = golden_set(name)
     pb = _native_batch(split_dir, tints)
     _, arrays = oracle_result_arrays(tints, orc.Params(**flags_to_kwargs(flags)))
