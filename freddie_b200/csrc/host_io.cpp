@@ -190,14 +190,6 @@ inline bool parse_chr(const char*& s, const char* e) {
   return true;
 }
 
-struct KeyHash {
-  size_t operator()(const std::vector<int32_t>& k) const {
-    uint64_t h = 1469598103934665603ull;
-    for (int32_t v : k) { h ^= (uint32_t)v; h *= 1099511628211ull; }
-    return (size_t)h;
-  }
-};
-
 std::string line_snip(const char* s, const char* e) {
   size_t n = (size_t)(e - s);
   if (n > 60) n = 60;

@@ -394,7 +394,7 @@ __global__ void k_cand_meta(const int* __restrict__ cand_flat, int n_cand, const
 
 // ---------------------------------------------------------------------------------------------
 // K3 variance threshold (one CTA per tint) over the tint's slice of the compacted positive samples
-// (written in sample order by k_phase1): numpy's pairwise summation tree (DOUBLE_pairwise_sum) for
+// (written in sample order by k_tile_lists): numpy's pairwise summation tree (DOUBLE_pairwise_sum) for
 // mean and variance:
 //   n < 8: sequential; n <= 128: eight strided accumulators, combined ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)),
 //   remainder added sequentially; else split at n/2 rounded down to a multiple of 8.
