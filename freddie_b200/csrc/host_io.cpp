@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <memory>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -88,14 +89,14 @@ struct FileBuf {
     return buf[which];
   }
   // `which`: 0 = split file, 1 = reads file (both may be alive in one thread at the same time)
-  bool load(const char* path, std::string& err, int which) {
+  bool load(const char* path, std::string& err, int which, bool always_map = false) {
     ProfScope ps(PROF_LOAD);
     int fd = open(path, O_RDONLY);
     if (fd < 0) { err = std::string("FileNotFoundError: ") + path + ": " + strerror(errno); return false; }
     struct stat st;
     if (fstat(fd, &st) != 0) { err = std::string("OSError: ") + path + ": " + strerror(errno); close(fd); return false; }
     n = (size_t)st.st_size;
-    if (n > SMALL) {
+    if (n > SMALL || (always_map && n > 0)) {
       void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
       if (m != MAP_FAILED) {
         p = (char*)m;
@@ -702,6 +703,12 @@ struct RawBuf {
     p = (T*)malloc((m ? m : 1) * sizeof(T));
     n = m;
   }
+  void borrow(T* ptr, size_t m) {  // storage owned by somebody who outlives this object (a file mapping)
+    if (!borrowed) free(p);
+    p = ptr;
+    n = m;
+    borrowed = true;
+  }
   void adopt(std::vector<T>&& v) {
     if (!borrowed) free(p);
     own = std::move(v);
@@ -715,6 +722,8 @@ struct RawBuf {
 };
 
 struct frs_parsed {
+  FileBuf* mapping = nullptr;  // frs_packed_read: the large arrays point into the mapped file
+  ~frs_parsed() { delete mapping; }
   std::vector<TintData> tints;
   // concatenated batch
   std::vector<int32_t> tint_island_off, tint_rep_off, tint_read_off, island_start, island_sample_off, rep_iv_off,
@@ -948,6 +957,177 @@ int frs_parsed_batch(const frs_parsed* P, frs_batch* b) {
 }
 
 void frs_parsed_free(frs_parsed* P) { delete P; }
+
+// ---------------------------------------------------------------------------------------------
+// Packed side-channel: a parsed batch as ONE binary file, so that a pipeline can hand
+// tints to this stage without the TSV round trip (text stays the default).  Layout, little-endian:
+//   "FRSBATC1" | u64 n_sections | n_sections x (u64 offset, u64 bytes) | sections, 64-byte aligned
+// Sections 0..21 are the arrays of frs_batch in declaration order; then per tint: id (i64), chr offsets
+// (u64[T+1]) + chr text; per read: rid (i64), the row's own tint column (i64), name offsets (u64[N+1]) +
+// names, chr offsets (u64[N+1]) + chr text -- everything frs_format_tints prints back.
+// ---------------------------------------------------------------------------------------------
+namespace {
+const char PACK_MAGIC[8] = {'F', 'R', 'S', 'B', 'A', 'T', 'C', '1'};
+enum { PK_BATCH0 = 0, PK_TINT_ID = 22, PK_TINT_CHR_OFF, PK_TINT_CHR, PK_READ_RID, PK_READ_TINT, PK_NAME_OFF, PK_NAMES,
+       PK_RCHR_OFF, PK_RCHR, PK_SECTIONS };
+struct Sec { const void* p; uint64_t bytes; };
+int pack_fail(char* err, size_t cap, int code, const std::string& m) {
+  if (err && cap) snprintf(err, cap, "%s", m.c_str());
+  return code;
+}
+}  // namespace
+
+int frs_packed_write(const frs_parsed* P, const char* path, char* err, size_t err_cap) {
+  if (err && err_cap) err[0] = 0;
+  if (!P || !path) return pack_fail(err, err_cap, FRS_ERR_ARG, "frs_packed_write: NULL argument");
+  const size_t T = P->tints.size(), N = P->read_rep.size();
+  std::vector<int64_t> tint_id(T), rid(N), rtint(N);
+  std::vector<uint64_t> tchr_off(T + 1, 0), name_off(N + 1, 0), rchr_off(N + 1, 0);
+  std::string tchr, names, rchr;
+  size_t r = 0;
+  for (size_t t = 0; t < T; ++t) {
+    const TintData& D = P->tints[t];
+    tint_id[t] = D.id;
+    tchr += D.chr;
+    tchr_off[t + 1] = tchr.size();
+    for (const ReadMeta& m : D.meta) {
+      rid[r] = m.rid;
+      rtint[r] = m.tint;
+      names.append(D.text, m.name_off, m.name_len);
+      name_off[r + 1] = names.size();
+      rchr.append(D.text, m.chr_off, m.chr_len);
+      rchr_off[r + 1] = rchr.size();
+      ++r;
+    }
+  }
+  if (r != N) return pack_fail(err, err_cap, FRS_ERR_STATE, "frs_packed_write: read tables out of step");
+  Sec sec[PK_SECTIONS] = {
+      {P->tint_island_off.data(), P->tint_island_off.size() * 4}, {P->tint_rep_off.data(), P->tint_rep_off.size() * 4},
+      {P->tint_read_off.data(), P->tint_read_off.size() * 4}, {P->island_start.data(), P->island_start.size() * 4},
+      {P->island_sample_off.data(), P->island_sample_off.size() * 4}, {P->rep_iv_off.data(), P->rep_iv_off.size() * 4},
+      {P->rep_weight.data(), P->rep_weight.size() * 4}, {P->rep_iv_fs.data(), P->rep_iv_fs.size() * 4},
+      {P->rep_iv_fe.data(), P->rep_iv_fe.size() * 4}, {P->read_rep.data(), P->read_rep.size() * 4},
+      {P->read_strand.data(), P->read_strand.size()}, {P->read_len.data(), P->read_len.size() * 4},
+      {P->read_iv_off.data(), P->read_iv_off.size() * 4}, {P->read_seq_off.data(), P->read_seq_off.size() * 8},
+      {P->riv_ts.data(), P->riv_ts.size() * 4}, {P->riv_te.data(), P->riv_te.size() * 4},
+      {P->riv_qs.data(), P->riv_qs.size() * 4}, {P->riv_qe.data(), P->riv_qe.size() * 4},
+      {P->riv_cig_off.data(), P->riv_cig_off.size() * 4}, {P->cigar.data(), P->cigar.size() * 4},
+      {P->seq_a.data(), P->seq_a.size() * 4}, {P->seq_t.data(), P->seq_t.size() * 4},
+      {tint_id.data(), T * 8}, {tchr_off.data(), (T + 1) * 8}, {tchr.data(), tchr.size()},
+      {rid.data(), N * 8}, {rtint.data(), N * 8}, {name_off.data(), (N + 1) * 8}, {names.data(), names.size()},
+      {rchr_off.data(), (N + 1) * 8}, {rchr.data(), rchr.size()},
+  };
+  FILE* f = fopen(path, "wb");
+  if (!f) return pack_fail(err, err_cap, FRS_ERR_IO, std::string("cannot open ") + path + ": " + strerror(errno));
+  std::vector<uint64_t> table(2 * PK_SECTIONS);
+  uint64_t at = 8 + 8 + 16 * (uint64_t)PK_SECTIONS;
+  for (int k = 0; k < PK_SECTIONS; ++k) {
+    at = (at + 63) & ~(uint64_t)63;
+    table[2 * (size_t)k] = at;
+    table[2 * (size_t)k + 1] = sec[k].bytes;
+    at += sec[k].bytes;
+  }
+  const uint64_t ns = PK_SECTIONS;
+  bool ok = fwrite(PACK_MAGIC, 1, 8, f) == 8 && fwrite(&ns, 8, 1, f) == 1 && fwrite(table.data(), 8, table.size(), f) == table.size();
+  uint64_t pos = 8 + 8 + 16 * (uint64_t)PK_SECTIONS;
+  static const char zeros[64] = {0};
+  for (int k = 0; k < PK_SECTIONS && ok; ++k) {
+    const uint64_t pad = table[2 * (size_t)k] - pos;
+    ok = (pad == 0 || fwrite(zeros, 1, (size_t)pad, f) == pad) &&
+         (sec[k].bytes == 0 || fwrite(sec[k].p, 1, (size_t)sec[k].bytes, f) == sec[k].bytes);
+    pos = table[2 * (size_t)k] + sec[k].bytes;
+  }
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) return pack_fail(err, err_cap, FRS_ERR_IO, std::string("short write to ") + path);
+  return 0;
+}
+
+int frs_packed_read(const char* path, frs_parsed** out, char* err, size_t err_cap) {
+  if (err && err_cap) err[0] = 0;
+  if (!path || !out) return pack_fail(err, err_cap, FRS_ERR_ARG, "frs_packed_read: NULL argument");
+  std::unique_ptr<FileBuf> fbp(new FileBuf());
+  FileBuf& fb = *fbp;
+  std::string e;
+  if (!fb.load(path, e, 0, true)) return pack_fail(err, err_cap, FRS_ERR_IO, e);
+  const std::string bad = std::string("not a packed batch (FRSBATC1): ") + path;
+  if (fb.n < 16 || memcmp(fb.p, PACK_MAGIC, 8) != 0) return pack_fail(err, err_cap, FRS_ERR_ARG, bad);
+  uint64_t ns;
+  memcpy(&ns, fb.p + 8, 8);
+  if (ns != PK_SECTIONS || fb.n < 16 + 16 * (size_t)PK_SECTIONS) return pack_fail(err, err_cap, FRS_ERR_ARG, bad);
+  uint64_t table[2 * PK_SECTIONS];
+  memcpy(table, fb.p + 16, sizeof table);
+  for (int k = 0; k < PK_SECTIONS; ++k)
+    if (table[2 * k] > fb.n || table[2 * k + 1] > fb.n - table[2 * k]) return pack_fail(err, err_cap, FRS_ERR_ARG, bad + " (section out of range)");
+  auto bytes = [&](int k) { return (size_t)table[2 * k + 1]; };
+  auto at = [&](int k) { return (const char*)fb.p + table[2 * k]; };
+  // element counts and their consistency
+  if (bytes(0) < 8 || bytes(0) % 4) return pack_fail(err, err_cap, FRS_ERR_ARG, bad);
+  const size_t T = bytes(0) / 4 - 1;
+  const size_t NI = bytes(3) / 4, NR = bytes(6) / 4, NRI = bytes(7) / 4, N = bytes(9) / 4, NV = bytes(14) / 4, NC = bytes(19) / 4,
+               NW = bytes(20) / 4;
+  const size_t want[PK_SECTIONS] = {(T + 1) * 4, (T + 1) * 4, (T + 1) * 4, NI * 4, (NI + 1) * 4, (NR + 1) * 4, NR * 4, NRI * 4, NRI * 4,
+                                    N * 4, N, N * 4, (N + 1) * 4, (N + 1) * 8, NV * 4, NV * 4, NV * 4, NV * 4, (NV + 1) * 4, NC * 4,
+                                    NW * 4, NW * 4, T * 8, (T + 1) * 8, bytes(PK_TINT_CHR), N * 8, N * 8, (N + 1) * 8,
+                                    bytes(PK_NAMES), (N + 1) * 8, bytes(PK_RCHR)};
+  for (int k = 0; k < PK_SECTIONS; ++k)
+    if (bytes(k) != want[k]) return pack_fail(err, err_cap, FRS_ERR_ARG, bad + " (inconsistent section sizes)");
+  frs_parsed* P = new frs_parsed();
+  auto fill = [&](auto& v, int k) {
+    using E = typename std::remove_reference<decltype(v)>::type::value_type;
+    v.resize(bytes(k) / sizeof(E));
+    if (bytes(k)) memcpy(v.data(), at(k), bytes(k));
+  };
+  fill(P->tint_island_off, 0); fill(P->tint_rep_off, 1); fill(P->tint_read_off, 2); fill(P->island_start, 3);
+  fill(P->island_sample_off, 4); fill(P->rep_iv_off, 5); fill(P->rep_weight, 6); fill(P->rep_iv_fs, 7); fill(P->rep_iv_fe, 8);
+  fill(P->read_rep, 9); fill(P->read_strand, 10); fill(P->read_len, 11); fill(P->read_iv_off, 12); fill(P->read_seq_off, 13);
+  fill(P->riv_ts, 14); fill(P->riv_te, 15); fill(P->riv_qs, 16); fill(P->riv_qe, 17); fill(P->riv_cig_off, 18);
+  if (fb.mapped) {  // the three large arrays stay in the page cache: no copy
+    P->cigar.borrow((uint32_t*)at(19), NC);
+    P->seq_a.borrow((uint32_t*)at(20), NW);
+    P->seq_t.borrow((uint32_t*)at(21), NW);
+  } else {
+    P->cigar.resize(NC); if (NC) memcpy(P->cigar.data(), at(19), NC * 4);
+    P->seq_a.resize(NW); if (NW) memcpy(P->seq_a.data(), at(20), NW * 4);
+    P->seq_t.resize(NW); if (NW) memcpy(P->seq_t.data(), at(21), NW * 4);
+  }
+  // offset tables must be monotone and end at the counts (frs_upload checks the batch arrays again)
+  const uint64_t* tco = (const uint64_t*)at(PK_TINT_CHR_OFF);
+  const uint64_t* no = (const uint64_t*)at(PK_NAME_OFF);
+  const uint64_t* co = (const uint64_t*)at(PK_RCHR_OFF);
+  bool mono = tco[0] == 0 && no[0] == 0 && co[0] == 0 && tco[T] == bytes(PK_TINT_CHR) && no[N] == bytes(PK_NAMES) &&
+              co[N] == bytes(PK_RCHR) && P->tint_read_off[0] == 0 && (size_t)P->tint_read_off[T] == N;
+  for (size_t t = 0; t < T && mono; ++t) mono = tco[t] <= tco[t + 1] && P->tint_read_off[t] <= P->tint_read_off[t + 1];
+  for (size_t i = 0; i < N && mono; ++i) mono = no[i] <= no[i + 1] && co[i] <= co[i + 1] && no[i + 1] - no[i] <= 254;
+  if (!mono) { delete P; return pack_fail(err, err_cap, FRS_ERR_ARG, bad + " (offset tables)"); }
+  const int64_t* tid = (const int64_t*)at(PK_TINT_ID);
+  const int64_t* rid = (const int64_t*)at(PK_READ_RID);
+  const int64_t* rti = (const int64_t*)at(PK_READ_TINT);
+  P->tints.resize(T);
+  for (size_t t = 0; t < T; ++t) {
+    TintData& D = P->tints[t];
+    D.id = tid[t];
+    D.chr.assign(at(PK_TINT_CHR) + tco[t], (size_t)(tco[t + 1] - tco[t]));
+    const size_t r0 = (size_t)P->tint_read_off[t], r1 = (size_t)P->tint_read_off[t + 1];
+    D.read_count = (int64_t)(r1 - r0);
+    D.meta.resize(r1 - r0);
+    D.text.reserve((size_t)(no[r1] - no[r0] + co[r1] - co[r0]));
+    for (size_t i = r0; i < r1; ++i) {
+      ReadMeta& m = D.meta[i - r0];
+      m.rid = rid[i];
+      m.tint = rti[i];
+      m.strand = P->read_strand[i] ? '-' : '+';
+      m.name_off = (uint32_t)D.text.size();
+      m.name_len = (uint32_t)(no[i + 1] - no[i]);
+      D.text.append(at(PK_NAMES) + no[i], m.name_len);
+      m.chr_off = (uint32_t)D.text.size();
+      m.chr_len = (uint32_t)(co[i + 1] - co[i]);
+      D.text.append(at(PK_RCHR) + co[i], m.chr_len);
+    }
+  }
+  if (fb.mapped) P->mapping = fbp.release();
+  *out = P;
+  return 0;
+}
 
 // run_segment output (:715-731): "#chr\tid\tpos,pos,...\n" then one row per read in file order;
 // gap strings sorted as python strings (:472), each followed by a comma.

@@ -31,14 +31,18 @@ def _paths(split_dir: str, outdir: str, chunk: Sequence[Tuple[str, int]]):
 class ParsedBatch:
     """A batch parsed by the native parser; owns the C++ object."""
 
-    def __init__(self, split_paths: List[bytes], reads_paths: List[bytes], threads: int):
+    def __init__(self, split_paths: List[bytes], reads_paths: List[bytes], threads: int, packed: bytes = None):
+        """Parses the tints' SPLIT files -- or, with ``packed``, loads a batch written by ``write_packed``."""
         self.lib = _lib.load()
-        n = len(split_paths)
         self.handle = C.c_void_p()
         err = C.create_string_buffer(1024)
-        a = (C.c_char_p * n)(*split_paths)
-        b = (C.c_char_p * n)(*reads_paths)
-        rc = self.lib.frs_parse_tints(a, b, n, threads, C.byref(self.handle), err, len(err))
+        if packed is not None:
+            rc = self.lib.frs_packed_read(packed, C.byref(self.handle), err, len(err))
+        else:
+            n = len(split_paths)
+            a = (C.c_char_p * n)(*split_paths)
+            b = (C.c_char_p * n)(*reads_paths)
+            rc = self.lib.frs_parse_tints(a, b, n, threads, C.byref(self.handle), err, len(err))
         if rc != 0:
             msg = err.value.decode(errors="replace")
             if msg.startswith("AssertionError"):
@@ -56,6 +60,17 @@ class ParsedBatch:
 
     def as_struct(self):
         return self.lean
+
+    @classmethod
+    def from_packed(cls, path: str) -> "ParsedBatch":
+        return cls([], [], 1, packed=path.encode())
+
+    def write_packed(self, path: str):
+        """The batch as one binary file (``frs_packed_write``): the side-channel that skips the TSV round trip."""
+        err = C.create_string_buffer(1024)
+        rc = self.lib.frs_packed_write(self.handle, path.encode(), err, len(err))
+        if rc != 0:
+            raise _lib.FrsError(rc, err.value.decode(errors="replace"))
 
     def format(self, res, out_paths: List[bytes], log_paths: List[bytes], threads: int):
         n = len(out_paths)
@@ -79,11 +94,16 @@ class ParsedBatch:
 
 
 def run_batch_native(eng: Engine, prm: SegmentParams, split_dir: str, outdir: str,
-                     chunk: Sequence[Tuple[str, int]], threads: int):
+                     chunk: Sequence[Tuple[str, int]], threads: int, packed_file: str = None):
+    """One batch, files to files: parse (or load ``packed_file``, a batch of exactly the tints of
+    ``chunk`` in that order), segment on ``eng``'s GPU, format."""
     prof = os.environ.get("FRS_CLI_PROFILE")
     t0 = time.perf_counter()
     sp, rp, op, lp = _paths(split_dir, outdir, chunk)
-    pb = ParsedBatch(sp, rp, threads)
+    pb = ParsedBatch.from_packed(packed_file) if packed_file else ParsedBatch(sp, rp, threads)
+    if pb.n_tints != len(chunk):
+        pb.close()
+        raise _lib.FrsError(-2, "%s holds %d tints, its index lists %d" % (packed_file, pb.n_tints, len(chunk)))
     t1 = time.perf_counter()
     try:
         res = eng.segment_batch(pb, prm)

@@ -65,8 +65,9 @@ class BatchFeed:
     """The batches of one GPU, handed out to that GPU's lanes (host threads) one at a time: every batch
     goes to exactly one lane, in order, and ``stop()`` (an error in any lane) ends the feed for all."""
 
-    def __init__(self, jobs: Sequence, costs: Sequence[Tuple[float, float]], batch_reads: int):
-        self._it = iter(batches(jobs, costs, batch_reads))
+    def __init__(self, jobs: Sequence, costs: Sequence[Tuple[float, float]], batch_reads: int, ready: Optional[Iterable] = None):
+        """``ready``: batches that already exist (a packed directory) instead of grouping ``jobs``."""
+        self._it = iter(ready) if ready is not None else iter(batches(jobs, costs, batch_reads))
         self._lock = threading.Lock()
         self._stopped = False
 

@@ -223,12 +223,21 @@ def run_directory(split_dir: str, outdir: str, prm: SegmentParams, threads: int 
     if n_dev <= 0:
         raise _engine._lib.FrsError(-1, "no CUDA device visible; freddie_b200 has no CPU fallback")
     n_gpus = n_dev if gpus <= 0 else min(gpus, n_dev)
-    jobs = list_tints(split_dir)
+    from . import packed as _packed
+    packed_batches = _packed.read_index(split_dir) if _packed.is_packed_dir(split_dir) else None
+    if packed_batches is not None:  # the packed side-channel: batches exist already, no TSV parse
+        native = True
+        jobs = [ct for b in packed_batches for ct in b["tints"]]
+    else:
+        jobs = list_tints(split_dir)
     for contig in {c for c, _ in jobs} | {c for c in os.listdir(split_dir) if os.path.isdir(os.path.join(split_dir, c))}:
         os.makedirs("{}/{}".format(outdir, contig), exist_ok=True)
     if native is None:
         native = hostio.available()
-    costs = [schedule.estimate_cost_from_files(split_dir, c, t) for c, t in jobs]
+    if packed_batches is not None:
+        costs = [(schedule.estimate_cost(b["reads"]), float(b["reads"])) for b in packed_batches]
+    else:
+        costs = [schedule.estimate_cost_from_files(split_dir, c, t) for c, t in jobs]
     shards = schedule.lpt_partition(costs, n_gpus)
     done = [0]
     total = len(jobs)
@@ -246,8 +255,14 @@ def run_directory(split_dir: str, outdir: str, prm: SegmentParams, threads: int 
             stats["reads"] += n_reads
             stats["dp_cells"] += cells
 
-    feeds = [schedule.BatchFeed([jobs[i] for i in shards[d]], [costs[i] for i in shards[d]], batch_reads)
-             for d in range(n_gpus)]
+    if packed_batches is not None:
+        feeds = [schedule.BatchFeed([], [], batch_reads, ready=[(packed_batches[i]["tints"], packed_batches[i]["file"])
+                                                                for i in shards[d]]) for d in range(n_gpus)]
+    else:
+        feeds = [schedule.BatchFeed([], [], batch_reads,
+                                    ready=((chunk, None) for chunk in schedule.batches(
+                                        [jobs[i] for i in shards[d]], [costs[i] for i in shards[d]], batch_reads)))
+                 for d in range(n_gpus)]
 
     def worker(dev, lane):
         try:
@@ -256,9 +271,9 @@ def run_directory(split_dir: str, outdir: str, prm: SegmentParams, threads: int 
             if os.environ.get("FRS_CLI_PROFILE"):
                 sys.stderr.write("[frs cli profile] context of GPU %d lane %d ready after %.3f s\n"
                                  % (dev, lane, time.perf_counter() - t_eng))
-            for chunk in feeds[dev]:
+            for chunk, packed_file in feeds[dev]:
                 if native:
-                    n_reads, cells = hostio.run_batch_native(eng, prm, split_dir, outdir, chunk, threads)
+                    n_reads, cells = hostio.run_batch_native(eng, prm, split_dir, outdir, chunk, threads, packed_file)
                 else:
                     tints = [_load_tint_py(split_dir, c, t) for c, t in chunk]
                     batch = pack_tints(tints)

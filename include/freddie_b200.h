@@ -217,6 +217,13 @@ void frs_parsed_free(frs_parsed* p);
 int frs_format_tints(const frs_parsed* p, const frs_result* res, const char* const* out_paths,
                      const char* const* log_paths, int n_threads, char* err, size_t err_cap);
 
+/* ---- packed side-channel: a parsed batch as one binary file ("FRSBATC1"), so that a
+ *      pipeline can hand tints to this stage without the TSV round trip of split_*.tsv / reads_*.tsv
+ *      (freddie_split.py:445-481 writes them, freddie_segment.py:121-185 reads them); text stays the
+ *      default.  frs_packed_read returns the same object frs_parse_tints does. ---- */
+int frs_packed_write(const frs_parsed* p, const char* path, char* err, size_t err_cap);
+int frs_packed_read(const char* path, frs_parsed** out, char* err, size_t err_cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -305,3 +305,18 @@ def test_errors_are_loud(golden_set, eng):
     bad.arrays["read_rep"][0] = 10 ** 6
     with pytest.raises(_lib.FrsError, match="rep"):
         eng.upload(bad)
+
+
+@pytest.mark.parametrize("name", ["cfg2_small", "cfg4_mini"])
+def test_cli_on_a_packed_directory_equals_reference_manifest(name, golden_set, manifest, tmp_path):
+    """The packed side-channel: SPLIT directory -> packed batches -> the same CLI.  The
+    SEGMENT directory must be the one the unmodified reference wrote from the TSV files."""
+    _, flags, split_dir = golden_set(name)
+    pk, out = str(tmp_path / "packed"), str(tmp_path / "seg")
+    r = subprocess.run([sys.executable, "-m", "freddie_b200.packed", "-s", split_dir, "-o", pk, "-t", "4",
+                        "--batch-reads", "700"], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([sys.executable, "-m", "freddie_b200.segment", "-s", pk, "-o", out, "-t", "4"] + flags,
+                       cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert sha_dir(out) == manifest[name]["outputs"]

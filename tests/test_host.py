@@ -351,3 +351,130 @@ def test_packed_batch_ships_read_intervals_once(golden_set):
         isl = np.searchsorted(iso, fs, side="right") - 1
         assert np.array_equal(ist[isl] + fs - iso[isl], a["riv_ts"][k0:k1])
         assert np.array_equal(ist[isl] + fe - iso[isl], a["riv_te"][k0:k1])
+
+
+# ---- packed side-channel --------------------------------------------------------
+def _batch_arrays(pb):
+    """Every array of a ParsedBatch's frs_batch as numpy copies, keyed by name."""
+    from freddie_b200 import _lib
+    st = pb.struct
+    n = {k: int(getattr(st, k)) for k in _lib.BATCH_COUNTS + ["n_seq_words"]}
+    size = dict(tint_island_off=n["n_tints"] + 1, tint_rep_off=n["n_tints"] + 1, tint_read_off=n["n_tints"] + 1,
+                island_start=n["n_islands"], island_sample_off=n["n_islands"] + 1, rep_iv_off=n["n_reps"] + 1,
+                rep_weight=n["n_reps"], rep_iv_fs=n["n_rep_ivs"], rep_iv_fe=n["n_rep_ivs"], read_rep=n["n_reads"],
+                read_strand=n["n_reads"], read_len=n["n_reads"], read_iv_off=n["n_reads"] + 1, read_seq_off=n["n_reads"] + 1,
+                riv_ts=n["n_read_ivs"], riv_te=n["n_read_ivs"], riv_qs=n["n_read_ivs"], riv_qe=n["n_read_ivs"],
+                riv_cig_off=n["n_read_ivs"] + 1, cigar=n["n_cigar_ops"], seq_is_a=n["n_seq_words"], seq_is_t=n["n_seq_words"])
+    ct = dict(read_strand=C.c_uint8, read_seq_off=C.c_int64, cigar=C.c_uint32, seq_is_a=C.c_uint32, seq_is_t=C.c_uint32)
+    out = dict(n)
+    for nm, k in size.items():
+        out[nm] = (np.ctypeslib.as_array(C.cast(getattr(st, nm), C.POINTER(ct.get(nm, C.c_int32))), shape=(k,)).copy()
+                   if k else np.zeros(0))
+    return out
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2_flagsA", "degenerate", "cfg4_mini"])
+def test_packed_batch_round_trip(name, golden_set, manifest, tmp_path, built_lib):
+    """frs_packed_write -> frs_packed_read gives back every array of the batch, and the formatter fed from
+    the re-read batch (names, chr and tint columns travel in the file) emits the reference's bytes."""
+    from freddie_b200 import _lib, hostio
+    tints, flags, split_dir = golden_set(name)
+    pb = _native_batch(split_dir, tints)
+    path = str(tmp_path / "b.frsb")
+    pb.write_packed(path)
+    rd = hostio.ParsedBatch.from_packed(path)
+    a, b = _batch_arrays(pb), _batch_arrays(rd)
+    assert a.keys() == b.keys()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    _, arrays = oracle_result_arrays(tints, orc.Params(**flags_to_kwargs(flags)))
+    res = _lib.FrsResult()
+    for k in _lib.RESULT_ARRAYS:
+        setattr(res, k, arrays[k].ctypes.data_as(C.c_void_p))
+
+    class R:
+        def as_struct(self):
+            return res
+    out = str(tmp_path / "seg")
+    ops, lps = [], []
+    for t in tints:
+        os.makedirs(os.path.join(out, t["chr"]), exist_ok=True)
+        ops.append(os.path.join(out, t["chr"], "segment_%s_%d.tsv" % (t["chr"], t["id"])).encode())
+        lps.append(os.path.join(out, t["chr"], "segment_%s_%d.log" % (t["chr"], t["id"])).encode())
+    rd.format(R(), ops, lps, 2)
+    assert sha_dir(out) == manifest[name]["outputs"]
+    pb.close()
+    rd.close()
+
+
+def test_packed_reader_rejects_damaged_files(golden_set, tmp_path, built_lib):
+    from freddie_b200 import _lib, hostio
+    tints, _, split_dir = golden_set("degenerate")
+    pb = _native_batch(split_dir, tints)
+    path = str(tmp_path / "b.frsb")
+    pb.write_packed(path)
+    pb.close()
+    raw = open(path, "rb").read()
+    for damaged in (raw[:100], b"NOTPACKD" + raw[8:], raw[:-40], raw[:16] + b"\xff" * 8 + raw[24:]):
+        bad = str(tmp_path / "bad.frsb")
+        open(bad, "wb").write(damaged)
+        with pytest.raises(_lib.FrsError, match="not a packed batch"):
+            hostio.ParsedBatch.from_packed(bad)
+    with pytest.raises(_lib.FrsError, match="FileNotFoundError"):
+        hostio.ParsedBatch.from_packed(str(tmp_path / "missing.frsb"))
+
+
+@pytest.mark.parametrize("mode", ["tsv", "packed"])
+def test_directory_driver_with_an_oracle_backed_engine(mode, golden_set, manifest, tmp_path, built_lib, monkeypatch):
+    """run_directory's plumbing without a GPU: batching, lanes, the packed index, the native parser and
+    formatter are the real ones; only the context that would run the kernels is replaced by one that
+    answers with the oracle's results for the batch it is handed.  Output must be the reference's."""
+    from freddie_b200 import _lib, packed, schedule, segment
+    from freddie_b200.engine import SegmentParams
+    name = "cfg2_flagsA"
+    tints, flags, split_dir = golden_set(name)
+    by_key = {(t["chr"], t["id"]): t for t in tints}
+    oprm = orc.Params(**flags_to_kwargs(flags))
+    src = split_dir
+    if mode == "packed":
+        src = str(tmp_path / "packed")
+        st = packed.pack_directory(split_dir, src, threads=2, batch_reads=400)
+        assert st["tints"] == len(tints) and st["batches"] > 1 and packed.is_packed_dir(src)
+        assert not packed.is_packed_dir(split_dir)
+
+    class Result:
+        def __init__(self, arrays, cells):
+            self.arrays, self.sizes = arrays, dict(dp_cells=cells)
+
+        def as_struct(self):
+            r = _lib.FrsResult()
+            for k in _lib.RESULT_ARRAYS:
+                setattr(r, k, self.arrays[k].ctypes.data_as(C.c_void_p))
+            return r
+
+    class OracleEngine:
+        """Finds the tints of the batch by its read ids... the batch carries no names, so match on sizes."""
+        def segment_batch(self, pb, prm):
+            st = pb.struct
+            tro = np.ctypeslib.as_array(C.cast(st.tint_read_off, C.POINTER(C.c_int32)), shape=(st.n_tints + 1,))
+            ist = np.ctypeslib.as_array(C.cast(st.island_start, C.POINTER(C.c_int32)), shape=(st.n_islands,))
+            tio = np.ctypeslib.as_array(C.cast(st.tint_island_off, C.POINTER(C.c_int32)), shape=(st.n_tints + 1,))
+            chosen = []
+            for k in range(st.n_tints):
+                first_island = int(ist[tio[k]])
+                n_reads = int(tro[k + 1] - tro[k])
+                hit = [t for t in tints if t["intervals"][0][0] == first_island and len(t["reads"]) == n_reads]
+                assert len(hit) == 1
+                chosen.append(hit[0])
+            _, arrays = oracle_result_arrays(chosen, oprm)
+            return Result(arrays, 0)
+
+    lib = _lib.load()
+    monkeypatch.setattr(lib, "frs_device_count", lambda: 1, raising=False)
+    monkeypatch.setattr(segment, "get_engine", lambda dev=0, lane=0: OracleEngine())
+    out = str(tmp_path / "seg")
+    prm = SegmentParams(oprm.sigma, oprm.tp, oprm.vf, oprm.mps, oprm.lo, oprm.ignore_ends)
+    stats = segment.run_directory(src, out, prm, threads=2, gpus=1, batch_reads=400, progress=False, lanes=2)
+    assert stats["tints"] == len(tints) and stats["reads"] == sum(len(t["reads"]) for t in tints)
+    assert sha_dir(out) == manifest[name]["outputs"]
+    assert len(by_key) == len(tints)
