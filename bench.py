@@ -12,6 +12,8 @@ interact, so there is no data-path collective, only the timing reduction).
 value  = reads/s with the packed batch already resident in HBM (K x frs_run, CUDA events).
 e2e    = reads/s through the C ABI with pinned HOST buffers: frs_upload + frs_run + frs_download.
 roofline = dominant kernel of the step, algorithmic bytes / CUDA-event time.
+cli    = files to files on a bounded prefix of the workload (SPLIT text -> native parser -> CUDA -> native
+         formatter -> SEGMENT files), the scope the reference itself is measured at (rank 0, N = 1 only).
 cpu_baseline = the oracle port (numpy restatement of the reference, NOT the product) on all host
 cores over a bounded sample of the same workload (rank 0, N = 1 only).
 """
@@ -367,6 +369,8 @@ def run_cuda_arm(args):
         stages=stages,
         setup_seconds=round(t_gen, 1),
     )
+    if world == 1 and not args.no_cli:
+        line["cli"] = cli_scope(tints, cores)
     if world == 1 and not args.no_cpu_baseline:
         r, c, sample = oracle_rate(tints, cores, int(os.environ.get("FRS_CPU_SAMPLE_READS", 300 * cores * 15)))
         line["cpu_baseline"] = dict(value=r, unit=UNIT, cores=cores, kind="port", dp_cells_per_sec=c,
@@ -375,6 +379,46 @@ def run_cuda_arm(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def cli_scope(tints, cores):
+    """The files-to-files scope of SURVEY.md 8d (what the reference is measured at): SPLIT text on disk ->
+    native parser -> CUDA pipeline -> native formatter -> SEGMENT files, through the drop-in directory driver
+    (`freddie_b200.segment.run_directory`), on a bounded prefix of the workload's tints.  Never fatal: the
+    kernel-path numbers above do not depend on it."""
+    import shutil
+    import tempfile
+    try:
+        from freddie_b200 import synth
+        from freddie_b200.engine import SegmentParams
+        from freddie_b200.segment import run_directory
+        n_target = int(os.environ.get("FRS_CLI_SAMPLE_READS", "50000"))
+        sample, n = [], 0
+        for t in tints:
+            sample.append(t)
+            n += len(t["reads"])
+            if n >= n_target:
+                break
+        work = tempfile.mkdtemp(prefix="frs_bench_cli_")
+        try:
+            sd, od = os.path.join(work, "split"), os.path.join(work, "seg")
+            synth.write_split_dir(sample, sd)
+            split_bytes = sum(os.path.getsize(os.path.join(b, f)) for b, _, fs in os.walk(sd) for f in fs)
+            run_directory(sd, od, SegmentParams(), threads=cores, gpus=1, progress=False)  # warm: contexts, buffers
+            shutil.rmtree(od, ignore_errors=True)
+            t0 = time.perf_counter()
+            st = run_directory(sd, od, SegmentParams(), threads=cores, gpus=1, progress=False)
+            dt = time.perf_counter() - t0
+            n_files = sum(len(fs) for _, _, fs in os.walk(od))
+            return dict(value=st["reads"] / dt, unit=UNIT, seconds=round(dt, 4), host_threads=cores,
+                        sample="first %d tints / %d reads of the workload, %.0f MB of SPLIT text in, %d files out"
+                               % (len(sample), st["reads"], split_bytes / 1e6, n_files),
+                        scope="files to files: native parser -> CUDA pipeline -> native formatter (second run, "
+                              "CUDA contexts warm)")
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
+    except Exception as e:  # noqa: BLE001
+        return dict(value=None, unit=UNIT, error="%s: %s" % (type(e).__name__, e))
 
 
 def _download_into(eng, res):
@@ -394,6 +438,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cli", action="store_true", help="skip the files-to-files scope")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
