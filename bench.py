@@ -384,14 +384,12 @@ def run_cuda_arm(args):
 def cli_scope(tints, cores):
     """The files-to-files scope of SURVEY.md 8d (what the reference is measured at): SPLIT text on disk ->
     native parser -> CUDA pipeline -> native formatter -> SEGMENT files, through the drop-in directory driver
-    (`freddie_b200.segment.run_directory`), on a bounded prefix of the workload's tints.  Never fatal: the
-    kernel-path numbers above do not depend on it."""
+    (`freddie_b200.segment.run_directory`), on a bounded prefix of the workload's tints.  Runs in a child
+    process with a time limit and is never fatal: the kernel-path numbers do not depend on it."""
     import shutil
     import tempfile
     try:
         from freddie_b200 import synth
-        from freddie_b200.engine import SegmentParams
-        from freddie_b200.segment import run_directory
         n_target = int(os.environ.get("FRS_CLI_SAMPLE_READS", "50000"))
         sample, n = [], 0
         for t in tints:
@@ -401,24 +399,42 @@ def cli_scope(tints, cores):
                 break
         work = tempfile.mkdtemp(prefix="frs_bench_cli_")
         try:
-            sd, od = os.path.join(work, "split"), os.path.join(work, "seg")
+            sd = os.path.join(work, "split")
             synth.write_split_dir(sample, sd)
-            split_bytes = sum(os.path.getsize(os.path.join(b, f)) for b, _, fs in os.walk(sd) for f in fs)
-            run_directory(sd, od, SegmentParams(), threads=cores, gpus=1, progress=False)  # warm: contexts, buffers
-            shutil.rmtree(od, ignore_errors=True)
-            t0 = time.perf_counter()
-            st = run_directory(sd, od, SegmentParams(), threads=cores, gpus=1, progress=False)
-            dt = time.perf_counter() - t0
-            n_files = sum(len(fs) for _, _, fs in os.walk(od))
-            return dict(value=st["reads"] / dt, unit=UNIT, seconds=round(dt, 4), host_threads=cores,
-                        sample="first %d tints / %d reads of the workload, %.0f MB of SPLIT text in, %d files out"
-                               % (len(sample), st["reads"], split_bytes / 1e6, n_files),
-                        scope="files to files: native parser -> CUDA pipeline -> native formatter (second run, "
-                              "CUDA contexts warm)")
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cli-run", work, "--cli-threads", str(cores)],
+                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=240)
+            if r.returncode != 0:
+                return dict(value=None, unit=UNIT, error=(r.stderr.strip().splitlines() or ["exit %d" % r.returncode])[-1][:300])
+            out = json.loads(r.stdout.strip().splitlines()[-1])
+            out["sample"] = "first %d tints of the workload: %s" % (len(sample), out.pop("sample"))
+            return out
         finally:
             shutil.rmtree(work, ignore_errors=True)
     except Exception as e:  # noqa: BLE001
         return dict(value=None, unit=UNIT, error="%s: %s" % (type(e).__name__, e))
+
+
+def cli_run(work, threads):
+    """Child of cli_scope: the directory driver twice over work/split (first run warms the CUDA contexts and
+    the library's buffers), one JSON object on stdout."""
+    import shutil
+    from freddie_b200.engine import SegmentParams
+    from freddie_b200.segment import run_directory
+    sd, od = os.path.join(work, "split"), os.path.join(work, "seg")
+    split_bytes = sum(os.path.getsize(os.path.join(b, f)) for b, _, fs in os.walk(sd) for f in fs)
+    t0 = time.perf_counter()
+    run_directory(sd, od, SegmentParams(), threads=threads, gpus=1, progress=False)
+    cold = time.perf_counter() - t0
+    shutil.rmtree(od, ignore_errors=True)
+    t0 = time.perf_counter()
+    st = run_directory(sd, od, SegmentParams(), threads=threads, gpus=1, progress=False)
+    dt = time.perf_counter() - t0
+    n_files = sum(len(fs) for _, _, fs in os.walk(od))
+    print(json.dumps(dict(
+        value=st["reads"] / dt, unit=UNIT, seconds=round(dt, 4), first_run_seconds=round(cold, 4), host_threads=threads,
+        sample="%d reads, %.0f MB of SPLIT text in, %d files out" % (st["reads"], split_bytes / 1e6, n_files),
+        scope="files to files: native parser -> CUDA pipeline -> native formatter (second run of the process: CUDA "
+              "contexts warm; first_run_seconds includes their creation)")))
 
 
 def _download_into(eng, res):
@@ -439,7 +455,12 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cli", action="store_true", help="skip the files-to-files scope")
+    ap.add_argument("--cli-run", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--cli-threads", type=int, default=1, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cli_run:
+        cli_run(args.cli_run, args.cli_threads)
+        return
     if args.impl == "reference":
         run_reference_arm(args)
     else:
