@@ -120,6 +120,8 @@ def load():
         lib.frs_packed_write.restype = C.c_int
         lib.frs_packed_read.argtypes = [C.c_char_p, C.POINTER(_p), C.c_char_p, C.c_size_t]
         lib.frs_packed_read.restype = C.c_int
+        lib.frs_packed_write_segment.argtypes = [_p, C.POINTER(FrsResult), C.c_char_p, C.c_char_p, C.c_size_t]
+        lib.frs_packed_write_segment.restype = C.c_int
     if lib.frs_abi_version() != 1:
         raise FrsError(-101, "ABI version mismatch")
     _lib = lib
@@ -130,5 +132,5 @@ EXPORTED = [
     "frs_abi_version", "frs_device_count", "frs_create", "frs_destroy", "frs_last_error", "frs_stream",
     "frs_upload", "frs_run", "frs_download", "frs_segment_batch", "frs_get_intermediate", "frs_set_profiling",
     "frs_get_timings", "frs_last_launch_count", "frs_set_option", "frs_get_stats", "frs_parse_tints", "frs_parsed_batch", "frs_parsed_free",
-    "frs_format_tints", "frs_packed_write", "frs_packed_read",
+    "frs_format_tints", "frs_packed_write", "frs_packed_read", "frs_packed_write_segment",
 ]

@@ -1042,6 +1042,71 @@ int frs_packed_write(const frs_parsed* P, const char* path, char* err, size_t er
   return 0;
 }
 
+// The SEGMENT twin ("FRSSEGM1"): what frs_format_tints prints, as arrays -- for a consumer that would
+// otherwise re-parse segment_*.tsv with regexes (freddie_cluster.py:119-172).  Sections: tint id, tint chr
+// offsets + text, tint_read_off, tint_rep_off, tint_final_off, final_pos, tint_digit_off, digits (ASCII,
+// rep-major), read_rep, read rid, read tint column, name offsets + names, chr offsets + chrs, read_strand,
+// read_head (8 x i32, FRS_HEAD_*), read_gap_off, gap_rec ((l1, f2, size) triples).
+int frs_packed_write_segment(const frs_parsed* P, const frs_result* R, const char* path, char* err, size_t err_cap) {
+  if (err && err_cap) err[0] = 0;
+  if (!P || !R || !path) return pack_fail(err, err_cap, FRS_ERR_ARG, "frs_packed_write_segment: NULL argument");
+  static const char MAGIC[8] = {'F', 'R', 'S', 'S', 'E', 'G', 'M', '1'};
+  const size_t T = P->tints.size(), N = P->read_rep.size();
+  std::vector<int64_t> tint_id(T), rid(N), rtint(N);
+  std::vector<uint64_t> tchr_off(T + 1, 0), name_off(N + 1, 0), rchr_off(N + 1, 0);
+  std::string tchr, names, rchr;
+  size_t r = 0;
+  for (size_t t = 0; t < T; ++t) {
+    const TintData& D = P->tints[t];
+    tint_id[t] = D.id;
+    tchr += D.chr;
+    tchr_off[t + 1] = tchr.size();
+    for (const ReadMeta& m : D.meta) {
+      rid[r] = m.rid;
+      rtint[r] = m.tint;
+      names.append(D.text, m.name_off, m.name_len);
+      name_off[r + 1] = names.size();
+      rchr.append(D.text, m.chr_off, m.chr_len);
+      rchr_off[r + 1] = rchr.size();
+      ++r;
+    }
+  }
+  if (r != N) return pack_fail(err, err_cap, FRS_ERR_STATE, "frs_packed_write_segment: read tables out of step");
+  const size_t NF = (size_t)R->tint_final_off[T], ND = (size_t)R->tint_digit_off[T], NG = (size_t)R->read_gap_off[N];
+  const Sec sec[] = {
+      {tint_id.data(), T * 8}, {tchr_off.data(), (T + 1) * 8}, {tchr.data(), tchr.size()},
+      {P->tint_read_off.data(), (T + 1) * 4}, {P->tint_rep_off.data(), (T + 1) * 4},
+      {R->tint_final_off, (T + 1) * 4}, {R->final_pos, NF * 4}, {R->tint_digit_off, (T + 1) * 8}, {R->digits, ND},
+      {P->read_rep.data(), N * 4}, {rid.data(), N * 8}, {rtint.data(), N * 8},
+      {name_off.data(), (N + 1) * 8}, {names.data(), names.size()}, {rchr_off.data(), (N + 1) * 8}, {rchr.data(), rchr.size()},
+      {P->read_strand.data(), N}, {R->read_head, N * 32}, {R->read_gap_off, (N + 1) * 4}, {R->gap_rec, NG * 12},
+  };
+  const int NS = (int)(sizeof sec / sizeof sec[0]);
+  FILE* f = fopen(path, "wb");
+  if (!f) return pack_fail(err, err_cap, FRS_ERR_IO, std::string("cannot open ") + path + ": " + strerror(errno));
+  std::vector<uint64_t> table(2 * (size_t)NS);
+  uint64_t at = 16 + 16 * (uint64_t)NS;
+  for (int k = 0; k < NS; ++k) {
+    at = (at + 63) & ~(uint64_t)63;
+    table[2 * (size_t)k] = at;
+    table[2 * (size_t)k + 1] = sec[k].bytes;
+    at += sec[k].bytes;
+  }
+  const uint64_t ns = (uint64_t)NS;
+  bool ok = fwrite(MAGIC, 1, 8, f) == 8 && fwrite(&ns, 8, 1, f) == 1 && fwrite(table.data(), 8, table.size(), f) == table.size();
+  uint64_t pos = 16 + 16 * (uint64_t)NS;
+  static const char zeros[64] = {0};
+  for (int k = 0; k < NS && ok; ++k) {
+    const uint64_t pad = table[2 * (size_t)k] - pos;
+    ok = (pad == 0 || fwrite(zeros, 1, (size_t)pad, f) == pad) &&
+         (sec[k].bytes == 0 || fwrite(sec[k].p, 1, (size_t)sec[k].bytes, f) == sec[k].bytes);
+    pos = table[2 * (size_t)k] + sec[k].bytes;
+  }
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) return pack_fail(err, err_cap, FRS_ERR_IO, std::string("short write to ") + path);
+  return 0;
+}
+
 int frs_packed_read(const char* path, frs_parsed** out, char* err, size_t err_cap) {
   if (err && err_cap) err[0] = 0;
   if (!path || !out) return pack_fail(err, err_cap, FRS_ERR_ARG, "frs_packed_read: NULL argument");

@@ -81,6 +81,15 @@ class ParsedBatch:
         if rc != 0:
             raise _lib.FrsError(rc, err.value.decode(errors="replace"))
 
+    def write_packed_segment(self, res, path: str):
+        """The results of the batch as one binary file (``frs_packed_write_segment``, "FRSSEGM1");
+        ``freddie_b200.packed.PackedSegment`` reads it back."""
+        err = C.create_string_buffer(1024)
+        r = res.as_struct()
+        rc = self.lib.frs_packed_write_segment(self.handle, C.byref(r), path.encode(), err, len(err))
+        if rc != 0:
+            raise _lib.FrsError(rc, err.value.decode(errors="replace"))
+
     def close(self):
         if self.handle:
             self.lib.frs_parsed_free(self.handle)
@@ -94,7 +103,8 @@ class ParsedBatch:
 
 
 def run_batch_native(eng: Engine, prm: SegmentParams, split_dir: str, outdir: str,
-                     chunk: Sequence[Tuple[str, int]], threads: int, packed_file: str = None):
+                     chunk: Sequence[Tuple[str, int]], threads: int, packed_file: str = None,
+                     packed_segment: str = None):
     """One batch, files to files: parse (or load ``packed_file``, a batch of exactly the tints of
     ``chunk`` in that order), segment on ``eng``'s GPU, format."""
     prof = os.environ.get("FRS_CLI_PROFILE")
@@ -109,6 +119,8 @@ def run_batch_native(eng: Engine, prm: SegmentParams, split_dir: str, outdir: st
         res = eng.segment_batch(pb, prm)
         t2 = time.perf_counter()
         pb.format(res, op, lp, threads)
+        if packed_segment:
+            pb.write_packed_segment(res, packed_segment)
         t3 = time.perf_counter()
         if prof:
             sys.stderr.write("[frs cli profile] batch of %d tints / %d reads: parse %.3f s  upload+kernels+download %.3f s  "

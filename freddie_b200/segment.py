@@ -69,6 +69,9 @@ def parse_args(argv=None):
     # additive flags of the B200 implementation
     parser.add_argument("--gpus", type=int, default=0, help="GPUs to use (0 = all visible)")
     parser.add_argument("--batch-reads", type=int, default=131072, help="Upper bound of reads per GPU batch")
+    parser.add_argument("--packed-segment", action="store_true",
+                        help="Also write every batch's results as a binary file under <outdir>/packed_segment/ "
+                             "(read back with freddie_b200.packed.PackedSegment); the TSV files are written as always")
     args = parser.parse_args(argv)
     assert 1 >= args.threshold_rate >= 0.5
     assert 10 > args.variance_factor > 0
@@ -212,7 +215,7 @@ def _load_tint_py(split_dir, contig, tint_id):
 
 def run_directory(split_dir: str, outdir: str, prm: SegmentParams, threads: int = 1, gpus: int = 0,
                   batch_reads: int = 131072, native: Optional[bool] = None, progress: bool = True,
-                  lanes: int = 2) -> dict:
+                  lanes: int = 2, packed_segment: bool = False) -> dict:
     """Segments every tint of a SPLIT directory; returns counters.  Output is independent of
     ``threads``, ``gpus``, ``lanes`` and batch composition.  Every GPU is fed by ``lanes`` host threads
     (one library context each) that take the GPU's batches in turn, so that parsing and formatting of
@@ -264,6 +267,18 @@ def run_directory(split_dir: str, outdir: str, prm: SegmentParams, threads: int 
                                         [jobs[i] for i in shards[d]], [costs[i] for i in shards[d]], batch_reads)))
                  for d in range(n_gpus)]
 
+    seg_index: List[dict] = []
+    if packed_segment:
+        os.makedirs(os.path.join(outdir, "packed_segment"), exist_ok=True)
+
+    def segment_file(chunk):
+        if not packed_segment:
+            return None
+        with lock:
+            name = "segment_batch_%05d.frsg" % len(seg_index)
+            seg_index.append(dict(file=name, tints=[[c, t] for c, t in chunk]))
+        return os.path.join(outdir, "packed_segment", name)
+
     def worker(dev, lane):
         try:
             t_eng = time.perf_counter()
@@ -273,7 +288,8 @@ def run_directory(split_dir: str, outdir: str, prm: SegmentParams, threads: int 
                                  % (dev, lane, time.perf_counter() - t_eng))
             for chunk, packed_file in feeds[dev]:
                 if native:
-                    n_reads, cells = hostio.run_batch_native(eng, prm, split_dir, outdir, chunk, threads, packed_file)
+                    n_reads, cells = hostio.run_batch_native(eng, prm, split_dir, outdir, chunk, threads, packed_file,
+                                                             segment_file(chunk))
                 else:
                     tints = [_load_tint_py(split_dir, c, t) for c, t in chunk]
                     batch = pack_tints(tints)
@@ -296,6 +312,10 @@ def run_directory(split_dir: str, outdir: str, prm: SegmentParams, threads: int 
         t.join()
     if errors:
         raise errors[0]
+    if packed_segment:
+        import json
+        with open(os.path.join(outdir, "packed_segment", "index.json"), "w") as fh:
+            json.dump(dict(format="freddie-b200-packed-segment-1", batches=seg_index), fh)
     return stats
 
 
@@ -305,7 +325,7 @@ def main(argv=None):
     prm = SegmentParams(args.sigma, args.threshold_rate, args.variance_factor, args.max_problem_size,
                         args.min_read_support_outside, not args.consider_ends)
     run_directory(args.split_dir, args.outdir, prm, threads=args.threads, gpus=args.gpus,
-                  batch_reads=args.batch_reads)
+                  batch_reads=args.batch_reads, packed_segment=args.packed_segment)
 
 
 if __name__ == "__main__":

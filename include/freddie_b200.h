@@ -223,6 +223,9 @@ int frs_format_tints(const frs_parsed* p, const frs_result* res, const char* con
  *      default.  frs_packed_read returns the same object frs_parse_tints does. ---- */
 int frs_packed_write(const frs_parsed* p, const char* path, char* err, size_t err_cap);
 int frs_packed_read(const char* path, frs_parsed** out, char* err, size_t err_cap);
+/* The SEGMENT twin ("FRSSEGM1"): the results of a batch as arrays, for a consumer that would otherwise
+ * re-parse segment_*.tsv (freddie_cluster.py:119-172); freddie_b200/packed.py reads it back. */
+int frs_packed_write_segment(const frs_parsed* p, const frs_result* res, const char* path, char* err, size_t err_cap);
 
 #ifdef __cplusplus
 }

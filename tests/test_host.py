@@ -474,7 +474,87 @@ def test_directory_driver_with_an_oracle_backed_engine(mode, golden_set, manifes
     monkeypatch.setattr(segment, "get_engine", lambda dev=0, lane=0: OracleEngine())
     out = str(tmp_path / "seg")
     prm = SegmentParams(oprm.sigma, oprm.tp, oprm.vf, oprm.mps, oprm.lo, oprm.ignore_ends)
-    stats = segment.run_directory(src, out, prm, threads=2, gpus=1, batch_reads=400, progress=False, lanes=2)
+    stats = segment.run_directory(src, out, prm, threads=2, gpus=1, batch_reads=400, progress=False, lanes=2,
+                                  packed_segment=(mode == "packed"))
     assert stats["tints"] == len(tints) and stats["reads"] == sum(len(t["reads"]) for t in tints)
-    assert sha_dir(out) == manifest[name]["outputs"]
     assert len(by_key) == len(tints)
+    if mode == "packed":  # --packed-segment: the binary twin next to the TSV files, same bytes when printed
+        import json
+        import shutil
+        idx = json.load(open(os.path.join(out, "packed_segment", "index.json")))
+        seen = []
+        for b in idx["batches"]:
+            ps = packed.PackedSegment(os.path.join(out, "packed_segment", b["file"]))
+            assert ps.tints() == [(c, t) for c, t in b["tints"]]
+            for k, (c, t) in enumerate(ps.tints()):
+                assert ps.text(k) == open(os.path.join(out, c, "segment_%s_%d.tsv" % (c, t))).read()
+                seen.append((c, t))
+        assert sorted(seen) == sorted(by_key)
+        shutil.rmtree(os.path.join(out, "packed_segment"))
+    assert sha_dir(out) == manifest[name]["outputs"]
+
+
+def _reference_read_segment():
+    """freddie_cluster.read_segment of the unmodified reference (authoring container only; gurobipy and
+    other solver-side imports are stubbed: read_segment is plain Python + re)."""
+    ref = "/root/reference/py"
+    if not os.path.isdir(ref):
+        return None
+    import importlib
+    import types
+    for m in ("gurobipy", "networkx"):
+        if m not in sys.modules:
+            try:
+                importlib.import_module(m)
+            except Exception:
+                sys.modules[m] = types.ModuleType(m)
+    sys.path.insert(0, ref)
+    try:
+        return importlib.import_module("freddie_cluster").read_segment
+    except Exception:
+        return None
+    finally:
+        sys.path.remove(ref)
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2_flagsA", "degenerate", "plateau"])
+def test_packed_segment_twin(name, golden_set, manifest, tmp_path, built_lib):
+    """frs_packed_write_segment -> PackedSegment: text(t) is the reference's SEGMENT file byte for byte, and
+    read_segment() equals what the reference's own freddie_cluster.read_segment parses from that text."""
+    import hashlib
+    from freddie_b200 import _lib, packed
+    tints, flags, split_dir = golden_set(name)
+    pb = _native_batch(split_dir, tints)
+    _, arrays = oracle_result_arrays(tints, orc.Params(**flags_to_kwargs(flags)))
+    res = _lib.FrsResult()
+    for k in _lib.RESULT_ARRAYS:
+        setattr(res, k, arrays[k].ctypes.data_as(C.c_void_p))
+
+    class R:
+        def as_struct(self):
+            return res
+    path = str(tmp_path / "seg.frsg")
+    pb.write_packed_segment(R(), path)
+    pb.close()
+    ps = packed.PackedSegment(path)
+    assert ps.tints() == [(t["chr"], t["id"]) for t in tints]
+    ref_read_segment = _reference_read_segment()
+    want_all = {}
+    for k, (c, i) in enumerate(ps.tints()):
+        text = ps.text(k)
+        assert hashlib.sha256(text.encode()).hexdigest() == manifest[name]["outputs"]["%s/segment_%s_%d.tsv" % (c, c, i)]
+        if ref_read_segment is not None:
+            f = str(tmp_path / ("segment_%s_%d.tsv" % (c, i)))
+            open(f, "w").write(text)
+            want_all.update(ref_read_segment(f))
+    if ref_read_segment is not None:
+        got = ps.read_segment()
+        assert got.keys() == want_all.keys()
+        for tid in got:
+            g, w = got[tid], want_all[tid]
+            assert g["segs"] == w["segs"] and g["chr"] == w["chr"] and g["read_reps"] == w["read_reps"], tid
+            assert g["reads"] == w["reads"], tid
+    with pytest.raises(ValueError):
+        bad = str(tmp_path / "bad.frsg")
+        open(bad, "wb").write(open(path, "rb").read()[:200])
+        packed.PackedSegment(bad)
