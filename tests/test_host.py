@@ -558,3 +558,33 @@ def test_packed_segment_twin(name, golden_set, manifest, tmp_path, built_lib):
         bad = str(tmp_path / "bad.frsg")
         open(bad, "wb").write(open(path, "rb").read()[:200])
         packed.PackedSegment(bad)
+
+
+@pytest.mark.parametrize("seed", [101, 102, 103, 104])
+def test_native_parser_on_fresh_random_tints(seed, tmp_path, built_lib, monkeypatch):
+    """Seeds that are not golden sets: the native parser (sequential and chunked paths) against the Python
+    packer on freshly generated tints, incl. a heavy-duplication tint (weighted read reps)."""
+    from freddie_b200 import _lib, hostio, synth
+    from freddie_b200.pack import pack_tints
+    from freddie_b200.segment import _load_tint_py
+    tints = synth.make_config(2, scale=0.004, seed=seed) + synth.make_config(3, scale=0.004, seed=seed)[:1]
+    for k, t in enumerate(tints):  # unique (contig, id) pairs inside one directory
+        t["id"] = k
+        for r in t["reads"]:
+            r["tint"] = k
+    d = str(tmp_path / "s")
+    synth.write_split_dir(tints, d)
+    ref = pack_tints([_load_tint_py(d, t["chr"], t["id"]) for t in tints])
+    for big in (None, "1"):
+        if big:
+            monkeypatch.setenv("FRS_PARSE_BIG_BYTES", big)
+        pb = _native_batch(d, tints, threads=3)
+        for k, v in ref.counts().items():
+            assert getattr(pb.struct, k) == v, k
+        for nm in _lib.BATCH_ARRAYS:
+            arr = ref.arrays[nm]
+            if arr.size == 0:
+                continue
+            ptr = C.cast(getattr(pb.struct, nm), C.POINTER(np.ctypeslib.as_ctypes_type(arr.dtype)))
+            assert np.array_equal(np.ctypeslib.as_array(ptr, shape=arr.shape), arr), (nm, big)
+        pb.close()
