@@ -502,17 +502,16 @@ def _reference_read_segment():
         return None
     import importlib
     import types
-    for m in ("gurobipy", "networkx"):
-        if m not in sys.modules:
-            try:
-                importlib.import_module(m)
-            except Exception:
-                sys.modules[m] = types.ModuleType(m)
+    try:
+        importlib.import_module("gurobipy")
+    except Exception:
+        stub = types.ModuleType("gurobipy")  # `from gurobipy import Model, GRB, quicksum, LinExpr` (:13)
+        for attr in ("Model", "GRB", "quicksum", "LinExpr"):
+            setattr(stub, attr, None)
+        sys.modules["gurobipy"] = stub
     sys.path.insert(0, ref)
     try:
-        return importlib.import_module("freddie_cluster").read_segment
-    except Exception:
-        return None
+        return importlib.import_module("freddie_cluster").read_segment  # a failure here must be loud
     finally:
         sys.path.remove(ref)
 
