@@ -132,10 +132,7 @@ def algorithmic_bytes(counts: dict, sizes: dict, cov_elems: int) -> dict:
 def oracle_rate(tints, threads: int, target_reads: int):
     """Oracle (CPU port of the reference algorithm) on a bounded, size-stratified sample of tints."""
     from multiprocessing import Pool
-    order = sorted(range(len(tints)), key=lambda i: len(tints[i]["reads"]))
-    stride = max(1, int(len(order) * (sum(len(t["reads"]) for t in tints) / len(tints)) / max(target_reads, 1)))
-    pick = order[stride // 2::stride]
-    sample = [tints[i] for i in pick]
+    sample = stratified_sample(tints, target_reads)
     n = sum(len(t["reads"]) for t in sample)
     t0 = time.perf_counter()
     with Pool(threads) as p:
@@ -152,35 +149,126 @@ def _oracle_one(tint):
     return len(tint["reads"]), st.get("cells", 0)
 
 
+def stratified_sample(tints, target_reads: int):
+    """Every k-th tint of the workload ordered by size: the sample keeps the size mix of the workload."""
+    order = sorted(range(len(tints)), key=lambda i: len(tints[i]["reads"]))
+    stride = max(1, int(len(order) * (sum(len(t["reads"]) for t in tints) / len(tints)) / max(target_reads, 1)))
+    pick = order[stride // 2::stride]
+    return [tints[i] for i in pick]
+
+
+class ReferenceRunner:
+    """The UNMODIFIED reference CLI (oracle/_ref, see oracle/build_ref.py) on a SPLIT sample in tmpfs:
+    ``freddie_segment.py -s SPLIT -o OUT -t <cores>``, wall clock around the subprocess."""
+
+    def __init__(self, sample, cores):
+        import tempfile
+        from freddie_b200 import synth
+        base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+        self.work = tempfile.mkdtemp(prefix="frs_ref_", dir=base)
+        self.split = os.path.join(self.work, "split")
+        synth.write_split_dir(sample, self.split)
+        self.reads = sum(len(t["reads"]) for t in sample)
+        self.tints = len(sample)
+        self.cores = cores
+
+    def run(self):
+        import shutil
+        from oracle import build_ref
+        out = os.path.join(self.work, "out")
+        shutil.rmtree(out, ignore_errors=True)
+        t0 = time.perf_counter()
+        r = subprocess.run(build_ref.command(self.split, out, self.cores), stdout=subprocess.DEVNULL,
+                           stderr=subprocess.PIPE, text=True)
+        dt = time.perf_counter() - t0
+        if r.returncode != 0:
+            raise RuntimeError("reference CLI failed: " + r.stderr[-500:])
+        n_out = sum(len(fs) for _, _, fs in os.walk(out))
+        if n_out != 2 * self.tints:
+            raise RuntimeError("reference CLI wrote %d files for %d tints" % (n_out, self.tints))
+        return dt
+
+    def close(self):
+        import shutil
+        shutil.rmtree(self.work, ignore_errors=True)
+
+
+def reference_rate(tints, cores: int, seconds: float):
+    """reads/s of the reference CLI on a size-stratified sample sized for about ``seconds`` of wall clock
+    (calibrated by a small first run).  Returns (rate, sample description)."""
+    probe = ReferenceRunner(stratified_sample(tints, 250 * cores), cores)
+    try:
+        dt = probe.run()
+        rate = probe.reads / dt
+    finally:
+        probe.close()
+    total = sum(len(t["reads"]) for t in tints)
+    run = ReferenceRunner(stratified_sample(tints, int(min(total, max(500, rate * seconds)))), cores)
+    try:
+        dt = run.run()
+        return run.reads / dt, dict(tints=run.tints, reads=run.reads, seconds=round(dt, 2), threads=cores)
+    finally:
+        run.close()
+
+
+def config_dict(args):
+    """The same object from both arms (the driver compares them)."""
+    return dict(workload=WORKLOADS[args.workload], scale=args.scale, params="defaults (sd=5 tp=0.9 vf=3 mps=50 lo=3)",
+                l2="cuda arm: flushed between timed steps (256 MiB memset)")
+
+
 def run_reference_arm(args):
+    """Times the reference's own CPU implementation on the box's host cores: the unmodified
+    ``freddie_segment.py`` (``oracle/_ref``) with ``-t <cores>``; each step is one run of the CLI over the
+    same bounded, size-stratified sample of the workload (SPLIT files in tmpfs)."""
     rank, _, world = rank_env()
     if rank != 0:
         return
+    from oracle import build_ref
     cores = os.cpu_count() or 1
     tints = make_workload(args.workload, args.scale, 2, min(cores, 16))
     total_steps = args.steps + args.warmup
-    budget = 150.0 / max(total_steps, 1)  # seconds of CPU work per step
-    rate_guess = 300.0 * cores
-    rates, cell_rates, secs, sample = [], [], [], None
-    for s in range(total_steps):
-        target = int(min(sum(len(t["reads"]) for t in tints), max(500, rate_guess * budget)))
-        r, c, sample = oracle_rate(tints, cores, target)
-        rate_guess = r
-        if s >= args.warmup:
-            rates.append(r)
-            cell_rates.append(c)
-            secs.append(sample["seconds"])
-    v = float(np.mean(rates))
+    budget = 170.0 / max(total_steps, 1)  # seconds of wall clock per step
+    if build_ref.available():
+        probe = ReferenceRunner(stratified_sample(tints, 250 * cores), cores)
+        try:
+            rate = probe.reads / probe.run()
+        finally:
+            probe.close()
+        total = sum(len(t["reads"]) for t in tints)
+        runner = ReferenceRunner(stratified_sample(tints, int(min(total, max(500, rate * budget)))), cores)
+        try:
+            secs = [runner.run() for _ in range(total_steps)][args.warmup:]
+        finally:
+            runner.close()
+        v = runner.reads / float(np.mean(secs))
+        kind = "reference"
+        sample = ("unmodified freddie_segment.py (oracle/_ref/freddie_segment.pyc, byte-compiled from the reference "
+                  "source) -t %d, files to files in tmpfs, on a size-stratified sample of the workload, the same "
+                  "sample every step: %d tints, %d reads, %.2f s per run" % (cores, runner.tints, runner.reads, float(np.mean(secs))))
+        cells = None
+    else:  # oracle/_ref was not built (no /root/reference at build time): time the port and say so
+        rates, cell_rates, secs, smp = [], [], [], None
+        rate_guess = 300.0 * cores
+        for s in range(total_steps):
+            target = int(min(sum(len(t["reads"]) for t in tints), max(500, rate_guess * budget)))
+            r, c, smp = oracle_rate(tints, cores, target)
+            rate_guess = r
+            if s >= args.warmup:
+                rates.append(r)
+                cell_rates.append(c)
+                secs.append(smp["seconds"])
+        v = float(np.mean(rates))
+        kind = "port"
+        sample = "oracle/segment_oracle.py (oracle/_ref not built) on a size-stratified sample per step: %s" % smp
+        cells = float(np.mean(cell_rates))
     line = dict(
         impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
         ms_per_step=float(np.mean(secs)) * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int32+f64",
-        data="synthetic", config=dict(workload=WORKLOADS[args.workload], scale=args.scale,
-                                      step="one bounded, size-stratified sample of the workload (see cpu_baseline.sample)"),
-        cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port",
-                          sample="oracle/segment_oracle.py (numpy restatement of freddie_segment.py; the reference "
-                                 "tree is not present on the GPU box) on a size-stratified sample per step: %s" % sample),
+        data="synthetic", config=config_dict(args),
+        cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind=kind, sample=sample),
         e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-        dp_cells_per_sec=float(np.mean(cell_rates)),
+        dp_cells_per_sec=cells,
     )
     print(json.dumps(line))
 

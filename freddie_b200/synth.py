@@ -411,14 +411,17 @@ def config_jobs(cfg: int, scale: float = 1.0, seed: Optional[int] = None) -> lis
 
 
 def iter_config(cfg: int, scale: float = 1.0, seed: Optional[int] = None, workers: int = 1, chunk_reads: int = 200000,
-                limit: Optional[int] = None):
+                limit: Optional[int] = None, select: Optional[Sequence[int]] = None):
     """Streams a config as lists of tints of about ``chunk_reads`` reads (same tints, same order as
     ``make_config``), so that whole-transcriptome configs never have to sit in host memory at once.
     ``limit``: only the first ``limit`` tints (every tint has its own child seed, so a prefix of a
-    config is byte-identical to the same tints of the full config)."""
+    config is byte-identical to the same tints of the full config).  ``select``: only the tints with
+    these indices (in the given order)."""
     jobs = config_jobs(cfg, scale, seed)
     if limit is not None:
         jobs = jobs[:limit]
+    if select is not None:
+        jobs = [jobs[i] for i in select]
     pool = None
     if workers > 1 and len(jobs) > 1:
         from multiprocessing import Pool

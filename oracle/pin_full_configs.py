@@ -43,12 +43,21 @@ def sha_file(p):
     return h.hexdigest()
 
 
-def write_config(cfg, split_dir, workers, scale=1.0, limit=None, chunk_reads=200000):
-    """Streams the config (or its first ``limit`` tints) to ``split_dir``; returns
+def parse_select(text):
+    """"0-399,60000,60004-60010" -> list of tint indices."""
+    out = []
+    for part in text.split(","):
+        a, _, b = part.partition("-")
+        out.extend(range(int(a), int(b or a) + 1))
+    return out
+
+
+def write_config(cfg, split_dir, workers, scale=1.0, limit=None, chunk_reads=200000, select=None):
+    """Streams the config (or its first ``limit`` tints / the tints ``select``) to ``split_dir``; returns
     ({(contig, id): n_reads}, describe dict)."""
     tints_meta = {}
     tot = dict(tints=0, reads=0, intervals=0, positions=0, islands=0)
-    for part in synth.iter_config(cfg, scale=scale, workers=workers, limit=limit, chunk_reads=chunk_reads):
+    for part in synth.iter_config(cfg, scale=scale, workers=workers, limit=limit, chunk_reads=chunk_reads, select=select):
         synth.write_split_dir(part, split_dir)
         d = synth.describe(part)
         for k in tot:
@@ -95,14 +104,18 @@ def main():
     ap.add_argument("--tints", type=int, default=None, help="pin only the first k tints of the config (cfg3: one "
                     "100 k-read tint costs the reference tens of minutes)")
     ap.add_argument("--chunk-reads", type=int, default=200000)
+    ap.add_argument("--select", default=None, help="pin only these tint indices, e.g. 0-999,60000-60004")
+    ap.add_argument("--name", default=None, help="manifest name (default cfg<N>)")
+    ap.add_argument("--merge", action="store_true", help="add the pinned tints to an existing manifest of that name")
     a = ap.parse_args()
-    name = "cfg%d" % a.cfg
+    name = a.name or "cfg%d" % a.cfg
     sd = os.path.join(a.work, name, "split")
     od = os.path.join(a.work, name, "ref")
     for d in (sd, od):
         shutil.rmtree(d, ignore_errors=True)
     t0 = time.time()
-    meta, desc = write_config(a.cfg, sd, a.threads, limit=a.tints, chunk_reads=a.chunk_reads)
+    meta, desc = write_config(a.cfg, sd, a.threads, limit=a.tints, chunk_reads=a.chunk_reads,
+                              select=parse_select(a.select) if a.select else None)
     keys = sorted(meta)
     t_gen = time.time() - t0
     print("%s: generated %s in %.0fs" % (name, desc, t_gen), flush=True)
@@ -120,10 +133,27 @@ def main():
     assert n_files == 2 * len(keys), (n_files, len(keys))
     gold = os.path.join(ROOT, "tests", "golden", "full")
     os.makedirs(gold, exist_ok=True)
-    man = dict(config=name, impl=a.impl, tints_pinned=len(keys), describe=desc, threads=a.threads, seconds=round(t_ref, 1),
-               reads_per_sec=round(desc["reads"] / t_ref, 1), input_digest=digest(m_in), output_digest=digest(m_out),
-               n_reads={k: meta[tuple([k.split("/")[0], int(k.split("/")[1])])] for k in m_in},
-               inputs=m_in, outputs=m_out)
+    n_reads = {k: meta[tuple([k.split("/")[0], int(k.split("/")[1])])] for k in m_in}
+    runs = [dict(tints=len(keys), reads=desc["reads"], threads=a.threads, seconds=round(t_ref, 1), select=a.select,
+                 limit=a.tints)]
+    if a.merge and os.path.exists(os.path.join(gold, name + ".json")):
+        with open(os.path.join(gold, name + ".json")) as fh:
+            old = json.load(fh)
+        assert old["impl"] == a.impl
+        for k in old["inputs"]:
+            if k in m_in:
+                assert old["inputs"][k] == m_in[k] and old["outputs"][k] == m_out[k], "re-pinned tint %s differs" % k
+        m_in = dict(old["inputs"], **m_in)
+        m_out = dict(old["outputs"], **m_out)
+        n_reads = dict(old["n_reads"], **n_reads)
+        runs = old.get("runs", [dict(tints=old["tints_pinned"], reads=old["describe"]["reads"], threads=old["threads"],
+                                     seconds=old["seconds"])]) + runs
+        desc = dict(tints=len(m_in), reads=sum(n_reads.values()))
+    # reads/s of the reference over every pinning run (wall clock, threads as recorded per run)
+    rps = round(sum(r["reads"] for r in runs) / max(sum(r["seconds"] for r in runs), 1e-9), 1)
+    man = dict(config=name, source_cfg=a.cfg, impl=a.impl, tints_pinned=len(m_in), describe=desc, threads=a.threads,
+               seconds=round(sum(r["seconds"] for r in runs), 1), reads_per_sec=rps, runs=runs,
+               input_digest=digest(m_in), output_digest=digest(m_out), n_reads=n_reads, inputs=m_in, outputs=m_out)
     with open(os.path.join(gold, name + ".json"), "w") as fh:
         json.dump(man, fh, sort_keys=True, separators=(",", ":"))
     print("%s: %s took %.0fs (%.0f reads/s on %d threads); output digest %s" % (
