@@ -243,7 +243,7 @@ def run_reference_arm(args):
             runner.close()
         v = runner.reads / float(np.mean(secs))
         kind = "reference"
-        sample = ("unmodified freddie_segment.py (oracle/_ref/freddie_segment.pyc, byte-compiled from the reference "
+        sample = ("unmodified freddie_segment.py (oracle/_ref/freddie_segment.bin, byte-compiled from the reference "
                   "source) -t %d, files to files in tmpfs, on a size-stratified sample of the workload, the same "
                   "sample every step: %d tints, %d reads, %.2f s per run" % (cores, runner.tints, runner.reads, float(np.mean(secs))))
         cells = None

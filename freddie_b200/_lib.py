@@ -16,7 +16,7 @@ FRS_MAX_STAGES = 32
 
 # taps (frs_get_intermediate)
 TAP_Y_RAW, TAP_Y, TAP_THR, TAP_CAND, TAP_FIXED, TAP_DP_FINAL, TAP_SUB_START, TAP_SUB_N = 1, 2, 3, 4, 5, 6, 7, 8
-TAP_COVERAGE, TAP_DP_TABLES, TAP_COV_OFF, TAP_SUB_TAB_OFF = 9, 10, 12, 13
+TAP_COVERAGE, TAP_DP_TABLES, TAP_COV_OFF, TAP_SUB_TAB_OFF, TAP_FINAL_FLAGS = 9, 10, 12, 13, 14
 OPT_SLAB_WORDS, OPT_KEEP_DP_TABLES, OPT_POLY_LONG_CLASS, OPT_LAZY_SEQ = 1, 2, 3, 4
 STAT_NAMES = ["h2d_upload", "h2d_run", "d2h_run", "clip_words", "seq_words", "poly_tasks", "poly_long_tasks"]
 

@@ -1018,6 +1018,7 @@ int frs_get_intermediate(frs_context* c, int which, void* dst, size_t cap, size_
     case FRS_TAP_DP_TABLES: src = c->b_tab.p; sz = c->tab_elems * 4; break;
     case FRS_TAP_COV_OFF: src = c->b_tint_cov_off.p; sz = (size_t)(c->hb.n_tints + 1) * 8; break;
     case FRS_TAP_SUB_TAB_OFF: src = c->b_sub_tab_off.p; sz = NS * 8; break;
+    case FRS_TAP_FINAL_FLAGS: src = c->b_sflag.p; sz = L; break;
     default: return fail(c, FRS_ERR_ARG, "frs_get_intermediate: unknown tap %d", which);
   }
   *bytes = sz;

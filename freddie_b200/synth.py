@@ -451,6 +451,32 @@ def iter_config(cfg: int, scale: float = 1.0, seed: Optional[int] = None, worker
             pool.join()
 
 
+def _write_job(arg):
+    job, split_dir = arg
+    t = _tint_job(job)
+    write_split_dir([t], split_dir)
+    return t["chr"], t["id"], len(t["reads"])
+
+
+def write_jobs(jobs: Sequence[tuple], split_dir: str, workers: int = 1) -> List[Tuple[str, int, int]]:
+    """Generates the tints of ``jobs`` (``config_jobs`` entries) and writes their SPLIT files from the worker
+    processes (largest first), so that neither the generation nor the text formatting of a giant tint
+    serialises the others.  Returns ``(contig, tint id, reads)`` per job, in job order."""
+    order = sorted(range(len(jobs)), key=lambda k: -jobs[k][3])
+    args = [(jobs[k], split_dir) for k in order]
+    os.makedirs(split_dir, exist_ok=True)
+    if workers > 1 and len(jobs) > 1:
+        from multiprocessing import Pool
+        with Pool(workers) as p:
+            res = p.map(_write_job, args, chunksize=1)
+    else:
+        res = [_write_job(a) for a in args]
+    out = [None] * len(jobs)
+    for k, r in zip(order, res):
+        out[k] = r
+    return out
+
+
 def make_config(cfg: int, scale: float = 1.0, seed: Optional[int] = None, workers: int = 1) -> List[dict]:
     """Realise a config as a list of tints (seeded, deterministic, independent of ``workers``)."""
     plan = config_plan(cfg, scale, seed)
@@ -532,6 +558,26 @@ def make_plateau_tint(contig: str = "chrP", tint_id: int = 0) -> dict:
     return dict(id=tint_id, chr=contig, intervals=merge_islands(reads), read_count=len(reads), reads=reads)
 
 
+def make_refine_tie_tint(contig: str = "chrR", tint_id: int = 0) -> dict:
+    """Equal-height refine peaks closer than find_peaks' distance of 20 (refine_segmentation,
+    freddie_segment.py:249-266): three groups of 30 identical reads put splice sites of equal
+    weight 12 apart -- a pair, a triple and a quadruple.  With ``-vf 9.9 -lo 100000`` nothing is fixed and
+    the DP keeps no interior candidate, so the whole island is one segment and refine decides alone; which
+    of the bit-equal peaks survive depends on the visiting order among equal priorities."""
+    reads = []
+    rid = 0
+    groups = [
+        [(1000, 1400), (1412, 2400)],                              # pair: 1400 | 1412
+        [(1000, 1700), (1712, 1724), (2024, 2400)],                # triple: 1700 | 1712 | 1724  (+ 2024 alone)
+        [(1000, 1100), (1112, 1124), (1136, 2400)],                # quadruple: 1100 | 1112 | 1124 | 1136
+    ]
+    for ivs in groups:
+        for _ in range(30):
+            reads.append(_simple_read(rid, contig, tint_id, "+" if rid % 2 else "-", ivs, 3, 5, "ACGT"[rid % 4]))
+            rid += 1
+    return dict(id=tint_id, chr=contig, intervals=merge_islands(reads), read_count=len(reads), reads=reads)
+
+
 GOLDEN_SETS = {
     # name: (builder kwargs, CLI flags)
     "cfg1": (dict(cfg=1), []),
@@ -547,6 +593,7 @@ GOLDEN_SETS = {
     "dup_heavy": (dict(special="dup_heavy"), []),
     "degenerate": (dict(special="degenerate"), []),
     "plateau": (dict(special="plateau"), []),
+    "refine_tie": (dict(special="refine_tie"), ["-vf", "9.9", "-lo", "100000"]),
 }
 
 
@@ -562,4 +609,6 @@ def make_golden_set(name: str) -> Tuple[List[dict], List[str]]:
                           opts=dict(dup_p=0.97, noise_p=0.3))], flags
     if kw.get("special") == "plateau":
         return [make_plateau_tint()], flags
+    if kw.get("special") == "refine_tie":
+        return [make_refine_tie_tint()], flags
     return make_config(**kw), flags

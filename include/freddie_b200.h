@@ -167,6 +167,8 @@ enum {
   FRS_TAP_COV_OFF = 12,   /* int64 [n_tints+1] element offset of each tint's coverage block */
   FRS_TAP_SUB_TAB_OFF = 13, /* int64 [n_subproblems] first element of each subproblem's table block (the
                                subproblem list and the blocks are in no particular order) */
+  FRS_TAP_FINAL_FLAGS = 14, /* u8 [n_samples] 1 at every final position after refine_segmentation (:249-266,
+                               :803-805): the DP-final candidates plus the positions refine added */
 };
 /* Copies min(cap_bytes, size) bytes of the tap to dst (host) and stores the full size in *bytes. */
 int frs_get_intermediate(frs_context* ctx, int which, void* dst, size_t cap_bytes, size_t* bytes);

@@ -5,11 +5,12 @@ TEST / MEASUREMENT INFRASTRUCTURE -- never imported by the product (``freddie_b2
 
 The reference is a Python script (``/root/reference/py/freddie_segment.py``; it needs only numpy and
 scipy, both in the image).  ``/root/reference`` exists in the authoring container only, so ``build()``
-byte-compiles the script *where it lies* into ``oracle/_ref/freddie_segment.pyc`` -- a git-ignored
+byte-compiles the script *where it lies* into ``oracle/_ref/freddie_segment.bin`` (a ``.pyc`` image under a
+name the snapshot keeps) -- a git-ignored
 build output that travels to the GPU box with the snapshot like the built ``.so`` -- and records the
 SHA-256 of the source it was compiled from.  No reference source is copied into the repository.
 
-``python oracle/_ref/freddie_segment.pyc -s SPLIT -o OUT -t N`` then runs the reference CLI exactly as
+``python oracle/_ref/freddie_segment.bin -s SPLIT -o OUT -t N`` then runs the reference CLI exactly as
 ``python /root/reference/py/freddie_segment.py`` does (same argv, same multiprocessing pool); it is what
 ``bench.py --impl reference`` and ``bench.py``'s ``cpu_baseline`` time on the GPU box's host cores, and
 what ``tests/`` may use as a second checker beside the oracle port.
@@ -23,7 +24,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = "/root/reference/py/freddie_segment.py"
 REF_DIR = os.path.join(HERE, "_ref")
-REF_PYC = os.path.join(REF_DIR, "freddie_segment.pyc")
+REF_PYC = os.path.join(REF_DIR, "freddie_segment.bin")  # CPython bytecode (runs by its magic number; *.pyc does not travel)
 REF_META = os.path.join(REF_DIR, "MANIFEST.json")
 
 
@@ -38,7 +39,7 @@ def build_ref(quiet: bool = True) -> bool:
             sha = hashlib.sha256(fh.read()).hexdigest()
         with open(REF_META, "w") as fh:
             json.dump(dict(source=REF_SRC, sha256=sha, python="%d.%d.%d" % sys.version_info[:3],
-                           artefact="freddie_segment.pyc (py_compile of the unmodified source, optimize=0)"), fh)
+                           artefact="freddie_segment.bin (py_compile of the unmodified source, optimize=0)"), fh)
         if not quiet:
             print("oracle/_ref: compiled %s (sha256 %s)" % (REF_SRC, sha[:16]))
     return available()

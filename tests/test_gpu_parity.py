@@ -15,7 +15,7 @@ from oracle import segment_oracle as orc
 pytestmark = pytest.mark.gpu
 
 ALL_SETS = ["degenerate", "plateau", "cfg1", "cfg2_small", "cfg2_flagsA", "cfg2_flagsB", "cfg2_sigma50",
-            "cfg2_mps11", "dup_heavy", "cfg3_mini", "cfg4_mini", "cfg5_mini"]
+            "cfg2_mps11", "dup_heavy", "cfg3_mini", "cfg4_mini", "cfg5_mini", "refine_tie"]
 
 
 @pytest.fixture(scope="module")
@@ -48,7 +48,7 @@ def test_segment_text_equals_oracle(name, golden_set, eng):
 
 
 @pytest.mark.parametrize("name", ["degenerate", "plateau", "cfg2_small", "cfg2_flagsA", "cfg2_flagsB", "cfg4_mini",
-                                  "dup_heavy", "cfg2_sigma50", "cfg2_mps11"])
+                                  "dup_heavy", "cfg2_sigma50", "cfg2_mps11", "refine_tie"])
 def test_cli_directory_equals_reference_manifest(name, golden_set, manifest, tmp_path):
     """The drop-in CLI (native parser + kernels + native formatter) against the SHA-256 manifest of the
     SEGMENT directory the unmodified reference wrote for the same SPLIT directory."""
@@ -84,12 +84,51 @@ def test_cfg1_taps_equal_reference_intermediates(golden_set, eng):
                             for a in range(len(off) - 1)])
     assert np.array_equal(fixed, wantf)
     assert res.arrays["final_pos"].tolist() == z["final_positions"].tolist()
-    # coverage: column sums of the last row of each island block reproduce the reference's C.sum() check
+    # coverage (get_cumulative_coverage, :188-246): P holds one row per candidate of the tint in flat
+    # coordinates, so inside an island  P[c0 + c] - P[c0]  must be the reference's C[c]; the checksum of the
+    # reference's own (K+1) x R matrix is reproduced from those rows plus the island's total row
     P = eng.tap(_lib.TAP_COVERAGE, np.uint32)
     R = batch.n_reps
     Rp = (R + 3) & ~3
     P = P.reshape(-1, Rp)
     assert P.shape[0] == len(cand)
+    assert not P[:, R:].any()  # padding columns
+    ot = copy.deepcopy(tints[0])
+    keys, _ = orc.build_reps(ot)
+    for a, isl in enumerate(ot["intervals"]):
+        c0, c1 = int(z["cand_off"][a]), int(z["cand_off"][a + 1])
+        rep_iv = [[(ts - isl[0], te - isl[0]) for ts, te in k if isl[0] <= ts <= isl[1]] for k in keys]
+        C = orc.coverage_matrix(rep_iv, z["cand"][c0:c1].tolist())
+        rows = (P[c0:c1, :R].astype(np.int64) - P[c0, :R].astype(np.int64))
+        assert np.array_equal(rows, C[:-1].astype(np.int64)), "coverage rows of island %d" % a
+        assert int(rows.sum() + C[-1].astype(np.uint64).sum()) == int(z["csum"][a]), "C.sum() of island %d" % a
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2_small", "cfg3_mini", "refine_tie", "dup_heavy"])
+def test_refine_tap_equals_oracle(name, golden_set, eng):
+    """refine_segmentation (:249-266): the positions refine ADDS to the DP-final breakpoints of every
+    island (tap: final flags per sample minus the DP-final candidates) against the oracle's list."""
+    from freddie_b200 import _lib
+    from freddie_b200.pack import pack_tints
+    tints, flags, _ = golden_set(name)
+    oprm, gprm = _params(flags)
+    n_extra = 0
+    for tint in tints[:6]:
+        batch = pack_tints([tint])
+        eng.segment_batch(batch, gprm)
+        flags_final = eng.tap(_lib.TAP_FINAL_FLAGS, np.uint8)
+        cand = eng.tap(_lib.TAP_CAND, np.int32)
+        dpf = eng.tap(_lib.TAP_DP_FINAL, np.uint8)
+        added = sorted(set(np.flatnonzero(flags_final).tolist()) - set(cand[dpf != 0].tolist()))
+        it = orc.segment_tint(copy.deepcopy(tint), oprm, keep=True)
+        off = np.cumsum([0] + [e - s + 1 for s, e in tint["intervals"]])
+        want = sorted(int(off[a]) + p for a, ex in enumerate(it["refine"]) for p in ex)
+        assert added == want
+        dp_want = sorted(int(off[a]) + it["cand"][a][c] for a, ch in enumerate(it["dp_final"]) for c in ch)
+        assert sorted(cand[dpf != 0].tolist()) == dp_want
+        n_extra += len(want)
+    if name in ("cfg1", "refine_tie"):
+        assert n_extra > 0  # the set does exercise refine
 
 
 def _check_dp_tables(eng, tint, oprm, limit=12):

@@ -8,7 +8,7 @@ import pytest
 from conftest import GOLDEN, digest, flags_to_kwargs, sha_dir
 from oracle import segment_oracle as orc
 
-FAST_SETS = ["degenerate", "plateau", "cfg2_flagsA", "cfg2_small", "cfg4_mini", "cfg5_mini"]
+FAST_SETS = ["degenerate", "plateau", "cfg2_flagsA", "cfg2_small", "cfg4_mini", "cfg5_mini", "refine_tie"]
 
 
 @pytest.mark.parametrize("name", FAST_SETS)
@@ -45,6 +45,33 @@ def test_cfg1_intermediates_bit_identical(golden_set):
     assert np.array_equal(np.concatenate(it["fixed"]), z["fixed"])
     assert t["final_positions"] == z["final_positions"].tolist()
     assert not it["ties"] or True  # ties are reported, not an error
+
+
+@pytest.mark.parametrize("name,n_ties", [("cfg1", 26), ("cfg2_small", 23), ("cfg4_mini", 11), ("cfg5_mini", 55),
+                                         ("cfg2_mps11", 3), ("dup_heavy", 0), ("plateau", 0)])
+def test_equal_height_refine_ties_are_pinned_by_the_golden_sets(name, n_ties, golden_set):
+    """Equal-height refine peaks closer than 20 inherit np.argsort's order among equal priorities in the
+    reference.  Integer-valued raw signals make such ties common: the golden sets hold
+    dozens of them, and their SEGMENT digests (unmodified reference, test_oracle_reproduces_reference_outputs
+    and the GPU CLI test) therefore pin the rule the oracle and the kernel implement -- a stable ascending
+    argsort, i.e. of two interacting equals the LATER peak is visited first and survives."""
+    import copy
+    tints, flags, _ = golden_set(name)
+    prm = orc.Params(**flags_to_kwargs(flags))
+    n = sum(len(orc.segment_tint(copy.deepcopy(t), prm, keep=True)["ties"]) for t in tints)
+    assert n == n_ties
+
+
+def test_refine_tie_set_pins_the_tie_rule(golden_set):
+    """The constructed ``refine_tie`` set isolates the rule: a pair, a triple and a quadruple of bit-equal
+    peaks 12 apart.  The unmodified reference (run in the authoring container, digest in the manifest and
+    checked by test_oracle_reproduces_reference_outputs) keeps the LATER peak of two interacting equals:
+    quadruple -> 2nd and 4th, pair -> 2nd, triple -> 1st and 3rd."""
+    tints, flags, _ = golden_set("refine_tie")
+    it = orc.segment_tint(tints[0], orc.Params(**flags_to_kwargs(flags)), keep=True)
+    assert it["ties"] == [(100, 112), (112, 124), (124, 136), (400, 412), (700, 712), (712, 724)]
+    assert it["refine"] == [[112, 136, 412, 700, 724, 1024]]
+    assert it["dp_final"] == [[0, 11]]  # nothing fixed, no interior candidate kept: refine decides alone
 
 
 def test_oracle_output_passes_the_consumers_grammar(golden_set, tmp_path):
