@@ -37,8 +37,13 @@ UNIT = "reads/s"
 KERNEL_OF = {"signal": "k_signal", "smooth": "k_smooth", "lists": "k_tile_lists", "coverage": "k_coverage",
              "refine": "k_refine_filter+k_refine", "digits": "k_digits", "gaps": "k_gap_prep+k_gap_sizes", "dp": "k_dp*"}
 WORKLOADS = {
-    "cfg2": "BASELINE configs[1]: synthetic chromosome-scale SPLIT, 200k reads across ~3k tints (seeded, per GPU)",
-    "cfg3": "BASELINE configs[2]: DP-dominated giant tints (scaled by --scale), per GPU",
+    "cfg2": "BASELINE configs[1]: synthetic chromosome-scale SPLIT, 200k reads across ~3k tints per GPU (one seeded "
+            "dataset of N x that size, its tints bin-packed over the N GPUs by estimated cost)",
+    "cfg3": "BASELINE configs[2]: DP-dominated giant tints, 20 x 100k reads (x --scale), per GPU",
+    "cfg4": "BASELINE configs[3]: power-law tint sizes 1..200k reads, ~2.2 M reads (x --scale): ONE dataset bin-packed "
+            "over the GPUs by estimated cost",
+    "cfg5": "BASELINE configs[4]: whole-transcriptome scale, 10 M reads across ~60k tints (x --scale): ONE dataset "
+            "bin-packed over the GPUs by estimated cost",
 }
 
 
@@ -49,7 +54,7 @@ def rank_env():
 
 def make_workload(workload: str, scale: float, seed: int, workers: int):
     from freddie_b200 import synth
-    cfg = {"cfg2": 2, "cfg3": 3}[workload]
+    cfg = {"cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 5}[workload]
     return synth.make_config(cfg, scale=scale, seed=seed, workers=workers)
 
 
@@ -274,30 +279,64 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def make_shard(args, rank, world, workers):
+    """The tints of THIS rank.  cfg2 (weak scaling): ONE dataset of world x 200 k reads / world x 3 k tints,
+    its tints bin-packed over the GPUs by estimated cost (schedule.lpt_partition, longest first), every rank
+    generates only its own shard.  cfg4 / cfg5 (strong scaling): one dataset of the named size, sharded the
+    same way.  cfg3: every rank its own realisation (20 equal giant tints do not need packing).
+    Returns (list of tint lists = the rank's batches, info)."""
+    from freddie_b200 import schedule, synth
+    cfg = {"cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 5}[args.workload]
+    if args.workload == "cfg3":
+        tints = synth.make_config(3, scale=args.scale, seed=3 + 1000 * rank, workers=workers)
+        return [[t] for t in tints] if args.scale >= 0.5 else [tints], dict(sharding="replicas (own seed per rank)")
+    scale = args.scale * (world if args.workload == "cfg2" else 1)
+    jobs = synth.config_jobs(cfg, scale=scale)
+    costs = [(schedule.estimate_cost(j[3]), float(j[3])) for j in jobs]
+    shards = schedule.lpt_partition(costs, world)
+    mine = sorted(shards[rank])
+    loads = [sum(costs[i][0] for i in sh) for sh in shards]
+    info = dict(sharding="one dataset, LPT bin-packing by estimated cost (freddie_b200.schedule)",
+                dataset_tints=len(jobs), dataset_reads=int(sum(j[3] for j in jobs)),
+                est_cost_imbalance=round(max(loads) / (sum(loads) / len(loads)), 4))
+    my_jobs = [jobs[i] for i in mine]
+    if args.workload == "cfg2":
+        return [synth.run_jobs(my_jobs, workers)], info
+    groups = list(schedule.batches(my_jobs, [costs[i] for i in mine], args.batch_reads))
+    return groups, info  # job lists: generated and packed group by group (a whole config does not fit in dicts)
+
+
 def run_cuda_arm(args):
     rank, local_rank, world = rank_env()
     cores = os.cpu_count() or 1
-    # torchrun pins OMP_NUM_THREADS=1 in its children; the library's host gather (clip words) and the
-    # native parser use OpenMP, so give every rank its share of the cores
+    # torchrun pins OMP_NUM_THREADS=1 in its children; the native parser uses OpenMP
     os.environ["OMP_NUM_THREADS"] = str(max(1, cores // max(world, 1)))
-    # keep stdout to the ONE JSON line: NCCL prints its version banner there at NCCL_DEBUG >= VERSION
-    if "FRS_NCCL_DEBUG" in os.environ:
-        os.environ["NCCL_DEBUG"] = os.environ["FRS_NCCL_DEBUG"]
-    else:
-        os.environ.pop("NCCL_DEBUG", None)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # the version banner goes to stdout at VERSION / INFO: keep stdout to ONE line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("INFO", "VERSION", "TRACE"):
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
+    from freddie_b200 import _lib, synth
     from freddie_b200.engine import Engine, SegmentParams
     from freddie_b200.pack import pack_tints
 
     t0 = time.time()
-    tints = make_workload(args.workload, args.scale, 2 + 1000 * rank, max(1, min(16, cores // world)))
-    batch = pack_tints(tints).pin()
+    workers = max(1, min(32, cores // world))
+    groups, shard_info = make_shard(args, rank, world, workers)
+    tints_for_cpu = groups[0] if args.workload == "cfg2" else None
+    batches = []
+    for g in groups:
+        tl = g if (g and isinstance(g[0], dict)) else synth.run_jobs(g, workers)
+        batches.append(pack_tints(tl).pin())
+        if tints_for_cpu is None:
+            batches[-1].tints = []  # keep the arrays only
+    del groups
     t_gen = time.time() - t0
-    n_reads = batch.n_reads
+    n_reads = sum(b.n_reads for b in batches)
+    n_tints = sum(b.n_tints for b in batches)
     prm = SegmentParams()
     eng = Engine(local_rank)
     stream = torch.cuda.ExternalStream(eng.lib.frs_stream(eng.ctx), device=torch.device("cuda", local_rank))
@@ -314,89 +353,127 @@ def run_cuda_arm(args):
             flush.zero_()
 
     # ---- warm-up: full end-to-end steps (also sizes every device buffer) ----
-    from freddie_b200 import _lib
     eng.set_option(_lib.OPT_LAZY_SEQ, 0)  # `value`: every input, sequence planes included, resident in HBM
-    res = None
-    for _ in range(max(args.warmup, 1)):
-        res = eng.segment_batch(batch, prm, pinned=True)
-    sizes = res.sizes
+    res_resident, sizes = [], []
+    for w in range(max(args.warmup, 1)):
+        res_resident, sizes = [], []
+        for b in batches:
+            res_resident.append(eng.segment_batch(b, prm, pinned=True))
+            sizes.append(dict(res_resident[-1].sizes, cov_elems=int(eng.tap(_lib.TAP_COV_OFF, np.int64)[-1])))
 
-    # ---- timed: K x frs_run on the resident batch ----
-    eng.upload(batch)
+    # ---- timed: K x frs_run per batch with the batch resident in HBM (upload outside the events) ----
     eng.set_profiling(True)
     sampler = ClockSampler(local_rank)
     stage_ms, stage_launch = {}, {}
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in batches]
+          for _ in range(args.steps)]
+    if len(batches) == 1:
+        eng.upload(batches[0])
     barrier()
     sampler.start()
     launches = 0
     for k in range(args.steps):
-        flush_l2()
-        ev[k][0].record(stream)
-        eng.run(prm)
-        ev[k][1].record(stream)
-        launches += eng.launch_count()
-        for name, ms, ln in eng.timings():
-            stage_ms[name] = stage_ms.get(name, 0.0) + ms
-            stage_launch[name] = ln
+        for i, b in enumerate(batches):
+            if len(batches) > 1:
+                eng.upload(b)
+            flush_l2()
+            ev[k][i][0].record(stream)
+            eng.run(prm)
+            ev[k][i][1].record(stream)
+            launches += eng.launch_count()
+            for name, ms, ln in eng.timings():
+                stage_ms[name] = stage_ms.get(name, 0.0) + ms
+                stage_launch[name] = stage_launch.get(name, 0) + ln
     barrier()
     clocks = sampler.stop()
-    t_dev = sum(a.elapsed_time(b) for a, b in ev) / 1e3
+    t_dev = sum(a.elapsed_time(b) for row in ev for a, b in row) / 1e3
     eng.set_profiling(False)
+    reruns_resident = eng.stats()["reruns"]
+    stage_launch = {k: v // (args.steps * len(batches)) if len(batches) == 1 else v // args.steps for k, v in stage_launch.items()}
 
-    # ---- timed: end to end through the C ABI with HOST buffers.  Every step uploads its inputs from
-    # pinned host memory, runs, and downloads the results into pinned host memory.  Several library
-    # contexts (one host thread each, up to 6: tests/e2e_probe.py shows the rate levelling off there)
-    # take alternate steps so that the copies and host round trips of one step overlap the kernels of
-    # the others, exactly as the CLI driver runs consecutive batches. ----
-    n_lanes = max(1, min(int(os.environ.get("FRS_E2E_LANES", "6")), args.steps))
-    lanes = []
-    for _ in range(n_lanes):
-        e2 = Engine(local_rank)
-        r2 = None
+    # ---- timed: end to end through the C ABI with pinned HOST buffers, ONE context, one host thread.
+    # Every step = frs_submit (host-to-device copies + every kernel, enqueued without a host round trip) +
+    # frs_wait + frs_fetch (device-to-host copies into pinned memory); two batches are in flight, so the
+    # copies of one step overlap the kernels of its neighbours on the copy engines.  `serial_value` is the
+    # same work with the synchronous calls (upload, run, download one after the other). ----
+    eng.set_option(_lib.OPT_LAZY_SEQ, 1)  # pinned planes stay on the host; the clip words are fetched by a kernel
+    n_ctx = max(1, int(os.environ.get("FRS_E2E_CONTEXTS", "2")))
+    ctxs = [eng] + [Engine(local_rank) for _ in range(n_ctx - 1)]
+    pong = []
+    for e2 in ctxs:
         for _ in range(max(args.warmup, 1)):
-            r2 = e2.segment_batch(batch, prm, pinned=True)
-        lanes.append((e2, r2))
-    st = lanes[0][0].stats()
-    h2d = st["h2d_upload"] + st["h2d_run"]
-    d2h = int(sum(v.nbytes for v in lanes[0][1].arrays.values())) + st["d2h_run"]
+            rr = [e2.segment_batch(b, prm, pinned=True) for b in batches]
+        pong.append([[e2.new_result(_sizes_obj(r), b, pinned=True) for r, b in zip(rr, batches)] for _ in range(2)])
+    res_lazy = rr
+    st = ctxs[0].stats()
+    h2d = sum(_upload_bytes(ctxs[0], b, prm) for b in batches)
+    d2h = int(sum(v.nbytes for r in res_lazy for v in r.arrays.values())) + len(batches) * 48 * 8
 
-    def lane_work(idx, steps):
-        e2, r2 = lanes[idx]
-        for _ in range(steps):
-            e2.upload(batch)
+    def pipelined(e2, bufs, work):
+        """work: list of batch indices in order; returns when everything has been fetched."""
+        prev = None
+        for n, i in enumerate(work + [None]):
+            tk = e2.submit(batches[i], prm) if i is not None else None
+            if prev is not None:
+                pt, pi, pn = prev
+                e2.wait(pt)
+                e2.fetch(pt, bufs[pn & 1][pi])
+            prev = (tk, i, n) if i is not None else None
+
+    def serial(e2, bufs, work):
+        for n, i in enumerate(work):
+            e2.upload(batches[i])
             e2.run(prm)
-            _download_into(e2, r2)
+            r = bufs[n & 1][i].as_struct()
+            e2._check(e2.lib.frs_download(e2.ctx, __import__("ctypes").byref(r)))
 
-    def timed_e2e(n_used):
-        per = [args.steps // n_used + (1 if i < args.steps % n_used else 0) for i in range(n_used)]
-        ths = [threading.Thread(target=lane_work, args=(i, per[i])) for i in range(n_used)]
+    def timed(fn, n_used):
+        work_all = [i for _ in range(args.steps) for i in range(len(batches))]
+        parts = [work_all[k::n_used] for k in range(n_used)]
+        ths = [threading.Thread(target=fn, args=(ctxs[k], pong[k], parts[k])) for k in range(n_used)]
         barrier()
         w0 = time.perf_counter()
-        for t in ths:
-            t.start()
-        for t in ths:
-            t.join()
+        if n_used == 1:
+            fn(ctxs[0], pong[0], parts[0])
+        else:
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
         torch.cuda.synchronize()
         return time.perf_counter() - w0
 
-    t_e2e_serial = timed_e2e(1)
-    t_e2e = timed_e2e(n_lanes)
+    timed(pipelined, 1)  # untimed pass: capacities of the lazy mode
+    t_serial = timed(serial, 1)
+    t_pipe1 = timed(pipelined, 1)
+    t_pipe2 = timed(pipelined, n_ctx) if n_ctx > 1 else t_pipe1
     barrier()
-    same = all(np.array_equal(lanes[0][1].arrays[k], res.arrays[k]) for k in res.arrays)
-    if not same:
-        raise RuntimeError("end-to-end (lazy sequence) results differ from the resident run")
+    for i in range(len(batches)):
+        for k in res_resident[i].arrays:
+            if not np.array_equal(pong[0][0][i].arrays[k], res_resident[i].arrays[k]) and \
+               not np.array_equal(pong[0][1][i].arrays[k], res_resident[i].arrays[k]):
+                raise RuntimeError("end-to-end (pipelined, lazy sequence) results differ from the resident run: %s" % k)
+    t_e2e = min(t_pipe1, t_pipe2)
 
-    # ---- reduce over ranks: max time, sum of units ----
-    tot_reads, tot_cells = n_reads, int(sizes["dp_cells"])
-    dp_ms = stage_ms.get("dp", 0.0) + stage_ms.get("dp_solve", 0.0)
+    # ---- reduce over ranks: max time, sum of units; per-rank busy times for the balance of the shard ----
+    tot_reads = n_reads
+    tot_cells = int(sum(s["dp_cells"] for s in sizes))
+    tot_rcells = int(sum(s["dp_read_cells"] for s in sizes))
+    dp_ms = stage_ms.get("dp", 0.0)
+    busy = [t_dev / args.steps]
+    busy_e2e = [t_e2e / args.steps]
+    reads_per_rank = [n_reads]
     if world > 1:
-        t = torch.tensor([t_dev, t_e2e, dp_ms, t_e2e_serial], device="cuda", dtype=torch.float64)
+        g = torch.zeros(world, 3, device="cuda", dtype=torch.float64)
+        g[rank, 0], g[rank, 1], g[rank, 2] = t_dev / args.steps, t_e2e / args.steps, n_reads
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        busy, busy_e2e, reads_per_rank = g[:, 0].tolist(), g[:, 1].tolist(), [int(x) for x in g[:, 2].tolist()]
+        t = torch.tensor([t_dev, t_e2e, dp_ms, t_serial, t_pipe1, t_pipe2], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_dev, t_e2e, dp_ms, t_e2e_serial = [float(x) for x in t.tolist()]
-        u = torch.tensor([n_reads, tot_cells, launches, h2d, d2h], device="cuda", dtype=torch.int64)
+        t_dev, t_e2e, dp_ms, t_serial, t_pipe1, t_pipe2 = [float(x) for x in t.tolist()]
+        u = torch.tensor([n_reads, tot_cells, launches, h2d, d2h, tot_rcells, n_tints], device="cuda", dtype=torch.int64)
         dist.all_reduce(u, op=dist.ReduceOp.SUM)
-        tot_reads, tot_cells, launches, h2d, d2h = [int(x) for x in u.tolist()]  # whole-job totals
+        tot_reads, tot_cells, launches, h2d, d2h, tot_rcells, n_tints = [int(x) for x in u.tolist()]  # whole-job totals
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -404,42 +481,58 @@ def run_cuda_arm(args):
 
     value = tot_reads * args.steps / t_dev
     e2e_v = tot_reads * args.steps / t_e2e
-    counts = batch.counts()
-    cov_elems = int(eng.tap(12, np.int64)[-1])  # FRS_TAP_COV_OFF: last entry = total coverage elements
-    alg = algorithmic_bytes(counts, sizes, cov_elems)
     peak, peak_src = peaks()
+    alg = {}
+    for b, sz, r in zip(batches, sizes, res_resident):
+        cov = int(sz.get("cov_elems", 0))
+        for k, v in algorithmic_bytes(b.counts(), sz, cov).items():
+            alg[k] = alg.get(k, 0) + v
     # dominant KERNEL of the step = the longest single launch.  Stages that are one launch on the context
-    # stream are timed exactly by their CUDA events; the DP stage is six kernels running concurrently on
-    # side streams (the longest of them is shorter than k_smooth, see profiles/*_launches.txt) and is
-    # issue-bound, not HBM-bound: it is reported in `dp_stage` instead.
-    single = [k for k in stage_ms if k in alg and stage_launch.get(k) == 1]
+    # stream are timed exactly by their CUDA events; the DP stage is several persistent kernels running
+    # concurrently on side streams and is issue-bound, not HBM-bound: it is reported in `dp_stage`.
+    per_step = lambda k: stage_ms[k] / args.steps  # noqa: E731
+    single = [k for k in stage_ms if k in alg and stage_launch.get(k) == len(batches)]
     dom = max(single or [k for k in stage_ms if k in alg], key=lambda k: stage_ms[k])
-    dom_ms = stage_ms[dom] / args.steps
+    dom_ms = per_step(dom)
     ach = alg[dom] / (dom_ms * 1e-3) / 1e9
-    stages = {k: dict(ms=round(v / args.steps, 4), launches=stage_launch[k],
-                      alg_GBps=(round(alg[k] / (v / args.steps * 1e-3) / 1e9, 1) if k in alg and v > 0 else None),
-                      hbm_frac=(round(alg[k] / (v / args.steps * 1e-3) / 1e9 / peak, 4) if k in alg and v > 0 else None))
+    stages = {k: dict(ms=round(per_step(k), 4), launches=stage_launch[k],
+                      alg_GBps=(round(alg[k] / (per_step(k) * 1e-3) / 1e9, 1) if k in alg and v > 0 else None),
+                      hbm_frac=(round(alg[k] / (per_step(k) * 1e-3) / 1e9 / peak, 4) if k in alg and v > 0 else None))
               for k, v in stage_ms.items()}
-    stream_ms = sum(v for k, v in stage_ms.items() if k in alg and k != "dp") / args.steps
-    stream_bytes = sum(b for k, b in alg.items() if k != "dp" and k in stage_ms)
+    stream_ms = sum(per_step(k) for k in stage_ms if k in alg and k != "dp")
+    stream_bytes = sum(bb for k, bb in alg.items() if k != "dp" and k in stage_ms)
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp) and args.workload == "cfg2" and args.scale == 1.0:
         traffic = json.load(open(tp)).get(dom)
+    # DP: read-cell updates against the POPC-limited ceiling: one POPC covers the predicate
+    # lanes of 32 read reps; 16 POPC / clk / SM (the quarter-rate integer pipe of sm_100, B300_MICROARCH.md)
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    popc_ceiling = 16.0 * 32.0 * 148.0 * sm_mhz * 1e6 * world
+    rcu = tot_rcells * args.steps / max(dp_ms * 1e-3, 1e-12)
+    mean = lambda xs: sum(xs) / len(xs)  # noqa: E731
+    cfg = config_dict(args)
     line = dict(
         metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-        ms_per_step=t_dev / args.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
-        dtype="int32+f64", data="synthetic",
-        config=dict(workload=WORKLOADS[args.workload], scale=args.scale, reads_per_gpu=n_reads, tints_per_gpu=len(tints),
-                    l2="flushed between timed steps (256 MiB memset)", params="defaults (sd=5 tp=0.9 vf=3 mps=50 lo=3)"),
+        ms_per_step=t_dev / args.steps * 1e3, higher_is_better=True,
+        scaling="weak" if args.workload in ("cfg2", "cfg3") else "strong", vs_baseline=None,
+        dtype="int32+f64", data="synthetic", config=cfg,
+        workload_detail=dict(reads=tot_reads, tints=n_tints, batches_per_gpu=len(batches), reads_per_gpu=reads_per_rank,
+                             **shard_info),
+        balance=dict(device_ms_per_gpu=[round(x * 1e3, 4) for x in busy], device_max_over_mean=round(max(busy) / mean(busy), 4),
+                     e2e_ms_per_gpu=[round(x * 1e3, 4) for x in busy_e2e], e2e_max_over_mean=round(max(busy_e2e) / mean(busy_e2e), 4)),
         e2e=dict(value=e2e_v, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                 timing="wall clock around K steps, synchronize on both sides; %d contexts take alternate steps" % n_lanes,
-                 serial_value=tot_reads * args.steps / t_e2e_serial,
-                 clip_words_per_step=st["clip_words"], seq_words_in_batch=st["seq_words"]),
+                 timing="wall clock around K steps, synchronize on both sides; frs_submit / frs_wait / frs_fetch with pinned "
+                        "host buffers, two batches in flight per context",
+                 one_context_value=tot_reads * args.steps / t_pipe1,
+                 contexts_value=tot_reads * args.steps / t_pipe2, contexts=n_ctx,
+                 serial_value=tot_reads * args.steps / t_serial,
+                 clip_words_per_step=st["clip_words"], seq_words_in_batch=st["seq_words"],
+                 reruns=sum(e2.stats()["reruns"] for e2 in ctxs)),
         gpu_launches=launches,
         clocks=clocks,
         roofline=dict(bound="hbm", kernel=KERNEL_OF.get(dom, dom), stage=dom, achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic,
-                      peak_source=peak_src, alg_bytes_per_launch=alg[dom], ms_per_launch=dom_ms,
+                      peak_source=peak_src, alg_bytes_per_launch=alg[dom] / len(batches), ms_per_launch=dom_ms / len(batches),
                       note="longest single launch of the step, timed by its own CUDA events; the concurrent DP kernels "
                            "are issue-bound and reported in dp_stage",
                       streaming_stages=dict(achieved=round(stream_bytes / (stream_ms * 1e-3) / 1e9, 1),
@@ -449,24 +542,52 @@ def run_cuda_arm(args):
         dp_stage=dict(bound="issue (VOTE/LOP3/POPC), not HBM: coverage rows are read once (TMA) and reused on chip",
                       ms=round(dp_ms / args.steps, 4), launches=stage_launch.get("dp"),
                       alg_GBps=round(alg["dp"] / (dp_ms / args.steps * 1e-3) / 1e9, 1) if dp_ms > 0 else None,
+                      rcu_per_sec=rcu, ceiling=popc_ceiling, frac=rcu / popc_ceiling,
+                      ceiling_how="16 POPC/clk/SM x 32 read reps per word x 148 SMs x %.0f MHz (median SM clock under load) x %d GPUs" % (sm_mhz, world),
                       evidence="profiles/: issue-slot utilisation and stall breakdown of every DP kernel"),
         dp_cells_per_sec=tot_cells * args.steps / max(dp_ms * 1e-3, 1e-12),
-        dp_read_cells_per_sec=int(sizes["dp_read_cells"]) * args.steps * world / max(dp_ms * 1e-3, 1e-12),
-        dp=dict(cells=int(sizes["dp_cells"]), subproblems=int(sizes["n_subproblems"]),
-                max_n=int(sizes["max_subproblem"]), candidates=int(sizes["n_candidates"])),
+        dp_read_cells_per_sec=rcu,
+        dp=dict(cells=tot_cells, subproblems=int(sum(s["n_subproblems"] for s in sizes)),
+                max_n=int(max(s["max_subproblem"] for s in sizes)), candidates=int(sum(s["n_candidates"] for s in sizes))),
         stages=stages,
         setup_seconds=round(t_gen, 1),
     )
-    if world == 1 and not args.no_cli:
-        line["cli"] = cli_scope(tints, cores)
-    if world == 1 and not args.no_cpu_baseline:
-        r, c, sample = oracle_rate(tints, cores, int(os.environ.get("FRS_CPU_SAMPLE_READS", 300 * cores * 15)))
-        line["cpu_baseline"] = dict(value=r, unit=UNIT, cores=cores, kind="port", dp_cells_per_sec=c,
-                                    sample="oracle/segment_oracle.py over a size-stratified sample of the same "
-                                           "workload: %s" % sample)
+    if world == 1 and not args.no_cli and tints_for_cpu is not None:
+        line["cli"] = cli_scope(tints_for_cpu, cores)
+    if world == 1 and not args.no_cpu_baseline and tints_for_cpu is not None:
+        from oracle import build_ref
+        r, c, sample = oracle_rate(tints_for_cpu, cores, int(os.environ.get("FRS_CPU_SAMPLE_READS", 300 * cores * 8)))
+        port = dict(value=r, unit=UNIT, cores=cores, kind="port", dp_cells_per_sec=c,
+                    sample="oracle/segment_oracle.py over a size-stratified sample of the same workload: %s" % sample)
+        if build_ref.available():
+            rr_, smp = reference_rate(tints_for_cpu, cores, float(os.environ.get("FRS_CPU_SECONDS", "15")))
+            line["cpu_baseline"] = dict(value=rr_, unit=UNIT, cores=cores, kind="reference",
+                                        sample="unmodified freddie_segment.py (oracle/_ref) -t %d, files to files in tmpfs, "
+                                               "size-stratified sample of the same workload: %s" % (cores, smp))
+            line["cpu_baseline_port"] = port
+        else:
+            line["cpu_baseline"] = port
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _sizes_obj(res):
+    """BatchResult.sizes (dict) -> an object with the attributes BatchResult's constructor reads."""
+    from freddie_b200 import _lib
+    s = _lib.FrsResultSizes()
+    for k, v in res.sizes.items():
+        setattr(s, k, v)
+    return s
+
+
+def _upload_bytes(eng, batch, prm):
+    """Bytes one step moves host -> device: the copies of frs_upload plus the plane words the clip-fetch kernel
+    reads from pinned host memory (lazy sequence mode)."""
+    st = eng.stats()
+    eng.segment_batch(batch, prm)
+    st = eng.stats()
+    return st["h2d_upload"] + st["h2d_run"]
 
 
 def cli_scope(tints, cores):
@@ -541,6 +662,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--batch-reads", type=int, default=131072, help="reads per GPU batch (cfg4 / cfg5 shards)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cli", action="store_true", help="skip the files-to-files scope")
     ap.add_argument("--cli-run", default=None, help=argparse.SUPPRESS)

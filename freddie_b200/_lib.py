@@ -18,7 +18,7 @@ FRS_MAX_STAGES = 32
 TAP_Y_RAW, TAP_Y, TAP_THR, TAP_CAND, TAP_FIXED, TAP_DP_FINAL, TAP_SUB_START, TAP_SUB_N = 1, 2, 3, 4, 5, 6, 7, 8
 TAP_COVERAGE, TAP_DP_TABLES, TAP_COV_OFF, TAP_SUB_TAB_OFF, TAP_FINAL_FLAGS = 9, 10, 12, 13, 14
 OPT_SLAB_WORDS, OPT_KEEP_DP_TABLES, OPT_POLY_LONG_CLASS, OPT_LAZY_SEQ = 1, 2, 3, 4
-STAT_NAMES = ["h2d_upload", "h2d_run", "d2h_run", "clip_words", "seq_words", "poly_tasks", "poly_long_tasks"]
+STAT_NAMES = ["h2d_upload", "h2d_run", "d2h_run", "clip_words", "seq_words", "poly_tasks", "poly_long_tasks", "reruns"]
 
 _p = C.c_void_p
 
@@ -84,6 +84,8 @@ def load():
     lib = C.CDLL(LIB_PATH)
     lib.frs_abi_version.restype = C.c_int
     lib.frs_device_count.restype = C.c_int
+    lib.frs_mem_info.argtypes = [C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    lib.frs_mem_info.restype = C.c_int
     lib.frs_create.argtypes = [C.c_int, C.POINTER(_p)]
     lib.frs_destroy.argtypes = [_p]
     lib.frs_destroy.restype = None
@@ -95,6 +97,9 @@ def load():
     lib.frs_run.argtypes = [_p, C.POINTER(FrsParams), C.POINTER(FrsResultSizes)]
     lib.frs_download.argtypes = [_p, C.POINTER(FrsResult)]
     lib.frs_segment_batch.argtypes = [_p, C.POINTER(FrsBatch), C.POINTER(FrsParams), C.POINTER(FrsResultSizes)]
+    lib.frs_submit.argtypes = [_p, C.POINTER(FrsBatch), C.POINTER(FrsParams), C.POINTER(C.c_int)]
+    lib.frs_wait.argtypes = [_p, C.c_int, C.POINTER(FrsResultSizes)]
+    lib.frs_fetch.argtypes = [_p, C.c_int, C.POINTER(FrsResult)]
     lib.frs_get_intermediate.argtypes = [_p, C.c_int, _p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.frs_set_profiling.argtypes = [_p, C.c_int]
     lib.frs_get_timings.argtypes = [_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_int)]
@@ -103,6 +108,7 @@ def load():
     lib.frs_get_stats.argtypes = [_p, C.POINTER(C.c_longlong), C.c_int]
     lib.frs_get_stats.restype = C.c_int
     for fn in ("frs_create", "frs_upload", "frs_run", "frs_download", "frs_segment_batch", "frs_get_intermediate",
+               "frs_submit", "frs_wait", "frs_fetch",
                "frs_set_profiling", "frs_get_timings", "frs_last_launch_count", "frs_set_option"):
         getattr(lib, fn).restype = C.c_int
     if hasattr(lib, "frs_parse_tints"):
@@ -129,8 +135,9 @@ def load():
 
 
 EXPORTED = [
-    "frs_abi_version", "frs_device_count", "frs_create", "frs_destroy", "frs_last_error", "frs_stream",
-    "frs_upload", "frs_run", "frs_download", "frs_segment_batch", "frs_get_intermediate", "frs_set_profiling",
+    "frs_abi_version", "frs_device_count", "frs_mem_info", "frs_create", "frs_destroy", "frs_last_error", "frs_stream",
+    "frs_upload", "frs_run", "frs_download", "frs_segment_batch", "frs_submit", "frs_wait", "frs_fetch",
+    "frs_get_intermediate", "frs_set_profiling",
     "frs_get_timings", "frs_last_launch_count", "frs_set_option", "frs_get_stats", "frs_parse_tints", "frs_parsed_batch", "frs_parsed_free",
     "frs_format_tints", "frs_packed_write", "frs_packed_read", "frs_packed_write_segment",
 ]

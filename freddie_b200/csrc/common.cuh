@@ -22,7 +22,34 @@ enum {
   DEVERR_POLY_RANGE = 7,        // freddie_segment.py:410,441,450
   DEVERR_BACKTRACE = 8,         // internal: DP backtrace ran off the table
   DEVERR_ISLAND = 9,            // freddie_segment.py:668  interval ends in different islands
+  DEVERR_DP_SMEM = 10,          // limit: a subproblem does not fit the DP kernel's shared memory
+  DEVERR_SCORE_RANGE = 11,      // limit: DP scores of a tint could leave the 30-bit range
 };
+
+// ---------------------------------------------------------------------------------------------
+// Device-side counters of one run: i64 slots written by the kernels and read by the host ONCE, at the
+// end of the run.  No launch of the pipeline depends on a host round trip: grids are sized from upper
+// bounds known at upload time (or are persistent) and read their true extents here; buffers whose size
+// is data-dependent and not linearly bounded (coverage matrix, DP tables, digits, ...) have a capacity
+// (Caps) -- a kernel that would leave it returns without writing, and the host grows the buffer and
+// repeats the run (first batches of a context only; capacities are grow-only).
+// ---------------------------------------------------------------------------------------------
+enum {
+  CNT_K = 0,       // candidates
+  CNT_NWORK = 2,   // DP work items (sum over classes)
+  CNT_COV = 3,     // coverage elements
+  CNT_REF2 = 9,    // refine work list after the filter (int)
+  CNT_REF = 10,    // refine work list (int)
+  CNT_NFIN = 11,   // final positions
+  CNT_NDIG = 12,   // digit bytes
+  CNT_NRUN = 13,   // 1-runs over all reps
+  CNT_NGAP = 14,   // gap records
+  CNT_CLIPW = 15,  // plane words of the soft clips (lazy sequence mode)
+  CNT_PLAN = 16,   // PLAN_SLOTS slots of the subproblem plan (kernels_dp.cuh)
+  CNT_ERR = 40,    // 4 ints: first device assert (code, item), poly tasks, long poly tasks
+  CNT_SLOTS = 48
+};
+struct Caps { i64 P, tab, work, split, dig, runs, gaps, clipw; };  // capacities in elements
 
 __device__ __forceinline__ void dev_fail(int* err, int code, int where) {
   if (atomicCAS(&err[0], 0, code) == 0) err[1] = where;

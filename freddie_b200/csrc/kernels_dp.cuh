@@ -25,7 +25,9 @@ __global__ void __launch_bounds__(COV_THREADS) k_coverage(const RepTile* __restr
                                                          const i64* __restrict__ tint_cov_off,
                                                          const int* __restrict__ rep_iv_off,
                                                          const int* __restrict__ iv_fs, const int* __restrict__ iv_fe,
-                                                         const int* __restrict__ cand_flat, u32* __restrict__ P) {
+                                                         const int* __restrict__ cand_flat, u32* __restrict__ P,
+                                                         const i64* __restrict__ cnt, i64 cap_P) {
+  if (cnt[CNT_COV] > cap_P) return;  // the matrix does not fit its buffer: the host grows it and repeats the run
   const RepTile tl = tiles[blockIdx.x];
   const int r0 = tint_rep_off[tl.tint];
   const int R = tint_rep_off[tl.tint + 1] - r0;
@@ -78,45 +80,50 @@ __global__ void k_tint_cov_sizes(int T, const int* __restrict__ tint_island_off,
 // K6 fixed candidates.  a: ends of each island and candidates above the tint's threshold.
 // b: break_large_problems over the SNAPSHOT of consecutive fixed pairs; additions go to fixed1.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_fixed_a(int n_cand, const int* __restrict__ cand_flat, const int* __restrict__ cand_island,
+__global__ void k_fixed_a(const i64* __restrict__ n_cand_p, const int* __restrict__ cand_flat, const int* __restrict__ cand_island,
                           const int* __restrict__ island_cand_off, const int* __restrict__ island_tint,
                           const double* __restrict__ y, const double* __restrict__ thr, u8* __restrict__ fixed0,
                           u8* __restrict__ fixed1) {
-  int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n_cand) return;
-  int isl = cand_island[q];
-  bool f = (q == island_cand_off[isl]) || (q == island_cand_off[isl + 1] - 1);
-  if (!f) f = y[cand_flat[q]] > thr[island_tint[isl]];
-  fixed0[q] = f;
-  fixed1[q] = f;
+  const int n_cand = (int)*n_cand_p;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_cand; q += gridDim.x * blockDim.x) {
+    int isl = cand_island[q];
+    bool f = (q == island_cand_off[isl]) || (q == island_cand_off[isl + 1] - 1);
+    if (!f) f = y[cand_flat[q]] > thr[island_tint[isl]];
+    fixed0[q] = f;
+    fixed1[q] = f;
+  }
 }
 
-__global__ void k_fixed_b(int n_cand, const int* __restrict__ cand_flat, const int* __restrict__ cand_island,
+__global__ void k_fixed_b(const i64* __restrict__ n_cand_p, const int* __restrict__ cand_flat, const int* __restrict__ cand_island,
                           const int* __restrict__ island_cand_off, const double* __restrict__ y, int mps,
                           const u8* __restrict__ fixed0, u8* __restrict__ fixed1, int* __restrict__ err) {
-  int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n_cand || !fixed0[q]) return;
-  int isl = cand_island[q];
-  int c0 = island_cand_off[isl], c1 = island_cand_off[isl + 1];
-  if (q == c1 - 1) return;
-  int e = q + 1;
-  while (!fixed0[e]) ++e;  // the island's last candidate is fixed
-  int size = e - q + 1;
-  if (size <= mps) return;
-  int cnt = (int)ceil((double)size / (double)mps);
-  double ps = __ddiv_rn((double)size, (double)cnt);
-  int s_local = q - c0;
-  for (int i = 1; i < cnt; ++i) {
-    int mid = (int)__dadd_rn((double)s_local, __dmul_rn((double)i, ps));
-    double best = -INFINITY;
-    int best_c = -1;
-    for (int c = mid - 5; c < mid + 5; ++c) {
-      if (c < 0 || c0 + c >= c1) { dev_fail(err, DEVERR_BREAK_LARGE_RANGE, q); return; }
-      double v = y[cand_flat[c0 + c]];
-      if (v > best) { best = v; best_c = c; }
+  const int n_cand = (int)*n_cand_p;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_cand; q += gridDim.x * blockDim.x) {
+    if (!fixed0[q]) continue;
+    int isl = cand_island[q];
+    int c0 = island_cand_off[isl], c1 = island_cand_off[isl + 1];
+    if (q == c1 - 1) continue;
+    int e = q + 1;
+    while (!fixed0[e]) ++e;  // the island's last candidate is fixed
+    int size = e - q + 1;
+    if (size <= mps) continue;
+    int cnt = (int)ceil((double)size / (double)mps);
+    double ps = __ddiv_rn((double)size, (double)cnt);
+    int s_local = q - c0;
+    for (int i = 1; i < cnt; ++i) {
+      int mid = (int)__dadd_rn((double)s_local, __dmul_rn((double)i, ps));
+      double best = -INFINITY;
+      int best_c = -1;
+      bool bad = false;
+      for (int c = mid - 5; c < mid + 5; ++c) {
+        if (c < 0 || c0 + c >= c1) { dev_fail(err, DEVERR_BREAK_LARGE_RANGE, q); bad = true; break; }
+        double v = y[cand_flat[c0 + c]];
+        if (v > best) { best = v; best_c = c; }
+      }
+      if (bad) break;
+      if (!(best > 0.0)) { dev_fail(err, DEVERR_BREAK_LARGE_POS, q); break; }
+      fixed1[c0 + best_c] = 1;
     }
-    if (!(best > 0.0)) { dev_fail(err, DEVERR_BREAK_LARGE_POS, q); return; }
-    fixed1[c0 + best_c] = 1;
   }
 }
 
@@ -187,88 +194,124 @@ __device__ __forceinline__ int warp_max_i(int v) {
 // sub_info[p] = class | fused << 8 | slab_words << 16;  sub_slabs[p] = CTAs of the subproblem.
 // sub_tab_off[p] = first int32 of the subproblem's global table block (pair-indexed ins [n(n-1)/2]
 // followed by out [C(n,3)]); only subproblems whose tables leave the chip own one.
-__global__ void k_sub_build(int n_cand, const u8* __restrict__ fixed, const int* __restrict__ cand_island,
+__global__ void k_sub_build(const i64* __restrict__ n_cand_p, const u8* __restrict__ fixed, const int* __restrict__ cand_island,
                             const int* __restrict__ island_cand_off, const int* __restrict__ island_tint,
-                            const int* __restrict__ tint_rep_off, int slab_cap, int keep_tables,
-                            int* __restrict__ sub_start, int* __restrict__ sub_n, int* __restrict__ sub_tint,
-                            int* __restrict__ sub_info, int* __restrict__ sub_slabs, i64* __restrict__ sub_tab_off,
-                            i64* __restrict__ plan) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+                            const int* __restrict__ tint_rep_off, const int* __restrict__ tint_read_off, int slab_cap,
+                            int keep_tables, int* __restrict__ sub_start, int* __restrict__ sub_n,
+                            int* __restrict__ sub_tint, int* __restrict__ sub_info, int* __restrict__ sub_slabs,
+                            i64* __restrict__ sub_tab_off, i64* __restrict__ plan, int* __restrict__ err) {
+  const int n_cand = (int)*n_cand_p;
   const int lane = threadIdx.x & 31;
-  int cls = -1, slabs = 0, n = 0, split = 0, info = 0, t = 0;
-  long long t3 = 0, rc = 0, sz = 0;
-  bool has = false;
-  if (q < n_cand && fixed[q]) {
-    const int isl = cand_island[q];
-    const int c1 = island_cand_off[isl + 1];
-    if (q < c1 - 1) {
-      int e = q + 1;
-      while (!fixed[e]) ++e;  // the island's last candidate is fixed
-      if (e - q >= 2) {
-        has = true;
-        n = e - q + 1;
-        t = island_tint[isl];
-        const int R = tint_rep_off[t + 1] - tint_rep_off[t];
-        const int words = (R + 31) >> 5;
-        const int sw = dp_slab_words(n, words, slab_cap);
-        const int fused = (n <= DP_SMEM_MAX_N && words <= sw) ? 1 : 0;
-        cls = dp_class_of(n, words, fused);
-        slabs = fused ? 1 : (words + sw - 1) / sw;
-        split = !fused;
-        t3 = (long long)n * (n - 1) * (n - 2) / 6;
-        rc = t3 * R;
-        info = cls | (fused << 8) | (sw << 16);
-        sz = (fused && !keep_tables) ? 0 : (long long)n * (n - 1) / 2 + t3;
+  // CTA-uniform trip count: every lane of a warp reaches the ballots
+  for (int q0 = blockIdx.x * blockDim.x; q0 < n_cand; q0 += gridDim.x * blockDim.x) {
+    const int q = q0 + threadIdx.x;
+    int cls = -1, slabs = 0, n = 0, split = 0, info = 0, t = 0;
+    long long t3 = 0, rc = 0, sz = 0;
+    bool has = false;
+    if (q < n_cand && fixed[q]) {
+      const int isl = cand_island[q];
+      const int c1 = island_cand_off[isl + 1];
+      if (q < c1 - 1) {
+        int e = q + 1;
+        while (!fixed[e]) ++e;  // the island's last candidate is fixed
+        if (e - q >= 2) {
+          has = true;
+          n = e - q + 1;
+          t = island_tint[isl];
+          const int R = tint_rep_off[t + 1] - tint_rep_off[t];
+          const int words = (R + 31) >> 5;
+          const int sw = dp_slab_words(n, words, slab_cap);
+          const int fused = (n <= DP_SMEM_MAX_N && words <= sw) ? 1 : 0;
+          cls = dp_class_of(n, words, fused);
+          slabs = fused ? 1 : (words + sw - 1) / sw;
+          split = !fused;
+          t3 = (long long)n * (n - 1) * (n - 2) / 6;
+          rc = t3 * R;
+          info = cls | (fused << 8) | (sw << 16);
+          sz = (fused && !keep_tables) ? 0 : (long long)n * (n - 1) / 2 + t3;
+          // |score| <= (segments of a path) x (reads of the tint): must stay inside the 30-bit range of FRS_NEG_INF
+          if ((long long)n * (tint_read_off[t + 1] - tint_read_off[t]) >= 0x3fffffffLL) dev_fail(err, DEVERR_SCORE_RANGE, t);
+        }
       }
     }
-  }
-  const unsigned m = __ballot_sync(0xffffffffu, has);
-  if (m == 0) return;
-  int base = 0;
-  if (lane == __ffs(m) - 1) base = (int)atomicAdd((unsigned long long*)&plan[PLAN_NSUB], (unsigned long long)__popc(m));
-  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-  if (has) {
-    const int p = base + __popc(m & ((1u << lane) - 1u));
-    sub_start[p] = q;
-    sub_n[p] = n;
-    sub_tint[p] = t;
-    sub_info[p] = info;
-    sub_slabs[p] = slabs;
-    sub_tab_off[p] = sz ? (i64)atomicAdd((unsigned long long*)&plan[PLAN_TAB], (unsigned long long)sz) : 0;
-  }
-  // warp-aggregated statistics
+    const unsigned m = __ballot_sync(0xffffffffu, has);
+    if (m == 0) continue;
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = (int)atomicAdd((unsigned long long*)&plan[PLAN_NSUB], (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (has) {
+      const int p = base + __popc(m & ((1u << lane) - 1u));
+      sub_start[p] = q;
+      sub_n[p] = n;
+      sub_tint[p] = t;
+      sub_info[p] = info;
+      sub_slabs[p] = slabs;
+      sub_tab_off[p] = sz ? (i64)atomicAdd((unsigned long long*)&plan[PLAN_TAB], (unsigned long long)sz) : 0;
+    }
+    // warp-aggregated statistics
 #pragma unroll
-  for (int c = 0; c < DP_CLASSES; ++c) {
-    long long s = warp_sum_ll(cls == c ? slabs : 0);
-    int mx = warp_max_i(cls == c ? n : 0);
-    if (lane == 0 && s) {
-      atomicAdd((unsigned long long*)&plan[PLAN_WORK + c], (unsigned long long)s);
-      atomicMax((long long*)&plan[PLAN_MAXN + c], (long long)mx);
+    for (int c = 0; c < DP_CLASSES; ++c) {
+      long long s = warp_sum_ll(cls == c ? slabs : 0);
+      int mx = warp_max_i(cls == c ? n : 0);
+      if (lane == 0 && s) {
+        atomicAdd((unsigned long long*)&plan[PLAN_WORK + c], (unsigned long long)s);
+        atomicMax((long long*)&plan[PLAN_MAXN + c], (long long)mx);
+      }
+    }
+    long long s_split = warp_sum_ll(split), s_t3 = warp_sum_ll(t3), s_rc = warp_sum_ll(rc);
+    int m_all = warp_max_i(n);
+    if (lane == 0) {
+      if (s_split) atomicAdd((unsigned long long*)&plan[PLAN_SPLIT], (unsigned long long)s_split);
+      if (s_t3) atomicAdd((unsigned long long*)&plan[PLAN_CELLS], (unsigned long long)s_t3);
+      if (s_rc) atomicAdd((unsigned long long*)&plan[PLAN_RCELLS], (unsigned long long)s_rc);
+      atomicMax((long long*)&plan[PLAN_MAXALL], (long long)m_all);
     }
   }
-  long long s_split = warp_sum_ll(split), s_t3 = warp_sum_ll(t3), s_rc = warp_sum_ll(rc);
-  int m_all = warp_max_i(n);
-  if (lane == 0) {
-    if (s_split) atomicAdd((unsigned long long*)&plan[PLAN_SPLIT], (unsigned long long)s_split);
-    if (s_t3) atomicAdd((unsigned long long*)&plan[PLAN_CELLS], (unsigned long long)s_t3);
-    if (s_rc) atomicAdd((unsigned long long*)&plan[PLAN_RCELLS], (unsigned long long)s_rc);
-    atomicMax((long long*)&plan[PLAN_MAXALL], (long long)m_all);
+}
+
+// One thread, after k_sub_build and the coverage-offset scan: first work item of every class, totals, and
+// the cursors of the work lists (fill cursors [0..DP_CLASSES], work-stealing cursors [8..8+DP_CLASSES]).
+__global__ void k_plan_finish(i64* __restrict__ cnt, const i64* __restrict__ tint_cov_off, int n_tints,
+                              int* __restrict__ bases /* [DP_CLASSES] */, int* __restrict__ cursor /* [16] */) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    i64 acc = 0;
+    for (int k = 0; k < DP_CLASSES; ++k) {
+      bases[k] = (int)(acc < 0x7fffffffLL ? acc : 0x7fffffffLL);
+      acc += cnt[CNT_PLAN + PLAN_WORK + k];
+    }
+    cnt[CNT_NWORK] = acc;
+    cnt[CNT_COV] = tint_cov_off[n_tints];
+    for (int k = 0; k < 16; ++k) cursor[k] = 0;
   }
+}
+
+// every data-dependent buffer of the DP stage fits its capacity (else the stage is skipped and repeated)
+__device__ __forceinline__ bool dp_caps_ok(const i64* __restrict__ cnt, const Caps& cp) {
+  return cnt[CNT_COV] <= cp.P && cnt[CNT_PLAN + PLAN_TAB] <= cp.tab && cnt[CNT_NWORK] <= cp.work &&
+         cnt[CNT_PLAN + PLAN_SPLIT] <= cp.split;
 }
 
 // work lists: class c owns work[base[c] .. base[c] + count[c]); cursor[c] starts at 0.  The order of
 // the items inside a class is arbitrary (atomics) -- results do not depend on it (integer sums).
-struct DpBases { int base[DP_CLASSES]; };
-__global__ void k_sub_fill(int n_sub, const int* __restrict__ sub_info, const int* __restrict__ sub_slabs,
-                           DpBases bases, int* __restrict__ cursor, DpWork* __restrict__ work,
-                           int* __restrict__ split_list) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_sub) return;
-  const int info = sub_info[p];
-  const int cls = info & 0xff, slabs = sub_slabs[p];
-  int off = bases.base[cls] + atomicAdd(&cursor[cls], slabs);
-  for (int s = 0; s < slabs; ++s) work[off + s] = DpWork{p, s};
-  if (!((info >> 8) & 1)) split_list[atomicAdd(&cursor[DP_CLASSES], 1)] = p;
+__global__ void k_sub_fill(const i64* __restrict__ cnt, Caps caps, const int* __restrict__ sub_info,
+                           const int* __restrict__ sub_slabs, const int* __restrict__ bases, int* __restrict__ cursor,
+                           DpWork* __restrict__ work, int* __restrict__ split_list) {
+  if (!dp_caps_ok(cnt, caps)) return;
+  const int n_sub = (int)cnt[CNT_PLAN + PLAN_NSUB];
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_sub; p += gridDim.x * blockDim.x) {
+    const int info = sub_info[p];
+    const int cls = info & 0xff, slabs = sub_slabs[p];
+    int off = bases[cls] + atomicAdd(&cursor[cls], slabs);
+    for (int s = 0; s < slabs; ++s) work[off + s] = DpWork{p, s};
+    if (!((info >> 8) & 1)) split_list[atomicAdd(&cursor[DP_CLASSES], 1)] = p;
+  }
+}
+
+// zeroes the global DP tables of the run (their size is only known on the device)
+__global__ void k_zero_tab(const i64* __restrict__ cnt, Caps caps, int* __restrict__ tab) {
+  if (!dp_caps_ok(cnt, caps)) return;
+  const i64 n = cnt[CNT_PLAN + PLAN_TAB];
+  for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (i64)gridDim.x * blockDim.x) tab[e] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -448,6 +491,11 @@ struct DpArgs {
   int* tab;        // global tables of the split / kept subproblems
   u8* final_flag;  // [n_cand]
   int* err;
+  const i64* cnt;  // device counters of the run (work counts per class, capacities check)
+  Caps caps;
+  const int* bases;  // [DP_CLASSES] first work item of each class
+  int* cursor;       // [8 + class] work-stealing cursors, [8 + DP_CLASSES] the solver's
+  int m_cap;         // upper bound of a subproblem's size (max_problem_size + 12, see k_fixed_b)
 };
 
 // shared-memory carve-up of k_dp for (M = largest n of the launch, wc, out table on chip?)
@@ -573,153 +621,173 @@ __device__ __forceinline__ void dp_triple_phase(const int n, const int nw, const
   }
 }
 
+// Persistent: the CTAs of a class take the class's work items from a shared cursor (work stealing: items
+// differ in cost by orders of magnitude) until the list is empty; the number of items is only known on
+// the device.  smem_bytes = dynamic shared memory of the launch; every item carves it for its own n.
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 ? 3 : 1)) k_dp(DpArgs A, const DpWork* __restrict__ work, int M, int wc,
-                                                int out_on_chip) {
+__global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 ? 3 : 1)) k_dp(DpArgs A, const DpWork* __restrict__ work_all,
+                                                int cls, int smem_bytes) {
   extern __shared__ __align__(16) unsigned char dsm[];
-  const DpWork wk = work[blockIdx.x];
-  const int p = wk.sub;
-  const int n = A.sub_n[p];
-  const int qs = A.sub_start[p];
-  const int t = A.sub_tint[p];
-  const bool fused = (A.sub_info[p] >> 8) & 1;
-  const int r0 = A.tint_rep_off[t];
-  const int R = A.tint_rep_off[t + 1] - r0;
-  const int Rp = (R + 3) & ~3;
-  const int words = (R + 31) >> 5;
-  const int sw = A.sub_info[p] >> 16;  // read-rep words per CTA of this subproblem
-  const int w_lo = fused ? 0 : wk.slab * sw;
-  const int w_hi = fused ? words : min(words, w_lo + sw);
-  const int p2 = n * (n - 1) / 2;
-  const int c3 = n * (n - 1) * (n - 2) / 6;
-  const int CW = 32 * wc;
-  const DpSmem L = dp_smem_layout(M, wc, out_on_chip);
-  unsigned long long* bar = (unsigned long long*)dsm;
-  u32* tile = (u32*)(dsm + L.tile);      // [n][CW]   (16-byte aligned rows)
-  uint2* ynm = (uint2*)(dsm + L.ynm);    // [p2][wc]  x = yea, y = nay
-  int* cf = (int*)(dsm + L.cf);
-  int* ty = (int*)(dsm + L.ty);
-  int* tn = (int*)(dsm + L.tn);
-  u32* planes = (u32*)(dsm + L.planes);  // [wc][32]
-  int* nplanes = (int*)(dsm + L.nplanes);
-  u32* vmask = (u32*)(dsm + L.vmask);
-  ushort2* munit = (ushort2*)(dsm + L.munit);
-  int* cumu = (int*)(dsm + L.cumu);
-  __shared__ int s_n_munit;
-  int* amb_s = (int*)(dsm + L.amb);      // [p2]
-  int* out_s = (int*)(dsm + L.out);      // [c3]
-
+  __shared__ int s_n_munit, s_item;
+  if (!dp_caps_ok(A.cnt, A.caps)) return;
+  const int n_work = (int)A.cnt[CNT_PLAN + PLAN_WORK + cls];
+  if (n_work == 0) return;
+  const DpWork* work = work_all + A.bases[cls];
+  const int out_on_chip = cls < 5 ? 1 : 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = THREADS / 32;
-  const u32* Prow0 = A.P + A.tint_cov_off[t] + (i64)(qs - A.tint_cand_off[t]) * Rp;
-  int* tab_g = A.tab + A.sub_tab_off[p];  // only dereferenced when the subproblem owns a block
-
+  unsigned long long* bar = (unsigned long long*)dsm;
   if (tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < n; i += THREADS) cf[i] = A.cand_flat[qs + i];
-  if (tid == 32 % THREADS) {  // unit tables of the two phases (a few hundred entries)
-    int u = 0;
-    for (int i = 0; i < n - 1; ++i)
-      for (int j0 = i + 1; j0 < n; j0 += DP_MASK_J) munit[u++] = make_ushort2((unsigned short)i, (unsigned short)j0);
-    s_n_munit = u;
-    int acc = 0;
-    cumu[0] = 0;
-    for (int j = 1; j <= n - 1; ++j) {
-      cumu[j] = acc;
-      acc += j * ((n - 1 - j + DP_TRI_K - 1) / DP_TRI_K);
-    }
-  }
-  if (out_on_chip) {
-    for (int e = tid; e < p2; e += THREADS) amb_s[e] = 0;
-    for (int e = tid; e < c3; e += THREADS) out_s[e] = 0;
-  }
-  __syncthreads();
-  // first chunk's TMA can fly while the cuts are computed
   u32 phase = 0;
-  auto issue = [&](int w0) {
-    int col0 = w0 * 32;
-    int cols = min(CW, Rp - col0);
-    u32 bytes = (u32)cols * 4u;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(bar, bytes * (u32)n);
-    for (int i = 0; i < n; ++i) tma_bulk_g2s(tile + (size_t)i * CW, Prow0 + (i64)i * Rp + col0, bytes, bar);
-  };
-  if (tid == 0 && w_lo < w_hi) issue(w_lo);
-  for (int e = tid; e < p2; e += THREADS) {
-    // decode pair e -> (i, j): rows are short, a linear walk is fine (done once per CTA)
-    int i = 0, rem = e;
-    while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
-    int j = i + 1 + rem;
-    int a, b;
-    length_cuts(cf[j] - cf[i] + 1, A.thr_table, A.thr_table_len, A.tp, a, b);
-    ty[e] = a;
-    tn[e] = b;
-  }
-
-  for (int w0 = w_lo; w0 < w_hi; w0 += wc) {
-    const int nw = min(wc, w_hi - w0);
-    // weight planes + valid-rep mask of the chunk's words
-    for (int w = warp; w < nw; w += NW) {
-      int rep = (w0 + w) * 32 + lane;
-      int wt = (rep < R) ? A.rep_weight[r0 + rep] : 0;
-      int mx = warp_max_i(wt);
-      int np = 32 - __clz(mx);
-      for (int b = 0; b < np; ++b) {
-        u32 m = __ballot_sync(0xffffffffu, (wt >> b) & 1);
-        if (lane == 0) planes[w * 32 + b] = m;
-      }
-      u32 vm = __ballot_sync(0xffffffffu, rep < R);
-      if (lane == 0) { nplanes[w] = np; vmask[w] = vm; }
+  for (;;) {
+    __syncthreads();  // the previous item is done with the shared memory (and the barrier is initialised)
+    if (tid == 0) s_item = atomicAdd(&A.cursor[8 + cls], 1);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= n_work) break;
+    const DpWork wk = work[item];
+    const int p = wk.sub;
+    const int n = A.sub_n[p];
+    int wc = DPT_MAXW;
+    while (wc > 1 && dp_smem_layout(n, wc, out_on_chip).total > smem_bytes) wc >>= 1;
+    const DpSmem L = dp_smem_layout(n, wc, out_on_chip);
+    if (L.total > smem_bytes || n > A.m_cap) {
+      if (tid == 0) dev_fail(A.err, DEVERR_DP_SMEM, n);
+      continue;
     }
-    __syncthreads();  // cuts + planes visible; previous chunk's triple phase done
-    mbar_wait(bar, phase);
-    phase ^= 1;
-    // ---- mask phase: rows i paired from both ends for balance.  Only the last word of a tint can
-    // hold lanes without a rep; every other chunk skips the masking ----
-    const bool tail_chunk = (w0 + nw == words) && (R & 31);
-    if (tail_chunk) dp_mask_phase<THREADS, true>(n, nw, wc, CW, tile, ty, tn, ynm, vmask, munit, s_n_munit);
-    else dp_mask_phase<THREADS, false>(n, nw, wc, CW, tile, ty, tn, ynm, vmask, munit, s_n_munit);
-    __syncthreads();  // masks complete, tile free
-    if (tid == 0 && w0 + wc < w_hi) issue(w0 + wc);
-    // ---- ins pass: ambiguous reps per pair ----
-    for (int e = tid; e < p2; e += THREADS) {
+    const int qs = A.sub_start[p];
+    const int t = A.sub_tint[p];
+    const bool fused = (A.sub_info[p] >> 8) & 1;
+    const int r0 = A.tint_rep_off[t];
+    const int R = A.tint_rep_off[t + 1] - r0;
+    const int Rp = (R + 3) & ~3;
+    const int words = (R + 31) >> 5;
+    const int sw = A.sub_info[p] >> 16;  // read-rep words per CTA of this subproblem
+    const int w_lo = fused ? 0 : wk.slab * sw;
+    const int w_hi = fused ? words : min(words, w_lo + sw);
+    const int p2 = n * (n - 1) / 2;
+    const int c3 = n * (n - 1) * (n - 2) / 6;
+    const int CW = 32 * wc;
+    u32* tile = (u32*)(dsm + L.tile);      // [n][CW]   (16-byte aligned rows)
+    uint2* ynm = (uint2*)(dsm + L.ynm);    // [p2][wc]  x = yea, y = nay
+    int* cf = (int*)(dsm + L.cf);
+    int* ty = (int*)(dsm + L.ty);
+    int* tn = (int*)(dsm + L.tn);
+    u32* planes = (u32*)(dsm + L.planes);  // [wc][32]
+    int* nplanes = (int*)(dsm + L.nplanes);
+    u32* vmask = (u32*)(dsm + L.vmask);
+    ushort2* munit = (ushort2*)(dsm + L.munit);
+    int* cumu = (int*)(dsm + L.cumu);
+    int* amb_s = (int*)(dsm + L.amb);      // [p2]
+    int* out_s = (int*)(dsm + L.out);      // [c3]
+    const u32* Prow0 = A.P + A.tint_cov_off[t] + (i64)(qs - A.tint_cand_off[t]) * Rp;
+    int* tab_g = A.tab + A.sub_tab_off[p];  // only dereferenced when the subproblem owns a block
+
+    for (int i = tid; i < n; i += THREADS) cf[i] = A.cand_flat[qs + i];
+    if (tid == 32 % THREADS) {  // unit tables of the two phases (a few hundred entries)
+      int u = 0;
+      for (int i = 0; i < n - 1; ++i)
+        for (int j0 = i + 1; j0 < n; j0 += DP_MASK_J) munit[u++] = make_ushort2((unsigned short)i, (unsigned short)j0);
+      s_n_munit = u;
       int acc = 0;
-      for (int w = 0; w < nw; ++w) {
-        const uint2 yn = ynm[(size_t)e * wc + w];
-        const u32 am = vmask[w] & ~(yn.x | yn.y);
-        if (am) acc += wpopc(am, planes + w * 32, nplanes[w]);
-      }
-      if (acc) {
-        if (out_on_chip) amb_s[e] += acc;
-        else atomicAdd(&tab_g[e], acc);
+      cumu[0] = 0;
+      for (int j = 1; j <= n - 1; ++j) {
+        cumu[j] = acc;
+        acc += j * ((n - 1 - j + DP_TRI_K - 1) / DP_TRI_K);
       }
     }
-    // ---- triple phase ----
-    {
-      bool w1 = true;  // every word of the chunk has unit weights only
-      for (int w = 0; w < nw; ++w) w1 = w1 && nplanes[w] <= 1;
-      int* dst = out_on_chip ? out_s : (tab_g + p2);
-      if (w1) dp_triple_phase<THREADS, true>(n, nw, wc, ynm, planes, nplanes, cumu, out_on_chip, dst);
-      else dp_triple_phase<THREADS, false>(n, nw, wc, ynm, planes, nplanes, cumu, out_on_chip, dst);
+    if (out_on_chip) {
+      for (int e = tid; e < p2; e += THREADS) amb_s[e] = 0;
+      for (int e = tid; e < c3; e += THREADS) out_s[e] = 0;
     }
-    __syncthreads();  // the next chunk rewrites the weight planes and the masks
-  }
+    __syncthreads();
+    // first chunk's TMA can fly while the cuts are computed
+    auto issue = [&](int w0) {
+      int col0 = w0 * 32;
+      int cols = min(CW, Rp - col0);
+      u32 bytes = (u32)cols * 4u;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(bar, bytes * (u32)n);
+      for (int i = 0; i < n; ++i) tma_bulk_g2s(tile + (size_t)i * CW, Prow0 + (i64)i * Rp + col0, bytes, bar);
+    };
+    if (tid == 0 && w_lo < w_hi) issue(w_lo);
+    for (int e = tid; e < p2; e += THREADS) {
+      // decode pair e -> (i, j): rows are short, a linear walk is fine (done once per item)
+      int i = 0, rem = e;
+      while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
+      int j = i + 1 + rem;
+      int a, b;
+      length_cuts(cf[j] - cf[i] + 1, A.thr_table, A.thr_table_len, A.tp, a, b);
+      ty[e] = a;
+      tn[e] = b;
+    }
 
-  if (!out_on_chip) return;  // class 4: tables are already in global memory
-  if (!fused) {
-    // split mode: add this slab's partial tables to the global ones
-    for (int e = tid; e < p2; e += THREADS) { int v = amb_s[e]; if (v) atomicAdd(&tab_g[e], v); }
-    for (int e = tid; e < c3; e += THREADS) { int v = out_s[e]; if (v) atomicAdd(&tab_g[p2 + e], v); }
-    return;
+    for (int w0 = w_lo; w0 < w_hi; w0 += wc) {
+      const int nw = min(wc, w_hi - w0);
+      // weight planes + valid-rep mask of the chunk's words
+      for (int w = warp; w < nw; w += NW) {
+        int rep = (w0 + w) * 32 + lane;
+        int wt = (rep < R) ? A.rep_weight[r0 + rep] : 0;
+        int mx = warp_max_i(wt);
+        int np = 32 - __clz(mx);
+        for (int b = 0; b < np; ++b) {
+          u32 m = __ballot_sync(0xffffffffu, (wt >> b) & 1);
+          if (lane == 0) planes[w * 32 + b] = m;
+        }
+        u32 vm = __ballot_sync(0xffffffffu, rep < R);
+        if (lane == 0) { nplanes[w] = np; vmask[w] = vm; }
+      }
+      __syncthreads();  // cuts + planes visible; previous chunk's triple phase done
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      // ---- mask phase.  Only the last word of a tint can hold lanes without a rep; every other chunk
+      // skips the masking ----
+      const bool tail_chunk = (w0 + nw == words) && (R & 31);
+      if (tail_chunk) dp_mask_phase<THREADS, true>(n, nw, wc, CW, tile, ty, tn, ynm, vmask, munit, s_n_munit);
+      else dp_mask_phase<THREADS, false>(n, nw, wc, CW, tile, ty, tn, ynm, vmask, munit, s_n_munit);
+      __syncthreads();  // masks complete, tile free
+      if (tid == 0 && w0 + wc < w_hi) issue(w0 + wc);
+      // ---- ins pass: ambiguous reps per pair ----
+      for (int e = tid; e < p2; e += THREADS) {
+        int acc = 0;
+        for (int w = 0; w < nw; ++w) {
+          const uint2 yn = ynm[(size_t)e * wc + w];
+          const u32 am = vmask[w] & ~(yn.x | yn.y);
+          if (am) acc += wpopc(am, planes + w * 32, nplanes[w]);
+        }
+        if (acc) {
+          if (out_on_chip) amb_s[e] += acc;
+          else atomicAdd(&tab_g[e], acc);
+        }
+      }
+      // ---- triple phase ----
+      {
+        bool w1 = true;  // every word of the chunk has unit weights only
+        for (int w = 0; w < nw; ++w) w1 = w1 && nplanes[w] <= 1;
+        int* dst = out_on_chip ? out_s : (tab_g + p2);
+        if (w1) dp_triple_phase<THREADS, true>(n, nw, wc, ynm, planes, nplanes, cumu, out_on_chip, dst);
+        else dp_triple_phase<THREADS, false>(n, nw, wc, ynm, planes, nplanes, cumu, out_on_chip, dst);
+      }
+      __syncthreads();  // the next chunk rewrites the weight planes and the masks
+    }
+
+    if (!out_on_chip) continue;  // class 5: tables are already in global memory
+    if (!fused) {
+      // split mode: add this slab's partial tables to the global ones
+      for (int e = tid; e < p2; e += THREADS) { int v = amb_s[e]; if (v) atomicAdd(&tab_g[e], v); }
+      for (int e = tid; e < c3; e += THREADS) { int v = out_s[e]; if (v) atomicAdd(&tab_g[p2 + e], v); }
+      continue;
+    }
+    if (A.keep_tables) {
+      for (int e = tid; e < p2; e += THREADS) tab_g[e] = amb_s[e];
+      for (int e = tid; e < c3; e += THREADS) tab_g[p2 + e] = out_s[e];
+    }
+    dp_solve<false, (THREADS == 128 ? 16 : 32)>(n, cf, amb_s, out_s, A.lo, (int*)(dsm + L.G), (short*)(dsm + L.arg), (int*)(dsm + L.red),
+                   A.final_flag + qs, A.err, p);
   }
-  if (A.keep_tables) {
-    for (int e = tid; e < p2; e += THREADS) tab_g[e] = amb_s[e];
-    for (int e = tid; e < c3; e += THREADS) tab_g[p2 + e] = out_s[e];
-  }
-  dp_solve<false, (THREADS == 128 ? 16 : 32)>(n, cf, amb_s, out_s, A.lo, (int*)(dsm + L.G), (short*)(dsm + L.arg), (int*)(dsm + L.red),
-                 A.final_flag + qs, A.err, p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -745,11 +813,18 @@ struct DpWarpSmem {
 };
 
 template <int MAXN>
-__global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWork* __restrict__ work, int n_work) {
+__global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWork* __restrict__ work_all, int cls) {
   extern __shared__ __align__(16) unsigned char dsm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int item = blockIdx.x * DPW_WARPS + warp;
-  if (item >= n_work) return;
+  if (!dp_caps_ok(A.cnt, A.caps)) return;
+  const int n_work = (int)A.cnt[CNT_PLAN + PLAN_WORK + cls];
+  const DpWork* work = work_all + A.bases[cls];
+ for (;;) {  // persistent warps: items from the class's cursor until the list is empty
+  int item = 0;
+  if (lane == 0) item = atomicAdd(&A.cursor[8 + cls], 1);
+  item = __shfl_sync(0xffffffffu, item, 0);
+  if (item >= n_work) break;
+  __syncwarp();
   DpWarpSmem<MAXN>& S = reinterpret_cast<DpWarpSmem<MAXN>*>(dsm)[warp];
   const int p = work[item].sub;
   const int n = A.sub_n[p];
@@ -830,6 +905,8 @@ __global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWo
     for (int e = lane; e < c3; e += 32) tab_g[p2 + e] = S.out[e];
   }
   dp_solve<true, (MAXN <= 8 ? 8 : 16)>(n, S.cf, S.amb, S.out, A.lo, S.G, S.arg, nullptr, A.final_flag + qs, A.err, p);
+  __syncwarp();
+ }
 }
 
 // K8 for split subproblems: tables summed in global memory by the slab CTAs of k_dp; staged into
@@ -838,23 +915,37 @@ __global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWo
 __global__ void __launch_bounds__(DPS_THREADS) k_dp_solve(DpArgs A, const int* __restrict__ split_list, int max_n,
                                                           int stage_max_n) {
   extern __shared__ __align__(16) int ssm[];
-  const int p = split_list[blockIdx.x];
-  const int n = A.sub_n[p], qs = A.sub_start[p];
+  __shared__ int s_item;
+  if (!dp_caps_ok(A.cnt, A.caps)) return;
+  const int n_split = (int)A.cnt[CNT_PLAN + PLAN_SPLIT];
   int* G = ssm;                         // [n][n]
   int* cf = G + max_n * max_n;          // [n]
   int* red = cf + max_n;                // [2*DPS_MAX_WARPS]
   short* arg = (short*)(red + 2 * DPS_MAX_WARPS);  // [n][n]
   int* stab = (int*)(arg + ((max_n * max_n + 1) & ~1));
-  const int* tab = A.tab + A.sub_tab_off[p];
-  const int p2 = n * (n - 1) / 2;
-  for (int i = threadIdx.x; i < n; i += DPS_THREADS) cf[i] = A.cand_flat[qs + i];
-  if (n <= stage_max_n) {
-    const int tot = p2 + n * (n - 1) * (n - 2) / 6;
-    for (int e = threadIdx.x; e < tot; e += DPS_THREADS) stab[e] = tab[e];
-    tab = stab;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_item = atomicAdd(&A.cursor[8 + DP_CLASSES], 1);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= n_split) break;
+    const int p = split_list[item];
+    const int n = A.sub_n[p], qs = A.sub_start[p];
+    if (n > max_n) {
+      if (threadIdx.x == 0) dev_fail(A.err, DEVERR_DP_SMEM, n);
+      continue;
+    }
+    const int* tab = A.tab + A.sub_tab_off[p];
+    const int p2 = n * (n - 1) / 2;
+    for (int i = threadIdx.x; i < n; i += DPS_THREADS) cf[i] = A.cand_flat[qs + i];
+    if (n <= stage_max_n) {
+      const int tot = p2 + n * (n - 1) * (n - 2) / 6;
+      for (int e = threadIdx.x; e < tot; e += DPS_THREADS) stab[e] = tab[e];
+      tab = stab;
+    }
+    __syncthreads();
+    dp_solve<false, 32>(n, cf, tab, tab + p2, A.lo, G, arg, red, A.final_flag + qs, A.err, p);
   }
-  __syncthreads();
-  dp_solve<false, 32>(n, cf, tab, tab + p2, A.lo, G, arg, red, A.final_flag + qs, A.err, p);
 }
 __host__ inline size_t dps_smem_bytes(int max_n, int stage_max_n) {
   size_t b = (size_t)max_n * max_n * 4 + (size_t)max_n * 4 + 2 * DPS_MAX_WARPS * 4 + (size_t)((max_n * max_n + 1) & ~1) * 2;

@@ -8,19 +8,21 @@
 // Pre-refine finals = candidates kept by fixed | DP.  One thread per candidate: mark its sample in the
 // per-sample flag array and, if the segment up to the next final of the island is longer than 40
 // samples (:252), append it to the refine work list (arbitrary order).
-__global__ void k_final_mark(int n_cand, const u8* __restrict__ dpfinal, const int* __restrict__ cand_flat,
+__global__ void k_final_mark(const i64* __restrict__ n_cand_p, const u8* __restrict__ dpfinal, const int* __restrict__ cand_flat,
                              const int* __restrict__ cand_island, const int* __restrict__ island_cand_off,
                              u8* __restrict__ sflag, int2* __restrict__ ref_list, int* __restrict__ ref_cnt) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n_cand || !dpfinal[q]) return;
-  const int a = cand_flat[q];
-  sflag[a] = 1;
-  const int c1 = island_cand_off[cand_island[q] + 1];
-  if (q >= c1 - 1) return;
-  int e = q + 1;
-  while (!dpfinal[e]) ++e;  // the island's last candidate is final
-  const int b = cand_flat[e];
-  if (b - a > 2 * 20) ref_list[atomicAdd(ref_cnt, 1)] = make_int2(a, b);
+  const int n_cand = (int)*n_cand_p;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_cand; q += gridDim.x * blockDim.x) {
+    if (!dpfinal[q]) continue;
+    const int a = cand_flat[q];
+    sflag[a] = 1;
+    const int c1 = island_cand_off[cand_island[q] + 1];
+    if (q >= c1 - 1) continue;
+    int e = q + 1;
+    while (!dpfinal[e]) ++e;  // the island's last candidate is final
+    const int b = cand_flat[e];
+    if (b - a > 2 * 20) ref_list[atomicAdd(ref_cnt, 1)] = make_int2(a, b);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -200,6 +202,19 @@ __global__ void k_seg_cuts(const i64* __restrict__ n_final_p, const int* __restr
   }
 }
 
+// Capacity guards of the output stages (see Caps in common.cuh): a stage whose data-dependent buffer is
+// too small is skipped -- and so is everything that would read its output -- and the host repeats the run.
+__device__ __forceinline__ bool digits_fit(const i64* __restrict__ cnt, const Caps& cp) { return cnt[CNT_NDIG] <= cp.dig; }
+__device__ __forceinline__ bool runs_fit(const i64* __restrict__ cnt, const Caps& cp) {
+  return digits_fit(cnt, cp) && cnt[CNT_NRUN] <= cp.runs;
+}
+__device__ __forceinline__ bool gaps_fit(const i64* __restrict__ cnt, const Caps& cp) {
+  return runs_fit(cnt, cp) && cnt[CNT_NGAP] <= cp.gaps;
+}
+__device__ __forceinline__ bool clips_fit(const i64* __restrict__ cnt, const Caps& cp) {
+  return gaps_fit(cnt, cp) && cnt[CNT_CLIPW] <= cp.clipw;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K10 digits (:808-838).  One thread per read rep walks the tint's final positions and its own
 // (ordered) intervals with two pointers: P(x) = samples of the rep strictly before flat x, and the
@@ -220,8 +235,9 @@ __global__ void __launch_bounds__(DIG_THREADS) k_digits(const RepTile* __restric
                                                        const int* __restrict__ final_flat,
                                                        const int* __restrict__ seg_ty, const int* __restrict__ seg_tn,
                                                        u8* __restrict__ digits, int* __restrict__ run_cnt /* zeroed */,
-                                                       int* __restrict__ err) {
+                                                       int* __restrict__ err, const i64* __restrict__ cnt, Caps caps) {
   __shared__ u8 tile[DIG_THREADS][DIG_SEGS + 1];
+  if (!digits_fit(cnt, caps)) return;
   const RepTile tl = tiles[blockIdx.x];
   const int r0 = tint_rep_off[tl.tint];
   const int R = tint_rep_off[tl.tint + 1] - r0;
@@ -298,10 +314,11 @@ __global__ void __launch_bounds__(DIG_THREADS) k_digits(const RepTile* __restric
 // ends found with ballots -- the k-th start and the k-th end of a row belong to the same run.
 __global__ void k_run_fill(int n_reps, const int* __restrict__ rep_tint, const int* __restrict__ tint_rep_off,
                            const int* __restrict__ tint_final_off, const i64* __restrict__ tint_digit_off,
-                           const u8* __restrict__ digits, const int* __restrict__ run_off, int2* __restrict__ runs) {
+                           const u8* __restrict__ digits, const int* __restrict__ run_off, int2* __restrict__ runs,
+                           const i64* __restrict__ cnt, Caps caps) {
   int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
-  if (r >= n_reps) return;
+  if (r >= n_reps || !runs_fit(cnt, caps)) return;
   int t = rep_tint[r];
   int S = tint_final_off[t + 1] - tint_final_off[t] - 1;
   const u8* row = digits + tint_digit_off[t] + (i64)(r - tint_rep_off[t]) * S;
@@ -379,6 +396,8 @@ struct GapArgs {
   int* task_order;    // [4N] slots, longest class first
   PolyRes* task_res;  // [4N]
   int long_class;     // tasks of classes >= long_class go to k_poly_long (default POLY_LONG_CLASS)
+  const i64* cnt;     // device counters + capacities of the run (guards)
+  Caps caps;
 };
 
 // forward_thread_cigar (:289-304): every op length, insertions included, is clipped by the remaining
@@ -451,7 +470,7 @@ __host__ __device__ __forceinline__ ClipGeo clip_geometry(int L, int n, bool is_
 // head[3] = q_ssc and head[6] = q_esc are provisional; k_gap_finish rewrites them.
 __global__ void __launch_bounds__(128) k_gap_prep(GapArgs A) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < A.n_reads) {
+  if (i < A.n_reads && gaps_fit(A.cnt, A.caps)) {
     int* head = A.read_head + (i64)i * 8;
     for (int k = 0; k < 8; ++k) head[k] = 0;
     int* cn = A.clip_n + (i64)i * 2;
@@ -497,21 +516,45 @@ __global__ void __launch_bounds__(128) k_gap_prep(GapArgs A) {
 }
 
 // K11a': one thread per unaligned-gap record: "{l1}-{f2}:{size}" (:455-471)
-__global__ void k_gap_sizes(GapArgs A, int n_gaps) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_gaps) return;
-  int* rec = A.gap_rec + (i64)g * 3;
-  const int l1 = rec[0], f2 = rec[1], i = rec[2];
-  const int* fpos = A.final_pos + A.tint_final_off[A.read_tint[i]];
-  const int i0 = A.read_iv_off[i], i1 = A.read_iv_off[i + 1];
-  const int L = A.read_len[i];
-  int qa, sa, qb, sb;
-  if (!interval_end(A, i0, i1, fpos[l1 + 1], qa, sa)) { dev_fail(A.err, DEVERR_THREAD_CIGAR, i); return; }
-  if (!interval_start(A, i0, i1, fpos[f2], qb, sb)) { dev_fail(A.err, DEVERR_THREAD_CIGAR, i); return; }
-  if (!(0 < qa && qa <= qb && qb < L)) { dev_fail(A.err, DEVERR_GAP_RANGE, i); return; }
-  int size = max(0, qb - qa + sa + sb);
-  if (!(size < L)) { dev_fail(A.err, DEVERR_GAP_RANGE, i); return; }
-  rec[2] = size;
+__global__ void k_gap_sizes(GapArgs A) {
+  if (!gaps_fit(A.cnt, A.caps)) return;
+  const int n_gaps = (int)A.cnt[CNT_NGAP];  // device-side count: the launch is a grid-stride loop
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n_gaps; g += gridDim.x * blockDim.x) {
+    int* rec = A.gap_rec + (i64)g * 3;
+    const int l1 = rec[0], f2 = rec[1], i = rec[2];
+    if (i < 0 || i >= A.n_reads) continue;  // record of a read that failed an assert in k_gap_prep (never written)
+    const int* fpos = A.final_pos + A.tint_final_off[A.read_tint[i]];
+    const int i0 = A.read_iv_off[i], i1 = A.read_iv_off[i + 1];
+    const int L = A.read_len[i];
+    int qa, sa, qb, sb;
+    if (!interval_end(A, i0, i1, fpos[l1 + 1], qa, sa)) { dev_fail(A.err, DEVERR_THREAD_CIGAR, i); continue; }
+    if (!interval_start(A, i0, i1, fpos[f2], qb, sb)) { dev_fail(A.err, DEVERR_THREAD_CIGAR, i); continue; }
+    if (!(0 < qa && qa <= qb && qb < L)) { dev_fail(A.err, DEVERR_GAP_RANGE, i); continue; }
+    int size = max(0, qb - qa + sa + sb);
+    if (!(size < L)) { dev_fail(A.err, DEVERR_GAP_RANGE, i); continue; }
+    rec[2] = size;
+  }
+}
+
+// Lazy sequence mode: the poly-A/T scans only read the soft clips, a few per cent of the reads' bases, and
+// the clips are only known after segmentation.  The caller's bit-planes stay in (pinned, device-mapped)
+// HOST memory; one thread per needed plane word fetches it over the bus into the compact device arrays the
+// scan kernels read (clip k owns words [clip_off[k], clip_off[k+1])).  Neighbouring threads read
+// neighbouring words (the end clip of a read and the start clip of the next one are adjacent in the
+// planes), so the requests coalesce into whole sectors.  No host round trip, no host gather.
+__global__ void __launch_bounds__(256) k_clip_gather(GapArgs A, const u32* __restrict__ host_a, const u32* __restrict__ host_t,
+                                                     u32* __restrict__ out_a, u32* __restrict__ out_t) {
+  if (!clips_fit(A.cnt, A.caps)) return;
+  const i64 total = A.cnt[CNT_CLIPW];
+  const int n_clip = A.n_reads * 2;
+  for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (i64)gridDim.x * blockDim.x) {
+    const int k = upper_row64(A.clip_off, n_clip, j);  // clip that owns compact word j
+    const int i = k >> 1;
+    const ClipGeo g = clip_geometry(A.read_len[i], A.clip_n[k], (k & 1) == 0, A.read_strand[i] != 0);
+    const i64 src = A.read_seq_off[i] + g.w_first + (j - A.clip_off[k]);
+    out_a[j] = host_a[src];
+    out_t[j] = host_t[src];
+  }
 }
 
 // Scan-task filter, one thread per slot.  A run that find_longest_poly keeps has len >= 20 and at most
@@ -525,7 +568,7 @@ __global__ void __launch_bounds__(128) k_poly_filter(GapArgs A, u8* __restrict__
   for (int k = threadIdx.x; k < POLY_CLASSES; k += blockDim.x) sh_cnt[k] = 0;
   __syncthreads();
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot < A.n_reads * 4) {
+  if (slot < A.n_reads * 4 && clips_fit(A.cnt, A.caps)) {
     const int i = slot >> 2, which = slot & 3, clip = slot >> 1;
     const int n = A.clip_n[clip];
     bool pass = false;
@@ -572,9 +615,9 @@ __global__ void k_poly_bases(int* __restrict__ cls_count, int long_class, int* _
 }
 
 __global__ void k_poly_scatter(int n_slots, const int* __restrict__ clip_n, const u8* __restrict__ pass_flag,
-                               int* __restrict__ cls_count, int* __restrict__ order) {
+                               int* __restrict__ cls_count, int* __restrict__ order, const i64* __restrict__ cnt, Caps caps) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_slots || !pass_flag[s]) return;
+  if (s >= n_slots || !clips_fit(cnt, caps) || !pass_flag[s]) return;
   int c = poly_class_dev(clip_n[s >> 1]);
   // warp-aggregate the cursor bump of lanes that share a class
   unsigned peers = __match_any_sync(__activemask(), c);
@@ -589,7 +632,7 @@ __global__ void k_poly_scatter(int n_slots, const int* __restrict__ clip_n, cons
 __global__ void __launch_bounds__(128) k_poly_scan(GapArgs A) {
   // tasks of the long classes (front of the order) belong to k_poly_long
   const int e = A.cls_count[A.long_class - 1] + blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= A.cls_count[2 * POLY_CLASSES]) return;
+  if (e >= A.cls_count[2 * POLY_CLASSES] || !clips_fit(A.cnt, A.caps)) return;
   const int slot = A.task_order[e];
   const int i = slot >> 2, which = slot & 3;
   const int clip = slot >> 1;
@@ -679,7 +722,7 @@ __global__ void __launch_bounds__(128) k_poly_long(GapArgs A) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int n_long = A.cls_count[A.long_class - 1];
+  const int n_long = clips_fit(A.cnt, A.caps) ? A.cls_count[A.long_class - 1] : 0;
   for (int e = gw; e < n_long; e += nwarps) {
     const int slot = A.task_order[e];
     const int i = slot >> 2, which = slot & 3;
@@ -762,7 +805,7 @@ __global__ void __launch_bounds__(128) k_poly_long(GapArgs A) {
 // and write the final head fields (:407-420, :438-454).
 __global__ void k_gap_finish(GapArgs A) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= A.n_reads) return;
+  if (i >= A.n_reads || !clips_fit(A.cnt, A.caps)) return;
   int* head = A.read_head + (i64)i * 8;
   if (!(head[0] & 1)) return;
   const int L = A.read_len[i];

@@ -112,14 +112,13 @@ __global__ void __launch_bounds__(SIG_THREADS) k_signal(const SigWork* __restric
 //      1 <= a, b <= n-2, y[a-1] < y[m] > y[b+1], and m == (a+b)>>1.
 //   3. per 32 samples one ballot word of candidates and one of positive samples (the input of the
 //      variance threshold, :757-759), plus the two counts of the tile.
-// k_tile_lists then writes the ordered candidate list and the ordered positive samples from the
-// masks (its offsets come from a two-level sum of the tile counts, no device-wide scan).  HBM traffic
-// of the two: 4 B read + 8 B written per sample, 1/4 B of masks, and the positive samples once more.
+// A second phase of the same launch then writes the ordered candidate list and the ordered positive samples
+// from the masks (k_smooth_lists below).  HBM traffic: 4 B read + 8 B written per sample, 1/4 B of masks, and
+// the positive samples once more.
 // ---------------------------------------------------------------------------------------------
 #define TILE_SAMPLES 1024
 #define GAUSS_THREADS 128
 #define TILE_WORDS (TILE_SAMPLES / 32)
-#define TILE_GROUP 1024  // tiles per group of the two-level count prefix
 
 // lo = island-local first sample of the tile; f0 / n = first flat sample / length of the island (copied
 // here so that a CTA learns its geometry from ONE 16-byte load instead of a chain of two)
@@ -188,14 +187,42 @@ __device__ double gauss_global(const int* __restrict__ yr, int n, int x, const d
   return acc;
 }
 
-__global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __restrict__ tiles,
-                                                         const int* __restrict__ island_sample_off,
-                                                         const int* __restrict__ y_raw,
-                                                         const double* __restrict__ gw, int lw,
-                                                         double* __restrict__ y, u32* __restrict__ cmask,
-                                                         u32* __restrict__ pmask, u32* __restrict__ tile_cnt,
-                                                         unsigned long long* __restrict__ group_sum /* zeroed */) {
+// ---------------------------------------------------------------------------------------------
+// k_smooth_lists: ONE persistent, cooperative launch for steps 1-3 above AND the ordered lists.
+//   phase A  the CTAs take chunks of SM_CHUNK consecutive tiles from a cursor (work stealing: live and dead
+//            tiles differ in cost).  Per tile: stage the raw samples, Gaussian, candidate / positive ballot
+//            words, counts.  The Gaussian weights are loaded once per CTA, the loops over the 32-sample words
+//            stop at the end of the tile (a median island is half a tile).  A chunk publishes the totals of
+//            its tiles.
+//   barrier  every CTA of the grid is resident (cooperative launch): one counter.
+//   phase B  chunks again; the offsets of a chunk into the ordered candidate list and the ordered positive
+//            samples = sum of the totals of the chunks before it (one strided sum per chunk -- not per tile),
+//            then its tiles in order with running offsets.  The ballot words of phase A are still in L2.
+// Replaces the two launches k_smooth + k_tile_lists (one pass less over the tile descriptors and the counts,
+// no per-tile prefix over up to 1024 earlier tiles, no per-tile CTA launch).
+// ---------------------------------------------------------------------------------------------
+#define SM_CHUNK 16
+struct SmoothSync { int cursor_a; int arrived; int cursor_b; int pad; };  // zeroed before the launch
+
+__device__ __forceinline__ int ld_acquire_i32(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+#ifndef SMOOTH_MIN_CTAS
+#define SMOOTH_MIN_CTAS 12
+#endif
+__global__ void __launch_bounds__(GAUSS_THREADS, SMOOTH_MIN_CTAS) k_smooth_lists(
+    const TileWork* __restrict__ tiles, int n_tiles, const int* __restrict__ island_tint,
+    const int* __restrict__ tint_island_off, int n_tints, const int* __restrict__ y_raw, const double* __restrict__ gw,
+    int lw, double* __restrict__ y, u32* __restrict__ cmask, u32* __restrict__ pmask, u32* __restrict__ tile_cnt,
+    unsigned long long* __restrict__ chunk_tot, SmoothSync* __restrict__ sync, int* __restrict__ cand_flat,
+    double* __restrict__ vbuf, int* __restrict__ tint_pos_off, i64* __restrict__ n_cand_out) {
   extern __shared__ __align__(16) unsigned char p1sm[];
+  __shared__ int s_chunk;
+  __shared__ unsigned long long s_red64[GAUSS_THREADS / 32];
+  __shared__ int pre_c[TILE_WORDS], pre_p[TILE_WORDS];
   const P1Smem Lo = p1_smem_layout(lw);
   double* wd = (double*)(p1sm + Lo.wd);
   int* ext = (int*)(p1sm + Lo.ext);          // raw tile + halo (int32 counts)
@@ -203,193 +230,210 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __rest
   u32* nz = (u32*)(p1sm + Lo.nz);            // bit s: staged sample s is non-zero
   int* red = (int*)(p1sm + Lo.red);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const TileWork tw = tiles[blockIdx.x];
-  const int f0 = tw.f0;
-  const int n = tw.n;
-  const int cnt = min(TILE_SAMPLES, n - tw.lo);
-  const int* yr = y_raw + f0;
-  for (int d = tid; d <= lw; d += GAUSS_THREADS) wd[d] = gw[lw - d];
-  const int span = cnt + 2 * lw + 2;
-  const int first = tw.lo - lw - 1;
-  const int span_r = (span + GAUSS_THREADS - 1) / GAUSS_THREADS * GAUSS_THREADS;
-  const bool interior = first >= 0 && first + span <= n;
-  const int n2 = 2 * n;
-  for (int s = tid; s < span_r; s += GAUSS_THREADS) {  // whole warps: the ballot needs every lane
-    int v = 0;
-    if (s < span) {
-      const int j0 = first + s;
-      int j = j0;
-      if (!interior) {
-        // scipy's reflect (d c b a | a b c d | d c b a): one fold covers every island longer than the halo
-        if (j0 < 0) j = -1 - j0;
-        else if (j0 >= n) j = n2 - 1 - j0;
-        if ((unsigned)j >= (unsigned)n) {  // island shorter than the halo: general period-2n fold
-          j = j0 % n2;
-          if (j < 0) j += n2;
-          if (j >= n) j = n2 - 1 - j;
+  const int n_chunks = (n_tiles + SM_CHUNK - 1) / SM_CHUNK;
+  for (int d = tid; d <= lw; d += GAUSS_THREADS) wd[d] = gw[lw - d];  // once per CTA
+
+  // ================================ phase A ================================
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_chunk = atomicAdd(&sync->cursor_a, 1);
+    __syncthreads();
+    const int chunk = s_chunk;
+    if (chunk >= n_chunks) break;
+    const int t_lo = chunk * SM_CHUNK, t_hi = min(n_tiles, t_lo + SM_CHUNK);
+    u32 tot_c = 0, tot_p = 0;  // thread 0
+    for (int tile = t_lo; tile < t_hi; ++tile) {
+      const TileWork tw = tiles[tile];
+      const int f0 = tw.f0;
+      const int n = tw.n;
+      const int cnt = min(TILE_SAMPLES, n - tw.lo);
+      const int nwords = (cnt + 31) >> 5;
+      const int* yr = y_raw + f0;
+      const int span = cnt + 2 * lw + 2;
+      const int first = tw.lo - lw - 1;
+      const int span_r = (span + GAUSS_THREADS - 1) / GAUSS_THREADS * GAUSS_THREADS;
+      const bool interior = first >= 0 && first + span <= n;
+      const int n2 = 2 * n;
+      for (int s = tid; s < span_r; s += GAUSS_THREADS) {  // whole warps: the ballot needs every lane
+        int v = 0;
+        if (s < span) {
+          const int j0 = first + s;
+          int j = j0;
+          if (!interior) {
+            // scipy's reflect (d c b a | a b c d | d c b a): one fold covers every island longer than the halo
+            if (j0 < 0) j = -1 - j0;
+            else if (j0 >= n) j = n2 - 1 - j0;
+            if ((unsigned)j >= (unsigned)n) {  // island shorter than the halo: general period-2n fold
+              j = j0 % n2;
+              if (j < 0) j += n2;
+              if (j >= n) j = n2 - 1 - j;
+            }
+          }
+          v = yr[j];
+          ext[s] = v;
+        }
+        const u32 m = __ballot_sync(0xffffffffu, v != 0);
+        if (lane == 0) nz[s >> 5] = m;
+      }
+      if (tid < 2) nz[(span_r >> 5) + tid] = 0u;
+      __syncthreads();
+      // bit w of wm: mask word w of the staged window has a non-zero sample (at most 50 words at sigma = 50)
+      unsigned long long wm;
+      {
+        const int n_nz = (span_r >> 5) + 2;
+        const u32 lo32 = __ballot_sync(0xffffffffu, lane < n_nz && nz[lane] != 0u);
+        const u32 hi32 = __ballot_sync(0xffffffffu, 32 + lane < n_nz && nz[32 + lane] != 0u);
+        wm = ((unsigned long long)hi32 << 32) | lo32;
+      }
+      // ---- Gaussian: the words of the tile are dealt round-robin to the warps (a short tile keeps all four
+      // busy), 32 samples per step (coalesced 256-byte stores) ----
+      u32 live = 0;  // bit k: this warp's k-th word has a non-zero input near its window (else its y is all 0)
+      for (int wi = warp, k = 0; wi < nwords; wi += GAUSS_THREADS / 32, ++k) {
+        const int xb = wi * 32;
+        const int x = xb + lane;
+        // inputs of this step: staged samples [xb + 1, xb + 32 + 2*lw]; testing the whole mask words that
+        // hold them is conservative (a false positive only runs the sparse filter over zeros: same bits)
+        const int w_a = (xb + 1) >> 5, w_b = (xb + 32 + 2 * lw) >> 5;  // w_b - w_a <= 14
+        const bool any = ((wm >> w_a) & ((2ull << (w_b - w_a)) - 1ull)) != 0ull;
+        double v = 0.0;
+        if (any) {
+          live |= 1u << k;
+          if (x < cnt) v = gauss_sparse(ext, nz, wd, lw, lw + 1 + x);
+        }
+        if (x < cnt) {
+          y[f0 + tw.lo + x] = v;
+          yout[1 + x] = v;
         }
       }
-      v = yr[j];
-      ext[s] = v;
-    }
-    const u32 m = __ballot_sync(0xffffffffu, v != 0);
-    if (lane == 0) nz[s >> 5] = m;
-  }
-  if (tid < 2) nz[(span_r >> 5) + tid] = 0u;
-  __syncthreads();
-  // bit w of wm: mask word w of the staged window has a non-zero sample (at most 50 words at sigma = 50)
-  unsigned long long wm;
-  {
-    const int n_nz = (span_r >> 5) + 2;
-    const u32 lo32 = __ballot_sync(0xffffffffu, lane < n_nz && nz[lane] != 0u);
-    const u32 hi32 = __ballot_sync(0xffffffffu, 32 + lane < n_nz && nz[32 + lane] != 0u);
-    wm = ((unsigned long long)hi32 << 32) | lo32;
-  }
-  // ---- Gaussian: a warp owns 256 consecutive samples, 32 per step (coalesced 256-byte stores) ----
-  u32 live = 0;  // bit it: step `it` of this warp has a non-zero input near its window (else its y is all 0)
-  for (int it = 0; it < TILE_WORDS / 4; ++it) {
-    const int xb = warp * (TILE_SAMPLES / 4) + it * 32;
-    if (xb >= cnt) break;
-    const int x = xb + lane;
-    // inputs of this step: staged samples [xb + 1, xb + 32 + 2*lw]; testing the whole mask words that
-    // hold them is conservative (a false positive only runs the sparse filter over zeros: same bits)
-    const int w_a = (xb + 1) >> 5, w_b = (xb + 32 + 2 * lw) >> 5;  // w_b - w_a <= 14
-    const bool any = ((wm >> w_a) & ((2ull << (w_b - w_a)) - 1ull)) != 0ull;
-    double v = 0.0;
-    if (any) {
-      live |= 1u << it;
-      if (x < cnt) v = gauss_sparse(ext, nz, wd, lw, lw + 1 + x);
-    }
-    if (x < cnt) {
-      y[f0 + tw.lo + x] = v;
-      yout[1 + x] = v;
-    }
-  }
-  if (tid == GAUSS_THREADS - 2) yout[0] = gauss_sparse(ext, nz, wd, lw, lw);              // sample lo - 1
-  if (tid == GAUSS_THREADS - 1) yout[cnt + 1] = gauss_sparse(ext, nz, wd, lw, lw + 1 + cnt);  // sample lo + cnt
-  __syncthreads();
-  // ---- candidates and positives ----
-  auto Y = [&](int X) -> double {  // island-local sample, 0 <= X < n
-    const int x = X - tw.lo;
-    return (x >= -1 && x <= cnt) ? yout[1 + x] : gauss_global(yr, n, X, wd, lw);
-  };
-  int nc = 0, np = 0;
-  u32* cm_out = cmask + (size_t)blockIdx.x * TILE_WORDS;
-  u32* pm_out = pmask + (size_t)blockIdx.x * TILE_WORDS;
-  for (int it = 0; it < TILE_WORDS / 4; ++it) {
-    const int wi = warp * (TILE_WORDS / 4) + it;
-    const int x = wi * 32 + lane, X = tw.lo + x;
-    bool is_c = false, is_p = false;
-    if (x < cnt) is_c = (X == 0 || X == n - 1);
-    if (((live >> it) & 1u) && x < cnt) {  // the same warp smoothed these samples: a dead step is all zeros
-      const double v = yout[1 + x];
-      is_p = v > 0.0;
-      if (!is_c && is_p) {
-        const double l = yout[x], r = yout[x + 2];
-        if (l < v && r < v) is_c = true;
-        else if (!(l > v) && !(r > v)) {  // a neighbour equals v: walk the plateau
-          int a = X, b = X;
-          while (a - 1 >= 0 && Y(a - 1) == v) --a;
-          while (b + 1 <= n - 1 && Y(b + 1) == v) ++b;
-          if (a >= 1 && b <= n - 2 && Y(a - 1) < v && Y(b + 1) < v && X == ((a + b) >> 1)) is_c = true;
+      if (tid == GAUSS_THREADS - 2) yout[0] = gauss_sparse(ext, nz, wd, lw, lw);              // sample lo - 1
+      if (tid == GAUSS_THREADS - 1) yout[cnt + 1] = gauss_sparse(ext, nz, wd, lw, lw + 1 + cnt);  // sample lo + cnt
+      __syncthreads();
+      // ---- candidates and positives ----
+      auto Y = [&](int X) -> double {  // island-local sample, 0 <= X < n
+        const int x = X - tw.lo;
+        return (x >= -1 && x <= cnt) ? yout[1 + x] : gauss_global(yr, n, X, wd, lw);
+      };
+      int nc = 0, np = 0;
+      u32* cm_out = cmask + (size_t)tile * TILE_WORDS;
+      u32* pm_out = pmask + (size_t)tile * TILE_WORDS;
+      for (int wi = warp, k = 0; wi < nwords; wi += GAUSS_THREADS / 32, ++k) {
+        const int x = wi * 32 + lane, X = tw.lo + x;
+        bool is_c = false, is_p = false;
+        if (x < cnt) is_c = (X == 0 || X == n - 1);
+        if (((live >> k) & 1u) && x < cnt) {  // the same warp smoothed these samples: a dead step is all zeros
+          const double v = yout[1 + x];
+          is_p = v > 0.0;
+          if (!is_c && is_p) {
+            const double l = yout[x], r = yout[x + 2];
+            if (l < v && r < v) is_c = true;
+            else if (!(l > v) && !(r > v)) {  // a neighbour equals v: walk the plateau
+              int a = X, b = X;
+              while (a - 1 >= 0 && Y(a - 1) == v) --a;
+              while (b + 1 <= n - 1 && Y(b + 1) == v) ++b;
+              if (a >= 1 && b <= n - 2 && Y(a - 1) < v && Y(b + 1) < v && X == ((a + b) >> 1)) is_c = true;
+            }
+          }
         }
+        const u32 cm = __ballot_sync(0xffffffffu, is_c), pm = __ballot_sync(0xffffffffu, is_p);
+        if (lane == 0) { cm_out[wi] = cm; pm_out[wi] = pm; }
+        nc += __popc(cm);
+        np += __popc(pm);
+      }
+      if (lane == 0) red[warp] = nc | (np << 16);
+      __syncthreads();  // also: the next tile may overwrite ext / nz / yout
+      if (tid == 0) {
+        const u32 v = (u32)(red[0] + red[1] + red[2] + red[3]);  // candidates | positives << 16
+        tile_cnt[tile] = v;
+        tot_c += v & 0xffffu;
+        tot_p += v >> 16;
       }
     }
-    const u32 cm = __ballot_sync(0xffffffffu, is_c), pm = __ballot_sync(0xffffffffu, is_p);
-    if (lane == 0) { cm_out[wi] = cm; pm_out[wi] = pm; }
-    nc += __popc(cm);
-    np += __popc(pm);
+    if (tid == 0) chunk_tot[chunk] = ((unsigned long long)tot_p << 32) | (unsigned long long)tot_c;
   }
-  if (lane == 0) red[warp] = nc | (np << 16);
+
+  // ================================ grid barrier ================================
   __syncthreads();
   if (tid == 0) {
-    const u32 v = (u32)(red[0] + red[1] + red[2] + red[3]);  // candidates | positives << 16
-    tile_cnt[blockIdx.x] = v;
-    // totals of every group of TILE_GROUP consecutive tiles: positives << 32 | candidates
-    atomicAdd(&group_sum[blockIdx.x / TILE_GROUP], ((unsigned long long)(v >> 16) << 32) | (unsigned long long)(v & 0xffffu));
+    __threadfence();
+    atomicAdd(&sync->arrived, 1);
+    while (ld_acquire_i32(&sync->arrived) < (int)gridDim.x) __nanosleep(64);
+  }
+  __syncthreads();
+
+  // ================================ phase B ================================
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_chunk = atomicAdd(&sync->cursor_b, 1);
+    __syncthreads();
+    const int chunk = s_chunk;
+    if (chunk >= n_chunks) break;
+    // (candidates, positives) of the chunks before this one
+    unsigned long long sum = 0;
+    for (int k = tid; k < chunk; k += GAUSS_THREADS) sum += __ldcg(&chunk_tot[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_red64[warp] = sum;
+    __syncthreads();
+    const unsigned long long before = s_red64[0] + s_red64[1] + s_red64[2] + s_red64[3];
+    int off_c = (int)(before & 0xffffffffull), off_p = (int)(before >> 32);
+    const int t_lo = chunk * SM_CHUNK, t_hi = min(n_tiles, t_lo + SM_CHUNK);
+    for (int tile = t_lo; tile < t_hi; ++tile) {
+      const TileWork tw = tiles[tile];
+      const int cnt = min(TILE_SAMPLES, tw.n - tw.lo);
+      const int nwords = (cnt + 31) >> 5;
+      const u32* cm_in = cmask + (size_t)tile * TILE_WORDS;
+      const u32* pm_in = pmask + (size_t)tile * TILE_WORDS;
+      const u32 tc = __ldcg(&tile_cnt[tile]);
+      if (warp == 0) {
+        int c = lane < nwords ? __popc(__ldcg(&cm_in[lane])) : 0, p = lane < nwords ? __popc(__ldcg(&pm_in[lane])) : 0;
+        const int c0 = c, p0 = p;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int a = __shfl_up_sync(0xffffffffu, c, o), b = __shfl_up_sync(0xffffffffu, p, o);
+          if (lane >= o) { c += a; p += b; }
+        }
+        pre_c[lane] = c - c0;
+        pre_p[lane] = p - p0;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        if (tw.lo == 0) {
+          const int t = island_tint[tw.island];
+          if (tw.island == tint_island_off[t]) tint_pos_off[t] = off_p;
+        }
+        if (tile == n_tiles - 1) {
+          tint_pos_off[n_tints] = off_p + (int)(tc >> 16);
+          *n_cand_out = (i64)off_c + (i64)(tc & 0xffffu);
+        }
+      }
+      const int fbase = tw.f0 + tw.lo;
+      const u32 lt = (1u << lane) - 1u;
+      for (int wi = warp; wi < nwords; wi += GAUSS_THREADS / 32) {
+        const u32 cm = __ldcg(&cm_in[wi]), pm = __ldcg(&pm_in[wi]);
+        const int f = fbase + wi * 32 + lane;
+        if ((cm >> lane) & 1u) cand_flat[off_c + pre_c[wi] + __popc(cm & lt)] = f;
+        if ((pm >> lane) & 1u) vbuf[off_p + pre_p[wi] + __popc(pm & lt)] = __ldcg(&y[f]);
+      }
+      off_c += (int)(tc & 0xffffu);
+      off_p += (int)(tc >> 16);
+      __syncthreads();  // pre_c / pre_p are rewritten by the next tile
+    }
   }
 }
 
-// Ordered candidate list and ordered positive samples of one tile from its ballot words.  The tile's
-// offsets into the two lists = totals of the tile groups before its group (k_smooth's atomics) + counts
-// of the earlier tiles of its own group: at most (n_tiles / TILE_GROUP + TILE_GROUP) cached loads per
-// CTA instead of a device-wide scan.  Also: per-tint offsets of the positive list and the totals.
-__global__ void __launch_bounds__(GAUSS_THREADS) k_tile_lists(const TileWork* __restrict__ tiles, int n_tiles,
-                                                             const int* __restrict__ island_sample_off,
-                                                             const int* __restrict__ island_tint,
-                                                             const int* __restrict__ tint_island_off, int n_tints,
-                                                             const u32* __restrict__ cmask, const u32* __restrict__ pmask,
-                                                             const u32* __restrict__ tile_cnt,
-                                                             const unsigned long long* __restrict__ group_sum,
-                                                             const double* __restrict__ y, int* __restrict__ cand_flat,
-                                                             double* __restrict__ vbuf, int* __restrict__ tint_pos_off,
-                                                             i64* __restrict__ n_cand_out) {
-  __shared__ int pre_c[TILE_WORDS], pre_p[TILE_WORDS];
-  __shared__ unsigned long long red[GAUSS_THREADS / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tile = blockIdx.x;
-  const u32* cm_in = cmask + (size_t)tile * TILE_WORDS;
-  const u32* pm_in = pmask + (size_t)tile * TILE_WORDS;
-  // ---- (candidates, positives) before this tile ----
-  unsigned long long s = 0;
-  const int g = tile / TILE_GROUP;
-  for (int k = tid; k < g; k += GAUSS_THREADS) s += group_sum[k];
-  for (int k = g * TILE_GROUP + tid; k < tile; k += GAUSS_THREADS) {
-    const u32 v = tile_cnt[k];
-    s += ((unsigned long long)(v >> 16) << 32) | (unsigned long long)(v & 0xffffu);
+// after compaction: per candidate rank q -> island id, and the island / tint offset tables.  The number of
+// candidates is read on the device (grid-stride: the launch does not depend on it).
+__global__ void k_cand_meta(const int* __restrict__ cand_flat, const i64* __restrict__ n_cand_p,
+                            const int* __restrict__ island_sample_off, int n_islands, int* __restrict__ cand_island,
+                            int* __restrict__ island_cand_off) {
+  const int n_cand = (int)*n_cand_p;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q <= n_cand; q += gridDim.x * blockDim.x) {
+    if (q == n_cand) { island_cand_off[n_islands] = n_cand; break; }
+    int f = cand_flat[q];
+    int isl = upper_row(island_sample_off, n_islands, f);
+    cand_island[q] = isl;
+    if (f == island_sample_off[isl]) island_cand_off[isl] = q;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) red[warp] = s;
-  if (warp == 0) {
-    int c = __popc(cm_in[lane]), p = __popc(pm_in[lane]);
-    const int c0 = c, p0 = p;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int a = __shfl_up_sync(0xffffffffu, c, o), b = __shfl_up_sync(0xffffffffu, p, o);
-      if (lane >= o) { c += a; p += b; }
-    }
-    pre_c[lane] = c - c0;
-    pre_p[lane] = p - p0;
-  }
-  __syncthreads();
-  const unsigned long long before = red[0] + red[1] + red[2] + red[3];
-  const int off_c = (int)(before & 0xffffffffull), off_p = (int)(before >> 32);
-  const TileWork tw = tiles[tile];
-  if (tid == 0) {
-    if (tw.lo == 0) {
-      const int t = island_tint[tw.island];
-      if (tw.island == tint_island_off[t]) tint_pos_off[t] = off_p;
-    }
-    if (tile == n_tiles - 1) {
-      const u32 v = tile_cnt[tile];
-      tint_pos_off[n_tints] = off_p + (int)(v >> 16);
-      *n_cand_out = (i64)off_c + (i64)(v & 0xffffu);
-    }
-  }
-  const int fbase = tw.f0 + tw.lo;
-  const u32 lt = (1u << lane) - 1u;
-  for (int it = 0; it < TILE_WORDS / 4; ++it) {
-    const int wi = warp * (TILE_WORDS / 4) + it;
-    const u32 cm = cm_in[wi], pm = pm_in[wi];
-    const int f = fbase + wi * 32 + lane;
-    if ((cm >> lane) & 1u) cand_flat[off_c + pre_c[wi] + __popc(cm & lt)] = f;
-    if ((pm >> lane) & 1u) vbuf[off_p + pre_p[wi] + __popc(pm & lt)] = y[f];
-  }
-}
-
-// after compaction: per candidate rank q -> island id, and the island / tint offset tables
-__global__ void k_cand_meta(const int* __restrict__ cand_flat, int n_cand, const int* __restrict__ island_sample_off,
-                            int n_islands, int* __restrict__ cand_island, int* __restrict__ island_cand_off) {
-  int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n_cand) {
-    if (q == n_cand) island_cand_off[n_islands] = n_cand;
-    return;
-  }
-  int f = cand_flat[q];
-  int isl = upper_row(island_sample_off, n_islands, f);
-  cand_island[q] = isl;
-  if (f == island_sample_off[isl]) island_cand_off[isl] = q;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -158,6 +158,36 @@ class Engine:
         sizes = self.run(prm)
         return self.download(sizes, pinned)
 
+    # -- pipelined form: two batches in flight, one host thread -------------------------------
+    def submit(self, batch: PackedBatch, prm: SegmentParams) -> int:
+        """Enqueues the copies and every kernel of ``batch`` and returns a ticket at once; the batch's
+        arrays must stay alive until ``wait`` has returned for that ticket."""
+        b = batch.as_struct()
+        p = prm.as_struct()
+        t = C.c_int(-1)
+        self._check(self.lib.frs_submit(self.ctx, C.byref(b), C.byref(p), C.byref(t)))
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[t.value] = (batch, prm)
+        self._batch = batch
+        return t.value
+
+    def wait(self, ticket: int) -> "_lib.FrsResultSizes":
+        sizes = _lib.FrsResultSizes()
+        self._check(self.lib.frs_wait(self.ctx, ticket, C.byref(sizes)))
+        return sizes
+
+    def fetch(self, ticket: int, res: "BatchResult") -> "BatchResult":
+        """Copies the results of ``ticket`` into ``res`` (sized from ``wait``'s answer) and frees the ticket."""
+        r = res.as_struct()
+        try:
+            self._check(self.lib.frs_fetch(self.ctx, ticket, C.byref(r)))
+        finally:
+            self._inflight.pop(ticket, None)
+        return res
+
+    def new_result(self, sizes, batch: PackedBatch, pinned: bool = False) -> "BatchResult":
+        return BatchResult(sizes, batch.n_tints, batch.n_reads, pinned)
+
     # -- instrumentation ----------------------------------------------------------------------
     def set_profiling(self, on: bool):
         self.lib.frs_set_profiling(self.ctx, int(on))

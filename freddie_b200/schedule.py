@@ -22,6 +22,14 @@ def estimate_cost(n_reads: float) -> float:
     return n_reads * (1.0 + k / 50.0)
 
 
+def estimate_device_bytes(n_reads: float) -> float:
+    """Rough device footprint of a tint inside a batch: packed inputs and per-read results (~2 KB per read
+    with resident sequence planes), the coverage matrix 4 x candidates x reps and the digit matrix
+    reps x segments -- the two blocks that grow faster than linearly with the tint."""
+    k = min(n_reads, 40000.0) / 40.0 + 20.0
+    return n_reads * 2048.0 + 4.0 * k * n_reads + n_reads * (k + 64.0)
+
+
 def estimate_cost_from_files(split_dir: str, contig: str, tint_id: int) -> Tuple[float, float]:
     """(cost, estimated reads) from the split file size alone -- no parsing."""
     p = "{}/{}/split_{}_{}.tsv".format(split_dir, contig, contig, tint_id)
@@ -46,17 +54,21 @@ def lpt_partition(costs: Sequence[Tuple[float, float]], n_bins: int) -> List[Lis
     return bins
 
 
-def batches(jobs: Sequence, costs: Sequence[Tuple[float, float]], batch_reads: int) -> Iterable[List]:
-    """Consecutive jobs grouped so that the estimated reads of a batch stay under ``batch_reads``
-    (a single larger tint forms its own batch)."""
+def batches(jobs: Sequence, costs: Sequence[Tuple[float, float]], batch_reads: int,
+            batch_bytes: Optional[float] = None) -> Iterable[List]:
+    """Consecutive jobs grouped so that the estimated reads of a batch stay under ``batch_reads`` and, with
+    ``batch_bytes``, its estimated device footprint (``estimate_device_bytes``) under that many bytes.  A
+    single tint above either bound forms its own batch -- a tint is never split."""
     cur: List = []
-    acc = 0.0
+    acc, mem = 0.0, 0.0
     for job, (_, n) in zip(jobs, costs):
-        if cur and acc + n > batch_reads:
+        m = estimate_device_bytes(n)
+        if cur and (acc + n > batch_reads or (batch_bytes is not None and mem + m > batch_bytes)):
             yield cur
-            cur, acc = [], 0.0
+            cur, acc, mem = [], 0.0, 0.0
         cur.append(job)
         acc += n
+        mem += m
     if cur:
         yield cur
 

@@ -7,14 +7,15 @@ Same CLI, same SPLIT-in / SEGMENT-out formats, same in-process seam::
             max_problem_size, min_read_support_outside, ignore_ends)          (reference :738-747)
 
 but every step of the hot path runs in the CUDA kernels of ``libfreddie_b200.so`` for a whole batch of
-tints at a time.  Tints are bin-packed by estimated cost across the visible GPUs (one host thread and
-one library context per GPU, no collective), batches are bounded by a memory estimate, and the host
-side only parses, packs and formats.  New flags are additive (``--gpus``, ``--batch-reads``); ``-t``
+tints at a time.  Tints are bin-packed by estimated cost across the visible GPUs (two host threads with
+one library context each per GPU, no collective), batches are bounded by a read count and by an estimate
+of their device footprint against the GPU's free memory, and the host side only parses, packs and formats.  New flags are additive (``--gpus``, ``--batch-reads``); ``-t``
 keeps its meaning of host worker threads (parsing / formatting).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import glob
 import os
 import re
@@ -242,6 +243,12 @@ def run_directory(split_dir: str, outdir: str, prm: SegmentParams, threads: int 
     else:
         costs = [schedule.estimate_cost_from_files(split_dir, c, t) for c, t in jobs]
     shards = schedule.lpt_partition(costs, n_gpus)
+    # a batch may take about a third of the free device memory of its GPU (two lanes per GPU in flight)
+    free_b = C.c_longlong(0)
+    total_b = C.c_longlong(0)
+    batch_bytes = None
+    if lib.frs_mem_info(0, C.byref(free_b), C.byref(total_b)) == 0 and free_b.value > 0:
+        batch_bytes = free_b.value / (1.5 * max(1, lanes))
     done = [0]
     total = len(jobs)
     step = max(1, ceil(total / 100)) if total else 1
@@ -264,7 +271,8 @@ def run_directory(split_dir: str, outdir: str, prm: SegmentParams, threads: int 
     else:
         feeds = [schedule.BatchFeed([], [], batch_reads,
                                     ready=((chunk, None) for chunk in schedule.batches(
-                                        [jobs[i] for i in shards[d]], [costs[i] for i in shards[d]], batch_reads)))
+                                        [jobs[i] for i in shards[d]], [costs[i] for i in shards[d]], batch_reads,
+                                        batch_bytes)))
                  for d in range(n_gpus)]
 
     seg_index: List[dict] = []

@@ -451,6 +451,20 @@ def iter_config(cfg: int, scale: float = 1.0, seed: Optional[int] = None, worker
             pool.join()
 
 
+def run_jobs(jobs: Sequence[tuple], workers: int = 1) -> List[dict]:
+    """The tints of ``jobs`` (``config_jobs`` entries), generated by a process pool, in job order."""
+    if workers > 1 and len(jobs) > 1:
+        from multiprocessing import Pool
+        order = sorted(range(len(jobs)), key=lambda k: -jobs[k][3])
+        with Pool(workers) as p:
+            res = p.map(_tint_job, [jobs[k] for k in order], chunksize=1 if len(jobs) < 256 else 8)
+        out = [None] * len(jobs)
+        for k, r in zip(order, res):
+            out[k] = r
+        return out
+    return [_tint_job(j) for j in jobs]
+
+
 def _write_job(arg):
     job, split_dir = arg
     t = _tint_job(job)
@@ -594,6 +608,8 @@ GOLDEN_SETS = {
     "degenerate": (dict(special="degenerate"), []),
     "plateau": (dict(special="plateau"), []),
     "refine_tie": (dict(special="refine_tie"), ["-vf", "9.9", "-lo", "100000"]),
+    "cfg2_mps9": (dict(cfg=2, scale=0.004, seed=16), ["-mps", "9", "-vf", "9.5"]),
+    "empty_tint": (dict(special="empty_tint"), []),
 }
 
 
@@ -611,4 +627,10 @@ def make_golden_set(name: str) -> Tuple[List[dict], List[str]]:
         return [make_plateau_tint()], flags
     if kw.get("special") == "refine_tie":
         return [make_refine_tie_tint()], flags
+    if kw.get("special") == "empty_tint":
+        # a tint without reads between two ordinary ones: the reference writes a header-only SEGMENT file
+        # whose positions are the ends of the islands (NaN threshold, no candidates but the ends)
+        return [make_plateau_tint("chrE", 0),
+                dict(id=1, chr="chrE", intervals=[(5000, 5400), (6000, 6100)], read_count=0, reads=[]),
+                make_refine_tie_tint("chrE", 2)], flags
     return make_config(**kw), flags

@@ -11,7 +11,7 @@
  *
  * Conventions: every function returns 0 on success, <0 on error (message via frs_last_error).  The
  * caller owns every host buffer; the library keeps no host pointer after a call returns.  One context
- * per GPU, used by one host thread at a time; all device work is ordered on the context's stream.
+ * per GPU, used by one host thread at a time; all device work is ordered on the context's streams.
  * No torch types, no C++ types.  There is NO CPU fallback: without a CUDA device frs_create fails.
  */
 #ifndef FREDDIE_B200_H
@@ -131,14 +131,16 @@ typedef struct {
 /* ---- context ---- */
 int frs_abi_version(void);
 int frs_device_count(void);
+/* free / total device memory in bytes (the directory driver bounds its batches with it) */
+int frs_mem_info(int device, long long* free_bytes, long long* total_bytes);
 int frs_create(int device, frs_context** out);
 void frs_destroy(frs_context* ctx);
 const char* frs_last_error(const frs_context* ctx); /* ctx may be NULL: last global error */
 void* frs_stream(frs_context* ctx);                 /* cudaStream_t of the context */
 
 /* ---- the hot path (replaces segment(), freddie_segment.py:738-844, for a batch of tints) ---- */
-/* H2D copy of the batch (async on the context stream; host arrays may be pinned or pageable).  With
- * FRS_OPT_LAZY_SEQ (default) the two sequence bit-planes are not copied here, see the option. */
+/* H2D copy of the batch (host arrays may be pinned or pageable); returns when the arrays have been read.
+ * With FRS_OPT_LAZY_SEQ (default) pinned sequence bit-planes are not copied here, see the option. */
 int frs_upload(frs_context* ctx, const frs_batch* batch);
 /* Runs every kernel of the pipeline on the uploaded batch; may be called repeatedly. */
 int frs_run(frs_context* ctx, const frs_params* prm, frs_result_sizes* sizes);
@@ -148,6 +150,20 @@ int frs_download(frs_context* ctx, const frs_result* out);
  * upload+run and leaves the download to the caller once it has sized its buffers. */
 int frs_segment_batch(frs_context* ctx, const frs_batch* batch, const frs_params* prm,
                       frs_result_sizes* sizes);
+
+/* ---- the same hot path, pipelined: up to two batches in flight per context, driven by ONE host thread.
+ * The reference overlaps tints with a process pool (imap_unordered, freddie_segment.py:871-876); here the
+ * copy of batch k+1 and the read-back of batch k-1 overlap the kernels of batch k on the copy engines.
+ *   frs_submit  enqueues the host-to-device copies and every kernel of the run and returns at once (no
+ *               host round trip inside a run: all counts stay on the device).  The batch arrays (and with
+ *               FRS_OPT_LAZY_SEQ the two sequence planes) must stay valid until frs_wait returns.
+ *   frs_wait    blocks until the run is complete and returns the result sizes (if a data-dependent buffer
+ *               was too small it is grown and the run repeated first: first batches of a context only).
+ *   frs_fetch   copies the results into caller buffers, blocks until they have arrived, frees the ticket.
+ * Tickets are slots: at most two may be outstanding, and they complete in submission order. */
+int frs_submit(frs_context* ctx, const frs_batch* batch, const frs_params* prm, int* ticket);
+int frs_wait(frs_context* ctx, int ticket, frs_result_sizes* sizes);
+int frs_fetch(frs_context* ctx, int ticket, const frs_result* out);
 
 /* ---- debug taps for per-step parity tests (values of the LAST frs_run) ---- */
 enum {
@@ -180,19 +196,22 @@ enum {
   FRS_OPT_KEEP_DP_TABLES = 2, /* also store the on-chip ins/out tables of small tints for FRS_TAP_DP_TABLES */
   FRS_OPT_POLY_LONG_CLASS = 3, /* length class (4 per octave: 36 = 512 bases, default) from which a poly-A/T
                                  clip scan is done by a whole warp instead of one thread; 1 = every scan */
-  FRS_OPT_LAZY_SEQ = 4,       /* 1 (default): frs_upload does NOT copy the sequence bit-planes; frs_run reads the
-                                 clip lengths back after segmentation, gathers only the plane words of the
-                                 soft-clips from the caller's seq_is_a / seq_is_t and uploads those.  The two
-                                 host arrays must then stay valid until frs_run returns.
-                                 0: frs_upload copies both planes whole (inputs fully resident in HBM). */
+  FRS_OPT_LAZY_SEQ = 4,       /* 1 (default): when the caller's seq_is_a / seq_is_t are pinned (or registered) host
+                                 memory, frs_upload does NOT copy them; after segmentation a kernel fetches only
+                                 the plane words of the soft clips straight from that memory (a few per cent of
+                                 the bases).  The two arrays must then stay valid until the run has finished.
+                                 Pageable planes are copied whole.
+                                 0: frs_upload always copies both planes whole (inputs fully resident in HBM). */
 };
 int frs_set_option(frs_context* ctx, int key, long long value);
 
 /* transfer statistics of the last frs_upload / frs_run; returns the number of statistics */
-#define FRS_N_STATS 7
-enum { FRS_STAT_H2D_UPLOAD = 0, FRS_STAT_H2D_RUN = 1, FRS_STAT_D2H_RUN = 2, FRS_STAT_CLIP_WORDS = 3,
+#define FRS_N_STATS 8
+enum { FRS_STAT_H2D_UPLOAD = 0, FRS_STAT_H2D_RUN = 1 /* bytes the device fetched from the caller's pinned planes */,
+       FRS_STAT_D2H_RUN = 2, FRS_STAT_CLIP_WORDS = 3,
        FRS_STAT_SEQ_WORDS = 4, FRS_STAT_POLY_TASKS = 5 /* poly-A/T scan tasks that survived the 5-stretch filter */,
-       FRS_STAT_POLY_LONG_TASKS = 6 /* of which scanned by a whole warp */ };
+       FRS_STAT_POLY_LONG_TASKS = 6 /* of which scanned by a whole warp */,
+       FRS_STAT_RERUNS = 7 /* runs of this context repeated because a buffer capacity was missed */ };
 int frs_get_stats(frs_context* ctx, long long* out, int n);
 
 /* ---- per-kernel device timing of the last frs_run (CUDA events on the context stream) ---- */

@@ -15,7 +15,7 @@ from oracle import segment_oracle as orc
 pytestmark = pytest.mark.gpu
 
 ALL_SETS = ["degenerate", "plateau", "cfg1", "cfg2_small", "cfg2_flagsA", "cfg2_flagsB", "cfg2_sigma50",
-            "cfg2_mps11", "dup_heavy", "cfg3_mini", "cfg4_mini", "cfg5_mini", "refine_tie"]
+            "cfg2_mps11", "dup_heavy", "cfg3_mini", "cfg4_mini", "cfg5_mini", "refine_tie", "cfg2_mps9", "empty_tint"]
 
 
 @pytest.fixture(scope="module")
@@ -48,7 +48,7 @@ def test_segment_text_equals_oracle(name, golden_set, eng):
 
 
 @pytest.mark.parametrize("name", ["degenerate", "plateau", "cfg2_small", "cfg2_flagsA", "cfg2_flagsB", "cfg4_mini",
-                                  "dup_heavy", "cfg2_sigma50", "cfg2_mps11", "refine_tie"])
+                                  "dup_heavy", "cfg2_sigma50", "cfg2_mps11", "refine_tie", "cfg2_mps9", "empty_tint"])
 def test_cli_directory_equals_reference_manifest(name, golden_set, manifest, tmp_path):
     """The drop-in CLI (native parser + kernels + native formatter) against the SHA-256 manifest of the
     SEGMENT directory the unmodified reference wrote for the same SPLIT directory."""
@@ -230,25 +230,111 @@ def test_warp_poly_scan_equals_thread_scan(name, golden_set, eng):
 
 
 @pytest.mark.parametrize("name", ["cfg1", "degenerate", "cfg2_small", "cfg4_mini"])
-def test_lazy_clip_upload_equals_resident_planes(name, golden_set, eng):
-    """Default mode uploads only the soft-clip words of the sequence bit-planes (gathered by the host
-    after segmentation); with the planes fully resident the results must be identical."""
+def test_lazy_clip_fetch_equals_resident_planes(name, golden_set, eng):
+    """Default mode with PINNED sequence planes: nothing of them is uploaded; after segmentation a kernel
+    fetches only the soft-clip words straight from the caller's host memory.  With the planes fully
+    resident (pageable arrays, or FRS_OPT_LAZY_SEQ = 0) the results must be identical."""
     from freddie_b200 import _lib
     from freddie_b200.pack import pack_tints
     tints, flags, _ = golden_set(name)
     _, gprm = _params(flags)
-    batch = pack_tints(tints)
-    lazy = eng.segment_batch(batch, gprm)
+    pinned = pack_tints(tints).pin()
+    lazy = eng.segment_batch(pinned, gprm)
     st = eng.stats()
-    assert st["clip_words"] <= st["seq_words"] and st["h2d_run"] >= 8 * st["clip_words"]
+    assert 0 < st["clip_words"] <= st["seq_words"] and st["h2d_run"] == 8 * st["clip_words"]
+    h_lazy = st["h2d_upload"]
     try:
         eng.set_option(_lib.OPT_LAZY_SEQ, 0)
-        full = eng.segment_batch(batch, gprm)
-        assert eng.stats()["h2d_run"] == 0
+        full = eng.segment_batch(pinned, gprm)
+        st = eng.stats()
+        assert st["h2d_run"] == 0 and st["h2d_upload"] == h_lazy + 8 * st["seq_words"]
     finally:
         eng.set_option(_lib.OPT_LAZY_SEQ, 1)
+    pageable = eng.segment_batch(pack_tints(tints), gprm)  # pageable planes are copied whole
+    assert eng.stats()["h2d_run"] == 0
     for k in lazy.arrays:
         assert np.array_equal(lazy.arrays[k], full.arrays[k]), (name, k)
+        assert np.array_equal(lazy.arrays[k], pageable.arrays[k]), (name, k)
+
+
+def test_pipelined_submit_wait_fetch_equals_the_synchronous_calls(golden_set):
+    """frs_submit / frs_wait / frs_fetch: two batches in flight in ONE context (the copies of one overlap the
+    kernels of the other); results must be those of upload + run + download, in any interleaving."""
+    from freddie_b200 import _lib
+    from freddie_b200.engine import Engine
+    from freddie_b200.pack import pack_tints
+    names = ["cfg2_small", "cfg4_mini", "cfg5_mini", "dup_heavy", "cfg1"]
+    batches, prms, want = [], [], []
+    ref = Engine(0)
+    for nme in names:
+        tints, flags, _ = golden_set(nme)
+        _, gprm = _params(flags)
+        b = pack_tints(tints).pin()
+        batches.append(b)
+        prms.append(gprm)
+        want.append(ref.segment_batch(b, gprm))
+    ref.close()
+    e = Engine(0)  # fresh context: its first runs also exercise the grow-and-repeat path of the capacities
+    try:
+        got = [None] * len(names)
+        t_prev = None
+        for k in range(len(names) + 1):
+            t_new = e.submit(batches[k], prms[k]) if k < len(names) else None
+            if t_prev is not None:
+                sizes = e.wait(t_prev)
+                got[k - 1] = e.fetch(t_prev, e.new_result(sizes, batches[k - 1], pinned=True))
+            t_prev = t_new
+        for k, nme in enumerate(names):
+            for a in want[k].arrays:
+                assert np.array_equal(want[k].arrays[a], got[k].arrays[a]), (nme, a)
+            assert want[k].sizes == got[k].sizes
+        # a third submit without a fetch is refused; so is a fetch of a free ticket
+        t0 = e.submit(batches[0], prms[0])
+        t1 = e.submit(batches[1], prms[1])
+        with pytest.raises(_lib.FrsError, match="in flight"):
+            e.submit(batches[2], prms[2])
+        s0, s1 = e.wait(t0), e.wait(t1)
+        r1 = e.fetch(t1, e.new_result(s1, batches[1]))
+        r0 = e.fetch(t0, e.new_result(s0, batches[0]))
+        assert all(np.array_equal(r0.arrays[a], want[0].arrays[a]) for a in r0.arrays)
+        assert all(np.array_equal(r1.arrays[a], want[1].arrays[a]) for a in r1.arrays)
+        with pytest.raises(_lib.FrsError, match="no batch in flight"):
+            e.fetch(t0, r0)
+        # the synchronous calls still work on the same context afterwards
+        again = e.segment_batch(batches[3], prms[3])
+        assert all(np.array_equal(again.arrays[a], want[3].arrays[a]) for a in again.arrays)
+    finally:
+        e.close()
+
+
+def test_capacity_miss_repeats_the_run(golden_set):
+    """Data-dependent buffers (coverage, DP tables, digits, runs, gaps, clip words) are sized from capacities
+    that only grow; a fresh context meets a batch whose needs exceed its first guesses, repeats the run with
+    larger buffers (no host round trip inside a run) and returns the same results."""
+    from freddie_b200 import _lib
+    from freddie_b200.engine import Engine
+    from freddie_b200.pack import pack_tints
+    tints, flags, _ = golden_set("cfg3_mini")
+    _, gprm = _params(flags)
+    small, _, _ = golden_set("degenerate")
+    e = Engine(0)
+    try:
+        e.set_option(_lib.OPT_SLAB_WORDS, 2)   # multi-CTA DP: global tables, many work items
+        e.segment_batch(pack_tints(small), gprm)
+        first = e.segment_batch(pack_tints(tints).pin(), gprm)
+        assert e.stats()["reruns"] >= 1
+        n = e.stats()["reruns"]
+        second = e.segment_batch(pack_tints(tints).pin(), gprm)
+        assert e.stats()["reruns"] == n           # capacities are warm now
+        for k in first.arrays:
+            assert np.array_equal(first.arrays[k], second.arrays[k]), k
+    finally:
+        e.close()
+    ref = Engine(0)
+    want = ref.segment_batch(pack_tints(tints), gprm)
+    ref.close()
+    for k in want.arrays:
+        assert np.array_equal(first.arrays[k], want.arrays[k]), k
 
 
 @pytest.mark.parametrize("name", ["cfg1", "degenerate", "dup_heavy", "cfg3_mini", "cfg5_mini"])
@@ -338,7 +424,7 @@ def test_errors_are_loud(golden_set, eng):
     from freddie_b200.pack import pack_tints
     tints, _, _ = golden_set("plateau")
     batch = pack_tints(tints)
-    with pytest.raises(_lib.FrsError, match="max_problem_size < 11"):
+    with pytest.raises(_lib.FrsError, match="max_problem_size < 9"):
         eng.segment_batch(batch, SegmentParams(max_problem_size=4))
     bad = pack_tints(tints)
     bad.arrays["read_rep"][0] = 10 ** 6

@@ -8,7 +8,7 @@ import pytest
 from conftest import GOLDEN, digest, flags_to_kwargs, sha_dir
 from oracle import segment_oracle as orc
 
-FAST_SETS = ["degenerate", "plateau", "cfg2_flagsA", "cfg2_small", "cfg4_mini", "cfg5_mini", "refine_tie"]
+FAST_SETS = ["degenerate", "plateau", "cfg2_flagsA", "cfg2_small", "cfg4_mini", "cfg5_mini", "refine_tie", "cfg2_mps9", "empty_tint"]
 
 
 @pytest.mark.parametrize("name", FAST_SETS)
