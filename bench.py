@@ -410,15 +410,31 @@ def run_cuda_arm(args):
     d2h = int(sum(v.nbytes for r in res_lazy for v in r.arrays.values())) + len(batches) * 48 * 8
 
     def pipelined(e2, bufs, work):
-        """work: list of batch indices in order; returns when everything has been fetched."""
-        prev = None
-        for n, i in enumerate(work + [None]):
-            tk = e2.submit(batches[i], prm) if i is not None else None
-            if prev is not None:
-                pt, pi, pn = prev
+        """work: list of batch indices in order.  Three batches in flight (copy in | kernels | copy out); the host
+        thread only ever blocks in frs_wait: the read-back of a batch is started (frs_fetch_start) and collected
+        one iteration later (frs_fetch_finish), behind the submit of the next batch."""
+        from collections import deque
+        fly = deque()
+        pending = None
+        for n, i in enumerate(work):
+            if pending is not None:
+                e2.fetch_finish(pending)
+                pending = None
+            fly.append((e2.submit(batches[i], prm), i, n))
+            if len(fly) == 3:
+                pt, pi, pn = fly.popleft()
                 e2.wait(pt)
-                e2.fetch(pt, bufs[pn & 1][pi])
-            prev = (tk, i, n) if i is not None else None
+                e2.fetch_start(pt, bufs[pn & 1][pi])
+                pending = pt
+        while fly:
+            if pending is not None:
+                e2.fetch_finish(pending)
+            pt, pi, pn = fly.popleft()
+            e2.wait(pt)
+            e2.fetch_start(pt, bufs[pn & 1][pi])
+            pending = pt
+        if pending is not None:
+            e2.fetch_finish(pending)
 
     def serial(e2, bufs, work):
         for n, i in enumerate(work):
@@ -523,7 +539,7 @@ def run_cuda_arm(args):
                      e2e_ms_per_gpu=[round(x * 1e3, 4) for x in busy_e2e], e2e_max_over_mean=round(max(busy_e2e) / mean(busy_e2e), 4)),
         e2e=dict(value=e2e_v, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                  timing="wall clock around K steps, synchronize on both sides; frs_submit / frs_wait / frs_fetch with pinned "
-                        "host buffers, two batches in flight per context",
+                        "host buffers, three batches in flight per context (copy in | kernels | copy out)",
                  one_context_value=tot_reads * args.steps / t_pipe1,
                  contexts_value=tot_reads * args.steps / t_pipe2, contexts=n_ctx,
                  serial_value=tot_reads * args.steps / t_serial,

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfreddie_b200.so")
+LIB_PATH = os.environ.get("FRS_LIB") or os.path.join(_HERE, "libfreddie_b200.so")  # FRS_LIB: development builds
 
 FRS_MAX_STAGES = 32
 
@@ -100,6 +100,8 @@ def load():
     lib.frs_submit.argtypes = [_p, C.POINTER(FrsBatch), C.POINTER(FrsParams), C.POINTER(C.c_int)]
     lib.frs_wait.argtypes = [_p, C.c_int, C.POINTER(FrsResultSizes)]
     lib.frs_fetch.argtypes = [_p, C.c_int, C.POINTER(FrsResult)]
+    lib.frs_fetch_start.argtypes = [_p, C.c_int, C.POINTER(FrsResult)]
+    lib.frs_fetch_finish.argtypes = [_p, C.c_int]
     lib.frs_get_intermediate.argtypes = [_p, C.c_int, _p, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.frs_set_profiling.argtypes = [_p, C.c_int]
     lib.frs_get_timings.argtypes = [_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_int)]
@@ -108,7 +110,7 @@ def load():
     lib.frs_get_stats.argtypes = [_p, C.POINTER(C.c_longlong), C.c_int]
     lib.frs_get_stats.restype = C.c_int
     for fn in ("frs_create", "frs_upload", "frs_run", "frs_download", "frs_segment_batch", "frs_get_intermediate",
-               "frs_submit", "frs_wait", "frs_fetch",
+               "frs_submit", "frs_wait", "frs_fetch", "frs_fetch_start", "frs_fetch_finish",
                "frs_set_profiling", "frs_get_timings", "frs_last_launch_count", "frs_set_option"):
         getattr(lib, fn).restype = C.c_int
     if hasattr(lib, "frs_parse_tints"):
@@ -136,7 +138,8 @@ def load():
 
 EXPORTED = [
     "frs_abi_version", "frs_device_count", "frs_mem_info", "frs_create", "frs_destroy", "frs_last_error", "frs_stream",
-    "frs_upload", "frs_run", "frs_download", "frs_segment_batch", "frs_submit", "frs_wait", "frs_fetch",
+    "frs_upload", "frs_run", "frs_download", "frs_segment_batch", "frs_submit", "frs_wait", "frs_fetch", "frs_fetch_start",
+    "frs_fetch_finish",
     "frs_get_intermediate", "frs_set_profiling",
     "frs_get_timings", "frs_last_launch_count", "frs_set_option", "frs_get_stats", "frs_parse_tints", "frs_parsed_batch", "frs_parsed_free",
     "frs_format_tints", "frs_packed_write", "frs_packed_read", "frs_packed_write_segment",

@@ -78,6 +78,27 @@ __device__ __forceinline__ void length_cuts(int len, const double* __restrict__ 
   tn = d - 1;
 }
 
+// The cuts depend on the length alone: a table for the lengths below CUT_TAB_N (one tiny launch per run)
+// replaces the fp64 divides in the kernels that need cuts per candidate pair / per segment.
+#define CUT_TAB_N 8192
+__global__ void k_cut_table(const double* __restrict__ tbl, int tbl_len, double tp, int2* __restrict__ cut_tab) {
+  const int len = blockIdx.x * blockDim.x + threadIdx.x;
+  if (len >= CUT_TAB_N) return;
+  int ty = 0x7fffffff, tn = -1;
+  if (len >= 1) length_cuts(len, tbl, tbl_len, tp, ty, tn);
+  cut_tab[len] = make_int2(ty, tn);
+}
+__device__ __forceinline__ void length_cuts_t(int len, const int2* __restrict__ cut_tab, const double* __restrict__ tbl,
+                                              int tbl_len, double tp, int& ty, int& tn) {
+  if (len >= 1 && len < CUT_TAB_N) {
+    const int2 v = __ldg(&cut_tab[len]);
+    ty = v.x;
+    tn = v.y;
+  } else {
+    length_cuts(len, tbl, tbl_len, tp, ty, tn);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // block-wide exclusive scan of one value per thread (blockDim.x <= 1024, multiple of 32)
 // ---------------------------------------------------------------------------------------------

@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -23,7 +24,7 @@ static thread_local char g_err[512] = "";
 #ifndef DP_BIG_THREADS
 #define DP_BIG_THREADS 1024  // CTA size of the DP kernel for subproblems with more than 32 candidates
 #endif
-#define FRS_SLOTS 2          // batches in flight per context (frs_submit / frs_wait / frs_fetch)
+#define FRS_SLOTS 3          // batches in flight per context (frs_submit / frs_wait / frs_fetch): copy in | kernels | copy out
 
 struct DBuf {
   void* p = nullptr;
@@ -46,9 +47,12 @@ struct Slot {
   DBuf b_tint_island_off, b_tint_rep_off, b_tint_read_off, b_island_start, b_island_sample_off, b_island_tint,
       b_rep_iv_off, b_rep_weight, b_rep_fs, b_rep_fe, b_rep_tint, b_read_rep, b_read_strand, b_read_len,
       b_read_iv_off, b_read_seq_off, b_read_tint, b_riv_ts, b_riv_te, b_riv_qs, b_riv_qe, b_riv_cig_off, b_cigar,
-      b_seq_a, b_seq_t, b_sig_work, b_tiles, b_cov_tiles, b_dig_tiles, b_tint_order, b_params;
+      b_seq_a, b_seq_t, b_sig_work, b_tiles, b_cov_tiles, b_dig_tiles, b_tint_order, b_params, b_cut_tab;
   // results (device)
   DBuf b_tint_final_off, b_final_pos, b_tint_digit_off, b_digits, b_read_head, b_read_gap_off, b_gap_rec, b_counters;
+  // working set of the run's TAIL (clip fetch, poly-A/T scans, head fields): it runs on its own stream beside
+  // the head of the next batch, so it owns its buffers
+  DBuf b_clip_n, b_clip_words, b_clip_off, b_clip_a, b_clip_t, b_task_order, b_task_res, b_poly_cls, b_poly_flag, b_bsum_tail;
   frs_batch hb;  // sizes of the batch; its pointers are not used after the upload
   int n_sig_work = 0, n_sig_direct = 0, n_tiles = 0, n_cov_tiles = 0, n_dig_tiles = 0;
   i64 est_P = 0, est_dig = 0;  // first guesses of the data-dependent capacities (from the batch's shape)
@@ -59,7 +63,8 @@ struct Slot {
   void* h_tab = nullptr;      // pinned staging of the derived work tables
   size_t h_tab_cap = 0;
   i64* h_cnt = nullptr;       // pinned landing area of the counters
-  cudaEvent_t ev_up = nullptr, ev_ran = nullptr, ev_cnt = nullptr, ev_down = nullptr;
+  cudaEvent_t ev_up = nullptr, ev_head = nullptr, ev_ran = nullptr, ev_cnt = nullptr, ev_down = nullptr;
+  cudaEvent_t tl[7] = {};  // FRS_HOST_PROFILE: timeline of the slot (copy in, head, tail, copy out)
   // parameters of the run (kept for a repeat after a capacity miss)
   frs_params prm;
   std::vector<double> prm_tables;
@@ -74,6 +79,8 @@ struct frs_context {
   int n_sm = 148;
   cudaStream_t stream = nullptr;                 // compute
   cudaStream_t st_in = nullptr, st_out = nullptr;  // host-to-device / device-to-host copies
+  cudaStream_t st_tail = nullptr, st_tail_side = nullptr;  // tail of a run (clip fetch + poly scans), beside the next head
+  cudaEvent_t ev_tfork = nullptr, ev_tjoin = nullptr;
   cudaStream_t side[FRS_SIDE_STREAMS] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[FRS_SIDE_STREAMS] = {};
   char err[512] = "";
@@ -91,10 +98,10 @@ struct frs_context {
       b_sub_n, b_sub_tint, b_sub_info, b_sub_slabs, b_sub_tab_off, b_bases, b_work, b_split_list, b_cursor,
       b_cov_sz, b_tint_cov_off, b_P, b_tab, b_dpfinal, b_ref_list, b_ref_list2, b_gbuf, b_pstate, b_final_flat,
       b_final_island, b_dig_sz, b_seg_ty, b_seg_tn,
-      b_run_cnt, b_run_off, b_runs, b_gap_cnt, b_clip_n, b_clip_words, b_clip_off, b_clip_a, b_clip_t, b_task_order,
-      b_task_res, b_poly_cls, b_poly_flag;
+      b_run_cnt, b_run_off, b_runs, b_gap_cnt;
   // options (frs_set_option)
   int opt_slab_words = 64, opt_keep_tables = 0, opt_poly_long_class = POLY_LONG_CLASS, opt_lazy_seq = 1;
+  cudaEvent_t ev_base = nullptr;  // FRS_HOST_PROFILE: origin of the timelines
   // timing
   Stage stages[FRS_MAX_STAGES];
   int n_stages = 0, cur_stage = -1, launch_count = 0;
@@ -124,6 +131,8 @@ static int quiesce(frs_context* c) {
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaStreamSynchronize(c->st_in));
   CK(cudaStreamSynchronize(c->st_out));
+  CK(cudaStreamSynchronize(c->st_tail));
+  CK(cudaStreamSynchronize(c->st_tail_side));
   for (int i = 0; i < FRS_SIDE_STREAMS; ++i) CK(cudaStreamSynchronize(c->side[i]));
   return 0;
 }
@@ -157,7 +166,10 @@ static int ensure(frs_context* c, DBuf& b, size_t bytes) {
     if (r_) return r_;                         \
   } while (0)
 
-static void stage_begin(frs_context* c, const char* name) {
+static void stage_begin(frs_context* c, const char* name, cudaStream_t on = nullptr) {
+  // a stage's two events are recorded on the stream its launches go to
+  static thread_local cudaStream_t cur_on = nullptr;
+  if (!on) on = c->stream;
   int s = -1;
   for (int i = 0; i < c->n_stages; ++i)
     if (c->stages[i].name == name) s = i;
@@ -169,15 +181,16 @@ static void stage_begin(frs_context* c, const char* name) {
     cudaEventCreate(&c->stages[s].ev0);
     cudaEventCreate(&c->stages[s].ev1);
   }
-  if (c->cur_stage >= 0 && c->profiling) cudaEventRecord(c->stages[c->cur_stage].ev1, c->stream);
+  if (c->cur_stage >= 0 && c->profiling) cudaEventRecord(c->stages[c->cur_stage].ev1, cur_on ? cur_on : c->stream);
   c->cur_stage = s;
+  cur_on = on;
   if (s >= 0) {
     c->stages[s].used = true;
-    if (c->profiling) cudaEventRecord(c->stages[s].ev0, c->stream);
+    if (c->profiling) cudaEventRecord(c->stages[s].ev0, on);
   }
 }
-static void stage_end(frs_context* c) {
-  if (c->cur_stage >= 0 && c->profiling) cudaEventRecord(c->stages[c->cur_stage].ev1, c->stream);
+static void stage_end(frs_context* c, cudaStream_t on = nullptr) {
+  if (c->cur_stage >= 0 && c->profiling) cudaEventRecord(c->stages[c->cur_stage].ev1, on ? on : c->stream);
   c->cur_stage = -1;
 }
 #define LAUNCHED()                                           \
@@ -197,18 +210,22 @@ static inline int gs_grid(i64 upper, int threads, int max_ctas = 148 * 8) {
 
 // device-wide helpers ------------------------------------------------------------------------
 template <typename TIn, typename TOut>
-static int scan_exclusive(frs_context* c, const TIn* in, i64 n, TOut* out) {
+static int scan_exclusive_on(frs_context* c, cudaStream_t st, DBuf& scratch, const TIn* in, i64 n, TOut* out) {
   if (n <= SCAN_SMALL_MAX && (const void*)in != (const void*)out) {
-    k_scan_small<TIn, TOut><<<1, 1024, 0, c->stream>>>(in, (int)n, out); LAUNCHED();
+    k_scan_small<TIn, TOut><<<1, 1024, 0, st>>>(in, (int)n, out); LAUNCHED();
     return 0;
   }
   int nb = cdiv(n > 0 ? n : 1, SCAN_TILE);
-  ENS(b_bsum, (size_t)(nb + 1) * 8);
-  i64* bs = c->b_bsum.as<i64>();
-  k_scan_block_sums<TIn><<<nb, SCAN_THREADS, 0, c->stream>>>(in, n, bs); LAUNCHED();
-  k_scan_bsums<<<1, 1024, 0, c->stream>>>(bs, nb); LAUNCHED();
-  k_scan_apply<TIn, TOut><<<nb, SCAN_THREADS, 0, c->stream>>>(in, n, bs, out); LAUNCHED();
+  { int r = ensure(c, scratch, (size_t)(nb + 1) * 8); if (r) return r; }
+  i64* bs = scratch.as<i64>();
+  k_scan_block_sums<TIn><<<nb, SCAN_THREADS, 0, st>>>(in, n, bs); LAUNCHED();
+  k_scan_bsums<<<1, 1024, 0, st>>>(bs, nb); LAUNCHED();
+  k_scan_apply<TIn, TOut><<<nb, SCAN_THREADS, 0, st>>>(in, n, bs, out); LAUNCHED();
   return 0;
+}
+template <typename TIn, typename TOut>
+static int scan_exclusive(frs_context* c, const TIn* in, i64 n, TOut* out) {
+  return scan_exclusive_on<TIn, TOut>(c, c->stream, c->b_bsum, in, n, out);
 }
 // compaction of byte flags; the count ends up in bsum[nb] and is copied to *count_out (device)
 static int compact_flags(frs_context* c, const u8* flags, i64 n, int* idx_out, i64* count_out) {
@@ -276,9 +293,13 @@ int frs_create(int device, frs_context** out) {
   c = new frs_context();
   c->device = device;
   bool ok = cudaSetDevice(device) == cudaSuccess &&
-            cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, -1) == cudaSuccess &&  // above the tail
             cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking) == cudaSuccess;
+            cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithPriority(&c->st_tail, cudaStreamNonBlocking, 0) == cudaSuccess &&
+            cudaStreamCreateWithPriority(&c->st_tail_side, cudaStreamNonBlocking, 0) == cudaSuccess &&
+            cudaEventCreateWithFlags(&c->ev_tfork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&c->ev_tjoin, cudaEventDisableTiming) == cudaSuccess;
   for (int k = 0; ok && k < FRS_SLOTS; ++k) {
     Slot& S = c->slot[k];
     memset(&S.hb, 0, sizeof S.hb);
@@ -287,6 +308,7 @@ int frs_create(int device, frs_context** out) {
     ok = cudaMallocHost((void**)&S.h_cnt, CNT_SLOTS * 8) == cudaSuccess &&
          cudaEventCreateWithFlags(&S.ev_up, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&S.ev_ran, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&S.ev_head, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&S.ev_cnt, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&S.ev_down, cudaEventDisableTiming) == cudaSuccess;
   }
@@ -294,6 +316,12 @@ int frs_create(int device, frs_context** out) {
     int r = fail(nullptr, FRS_ERR_CUDA, "frs_create: %s", cudaGetErrorString(cudaGetLastError()));
     delete c;
     return r;
+  }
+  if (getenv("FRS_HOST_PROFILE")) {
+    cudaEventCreate(&c->ev_base);
+    cudaEventRecord(c->ev_base, c->stream);
+    for (int k = 0; k < FRS_SLOTS; ++k)
+      for (int e = 0; e < 7; ++e) cudaEventCreate(&c->slot[k].tl[e]);
   }
   cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device);
   if (c->n_sm < 1) c->n_sm = 148;
@@ -333,6 +361,8 @@ void frs_destroy(frs_context* c) {
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->st_in);
   cudaStreamSynchronize(c->st_out);
+  if (c->st_tail) cudaStreamSynchronize(c->st_tail);
+  if (c->st_tail_side) cudaStreamSynchronize(c->st_tail_side);
   for (DBuf* b : c->all)
     if (b->p) cudaFree(b->p);
   for (int i = 0; i < c->n_stages; ++i) {
@@ -345,6 +375,7 @@ void frs_destroy(frs_context* c) {
     if (S.h_tab) cudaFreeHost(S.h_tab);
     if (S.ev_up) cudaEventDestroy(S.ev_up);
     if (S.ev_ran) cudaEventDestroy(S.ev_ran);
+    if (S.ev_head) cudaEventDestroy(S.ev_head);
     if (S.ev_cnt) cudaEventDestroy(S.ev_cnt);
     if (S.ev_down) cudaEventDestroy(S.ev_down);
   }
@@ -356,6 +387,10 @@ void frs_destroy(frs_context* c) {
   cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->st_in);
   cudaStreamDestroy(c->st_out);
+  if (c->st_tail) cudaStreamDestroy(c->st_tail);
+  if (c->st_tail_side) cudaStreamDestroy(c->st_tail_side);
+  if (c->ev_tfork) cudaEventDestroy(c->ev_tfork);
+  if (c->ev_tjoin) cudaEventDestroy(c->ev_tjoin);
   delete c;
 }
 
@@ -404,6 +439,7 @@ int frs_get_timings(frs_context* c, const char** names, float* ms, int* launches
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->st_tail);
   int k = 0;
   for (int i = 0; i < c->n_stages; ++i) {
     if (!c->stages[i].used) continue;
@@ -449,6 +485,8 @@ static int stage_upload(frs_context* c, Slot& S, const frs_batch* b) {
   for (int i = 0; i < NI; ++i)
     if (b->island_sample_off[i + 1] - b->island_sample_off[i] < 2)
       return fail(c, FRS_ERR_ARG, "AssertionError: island %d is empty (freddie_segment.py:140)", i);
+  static const bool prof = getenv("FRS_HOST_PROFILE") != nullptr;
+  const auto tp0 = std::chrono::steady_clock::now();
   // the slot's previous results must have left the device before its buffers are reused
   if (S.down_pending) { CK(cudaEventSynchronize(S.ev_down)); S.down_pending = false; }
   S.hb = *b;
@@ -459,18 +497,40 @@ static int stage_upload(frs_context* c, Slot& S, const frs_batch* b) {
   std::vector<RepTile> cov_tiles, dig_tiles;
   const int DIG_REPS = DIG_THREADS;
   i64 est_P = 0, est_dig = 0;
+  tiles.reserve((size_t)b->n_samples / TILE_SAMPLES + (size_t)NI + 16);
+  cov_tiles.reserve((size_t)NR / COV_THREADS + (size_t)T + 16);
+  dig_tiles.reserve((size_t)NR / DIG_REPS + (size_t)T + 16);
+  // every read points at a rep of its own tint with the same number of intervals (the dedupe key of
+  // read_split, freddie_segment.py:165-170); checked before anything is copied
+  {
+    long long bad_read = -1;
+    int bad_kind = 0;
+#pragma omp parallel for schedule(static) if (N > 65536)
+    for (int t = 0; t < T; ++t) {
+      const int r0 = b->tint_rep_off[t], r1 = b->tint_rep_off[t + 1];
+      for (int r = b->tint_read_off[t]; r < b->tint_read_off[t + 1]; ++r) {
+        const int rep = b->read_rep[r];
+        int kind = 0;
+        if (rep < r0 || rep >= r1) kind = 1;
+        else if (b->read_iv_off[r + 1] - b->read_iv_off[r] != b->rep_iv_off[rep + 1] - b->rep_iv_off[rep]) kind = 2;
+        if (kind) {
+#pragma omp critical
+          if (bad_read < 0 || r < bad_read) { bad_read = r; bad_kind = kind; }
+        }
+      }
+    }
+    if (bad_kind == 1)
+      return fail(c, FRS_ERR_ARG, "frs_upload: read %lld points at rep %d of another tint", bad_read, b->read_rep[bad_read]);
+    if (bad_kind == 2)
+      return fail(c, FRS_ERR_ARG, "frs_upload: read %lld and its rep %d differ in their number of intervals", bad_read,
+                  b->read_rep[bad_read]);
+  }
   for (int t = 0; t < T; ++t) {
     for (int i = b->tint_island_off[t]; i < b->tint_island_off[t + 1]; ++i) {
       int n = b->island_sample_off[i + 1] - b->island_sample_off[i];
       for (int lo = 0; lo < n; lo += TILE_SAMPLES) tiles.push_back(TileWork{i, lo, b->island_sample_off[i], n});
     }
     int r0 = b->tint_rep_off[t], r1 = b->tint_rep_off[t + 1];
-    for (int r = b->tint_read_off[t]; r < b->tint_read_off[t + 1]; ++r) {
-      const int rep = b->read_rep[r];
-      if (rep < r0 || rep >= r1) return fail(c, FRS_ERR_ARG, "frs_upload: read %d points at rep %d of another tint", r, rep);
-      if (b->read_iv_off[r + 1] - b->read_iv_off[r] != b->rep_iv_off[rep + 1] - b->rep_iv_off[rep])
-        return fail(c, FRS_ERR_ARG, "frs_upload: read %d and its rep %d differ in their number of intervals", r, rep);
-    }
     int s0 = b->island_sample_off[b->tint_island_off[t]], s1 = b->island_sample_off[b->tint_island_off[t + 1]];
     int single = (r1 - r0) <= SIG_REPS;
     const i64 n_endpoints = 2 * (i64)(b->rep_iv_off[r1] - b->rep_iv_off[r0]);
@@ -512,7 +572,9 @@ static int stage_upload(frs_context* c, Slot& S, const frs_batch* b) {
   S.n_tiles = (int)tiles.size();
   S.n_cov_tiles = (int)cov_tiles.size();
   S.n_dig_tiles = (int)dig_tiles.size();
+  const auto tp1 = std::chrono::steady_clock::now();
   // ---- copies ----
+  if (S.tl[0]) cudaEventRecord(S.tl[0], c->st_in);
   S.st_h2d_upload = 0;
   H2D(b_tint_island_off, b->tint_island_off, (size_t)(T + 1) * 4);
   H2D(b_tint_rep_off, b->tint_rep_off, (size_t)(T + 1) * 4);
@@ -600,6 +662,12 @@ static int stage_upload(frs_context* c, Slot& S, const frs_batch* b) {
     H2D(b_dig_tiles, (char*)S.h_tab + off[4], bytes[4]);
   }
   CK(cudaEventRecord(S.ev_up, c->st_in));
+  if (S.tl[1]) cudaEventRecord(S.tl[1], c->st_in);
+  if (prof) {
+    const auto tp2 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[frs host profile] upload: checks + tables %.3f ms, copies enqueued %.3f ms\n",
+            std::chrono::duration<double, std::milli>(tp1 - tp0).count(), std::chrono::duration<double, std::milli>(tp2 - tp1).count());
+  }
   S.uploaded = true;
   S.enqueued = false;
   S.ran = false;
@@ -669,6 +737,7 @@ static int enqueue_run(frs_context* c, Slot& S) {
   const int lw = prm->gauss_radius, rr = prm->refine_radius;
   const size_t ptab = (size_t)prm->thr_table_len + (2 * lw + 1) + (2 * rr + 1);
   ENSS(b_params, ptab * 8);
+  ENSS(b_cut_tab, CUT_TAB_N * sizeof(int2));
   ENSS(b_counters, CNT_SLOTS * 8);
   ENS(b_yraw, L * 4);
   ENS(b_y, L * 8);
@@ -677,7 +746,7 @@ static int enqueue_run(frs_context* c, Slot& S) {
   ENS(b_vbuf, L * 8);
   ENS(b_tint_pos_off, (size_t)(T + 1) * 4);
   const size_t n_chunks = ((size_t)S.n_tiles + SM_CHUNK - 1) / SM_CHUNK;
-  ENS(b_tile_state, n_chunks * 8 + sizeof(SmoothSync) + (size_t)S.n_tiles * (2 * TILE_WORDS * 4 + 4) + 64);
+  ENS(b_tile_state, (n_chunks + n_chunks / SM_GROUP + 1) * 8 + sizeof(SmoothSync) + (size_t)S.n_tiles * (2 * TILE_WORDS * 4 + 16) + 64);
   ENS(b_thr, (size_t)T * 8);
   {
     size_t nh = (size_t)L / 8 + 64 * (size_t)T + 64;  // heap scratch of the giant tints (see k_threshold)
@@ -724,16 +793,17 @@ static int enqueue_run(frs_context* c, Slot& S) {
   ENS(b_runs, cp.runs * 8);
   ENSS(b_read_head, (size_t)N * 32);
   ENSS(b_gap_rec, cp.gaps * 12);
-  ENS(b_clip_n, (size_t)N * 8);
-  ENS(b_clip_words, (size_t)N * 8);
-  ENS(b_clip_off, (size_t)N * 16 + 8);
-  ENS(b_task_order, (size_t)N * 16);
-  ENS(b_task_res, (size_t)N * 4 * sizeof(PolyRes));
-  ENS(b_poly_cls, (2 * POLY_CLASSES + 1) * 4);
-  ENS(b_poly_flag, (size_t)N * 4);
+  ENSS(b_clip_n, (size_t)N * 8);
+  ENSS(b_clip_words, (size_t)N * 8);
+  ENSS(b_clip_off, (size_t)N * 16 + 8);
+  ENSS(b_task_order, (size_t)N * 16);
+  ENSS(b_task_res, (size_t)N * 4 * sizeof(PolyRes));
+  ENSS(b_poly_cls, (2 * POLY_CLASSES + 1) * 4);
+  ENSS(b_poly_flag, (size_t)N * 4);
+  ENSS(b_bsum_tail, ((size_t)N * 2 / SCAN_TILE + 2) * 8);
   if (!S.seq_resident) {
-    ENS(b_clip_a, cp.clipw * 4);
-    ENS(b_clip_t, cp.clipw * 4);
+    ENSS(b_clip_a, cp.clipw * 4);
+    ENSS(b_clip_t, cp.clipw * 4);
   }
   // subproblems are at most max_problem_size + 11 candidates long (k_fixed_b: anchors move by < 5 + 5);
   // the solver keeps G / arg of the largest one in shared memory and stages the tables of those that fit
@@ -746,11 +816,14 @@ static int enqueue_run(frs_context* c, Slot& S) {
   CK(cudaStreamWaitEvent(st, S.ev_up, 0));
   if (S.down_pending) CK(cudaStreamWaitEvent(st, S.ev_down, 0));
 
+  if (S.tl[2]) cudaEventRecord(S.tl[2], st);
   // parameter tables
   double* d_tbl = S.b_params.as<double>();
   double* d_gw = d_tbl + prm->thr_table_len;
   double* d_rw = d_gw + (2 * lw + 1);
   CK(cudaMemcpyAsync(d_tbl, S.prm_tables.data(), ptab * 8, cudaMemcpyHostToDevice, st));
+  const int2* d_cut = S.b_cut_tab.as<int2>();
+  k_cut_table<<<CUT_TAB_N / 256, 256, 0, st>>>(d_tbl, prm->thr_table_len, prm->tp, S.b_cut_tab.as<int2>());
 
   i64* d_cnt = S.b_counters.as<i64>();
   CK(cudaMemsetAsync(d_cnt, 0, CNT_SLOTS * 8, st));
@@ -779,32 +852,28 @@ static int enqueue_run(frs_context* c, Slot& S) {
 
   stage_begin(c, "smooth");
   {
-    // chunk totals | sync words | per tile: candidate / positive ballot words, packed counts
-    unsigned long long* d_ctot = c->b_tile_state.as<unsigned long long>();
-    SmoothSync* d_sync = (SmoothSync*)(d_ctot + n_chunks);
-    u32* d_cmask = (u32*)(d_sync + 1);
+    // group totals | sync words | chunk totals | per tile: candidate / positive ballot words, packed counts
+    const size_t n_groups = n_chunks / SM_GROUP + 1;
+    unsigned long long* d_gtot = c->b_tile_state.as<unsigned long long>();
+    SmoothSync* d_sync = (SmoothSync*)(d_gtot + n_groups);
+    unsigned long long* d_ctot = (unsigned long long*)(d_sync + 1);
+    u32* d_cmask = (u32*)(d_ctot + n_chunks);
     u32* d_pmask = d_cmask + (size_t)S.n_tiles * TILE_WORDS;
     u32* d_tcnt = d_pmask + (size_t)S.n_tiles * TILE_WORDS;
-    CK(cudaMemsetAsync(d_sync, 0, sizeof(SmoothSync), st));
-    const size_t sm = (size_t)p1_smem_layout(lw).total;
+    CK(cudaMemsetAsync(d_gtot, 0, (n_groups + n_chunks) * 8 + sizeof(SmoothSync), st));  // group totals, sync, chunk totals
+    const size_t sm = (size_t)wq_smem_layout(lw).total;
     if (sm > 48 * 1024) CK(cudaFuncSetAttribute(k_smooth_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_smooth_lists, GAUSS_THREADS, sm));
     if (occ < 1) return fail(c, FRS_ERR_LIMIT, "k_smooth_lists does not fit an SM at sigma = %g", prm->sigma);
-    // persistent and cooperative: every CTA is resident (the kernel has a grid-wide barrier)
+    // persistent, with a grid-wide barrier: the grid is what fits the machine when the kernel has it alone, so
+    // every CTA becomes resident (kernels of the previous batch's tail that hold SM slots finish on their own;
+    // a cooperative launch would wait for an EMPTY machine and serialise the head behind that tail)
     const int grid = (int)std::min<i64>((i64)n_chunks, (i64)occ * c->n_sm);
-    const TileWork* a_tiles = S.b_tiles.as<TileWork>();
-    int a_ntiles = S.n_tiles, a_T = T, a_lw = lw;
-    const int* a_yraw = c->b_yraw.as<int>();
-    const double* a_gw = d_gw;
-    double* a_y = c->b_y.as<double>();
-    int* a_cand = c->b_cand_flat.as<int>();
-    double* a_vbuf = c->b_vbuf.as<double>();
-    int* a_tpo = c->b_tint_pos_off.as<int>();
-    i64* a_k = d_cnt + CNT_K;
-    void* args[] = {&a_tiles, &a_ntiles, &d_island_tint, &d_tint_island_off, &a_T, &a_yraw, &a_gw, &a_lw, &a_y,
-                    &d_cmask, &d_pmask, &d_tcnt, &d_ctot, &d_sync, &a_cand, &a_vbuf, &a_tpo, &a_k};
-    CK(cudaLaunchCooperativeKernel((const void*)k_smooth_lists, dim3(grid), dim3(GAUSS_THREADS), args, sm, st));
+    k_smooth_lists<<<grid, GAUSS_THREADS, sm, st>>>(S.b_tiles.as<TileWork>(), S.n_tiles, d_island_tint, d_tint_island_off, T,
+                                                    c->b_yraw.as<int>(), d_gw, lw, c->b_y.as<double>(), d_cmask, d_pmask,
+                                                    d_tcnt, d_ctot, d_gtot, d_sync, c->b_cand_flat.as<int>(),
+                                                    c->b_vbuf.as<double>(), c->b_tint_pos_off.as<int>(), d_cnt + CNT_K);
     LAUNCHED();
   }
 
@@ -871,7 +940,7 @@ static int enqueue_run(frs_context* c, Slot& S) {
     A.tint_rep_off = d_tint_rep_off; A.tint_cand_off = c->b_tint_cand_off.as<int>();
     A.tint_cov_off = c->b_tint_cov_off.as<i64>(); A.rep_weight = S.b_rep_weight.as<int>();
     A.cand_flat = c->b_cand_flat.as<int>(); A.P = c->b_P.as<u32>();
-    A.thr_table = d_tbl; A.thr_table_len = prm->thr_table_len; A.tp = prm->tp;
+    A.thr_table = d_tbl; A.thr_table_len = prm->thr_table_len; A.tp = prm->tp; A.cut_tab = d_cut;
     A.lo = prm->lo; A.keep_tables = keep;
     A.tab = c->b_tab.as<int>(); A.final_flag = c->b_dpfinal.as<u8>(); A.err = d_err;
     A.cnt = d_cnt; A.caps = cp; A.bases = c->b_bases.as<int>(); A.cursor = c->b_cursor.as<int>();
@@ -941,7 +1010,7 @@ static int enqueue_run(frs_context* c, Slot& S) {
   LAUNCHED();
   { int r = scan_exclusive<i64, i64>(c, c->b_dig_sz.as<i64>(), T, S.b_tint_digit_off.as<i64>()); if (r) return r; }
   CK(cudaMemcpyAsync(d_cnt + CNT_NDIG, S.b_tint_digit_off.as<i64>() + T, 8, cudaMemcpyDeviceToDevice, st));
-  k_seg_cuts<<<148 * 4, 256, 0, st>>>(d_nfin, c->b_final_flat.as<int>(), c->b_final_island.as<int>(), d_tbl,
+  k_seg_cuts<<<148 * 4, 256, 0, st>>>(d_nfin, c->b_final_flat.as<int>(), c->b_final_island.as<int>(), d_cut, d_tbl,
                                       prm->thr_table_len, prm->tp, c->b_seg_ty.as<int>(), c->b_seg_tn.as<int>());
   LAUNCHED();
 
@@ -980,49 +1049,62 @@ static int enqueue_run(frs_context* c, Slot& S) {
     G.read_seq_off = S.b_read_seq_off.as<i64>(); G.read_tint = S.b_read_tint.as<int>();
     G.riv_ts = S.b_riv_ts.as<int>(); G.riv_te = S.b_riv_te.as<int>(); G.riv_qs = S.b_riv_qs.as<int>();
     G.riv_qe = S.b_riv_qe.as<int>(); G.riv_cig_off = S.b_riv_cig_off.as<int>(); G.cigar = S.b_cigar.as<u32>();
-    G.seq_a = S.seq_resident ? S.b_seq_a.as<u32>() : c->b_clip_a.as<u32>();
-    G.seq_t = S.seq_resident ? S.b_seq_t.as<u32>() : c->b_clip_t.as<u32>();
+    G.seq_a = S.seq_resident ? S.b_seq_a.as<u32>() : S.b_clip_a.as<u32>();
+    G.seq_t = S.seq_resident ? S.b_seq_t.as<u32>() : S.b_clip_t.as<u32>();
     G.run_off = c->b_run_off.as<int>();
     G.runs = c->b_runs.as<int2>(); G.tint_final_off = S.b_tint_final_off.as<int>();
     G.final_pos = S.b_final_pos.as<int>(); G.read_gap_off = S.b_read_gap_off.as<int>();
     G.read_head = S.b_read_head.as<int>(); G.gap_rec = S.b_gap_rec.as<int>(); G.err = d_err;
-    G.clip_n = c->b_clip_n.as<int>(); G.clip_words = c->b_clip_words.as<int>(); G.clip_off = c->b_clip_off.as<i64>();
+    G.clip_n = S.b_clip_n.as<int>(); G.clip_words = S.b_clip_words.as<int>(); G.clip_off = S.b_clip_off.as<i64>();
     G.seq_resident = S.seq_resident ? 1 : 0;
-    G.cls_count = c->b_poly_cls.as<int>();
-    G.task_order = c->b_task_order.as<int>(); G.task_res = c->b_task_res.as<PolyRes>();
+    G.cls_count = S.b_poly_cls.as<int>();
+    G.task_order = S.b_task_order.as<int>(); G.task_res = S.b_task_res.as<PolyRes>();
     G.long_class = c->opt_poly_long_class;
     G.cnt = d_cnt; G.caps = cp;
-    CK(cudaMemsetAsync(c->b_poly_cls.p, 0, (2 * POLY_CLASSES + 1) * 4, st));
     k_gap_prep<<<cdiv(N, 128), 128, 0, st>>>(G); LAUNCHED();
     k_gap_sizes<<<gs_grid((i64)N * 2, 128, 148 * 8), 128, 0, st>>>(G); LAUNCHED();
+    stage_end(c);
+    // ---- TAIL of the run, on its own stream: it touches only buffers of this slot, so the head of the next
+    // batch (compute stream) runs beside it -- the clip fetch is bound by the bus, not by the SMs ----
+    cudaStream_t tl = c->st_tail;
+    if (S.tl[3]) cudaEventRecord(S.tl[3], st);
+    CK(cudaEventRecord(S.ev_head, st));
+    CK(cudaStreamWaitEvent(tl, S.ev_head, 0));
+    CK(cudaMemsetAsync(S.b_poly_cls.p, 0, (2 * POLY_CLASSES + 1) * 4, tl));
     if (!S.seq_resident) {
-      stage_begin(c, "clip_fetch");
+      stage_begin(c, "clip_fetch", tl);
       // compact offsets of the clips' plane words (total at [2N]), then the words themselves, straight from
       // the caller's pinned planes
-      { int r = scan_exclusive<int, i64>(c, c->b_clip_words.as<int>(), (i64)N * 2, c->b_clip_off.as<i64>()); if (r) return r; }
-      CK(cudaMemcpyAsync(d_cnt + CNT_CLIPW, c->b_clip_off.as<i64>() + (i64)N * 2, 8, cudaMemcpyDeviceToDevice, st));
-      k_clip_gather<<<148 * 8, 256, 0, st>>>(G, S.zc_a, S.zc_t, c->b_clip_a.as<u32>(), c->b_clip_t.as<u32>());
+      { int r = scan_exclusive_on<int, i64>(c, tl, S.b_bsum_tail, S.b_clip_words.as<int>(), (i64)N * 2, S.b_clip_off.as<i64>()); if (r) return r; }
+      CK(cudaMemcpyAsync(d_cnt + CNT_CLIPW, S.b_clip_off.as<i64>() + (i64)N * 2, 8, cudaMemcpyDeviceToDevice, tl));
+      // few CTAs: the kernel waits on the bus, and the SMs belong to the head of the next batch meanwhile
+      k_clip_gather<<<c->n_sm, 256, 0, tl>>>(G, S.zc_a, S.zc_t, S.b_clip_a.as<u32>(), S.b_clip_t.as<u32>());
       LAUNCHED();
     }
-    stage_begin(c, "poly");
-    k_poly_filter<<<cdiv((i64)N * 4, 128), 128, 0, st>>>(G, c->b_poly_flag.as<u8>()); LAUNCHED();
-    k_poly_bases<<<1, 32, 0, st>>>(G.cls_count, G.long_class, d_err + 2); LAUNCHED();
-    k_poly_scatter<<<cdiv((i64)N * 4, 256), 256, 0, st>>>(N * 4, G.clip_n, c->b_poly_flag.as<u8>(), G.cls_count,
+    stage_begin(c, "poly", tl);
+    k_poly_filter<<<cdiv((i64)N * 4, 128), 128, 0, tl>>>(G, S.b_poly_flag.as<u8>()); LAUNCHED();
+    k_poly_bases<<<1, 32, 0, tl>>>(G.cls_count, G.long_class, d_err + 2); LAUNCHED();
+    k_poly_scatter<<<cdiv((i64)N * 4, 256), 256, 0, tl>>>(N * 4, G.clip_n, S.b_poly_flag.as<u8>(), G.cls_count,
                                                            G.task_order, d_cnt, cp); LAUNCHED();
     // long clips (one warp each) run beside the short ones (one thread each)
-    CK(cudaEventRecord(c->ev_fork, st));
-    CK(cudaStreamWaitEvent(c->side[0], c->ev_fork, 0));
-    k_poly_long<<<148 * 4, 128, 0, c->side[0]>>>(G); LAUNCHED();
-    CK(cudaEventRecord(c->ev_join[0], c->side[0]));
-    k_poly_scan<<<cdiv((i64)N * 4, 128), 128, 0, st>>>(G); LAUNCHED();
-    CK(cudaStreamWaitEvent(st, c->ev_join[0], 0));
-    k_gap_finish<<<cdiv(N, 128), 128, 0, st>>>(G); LAUNCHED();
+    CK(cudaEventRecord(c->ev_tfork, tl));
+    CK(cudaStreamWaitEvent(c->st_tail_side, c->ev_tfork, 0));
+    k_poly_long<<<148 * 4, 128, 0, c->st_tail_side>>>(G); LAUNCHED();
+    CK(cudaEventRecord(c->ev_tjoin, c->st_tail_side));
+    k_poly_scan<<<cdiv((i64)N * 4, 128), 128, 0, tl>>>(G); LAUNCHED();
+    CK(cudaStreamWaitEvent(tl, c->ev_tjoin, 0));
+    k_gap_finish<<<cdiv(N, 128), 128, 0, tl>>>(G); LAUNCHED();
+    stage_end(c, tl);
+  } else {
+    stage_end(c);
+    CK(cudaEventRecord(S.ev_head, st));
+    CK(cudaStreamWaitEvent(c->st_tail, S.ev_head, 0));
   }
-  stage_end(c);
   // the ONE read-back of the run: every count, the plan and the assert channel
-  CK(cudaEventRecord(S.ev_ran, st));
-  CK(cudaMemcpyAsync(S.h_cnt, d_cnt, CNT_SLOTS * 8, cudaMemcpyDeviceToHost, st));
-  CK(cudaEventRecord(S.ev_cnt, st));
+  CK(cudaEventRecord(S.ev_ran, c->st_tail));
+  if (S.tl[4]) cudaEventRecord(S.tl[4], c->st_tail);
+  CK(cudaMemcpyAsync(S.h_cnt, d_cnt, CNT_SLOTS * 8, cudaMemcpyDeviceToHost, c->st_tail));
+  CK(cudaEventRecord(S.ev_cnt, c->st_tail));
   CK(cudaGetLastError());
   S.enqueued = true;
   S.ran = false;
@@ -1099,6 +1181,7 @@ static int enqueue_download(frs_context* c, Slot& S, const frs_result* o) {
   if (!S.ran) return fail(c, FRS_ERR_STATE, "frs_download: no results (call frs_run first)");
   const int T = S.hb.n_tints, N = S.hb.n_reads;
   CK(cudaStreamWaitEvent(c->st_out, S.ev_ran, 0));
+  if (S.tl[5]) cudaEventRecord(S.tl[5], c->st_out);
   D2H(o->tint_final_off, b_tint_final_off, (size_t)(T + 1) * 4);
   D2H(o->final_pos, b_final_pos, S.sizes.n_final * 4);
   D2H(o->tint_digit_off, b_tint_digit_off, (size_t)(T + 1) * 8);
@@ -1107,6 +1190,7 @@ static int enqueue_download(frs_context* c, Slot& S, const frs_result* o) {
   D2H(o->read_gap_off, b_read_gap_off, (size_t)(N + 1) * 4);
   D2H(o->gap_rec, b_gap_rec, S.sizes.n_gap_records * 12);
   CK(cudaEventRecord(S.ev_down, c->st_out));
+  if (S.tl[6]) cudaEventRecord(S.tl[6], c->st_out);
   S.down_pending = true;
   return 0;
 }
@@ -1164,9 +1248,17 @@ int frs_submit(frs_context* c, const frs_batch* b, const frs_params* prm, int* t
   if (S.busy) return fail(c, FRS_ERR_STATE, "frs_submit: %d batches are in flight already (frs_fetch the oldest first)", FRS_SLOTS);
   int r = check_params(c, prm);
   if (r) return r;
+  static const bool prof = getenv("FRS_HOST_PROFILE") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
   if ((r = stage_upload(c, S, b))) return r;
+  const auto t1 = std::chrono::steady_clock::now();
   keep_params(S, prm);
   if ((r = enqueue_run(c, S))) return r;
+  if (prof) {
+    const auto t2 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[frs host profile] submit: upload side %.3f ms, run side %.3f ms\n",
+            std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count());
+  }
   S.busy = true;
   c->cur = k;
   *ticket = k;
@@ -1184,18 +1276,42 @@ int frs_wait(frs_context* c, int ticket, frs_result_sizes* sizes_out) {
   return 0;
 }
 
-int frs_fetch(frs_context* c, int ticket, const frs_result* o) {
+int frs_fetch_start(frs_context* c, int ticket, const frs_result* o) {
   if (!c || !o || ticket < 0 || ticket >= FRS_SLOTS) return fail(c, FRS_ERR_ARG, "frs_fetch: bad argument");
   CK(cudaSetDevice(c->device));
   Slot& S = c->slot[ticket];
   if (!S.busy) return fail(c, FRS_ERR_STATE, "frs_fetch: no batch in flight under this ticket");
+  if (S.down_pending) return fail(c, FRS_ERR_STATE, "frs_fetch_start: the results of this ticket are being copied already");
   int r = 0;
   if (!S.ran) r = finish_run(c, S);
   if (!r) r = enqueue_download(c, S, o);
-  if (!r && cudaEventSynchronize(S.ev_down) != cudaSuccess) r = fail(c, FRS_ERR_CUDA, "frs_fetch: %s", cudaGetErrorString(cudaGetLastError()));
+  if (r) S.busy = false;
+  return r;
+}
+
+int frs_fetch_finish(frs_context* c, int ticket) {
+  if (!c || ticket < 0 || ticket >= FRS_SLOTS) return fail(c, FRS_ERR_ARG, "frs_fetch: bad argument");
+  CK(cudaSetDevice(c->device));
+  Slot& S = c->slot[ticket];
+  if (!S.busy || !S.down_pending) return fail(c, FRS_ERR_STATE, "frs_fetch_finish: no copy in flight under this ticket");
+  int r = 0;
+  if (cudaEventSynchronize(S.ev_down) != cudaSuccess) r = fail(c, FRS_ERR_CUDA, "frs_fetch: %s", cudaGetErrorString(cudaGetLastError()));
+  if (!r && S.tl[6] && c->ev_base) {
+    cudaEventSynchronize(S.tl[6]);
+    float t[7];
+    for (int e = 0; e < 7; ++e) cudaEventElapsedTime(&t[e], c->ev_base, S.tl[e]);
+    fprintf(stderr, "[frs timeline] slot %d: h2d %.3f-%.3f  head %.3f-%.3f  tail -%.3f  d2h %.3f-%.3f ms\n", ticket, t[0], t[1], t[2],
+            t[3], t[4], t[5], t[6]);
+  }
   S.down_pending = false;
   S.busy = false;
   return r;
+}
+
+int frs_fetch(frs_context* c, int ticket, const frs_result* o) {
+  int r = frs_fetch_start(c, ticket, o);
+  if (r) return r;
+  return frs_fetch_finish(c, ticket);
 }
 
 int frs_get_intermediate(frs_context* c, int which, void* dst, size_t cap, size_t* bytes) {

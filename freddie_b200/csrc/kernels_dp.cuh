@@ -487,6 +487,7 @@ struct DpArgs {
   const int* tint_rep_off; const int* tint_cand_off; const i64* tint_cov_off;
   const int* rep_weight; const int* cand_flat; const u32* P;
   const double* thr_table; int thr_table_len; double tp;
+  const int2* cut_tab;  // integer cuts of the lengths below CUT_TAB_N (k_cut_table)
   int lo; int keep_tables;
   int* tab;        // global tables of the split / kept subproblems
   u8* final_flag;  // [n_cand]
@@ -720,7 +721,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 
       while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
       int j = i + 1 + rem;
       int a, b;
-      length_cuts(cf[j] - cf[i] + 1, A.thr_table, A.thr_table_len, A.tp, a, b);
+      length_cuts_t(cf[j] - cf[i] + 1, A.cut_tab, A.thr_table, A.thr_table_len, A.tp, a, b);
       ty[e] = a;
       tn[e] = b;
     }
@@ -844,7 +845,7 @@ __global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWo
     while (rem >= n - 1 - i) { rem -= n - 1 - i; ++i; }
     int j = i + 1 + rem;
     int a, b;
-    length_cuts(S.cf[j] - S.cf[i] + 1, A.thr_table, A.thr_table_len, A.tp, a, b);
+    length_cuts_t(S.cf[j] - S.cf[i] + 1, A.cut_tab, A.thr_table, A.thr_table_len, A.tp, a, b);
     S.ty[e] = a;
     S.tn[e] = b;
     S.amb[e] = 0;

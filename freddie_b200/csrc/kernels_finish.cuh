@@ -190,13 +190,14 @@ __global__ void k_digit_sizes(int n_tints, const int* __restrict__ tint_rep_off,
 
 // per final e (segment e -> e+1): integer cuts of the segment, or a separator marker
 __global__ void k_seg_cuts(const i64* __restrict__ n_final_p, const int* __restrict__ final_flat,
-                           const int* __restrict__ final_island, const double* __restrict__ tbl, int tbl_len, double tp,
+                           const int* __restrict__ final_island, const int2* __restrict__ cut_tab,
+                           const double* __restrict__ tbl, int tbl_len, double tp,
                            int* __restrict__ seg_ty, int* __restrict__ seg_tn) {
   const int n_final = (int)*n_final_p;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_final; e += gridDim.x * blockDim.x) {
     int ty = 0x7fffffff, tn = -2;  // tn == -2 marks "no segment" (island separator or tint end)
     if (e + 1 < n_final && final_island[e] == final_island[e + 1])
-      length_cuts(final_flat[e + 1] - final_flat[e] + 1, tbl, tbl_len, tp, ty, tn);
+      length_cuts_t(final_flat[e + 1] - final_flat[e] + 1, cut_tab, tbl, tbl_len, tp, ty, tn);
     seg_ty[e] = ty;
     seg_tn[e] = tn;
   }

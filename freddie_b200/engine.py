@@ -63,6 +63,8 @@ class SegmentParams:
         self.rw = gaussian_kernel(self.sigma, 1.0)
 
     def as_struct(self) -> "_lib.FrsParams":
+        if getattr(self, "_struct", None) is not None:
+            return self._struct
         p = _lib.FrsParams()
         p.sigma, p.tp, p.vf = self.sigma, self.tp, self.vf
         p.mps, p.lo, p.ignore_ends = self.mps, self.lo, int(self.ignore_ends)
@@ -72,6 +74,7 @@ class SegmentParams:
         p.refine_w = self.rw.ctypes.data_as(C.c_void_p)
         p.gauss_radius = (len(self.gw) - 1) // 2
         p.refine_radius = (len(self.rw) - 1) // 2
+        self._struct = p
         return p
 
 
@@ -98,10 +101,12 @@ class BatchResult:
                 self.arrays[k] = np.empty(int(n), dtype=dt)
 
     def as_struct(self) -> "_lib.FrsResult":
-        r = _lib.FrsResult()
-        for k in _lib.RESULT_ARRAYS:
-            setattr(r, k, self.arrays[k].ctypes.data_as(C.c_void_p))
-        return r
+        if getattr(self, "_struct", None) is None:
+            r = _lib.FrsResult()
+            for k in _lib.RESULT_ARRAYS:
+                setattr(r, k, self.arrays[k].ctypes.data_as(C.c_void_p))
+            self._struct = r
+        return self._struct
 
 
 class Engine:
@@ -184,6 +189,19 @@ class Engine:
         finally:
             self._inflight.pop(ticket, None)
         return res
+
+    def fetch_start(self, ticket: int, res: "BatchResult") -> "BatchResult":
+        """First half of ``fetch``: enqueues the copies into ``res`` and returns at once."""
+        r = res.as_struct()
+        self._check(self.lib.frs_fetch_start(self.ctx, ticket, C.byref(r)))
+        return res
+
+    def fetch_finish(self, ticket: int) -> None:
+        """Second half: blocks until the copies of ``fetch_start`` have arrived; frees the ticket."""
+        try:
+            self._check(self.lib.frs_fetch_finish(self.ctx, ticket))
+        finally:
+            self._inflight.pop(ticket, None)
 
     def new_result(self, sizes, batch: PackedBatch, pinned: bool = False) -> "BatchResult":
         return BatchResult(sizes, batch.n_tints, batch.n_reads, pinned)

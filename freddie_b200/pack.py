@@ -49,6 +49,11 @@ class PackedBatch:
         )
 
     def as_struct(self) -> "_lib.FrsBatch":
+        """The ``frs_batch`` view of the arrays (cached: building ~30 ctypes pointers costs more than enqueueing
+        the batch; the cache is dropped when ``derive_riv`` or the arrays change identity)."""
+        key = (self.derive_riv, tuple(id(v) for v in self.arrays.values()))
+        if getattr(self, "_struct_key", None) == key:
+            return self._struct
         b = _lib.FrsBatch()
         for k, v in self.counts().items():
             setattr(b, k, v)
@@ -59,6 +64,7 @@ class PackedBatch:
             arr = self.arrays[name]
             assert arr.dtype == _DTYPES[name] and arr.flags["C_CONTIGUOUS"], name
             setattr(b, name, arr.ctypes.data_as(C.c_void_p))
+        self._struct, self._struct_key = b, key
         return b
 
     def nbytes(self) -> int:

@@ -151,7 +151,7 @@ int frs_download(frs_context* ctx, const frs_result* out);
 int frs_segment_batch(frs_context* ctx, const frs_batch* batch, const frs_params* prm,
                       frs_result_sizes* sizes);
 
-/* ---- the same hot path, pipelined: up to two batches in flight per context, driven by ONE host thread.
+/* ---- the same hot path, pipelined: up to three batches in flight per context (copy in | kernels | copy out), ONE host thread.
  * The reference overlaps tints with a process pool (imap_unordered, freddie_segment.py:871-876); here the
  * copy of batch k+1 and the read-back of batch k-1 overlap the kernels of batch k on the copy engines.
  *   frs_submit  enqueues the host-to-device copies and every kernel of the run and returns at once (no
@@ -160,10 +160,16 @@ int frs_segment_batch(frs_context* ctx, const frs_batch* batch, const frs_params
  *   frs_wait    blocks until the run is complete and returns the result sizes (if a data-dependent buffer
  *               was too small it is grown and the run repeated first: first batches of a context only).
  *   frs_fetch   copies the results into caller buffers, blocks until they have arrived, frees the ticket.
- * Tickets are slots: at most two may be outstanding, and they complete in submission order. */
+ * Tickets are slots: at most three may be outstanding, and they complete in submission order.  The tail of a
+ * run (clip fetch from pinned host memory, poly-A/T scans) executes on its own stream beside the head of the
+ * next batch. */
 int frs_submit(frs_context* ctx, const frs_batch* batch, const frs_params* prm, int* ticket);
 int frs_wait(frs_context* ctx, int ticket, frs_result_sizes* sizes);
 int frs_fetch(frs_context* ctx, int ticket, const frs_result* out);
+/* frs_fetch in two halves, for a host loop that never blocks on a copy: _start enqueues the device-to-host
+ * copies (after frs_wait), _finish blocks until they have arrived and frees the ticket. */
+int frs_fetch_start(frs_context* ctx, int ticket, const frs_result* out);
+int frs_fetch_finish(frs_context* ctx, int ticket);
 
 /* ---- debug taps for per-step parity tests (values of the LAST frs_run) ---- */
 enum {

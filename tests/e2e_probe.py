@@ -58,23 +58,34 @@ bufs = [e.new_result(s0, batch, pinned=True) for _ in range(2)]
 e.fetch(tk0, bufs[0])
 
 K = 20
+from collections import deque  # noqa: E402
 acc = dict(submit=0.0, wait=0.0, fetch=0.0)
 torch.cuda.synchronize()
 w0 = time.perf_counter()
-prev = None
-for k in range(K + 1):
+fly = deque()
+pending = None
+for k in range(K + 2):
     t0 = time.perf_counter()
-    tk = e.submit(batch, prm) if k < K else None
+    if pending is not None:
+        e.fetch_finish(pending)
+        pending = None
+    ta = time.perf_counter()
+    if k < K:
+        fly.append(e.submit(batch, prm))
     t1 = time.perf_counter()
-    acc["submit"] += t1 - t0
-    if prev is not None:
-        e.wait(prev)
+    acc["fetch"] += ta - t0
+    acc["submit"] += t1 - ta
+    if len(fly) == 3 or (k >= K and fly):
+        pt = fly.popleft()
+        e.wait(pt)
         t2 = time.perf_counter()
-        e.fetch(prev, bufs[k & 1])
+        e.fetch_start(pt, bufs[k & 1])
+        pending = pt
         t3 = time.perf_counter()
         acc["wait"] += t2 - t1
         acc["fetch"] += t3 - t2
-    prev = tk
+if pending is not None:
+    e.fetch_finish(pending)
 torch.cuda.synchronize()
 dt = time.perf_counter() - w0
 print("pipelined, one context: %.3f ms/step (%.1f M reads/s); host time per step: submit %.3f  wait %.3f  fetch %.3f ms" % (

@@ -258,7 +258,7 @@ def test_lazy_clip_fetch_equals_resident_planes(name, golden_set, eng):
 
 
 def test_pipelined_submit_wait_fetch_equals_the_synchronous_calls(golden_set):
-    """frs_submit / frs_wait / frs_fetch: two batches in flight in ONE context (the copies of one overlap the
+    """frs_submit / frs_wait / frs_fetch: up to three batches in flight in ONE context (the copies of one overlap the
     kernels of the other); results must be those of upload + run + download, in any interleaving."""
     from freddie_b200 import _lib
     from freddie_b200.engine import Engine
@@ -288,18 +288,30 @@ def test_pipelined_submit_wait_fetch_equals_the_synchronous_calls(golden_set):
             for a in want[k].arrays:
                 assert np.array_equal(want[k].arrays[a], got[k].arrays[a]), (nme, a)
             assert want[k].sizes == got[k].sizes
-        # a third submit without a fetch is refused; so is a fetch of a free ticket
+        # three batches may be in flight; a fourth submit without a fetch is refused; so is a fetch of a free ticket
         t0 = e.submit(batches[0], prms[0])
         t1 = e.submit(batches[1], prms[1])
+        t2 = e.submit(batches[2], prms[2])
         with pytest.raises(_lib.FrsError, match="in flight"):
-            e.submit(batches[2], prms[2])
-        s0, s1 = e.wait(t0), e.wait(t1)
+            e.submit(batches[3], prms[3])
+        s0, s1, s2 = e.wait(t0), e.wait(t1), e.wait(t2)
         r1 = e.fetch(t1, e.new_result(s1, batches[1]))
+        r2 = e.fetch(t2, e.new_result(s2, batches[2]))
         r0 = e.fetch(t0, e.new_result(s0, batches[0]))
         assert all(np.array_equal(r0.arrays[a], want[0].arrays[a]) for a in r0.arrays)
         assert all(np.array_equal(r1.arrays[a], want[1].arrays[a]) for a in r1.arrays)
+        assert all(np.array_equal(r2.arrays[a], want[2].arrays[a]) for a in r2.arrays)
         with pytest.raises(_lib.FrsError, match="no batch in flight"):
             e.fetch(t0, r0)
+        # fetch in two halves: the copy of one batch is collected behind the submit of another
+        ta = e.submit(batches[4], prms[4])
+        sa = e.wait(ta)
+        ra = e.fetch_start(ta, e.new_result(sa, batches[4], pinned=True))
+        tb = e.submit(batches[0], prms[0])
+        e.fetch_finish(ta)
+        assert all(np.array_equal(ra.arrays[a], want[4].arrays[a]) for a in ra.arrays)
+        rb = e.fetch(tb, e.new_result(e.wait(tb), batches[0]))
+        assert all(np.array_equal(rb.arrays[a], want[0].arrays[a]) for a in rb.arrays)
         # the synchronous calls still work on the same context afterwards
         again = e.segment_batch(batches[3], prms[3])
         assert all(np.array_equal(again.arrays[a], want[3].arrays[a]) for a in again.arrays)
