@@ -309,6 +309,8 @@ def make_shard(args, rank, world, workers):
 def run_cuda_arm(args):
     rank, local_rank, world = rank_env()
     cores = os.cpu_count() or 1
+    # a context drives ~12 streams (copy in / out, head, tail, DP classes): give each its own hardware queue
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     # torchrun pins OMP_NUM_THREADS=1 in its children; the native parser uses OpenMP
     os.environ["OMP_NUM_THREADS"] = str(max(1, cores // max(world, 1)))
     os.environ.setdefault("NCCL_DEBUG", "WARN")  # the version banner goes to stdout at VERSION / INFO: keep stdout to ONE line
@@ -410,17 +412,17 @@ def run_cuda_arm(args):
     d2h = int(sum(v.nbytes for r in res_lazy for v in r.arrays.values())) + len(batches) * 48 * 8
 
     def pipelined(e2, bufs, work):
-        """work: list of batch indices in order.  Three batches in flight (copy in | kernels | copy out); the host
-        thread only ever blocks in frs_wait: the read-back of a batch is started (frs_fetch_start) and collected
-        one iteration later (frs_fetch_finish), behind the submit of the next batch."""
+        """work: list of batch indices in order.  Up to four batches in flight (copy in | head kernels | tail |
+        copy out); the host thread only ever blocks in frs_wait: the read-back of a batch is started
+        (frs_fetch_start) and collected one iteration later (frs_fetch_finish), behind the submit of the next."""
         from collections import deque
         fly = deque()
         pending = None
         for n, i in enumerate(work):
+            fly.append((e2.submit(batches[i], prm), i, n))
             if pending is not None:
                 e2.fetch_finish(pending)
                 pending = None
-            fly.append((e2.submit(batches[i], prm), i, n))
             if len(fly) == 3:
                 pt, pi, pn = fly.popleft()
                 e2.wait(pt)
@@ -539,7 +541,7 @@ def run_cuda_arm(args):
                      e2e_ms_per_gpu=[round(x * 1e3, 4) for x in busy_e2e], e2e_max_over_mean=round(max(busy_e2e) / mean(busy_e2e), 4)),
         e2e=dict(value=e2e_v, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                  timing="wall clock around K steps, synchronize on both sides; frs_submit / frs_wait / frs_fetch with pinned "
-                        "host buffers, three batches in flight per context (copy in | kernels | copy out)",
+                        "host buffers, up to four batches in flight per context (copy in | head kernels | tail | copy out)",
                  one_context_value=tot_reads * args.steps / t_pipe1,
                  contexts_value=tot_reads * args.steps / t_pipe2, contexts=n_ctx,
                  serial_value=tot_reads * args.steps / t_serial,
@@ -569,7 +571,7 @@ def run_cuda_arm(args):
         setup_seconds=round(t_gen, 1),
     )
     if world == 1 and not args.no_cli and tints_for_cpu is not None:
-        line["cli"] = cli_scope(tints_for_cpu, cores)
+        line["cli"] = cli_scope(cores)
     if world == 1 and not args.no_cpu_baseline and tints_for_cpu is not None:
         from oracle import build_ref
         r, c, sample = oracle_rate(tints_for_cpu, cores, int(os.environ.get("FRS_CPU_SAMPLE_READS", 300 * cores * 8)))
@@ -606,32 +608,42 @@ def _upload_bytes(eng, batch, prm):
     return st["h2d_upload"] + st["h2d_run"]
 
 
-def cli_scope(tints, cores):
+def cli_scope(cores):
     """The files-to-files scope of SURVEY.md 8d (what the reference is measured at): SPLIT text on disk ->
-    native parser -> CUDA pipeline -> native formatter -> SEGMENT files, through the drop-in directory driver
-    (`freddie_b200.segment.run_directory`), on a bounded prefix of the workload's tints.  Runs in a child
-    process with a time limit and is never fatal: the kernel-path numbers do not depend on it."""
+    native parser -> CUDA pipeline -> native formatter -> SEGMENT files, over the WHOLE workload of one GPU.
+    `value` is the cold number a user sees: wall clock of a fresh ``python -m freddie_b200.segment`` process
+    (interpreter start, imports, CUDA context creation, every allocation included); `warm_value` is a second
+    pass inside one process (contexts and buffers warm).  Child processes with a time limit, never fatal: the
+    kernel-path numbers do not depend on it."""
     import shutil
     import tempfile
     try:
         from freddie_b200 import synth
-        n_target = int(os.environ.get("FRS_CLI_SAMPLE_READS", "50000"))
-        sample, n = [], 0
-        for t in tints:
-            sample.append(t)
-            n += len(t["reads"])
-            if n >= n_target:
-                break
         work = tempfile.mkdtemp(prefix="frs_bench_cli_")
         try:
             sd = os.path.join(work, "split")
-            synth.write_split_dir(sample, sd)
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cli-run", work, "--cli-threads", str(cores)],
-                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=240)
+            jobs = synth.config_jobs(2)
+            made = synth.write_jobs(jobs, sd, workers=max(1, min(32, cores)))
+            n_reads = sum(m[2] for m in made)
+            split_bytes = sum(os.path.getsize(os.path.join(b, f)) for b, _, fs in os.walk(sd) for f in fs)
+            od = os.path.join(work, "seg_cold")
+            t0 = time.perf_counter()
+            r = subprocess.run([sys.executable, "-m", "freddie_b200.segment", "-s", sd, "-o", od, "-t", str(cores)],
+                               cwd=ROOT, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, timeout=300)
+            cold = time.perf_counter() - t0
             if r.returncode != 0:
                 return dict(value=None, unit=UNIT, error=(r.stderr.strip().splitlines() or ["exit %d" % r.returncode])[-1][:300])
-            out = json.loads(r.stdout.strip().splitlines()[-1])
-            out["sample"] = "first %d tints of the workload: %s" % (len(sample), out.pop("sample"))
+            n_files = sum(len(fs) for _, _, fs in os.walk(od))
+            out = dict(value=n_reads / cold, unit=UNIT, seconds=round(cold, 3), host_threads=cores,
+                       sample="whole workload: %d tints, %d reads, %.0f MB of SPLIT text in, %d files out" % (
+                           len(made), n_reads, split_bytes / 1e6, n_files),
+                       scope="files to files, cold: a fresh `python -m freddie_b200.segment -s SPLIT -o OUT -t %d` process "
+                             "(interpreter, imports, CUDA context creation and all allocations inside the wall clock)" % cores)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cli-run", work, "--cli-threads", str(cores)],
+                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+            if r.returncode == 0:
+                w = json.loads(r.stdout.strip().splitlines()[-1])
+                out.update(warm_value=w["value"], warm_seconds=w["seconds"], in_process_first_run_seconds=w["first_run_seconds"])
             return out
         finally:
             shutil.rmtree(work, ignore_errors=True)
@@ -640,26 +652,20 @@ def cli_scope(tints, cores):
 
 
 def cli_run(work, threads):
-    """Child of cli_scope: the directory driver twice over work/split (first run warms the CUDA contexts and
-    the library's buffers), one JSON object on stdout."""
+    """Child of cli_scope: the directory driver twice over work/split inside ONE process (the second pass has
+    warm CUDA contexts and buffers), one JSON object on stdout."""
     import shutil
     from freddie_b200.engine import SegmentParams
     from freddie_b200.segment import run_directory
     sd, od = os.path.join(work, "split"), os.path.join(work, "seg")
-    split_bytes = sum(os.path.getsize(os.path.join(b, f)) for b, _, fs in os.walk(sd) for f in fs)
     t0 = time.perf_counter()
     run_directory(sd, od, SegmentParams(), threads=threads, gpus=1, progress=False)
-    cold = time.perf_counter() - t0
+    first = time.perf_counter() - t0
     shutil.rmtree(od, ignore_errors=True)
     t0 = time.perf_counter()
     st = run_directory(sd, od, SegmentParams(), threads=threads, gpus=1, progress=False)
     dt = time.perf_counter() - t0
-    n_files = sum(len(fs) for _, _, fs in os.walk(od))
-    print(json.dumps(dict(
-        value=st["reads"] / dt, unit=UNIT, seconds=round(dt, 4), first_run_seconds=round(cold, 4), host_threads=threads,
-        sample="%d reads, %.0f MB of SPLIT text in, %d files out" % (st["reads"], split_bytes / 1e6, n_files),
-        scope="files to files: native parser -> CUDA pipeline -> native formatter (second run of the process: CUDA "
-              "contexts warm; first_run_seconds includes their creation)")))
+    print(json.dumps(dict(value=st["reads"] / dt, unit=UNIT, seconds=round(dt, 4), first_run_seconds=round(first, 4))))
 
 
 def _download_into(eng, res):

@@ -43,7 +43,8 @@ BATCH_ARRAYS = [
 
 class FrsBatch(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in BATCH_COUNTS] + [("n_seq_words", C.c_int64)]
-                + [(n, _p) for n in BATCH_ARRAYS])
+                + [(n, _p) for n in BATCH_ARRAYS]
+                + [("seq_edge_words", C.c_int32), ("reserved0", C.c_int32), ("seq_edge", _p)])
 
 
 class FrsResultSizes(C.Structure):
@@ -130,7 +131,7 @@ def load():
         lib.frs_packed_read.restype = C.c_int
         lib.frs_packed_write_segment.argtypes = [_p, C.POINTER(FrsResult), C.c_char_p, C.c_char_p, C.c_size_t]
         lib.frs_packed_write_segment.restype = C.c_int
-    if lib.frs_abi_version() != 1:
+    if lib.frs_abi_version() != 2:
         raise FrsError(-101, "ABI version mismatch")
     _lib = lib
     return lib

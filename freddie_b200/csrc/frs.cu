@@ -24,7 +24,7 @@ static thread_local char g_err[512] = "";
 #ifndef DP_BIG_THREADS
 #define DP_BIG_THREADS 1024  // CTA size of the DP kernel for subproblems with more than 32 candidates
 #endif
-#define FRS_SLOTS 3          // batches in flight per context (frs_submit / frs_wait / frs_fetch): copy in | kernels | copy out
+#define FRS_SLOTS 4          // batches in flight per context: copy in | head kernels | tail | copy out
 
 struct DBuf {
   void* p = nullptr;
@@ -53,6 +53,8 @@ struct Slot {
   // working set of the run's TAIL (clip fetch, poly-A/T scans, head fields): it runs on its own stream beside
   // the head of the next batch, so it owns its buffers
   DBuf b_clip_n, b_clip_words, b_clip_off, b_clip_a, b_clip_t, b_task_order, b_task_res, b_poly_cls, b_poly_flag, b_bsum_tail;
+  DBuf b_seq_edge, b_clip_eoff;  // edge store of the batch (input) and the clips' offsets into it
+  int edge_words = 0;            // > 0: the edge store is in use for this batch
   frs_batch hb;  // sizes of the batch; its pointers are not used after the upload
   int n_sig_work = 0, n_sig_direct = 0, n_tiles = 0, n_cov_tiles = 0, n_dig_tiles = 0;
   i64 est_P = 0, est_dig = 0;  // first guesses of the data-dependent capacities (from the batch's shape)
@@ -619,9 +621,14 @@ static int stage_upload(frs_context* c, Slot& S, const frs_batch* b) {
       S.seq_resident = false;
     }
   }
+  S.edge_words = 0;
   if (S.seq_resident) {
     H2D(b_seq_a, b->seq_is_a, (size_t)b->n_seq_words * 4);
     H2D(b_seq_t, b->seq_is_t, (size_t)b->n_seq_words * 4);
+  } else if (b->seq_edge && b->seq_edge_words > 0 && b->seq_edge_words <= 64) {
+    // dense copy of every read's first / last plane words: most clips never touch the bus again
+    S.edge_words = b->seq_edge_words;
+    H2D(b_seq_edge, b->seq_edge, (size_t)N * 4 * (size_t)S.edge_words * 4);
   }
   // owner tables (tint of every island / rep / read) are derived on the device
   ENSS(b_island_tint, (size_t)NI * 4);
@@ -745,8 +752,8 @@ static int enqueue_run(frs_context* c, Slot& S) {
   ENS(b_cand_flat, KMAX * 4);
   ENS(b_vbuf, L * 8);
   ENS(b_tint_pos_off, (size_t)(T + 1) * 4);
-  const size_t n_chunks = ((size_t)S.n_tiles + SM_CHUNK - 1) / SM_CHUNK;
-  ENS(b_tile_state, (n_chunks + n_chunks / SM_GROUP + 1) * 8 + sizeof(SmoothSync) + (size_t)S.n_tiles * (2 * TILE_WORDS * 4 + 16) + 64);
+  const size_t n_groups = (size_t)S.n_tiles / TILE_GROUP + 1;
+  ENS(b_tile_state, n_groups * 8 + (size_t)S.n_tiles * (2 * TILE_WORDS * 4 + 4) + 64);
   ENS(b_thr, (size_t)T * 8);
   {
     size_t nh = (size_t)L / 8 + 64 * (size_t)T + 64;  // heap scratch of the giant tints (see k_threshold)
@@ -801,6 +808,7 @@ static int enqueue_run(frs_context* c, Slot& S) {
   ENSS(b_poly_cls, (2 * POLY_CLASSES + 1) * 4);
   ENSS(b_poly_flag, (size_t)N * 4);
   ENSS(b_bsum_tail, ((size_t)N * 2 / SCAN_TILE + 2) * 8);
+  if (S.edge_words) ENSS(b_clip_eoff, (size_t)N * 8);
   if (!S.seq_resident) {
     ENSS(b_clip_a, cp.clipw * 4);
     ENSS(b_clip_t, cp.clipw * 4);
@@ -852,28 +860,22 @@ static int enqueue_run(frs_context* c, Slot& S) {
 
   stage_begin(c, "smooth");
   {
-    // group totals | sync words | chunk totals | per tile: candidate / positive ballot words, packed counts
-    const size_t n_groups = n_chunks / SM_GROUP + 1;
-    unsigned long long* d_gtot = c->b_tile_state.as<unsigned long long>();
-    SmoothSync* d_sync = (SmoothSync*)(d_gtot + n_groups);
-    unsigned long long* d_ctot = (unsigned long long*)(d_sync + 1);
-    u32* d_cmask = (u32*)(d_ctot + n_chunks);
+    // group totals | per tile: candidate / positive ballot words, packed counts
+    unsigned long long* d_gsum = c->b_tile_state.as<unsigned long long>();
+    u32* d_cmask = (u32*)(d_gsum + n_groups);
     u32* d_pmask = d_cmask + (size_t)S.n_tiles * TILE_WORDS;
     u32* d_tcnt = d_pmask + (size_t)S.n_tiles * TILE_WORDS;
-    CK(cudaMemsetAsync(d_gtot, 0, (n_groups + n_chunks) * 8 + sizeof(SmoothSync), st));  // group totals, sync, chunk totals
-    const size_t sm = (size_t)wq_smem_layout(lw).total;
-    if (sm > 48 * 1024) CK(cudaFuncSetAttribute(k_smooth_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_smooth_lists, GAUSS_THREADS, sm));
-    if (occ < 1) return fail(c, FRS_ERR_LIMIT, "k_smooth_lists does not fit an SM at sigma = %g", prm->sigma);
-    // persistent, with a grid-wide barrier: the grid is what fits the machine when the kernel has it alone, so
-    // every CTA becomes resident (kernels of the previous batch's tail that hold SM slots finish on their own;
-    // a cooperative launch would wait for an EMPTY machine and serialise the head behind that tail)
-    const int grid = (int)std::min<i64>((i64)n_chunks, (i64)occ * c->n_sm);
-    k_smooth_lists<<<grid, GAUSS_THREADS, sm, st>>>(S.b_tiles.as<TileWork>(), S.n_tiles, d_island_tint, d_tint_island_off, T,
-                                                    c->b_yraw.as<int>(), d_gw, lw, c->b_y.as<double>(), d_cmask, d_pmask,
-                                                    d_tcnt, d_ctot, d_gtot, d_sync, c->b_cand_flat.as<int>(),
-                                                    c->b_vbuf.as<double>(), c->b_tint_pos_off.as<int>(), d_cnt + CNT_K);
+    CK(cudaMemsetAsync(d_gsum, 0, n_groups * 8, st));
+    const size_t sm = (size_t)p1_smem_layout(lw).total;
+    if (sm > 48 * 1024) CK(cudaFuncSetAttribute(k_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_smooth<<<S.n_tiles, GAUSS_THREADS, sm, st>>>(S.b_tiles.as<TileWork>(), d_island_sample_off, c->b_yraw.as<int>(),
+                                                    d_gw, lw, c->b_y.as<double>(), d_cmask, d_pmask, d_tcnt, d_gsum);
+    LAUNCHED();
+    stage_begin(c, "lists");
+    k_tile_lists<<<S.n_tiles, GAUSS_THREADS, 0, st>>>(S.b_tiles.as<TileWork>(), S.n_tiles, d_island_sample_off,
+                                                       d_island_tint, d_tint_island_off, T, d_cmask, d_pmask, d_tcnt,
+                                                       d_gsum, c->b_y.as<double>(), c->b_cand_flat.as<int>(),
+                                                       c->b_vbuf.as<double>(), c->b_tint_pos_off.as<int>(), d_cnt + CNT_K);
     LAUNCHED();
   }
 
@@ -946,6 +948,13 @@ static int enqueue_run(frs_context* c, Slot& S) {
     A.cnt = d_cnt; A.caps = cp; A.bases = c->b_bases.as<int>(); A.cursor = c->b_cursor.as<int>();
     A.m_cap = dp_max_n;
     const DpWork* wl = c->b_work.as<DpWork>();
+    // persistent CTAs per SM of the six classes (development knob: FRS_DP_GRIDS="8,3,6,3,1,1")
+    static int dp_cps[DP_CLASSES] = {8, 3, 6, 3, 1, 1};
+    static bool dp_cps_read = false;
+    if (!dp_cps_read) {
+      dp_cps_read = true;
+      if (const char* e = getenv("FRS_DP_GRIDS")) sscanf(e, "%d,%d,%d,%d,%d,%d", &dp_cps[0], &dp_cps[1], &dp_cps[2], &dp_cps[3], &dp_cps[4], &dp_cps[5]);
+    }
     // the classes are independent: persistent launches on side streams, so that the few long CTAs of the
     // large classes overlap the many short items of the small ones (fork / join with events)
     CK(cudaEventRecord(c->ev_fork, st));
@@ -956,11 +965,11 @@ static int enqueue_run(frs_context* c, Slot& S) {
       cudaStream_t ks = c->side[sidx];
       CK(cudaStreamWaitEvent(ks, c->ev_fork, 0));
       switch (k) {
-        case 0: k_dp_warp<8><<<148 * 8, DPW_WARPS * 32, DPW_WARPS * sizeof(DpWarpSmem<8>), ks>>>(A, wl, 0); break;
-        case 1: k_dp_warp<16><<<148 * 3, DPW_WARPS * 32, DPW_WARPS * sizeof(DpWarpSmem<16>), ks>>>(A, wl, 1); break;
-        case 2: { const int sm = dp_smem_layout(16, DPT_MAXW, 1).total; k_dp<128><<<148 * 6, 128, sm, ks>>>(A, wl, 2, sm); break; }
-        case 3: { const int sm = dp_smem_layout(32, DPT_MAXW, 1).total; k_dp<256><<<148 * 3, 256, sm, ks>>>(A, wl, 3, sm); break; }
-        default: { const int sm = 226 * 1024; k_dp<DP_BIG_THREADS><<<148, DP_BIG_THREADS, sm, ks>>>(A, wl, k, sm); break; }
+        case 0: k_dp_warp<8><<<c->n_sm * dp_cps[0], DPW_WARPS * 32, DPW_WARPS * sizeof(DpWarpSmem<8>), ks>>>(A, wl, 0); break;
+        case 1: k_dp_warp<16><<<c->n_sm * dp_cps[1], DPW_WARPS * 32, DPW_WARPS * sizeof(DpWarpSmem<16>), ks>>>(A, wl, 1); break;
+        case 2: { const int sm = dp_smem_layout(16, DPT_MAXW, 1).total; k_dp<128><<<c->n_sm * dp_cps[2], 128, sm, ks>>>(A, wl, 2, sm); break; }
+        case 3: { const int sm = dp_smem_layout(32, DPT_MAXW, 1).total; k_dp<256><<<c->n_sm * dp_cps[3], 256, sm, ks>>>(A, wl, 3, sm); break; }
+        default: { const int sm = 226 * 1024; k_dp<DP_BIG_THREADS><<<c->n_sm * dp_cps[k], DP_BIG_THREADS, sm, ks>>>(A, wl, k, sm); break; }
       }
       LAUNCHED();
       CK(cudaEventRecord(c->ev_join[sidx], ks));
@@ -1061,6 +1070,9 @@ static int enqueue_run(frs_context* c, Slot& S) {
     G.task_order = S.b_task_order.as<int>(); G.task_res = S.b_task_res.as<PolyRes>();
     G.long_class = c->opt_poly_long_class;
     G.cnt = d_cnt; G.caps = cp;
+    G.edge = S.edge_words ? S.b_seq_edge.as<u32>() : nullptr;
+    G.edge_words = S.edge_words;
+    G.clip_eoff = S.edge_words ? S.b_clip_eoff.as<int>() : nullptr;
     k_gap_prep<<<cdiv(N, 128), 128, 0, st>>>(G); LAUNCHED();
     k_gap_sizes<<<gs_grid((i64)N * 2, 128, 148 * 8), 128, 0, st>>>(G); LAUNCHED();
     stage_end(c);
@@ -1077,8 +1089,10 @@ static int enqueue_run(frs_context* c, Slot& S) {
       // the caller's pinned planes
       { int r = scan_exclusive_on<int, i64>(c, tl, S.b_bsum_tail, S.b_clip_words.as<int>(), (i64)N * 2, S.b_clip_off.as<i64>()); if (r) return r; }
       CK(cudaMemcpyAsync(d_cnt + CNT_CLIPW, S.b_clip_off.as<i64>() + (i64)N * 2, 8, cudaMemcpyDeviceToDevice, tl));
-      // few CTAs: the kernel waits on the bus, and the SMs belong to the head of the next batch meanwhile
-      k_clip_gather<<<c->n_sm, 256, 0, tl>>>(G, S.zc_a, S.zc_t, S.b_clip_a.as<u32>(), S.b_clip_t.as<u32>());
+      // a few CTAs only: the kernel waits on the bus (the bus allows a few hundred reads in flight, not tens of
+      // thousands), and loads from host memory that are pending for microseconds fill the miss queues of the SM
+      // they run on -- the other SMs belong to the head of the next batch meanwhile
+      k_clip_gather<<<S.edge_words ? 24 : c->n_sm, 256, 0, tl>>>(G, S.zc_a, S.zc_t, S.b_clip_a.as<u32>(), S.b_clip_t.as<u32>());
       LAUNCHED();
     }
     stage_begin(c, "poly", tl);

@@ -142,7 +142,9 @@ __global__ void k_fixed_b(const i64* __restrict__ n_cand_p, const int* __restric
 // ---------------------------------------------------------------------------------------------
 #define DP_CLASSES 6
 #define DP_SMEM_MAX_N 56
+#ifndef DP_WARP_MAX_WORDS
 #define DP_WARP_MAX_WORDS 16
+#endif
 // counter slots (i64) written by k_sub_plan
 #define PLAN_WORK 0     // [6] work items per class
 #define PLAN_MAXN 6     // [6] largest n per class

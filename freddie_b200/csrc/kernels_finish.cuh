@@ -399,7 +399,22 @@ struct GapArgs {
   int long_class;     // tasks of classes >= long_class go to k_poly_long (default POLY_LONG_CLASS)
   const i64* cnt;     // device counters + capacities of the run (guards)
   Caps caps;
+  // edge store (lazy sequence mode, optional): first / last edge_words plane words of every read, resident
+  const u32* edge;    // [n_reads][2 sides][2 planes][edge_words] or NULL
+  int edge_words;
+  int* clip_eoff;     // [2N] >= 0: the clip's words start at edge + clip_eoff (plane A; plane T at + edge_words);
+                      //       -1: they are in seq_a / seq_t at clip_off
 };
+
+// first plane word of a clip: the edge store when the clip fits one of its blocks, else the (gathered or
+// resident) plane arrays
+__device__ __forceinline__ const u32* clip_plane(const GapArgs& A, int clip, bool plane_a) {
+  if (A.edge) {
+    const int eo = A.clip_eoff[clip];
+    if (eo >= 0) return A.edge + eo + (plane_a ? 0 : A.edge_words);
+  }
+  return (plane_a ? A.seq_a : A.seq_t) + A.clip_off[clip];
+}
 
 // forward_thread_cigar (:289-304): every op length, insertions included, is clipped by the remaining
 // target distance.  Returns false if the CIGAR is exhausted before reaching t_goal.
@@ -496,17 +511,23 @@ __global__ void __launch_bounds__(128) k_gap_prep(GapArgs A) {
         head[6] = q_esc;
         const int ns = q_ssc, ne = L - q_esc;
         const bool minus = A.read_strand[i] != 0;
-        if (ns >= 20) {
-          cn[0] = ns;
-          const ClipGeo g = clip_geometry(L, ns, true, minus);
-          cw[0] = g.n_words;
-          if (A.seq_resident) A.clip_off[2 * (i64)i] = A.read_seq_off[i] + g.w_first;
-        }
-        if (ne >= 20) {
-          cn[1] = ne;
-          const ClipGeo g = clip_geometry(L, ne, false, minus);
-          cw[1] = g.n_words;
-          if (A.seq_resident) A.clip_off[2 * (i64)i + 1] = A.read_seq_off[i] + g.w_first;
+        const int nwr = (L + 31) >> 5;  // plane words of the read
+        for (int side = 0; side < 2; ++side) {  // 0: start clip, 1: end clip
+          const int nb = side == 0 ? ns : ne;
+          if (nb < 20) continue;
+          cn[side] = nb;
+          const ClipGeo g = clip_geometry(L, nb, side == 0, minus);
+          if (A.edge && g.n_words <= A.edge_words) {
+            // the clip lies inside the read's first or last edge_words plane words: read it from the edge store
+            const bool at_begin = (side == 0) != minus;
+            const int idx = at_begin ? 0 : g.w_first - max(0, nwr - A.edge_words);
+            A.clip_eoff[2 * (i64)i + side] = (int)((((i64)i * 2 + (at_begin ? 0 : 1)) * 2) * A.edge_words + idx);
+            cw[side] = 0;
+          } else {
+            if (A.edge) A.clip_eoff[2 * (i64)i + side] = -1;
+            cw[side] = g.n_words;
+            if (A.seq_resident) A.clip_off[2 * (i64)i + side] = A.read_seq_off[i] + g.w_first;
+          }
         }
         // unaligned gaps between consecutive 1-runs (:455-471): (l1, f2, owner); k_gap_sizes fills the size
         int* rec = A.gap_rec + (i64)A.read_gap_off[i] * 3;
@@ -576,7 +597,7 @@ __global__ void __launch_bounds__(128) k_poly_filter(GapArgs A, u8* __restrict__
     if (n >= 20) {
       const bool minus = A.read_strand[i] != 0;
       const bool want_a = (which & 1) == 0;
-      const u32* pl = ((want_a != minus) ? A.seq_a : A.seq_t) + A.clip_off[clip];
+      const u32* pl = clip_plane(A, clip, want_a != minus);
       const ClipGeo geo = clip_geometry(A.read_len[i], n, which < 2, minus);
       const int last = geo.idx0 + geo.step * (n - 1);
       const int b_lo = min(geo.idx0, last), b_hi = max(geo.idx0, last);  // clip bits, relative to the first word
@@ -641,7 +662,7 @@ __global__ void __launch_bounds__(128) k_poly_scan(GapArgs A) {
   const bool minus = A.read_strand[i] != 0;
   const bool want_a = (which & 1) == 0;
   // '+': seq[..] == ch; '-': reversed read, complemented target base (:392-401, :422-431)
-  const u32* pl = ((want_a != minus) ? A.seq_a : A.seq_t) + A.clip_off[clip];
+  const u32* pl = clip_plane(A, clip, want_a != minus);
   const ClipGeo geo = clip_geometry(A.read_len[i], n, which < 2, minus);
   const int step = geo.step;
   int idx = geo.idx0;
@@ -731,7 +752,7 @@ __global__ void __launch_bounds__(128) k_poly_long(GapArgs A) {
     const int n = A.clip_n[clip];
     const bool minus = A.read_strand[i] != 0;
     const bool want_a = (which & 1) == 0;
-    const u32* pl = ((want_a != minus) ? A.seq_a : A.seq_t) + A.clip_off[clip];
+    const u32* pl = clip_plane(A, clip, want_a != minus);
     const ClipGeo geo = clip_geometry(A.read_len[i], n, which < 2, minus);
     const int nwords = geo.n_words, step = geo.step, idx_start = geo.idx0;
     bool open = false;

@@ -112,9 +112,13 @@ __global__ void __launch_bounds__(SIG_THREADS) k_signal(const SigWork* __restric
 //      1 <= a, b <= n-2, y[a-1] < y[m] > y[b+1], and m == (a+b)>>1.
 //   3. per 32 samples one ballot word of candidates and one of positive samples (the input of the
 //      variance threshold, :757-759), plus the two counts of the tile.
-// A second phase of the same launch then writes the ordered candidate list and the ordered positive samples
-// from the masks (k_smooth_lists below).  HBM traffic: 4 B read + 8 B written per sample, 1/4 B of masks, and
-// the positive samples once more.
+// k_tile_lists then writes the ordered candidate list and the ordered positive samples from the
+// masks (its offsets come from a two-level sum of the tile counts, no device-wide scan).  HBM traffic
+// of the two: 4 B read + 8 B written per sample, 1/4 B of masks, and the positive samples once more.
+// (Tried on B200 and dropped, byte-identical but slower: ordered lists by decoupled look-back inside k_smooth;
+// one persistent launch with a grid barrier between the two phases, 382 us against 263 + 91 us; the same with
+// warp-level quarter tiles, 430-470 us -- the per-tile fixed cost, ~400 warp instructions, is what dominates,
+// and smaller units pay it more often.)
 // ---------------------------------------------------------------------------------------------
 #define TILE_SAMPLES 1024
 #define GAUSS_THREADS 128
@@ -137,22 +141,6 @@ __host__ __device__ inline P1Smem p1_smem_layout(int lw) {
   s.nz = o; o += ((span + 127) / 128 * 4 + 2) * 4;
   s.red = o; o += 16 * 4;
   s.total = (o + 15) & ~15;
-  return s;
-}
-
-// k_smooth_lists: per-warp slices (a warp stages, smooths and scans one quarter of a tile on its own)
-#define WQ_WORDS 8  // 32-sample words per quarter
-struct WqSmem { int yout, ext, nz, per_warp, wd, total; };
-__host__ __device__ inline WqSmem wq_smem_layout(int lw) {
-  const int H = (lw + 1 + 31) >> 5;
-  WqSmem s;
-  int o = 0;
-  s.yout = o; o += (WQ_WORDS * 32 + 2) * 8;
-  s.ext = o; o += (WQ_WORDS + 2 * H) * 32 * 4;
-  s.nz = o; o += (WQ_WORDS + 2 * H + 2) * 4;
-  s.per_warp = (o + 15) & ~15;
-  s.wd = s.per_warp * (GAUSS_THREADS / 32);
-  s.total = (s.wd + (lw + 1) * 8 + 15) & ~15;
   return s;
 }
 
@@ -203,248 +191,198 @@ __device__ double gauss_global(const int* __restrict__ yr, int n, int x, const d
   return acc;
 }
 
-// ---------------------------------------------------------------------------------------------
-// k_smooth_lists: ONE persistent, cooperative launch for steps 1-3 above AND the ordered lists.
-//   phase A  the CTAs take chunks of SM_CHUNK consecutive tiles from a cursor (work stealing: live and dead
-//            tiles differ in cost).  Per tile: stage the raw samples, Gaussian, candidate / positive ballot
-//            words, counts.  The Gaussian weights are loaded once per CTA, the loops over the 32-sample words
-//            stop at the end of the tile (a median island is half a tile).  A chunk publishes the totals of
-//            its tiles.
-//   barrier  every CTA of the grid is resident (cooperative launch): one counter.
-//   phase B  chunks again; the offsets of a chunk into the ordered candidate list and the ordered positive
-//            samples = totals of the chunk groups before it + totals of the earlier chunks of its group (one
-//            short strided sum per chunk), then its tiles in order with running offsets.  The ballot words of phase A are still in L2.
-// Replaces the two launches k_smooth + k_tile_lists (one pass less over the tile descriptors and the counts,
-// no per-tile prefix over up to 1024 earlier tiles, no per-tile CTA launch).
-// ---------------------------------------------------------------------------------------------
-#ifndef SM_CHUNK
-#define SM_CHUNK 4       // tiles per chunk (unit of the work stealing and of the list offsets)
-#endif
-#define SM_GROUP 64      // chunks per group of the two-level offset sum
-struct SmoothSync { int cursor_a; int arrived; int cursor_b; int pad; };  // zeroed before the launch
+#define TILE_GROUP 1024  // tiles per group of the two-level count prefix
 
-__device__ __forceinline__ int ld_acquire_i32(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-#ifndef SMOOTH_MIN_CTAS
-#define SMOOTH_MIN_CTAS 8
-#endif
-__global__ void __launch_bounds__(GAUSS_THREADS, SMOOTH_MIN_CTAS) k_smooth_lists(
-    const TileWork* __restrict__ tiles, int n_tiles, const int* __restrict__ island_tint,
-    const int* __restrict__ tint_island_off, int n_tints, const int* __restrict__ y_raw, const double* __restrict__ gw,
-    int lw, double* __restrict__ y, u32* __restrict__ cmask, u32* __restrict__ pmask, u32* __restrict__ tile_cnt,
-    unsigned long long* __restrict__ chunk_tot, unsigned long long* __restrict__ group_tot /* zeroed */,
-    SmoothSync* __restrict__ sync, int* __restrict__ cand_flat,
-    double* __restrict__ vbuf, int* __restrict__ tint_pos_off, i64* __restrict__ n_cand_out) {
+__global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __restrict__ tiles,
+                                                         const int* __restrict__ island_sample_off,
+                                                         const int* __restrict__ y_raw,
+                                                         const double* __restrict__ gw, int lw,
+                                                         double* __restrict__ y, u32* __restrict__ cmask,
+                                                         u32* __restrict__ pmask, u32* __restrict__ tile_cnt,
+                                                         unsigned long long* __restrict__ group_sum /* zeroed */) {
   extern __shared__ __align__(16) unsigned char p1sm[];
-  __shared__ int s_chunk;
-  __shared__ unsigned long long s_red64[GAUSS_THREADS / 32];
-  static_assert(TILE_SAMPLES == 4 * WQ_WORDS * 32, "a tile is four quarters");
-  __shared__ int pre_c[TILE_WORDS], pre_p[TILE_WORDS];
+  const P1Smem Lo = p1_smem_layout(lw);
+  double* wd = (double*)(p1sm + Lo.wd);
+  int* ext = (int*)(p1sm + Lo.ext);          // raw tile + halo (int32 counts)
+  double* yout = (double*)(p1sm + Lo.yout);  // yout[1 + x] = y of tile sample x; [0], [cnt+1] = neighbours
+  u32* nz = (u32*)(p1sm + Lo.nz);            // bit s: staged sample s is non-zero
+  int* red = (int*)(p1sm + Lo.red);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const WqSmem Lo = wq_smem_layout(lw);
-  unsigned char* wsm = p1sm + (size_t)warp * Lo.per_warp;  // this warp's slice
-  double* yout = (double*)(wsm + Lo.yout);  // yout[1 + x] = y of quarter sample x; [0], [qcnt+1] = neighbours
-  int* ext = (int*)(wsm + Lo.ext);          // raw quarter + halo words (int32 counts)
-  u32* nz = (u32*)(wsm + Lo.nz);            // bit s: staged sample s is non-zero
-  double* wd = (double*)(p1sm + Lo.wd);     // shared by the warps
-  const int n_chunks = (n_tiles + SM_CHUNK - 1) / SM_CHUNK;
-  for (int d = tid; d <= lw; d += GAUSS_THREADS) wd[d] = gw[lw - d];  // once per CTA
-
-  // ================================ phase A ================================
-  // Warp-level units: a tile is cut into quarters of WQ_WORDS words (256 samples), every quarter is staged,
-  // smoothed and scanned for candidates by ONE warp in its own slice of shared memory -- no CTA-wide barrier
-  // inside a chunk, and a short island (median: half a tile) costs only the quarters it has.
-  const int H = (lw + 1 + 31) >> 5;  // halo words on each side of a quarter (one extra sample for the neighbours)
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) s_chunk = atomicAdd(&sync->cursor_a, 1);
-    __syncthreads();
-    const int chunk = s_chunk;
-    if (chunk >= n_chunks) break;
-    const int t_lo = chunk * SM_CHUNK, t_hi = min(n_tiles, t_lo + SM_CHUNK);
-    unsigned long long tot = 0;  // candidates | positives << 32 of this warp's quarters
-    int unit = 0;
-    for (int tile = t_lo; tile < t_hi; ++tile) {
-      const TileWork tw = tiles[tile];
-      const int n = tw.n;
-      const int cnt = min(TILE_SAMPLES, n - tw.lo);
-      const int nq = (cnt + WQ_WORDS * 32 - 1) / (WQ_WORDS * 32);
-      const int* yr = y_raw + tw.f0;
-      for (int q = 0; q < nq; ++q, ++unit) {
-        if ((unit & (GAUSS_THREADS / 32 - 1)) != warp) continue;  // the quarters of the chunk, dealt to the warps
-        const int q0 = q * (WQ_WORDS * 32);
-        const int qcnt = min(WQ_WORDS * 32, cnt - q0);
-        const int nw = (qcnt + 31) >> 5;
-        const int nsw = nw + 2 * H;
-        const int base = tw.lo + q0 - H * 32;  // island sample of staged sample 0
-        const bool interior = base >= 0 && base + nsw * 32 <= n;
-        const int n2 = 2 * n;
-        __syncwarp();
-        u32 wm = 0;  // bit w: staged word w has a non-zero sample
-#pragma unroll 5
-        for (int sw = 0; sw < nsw; ++sw) {
-          const int j0 = base + sw * 32 + lane;
-          int j = j0;
-          if (!interior) {
-            // scipy's reflect (d c b a | a b c d | d c b a): one fold covers every island longer than the halo
-            if (j0 < 0) j = -1 - j0;
-            else if (j0 >= n) j = n2 - 1 - j0;
-            if ((unsigned)j >= (unsigned)n) {  // island shorter than the halo: general period-2n fold
-              j = j0 % n2;
-              if (j < 0) j += n2;
-              if (j >= n) j = n2 - 1 - j;
-            }
-          }
-          const int v = yr[j];
-          ext[sw * 32 + lane] = v;
-          const u32 m = __ballot_sync(0xffffffffu, v != 0);
-          if (lane == 0) nz[sw] = m;
-          wm |= (m != 0u ? 1u : 0u) << sw;
+  const TileWork tw = tiles[blockIdx.x];
+  const int f0 = tw.f0;
+  const int n = tw.n;
+  const int cnt = min(TILE_SAMPLES, n - tw.lo);
+  const int* yr = y_raw + f0;
+  for (int d = tid; d <= lw; d += GAUSS_THREADS) wd[d] = gw[lw - d];
+  const int span = cnt + 2 * lw + 2;
+  const int first = tw.lo - lw - 1;
+  const int span_r = (span + GAUSS_THREADS - 1) / GAUSS_THREADS * GAUSS_THREADS;
+  const bool interior = first >= 0 && first + span <= n;
+  const int n2 = 2 * n;
+  for (int s = tid; s < span_r; s += GAUSS_THREADS) {  // whole warps: the ballot needs every lane
+    int v = 0;
+    if (s < span) {
+      const int j0 = first + s;
+      int j = j0;
+      if (!interior) {
+        // scipy's reflect (d c b a | a b c d | d c b a): one fold covers every island longer than the halo
+        if (j0 < 0) j = -1 - j0;
+        else if (j0 >= n) j = n2 - 1 - j0;
+        if ((unsigned)j >= (unsigned)n) {  // island shorter than the halo: general period-2n fold
+          j = j0 % n2;
+          if (j < 0) j += n2;
+          if (j >= n) j = n2 - 1 - j;
         }
-        if (lane < 2) nz[nsw + lane] = 0u;
-        __syncwarp();
-        const int c0 = H * 32;                       // staged index of the quarter's first sample
-        const int fq = tw.f0 + tw.lo + q0;           // its flat sample
-        u32 live = 0;  // bit xw: word xw has a non-zero input near its window (else its y is all 0)
-        if (wm == 0u) {
-          for (int xw = 0; xw < nw; ++xw)
-            if (xw * 32 + lane < qcnt) y[fq + xw * 32 + lane] = 0.0;
-        } else {
-          for (int xw = 0; xw < nw; ++xw) {
-            const int x = xw * 32 + lane;
-            // inputs of this word: staged samples [c0 + 32 xw - lw, c0 + 32 xw + 31 + lw]; testing the whole mask
-            // words that hold them is conservative (a false positive only filters zeros: same bits)
-            const int w_a = (c0 + xw * 32 - lw) >> 5, w_b = (c0 + xw * 32 + 31 + lw) >> 5;
-            const bool any = ((wm >> w_a) & ((2u << (w_b - w_a)) - 1u)) != 0u;
-            double v = 0.0;
-            if (any) {
-              live |= 1u << xw;
-              if (x < qcnt) v = gauss_sparse(ext, nz, wd, lw, c0 + x);
-            }
-            if (x < qcnt) {
-              y[fq + x] = v;
-              yout[1 + x] = v;
-            }
-          }
-          if (lane == 0) yout[0] = gauss_sparse(ext, nz, wd, lw, c0 - 1);            // sample before the quarter
-          if (lane == 1) yout[qcnt + 1] = gauss_sparse(ext, nz, wd, lw, c0 + qcnt);  // sample after it
-          __syncwarp();
-        }
-        // ---- candidates and positives ----
-        auto Y = [&](int X) -> double {  // island-local sample, 0 <= X < n
-          const int x = X - tw.lo - q0;
-          return (x >= -1 && x <= qcnt) ? yout[1 + x] : gauss_global(yr, n, X, wd, lw);
-        };
-        int nc = 0, np = 0;
-        u32* cm_out = cmask + (size_t)tile * TILE_WORDS + q * WQ_WORDS;
-        u32* pm_out = pmask + (size_t)tile * TILE_WORDS + q * WQ_WORDS;
-        for (int xw = 0; xw < nw; ++xw) {
-          const int x = xw * 32 + lane, X = tw.lo + q0 + x;
-          bool is_c = false, is_p = false;
-          if (x < qcnt) is_c = (X == 0 || X == n - 1);
-          if (((live >> xw) & 1u) && x < qcnt) {  // a dead word is all zeros
-            const double v = yout[1 + x];
-            is_p = v > 0.0;
-            if (!is_c && is_p) {
-              const double l = yout[x], r = yout[x + 2];
-              if (l < v && r < v) is_c = true;
-              else if (!(l > v) && !(r > v)) {  // a neighbour equals v: walk the plateau
-                int a = X, b = X;
-                while (a - 1 >= 0 && Y(a - 1) == v) --a;
-                while (b + 1 <= n - 1 && Y(b + 1) == v) ++b;
-                if (a >= 1 && b <= n - 2 && Y(a - 1) < v && Y(b + 1) < v && X == ((a + b) >> 1)) is_c = true;
-              }
-            }
-          }
-          const u32 cm = __ballot_sync(0xffffffffu, is_c), pm = __ballot_sync(0xffffffffu, is_p);
-          if (lane == 0) { cm_out[xw] = cm; pm_out[xw] = pm; }
-          nc += __popc(cm);
-          np += __popc(pm);
-        }
-        if (lane == 0) tile_cnt[(size_t)tile * 4 + q] = (u32)(nc | (np << 16));  // per quarter
-        tot += ((unsigned long long)np << 32) | (unsigned long long)nc;
       }
+      v = yr[j];
+      ext[s] = v;
     }
-    if (lane == 0 && tot) {
-      atomicAdd(&chunk_tot[chunk], tot);
-      atomicAdd(&group_tot[chunk / SM_GROUP], tot);
+    const u32 m = __ballot_sync(0xffffffffu, v != 0);
+    if (lane == 0) nz[s >> 5] = m;
+  }
+  if (tid < 2) nz[(span_r >> 5) + tid] = 0u;
+  __syncthreads();
+  // bit w of wm: mask word w of the staged window has a non-zero sample (at most 50 words at sigma = 50)
+  unsigned long long wm;
+  {
+    const int n_nz = (span_r >> 5) + 2;
+    const u32 lo32 = __ballot_sync(0xffffffffu, lane < n_nz && nz[lane] != 0u);
+    const u32 hi32 = __ballot_sync(0xffffffffu, 32 + lane < n_nz && nz[32 + lane] != 0u);
+    wm = ((unsigned long long)hi32 << 32) | lo32;
+  }
+  // ---- Gaussian: a warp owns 256 consecutive samples, 32 per step (coalesced 256-byte stores) ----
+  u32 live = 0;  // bit it: step `it` of this warp has a non-zero input near its window (else its y is all 0)
+  for (int it = 0; it < TILE_WORDS / 4; ++it) {
+    const int xb = warp * (TILE_SAMPLES / 4) + it * 32;
+    if (xb >= cnt) break;
+    const int x = xb + lane;
+    // inputs of this step: staged samples [xb + 1, xb + 32 + 2*lw]; testing the whole mask words that
+    // hold them is conservative (a false positive only runs the sparse filter over zeros: same bits)
+    const int w_a = (xb + 1) >> 5, w_b = (xb + 32 + 2 * lw) >> 5;  // w_b - w_a <= 14
+    const bool any = ((wm >> w_a) & ((2ull << (w_b - w_a)) - 1ull)) != 0ull;
+    double v = 0.0;
+    if (any) {
+      live |= 1u << it;
+      if (x < cnt) v = gauss_sparse(ext, nz, wd, lw, lw + 1 + x);
+    }
+    if (x < cnt) {
+      y[f0 + tw.lo + x] = v;
+      yout[1 + x] = v;
     }
   }
-
-  // ================================ grid barrier ================================
+  if (tid == GAUSS_THREADS - 2) yout[0] = gauss_sparse(ext, nz, wd, lw, lw);              // sample lo - 1
+  if (tid == GAUSS_THREADS - 1) yout[cnt + 1] = gauss_sparse(ext, nz, wd, lw, lw + 1 + cnt);  // sample lo + cnt
+  __syncthreads();
+  // ---- candidates and positives ----
+  auto Y = [&](int X) -> double {  // island-local sample, 0 <= X < n
+    const int x = X - tw.lo;
+    return (x >= -1 && x <= cnt) ? yout[1 + x] : gauss_global(yr, n, X, wd, lw);
+  };
+  int nc = 0, np = 0;
+  u32* cm_out = cmask + (size_t)blockIdx.x * TILE_WORDS;
+  u32* pm_out = pmask + (size_t)blockIdx.x * TILE_WORDS;
+  for (int it = 0; it < TILE_WORDS / 4; ++it) {
+    const int wi = warp * (TILE_WORDS / 4) + it;
+    if (wi * 32 >= cnt) break;  // a median island is half a tile: k_tile_lists only reads the words a tile has
+    const int x = wi * 32 + lane, X = tw.lo + x;
+    bool is_c = false, is_p = false;
+    if (x < cnt) is_c = (X == 0 || X == n - 1);
+    if (((live >> it) & 1u) && x < cnt) {  // the same warp smoothed these samples: a dead step is all zeros
+      const double v = yout[1 + x];
+      is_p = v > 0.0;
+      if (!is_c && is_p) {
+        const double l = yout[x], r = yout[x + 2];
+        if (l < v && r < v) is_c = true;
+        else if (!(l > v) && !(r > v)) {  // a neighbour equals v: walk the plateau
+          int a = X, b = X;
+          while (a - 1 >= 0 && Y(a - 1) == v) --a;
+          while (b + 1 <= n - 1 && Y(b + 1) == v) ++b;
+          if (a >= 1 && b <= n - 2 && Y(a - 1) < v && Y(b + 1) < v && X == ((a + b) >> 1)) is_c = true;
+        }
+      }
+    }
+    const u32 cm = __ballot_sync(0xffffffffu, is_c), pm = __ballot_sync(0xffffffffu, is_p);
+    if (lane == 0) { cm_out[wi] = cm; pm_out[wi] = pm; }
+    nc += __popc(cm);
+    np += __popc(pm);
+  }
+  if (lane == 0) red[warp] = nc | (np << 16);
   __syncthreads();
   if (tid == 0) {
-    __threadfence();
-    atomicAdd(&sync->arrived, 1);
-    while (ld_acquire_i32(&sync->arrived) < (int)gridDim.x) __nanosleep(64);
+    const u32 v = (u32)(red[0] + red[1] + red[2] + red[3]);  // candidates | positives << 16
+    tile_cnt[blockIdx.x] = v;
+    // totals of every group of TILE_GROUP consecutive tiles: positives << 32 | candidates
+    atomicAdd(&group_sum[blockIdx.x / TILE_GROUP], ((unsigned long long)(v >> 16) << 32) | (unsigned long long)(v & 0xffffu));
+  }
+}
+
+// Ordered candidate list and ordered positive samples of one tile from its ballot words.  The tile's
+// offsets into the two lists = totals of the tile groups before its group (k_smooth's atomics) + counts
+// of the earlier tiles of its own group: at most (n_tiles / TILE_GROUP + TILE_GROUP) cached loads per
+// CTA instead of a device-wide scan.  Also: per-tint offsets of the positive list and the totals.
+__global__ void __launch_bounds__(GAUSS_THREADS) k_tile_lists(const TileWork* __restrict__ tiles, int n_tiles,
+                                                             const int* __restrict__ island_sample_off,
+                                                             const int* __restrict__ island_tint,
+                                                             const int* __restrict__ tint_island_off, int n_tints,
+                                                             const u32* __restrict__ cmask, const u32* __restrict__ pmask,
+                                                             const u32* __restrict__ tile_cnt,
+                                                             const unsigned long long* __restrict__ group_sum,
+                                                             const double* __restrict__ y, int* __restrict__ cand_flat,
+                                                             double* __restrict__ vbuf, int* __restrict__ tint_pos_off,
+                                                             i64* __restrict__ n_cand_out) {
+  __shared__ int pre_c[TILE_WORDS], pre_p[TILE_WORDS];
+  __shared__ unsigned long long red[GAUSS_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x;
+  const u32* cm_in = cmask + (size_t)tile * TILE_WORDS;
+  const u32* pm_in = pmask + (size_t)tile * TILE_WORDS;
+  // ---- (candidates, positives) before this tile ----
+  unsigned long long s = 0;
+  const int g = tile / TILE_GROUP;
+  for (int k = tid; k < g; k += GAUSS_THREADS) s += group_sum[k];
+  for (int k = g * TILE_GROUP + tid; k < tile; k += GAUSS_THREADS) {
+    const u32 v = tile_cnt[k];
+    s += ((unsigned long long)(v >> 16) << 32) | (unsigned long long)(v & 0xffffu);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) red[warp] = s;
+  const TileWork tw = tiles[tile];
+  const int nwords = (min(TILE_SAMPLES, tw.n - tw.lo) + 31) >> 5;  // k_smooth wrote only these
+  if (warp == 0) {
+    int c = lane < nwords ? __popc(cm_in[lane]) : 0, p = lane < nwords ? __popc(pm_in[lane]) : 0;
+    const int c0 = c, p0 = p;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, c, o), b = __shfl_up_sync(0xffffffffu, p, o);
+      if (lane >= o) { c += a; p += b; }
+    }
+    pre_c[lane] = c - c0;
+    pre_p[lane] = p - p0;
   }
   __syncthreads();
-
-  // ================================ phase B ================================
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) s_chunk = atomicAdd(&sync->cursor_b, 1);
-    __syncthreads();
-    const int chunk = s_chunk;
-    if (chunk >= n_chunks) break;
-    // (candidates, positives) of the chunks before this one: whole groups, then the chunks of its own group
-    unsigned long long sum = 0;
-    const int g = chunk / SM_GROUP;
-    for (int k = tid; k < g; k += GAUSS_THREADS) sum += __ldcg(&group_tot[k]);
-    for (int k = g * SM_GROUP + tid; k < chunk; k += GAUSS_THREADS) sum += __ldcg(&chunk_tot[k]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) s_red64[warp] = sum;
-    __syncthreads();
-    const unsigned long long before = s_red64[0] + s_red64[1] + s_red64[2] + s_red64[3];
-    int off_c = (int)(before & 0xffffffffull), off_p = (int)(before >> 32);
-    const int t_lo = chunk * SM_CHUNK, t_hi = min(n_tiles, t_lo + SM_CHUNK);
-    for (int tile = t_lo; tile < t_hi; ++tile) {
-      const TileWork tw = tiles[tile];
-      const int cnt = min(TILE_SAMPLES, tw.n - tw.lo);
-      const int nwords = (cnt + 31) >> 5;
-      const u32* cm_in = cmask + (size_t)tile * TILE_WORDS;
-      const u32* pm_in = pmask + (size_t)tile * TILE_WORDS;
-      u32 tc = 0;  // candidates | positives << 16 of the tile = sum over its quarters
-      for (int q = 0; q * (WQ_WORDS * 32) < cnt; ++q) tc += __ldcg(&tile_cnt[(size_t)tile * 4 + q]);
-      if (warp == 0) {
-        int c = lane < nwords ? __popc(__ldcg(&cm_in[lane])) : 0, p = lane < nwords ? __popc(__ldcg(&pm_in[lane])) : 0;
-        const int c0 = c, p0 = p;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int a = __shfl_up_sync(0xffffffffu, c, o), b = __shfl_up_sync(0xffffffffu, p, o);
-          if (lane >= o) { c += a; p += b; }
-        }
-        pre_c[lane] = c - c0;
-        pre_p[lane] = p - p0;
-      }
-      __syncthreads();
-      if (tid == 0) {
-        if (tw.lo == 0) {
-          const int t = island_tint[tw.island];
-          if (tw.island == tint_island_off[t]) tint_pos_off[t] = off_p;
-        }
-        if (tile == n_tiles - 1) {
-          tint_pos_off[n_tints] = off_p + (int)(tc >> 16);
-          *n_cand_out = (i64)off_c + (i64)(tc & 0xffffu);
-        }
-      }
-      const int fbase = tw.f0 + tw.lo;
-      const u32 lt = (1u << lane) - 1u;
-      for (int wi = warp; wi < nwords; wi += GAUSS_THREADS / 32) {
-        const u32 cm = __ldcg(&cm_in[wi]), pm = __ldcg(&pm_in[wi]);
-        const int f = fbase + wi * 32 + lane;
-        if ((cm >> lane) & 1u) cand_flat[off_c + pre_c[wi] + __popc(cm & lt)] = f;
-        if ((pm >> lane) & 1u) vbuf[off_p + pre_p[wi] + __popc(pm & lt)] = __ldcg(&y[f]);
-      }
-      off_c += (int)(tc & 0xffffu);
-      off_p += (int)(tc >> 16);
-      __syncthreads();  // pre_c / pre_p are rewritten by the next tile
+  const unsigned long long before = red[0] + red[1] + red[2] + red[3];
+  const int off_c = (int)(before & 0xffffffffull), off_p = (int)(before >> 32);
+  if (tid == 0) {
+    if (tw.lo == 0) {
+      const int t = island_tint[tw.island];
+      if (tw.island == tint_island_off[t]) tint_pos_off[t] = off_p;
     }
+    if (tile == n_tiles - 1) {
+      const u32 v = tile_cnt[tile];
+      tint_pos_off[n_tints] = off_p + (int)(v >> 16);
+      *n_cand_out = (i64)off_c + (i64)(v & 0xffffu);
+    }
+  }
+  const int fbase = tw.f0 + tw.lo;
+  const u32 lt = (1u << lane) - 1u;
+  for (int it = 0; it < TILE_WORDS / 4; ++it) {
+    const int wi = warp * (TILE_WORDS / 4) + it;
+    if (wi >= nwords) break;
+    const u32 cm = cm_in[wi], pm = pm_in[wi];
+    const int f = fbase + wi * 32 + lane;
+    if ((cm >> lane) & 1u) cand_flat[off_c + pre_c[wi] + __popc(cm & lt)] = f;
+    if ((pm >> lane) & 1u) vbuf[off_p + pre_p[wi] + __popc(pm & lt)] = y[f];
   }
 }
 

@@ -102,18 +102,23 @@ class ParsedBatch:
             pass
 
 
-def run_batch_native(eng: Engine, prm: SegmentParams, split_dir: str, outdir: str,
-                     chunk: Sequence[Tuple[str, int]], threads: int, packed_file: str = None,
-                     packed_segment: str = None):
-    """One batch, files to files: parse (or load ``packed_file``, a batch of exactly the tints of
-    ``chunk`` in that order), segment on ``eng``'s GPU, format."""
-    prof = os.environ.get("FRS_CLI_PROFILE")
+def parse_batch_native(split_dir: str, outdir: str, chunk: Sequence[Tuple[str, int]], threads: int,
+                       packed_file: str = None):
+    """Host half of a batch that needs no GPU: parse the tints of ``chunk`` (or load ``packed_file``, a batch of
+    exactly those tints in that order).  Returns (ParsedBatch, output paths, log paths, seconds)."""
     t0 = time.perf_counter()
     sp, rp, op, lp = _paths(split_dir, outdir, chunk)
     pb = ParsedBatch.from_packed(packed_file) if packed_file else ParsedBatch(sp, rp, threads)
     if pb.n_tints != len(chunk):
         pb.close()
         raise _lib.FrsError(-2, "%s holds %d tints, its index lists %d" % (packed_file, pb.n_tints, len(chunk)))
+    return pb, op, lp, time.perf_counter() - t0
+
+
+def run_parsed_native(eng: Engine, prm: SegmentParams, parsed, chunk, threads: int, packed_segment: str = None):
+    """GPU half + formatter of a batch parsed by ``parse_batch_native``; frees the parsed batch."""
+    prof = os.environ.get("FRS_CLI_PROFILE")
+    pb, op, lp, t_parse = parsed
     t1 = time.perf_counter()
     try:
         res = eng.segment_batch(pb, prm)
@@ -124,7 +129,15 @@ def run_batch_native(eng: Engine, prm: SegmentParams, split_dir: str, outdir: st
         t3 = time.perf_counter()
         if prof:
             sys.stderr.write("[frs cli profile] batch of %d tints / %d reads: parse %.3f s  upload+kernels+download %.3f s  "
-                             "format+write %.3f s\n" % (len(chunk), pb.n_reads, t1 - t0, t2 - t1, t3 - t2))
+                             "format+write %.3f s\n" % (len(chunk), pb.n_reads, t_parse, t2 - t1, t3 - t2))
         return pb.n_reads, int(res.sizes["dp_cells"])
     finally:
         pb.close()
+
+
+def run_batch_native(eng: Engine, prm: SegmentParams, split_dir: str, outdir: str,
+                     chunk: Sequence[Tuple[str, int]], threads: int, packed_file: str = None,
+                     packed_segment: str = None):
+    """One batch, files to files: parse (or load ``packed_file``), segment on ``eng``'s GPU, format."""
+    parsed = parse_batch_native(split_dir, outdir, chunk, threads, packed_file)
+    return run_parsed_native(eng, prm, parsed, chunk, threads, packed_segment)

@@ -48,10 +48,38 @@ class PackedBatch:
             n_cigar_ops=len(a["cigar"]), n_samples=int(a["island_sample_off"][-1]), n_seq_words=len(a["seq_is_a"]),
         )
 
+    EDGE_WORDS = 8  # plane words per side in the edge store (256 bases: ~5 of 6 soft clips of ONT-like reads)
+
+    def build_edge_store(self, words: int = None) -> np.ndarray:
+        """``frs_batch.seq_edge``: the first and the last ``words`` plane words of every read, dense
+        (``[read][side][plane][word]``, left-aligned, zero-padded).  The soft clips that the poly-A/T scans read
+        sit at the two ends of a read; with this store the library copies them in one dense DMA."""
+        E = int(words or self.EDGE_WORDS)
+        a = self.arrays
+        off = a["read_seq_off"].astype(np.int64)
+        n = len(off) - 1
+        out = np.zeros((n, 2, 2, E), dtype=np.uint32)
+        if n and len(a["seq_is_a"]):
+            k = np.arange(E, dtype=np.int64)[None, :]
+            lo, hi = off[:-1, None], off[1:, None]
+            first = lo + k                                  # words [0, E) of the read
+            last = np.maximum(lo, hi - E) + k               # words [max(0, nw - E), nw), left-aligned
+            top = len(a["seq_is_a"]) - 1
+            for side, idx in ((0, first), (1, last)):
+                ok = idx < hi
+                src = np.minimum(idx, top)
+                out[:, side, 0, :] = np.where(ok, a["seq_is_a"][src], 0)
+                out[:, side, 1, :] = np.where(ok, a["seq_is_t"][src], 0)
+        self.seq_edge = np.ascontiguousarray(out.reshape(-1))
+        self.seq_edge_words = E
+        self._struct_key = None
+        return self.seq_edge
+
     def as_struct(self) -> "_lib.FrsBatch":
         """The ``frs_batch`` view of the arrays (cached: building ~30 ctypes pointers costs more than enqueueing
         the batch; the cache is dropped when ``derive_riv`` or the arrays change identity)."""
-        key = (self.derive_riv, tuple(id(v) for v in self.arrays.values()))
+        edge = getattr(self, "seq_edge", None)
+        key = (self.derive_riv, id(edge), tuple(id(v) for v in self.arrays.values()))
         if getattr(self, "_struct_key", None) == key:
             return self._struct
         b = _lib.FrsBatch()
@@ -64,16 +92,25 @@ class PackedBatch:
             arr = self.arrays[name]
             assert arr.dtype == _DTYPES[name] and arr.flags["C_CONTIGUOUS"], name
             setattr(b, name, arr.ctypes.data_as(C.c_void_p))
+        if edge is not None and len(edge):
+            b.seq_edge_words = self.seq_edge_words
+            b.seq_edge = edge.ctypes.data_as(C.c_void_p)
         self._struct, self._struct_key = b, key
         return b
 
     def nbytes(self) -> int:
         return int(sum(v.nbytes for v in self.arrays.values()))
 
-    def pin(self):
-        """Moves the arrays into page-locked host memory (torch is used for buffer management only)."""
+    def pin(self, edge_words: int = None):
+        """Moves the arrays into page-locked host memory (torch is used for buffer management only) and adds
+        the edge store of the sequence planes (``build_edge_store``; ``edge_words=0``: none)."""
         import torch
         self._pinned = {}
+        if edge_words is None or edge_words > 0:
+            e = self.build_edge_store(edge_words)
+            te = torch.from_numpy(e if e.size else np.zeros(1, dtype=np.uint32)).pin_memory()
+            self._pinned["seq_edge"] = te
+            self.seq_edge = te.numpy()[: e.size]
         for k, v in list(self.arrays.items()):
             t = torch.from_numpy(v if v.size else np.zeros(1, dtype=v.dtype))
             t = t.pin_memory()

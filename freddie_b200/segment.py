@@ -290,14 +290,31 @@ def run_directory(split_dir: str, outdir: str, prm: SegmentParams, threads: int 
     def worker(dev, lane):
         try:
             t_eng = time.perf_counter()
-            eng = get_engine(dev, lane)
-            if os.environ.get("FRS_CLI_PROFILE"):
-                sys.stderr.write("[frs cli profile] context of GPU %d lane %d ready after %.3f s\n"
-                                 % (dev, lane, time.perf_counter() - t_eng))
+            # the CUDA context of the lane is created on a helper thread while the lane parses its first batch
+            # (context creation costs as much as parsing ~100 k reads and needs nothing from the host side)
+            box = {}
+
+            def make_engine():
+                try:
+                    box["eng"] = get_engine(dev, lane)
+                except BaseException as e:  # noqa: BLE001
+                    box["err"] = e
+
+            maker = threading.Thread(target=make_engine)
+            maker.start()
+            eng = None
             for chunk, packed_file in feeds[dev]:
+                parsed = hostio.parse_batch_native(split_dir, outdir, chunk, threads, packed_file) if native else None
+                if eng is None:
+                    maker.join()
+                    if "err" in box:
+                        raise box["err"]
+                    eng = box["eng"]
+                    if os.environ.get("FRS_CLI_PROFILE"):
+                        sys.stderr.write("[frs cli profile] context of GPU %d lane %d ready after %.3f s\n"
+                                         % (dev, lane, time.perf_counter() - t_eng))
                 if native:
-                    n_reads, cells = hostio.run_batch_native(eng, prm, split_dir, outdir, chunk, threads, packed_file,
-                                                             segment_file(chunk))
+                    n_reads, cells = hostio.run_parsed_native(eng, prm, parsed, chunk, threads, segment_file(chunk))
                 else:
                     tints = [_load_tint_py(split_dir, c, t) for c, t in chunk]
                     batch = pack_tints(tints)
@@ -308,6 +325,7 @@ def run_directory(split_dir: str, outdir: str, prm: SegmentParams, threads: int 
                             fh.write(format_tint(batch, res, k))
                     n_reads, cells = batch.n_reads, int(res.sizes["dp_cells"])
                 tick(len(chunk), n_reads, cells)
+            maker.join()
         except BaseException as e:  # propagate like the reference: the whole run aborts
             errors.append(e)
             for f in feeds:

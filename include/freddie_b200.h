@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define FRS_ABI_VERSION 1
+#define FRS_ABI_VERSION 2
 
 /* error codes */
 #define FRS_OK 0
@@ -90,6 +90,15 @@ typedef struct {
   const uint32_t* cigar;       /* [n_cigar_ops] (len << 4) | op, op: 0 M/X/=, 1 I, 2 D, 3 other */
   const uint32_t* seq_is_a;    /* [n_seq_words] bit b of word w of a read = (seq[32w+b]=='A') */
   const uint32_t* seq_is_t;    /* [n_seq_words] same for 'T' */
+  /* optional EDGE STORE (may be NULL / 0): the first and the last seq_edge_words plane words of every read, dense:
+   * seq_edge[((read*2 + side)*2 + plane)*E + w], side 0 = words [0, min(E, nw)) of the read's planes, side 1 =
+   * words [max(0, nw-E), nw), both left-aligned and zero-padded, plane 0 = isA, 1 = isT, nw = words of the read.
+   * The poly-A/T scans only read the soft clips, which sit at the two ends of a read: with pinned planes and an
+   * edge store, frs_upload copies the store whole (one dense DMA) and only the few clips longer than 32*E bases
+   * are fetched from the planes afterwards. */
+  int32_t seq_edge_words;
+  int32_t reserved0;
+  const uint32_t* seq_edge;
 } frs_batch;
 
 /* Sizes of the variable-length results of the batch that was just run. */
@@ -151,7 +160,7 @@ int frs_download(frs_context* ctx, const frs_result* out);
 int frs_segment_batch(frs_context* ctx, const frs_batch* batch, const frs_params* prm,
                       frs_result_sizes* sizes);
 
-/* ---- the same hot path, pipelined: up to three batches in flight per context (copy in | kernels | copy out), ONE host thread.
+/* ---- the same hot path, pipelined: up to four batches in flight per context (copy in | kernels | tail | copy out), ONE host thread.
  * The reference overlaps tints with a process pool (imap_unordered, freddie_segment.py:871-876); here the
  * copy of batch k+1 and the read-back of batch k-1 overlap the kernels of batch k on the copy engines.
  *   frs_submit  enqueues the host-to-device copies and every kernel of the run and returns at once (no
@@ -160,7 +169,7 @@ int frs_segment_batch(frs_context* ctx, const frs_batch* batch, const frs_params
  *   frs_wait    blocks until the run is complete and returns the result sizes (if a data-dependent buffer
  *               was too small it is grown and the run repeated first: first batches of a context only).
  *   frs_fetch   copies the results into caller buffers, blocks until they have arrived, frees the ticket.
- * Tickets are slots: at most three may be outstanding, and they complete in submission order.  The tail of a
+  * Tickets are slots: at most four may be outstanding, and they complete in submission order.  The tail of a
  * run (clip fetch from pinned host memory, poly-A/T scans) executes on its own stream beside the head of the
  * next batch. */
 int frs_submit(frs_context* ctx, const frs_batch* batch, const frs_params* prm, int* ticket);

@@ -57,37 +57,48 @@ s0 = e.wait(tk0)
 bufs = [e.new_result(s0, batch, pinned=True) for _ in range(2)]
 e.fetch(tk0, bufs[0])
 
-K = 20
 from collections import deque  # noqa: E402
-acc = dict(submit=0.0, wait=0.0, fetch=0.0)
-torch.cuda.synchronize()
-w0 = time.perf_counter()
-fly = deque()
-pending = None
-for k in range(K + 2):
-    t0 = time.perf_counter()
+
+
+def pipelined(K):
+    acc = dict(submit=0.0, wait=0.0, fetch=0.0)
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    fly = deque()
+    pending = None
+    for k in range(K + 2):
+        t0 = time.perf_counter()
+        if k < K:
+            fly.append(e.submit(batch, prm))
+        ta = time.perf_counter()
+        if pending is not None:
+            e.fetch_finish(pending)
+            pending = None
+        t1 = time.perf_counter()
+        acc["submit"] += ta - t0
+        acc["fetch"] += t1 - ta
+        if len(fly) == 3 or (k >= K and fly):
+            pt = fly.popleft()
+            e.wait(pt)
+            t2 = time.perf_counter()
+            e.fetch_start(pt, bufs[k & 1])
+            pending = pt
+            t3 = time.perf_counter()
+            acc["wait"] += t2 - t1
+            acc["fetch"] += t3 - t2
     if pending is not None:
         e.fetch_finish(pending)
-        pending = None
-    ta = time.perf_counter()
-    if k < K:
-        fly.append(e.submit(batch, prm))
-    t1 = time.perf_counter()
-    acc["fetch"] += ta - t0
-    acc["submit"] += t1 - ta
-    if len(fly) == 3 or (k >= K and fly):
-        pt = fly.popleft()
-        e.wait(pt)
-        t2 = time.perf_counter()
-        e.fetch_start(pt, bufs[k & 1])
-        pending = pt
-        t3 = time.perf_counter()
-        acc["wait"] += t2 - t1
-        acc["fetch"] += t3 - t2
-if pending is not None:
-    e.fetch_finish(pending)
-torch.cuda.synchronize()
-dt = time.perf_counter() - w0
+    torch.cuda.synchronize()
+    return time.perf_counter() - w0, acc
+
+
+pipelined(6)  # every slot has its buffers now
+K = 20
+e.set_profiling(True)
+dt, acc = pipelined(K)
+print("stages of the last pipelined run (its head ran beside the previous tail): " + "  ".join("%s %.3f" % (n, ms) for n, ms, _ in e.timings()))
+e.set_profiling(False)
+dt, acc = pipelined(K)
 print("pipelined, one context: %.3f ms/step (%.1f M reads/s); host time per step: submit %.3f  wait %.3f  fetch %.3f ms" % (
     dt / K * 1e3, batch.n_reads * K / dt / 1e6, acc["submit"] / K * 1e3, acc["wait"] / K * 1e3, acc["fetch"] / K * 1e3))
 

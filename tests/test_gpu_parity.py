@@ -238,11 +238,11 @@ def test_lazy_clip_fetch_equals_resident_planes(name, golden_set, eng):
     from freddie_b200.pack import pack_tints
     tints, flags, _ = golden_set(name)
     _, gprm = _params(flags)
-    pinned = pack_tints(tints).pin()
+    pinned = pack_tints(tints).pin(edge_words=0)  # no edge store: every clip word crosses the bus on demand
     lazy = eng.segment_batch(pinned, gprm)
     st = eng.stats()
     assert 0 < st["clip_words"] <= st["seq_words"] and st["h2d_run"] == 8 * st["clip_words"]
-    h_lazy = st["h2d_upload"]
+    h_lazy, w_lazy = st["h2d_upload"], st["clip_words"]
     try:
         eng.set_option(_lib.OPT_LAZY_SEQ, 0)
         full = eng.segment_batch(pinned, gprm)
@@ -255,10 +255,21 @@ def test_lazy_clip_fetch_equals_resident_planes(name, golden_set, eng):
     for k in lazy.arrays:
         assert np.array_equal(lazy.arrays[k], full.arrays[k]), (name, k)
         assert np.array_equal(lazy.arrays[k], pageable.arrays[k]), (name, k)
+    # with an edge store (first / last E plane words of every read, copied densely at upload) only the clips
+    # longer than 32 E bases are fetched afterwards; E = 1 and 2 leave many of those, the default E few
+    for E in (1, 2, None):
+        b = pack_tints(tints).pin(edge_words=E)
+        got = eng.segment_batch(b, gprm)
+        st = eng.stats()
+        assert st["clip_words"] <= w_lazy and st["h2d_run"] == 8 * st["clip_words"]
+        assert E is not None or name == "degenerate" or st["clip_words"] < w_lazy
+        assert st["h2d_upload"] == h_lazy + 16 * b.n_reads * b.seq_edge_words
+        for k in lazy.arrays:
+            assert np.array_equal(lazy.arrays[k], got.arrays[k]), (name, E, k)
 
 
 def test_pipelined_submit_wait_fetch_equals_the_synchronous_calls(golden_set):
-    """frs_submit / frs_wait / frs_fetch: up to three batches in flight in ONE context (the copies of one overlap the
+    """frs_submit / frs_wait / frs_fetch: up to four batches in flight in ONE context (the copies of one overlap the
     kernels of the other); results must be those of upload + run + download, in any interleaving."""
     from freddie_b200 import _lib
     from freddie_b200.engine import Engine
@@ -288,13 +299,16 @@ def test_pipelined_submit_wait_fetch_equals_the_synchronous_calls(golden_set):
             for a in want[k].arrays:
                 assert np.array_equal(want[k].arrays[a], got[k].arrays[a]), (nme, a)
             assert want[k].sizes == got[k].sizes
-        # three batches may be in flight; a fourth submit without a fetch is refused; so is a fetch of a free ticket
+        # four batches may be in flight; a fifth submit without a fetch is refused; so is a fetch of a free ticket
         t0 = e.submit(batches[0], prms[0])
         t1 = e.submit(batches[1], prms[1])
         t2 = e.submit(batches[2], prms[2])
+        t3 = e.submit(batches[3], prms[3])
         with pytest.raises(_lib.FrsError, match="in flight"):
-            e.submit(batches[3], prms[3])
+            e.submit(batches[4], prms[4])
         s0, s1, s2 = e.wait(t0), e.wait(t1), e.wait(t2)
+        r3 = e.fetch(t3, e.new_result(e.wait(t3), batches[3]))
+        assert all(np.array_equal(r3.arrays[a], want[3].arrays[a]) for a in r3.arrays)
         r1 = e.fetch(t1, e.new_result(s1, batches[1]))
         r2 = e.fetch(t2, e.new_result(s2, batches[2]))
         r0 = e.fetch(t0, e.new_result(s0, batches[0]))
