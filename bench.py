@@ -399,7 +399,7 @@ def run_cuda_arm(args):
     # copies of one step overlap the kernels of its neighbours on the copy engines.  `serial_value` is the
     # same work with the synchronous calls (upload, run, download one after the other). ----
     eng.set_option(_lib.OPT_LAZY_SEQ, 1)  # pinned planes stay on the host; the clip words are fetched by a kernel
-    n_ctx = max(1, int(os.environ.get("FRS_E2E_CONTEXTS", "2")))
+    n_ctx = max(1, int(os.environ.get("FRS_E2E_CONTEXTS", "1")))  # more contexts only add contention (measured: 2 -> 0.65x)
     ctxs = [eng] + [Engine(local_rank) for _ in range(n_ctx - 1)]
     pong = []
     for e2 in ctxs:

@@ -481,6 +481,8 @@ def select_by_distance(peaks: Sequence[int], priority: Sequence[float], distance
     m = len(peaks)
     keep = [True] * m
     order = sorted(range(m), key=lambda t: priority[t])  # stable
+    if TIE_EXPLORER is not None:
+        order = TIE_EXPLORER.reorder(order, priority)
     if tie_log is not None:
         for a in range(m - 1):
             if priority[a] == priority[a + 1] and peaks[a + 1] - peaks[a] < distance:
@@ -498,6 +500,81 @@ def select_by_distance(peaks: Sequence[int], priority: Sequence[float], distance
             keep[k] = False
             k += 1
     return [peaks[t] for t in range(m) if keep[t]]
+
+
+class TieExplorer:
+    """Test helper for the one platform-dependent corner of the reference: scipy's
+    ``_select_by_peak_distance`` visits peaks in ``np.argsort(priority)`` order, and numpy's default sort is
+    NOT stable (AVX-512 / AVX2 sorting networks): among bit-equal heights the order is an artefact of the
+    network, not of the data.  The restatement (and the CUDA kernel) define it as the stable order.  To show
+    that a SEGMENT file of the reference that differs from ours differs ONLY by such a choice, this class
+    re-orders every group of equal priorities by a chosen permutation; ``explain_by_ties`` searches the
+    permutations for one that reproduces the reference's bytes."""
+
+    def __init__(self):
+        self.sizes: List[int] = []   # probe mode: sizes of the equal-priority groups, in call order
+        self.choice = None           # list of permutations (tuples), one per group; None = probe
+
+    def reorder(self, order, priority):
+        out, i = [], 0
+        while i < len(order):
+            j = i
+            while j + 1 < len(order) and priority[order[j + 1]] == priority[order[i]]:
+                j += 1
+            grp = order[i:j + 1]
+            if len(grp) > 1:
+                if self.choice is None:
+                    self.sizes.append(len(grp))
+                else:
+                    perm = self.choice[self._k] if self._k < len(self.choice) else None
+                    self._k += 1
+                    if perm is not None:
+                        grp = [grp[x] for x in perm]
+            out.extend(grp)
+            i = j + 1
+        return out
+
+
+TIE_EXPLORER: Optional[TieExplorer] = None
+
+
+def explain_by_ties(tint: dict, prm: "Params", want_text: Optional[str] = None, limit: int = 20000,
+                    want_sha16: Optional[str] = None) -> Optional[list]:
+    """Searches the visiting orders among equal-height refine peaks for one under which this restatement
+    writes ``want_text`` (or a file whose SHA-256 starts with ``want_sha16``) for ``tint``.  Returns the chosen
+    permutations (one per group of equal heights), or None if no order within ``limit`` combinations does --
+    i.e. the difference is NOT a tie artefact."""
+    import copy
+    import hashlib
+    import itertools
+    global TIE_EXPLORER
+    probe = TieExplorer()
+    TIE_EXPLORER = probe
+    try:
+        segment_tint(copy.deepcopy(tint), prm)
+    finally:
+        TIE_EXPLORER = None
+    options = [list(itertools.permutations(range(n))) if n <= 4 else [tuple(range(n)), tuple(reversed(range(n)))]
+               for n in probe.sizes]
+    total = 1
+    for o in options:
+        total *= len(o)
+        if total > limit:
+            return None
+    for combo in itertools.product(*options):
+        ex = TieExplorer()
+        ex.choice, ex._k = list(combo), 0
+        TIE_EXPLORER = ex
+        try:
+            t = copy.deepcopy(tint)
+            segment_tint(t, prm)
+        finally:
+            TIE_EXPLORER = None
+        text = format_segment(t)
+        if (want_text is not None and text == want_text) or (
+                want_sha16 is not None and hashlib.sha256(text.encode()).hexdigest()[:16] == want_sha16):
+            return list(combo)
+    return None
 
 
 def refine(y_raw: np.ndarray, final: Sequence[int], sigma: float, weights1: np.ndarray,

@@ -74,6 +74,28 @@ def test_refine_tie_set_pins_the_tie_rule(golden_set):
     assert it["dp_final"] == [[0, 11]]  # nothing fixed, no interior candidate kept: refine decides alone
 
 
+def test_unstable_argsort_corner_is_explained_by_the_tie_explorer():
+    """Tint chr2/726 of BASELINE config 5 (173 reads): its refine step meets two bit-equal peaks 2 samples apart
+    inside an array of 8 peaks, and on the authoring machine numpy's (unstable, AVX-512) argsort visits the
+    EARLIER one first -- the pinned reference file keeps position 8816890 where the stable rule keeps 8816892.
+    The restatement must differ from the pinned digest, and the tie explorer must find the one flip that
+    reproduces it (this is what the full-size GPU test relies on to tell a tie artefact from a real mismatch)."""
+    import hashlib
+    import json
+    from freddie_b200 import synth
+    man = json.load(open(os.path.join(GOLDEN, "full", "cfg5_slice.json")))
+    job = [j for j in synth.config_jobs(5) if j[5] == "chr2" and j[2] == 726][0]
+    tint = synth._tint_job(job)
+    import copy
+    ot = copy.deepcopy(tint)
+    it = orc.segment_tint(ot, orc.Params(), keep=True)
+    assert it["ties"] == [(36, 38)]
+    want = man["outputs"]["chr2/726"]
+    assert hashlib.sha256(orc.format_segment(ot).encode()).hexdigest()[:16] != want
+    perm = orc.explain_by_ties(tint, orc.Params(), want_sha16=want)
+    assert perm is not None and (1, 0) in perm
+
+
 def test_oracle_output_passes_the_consumers_grammar(golden_set, tmp_path):
     """freddie_cluster.read_segment's regexes (freddie_cluster.py:15-34) restated: every row parses,
     positions strictly increase, one digit per segment, gap indices in range (:131-169)."""
