@@ -741,6 +741,7 @@ static int enqueue_run(frs_context* c, Slot& S) {
   S.caps_used = cp;  // by value in every launch below: a later growth (other slot) does not change this run
 
   // every buffer of the run, before the first launch (a growing buffer drains the context)
+  const auto tr0 = std::chrono::steady_clock::now();
   const int lw = prm->gauss_radius, rr = prm->refine_radius;
   const size_t ptab = (size_t)prm->thr_table_len + (2 * lw + 1) + (2 * rr + 1);
   ENSS(b_params, ptab * 8);
@@ -820,6 +821,8 @@ static int enqueue_run(frs_context* c, Slot& S) {
   while (dp_stage_n > 0 && dps_smem_bytes(dp_max_n, dp_stage_n) > 216 * 1024) dp_stage_n -= 4;
   if (dp_stage_n < 0) dp_stage_n = 0;
 
+  static const bool prof_run = getenv("FRS_HOST_PROFILE") != nullptr;
+  const auto tr1 = std::chrono::steady_clock::now();
   // the run starts when the batch has arrived and the slot's previous results have been read back
   CK(cudaStreamWaitEvent(st, S.ev_up, 0));
   if (S.down_pending) CK(cudaStreamWaitEvent(st, S.ev_down, 0));
@@ -1120,6 +1123,11 @@ static int enqueue_run(frs_context* c, Slot& S) {
   CK(cudaMemcpyAsync(S.h_cnt, d_cnt, CNT_SLOTS * 8, cudaMemcpyDeviceToHost, c->st_tail));
   CK(cudaEventRecord(S.ev_cnt, c->st_tail));
   CK(cudaGetLastError());
+  if (prof_run) {
+    const auto tr2 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[frs host profile] run: buffers %.3f ms, launches enqueued %.3f ms\n",
+            std::chrono::duration<double, std::milli>(tr1 - tr0).count(), std::chrono::duration<double, std::milli>(tr2 - tr1).count());
+  }
   S.enqueued = true;
   S.ran = false;
   return 0;
@@ -1128,8 +1136,13 @@ static int enqueue_run(frs_context* c, Slot& S) {
 // waits for the run of the slot; repeats it with larger buffers if a capacity was missed
 static int finish_run(frs_context* c, Slot& S) {
   if (!S.enqueued) return fail(c, FRS_ERR_STATE, "frs_run: nothing enqueued");
+  static const bool prof_fin = getenv("FRS_HOST_PROFILE") != nullptr;
   for (int attempt = 0;; ++attempt) {
+    const auto tf0 = std::chrono::steady_clock::now();
     CK(cudaEventSynchronize(S.ev_cnt));
+    if (prof_fin)
+      fprintf(stderr, "[frs host profile] run: waited %.3f ms for the device (attempt %d)\n",
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tf0).count(), attempt);
     const i64* h = S.h_cnt;
     const int* he = (const int*)(h + CNT_ERR);
     Caps& cp = c->caps;

@@ -16,10 +16,15 @@ def estimate_reads_from_bytes(split_bytes: int) -> float:
 
 
 def estimate_cost(n_reads: float) -> float:
-    """Relative cost of a tint: streaming steps are linear in the reads; the DP tables grow with
-    candidates x reads, and the candidate count itself grows with the read count before saturating."""
-    k = min(n_reads, 40000.0) / 40.0 + 20.0  # rough candidate count
-    return n_reads * (1.0 + k / 50.0)
+    """Relative GPU cost of a tint, from the only quantity known before parsing: its read count.
+
+    SURVEY.md 8e proposes a model in L, K and R; measured on B200 (``profiles/cost_model.py``, one tint per
+    batch, 1 ... 50 k reads, ``profiles/r02_cost_model_*.txt``) the device time of a tint is close to LINEAR in
+    its reads (~0.05 ms per 1 000 reads) on top of a small per-tint constant -- every stage but the DP streams
+    over reads / samples, and the DP's work per read saturates once the candidate count does.  The first
+    model of this file (reads x candidates, quadratic up to 40 k reads) ranked tints correctly (Spearman 0.97)
+    but overweighted large tints by up to 58x, which starves the GPU that holds a giant tint of other work."""
+    return float(n_reads) + 50.0
 
 
 def estimate_device_bytes(n_reads: float) -> float:
@@ -57,13 +62,15 @@ def lpt_partition(costs: Sequence[Tuple[float, float]], n_bins: int) -> List[Lis
 def batches(jobs: Sequence, costs: Sequence[Tuple[float, float]], batch_reads: int,
             batch_bytes: Optional[float] = None) -> Iterable[List]:
     """Consecutive jobs grouped so that the estimated reads of a batch stay under ``batch_reads`` and, with
-    ``batch_bytes``, its estimated device footprint (``estimate_device_bytes``) under that many bytes.  A
+    ``batch_bytes``, its estimated device footprint (``estimate_device_bytes``) under that many bytes
+    (``batch_bytes`` may be a callable that returns the bound, or None while it is not known yet).  A
     single tint above either bound forms its own batch -- a tint is never split."""
     cur: List = []
     acc, mem = 0.0, 0.0
     for job, (_, n) in zip(jobs, costs):
         m = estimate_device_bytes(n)
-        if cur and (acc + n > batch_reads or (batch_bytes is not None and mem + m > batch_bytes)):
+        bb = batch_bytes() if callable(batch_bytes) else batch_bytes
+        if cur and (acc + n > batch_reads or (bb is not None and mem + m > bb)):
             yield cur
             cur, acc, mem = [], 0.0, 0.0
         cur.append(job)

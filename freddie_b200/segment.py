@@ -243,12 +243,20 @@ def run_directory(split_dir: str, outdir: str, prm: SegmentParams, threads: int 
     else:
         costs = [schedule.estimate_cost_from_files(split_dir, c, t) for c, t in jobs]
     shards = schedule.lpt_partition(costs, n_gpus)
-    # a batch may take about a third of the free device memory of its GPU (two lanes per GPU in flight)
-    free_b = C.c_longlong(0)
-    total_b = C.c_longlong(0)
-    batch_bytes = None
-    if lib.frs_mem_info(0, C.byref(free_b), C.byref(total_b)) == 0 and free_b.value > 0:
-        batch_bytes = free_b.value / (1.5 * max(1, lanes))
+    # a batch may take about a third of the free device memory of its GPU (two lanes per GPU in flight).  The
+    # query needs a CUDA context, so it is made by the first lane whose context exists (never on this thread,
+    # before the lanes have started): until then only the read-count bound applies.
+    mem_bound = {}
+
+    def batch_bytes():
+        return mem_bound.get("bytes")
+
+    def learn_memory(dev):
+        if "bytes" in mem_bound:
+            return
+        free_b, total_b = C.c_longlong(0), C.c_longlong(0)
+        if lib.frs_mem_info(dev, C.byref(free_b), C.byref(total_b)) == 0 and free_b.value > 0:
+            mem_bound["bytes"] = free_b.value / (1.5 * max(1, lanes))
     done = [0]
     total = len(jobs)
     step = max(1, ceil(total / 100)) if total else 1
@@ -310,6 +318,7 @@ def run_directory(split_dir: str, outdir: str, prm: SegmentParams, threads: int 
                     if "err" in box:
                         raise box["err"]
                     eng = box["eng"]
+                    learn_memory(dev)
                     if os.environ.get("FRS_CLI_PROFILE"):
                         sys.stderr.write("[frs cli profile] context of GPU %d lane %d ready after %.3f s\n"
                                          % (dev, lane, time.perf_counter() - t_eng))
