@@ -313,9 +313,8 @@ def run_cuda_arm(args):
     os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     # torchrun pins OMP_NUM_THREADS=1 in its children; the native parser uses OpenMP
     os.environ["OMP_NUM_THREADS"] = str(max(1, cores // max(world, 1)))
-    os.environ.setdefault("NCCL_DEBUG", "WARN")  # the version banner goes to stdout at VERSION / INFO: keep stdout to ONE line
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("INFO", "VERSION", "TRACE"):
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # NCCL logs (version banner, INFO lines the driver may ask for with NCCL_DEBUG) go to stderr: stdout is ONE line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     if world > 1:
         import torch.distributed as dist

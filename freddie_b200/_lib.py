@@ -44,7 +44,8 @@ BATCH_ARRAYS = [
 class FrsBatch(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in BATCH_COUNTS] + [("n_seq_words", C.c_int64)]
                 + [(n, _p) for n in BATCH_ARRAYS]
-                + [("seq_edge_words", C.c_int32), ("reserved0", C.c_int32), ("seq_edge", _p)])
+                + [("seq_edge_words", C.c_int32), ("reserved0", C.c_int32), ("seq_edge", _p),
+                   ("cigar16", _p), ("riv_cig_n", _p), ("qe_from_cigar", C.c_int32), ("reserved1", C.c_int32)])
 
 
 class FrsResultSizes(C.Structure):

@@ -254,6 +254,41 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_flag_compact(const u8* __restr
   }
 }
 
+// Zero fill and small copies as KERNELS: a run must not touch the copy engines, which carry the next batch in
+// and the previous one out (a cudaMemsetAsync / device-to-device cudaMemcpyAsync of a run queues behind
+// those transfers: measured, the head of a pipelined run took 2.7 ms instead of 1.9 ms).
+__global__ void k_zero16(uint4* __restrict__ p, size_t n16) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+    p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+// dst[k] = (i64) value at src[k] for up to 4 scattered words: the totals of scans into the counter block
+struct CopyWords { i64* dst[4]; const void* src[4]; int bytes[4]; int n; };
+__global__ void k_copy_words(CopyWords w) {
+  const int k = threadIdx.x;
+  if (k < w.n) *w.dst[k] = w.bytes[k] == 8 ? *(const i64*)w.src[k] : (i64)*(const int*)w.src[k];
+}
+// final flags of the DP start as the fixed flags (only the candidates that exist)
+__global__ void k_copy_flags(const i64* __restrict__ n_p, const u8* __restrict__ src, u8* __restrict__ dst) {
+  const i64 n = *n_p;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// compact batch encodings -> the arrays the kernels read (frs_batch.cigar16 / riv_cig_n / qe_from_cigar)
+__global__ void k_widen_u16(const unsigned short* __restrict__ in, i64 n, u32* __restrict__ out) {
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) out[i] = in[i];
+}
+__global__ void k_derive_qe(i64 n_ivs, const int* __restrict__ qs, const int* __restrict__ cig_off,
+                            const u32* __restrict__ cigar, int* __restrict__ qe) {
+  for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < n_ivs; k += (i64)gridDim.x * blockDim.x) {
+    int q = qs[k];
+    for (int c = cig_off[k]; c < cig_off[k + 1]; ++c) {
+      const u32 op = cigar[c];
+      if ((op & 15u) <= 1u) q += (int)(op >> 4);  // 0: M/X/=, 1: I consume query bases
+    }
+    qe[k] = q;
+  }
+}
+
 // largest i in [0, n) with off[i] <= x  (off ascending, off[0] <= x)
 __device__ __forceinline__ int upper_row(const int* __restrict__ off, int n, int x) {
   int lo = 0, hi = n;  // invariant: off[lo] <= x, (hi == n or off[hi] > x)

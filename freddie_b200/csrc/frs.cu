@@ -54,6 +54,7 @@ struct Slot {
   // the head of the next batch, so it owns its buffers
   DBuf b_clip_n, b_clip_words, b_clip_off, b_clip_a, b_clip_t, b_task_order, b_task_res, b_poly_cls, b_poly_flag, b_bsum_tail;
   DBuf b_seq_edge, b_clip_eoff;  // edge store of the batch (input) and the clips' offsets into it
+  DBuf b_cigar16, b_cig_n, b_bsum_in;  // compact encodings as they arrive, scratch of the expanding scan
   int edge_words = 0;            // > 0: the edge store is in use for this batch
   frs_batch hb;  // sizes of the batch; its pointers are not used after the upload
   int n_sig_work = 0, n_sig_direct = 0, n_tiles = 0, n_cov_tiles = 0, n_dig_tiles = 0;
@@ -70,6 +71,7 @@ struct Slot {
   // parameters of the run (kept for a repeat after a capacity miss)
   frs_params prm;
   std::vector<double> prm_tables;
+  std::vector<double> dev_tables;  // what the slot's device tables hold (tables + tp), empty = nothing yet
   Caps caps_used = {0, 0, 0, 0, 0, 0, 0, 0};  // capacities the enqueued run was launched with
   frs_result_sizes sizes;
   i64 n_cand = 0, n_sub = 0, cov_elems = 0, tab_elems = 0, clip_words = 0;
@@ -211,6 +213,20 @@ static inline int gs_grid(i64 upper, int threads, int max_ctas = 148 * 8) {
 }
 
 // device-wide helpers ------------------------------------------------------------------------
+// zero fill by a kernel (every buffer has at least 256 bytes of slack behind `bytes`: rounding up to 16 is safe)
+static void dev_zero(frs_context* c, cudaStream_t st, void* p, size_t bytes) {
+  if (!bytes) return;
+  const size_t n16 = (bytes + 15) / 16;
+  const size_t g = (n16 + 255) / 256;
+  k_zero16<<<(unsigned)(g < (size_t)c->n_sm * 16 ? g : (size_t)c->n_sm * 16), 256, 0, st>>>((uint4*)p, n16);
+  c->launch_count++;
+}
+static void dev_copy_word(frs_context* c, cudaStream_t st, i64* dst, const void* src, int bytes) {
+  CopyWords w;
+  w.n = 1; w.dst[0] = dst; w.src[0] = src; w.bytes[0] = bytes;
+  k_copy_words<<<1, 32, 0, st>>>(w);
+  c->launch_count++;
+}
 template <typename TIn, typename TOut>
 static int scan_exclusive_on(frs_context* c, cudaStream_t st, DBuf& scratch, const TIn* in, i64 n, TOut* out) {
   if (n <= SCAN_SMALL_MAX && (const void*)in != (const void*)out) {
@@ -237,7 +253,7 @@ static int compact_flags(frs_context* c, const u8* flags, i64 n, int* idx_out, i
   k_flag_sums<<<nb, SCAN_THREADS, 0, c->stream>>>(flags, n, bs); LAUNCHED();
   k_scan_bsums<<<1, 1024, 0, c->stream>>>(bs, nb); LAUNCHED();
   k_flag_compact<<<nb, SCAN_THREADS, 0, c->stream>>>(flags, n, bs, idx_out); LAUNCHED();
-  CK(cudaMemcpyAsync(count_out, bs + nb, 8, cudaMemcpyDeviceToDevice, c->stream));
+  dev_copy_word(c, c->stream, count_out, bs + nb, 8);
   return 0;
 }
 static const char* deverr_text(int code) {
@@ -476,9 +492,11 @@ static int stage_upload(frs_context* c, Slot& S, const frs_batch* b) {
       b->tint_rep_off[T] != NR || b->tint_read_off[0] != 0 || b->tint_read_off[T] != N ||
       b->island_sample_off[0] != 0 || b->island_sample_off[NI] != b->n_samples || b->rep_iv_off[0] != 0 ||
       b->rep_iv_off[NR] != b->n_rep_ivs || b->read_iv_off[0] != 0 || b->read_iv_off[N] != b->n_read_ivs ||
-      b->riv_cig_off[0] != 0 || b->riv_cig_off[b->n_read_ivs] != b->n_cigar_ops || b->read_seq_off[0] != 0 ||
-      b->read_seq_off[N] != b->n_seq_words)
+      (b->riv_cig_off && (b->riv_cig_off[0] != 0 || b->riv_cig_off[b->n_read_ivs] != b->n_cigar_ops)) ||
+      b->read_seq_off[0] != 0 || b->read_seq_off[N] != b->n_seq_words)
     return fail(c, FRS_ERR_ARG, "frs_upload: inconsistent offset tables");
+  if ((!b->cigar && !b->cigar16) || (!b->riv_cig_off && !b->riv_cig_n) || (!b->riv_qe && !b->qe_from_cigar))
+    return fail(c, FRS_ERR_ARG, "frs_upload: cigar / riv_cig_off / riv_qe missing without their compact form");
   for (int t = 0; t < T; ++t)
     // a tint without reads is legal (the reference writes a header-only SEGMENT file for it)
     if (b->tint_island_off[t + 1] <= b->tint_island_off[t] || b->tint_rep_off[t + 1] < b->tint_rep_off[t] ||
@@ -601,9 +619,33 @@ static int stage_upload(frs_context* c, Slot& S, const frs_batch* b) {
     H2D(b_riv_te, b->riv_te, (size_t)b->n_read_ivs * 4);
   }
   H2D(b_riv_qs, b->riv_qs, (size_t)b->n_read_ivs * 4);
-  H2D(b_riv_qe, b->riv_qe, (size_t)b->n_read_ivs * 4);
-  H2D(b_riv_cig_off, b->riv_cig_off, (size_t)(b->n_read_ivs + 1) * 4);
-  H2D(b_cigar, b->cigar, (size_t)b->n_cigar_ops * 4);
+  // CIGAR ops, their offsets and the query ends: whole, or in their compact forms (expanded by kernels below)
+  if (b->cigar16) {
+    H2D(b_cigar16, b->cigar16, (size_t)b->n_cigar_ops * 2);
+    ENSS(b_cigar, (size_t)b->n_cigar_ops * 4);
+    if (b->n_cigar_ops > 0)
+      k_widen_u16<<<gs_grid(b->n_cigar_ops, 256), 256, 0, c->st_in>>>(S.b_cigar16.as<unsigned short>(), b->n_cigar_ops, S.b_cigar.as<u32>());
+  } else {
+    H2D(b_cigar, b->cigar, (size_t)b->n_cigar_ops * 4);
+  }
+  if (b->riv_cig_n) {
+    H2D(b_cig_n, b->riv_cig_n, (size_t)b->n_read_ivs);
+    ENSS(b_riv_cig_off, (size_t)(b->n_read_ivs + 1) * 4);
+    const int saved = c->launch_count;
+    int r = scan_exclusive_on<u8, int>(c, c->st_in, S.b_bsum_in, S.b_cig_n.as<u8>(), (i64)b->n_read_ivs, S.b_riv_cig_off.as<int>());
+    c->launch_count = saved;
+    if (r) return r;
+  } else {
+    H2D(b_riv_cig_off, b->riv_cig_off, (size_t)(b->n_read_ivs + 1) * 4);
+  }
+  if (b->riv_qe) {
+    H2D(b_riv_qe, b->riv_qe, (size_t)b->n_read_ivs * 4);
+  } else {
+    ENSS(b_riv_qe, (size_t)b->n_read_ivs * 4);
+    if (b->n_read_ivs > 0)
+      k_derive_qe<<<gs_grid(b->n_read_ivs, 256), 256, 0, c->st_in>>>(b->n_read_ivs, S.b_riv_qs.as<int>(), S.b_riv_cig_off.as<int>(),
+                                                                   S.b_cigar.as<u32>(), S.b_riv_qe.as<int>());
+  }
   // sequence bit-planes.  The poly-A/T scans only look at the soft clips of a read, and those are known
   // after segmentation.  Lazy mode (default): when the caller's planes are pinned / registered host memory
   // the device can address, nothing is copied here and k_clip_gather fetches just the clip words during the
@@ -832,12 +874,20 @@ static int enqueue_run(frs_context* c, Slot& S) {
   double* d_tbl = S.b_params.as<double>();
   double* d_gw = d_tbl + prm->thr_table_len;
   double* d_rw = d_gw + (2 * lw + 1);
-  CK(cudaMemcpyAsync(d_tbl, S.prm_tables.data(), ptab * 8, cudaMemcpyHostToDevice, st));
   const int2* d_cut = S.b_cut_tab.as<int2>();
-  k_cut_table<<<CUT_TAB_N / 256, 256, 0, st>>>(d_tbl, prm->thr_table_len, prm->tp, S.b_cut_tab.as<int2>());
+  std::vector<double> key = S.prm_tables;
+  key.push_back(prm->tp);
+  key.push_back((double)prm->thr_table_len);
+  key.push_back((double)lw);
+  if (S.dev_tables != key) {  // else the tables of the slot are those of its last run: nothing to copy
+    CK(cudaMemcpyAsync(d_tbl, S.prm_tables.data(), ptab * 8, cudaMemcpyHostToDevice, st));
+    k_cut_table<<<CUT_TAB_N / 256, 256, 0, st>>>(d_tbl, prm->thr_table_len, prm->tp, S.b_cut_tab.as<int2>());
+    LAUNCHED();
+    S.dev_tables.swap(key);
+  }
 
   i64* d_cnt = S.b_counters.as<i64>();
-  CK(cudaMemsetAsync(d_cnt, 0, CNT_SLOTS * 8, st));
+  dev_zero(c, st, d_cnt, CNT_SLOTS * 8);
   int* d_err = (int*)(d_cnt + CNT_ERR);
 
   const int* d_tint_island_off = S.b_tint_island_off.as<int>();
@@ -847,7 +897,7 @@ static int enqueue_run(frs_context* c, Slot& S) {
 
   // ================= phase 1: signal -> smoothed signal -> candidates, threshold =================
   stage_begin(c, "signal");
-  CK(cudaMemsetAsync(c->b_yraw.p, 0, L * 4, st));
+  dev_zero(c, st, c->b_yraw.p, L * 4);
   if (S.n_sig_work > 0) {
     k_signal<<<S.n_sig_work, SIG_THREADS, SIG_BINS * 4, st>>>(S.b_sig_work.as<SigWork>(), S.b_rep_iv_off.as<int>(),
                                                                S.b_rep_weight.as<int>(), S.b_rep_fs.as<int>(),
@@ -868,7 +918,7 @@ static int enqueue_run(frs_context* c, Slot& S) {
     u32* d_cmask = (u32*)(d_gsum + n_groups);
     u32* d_pmask = d_cmask + (size_t)S.n_tiles * TILE_WORDS;
     u32* d_tcnt = d_pmask + (size_t)S.n_tiles * TILE_WORDS;
-    CK(cudaMemsetAsync(d_gsum, 0, n_groups * 8, st));
+    dev_zero(c, st, d_gsum, n_groups * 8);
     const size_t sm = (size_t)p1_smem_layout(lw).total;
     if (sm > 48 * 1024) CK(cudaFuncSetAttribute(k_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k_smooth<<<S.n_tiles, GAUSS_THREADS, sm, st>>>(S.b_tiles.as<TileWork>(), d_island_sample_off, c->b_yraw.as<int>(),
@@ -929,7 +979,8 @@ static int enqueue_run(frs_context* c, Slot& S) {
       d_cnt, S.n_cov_tiles > 0 ? cp.P : -1);
   LAUNCHED();
 
-  CK(cudaMemcpyAsync(c->b_dpfinal.p, c->b_fixed1.p, KMAX, cudaMemcpyDeviceToDevice, st));
+  k_copy_flags<<<g_cand, 256, 0, st>>>(d_K, c->b_fixed1.as<u8>(), c->b_dpfinal.as<u8>());
+  LAUNCHED();
   {
     stage_begin(c, "dp_plan");
     k_sub_fill<<<gs_grid(NSUB_MAX, 256, 148 * 4), 256, 0, st>>>(d_cnt, cp, c->b_sub_info.as<int>(), c->b_sub_slabs.as<int>(),
@@ -996,7 +1047,7 @@ static int enqueue_run(frs_context* c, Slot& S) {
 
   // ================= phase 3: refine, final positions, digits =================
   stage_begin(c, "refine");
-  CK(cudaMemsetAsync(c->b_sflag.p, 0, L, st));
+  dev_zero(c, st, c->b_sflag.p, L);
   int* d_ref_cnt = (int*)(d_cnt + CNT_REF);
   int* d_ref_cnt2 = (int*)(d_cnt + CNT_REF2);
   k_final_mark<<<g_cand, 256, 0, st>>>(d_K, c->b_dpfinal.as<u8>(), c->b_cand_flat.as<int>(),
@@ -1021,13 +1072,13 @@ static int enqueue_run(frs_context* c, Slot& S) {
   k_digit_sizes<<<cdiv(T, 256), 256, 0, st>>>(T, d_tint_rep_off, S.b_tint_final_off.as<int>(), c->b_dig_sz.as<i64>());
   LAUNCHED();
   { int r = scan_exclusive<i64, i64>(c, c->b_dig_sz.as<i64>(), T, S.b_tint_digit_off.as<i64>()); if (r) return r; }
-  CK(cudaMemcpyAsync(d_cnt + CNT_NDIG, S.b_tint_digit_off.as<i64>() + T, 8, cudaMemcpyDeviceToDevice, st));
+  dev_copy_word(c, st, d_cnt + CNT_NDIG, S.b_tint_digit_off.as<i64>() + T, 8);
   k_seg_cuts<<<148 * 4, 256, 0, st>>>(d_nfin, c->b_final_flat.as<int>(), c->b_final_island.as<int>(), d_cut, d_tbl,
                                       prm->thr_table_len, prm->tp, c->b_seg_ty.as<int>(), c->b_seg_tn.as<int>());
   LAUNCHED();
 
   stage_begin(c, "digits");
-  CK(cudaMemsetAsync(c->b_run_cnt.p, 0, (size_t)std::max(NR, 1) * 4, st));
+  dev_zero(c, st, c->b_run_cnt.p, (size_t)std::max(NR, 1) * 4);
   if (S.n_dig_tiles > 0) {
     k_digits<<<dim3((unsigned)S.n_dig_tiles, DIG_CHUNKS), DIG_THREADS, 0, st>>>(
         S.b_dig_tiles.as<RepTile>(), d_tint_rep_off, S.b_tint_final_off.as<int>(), S.b_tint_digit_off.as<i64>(),
@@ -1038,13 +1089,13 @@ static int enqueue_run(frs_context* c, Slot& S) {
 
   stage_begin(c, "runs");
   { int r = scan_exclusive<int, int>(c, c->b_run_cnt.as<int>(), NR, c->b_run_off.as<int>()); if (r) return r; }
-  CK(cudaMemcpyAsync(d_cnt + CNT_NRUN, c->b_run_off.as<int>() + NR, 4, cudaMemcpyDeviceToDevice, st));
+  dev_copy_word(c, st, d_cnt + CNT_NRUN, c->b_run_off.as<int>() + NR, 4);
   if (N > 0) {
     k_gap_count<<<cdiv(N, 256), 256, 0, st>>>(N, S.b_read_rep.as<int>(), c->b_run_off.as<int>(), c->b_gap_cnt.as<int>());
     LAUNCHED();
   }
   { int r = scan_exclusive<int, int>(c, c->b_gap_cnt.as<int>(), N, S.b_read_gap_off.as<int>()); if (r) return r; }
-  CK(cudaMemcpyAsync(d_cnt + CNT_NGAP, S.b_read_gap_off.as<int>() + N, 4, cudaMemcpyDeviceToDevice, st));
+  dev_copy_word(c, st, d_cnt + CNT_NGAP, S.b_read_gap_off.as<int>() + N, 4);
   if (NR > 0) {
     k_run_fill<<<cdiv((i64)NR * 32, 256), 256, 0, st>>>(NR, S.b_rep_tint.as<int>(), d_tint_rep_off,
                                                         S.b_tint_final_off.as<int>(), S.b_tint_digit_off.as<i64>(),
@@ -1085,13 +1136,13 @@ static int enqueue_run(frs_context* c, Slot& S) {
     if (S.tl[3]) cudaEventRecord(S.tl[3], st);
     CK(cudaEventRecord(S.ev_head, st));
     CK(cudaStreamWaitEvent(tl, S.ev_head, 0));
-    CK(cudaMemsetAsync(S.b_poly_cls.p, 0, (2 * POLY_CLASSES + 1) * 4, tl));
+    dev_zero(c, tl, S.b_poly_cls.p, (2 * POLY_CLASSES + 1) * 4);
     if (!S.seq_resident) {
       stage_begin(c, "clip_fetch", tl);
       // compact offsets of the clips' plane words (total at [2N]), then the words themselves, straight from
       // the caller's pinned planes
       { int r = scan_exclusive_on<int, i64>(c, tl, S.b_bsum_tail, S.b_clip_words.as<int>(), (i64)N * 2, S.b_clip_off.as<i64>()); if (r) return r; }
-      CK(cudaMemcpyAsync(d_cnt + CNT_CLIPW, S.b_clip_off.as<i64>() + (i64)N * 2, 8, cudaMemcpyDeviceToDevice, tl));
+      dev_copy_word(c, tl, d_cnt + CNT_CLIPW, S.b_clip_off.as<i64>() + (i64)N * 2, 8);
       // a few CTAs only: the kernel waits on the bus (the bus allows a few hundred reads in flight, not tens of
       // thousands), and loads from host memory that are pending for microseconds fill the miss queues of the SM
       // they run on -- the other SMs belong to the head of the next batch meanwhile

@@ -48,7 +48,7 @@ class PackedBatch:
             n_cigar_ops=len(a["cigar"]), n_samples=int(a["island_sample_off"][-1]), n_seq_words=len(a["seq_is_a"]),
         )
 
-    EDGE_WORDS = 8  # plane words per side in the edge store (256 bases: ~5 of 6 soft clips of ONT-like reads)
+    EDGE_WORDS = 16  # plane words per side in the edge store (512 bases: ~19 of 20 soft clips of ONT-like reads)
 
     def build_edge_store(self, words: int = None) -> np.ndarray:
         """``frs_batch.seq_edge``: the first and the last ``words`` plane words of every read, dense
@@ -75,11 +75,34 @@ class PackedBatch:
         self._struct_key = None
         return self.seq_edge
 
+    def compact(self) -> "PackedBatch":
+        """Adds the compact encodings ``frs_batch`` accepts for three per-interval arrays (a quarter of the bytes
+        of a batch): CIGAR ops as uint16 when every length is < 4096, op counts per interval as uint8 instead
+        of int32 offsets, and the query ends left out when they equal ``qs`` + the query bases the interval's
+        CIGAR consumes.  Each one only when it is exact for this batch; the full arrays stay available."""
+        a = self.arrays
+        self.compact_arrays = {}
+        cig = a["cigar"]
+        if len(cig) == 0 or int(cig.max()) < (1 << 16):
+            self.compact_arrays["cigar16"] = np.ascontiguousarray(cig.astype(np.uint16))
+        n = np.diff(a["riv_cig_off"])
+        if len(n) == 0 or int(n.max()) < 256:
+            self.compact_arrays["riv_cig_n"] = np.ascontiguousarray(n.astype(np.uint8))
+        ql = np.where((cig & 15) <= 1, cig >> 4, 0).astype(np.int64)
+        csum = np.concatenate([[0], np.cumsum(ql)])
+        off = a["riv_cig_off"].astype(np.int64)
+        self.qe_from_cigar = bool(np.array_equal(a["riv_qs"].astype(np.int64) + csum[off[1:]] - csum[off[:-1]],
+                                                 a["riv_qe"].astype(np.int64)))
+        self._struct_key = None
+        return self
+
     def as_struct(self) -> "_lib.FrsBatch":
         """The ``frs_batch`` view of the arrays (cached: building ~30 ctypes pointers costs more than enqueueing
         the batch; the cache is dropped when ``derive_riv`` or the arrays change identity)."""
         edge = getattr(self, "seq_edge", None)
-        key = (self.derive_riv, id(edge), tuple(id(v) for v in self.arrays.values()))
+        comp = getattr(self, "compact_arrays", None) or {}
+        qe_c = bool(getattr(self, "qe_from_cigar", False)) and bool(comp)
+        key = (self.derive_riv, id(edge), id(comp), qe_c, tuple(id(v) for v in self.arrays.values()))
         if getattr(self, "_struct_key", None) == key:
             return self._struct
         b = _lib.FrsBatch()
@@ -89,23 +112,37 @@ class PackedBatch:
             if self.derive_riv and name in ("riv_ts", "riv_te"):
                 setattr(b, name, None)  # the library derives them from the rep intervals (no copy)
                 continue
+            if (name == "cigar" and "cigar16" in comp) or (name == "riv_cig_off" and "riv_cig_n" in comp) or (
+                    name == "riv_qe" and qe_c):
+                setattr(b, name, None)  # travels in its compact form
+                continue
             arr = self.arrays[name]
             assert arr.dtype == _DTYPES[name] and arr.flags["C_CONTIGUOUS"], name
             setattr(b, name, arr.ctypes.data_as(C.c_void_p))
         if edge is not None and len(edge):
             b.seq_edge_words = self.seq_edge_words
             b.seq_edge = edge.ctypes.data_as(C.c_void_p)
+        for name, arr in comp.items():
+            setattr(b, name, arr.ctypes.data_as(C.c_void_p))
+        b.qe_from_cigar = int(qe_c)
         self._struct, self._struct_key = b, key
         return b
 
     def nbytes(self) -> int:
         return int(sum(v.nbytes for v in self.arrays.values()))
 
-    def pin(self, edge_words: int = None):
-        """Moves the arrays into page-locked host memory (torch is used for buffer management only) and adds
-        the edge store of the sequence planes (``build_edge_store``; ``edge_words=0``: none)."""
+    def pin(self, edge_words: int = None, compact: bool = True):
+        """Moves the arrays into page-locked host memory (torch is used for buffer management only), adds
+        the edge store of the sequence planes (``build_edge_store``; ``edge_words=0``: none) and the compact
+        encodings of ``compact()``."""
         import torch
         self._pinned = {}
+        if compact:
+            self.compact()
+            for k, v in list(self.compact_arrays.items()):
+                t = torch.from_numpy(v if v.size else np.zeros(1, dtype=v.dtype)).pin_memory()
+                self._pinned["c_" + k] = t
+                self.compact_arrays[k] = t.numpy()[: v.size] if v.size else t.numpy()[:0]
         if edge_words is None or edge_words > 0:
             e = self.build_edge_store(edge_words)
             te = torch.from_numpy(e if e.size else np.zeros(1, dtype=np.uint32)).pin_memory()

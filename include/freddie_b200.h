@@ -99,6 +99,16 @@ typedef struct {
   int32_t seq_edge_words;
   int32_t reserved0;
   const uint32_t* seq_edge;
+  /* optional COMPACT encodings of three read-interval arrays (each may be NULL; a quarter of the batch's bytes on
+   * the bus): expanded on the device into the arrays above, which may then be NULL themselves.
+   *   cigar16    [n_cigar_ops]  the same (len << 4) | op values as `cigar` when every len < 4096
+   *   riv_cig_n  [n_read_ivs]   CIGAR ops of each interval (< 256) instead of the offsets `riv_cig_off`
+   *   riv_qe == NULL (with qe_from_cigar = 1): qe = qs + query bases the interval's CIGAR consumes (M/X/=/I);
+   *              the packer sets it only after checking that equality on every interval */
+  const uint16_t* cigar16;
+  const uint8_t* riv_cig_n;
+  int32_t qe_from_cigar;
+  int32_t reserved1;
 } frs_batch;
 
 /* Sizes of the variable-length results of the batch that was just run. */

@@ -20,7 +20,7 @@ from freddie_b200.engine import Engine, SegmentParams  # noqa: E402
 from freddie_b200.pack import pack_tints  # noqa: E402
 
 tints = synth.make_config(2, scale=float(os.environ.get("SCALE", "1")), seed=2, workers=16)
-batch = pack_tints(tints).pin()
+batch = pack_tints(tints).pin(edge_words=int(os.environ.get("EDGE", "8")))
 prm = SegmentParams()
 e = Engine(0)
 r = None

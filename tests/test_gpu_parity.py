@@ -268,6 +268,31 @@ def test_lazy_clip_fetch_equals_resident_planes(name, golden_set, eng):
             assert np.array_equal(lazy.arrays[k], got.arrays[k]), (name, E, k)
 
 
+@pytest.mark.parametrize("name", ["cfg1", "cfg2_small", "dup_heavy", "cfg3_mini", "degenerate"])
+def test_compact_interval_encodings_equal_the_full_arrays(name, golden_set, eng):
+    """frs_batch.cigar16 / riv_cig_n / qe_from_cigar: CIGAR ops as uint16, op counts as uint8 and query ends derived
+    from qs + CIGAR are expanded on the device into the arrays the kernels read; results must equal those with the
+    full arrays, and the upload must shrink by exactly the bytes saved."""
+    from freddie_b200.pack import pack_tints
+    tints, flags, _ = golden_set(name)
+    _, gprm = _params(flags)
+    full = pack_tints(tints)
+    want = eng.segment_batch(full, gprm)
+    h_full = eng.stats()["h2d_upload"]
+    comp = pack_tints(tints).compact()
+    assert set(comp.compact_arrays) == {"cigar16", "riv_cig_n"} and comp.qe_from_cigar
+    got = eng.segment_batch(comp, gprm)
+    c = full.counts()
+    saved = 2 * c["n_cigar_ops"] + (4 * (c["n_read_ivs"] + 1) - c["n_read_ivs"]) + 4 * c["n_read_ivs"]
+    assert h_full - eng.stats()["h2d_upload"] == saved
+    for k in want.arrays:
+        assert np.array_equal(want.arrays[k], got.arrays[k]), (name, k)
+    # an interval whose query end is NOT qs + CIGAR keeps its array
+    odd = pack_tints(tints)
+    odd.arrays["riv_qe"][0] += 1
+    assert not odd.compact().qe_from_cigar and odd.as_struct().riv_qe is not None
+
+
 def test_pipelined_submit_wait_fetch_equals_the_synchronous_calls(golden_set):
     """frs_submit / frs_wait / frs_fetch: up to four batches in flight in ONE context (the copies of one overlap the
     kernels of the other); results must be those of upload + run + download, in any interleaving."""
