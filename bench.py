@@ -411,8 +411,8 @@ def run_cuda_arm(args):
     d2h = int(sum(v.nbytes for r in res_lazy for v in r.arrays.values())) + len(batches) * 48 * 8
 
     def pipelined(e2, bufs, work):
-        """work: list of batch indices in order.  Up to four batches in flight (copy in | head kernels | tail |
-        copy out); the host thread only ever blocks in frs_wait: the read-back of a batch is started
+        """work: list of batch indices in order.  Up to five batches in flight (copy in | head kernels | tail |
+        copy out, one queued behind them); the host thread only ever blocks in frs_wait: the read-back of a batch is started
         (frs_fetch_start) and collected one iteration later (frs_fetch_finish), behind the submit of the next."""
         from collections import deque
         fly = deque()
@@ -422,7 +422,7 @@ def run_cuda_arm(args):
             if pending is not None:
                 e2.fetch_finish(pending)
                 pending = None
-            if len(fly) == 3:
+            if len(fly) == 4:
                 pt, pi, pn = fly.popleft()
                 e2.wait(pt)
                 e2.fetch_start(pt, bufs[pn & 1][pi])
@@ -540,7 +540,7 @@ def run_cuda_arm(args):
                      e2e_ms_per_gpu=[round(x * 1e3, 4) for x in busy_e2e], e2e_max_over_mean=round(max(busy_e2e) / mean(busy_e2e), 4)),
         e2e=dict(value=e2e_v, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                  timing="wall clock around K steps, synchronize on both sides; frs_submit / frs_wait / frs_fetch with pinned "
-                        "host buffers, up to four batches in flight per context (copy in | head kernels | tail | copy out)",
+                        "host buffers, up to five batches in flight per context (copy in | head kernels | tail | copy out, one queued)",
                  one_context_value=tot_reads * args.steps / t_pipe1,
                  contexts_value=tot_reads * args.steps / t_pipe2, contexts=n_ctx,
                  serial_value=tot_reads * args.steps / t_serial,

@@ -18,7 +18,7 @@ FRS_MAX_STAGES = 32
 TAP_Y_RAW, TAP_Y, TAP_THR, TAP_CAND, TAP_FIXED, TAP_DP_FINAL, TAP_SUB_START, TAP_SUB_N = 1, 2, 3, 4, 5, 6, 7, 8
 TAP_COVERAGE, TAP_DP_TABLES, TAP_COV_OFF, TAP_SUB_TAB_OFF, TAP_FINAL_FLAGS = 9, 10, 12, 13, 14
 OPT_SLAB_WORDS, OPT_KEEP_DP_TABLES, OPT_POLY_LONG_CLASS, OPT_LAZY_SEQ = 1, 2, 3, 4
-STAT_NAMES = ["h2d_upload", "h2d_run", "d2h_run", "clip_words", "seq_words", "poly_tasks", "poly_long_tasks", "reruns"]
+STAT_NAMES = ["h2d_upload", "h2d_run", "d2h_run", "clip_words", "seq_words", "poly_tasks", "poly_long_tasks", "reruns", "h2d_copies"]
 
 _p = C.c_void_p
 
@@ -44,7 +44,7 @@ BATCH_ARRAYS = [
 class FrsBatch(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in BATCH_COUNTS] + [("n_seq_words", C.c_int64)]
                 + [(n, _p) for n in BATCH_ARRAYS]
-                + [("seq_edge_words", C.c_int32), ("reserved0", C.c_int32), ("seq_edge", _p),
+                + [("seq_edge_words", C.c_int32), ("host_arena", C.c_int32), ("seq_edge", _p),
                    ("cigar16", _p), ("riv_cig_n", _p), ("qe_from_cigar", C.c_int32), ("reserved1", C.c_int32)])
 
 

@@ -125,34 +125,75 @@ class PackedBatch:
         for name, arr in comp.items():
             setattr(b, name, arr.ctypes.data_as(C.c_void_p))
         b.qe_from_cigar = int(qe_c)
+        b.host_arena = int(bool(getattr(self, "host_arena", False)))
         self._struct, self._struct_key = b, key
         return b
 
     def nbytes(self) -> int:
         return int(sum(v.nbytes for v in self.arrays.values()))
 
+    # order in which frs_upload copies the arrays of a batch (frs.cu: stage_upload); arrays laid out in this
+    # order inside one pinned allocation, each at the next multiple of 256 bytes, cross the bus as one copy
+    UPLOAD_ORDER = ["tint_island_off", "tint_rep_off", "tint_read_off", "island_start", "island_sample_off",
+                    "rep_iv_off", "rep_weight", "rep_iv_fs", "rep_iv_fe", "read_rep", "read_strand", "read_len",
+                    "read_iv_off", "read_seq_off", "riv_ts", "riv_te", "riv_qs", "cigar", "riv_cig_off", "riv_qe"]
+
     def pin(self, edge_words: int = None, compact: bool = True):
         """Moves the arrays into page-locked host memory (torch is used for buffer management only), adds
         the edge store of the sequence planes (``build_edge_store``; ``edge_words=0``: none) and the compact
-        encodings of ``compact()``."""
+        encodings of ``compact()``.  Everything ``frs_upload`` copies is placed in ONE pinned allocation in the
+        library's upload order (``frs_batch.host_arena``): the arrays that travel first, in order, then the
+        ones that stay behind (full forms of compacted arrays, derivable arrays)."""
         import torch
         self._pinned = {}
         if compact:
             self.compact()
-            for k, v in list(self.compact_arrays.items()):
-                t = torch.from_numpy(v if v.size else np.zeros(1, dtype=v.dtype)).pin_memory()
-                self._pinned["c_" + k] = t
-                self.compact_arrays[k] = t.numpy()[: v.size] if v.size else t.numpy()[:0]
-        if edge_words is None or edge_words > 0:
-            e = self.build_edge_store(edge_words)
-            te = torch.from_numpy(e if e.size else np.zeros(1, dtype=np.uint32)).pin_memory()
-            self._pinned["seq_edge"] = te
-            self.seq_edge = te.numpy()[: e.size]
-        for k, v in list(self.arrays.items()):
-            t = torch.from_numpy(v if v.size else np.zeros(1, dtype=v.dtype))
-            t = t.pin_memory()
+        comp = getattr(self, "compact_arrays", None) or {}
+        qe_c = bool(getattr(self, "qe_from_cigar", False)) and bool(comp)
+        edge = self.build_edge_store(edge_words) if (edge_words is None or edge_words > 0) else None
+        sent, kept = [], []
+        for name in self.UPLOAD_ORDER:
+            if self.derive_riv and name in ("riv_ts", "riv_te"):
+                kept.append(("a", name))
+            elif name == "cigar" and "cigar16" in comp:
+                sent.append(("c", "cigar16"))
+                kept.append(("a", name))
+            elif name == "riv_cig_off" and "riv_cig_n" in comp:
+                sent.append(("c", "riv_cig_n"))
+                kept.append(("a", name))
+            elif name == "riv_qe" and qe_c:
+                kept.append(("a", name))
+            else:
+                sent.append(("a", name))
+        if edge is not None:
+            sent.append(("e", "seq_edge"))
+        items = sent + kept
+        get = lambda kind, name: (self.arrays if kind == "a" else comp)[name] if kind != "e" else edge  # noqa: E731
+        al = lambda n: (max(int(n), 16) + 255) & ~255  # noqa: E731
+        total = sum(al(get(k, n).nbytes) for k, n in items)
+        arena = torch.empty(total + 256, dtype=torch.uint8).pin_memory()
+        self._pinned["arena"] = arena
+        base = arena.numpy()
+        skew = (-base.ctypes.data) % 256  # the allocation is page-aligned in practice; keep the rule anyway
+        off = skew
+        for kind, name in items:
+            v = get(kind, name)
+            view = base[off:off + v.nbytes].view(v.dtype)
+            view[...] = v
+            if kind == "a":
+                self.arrays[name] = view
+            elif kind == "c":
+                comp[name] = view
+            else:
+                self.seq_edge = view
+            off += al(v.nbytes)
+        for k in ("seq_is_a", "seq_is_t"):  # the planes stay where they are read from on demand
+            v = self.arrays[k]
+            t = torch.from_numpy(v if v.size else np.zeros(1, dtype=v.dtype)).pin_memory()
             self._pinned[k] = t
             self.arrays[k] = t.numpy()[: v.size] if v.size else t.numpy()[:0]
+        self.host_arena = True
+        self._struct_key = None
         return self
 
 

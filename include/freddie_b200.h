@@ -97,7 +97,10 @@ typedef struct {
    * edge store, frs_upload copies the store whole (one dense DMA) and only the few clips longer than 32*E bases
    * are fetched from the planes afterwards. */
   int32_t seq_edge_words;
-  int32_t reserved0;
+  int32_t host_arena; /* 1: the arrays of this struct that are copied (all but the two sequence planes) lie in ONE pinned
+                         allocation, in the order of the fields of this struct (compact forms in the place of the
+                         arrays they stand for, seq_edge last), each starting at the next multiple of 256 bytes:
+                         frs_upload then moves them with a few large copies.  0: no assumption. */
   const uint32_t* seq_edge;
   /* optional COMPACT encodings of three read-interval arrays (each may be NULL; a quarter of the batch's bytes on
    * the bus): expanded on the device into the arrays above, which may then be NULL themselves.
@@ -170,7 +173,7 @@ int frs_download(frs_context* ctx, const frs_result* out);
 int frs_segment_batch(frs_context* ctx, const frs_batch* batch, const frs_params* prm,
                       frs_result_sizes* sizes);
 
-/* ---- the same hot path, pipelined: up to four batches in flight per context (copy in | kernels | tail | copy out), ONE host thread.
+/* ---- the same hot path, pipelined: up to six batches in flight per context (copy in | kernels | tail | copy out), ONE host thread.
  * The reference overlaps tints with a process pool (imap_unordered, freddie_segment.py:871-876); here the
  * copy of batch k+1 and the read-back of batch k-1 overlap the kernels of batch k on the copy engines.
  *   frs_submit  enqueues the host-to-device copies and every kernel of the run and returns at once (no
@@ -179,7 +182,7 @@ int frs_segment_batch(frs_context* ctx, const frs_batch* batch, const frs_params
  *   frs_wait    blocks until the run is complete and returns the result sizes (if a data-dependent buffer
  *               was too small it is grown and the run repeated first: first batches of a context only).
  *   frs_fetch   copies the results into caller buffers, blocks until they have arrived, frees the ticket.
-  * Tickets are slots: at most four may be outstanding, and they complete in submission order.  The tail of a
+  * Tickets are slots: at most six may be outstanding, and they complete in submission order.  The tail of a
  * run (clip fetch from pinned host memory, poly-A/T scans) executes on its own stream beside the head of the
  * next batch. */
 int frs_submit(frs_context* ctx, const frs_batch* batch, const frs_params* prm, int* ticket);
@@ -231,12 +234,13 @@ enum {
 int frs_set_option(frs_context* ctx, int key, long long value);
 
 /* transfer statistics of the last frs_upload / frs_run; returns the number of statistics */
-#define FRS_N_STATS 8
+#define FRS_N_STATS 9
 enum { FRS_STAT_H2D_UPLOAD = 0, FRS_STAT_H2D_RUN = 1 /* bytes the device fetched from the caller's pinned planes */,
        FRS_STAT_D2H_RUN = 2, FRS_STAT_CLIP_WORDS = 3,
        FRS_STAT_SEQ_WORDS = 4, FRS_STAT_POLY_TASKS = 5 /* poly-A/T scan tasks that survived the 5-stretch filter */,
        FRS_STAT_POLY_LONG_TASKS = 6 /* of which scanned by a whole warp */,
-       FRS_STAT_RERUNS = 7 /* runs of this context repeated because a buffer capacity was missed */ };
+       FRS_STAT_RERUNS = 7 /* runs of this context repeated because a buffer capacity was missed */,
+       FRS_STAT_H2D_COPIES = 8 /* host-to-device copies the last upload issued (adjacent arrays are merged) */ };
 int frs_get_stats(frs_context* ctx, long long* out, int n);
 
 /* ---- per-kernel device timing of the last frs_run (CUDA events on the context stream) ---- */

@@ -20,7 +20,7 @@ from freddie_b200.engine import Engine, SegmentParams  # noqa: E402
 from freddie_b200.pack import pack_tints  # noqa: E402
 
 tints = synth.make_config(2, scale=float(os.environ.get("SCALE", "1")), seed=2, workers=16)
-batch = pack_tints(tints).pin(edge_words=int(os.environ.get("EDGE", "8")))
+batch = pack_tints(tints).pin(edge_words=int(os.environ["EDGE"]) if "EDGE" in os.environ else None)
 prm = SegmentParams()
 e = Engine(0)
 r = None
@@ -66,7 +66,7 @@ def pipelined(K):
     w0 = time.perf_counter()
     fly = deque()
     pending = None
-    for k in range(K + 2):
+    for k in range(K + 6):
         t0 = time.perf_counter()
         if k < K:
             fly.append(e.submit(batch, prm))
@@ -77,7 +77,7 @@ def pipelined(K):
         t1 = time.perf_counter()
         acc["submit"] += ta - t0
         acc["fetch"] += t1 - ta
-        if len(fly) == 3 or (k >= K and fly):
+        if len(fly) == int(os.environ.get("DEPTH", "4")) or (k >= K and fly):
             pt = fly.popleft()
             e.wait(pt)
             t2 = time.perf_counter()
@@ -92,7 +92,7 @@ def pipelined(K):
     return time.perf_counter() - w0, acc
 
 
-pipelined(6)  # every slot has its buffers now
+pipelined(12)  # every slot has its buffers now
 K = 20
 e.set_profiling(True)
 dt, acc = pipelined(K)

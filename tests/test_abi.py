@@ -22,10 +22,11 @@ def test_header_symbols_are_exported(built_lib):
 
 def test_abi_version_and_struct_sizes(built_lib):
     from freddie_b200 import _lib
-    assert built_lib.frs_abi_version() == 1
+    assert built_lib.frs_abi_version() == 2
     # layouts the header promises (x86-64 SysV): 3 doubles + 4 int32 + 3 pointers + 2 int32
     assert C.sizeof(_lib.FrsParams) == 3 * 8 + 4 * 4 + 3 * 8 + 2 * 4
-    assert C.sizeof(_lib.FrsBatch) == 8 * 4 + 8 + 22 * 8
+    # 8 counts + n_seq_words + 22 arrays + (seq_edge_words, host_arena) + seq_edge, cigar16, riv_cig_n + (qe_from_cigar, reserved1)
+    assert C.sizeof(_lib.FrsBatch) == 8 * 4 + 8 + 22 * 8 + 8 + 3 * 8 + 8
     assert C.sizeof(_lib.FrsResultSizes) == 7 * 8 + 2 * 4
     assert C.sizeof(_lib.FrsResult) == 7 * 8
 

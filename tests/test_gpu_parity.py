@@ -287,6 +287,14 @@ def test_compact_interval_encodings_equal_the_full_arrays(name, golden_set, eng)
     assert h_full - eng.stats()["h2d_upload"] == saved
     for k in want.arrays:
         assert np.array_equal(want.arrays[k], got.arrays[k]), (name, k)
+    n_copies = eng.stats()["h2d_copies"]
+    assert n_copies >= 20  # separately allocated arrays: one copy each
+    # the same batch in ONE pinned arena laid out in the library's upload order: a handful of large copies
+    arena = pack_tints(tints).pin()
+    got = eng.segment_batch(arena, gprm)
+    assert eng.stats()["h2d_copies"] <= 3, eng.stats()
+    for k in want.arrays:
+        assert np.array_equal(want.arrays[k], got.arrays[k]), (name, k)
     # an interval whose query end is NOT qs + CIGAR keeps its array
     odd = pack_tints(tints)
     odd.arrays["riv_qe"][0] += 1
@@ -294,7 +302,7 @@ def test_compact_interval_encodings_equal_the_full_arrays(name, golden_set, eng)
 
 
 def test_pipelined_submit_wait_fetch_equals_the_synchronous_calls(golden_set):
-    """frs_submit / frs_wait / frs_fetch: up to four batches in flight in ONE context (the copies of one overlap the
+    """frs_submit / frs_wait / frs_fetch: up to six batches in flight in ONE context (the copies of one overlap the
     kernels of the other); results must be those of upload + run + download, in any interleaving."""
     from freddie_b200 import _lib
     from freddie_b200.engine import Engine
@@ -324,13 +332,18 @@ def test_pipelined_submit_wait_fetch_equals_the_synchronous_calls(golden_set):
             for a in want[k].arrays:
                 assert np.array_equal(want[k].arrays[a], got[k].arrays[a]), (nme, a)
             assert want[k].sizes == got[k].sizes
-        # four batches may be in flight; a fifth submit without a fetch is refused; so is a fetch of a free ticket
+        # six batches may be in flight; a seventh submit without a fetch is refused; so is a fetch of a free ticket
         t0 = e.submit(batches[0], prms[0])
         t1 = e.submit(batches[1], prms[1])
         t2 = e.submit(batches[2], prms[2])
         t3 = e.submit(batches[3], prms[3])
+        t4 = e.submit(batches[4], prms[4])
+        t5 = e.submit(batches[0], prms[0])
         with pytest.raises(_lib.FrsError, match="in flight"):
-            e.submit(batches[4], prms[4])
+            e.submit(batches[1], prms[1])
+        for tk, kb in ((t4, 4), (t5, 0)):
+            rk = e.fetch(tk, e.new_result(e.wait(tk), batches[kb]))
+            assert all(np.array_equal(rk.arrays[a], want[kb].arrays[a]) for a in rk.arrays)
         s0, s1, s2 = e.wait(t0), e.wait(t1), e.wait(t2)
         r3 = e.fetch(t3, e.new_result(e.wait(t3), batches[3]))
         assert all(np.array_equal(r3.arrays[a], want[3].arrays[a]) for a in r3.arrays)
