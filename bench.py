@@ -216,6 +216,96 @@ def reference_rate(tints, cores: int, seconds: float):
         run.close()
 
 
+def _ref_cluster_one(path):
+    """read_segment + preprocess_ilp + partition_reads of the UNMODIFIED reference on one SEGMENT file
+    (freddie_cluster.py:119-172, :277-328, :198-274) -> (reads, digest of the canonical serialisation)."""
+    import contextlib
+    import hashlib
+    import io
+    from oracle import build_ref
+    from oracle import cluster_prep_oracle as cpo
+    fc = build_ref.reference_cluster_module()
+    tint = list(fc.read_segment(path).values())[0]
+    fc.preprocess_ilp(tint, dict(recycle_model="constant"))
+    with contextlib.redirect_stdout(io.StringIO()):  # partition_reads prints every piece
+        fc.partition_reads(tint, 1000)
+    d = tint["ilp_data"]
+    U = len(tint["read_reps"])
+    gaps = [tint["reads"][tint["read_reps"][i][0]]["gaps"] for i in range(U)]
+    cat = [tint["reads"][tint["read_reps"][i][0]]["poly_tail_category"] for i in range(U)]
+    s = cpo.canonical(d["I"], d["C"], d["FL"], cat, d["garbage_cost"], gaps, tint["partitions"])
+    return len(tint["reads"]), hashlib.sha256(s.encode()).hexdigest()
+
+
+def cluster_prep_scope(device, batch, res, cores):
+    """read-rep merge + preprocess_ilp + partition_reads of every tint of the workload in ONE
+    frs_cprep_run (host arrays in, host arrays out), beside the unmodified reference functions on a bounded
+    sample of the same tints (all host cores, one tint per task) whose results are compared digest by digest."""
+    import hashlib
+    import shutil
+    import tempfile
+    from freddie_b200.cluster_prep import ClusterPrep, batch_from_segment
+    from freddie_b200.engine import format_tint
+    cb = batch_from_segment(batch.arrays, res.arrays)
+    ctx = ClusterPrep(device)
+    out = None
+    for _ in range(2):
+        out = ctx.run(cb, 1000)
+    K = 5
+    t0 = time.perf_counter()
+    for _ in range(K):
+        out = ctx.run(cb, 1000)
+    dt = (time.perf_counter() - t0) / K
+    in_bytes = int(sum(np.asarray(v).nbytes for v in out.batch.values()))
+    out_bytes = int(sum(v.nbytes for v in out.a.values()))
+    obj = dict(value=batch.n_reads / dt, unit="reads/s", seconds=round(dt, 5),
+               scope="host arrays of the segment stage in -> frs_cprep_run + frs_cprep_fetch -> host arrays out (copies and "
+                     "host bookkeeping inside the wall clock), maximum_ilp_size 1000",
+               device_ms={k: round(v, 4) for k, v in out.timings_ms.items()}, launches=out.sizes["launches"],
+               h2d_bytes=in_bytes, d2h_bytes=out_bytes,
+               counts={k: out.sizes[k] for k in ("n_reps", "n_structs", "n_parts", "n_incomp", "edges_before", "edges_after", "prune_rounds")},
+               reads=batch.n_reads, tints=batch.n_tints)
+    from oracle import build_ref
+    if build_ref.cluster_available():
+        from multiprocessing import Pool
+        from oracle import cluster_prep_oracle as cpo
+        # bounded sample: every k-th tint by size, cost ~ reads^2 (the reference's pair loop is pure Python)
+        tro = np.asarray(batch.arrays["tint_read_off"])
+        n = np.diff(tro)
+        order = np.argsort(n, kind="stable")
+        budget = float(os.environ.get("FRS_CLUSTER_PAIRS", 1.2e6)) * cores
+        stride = max(1, int(np.ceil(float((n.astype(np.float64) ** 2).sum()) / budget)))
+        pick = [int(t) for t in order[stride // 2::stride] if n[t] > 0]
+        base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+        work = tempfile.mkdtemp(prefix="frs_refc_", dir=base)
+        try:
+            paths = []
+            for t in pick:
+                paths.append(os.path.join(work, "segment_%d.tsv" % t))
+                with open(paths[-1], "w") as fh:
+                    fh.write(format_tint(batch, res, t))
+            t0 = time.perf_counter()
+            with Pool(cores) as p:
+                ref = p.map(_ref_cluster_one, paths, chunksize=1)
+            rdt = time.perf_counter() - t0
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
+        same = 0
+        for t, (_, dg) in zip(pick, ref):
+            r = out.tint(t, "constant")
+            mine = hashlib.sha256(cpo.canonical(r["I"], r["C"], r["FL"], r["cat"], r["garbage_cost"], r["gaps"],
+                                                r["partitions"]).encode()).hexdigest()
+            same += mine == dg
+        rn = int(sum(x[0] for x in ref))
+        obj["cpu_baseline"] = dict(value=rn / rdt, unit="reads/s", cores=cores, kind="reference",
+                                   sample="unmodified read_segment + preprocess_ilp + partition_reads (oracle/_ref/freddie_cluster.bin), "
+                                          "one tint per task on %d processes, every %d-th tint by size: %d tints, %d reads, %.2f s"
+                                          % (cores, stride, len(pick), rn, rdt),
+                                   parity="%d of %d sampled tints equal the CUDA path's canonical digest" % (same, len(pick)))
+    ctx.close()
+    return obj
+
+
 def config_dict(args):
     """The same object from both arms (the driver compares them)."""
     return dict(workload=WORKLOADS[args.workload], scale=args.scale, params="defaults (sd=5 tp=0.9 vf=3 mps=50 lo=3)",
@@ -571,6 +661,11 @@ def run_cuda_arm(args):
     )
     if world == 1 and not args.no_cli and tints_for_cpu is not None:
         line["cli"] = cli_scope(cores)
+    if world == 1 and tints_for_cpu is not None and len(batches) == 1 and not os.environ.get("FRS_NO_CLUSTER_PREP"):
+        try:  # the next row of the scope table; never costs the bench line
+            line["cluster_prep"] = cluster_prep_scope(local_rank, batches[0], res_lazy[0], cores)
+        except Exception as e:  # noqa: BLE001
+            line["cluster_prep"] = dict(error=repr(e)[:300])
     if world == 1 and not args.no_cpu_baseline and tints_for_cpu is not None:
         from oracle import build_ref
         r, c, sample = oracle_rate(tints_for_cpu, cores, int(os.environ.get("FRS_CPU_SAMPLE_READS", 300 * cores * 8)))

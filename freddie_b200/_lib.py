@@ -63,6 +63,28 @@ class FrsResult(C.Structure):
     _fields_ = [(n, _p) for n in RESULT_ARRAYS]
 
 
+CLUSTER_BATCH_ARRAYS = ["tint_read_off", "tint_seg_n", "tint_digit_off", "read_row", "digits", "read_head", "read_gap_off", "gap_rec"]
+CLUSTER_RESULT_ARRAYS = [
+    ("tint_rep_off", "i4"), ("read_rep", "i4"), ("rep_first_read", "i4"), ("rep_count", "i4"), ("rep_fl", "i4"), ("rep_cat", "u1"),
+    ("rep_gap", "i4"), ("tint_row_off", "i8"), ("I", "u1"), ("C", "u1"), ("tint_struct_off", "i4"), ("rep_struct", "i4"),
+    ("tint_part_off", "i4"), ("part_rid_off", "i4"), ("part_rids", "i4"), ("part_inc_off", "i8"), ("inc", "i4"), ("tint_edges", "i8"),
+]
+
+
+class FrsClusterBatch(C.Structure):
+    _fields_ = [("n_tints", C.c_int32), ("n_reads", C.c_int32)] + [(n, _p) for n in CLUSTER_BATCH_ARRAYS]
+
+
+class FrsClusterSizes(C.Structure):
+    _fields_ = [("n_reps", C.c_int64), ("n_structs", C.c_int64), ("n_parts", C.c_int64), ("n_incomp", C.c_int64),
+                ("n_row_bytes", C.c_int64), ("edges_before", C.c_int64), ("edges_after", C.c_int64),
+                ("prune_rounds", C.c_int32), ("launches", C.c_int32)]
+
+
+class FrsClusterResult(C.Structure):
+    _fields_ = [(n, _p) for n, _ in CLUSTER_RESULT_ARRAYS]
+
+
 class FrsError(RuntimeError):
     """Raised for every non-zero status of the library.  ``code`` is the FRS_ERR_* value."""
 
@@ -132,6 +154,16 @@ def load():
         lib.frs_packed_read.restype = C.c_int
         lib.frs_packed_write_segment.argtypes = [_p, C.POINTER(FrsResult), C.c_char_p, C.c_char_p, C.c_size_t]
         lib.frs_packed_write_segment.restype = C.c_int
+    lib.frs_cprep_create.argtypes = [C.c_int, C.POINTER(_p)]
+    lib.frs_cprep_destroy.argtypes = [_p]
+    lib.frs_cprep_destroy.restype = None
+    lib.frs_cprep_last_error.argtypes = [_p]
+    lib.frs_cprep_last_error.restype = C.c_char_p
+    lib.frs_cprep_run.argtypes = [_p, C.POINTER(FrsClusterBatch), C.c_int, C.POINTER(FrsClusterSizes)]
+    lib.frs_cprep_fetch.argtypes = [_p, C.POINTER(FrsClusterResult)]
+    lib.frs_cprep_timings.argtypes = [_p, C.POINTER(C.c_float), C.c_int]
+    for fn in ("frs_cprep_create", "frs_cprep_run", "frs_cprep_fetch", "frs_cprep_timings"):
+        getattr(lib, fn).restype = C.c_int
     if lib.frs_abi_version() != 2:
         raise FrsError(-101, "ABI version mismatch")
     _lib = lib
@@ -145,4 +177,5 @@ EXPORTED = [
     "frs_get_intermediate", "frs_set_profiling",
     "frs_get_timings", "frs_last_launch_count", "frs_set_option", "frs_get_stats", "frs_parse_tints", "frs_parsed_batch", "frs_parsed_free",
     "frs_format_tints", "frs_packed_write", "frs_packed_read", "frs_packed_write_segment",
+    "frs_cprep_create", "frs_cprep_destroy", "frs_cprep_last_error", "frs_cprep_run", "frs_cprep_fetch", "frs_cprep_timings",
 ]

@@ -277,6 +277,77 @@ int frs_packed_read(const char* path, frs_parsed** out, char* err, size_t err_ca
  * re-parse segment_*.tsv (freddie_cluster.py:119-172); freddie_b200/packed.py reads it back. */
 int frs_packed_write_segment(const frs_parsed* p, const frs_result* res, const char* path, char* err, size_t err_cap);
 
+/* =========================================================================================================
+ * Next row of the scope table: the Gurobi-free front of freddie_cluster.py, on the arrays
+ * the segment stage produces (the FRSSEGM1 arrays = frs_result + the batch's read tables).  Replaces, per tint:
+ *   read_segment's read-rep merge          freddie_cluster.py:154-164  (key: digits with 2->0, internal gap
+ *                                           sizes and poly-tail lengths, sizes <= 10 as 0, in the file's order)
+ *   preprocess_ilp                         :277-328  (I, C, FL, poly-tail category, the added tail gap;
+ *                                           garbage_cost of the `constant` model = 3 x reads of the rep)
+ *   partition_reads                        :198-274  (structures (I row, FL, category) merged in first-seen
+ *                                           order, the O(U^2 M) pair test, synchronous pruning rounds of the
+ *                                           compatibility graph, connected components, even pieces of at most
+ *                                           maximum_ilp_size structures, incompatible rep pairs per piece)
+ * Everything quadratic runs in CUDA kernels on bit-packed rows (kernels_cluster.cuh); the list bookkeeping
+ * between them (stable grouping, pieces) is native host code inside the library.  No CPU fallback.
+ * ========================================================================================================= */
+typedef struct frs_cprep frs_cprep;
+
+typedef struct {
+  int32_t n_tints, n_reads;
+  const int32_t* tint_read_off;  /* [n_tints+1] reads of tint t */
+  const int32_t* tint_seg_n;     /* [n_tints]   M = segments of the tint (final positions - 1), >= 1 */
+  const int64_t* tint_digit_off; /* [n_tints+1] first byte of the tint's digit rows in `digits` (rows of M bytes) */
+  const int32_t* read_row;       /* [n_reads]   digit row of the read inside its tint (FRSSEGM1: read_rep - tint_rep_off) */
+  const uint8_t* digits;         /* ASCII '0' '1' '2', frs_result.digits */
+  const int32_t* read_head;      /* [8*n_reads] frs_result.read_head */
+  const int32_t* read_gap_off;   /* [n_reads+1] frs_result.read_gap_off */
+  const int32_t* gap_rec;        /* [3*n_gaps]  frs_result.gap_rec (seg a, seg b, size), any order inside a read */
+} frs_cluster_batch;
+
+typedef struct {
+  int64_t n_reps;       /* read reps over all tints (= entries of part_rids) */
+  int64_t n_structs;    /* distinct structures */
+  int64_t n_parts;      /* partitions */
+  int64_t n_incomp;     /* incompatible rep pairs over all partitions */
+  int64_t n_row_bytes;  /* sum over tints of reps x M (size of I and of C) */
+  int64_t edges_before, edges_after; /* compatibility graph edges over all tints, before / after pruning */
+  int32_t prune_rounds; /* pruning rounds executed (the last one removes nothing) */
+  int32_t launches;     /* kernel launches of this run */
+} frs_cluster_sizes;
+
+/* caller-allocated host arrays (sizes from frs_cluster_sizes); any pointer may be NULL (skipped) */
+typedef struct {
+  int32_t* tint_rep_off;    /* [n_tints+1] */
+  int32_t* read_rep;        /* [n_reads]   rep of the read, local to its tint, in first-seen order (read_segment) */
+  int32_t* rep_first_read;  /* [n_reps]    first read of the rep (local index): the read preprocess_ilp looks at */
+  int32_t* rep_count;       /* [n_reps]    reads of the rep (garbage_cost `constant` = 3 x this) */
+  int32_t* rep_fl;          /* [2*n_reps]  FL (:311) */
+  uint8_t* rep_cat;         /* [n_reps]    'N' 'S' 'E' (:297-308) */
+  int32_t* rep_gap;         /* [3*n_reps]  for cat != 'N': key (a, b) and value of the gap preprocess_ilp adds (:302,:306) */
+  int64_t* tint_row_off;    /* [n_tints+1] first byte of the tint's rows in I / C (rows of M bytes, rep order) */
+  uint8_t* I;               /* [n_row_bytes] 0/1 (:289-291) */
+  uint8_t* C;               /* [n_row_bytes] 0/1 (:312-316) */
+  int32_t* tint_struct_off; /* [n_tints+1] */
+  int32_t* rep_struct;      /* [n_reps]    structure of the rep, local to its tint, first-seen order (:207-218) */
+  int32_t* tint_part_off;   /* [n_tints+1] */
+  int32_t* part_rid_off;    /* [n_parts+1] into part_rids */
+  int32_t* part_rids;       /* [n_reps]    rep ids (local to the tint) of every partition (:263-265) */
+  int64_t* part_inc_off;    /* [n_parts+1] into inc (pairs) */
+  int32_t* inc;             /* [2*n_incomp] (rid_1, rid_2) in the reference's order (:266-273) */
+  int64_t* tint_edges;      /* [2*n_tints] edges before / after pruning per tint */
+} frs_cluster_result;
+
+int frs_cprep_create(int device, frs_cprep** out);
+void frs_cprep_destroy(frs_cprep* c);
+const char* frs_cprep_last_error(frs_cprep* c);
+/* copies the batch in and runs every step; the results stay on the device / in the object until the next run */
+int frs_cprep_run(frs_cprep* c, const frs_cluster_batch* batch, int maximum_ilp_size, frs_cluster_sizes* sizes);
+int frs_cprep_fetch(frs_cprep* c, const frs_cluster_result* out);
+/* device milliseconds of the last run: [0] dedupe + preprocess, [1] pair test, [2] pruning, [3] components,
+ * [4] incompatible pairs; returns the number of entries */
+int frs_cprep_timings(frs_cprep* c, float* ms, int n);
+
 #ifdef __cplusplus
 }
 #endif

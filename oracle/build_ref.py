@@ -26,6 +26,10 @@ REF_SRC = "/root/reference/py/freddie_segment.py"
 REF_DIR = os.path.join(HERE, "_ref")
 REF_PYC = os.path.join(REF_DIR, "freddie_segment.bin")  # CPython bytecode (runs by its magic number; *.pyc does not travel)
 REF_META = os.path.join(REF_DIR, "MANIFEST.json")
+# the cluster stage's Gurobi-free front: read_segment / preprocess_ilp / partition_reads are
+# called as functions of the compiled module (gurobipy is stubbed when absent: they never touch it)
+REF_CLUSTER_SRC = "/root/reference/py/freddie_cluster.py"
+REF_CLUSTER_PYC = os.path.join(REF_DIR, "freddie_cluster.bin")
 
 
 def build_ref(quiet: bool = True) -> bool:
@@ -37,9 +41,19 @@ def build_ref(quiet: bool = True) -> bool:
                            invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
         with open(REF_SRC, "rb") as fh:
             sha = hashlib.sha256(fh.read()).hexdigest()
+        meta = dict(source=REF_SRC, sha256=sha, python="%d.%d.%d" % sys.version_info[:3],
+                    artefact="freddie_segment.bin (py_compile of the unmodified source, optimize=0)")
+        if os.path.exists(REF_CLUSTER_SRC):
+            import warnings
+            with warnings.catch_warnings():  # the source has '\d' in plain strings (SyntaxWarning on 3.12)
+                warnings.simplefilter("ignore")
+                py_compile.compile(REF_CLUSTER_SRC, cfile=REF_CLUSTER_PYC, doraise=True, optimize=0,
+                                   invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+            with open(REF_CLUSTER_SRC, "rb") as fh:
+                meta["cluster"] = dict(source=REF_CLUSTER_SRC, sha256=hashlib.sha256(fh.read()).hexdigest(),
+                                       artefact="freddie_cluster.bin")
         with open(REF_META, "w") as fh:
-            json.dump(dict(source=REF_SRC, sha256=sha, python="%d.%d.%d" % sys.version_info[:3],
-                           artefact="freddie_segment.bin (py_compile of the unmodified source, optimize=0)"), fh)
+            json.dump(meta, fh)
         if not quiet:
             print("oracle/_ref: compiled %s (sha256 %s)" % (REF_SRC, sha[:16]))
     return available()
@@ -47,6 +61,38 @@ def build_ref(quiet: bool = True) -> bool:
 
 def available() -> bool:
     return os.path.exists(REF_PYC)
+
+
+def cluster_available() -> bool:
+    return os.path.exists(REF_CLUSTER_PYC)
+
+
+_cluster_mod = None
+
+
+def reference_cluster_module():
+    """The unmodified freddie_cluster module from its compiled artefact (functions only; main() is not run)."""
+    global _cluster_mod
+    if _cluster_mod is None:
+        import importlib.machinery
+        import importlib.util
+        import types
+        try:
+            import gurobipy  # noqa: F401
+        except Exception:
+            stub = types.ModuleType("gurobipy")  # `from gurobipy import Model, GRB, quicksum, LinExpr` (:13)
+            for attr in ("Model", "GRB", "quicksum", "LinExpr"):
+                setattr(stub, attr, None)
+            sys.modules["gurobipy"] = stub
+        import warnings
+        loader = importlib.machinery.SourcelessFileLoader("freddie_cluster_ref", REF_CLUSTER_PYC)
+        spec = importlib.util.spec_from_loader("freddie_cluster_ref", loader)
+        mod = importlib.util.module_from_spec(spec)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            loader.exec_module(mod)
+        _cluster_mod = mod
+    return _cluster_mod
 
 
 def command(split_dir: str, out_dir: str, threads: int, flags=()):
