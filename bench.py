@@ -405,6 +405,10 @@ def run_cuda_arm(args):
     os.environ["OMP_NUM_THREADS"] = str(max(1, cores // max(world, 1)))
     # NCCL logs (version banner, INFO lines the driver may ask for with NCCL_DEBUG) go to stderr: stdout is ONE line
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # host threads and pinned buffers of this rank next to its GPU (first-touch allocation follows the CPU affinity)
+    from freddie_b200 import affinity
+    all_cpus = os.sched_getaffinity(0)
+    numa = affinity.bind_to_gpu(local_rank)
     import torch
     if world > 1:
         import torch.distributed as dist
@@ -659,6 +663,8 @@ def run_cuda_arm(args):
         stages=stages,
         setup_seconds=round(t_gen, 1),
     )
+    line["numa"] = numa
+    os.sched_setaffinity(0, all_cpus)  # the CPU arms below use every host core
     if world == 1 and not args.no_cli and tints_for_cpu is not None:
         line["cli"] = cli_scope(cores)
     if world == 1 and tints_for_cpu is not None and len(batches) == 1 and not os.environ.get("FRS_NO_CLUSTER_PREP"):

@@ -788,7 +788,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 
       for (int e = tid; e < p2; e += THREADS) tab_g[e] = amb_s[e];
       for (int e = tid; e < c3; e += THREADS) tab_g[p2 + e] = out_s[e];
     }
-    dp_solve<false, (THREADS == 128 ? 16 : 32)>(n, cf, amb_s, out_s, A.lo, (int*)(dsm + L.G), (short*)(dsm + L.arg), (int*)(dsm + L.red),
+    dp_solve<false, (THREADS <= 256 ? 8 : 16)>(n, cf, amb_s, out_s, A.lo, (int*)(dsm + L.G), (short*)(dsm + L.arg), (int*)(dsm + L.red),
                    A.final_flag + qs, A.err, p);
   }
 }
@@ -807,21 +807,30 @@ struct DpWarpSmem {
   static constexpr int C3 = MAXN * (MAXN - 1) * (MAXN - 2) / 6;
   u32 tile[MAXN][32];
   uint2 yn[P2];
-  int ty[P2], tn[P2], amb[P2];
+  int2 cut[P2];  // x = ty, y = tn
+  int amb[P2];
   int out[C3];
   int G[MAXN * MAXN];
   short arg[MAXN * MAXN];
   int cf[MAXN];
+  int mid[MAXN];  // triple_mid_off(j, n) of the current subproblem
   u32 planes[32];
 };
 
 template <int MAXN>
 __global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWork* __restrict__ work_all, int cls) {
   extern __shared__ __align__(16) unsigned char dsm[];
+  __shared__ uchar2 s_ji[(MAXN - 1) * (MAXN - 2) / 2];  // (middle j, left i) of every lane slot of the triple phase
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (!dp_caps_ok(A.cnt, A.caps)) return;
   const int n_work = (int)A.cnt[CNT_PLAN + PLAN_WORK + cls];
   const DpWork* work = work_all + A.bases[cls];
+  for (int q = threadIdx.x; q < (MAXN - 1) * (MAXN - 2) / 2; q += DPW_WARPS * 32) {
+    int j = 1, rem = q;
+    while (rem >= j) { rem -= j; ++j; }
+    s_ji[q] = make_uchar2((unsigned char)j, (unsigned char)rem);
+  }
+  __syncthreads();
  for (;;) {  // persistent warps: items from the class's cursor until the list is empty
   int item = 0;
   if (lane == 0) item = atomicAdd(&A.cursor[8 + cls], 1);
@@ -848,10 +857,10 @@ __global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWo
     int j = i + 1 + rem;
     int a, b;
     length_cuts_t(S.cf[j] - S.cf[i] + 1, A.cut_tab, A.thr_table, A.thr_table_len, A.tp, a, b);
-    S.ty[e] = a;
-    S.tn[e] = b;
+    S.cut[e] = make_int2(a, b);
     S.amb[e] = 0;
   }
+  if (lane < n) S.mid[lane] = triple_mid_off(lane, n);
   for (int e = lane; e < c3; e += 32) S.out[e] = 0;
   const int npair_ij = (n - 2) * (n - 1) / 2;  // (j, i) with 1 <= j <= n-2, i < j
   for (int w = 0; w < words; ++w) {
@@ -872,11 +881,13 @@ __global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWo
     int e = 0;
     for (int i = 0; i < n - 1; ++i) {
       const u32 ri = S.tile[i][lane];
+#pragma unroll 4
       for (int j = i + 1; j < n; ++j, ++e) {
         const int cov = (int)(S.tile[j][lane] - ri);
-        const u32 by = __ballot_sync(0xffffffffu, valid && cov >= S.ty[e]);
-        const u32 bn = __ballot_sync(0xffffffffu, valid && cov <= S.tn[e]);
-        if (lane == (e & 31)) S.yn[e] = make_uint2(by, bn);
+        const int2 cut = S.cut[e];
+        const u32 by = __ballot_sync(0xffffffffu, valid && cov >= cut.x);
+        const u32 bn = __ballot_sync(0xffffffffu, valid && cov <= cut.y);
+        if (lane == 0) S.yn[e] = make_uint2(by, bn);
       }
     }
     __syncwarp();
@@ -888,12 +899,11 @@ __global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWo
     }
     // triples: lanes over (j, i), loop over k
     for (int q = lane; q < npair_ij; q += 32) {
-      int j = 1, rem = q;
-      while (rem >= j) { rem -= j; ++j; }
-      const int i = rem;
+      const uchar2 ji = s_ji[q];  // q = j (j - 1) / 2 + i, independent of n
+      const int j = ji.x, i = ji.y;
       const uint2 ij = S.yn[pair_index(i, j, n)];
       const uint2* jk = S.yn + pair_index(j, j + 1, n);
-      int* o = S.out + triple_mid_off(j, n) + i;
+      int* o = S.out + S.mid[j] + i;
       for (int k = j + 1; k < n; ++k, ++jk, o += j) {
         const uint2 v = *jk;
         const u32 m = (ij.x & v.y) | (ij.y & v.x);
@@ -907,7 +917,7 @@ __global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWo
     for (int e = lane; e < p2; e += 32) tab_g[e] = S.amb[e];
     for (int e = lane; e < c3; e += 32) tab_g[p2 + e] = S.out[e];
   }
-  dp_solve<true, (MAXN <= 8 ? 8 : 16)>(n, S.cf, S.amb, S.out, A.lo, S.G, S.arg, nullptr, A.final_flag + qs, A.err, p);
+  dp_solve<true, (MAXN <= 8 ? 4 : 2)>(n, S.cf, S.amb, S.out, A.lo, S.G, S.arg, nullptr, A.final_flag + qs, A.err, p);
   __syncwarp();
  }
 }
@@ -947,7 +957,7 @@ __global__ void __launch_bounds__(DPS_THREADS) k_dp_solve(DpArgs A, const int* _
       tab = stab;
     }
     __syncthreads();
-    dp_solve<false, 32>(n, cf, tab, tab + p2, A.lo, G, arg, red, A.final_flag + qs, A.err, p);
+    dp_solve<false, 4>(n, cf, tab, tab + p2, A.lo, G, arg, red, A.final_flag + qs, A.err, p);
   }
 }
 __host__ inline size_t dps_smem_bytes(int max_n, int stage_max_n) {

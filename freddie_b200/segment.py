@@ -297,6 +297,9 @@ def run_directory(split_dir: str, outdir: str, prm: SegmentParams, threads: int 
 
     def worker(dev, lane):
         try:
+            if n_gpus > 1:  # this lane's threads, parse teams and pinned buffers next to its GPU
+                from . import affinity
+                affinity.bind_to_gpu(dev)
             t_eng = time.perf_counter()
             # the CUDA context of the lane is created on a helper thread while the lane parses its first batch
             # (context creation costs as much as parsing ~100 k reads and needs nothing from the host side)
