@@ -502,8 +502,10 @@ struct DpArgs {
 };
 
 // shared-memory carve-up of k_dp for (M = largest n of the launch, wc, out table on chip?)
+#define DP_PASS_WORDS 64                       // read-rep words classified per pass (see k_dp)
+#define DP_LIVE_CAP (DP_PASS_WORDS * 32 + DPT_MAXW * 32 + 2)  // queue of live reps: a pass + the carry of the previous one + the two synthetic columns
 struct DpSmem {
-  int tile, ynm, cf, ty, tn, planes, nplanes, vmask, munit, cumu, amb, out, G, arg, red, total;
+  int tile, ynm, cf, ty, tn, planes, nplanes, vmask, munit, cumu, amb, out, G, arg, live, red, total;
 };
 __host__ __device__ inline DpSmem dp_smem_layout(int M, int wc, int out_on_chip) {
   DpSmem s;
@@ -522,8 +524,14 @@ __host__ __device__ inline DpSmem dp_smem_layout(int M, int wc, int out_on_chip)
   s.cumu = o; o += (M + 1) * 4;                    // triple-phase units: prefix of j * ceil((n-1-j)/DP_TRI_K)
   s.amb = o; o += out_on_chip ? p2 * 4 : 0;
   s.out = o; o += out_on_chip ? c3 * 4 : 0;
-  s.G = o; o += out_on_chip ? M * M * 4 : 0;
-  s.arg = o; o += out_on_chip ? M * M * 2 : 0;
+  // G and arg are written by the solver, after the last chunk: the queue of live reps shares their bytes
+  s.G = o;
+  s.live = o;
+  s.arg = o + (out_on_chip ? M * M * 4 : 0);
+  {
+    const int solver = out_on_chip ? M * M * 6 : 0, queue = DP_LIVE_CAP * 4;
+    o += solver > queue ? solver : queue;
+  }
   o = (o + 3) & ~3;
   s.red = o; o += 2 * DPS_MAX_WARPS * 4;
   s.total = (o + 15) & ~15;
@@ -631,7 +639,7 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 ? 3 : 1)) k_dp(DpArgs A, const DpWork* __restrict__ work_all,
                                                 int cls, int smem_bytes) {
   extern __shared__ __align__(16) unsigned char dsm[];
-  __shared__ int s_n_munit, s_item;
+  __shared__ int s_n_munit, s_item, s_nq, s_wfull, s_wdead;
   if (!dp_caps_ok(A.cnt, A.caps)) return;
   const int n_work = (int)A.cnt[CNT_PLAN + PLAN_WORK + cls];
   if (n_work == 0) return;
@@ -707,16 +715,33 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 
       for (int e = tid; e < c3; e += THREADS) out_s[e] = 0;
     }
     __syncthreads();
-    // first chunk's TMA can fly while the cuts are computed
-    auto issue = [&](int w0) {
-      int col0 = w0 * 32;
-      int cols = min(CW, Rp - col0);
-      u32 bytes = (u32)cols * 4u;
+    // cuts of every pair (the TMA copies of the first pass fly meanwhile)
+    // ---- Rep compaction.  For a read rep r let c = P[last][r] - P[first][r], the samples of the whole window
+    // [cf[0], cf[n-1]) it covers.  c == 0: every pair of the subproblem sees coverage 0; c == window: every pair
+    // (i, j) sees cf[j] - cf[i].  All reps of one of these two kinds have the same coverage row, so they are ONE
+    // synthetic column each, weighted with the sum of their weights (the zero column is "nay" everywhere for the
+    // usual thresholds and then adds nothing, but it is evaluated like any other: exact for every -tp).  Only
+    // the reps in between (an alignment boundary inside the window) need their own bit.  Passes of
+    // DP_PASS_WORDS words: TMA bulk copies stage the first and the last coverage row of the pass, the warps
+    // classify and queue the partial reps, and the chunk loop gathers the n rows for queued reps only
+    // (typically 40 % of the reps on the synthetic configs; all sums are integer, the order is free). ----
+    int* live = (int*)(dsm + L.live);  // queue: tint-local rep index; -1 / -2 = the synthetic full / zero coverage column
+    auto issue_rows = [&](int ws, int we) {  // first / last row of words [ws, we) -> tile rows 0 / 1 (as 2 x 2048 u32)
+      const int col0 = ws * 32;
+      const int cols = min(we * 32, Rp) - col0;
+      const u32 bytes = (u32)cols * 4u;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(bar, bytes * (u32)n);
-      for (int i = 0; i < n; ++i) tma_bulk_g2s(tile + (size_t)i * CW, Prow0 + (i64)i * Rp + col0, bytes, bar);
+      mbar_expect_tx(bar, bytes * 2u);
+      tma_bulk_g2s(tile, Prow0 + col0, bytes, bar);
+      tma_bulk_g2s(tile + DP_PASS_WORDS * 32, Prow0 + (i64)(n - 1) * Rp + col0, bytes, bar);
     };
-    if (tid == 0 && w_lo < w_hi) issue(w_lo);
+    const bool tma_rows = 2 * DP_PASS_WORDS * 32 <= n * CW;  // the two staged rows fit the tile (n >= 16 at wc = 4 ...)
+    if (tid == 0) {
+      s_nq = 0;
+      s_wfull = 0;
+      s_wdead = 0;
+      if (tma_rows && w_lo < w_hi) issue_rows(w_lo, min(w_hi, w_lo + DP_PASS_WORDS));
+    }
     for (int e = tid; e < p2; e += THREADS) {
       // decode pair e -> (i, j): rows are short, a linear walk is fine (done once per item)
       int i = 0, rem = e;
@@ -727,32 +752,42 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 
       ty[e] = a;
       tn[e] = b;
     }
+    const u32 win = (u32)(cf[n - 1] - cf[0]);  // samples of the window: coverage of a rep that spans it
+    int head = 0;                              // first queued rep not yet processed (CTA-uniform)
 
-    for (int w0 = w_lo; w0 < w_hi; w0 += wc) {
-      const int nw = min(wc, w_hi - w0);
-      // weight planes + valid-rep mask of the chunk's words
+    // one chunk: the queued reps live[head .. head + ncol)
+    auto run_chunk = [&](const int ncol) {
+      const int nw = (ncol + 31) >> 5;
+      // weight planes + valid mask of the chunk's words, gather of the n coverage rows
       for (int w = warp; w < nw; w += NW) {
-        int rep = (w0 + w) * 32 + lane;
-        int wt = (rep < R) ? A.rep_weight[r0 + rep] : 0;
-        int mx = warp_max_i(wt);
-        int np = 32 - __clz(mx);
+        const int c = w * 32 + lane;
+        int wt = 0;
+        if (c < ncol) {
+          const int rep = live[head + c];
+          wt = rep >= 0 ? A.rep_weight[r0 + rep] : rep == -1 ? s_wfull : s_wdead;
+        }
+        const int mx = warp_max_i(wt);
+        const int np = 32 - __clz(mx);
         for (int b = 0; b < np; ++b) {
-          u32 m = __ballot_sync(0xffffffffu, (wt >> b) & 1);
+          const u32 m = __ballot_sync(0xffffffffu, (wt >> b) & 1);
           if (lane == 0) planes[w * 32 + b] = m;
         }
-        u32 vm = __ballot_sync(0xffffffffu, rep < R);
+        const u32 vm = __ballot_sync(0xffffffffu, c < ncol);
         if (lane == 0) { nplanes[w] = np; vmask[w] = vm; }
       }
-      __syncthreads();  // cuts + planes visible; previous chunk's triple phase done
-      mbar_wait(bar, phase);
-      phase ^= 1;
-      // ---- mask phase.  Only the last word of a tint can hold lanes without a rep; every other chunk
-      // skips the masking ----
-      const bool tail_chunk = (w0 + nw == words) && (R & 31);
-      if (tail_chunk) dp_mask_phase<THREADS, true>(n, nw, wc, CW, tile, ty, tn, ynm, vmask, munit, s_n_munit);
+      for (int u = warp; u < n * nw; u += NW) {  // a warp fetches word w of row i: 32 queued reps
+        const int i = u / nw, c = (u - i * nw) * 32 + lane;
+        u32 v = 0;
+        if (c < ncol) {
+          const int rep = live[head + c];
+          v = rep >= 0 ? Prow0[(i64)i * Rp + rep] : rep == -1 ? (u32)(cf[i] - cf[0]) : 0u;
+        }
+        tile[(size_t)i * CW + c] = v;
+      }
+      __syncthreads();
+      if (ncol & 31) dp_mask_phase<THREADS, true>(n, nw, wc, CW, tile, ty, tn, ynm, vmask, munit, s_n_munit);
       else dp_mask_phase<THREADS, false>(n, nw, wc, CW, tile, ty, tn, ynm, vmask, munit, s_n_munit);
       __syncthreads();  // masks complete, tile free
-      if (tid == 0 && w0 + wc < w_hi) issue(w0 + wc);
       // ---- ins pass: ambiguous reps per pair ----
       for (int e = tid; e < p2; e += THREADS) {
         int acc = 0;
@@ -774,8 +809,74 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 
         if (w1) dp_triple_phase<THREADS, true>(n, nw, wc, ynm, planes, nplanes, cumu, out_on_chip, dst);
         else dp_triple_phase<THREADS, false>(n, nw, wc, ynm, planes, nplanes, cumu, out_on_chip, dst);
       }
-      __syncthreads();  // the next chunk rewrites the weight planes and the masks
+      __syncthreads();  // the next chunk rewrites the weight planes, the masks and the tile
+    };
+
+    for (int ws = w_lo; ws < w_hi; ws += DP_PASS_WORDS) {
+      const int we = min(w_hi, ws + DP_PASS_WORDS);
+      __syncthreads();  // cuts visible (first pass); queue carry in place, tile free (later passes)
+      if (tma_rows) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+      }
+      // ---- classify the reps of the pass ----
+      for (int w = ws + warp; w < we; w += NW) {
+        const int rep = w * 32 + lane;
+        u32 c = 0;
+        int wt = 0, wd = 0;
+        bool part = false;
+        if (rep < R) {
+          if (tma_rows) c = tile[DP_PASS_WORDS * 32 + rep - ws * 32] - tile[rep - ws * 32];
+          else c = Prow0[(i64)(n - 1) * Rp + rep] - Prow0[rep];
+          part = c != 0u && c != win;
+          if (!part) {
+            const int x = A.rep_weight[r0 + rep];
+            if (c == win) wt = x; else wd = x;
+          }
+        }
+        const u32 m = __ballot_sync(0xffffffffu, part);
+        int wsum = wt, dsum = wd;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+          dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+        }
+        int base = 0;
+        if (lane == 0) {
+          if (m) base = atomicAdd(&s_nq, __popc(m));
+          if (wsum) atomicAdd(&s_wfull, wsum);
+          if (dsum) atomicAdd(&s_wdead, dsum);
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (part) live[base + __popc(m & ((1u << lane) - 1u))] = rep;
+      }
+      __syncthreads();  // queue complete, staged rows free
+      if (tid == 0 && we >= w_hi) {  // last pass: the reps that span / miss the window, one column each
+        int q = s_nq;
+        if (s_wfull > 0) live[q++] = -1;
+        if (s_wdead > 0) live[q++] = -2;
+        s_nq = q;
+      }
+      __syncthreads();
+      const int nq = s_nq;
+      const bool last = we >= w_hi;
+      while (nq - head >= CW || (last && nq - head > 0)) {
+        const int ncol = min(CW, nq - head);
+        run_chunk(ncol);
+        head += ncol;
+      }
+      if (!last) {  // carry the tail of the queue (< CW reps) to its front; the next pass's rows may fly now
+        if (tid == 0 && tma_rows) issue_rows(we, min(w_hi, we + DP_PASS_WORDS));
+        const int rest = nq - head;
+        int v = 0;
+        if (tid < rest) v = live[head + tid];
+        __syncthreads();
+        if (tid < rest) live[tid] = v;
+        if (tid == 0) s_nq = rest;
+        head = 0;
+      }
     }
+    __syncthreads();
 
     if (!out_on_chip) continue;  // class 5: tables are already in global memory
     if (!fused) {
@@ -815,6 +916,7 @@ struct DpWarpSmem {
   int cf[MAXN];
   int mid[MAXN];  // triple_mid_off(j, n) of the current subproblem
   u32 planes[32];
+  unsigned short queue[64];  // queued reps (tint-local index; 0xffff = the synthetic full-coverage rep)
 };
 
 template <int MAXN>
@@ -863,10 +965,18 @@ __global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWo
   if (lane < n) S.mid[lane] = triple_mid_off(lane, n);
   for (int e = lane; e < c3; e += 32) S.out[e] = 0;
   const int npair_ij = (n - 2) * (n - 1) / 2;  // (j, i) with 1 <= j <= n-2, i < j
-  for (int w = 0; w < words; ++w) {
-    const int rep = w * 32 + lane;
-    const bool valid = rep < R;
-    const int wt = valid ? A.rep_weight[r0 + rep] : 0;
+  // Rep compaction (see k_dp): the reps that miss the window [cf[0], cf[n-1]) and the reps that span it are one
+  // synthetic column each with the sum of their weights, only the reps in between are queued; a word of
+  // 32 QUEUED reps is processed whenever the queue holds one.
+  const u32 win = (u32)(S.cf[n - 1] - S.cf[0]);
+  const u32* Plast = Prow0 + (i64)(n - 1) * Rp;
+  int nq = 0, wfull = 0, wdead = 0;
+  // one compacted word: the queued reps queue[0 .. cnt)
+  auto process = [&](const int cnt) {
+    const bool valid = lane < cnt;
+    const int rep = valid ? (int)S.queue[lane] : 0;
+    const bool syn = valid && rep >= 0xfffe;  // 0xffff: spans the window, 0xfffe: misses it
+    const int wt = valid ? (syn ? (rep == 0xffff ? wfull : wdead) : A.rep_weight[r0 + rep]) : 0;
     const int np = 32 - __clz(warp_max_i(wt));
     const u32 vm = __ballot_sync(0xffffffffu, valid);
     __syncwarp();  // previous word's readers are done with tile / yn / planes
@@ -875,7 +985,9 @@ __global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWo
         u32 m = __ballot_sync(0xffffffffu, (wt >> b) & 1);
         if (lane == 0) S.planes[b] = m;
       }
-    for (int i = 0; i < n; ++i) S.tile[i][lane] = valid ? Prow0[(i64)i * Rp + rep] : 0u;
+    const int cf0 = S.cf[0];
+    for (int i = 0; i < n; ++i)
+      S.tile[i][lane] = !valid ? 0u : syn ? (rep == 0xffff ? (u32)(S.cf[i] - cf0) : 0u) : Prow0[(i64)i * Rp + rep];
     __syncwarp();
     // masks
     int e = 0;
@@ -910,6 +1022,58 @@ __global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWo
         if (m) *o += wpopc(m, S.planes, np);
       }
     }
+    __syncwarp();
+  };
+  // removes the first cnt entries of the queue
+  auto pop = [&](const int cnt) {
+    const int rest = nq - cnt;
+    const unsigned short v = lane < rest ? S.queue[cnt + lane] : (unsigned short)0;
+    __syncwarp();
+    if (lane < rest) S.queue[lane] = v;
+    nq = rest;
+    __syncwarp();
+  };
+  for (int w = 0; w < words; ++w) {
+    const int rep = w * 32 + lane;
+    int wt = 0, wd = 0;
+    bool part = false;
+    if (rep < R) {
+      const u32 c = Plast[rep] - Prow0[rep];
+      part = c != 0u && c != win;
+      if (!part) {
+        const int x = A.rep_weight[r0 + rep];
+        if (c == win) wt = x; else wd = x;
+      }
+    }
+    const u32 m = __ballot_sync(0xffffffffu, part);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      wt += __shfl_xor_sync(0xffffffffu, wt, o);
+      wd += __shfl_xor_sync(0xffffffffu, wd, o);
+    }
+    wfull += wt;
+    wdead += wd;
+    if (part) S.queue[nq + __popc(m & ((1u << lane) - 1u))] = (unsigned short)rep;
+    nq += __popc(m);
+    __syncwarp();
+    if (nq >= 32) {
+      process(32);
+      pop(32);
+    }
+  }
+  if (wfull > 0) {
+    if (lane == 0) S.queue[nq] = (unsigned short)0xffff;
+    ++nq;
+  }
+  if (wdead > 0) {
+    if (lane == 0) S.queue[nq] = (unsigned short)0xfffe;
+    ++nq;
+  }
+  __syncwarp();
+  while (nq > 0) {
+    const int cnt = min(32, nq);
+    process(cnt);
+    pop(cnt);
   }
   __syncwarp();
   if (A.keep_tables) {
