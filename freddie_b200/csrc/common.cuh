@@ -47,7 +47,8 @@ enum {
   CNT_CLIPW = 15,  // plane words of the soft clips (lazy sequence mode)
   CNT_PLAN = 16,   // PLAN_SLOTS slots of the subproblem plan (kernels_dp.cuh)
   CNT_ERR = 40,    // 4 ints: first device assert (code, item), poly tasks, long poly tasks
-  CNT_SLOTS = 48
+  CNT_BUCKET = 48, // DP work items per (class, cost bucket): DP_CLASSES x DP_BUCKETS slots (kernels_dp.cuh)
+  CNT_SLOTS = 96
 };
 struct Caps { i64 P, tab, work, split, dig, runs, gaps, clipw; };  // capacities in elements
 

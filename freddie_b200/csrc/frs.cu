@@ -786,6 +786,18 @@ static int enqueue_prep(frs_context* c, Slot& S, cudaStream_t st) {
   return 0;
 }
 
+// largest tint (in words of 32 read reps) whose small subproblems are solved by one warp each (k_dp_warp);
+// larger tints go to the CTA classes, where the warps of a CTA share the words of a chunk.  FRS_DP_WARP_WORDS:
+// development knob.
+static int dp_warp_words() {
+  static int v = -1;
+  if (v < 0) {
+    v = DP_WARP_MAX_WORDS;
+    if (const char* e = getenv("FRS_DP_WARP_WORDS")) v = std::max(1, std::min(2047, atoi(e)));
+  }
+  return v;
+}
+
 static int check_params(frs_context* c, const frs_params* prm) {
   // parse_args asserts (freddie_segment.py:104-109)
   if (!(prm->tp >= 0.5 && prm->tp <= 1.0)) return fail(c, FRS_ERR_ARG, "AssertionError: 1 >= threshold_rate >= 0.5");
@@ -876,8 +888,8 @@ static int enqueue_run(frs_context* c, Slot& S) {
   ENS(b_tint_cand_off, (size_t)(T + 1) * 4);
   ENS(b_cov_sz, (size_t)(T + 1) * 8);
   ENS(b_tint_cov_off, (size_t)(T + 1) * 8);
-  ENS(b_bases, 16 * 4);
-  ENS(b_cursor, 16 * 4);
+  ENS(b_bases, (16 + DP_CLASSES * DP_BUCKETS) * 4);
+  ENS(b_cursor, (16 + DP_CLASSES * DP_BUCKETS) * 4);
   ENS(b_P, cp.P * 4);
   ENS(b_dpfinal, KMAX);
   ENS(b_work, cp.work * 8);
@@ -1021,7 +1033,7 @@ static int enqueue_run(frs_context* c, Slot& S) {
   const int keep = c->opt_keep_tables;
   k_sub_build<<<g_cand, 256, 0, st>>>(d_K, c->b_fixed1.as<u8>(), c->b_cand_island.as<int>(),
                                       c->b_island_cand_off.as<int>(), d_island_tint, d_tint_rep_off,
-                                      S.b_tint_read_off.as<int>(), slab_words, keep,
+                                      S.b_tint_read_off.as<int>(), slab_words, dp_warp_words(), keep,
                                       c->b_sub_start.as<int>(), c->b_sub_n.as<int>(), c->b_sub_tint.as<int>(),
                                       c->b_sub_info.as<int>(), c->b_sub_slabs.as<int>(), c->b_sub_tab_off.as<i64>(),
                                       d_cnt + CNT_PLAN, d_err);

@@ -155,14 +155,26 @@ __global__ void k_fixed_b(const i64* __restrict__ n_cand_p, const int* __restric
 #define PLAN_NSUB 16    // number of subproblems
 #define PLAN_TAB 17     // int32 elements of the global DP tables
 #define PLAN_SLOTS 20
+// Work items of a class are listed heaviest first: every subproblem falls into one of DP_BUCKETS cost buckets
+// (log2 of n^2 x words of an item), a class's list is the concatenation of its buckets in descending order, and
+// the persistent CTAs / warps take items from the front.  Without it the order is arbitrary and a heavy item
+// taken last is the tail of the launch (measured on config 2: 14 % of the warp slots busy on average).
+#define DP_BUCKETS 8
+__host__ __device__ inline int dp_bucket_of(int n, int item_words) {
+  const long long cost = (long long)n * n * (item_words > 0 ? item_words : 1);
+  int lg = 0;
+  while ((cost >> (lg + 1)) > 0) ++lg;
+  const int b = (lg - 6) / 2;
+  return b < 0 ? 0 : b >= DP_BUCKETS ? DP_BUCKETS - 1 : b;
+}
 
 struct DpWork { int sub; int slab; };
 
 // classes: 0 / 1 = one WARP per subproblem (n <= 8 / 16, tint of at most 512 reps);
 //          2 / 3 / 4 = one CTA of 128 / 256 / 512 threads per (subproblem, slab), n <= 16 / 32 / 56;
 //          5 = n > 56 (only reachable with a large -mps): out table in global memory, always split.
-__host__ __device__ inline int dp_class_of(int n, int words, int fused) {
-  if (fused && n <= 16 && words <= DP_WARP_MAX_WORDS) return n <= 8 ? 0 : 1;
+__host__ __device__ inline int dp_class_of(int n, int words, int fused, int warp_max_words) {
+  if (fused && n <= 16 && words <= warp_max_words) return n <= 8 ? 0 : 1;
   return n <= 16 ? 2 : n <= 32 ? 3 : n <= DP_SMEM_MAX_N ? 4 : 5;
 }
 
@@ -199,7 +211,7 @@ __device__ __forceinline__ int warp_max_i(int v) {
 __global__ void k_sub_build(const i64* __restrict__ n_cand_p, const u8* __restrict__ fixed, const int* __restrict__ cand_island,
                             const int* __restrict__ island_cand_off, const int* __restrict__ island_tint,
                             const int* __restrict__ tint_rep_off, const int* __restrict__ tint_read_off, int slab_cap,
-                            int keep_tables, int* __restrict__ sub_start, int* __restrict__ sub_n,
+                            int warp_max_words, int keep_tables, int* __restrict__ sub_start, int* __restrict__ sub_n,
                             int* __restrict__ sub_tint, int* __restrict__ sub_info, int* __restrict__ sub_slabs,
                             i64* __restrict__ sub_tab_off, i64* __restrict__ plan, int* __restrict__ err) {
   const int n_cand = (int)*n_cand_p;
@@ -207,7 +219,7 @@ __global__ void k_sub_build(const i64* __restrict__ n_cand_p, const u8* __restri
   // CTA-uniform trip count: every lane of a warp reaches the ballots
   for (int q0 = blockIdx.x * blockDim.x; q0 < n_cand; q0 += gridDim.x * blockDim.x) {
     const int q = q0 + threadIdx.x;
-    int cls = -1, slabs = 0, n = 0, split = 0, info = 0, t = 0;
+    int cls = -1, slabs = 0, n = 0, split = 0, info = 0, t = 0, bucket = 0;
     long long t3 = 0, rc = 0, sz = 0;
     bool has = false;
     if (q < n_cand && fixed[q]) {
@@ -224,12 +236,13 @@ __global__ void k_sub_build(const i64* __restrict__ n_cand_p, const u8* __restri
           const int words = (R + 31) >> 5;
           const int sw = dp_slab_words(n, words, slab_cap);
           const int fused = (n <= DP_SMEM_MAX_N && words <= sw) ? 1 : 0;
-          cls = dp_class_of(n, words, fused);
+          cls = dp_class_of(n, words, fused, warp_max_words);
           slabs = fused ? 1 : (words + sw - 1) / sw;
+          bucket = dp_bucket_of(n, fused ? words : sw);
           split = !fused;
           t3 = (long long)n * (n - 1) * (n - 2) / 6;
           rc = t3 * R;
-          info = cls | (fused << 8) | (sw << 16);
+          info = cls | (fused << 8) | (bucket << 12) | (sw << 16);
           sz = (fused && !keep_tables) ? 0 : (long long)n * (n - 1) / 2 + t3;
           // |score| <= (segments of a path) x (reads of the tint): must stay inside the 30-bit range of FRS_NEG_INF
           if ((long long)n * (tint_read_off[t + 1] - tint_read_off[t]) >= 0x3fffffffLL) dev_fail(err, DEVERR_SCORE_RANGE, t);
@@ -249,6 +262,12 @@ __global__ void k_sub_build(const i64* __restrict__ n_cand_p, const u8* __restri
       sub_info[p] = info;
       sub_slabs[p] = slabs;
       sub_tab_off[p] = sz ? (i64)atomicAdd((unsigned long long*)&plan[PLAN_TAB], (unsigned long long)sz) : 0;
+      // items per (class, bucket), aggregated over the lanes that share the key
+      const int key = cls * DP_BUCKETS + bucket;
+      const unsigned grp = __match_any_sync(m, key);
+      const int tot = __reduce_add_sync(grp, slabs);
+      if (lane == __ffs(grp) - 1)
+        atomicAdd((unsigned long long*)&plan[CNT_BUCKET - CNT_PLAN + key], (unsigned long long)tot);
     }
     // warp-aggregated statistics
 #pragma unroll
@@ -274,16 +293,20 @@ __global__ void k_sub_build(const i64* __restrict__ n_cand_p, const u8* __restri
 // One thread, after k_sub_build and the coverage-offset scan: first work item of every class, totals, and
 // the cursors of the work lists (fill cursors [0..DP_CLASSES], work-stealing cursors [8..8+DP_CLASSES]).
 __global__ void k_plan_finish(i64* __restrict__ cnt, const i64* __restrict__ tint_cov_off, int n_tints,
-                              int* __restrict__ bases /* [DP_CLASSES] */, int* __restrict__ cursor /* [16] */) {
+                              int* __restrict__ bases /* [16 + DP_CLASSES * DP_BUCKETS]: classes, then (class, bucket) */,
+                              int* __restrict__ cursor /* [16 + DP_CLASSES * DP_BUCKETS] */) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     i64 acc = 0;
     for (int k = 0; k < DP_CLASSES; ++k) {
       bases[k] = (int)(acc < 0x7fffffffLL ? acc : 0x7fffffffLL);
-      acc += cnt[CNT_PLAN + PLAN_WORK + k];
+      for (int b = DP_BUCKETS - 1; b >= 0; --b) {  // heaviest bucket first
+        bases[16 + k * DP_BUCKETS + b] = (int)(acc < 0x7fffffffLL ? acc : 0x7fffffffLL);
+        acc += cnt[CNT_BUCKET + k * DP_BUCKETS + b];
+      }
     }
     cnt[CNT_NWORK] = acc;
     cnt[CNT_COV] = tint_cov_off[n_tints];
-    for (int k = 0; k < 16; ++k) cursor[k] = 0;
+    for (int k = 0; k < 16 + DP_CLASSES * DP_BUCKETS; ++k) cursor[k] = 0;
   }
 }
 
@@ -303,7 +326,8 @@ __global__ void k_sub_fill(const i64* __restrict__ cnt, Caps caps, const int* __
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_sub; p += gridDim.x * blockDim.x) {
     const int info = sub_info[p];
     const int cls = info & 0xff, slabs = sub_slabs[p];
-    int off = bases[cls] + atomicAdd(&cursor[cls], slabs);
+    const int key = 16 + cls * DP_BUCKETS + ((info >> 12) & 7);
+    int off = bases[key] + atomicAdd(&cursor[key], slabs);
     for (int s = 0; s < slabs; ++s) work[off + s] = DpWork{p, s};
     if (!((info >> 8) & 1)) split_list[atomicAdd(&cursor[DP_CLASSES], 1)] = p;
   }
@@ -502,10 +526,18 @@ struct DpArgs {
 };
 
 // shared-memory carve-up of k_dp for (M = largest n of the launch, wc, out table on chip?)
+// yea / nay bits of the two synthetic columns for a pair of span `d` samples with cuts (ty, tn): a rep that covers
+// the whole window has coverage d on the pair, a rep that misses it has 0
+__device__ __forceinline__ u8 dp_pair_flags(int d, int ty, int tn) {
+  return (u8)((d >= ty ? 1 : 0) | (d <= tn ? 2 : 0) | (0 >= ty ? 4 : 0) | (0 <= tn ? 8 : 0));
+}
+// bit 0 / bit 2: the (spanning / missing) column is in out(i,j,k) = (yea_ij & nay_jk) | (nay_ij & yea_jk)
+__device__ __forceinline__ u32 dp_flag_cross(u32 fij, u32 fjk) { return ((fij & (fjk >> 1)) | ((fij >> 1) & fjk)) & 5u; }
+
 #define DP_PASS_WORDS 64                       // read-rep words classified per pass (see k_dp)
-#define DP_LIVE_CAP (DP_PASS_WORDS * 32 + DPT_MAXW * 32 + 2)  // queue of live reps: a pass + the carry of the previous one + the two synthetic columns
+#define DP_LIVE_CAP (DP_PASS_WORDS * 32 + DPT_MAXW * 32)  // queue of live reps: a pass + the carry of the previous one
 struct DpSmem {
-  int tile, ynm, cf, ty, tn, planes, nplanes, vmask, munit, cumu, amb, out, G, arg, live, red, total;
+  int tile, ynm, cf, ty, tn, pf, planes, nplanes, vmask, munit, cumu, amb, out, G, arg, live, red, total;
 };
 __host__ __device__ inline DpSmem dp_smem_layout(int M, int wc, int out_on_chip) {
   DpSmem s;
@@ -517,6 +549,7 @@ __host__ __device__ inline DpSmem dp_smem_layout(int M, int wc, int out_on_chip)
   s.cf = o; o += M * 4;
   s.ty = o; o += p2 * 4;
   s.tn = o; o += p2 * 4;
+  s.pf = o; o += (p2 + 3) & ~3;  // dp_pair_flags of every pair
   s.planes = o; o += wc * 32 * 4;
   s.nplanes = o; o += wc * 4;
   s.vmask = o; o += wc * 4;
@@ -718,14 +751,15 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 
     // cuts of every pair (the TMA copies of the first pass fly meanwhile)
     // ---- Rep compaction.  For a read rep r let c = P[last][r] - P[first][r], the samples of the whole window
     // [cf[0], cf[n-1]) it covers.  c == 0: every pair of the subproblem sees coverage 0; c == window: every pair
-    // (i, j) sees cf[j] - cf[i].  All reps of one of these two kinds have the same coverage row, so they are ONE
-    // synthetic column each, weighted with the sum of their weights (the zero column is "nay" everywhere for the
-    // usual thresholds and then adds nothing, but it is evaluated like any other: exact for every -tp).  Only
-    // the reps in between (an alignment boundary inside the window) need their own bit.  Passes of
+    // (i, j) sees cf[j] - cf[i].  All reps of one of these two kinds have the same coverage row: two synthetic
+    // columns, weighted with the sums of their weights, whose yea / nay bits per pair follow from the cuts alone
+    // (dp_pair_flags) and whose contribution is added in closed form after the chunk loop (exact for every -tp).
+    // Only the reps in between (an alignment boundary inside the window) need their own bit.  Passes of
     // DP_PASS_WORDS words: TMA bulk copies stage the first and the last coverage row of the pass, the warps
     // classify and queue the partial reps, and the chunk loop gathers the n rows for queued reps only
     // (typically 40 % of the reps on the synthetic configs; all sums are integer, the order is free). ----
-    int* live = (int*)(dsm + L.live);  // queue: tint-local rep index; -1 / -2 = the synthetic full / zero coverage column
+    int* live = (int*)(dsm + L.live);  // queue of tint-local rep indices
+    u8* pf = dsm + L.pf;
     auto issue_rows = [&](int ws, int we) {  // first / last row of words [ws, we) -> tile rows 0 / 1 (as 2 x 2048 u32)
       const int col0 = ws * 32;
       const int cols = min(we * 32, Rp) - col0;
@@ -751,6 +785,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 
       length_cuts_t(cf[j] - cf[i] + 1, A.cut_tab, A.thr_table, A.thr_table_len, A.tp, a, b);
       ty[e] = a;
       tn[e] = b;
+      pf[e] = dp_pair_flags(cf[j] - cf[i], a, b);
     }
     const u32 win = (u32)(cf[n - 1] - cf[0]);  // samples of the window: coverage of a rep that spans it
     int head = 0;                              // first queued rep not yet processed (CTA-uniform)
@@ -763,8 +798,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 
         const int c = w * 32 + lane;
         int wt = 0;
         if (c < ncol) {
-          const int rep = live[head + c];
-          wt = rep >= 0 ? A.rep_weight[r0 + rep] : rep == -1 ? s_wfull : s_wdead;
+          wt = A.rep_weight[r0 + live[head + c]];
         }
         const int mx = warp_max_i(wt);
         const int np = 32 - __clz(mx);
@@ -778,10 +812,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 
       for (int u = warp; u < n * nw; u += NW) {  // a warp fetches word w of row i: 32 queued reps
         const int i = u / nw, c = (u - i * nw) * 32 + lane;
         u32 v = 0;
-        if (c < ncol) {
-          const int rep = live[head + c];
-          v = rep >= 0 ? Prow0[(i64)i * Rp + rep] : rep == -1 ? (u32)(cf[i] - cf[0]) : 0u;
-        }
+        if (c < ncol) v = Prow0[(i64)i * Rp + live[head + c]];
         tile[(size_t)i * CW + c] = v;
       }
       __syncthreads();
@@ -851,13 +882,6 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 
         if (part) live[base + __popc(m & ((1u << lane) - 1u))] = rep;
       }
       __syncthreads();  // queue complete, staged rows free
-      if (tid == 0 && we >= w_hi) {  // last pass: the reps that span / miss the window, one column each
-        int q = s_nq;
-        if (s_wfull > 0) live[q++] = -1;
-        if (s_wdead > 0) live[q++] = -2;
-        s_nq = q;
-      }
-      __syncthreads();
       const int nq = s_nq;
       const bool last = we >= w_hi;
       while (nq - head >= CW || (last && nq - head > 0)) {
@@ -877,6 +901,35 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 
       }
     }
     __syncthreads();
+    // ---- the two synthetic columns in closed form ----
+    if (s_wfull > 0 || s_wdead > 0) {
+      const int wf = s_wfull, wd = s_wdead;
+      for (int e = tid; e < p2; e += THREADS) {
+        const u32 f = pf[e];
+        const int v = ((f & 3u) ? 0 : wf) + ((f & 12u) ? 0 : wd);
+        if (v) {
+          if (out_on_chip) amb_s[e] += v;
+          else atomicAdd(&tab_g[e], v);
+        }
+      }
+      int* dst = out_on_chip ? out_s : (tab_g + p2);
+      for (int q = tid; q < (n - 1) * (n - 2) / 2; q += THREADS) {  // (j, i): q = j (j - 1) / 2 + i
+        int j = 1, i = q;
+        while (i >= j) { i -= j; ++j; }
+        const u32 fij = pf[pair_index(i, j, n)];
+        const u8* fjk = pf + pair_index(j, j + 1, n);
+        int o = triple_mid_off(j, n) + i;
+        for (int k = j + 1; k < n; ++k, ++fjk, o += j) {
+          const u32 m = dp_flag_cross(fij, *fjk);
+          if (m) {
+            const int v = ((m & 1u) ? wf : 0) + ((m & 4u) ? wd : 0);
+            if (out_on_chip) dst[o] += v;
+            else atomicAdd(&dst[o], v);
+          }
+        }
+      }
+      __syncthreads();
+    }
 
     if (!out_on_chip) continue;  // class 5: tables are already in global memory
     if (!fused) {
@@ -916,7 +969,8 @@ struct DpWarpSmem {
   int cf[MAXN];
   int mid[MAXN];  // triple_mid_off(j, n) of the current subproblem
   u32 planes[32];
-  unsigned short queue[64];  // queued reps (tint-local index; 0xffff = the synthetic full-coverage rep)
+  unsigned short queue[64];  // queued reps (tint-local index)
+  u8 pf[(P2 + 3) & ~3];      // per pair: bit 0 / 1 = yea / nay of a rep that spans the window, bit 2 / 3 = of one that misses it
 };
 
 template <int MAXN>
@@ -961,12 +1015,13 @@ __global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWo
     length_cuts_t(S.cf[j] - S.cf[i] + 1, A.cut_tab, A.thr_table, A.thr_table_len, A.tp, a, b);
     S.cut[e] = make_int2(a, b);
     S.amb[e] = 0;
+    S.pf[e] = dp_pair_flags(S.cf[j] - S.cf[i], a, b);
   }
   if (lane < n) S.mid[lane] = triple_mid_off(lane, n);
   for (int e = lane; e < c3; e += 32) S.out[e] = 0;
   const int npair_ij = (n - 2) * (n - 1) / 2;  // (j, i) with 1 <= j <= n-2, i < j
-  // Rep compaction (see k_dp): the reps that miss the window [cf[0], cf[n-1]) and the reps that span it are one
-  // synthetic column each with the sum of their weights, only the reps in between are queued; a word of
+  // Rep compaction (see k_dp): the reps that miss the window [cf[0], cf[n-1]) and the reps that span it are two
+  // synthetic columns (added in closed form after the loop), only the reps in between are queued; a word of
   // 32 QUEUED reps is processed whenever the queue holds one.
   const u32 win = (u32)(S.cf[n - 1] - S.cf[0]);
   const u32* Plast = Prow0 + (i64)(n - 1) * Rp;
@@ -975,8 +1030,7 @@ __global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWo
   auto process = [&](const int cnt) {
     const bool valid = lane < cnt;
     const int rep = valid ? (int)S.queue[lane] : 0;
-    const bool syn = valid && rep >= 0xfffe;  // 0xffff: spans the window, 0xfffe: misses it
-    const int wt = valid ? (syn ? (rep == 0xffff ? wfull : wdead) : A.rep_weight[r0 + rep]) : 0;
+    const int wt = valid ? A.rep_weight[r0 + rep] : 0;
     const int np = 32 - __clz(warp_max_i(wt));
     const u32 vm = __ballot_sync(0xffffffffu, valid);
     __syncwarp();  // previous word's readers are done with tile / yn / planes
@@ -985,9 +1039,7 @@ __global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWo
         u32 m = __ballot_sync(0xffffffffu, (wt >> b) & 1);
         if (lane == 0) S.planes[b] = m;
       }
-    const int cf0 = S.cf[0];
-    for (int i = 0; i < n; ++i)
-      S.tile[i][lane] = !valid ? 0u : syn ? (rep == 0xffff ? (u32)(S.cf[i] - cf0) : 0u) : Prow0[(i64)i * Rp + rep];
+    for (int i = 0; i < n; ++i) S.tile[i][lane] = valid ? Prow0[(i64)i * Rp + rep] : 0u;
     __syncwarp();
     // masks
     int e = 0;
@@ -1061,19 +1113,29 @@ __global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWo
       pop(32);
     }
   }
-  if (wfull > 0) {
-    if (lane == 0) S.queue[nq] = (unsigned short)0xffff;
-    ++nq;
-  }
-  if (wdead > 0) {
-    if (lane == 0) S.queue[nq] = (unsigned short)0xfffe;
-    ++nq;
-  }
-  __syncwarp();
   while (nq > 0) {
     const int cnt = min(32, nq);
     process(cnt);
     pop(cnt);
+  }
+  // the two synthetic columns in closed form: their yea / nay bits per pair are the flags of S.pf
+  if (wfull > 0 || wdead > 0) {
+    __syncwarp();
+    for (int q = lane; q < p2; q += 32) {
+      const u32 f = S.pf[q];
+      S.amb[q] += ((f & 3u) ? 0 : wfull) + ((f & 12u) ? 0 : wdead);
+    }
+    for (int q = lane; q < npair_ij; q += 32) {
+      const uchar2 ji = s_ji[q];
+      const int j = ji.x, i = ji.y;
+      const u32 fij = S.pf[pair_index(i, j, n)];
+      const u8* fjk = S.pf + pair_index(j, j + 1, n);
+      int* o = S.out + S.mid[j] + i;
+      for (int k = j + 1; k < n; ++k, ++fjk, o += j) {
+        const u32 m = dp_flag_cross(fij, *fjk);
+        if (m) *o += ((m & 1u) ? wfull : 0) + ((m & 4u) ? wdead : 0);
+      }
+    }
   }
   __syncwarp();
   if (A.keep_tables) {
