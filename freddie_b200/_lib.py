@@ -85,6 +85,23 @@ class FrsClusterResult(C.Structure):
     _fields_ = [(n, _p) for n, _ in CLUSTER_RESULT_ARRAYS]
 
 
+class FrsSplitBatch(C.Structure):
+    _fields_ = [("n_groups", C.c_int32), ("n_reads", C.c_int32), ("group_read_off", _p), ("read_iv_off", _p), ("iv_s", _p),
+                ("iv_e", _p), ("max_intervals", C.c_int32), ("max_reads", C.c_int32)]
+
+
+class FrsSplitSizes(C.Structure):
+    _fields_ = [("n_tints", C.c_int64), ("n_tint_ivs", C.c_int64), ("n_tint_rids", C.c_int64), ("n_simple", C.c_int64),
+                ("n_big", C.c_int32), ("launches", C.c_int32)]
+
+
+SPLIT_RESULT_ARRAYS = ["group_tint_off", "tint_iv_off", "tint_iv_s", "tint_iv_e", "tint_rid_off", "tint_rids"]
+
+
+class FrsSplitResult(C.Structure):
+    _fields_ = [(n, _p) for n in SPLIT_RESULT_ARRAYS]
+
+
 class FrsError(RuntimeError):
     """Raised for every non-zero status of the library.  ``code`` is the FRS_ERR_* value."""
 
@@ -164,6 +181,17 @@ def load():
     lib.frs_cprep_timings.argtypes = [_p, C.POINTER(C.c_float), C.c_int]
     for fn in ("frs_cprep_create", "frs_cprep_run", "frs_cprep_fetch", "frs_cprep_timings"):
         getattr(lib, fn).restype = C.c_int
+    lib.frs_split_create.argtypes = [C.c_int, C.POINTER(_p)]
+    lib.frs_split_destroy.argtypes = [_p]
+    lib.frs_split_destroy.restype = None
+    lib.frs_split_last_error.argtypes = [_p]
+    lib.frs_split_last_error.restype = C.c_char_p
+    lib.frs_split_run.argtypes = [_p, C.POINTER(FrsSplitBatch), C.POINTER(FrsSplitSizes)]
+    lib.frs_split_fetch.argtypes = [_p, C.POINTER(FrsSplitResult)]
+    lib.frs_split_last_ms.argtypes = [_p]
+    lib.frs_split_last_ms.restype = C.c_float
+    for fn in ("frs_split_create", "frs_split_run", "frs_split_fetch"):
+        getattr(lib, fn).restype = C.c_int
     if lib.frs_abi_version() != 2:
         raise FrsError(-101, "ABI version mismatch")
     _lib = lib
@@ -177,5 +205,6 @@ EXPORTED = [
     "frs_get_intermediate", "frs_set_profiling",
     "frs_get_timings", "frs_last_launch_count", "frs_set_option", "frs_get_stats", "frs_parse_tints", "frs_parsed_batch", "frs_parsed_free",
     "frs_format_tints", "frs_packed_write", "frs_packed_read", "frs_packed_write_segment",
+    "frs_split_create", "frs_split_destroy", "frs_split_last_error", "frs_split_run", "frs_split_fetch", "frs_split_last_ms",
     "frs_cprep_create", "frs_cprep_destroy", "frs_cprep_last_error", "frs_cprep_run", "frs_cprep_fetch", "frs_cprep_timings",
 ]

@@ -248,7 +248,7 @@ int frs_cprep_run(frs_cprep* c, const frs_cluster_batch* b, int maximum_ilp_size
   ENS(d_row_first, (size_t)n_rows * 4);
   int* d_err = c->d_err.as<int>();
   if (n_rows > 0) {
-    k_cp_fill<<<std::min(blocks(tabr_off[T], 256), 4096u), 256, 0, c->st>>>(c->d_tab.as<int>(), tabr_off[T], CP_EMPTY);
+    k_cp_fill<int><<<std::min(blocks(tabr_off[T], 256), 4096u), 256, 0, c->st>>>(c->d_tab.as<int>(), tabr_off[T], CP_EMPTY);
     k_cp_row_bits<<<blocks((i64)n_rows * 32, 256), 256, 0, c->st>>>(
         n_rows, T, c->d_tint_row_off.as<int>(), c->d_tint_seg_n.as<int>(), c->d_tint_digit_off.as<i64>(),
         c->d_rowword_off.as<i64>(), c->d_digits.as<u8>(), c->d_rowbits.as<u32>(), c->d_row_f.as<int>(), c->d_row_l.as<int>(),
@@ -279,7 +279,7 @@ int frs_cprep_run(frs_cprep* c, const frs_cluster_batch* b, int maximum_ilp_size
   ENS(d_tint_struct_off, (size_t)(T + 1) * 4);
   int U = 0, S_tot = 0;
   if (N > 0) {
-    k_cp_fill<<<std::min(blocks(tabn_off[T], 256), 4096u), 256, 0, c->st>>>(c->d_tab.as<int>(), tabn_off[T], CP_EMPTY);
+    k_cp_fill<int><<<std::min(blocks(tabn_off[T], 256), 4096u), 256, 0, c->st>>>(c->d_tab.as<int>(), tabn_off[T], CP_EMPTY);
     CPK(cudaMemsetAsync(c->d_count.p, 0, (size_t)N * 4, c->st));
     k_cp_read_key<<<blocks(N, 128), 128, 0, c->st>>>(
         N, T, c->d_tint_read_off.as<int>(), c->d_tint_row_off.as<int>(), c->d_read_row.as<int>(), c->d_row_first.as<int>(),
@@ -327,7 +327,7 @@ int frs_cprep_run(frs_cprep* c, const frs_cluster_batch* b, int maximum_ilp_size
   c->launches += 1;
   if (U > 0) {
     // the read tables' regions are large enough for the reps of a tint (U_t <= N_t)
-    k_cp_fill<<<std::min(blocks(tabn_off[T], 256), 4096u), 256, 0, c->st>>>(c->d_tab.as<int>(), tabn_off[T], CP_EMPTY);
+    k_cp_fill<int><<<std::min(blocks(tabn_off[T], 256), 4096u), 256, 0, c->st>>>(c->d_tab.as<int>(), tabn_off[T], CP_EMPTY);
     CPK(cudaMemsetAsync(c->d_scount.p, 0, (size_t)U * 4, c->st));
     k_cp_struct_insert<<<blocks(U, 128), 128, 0, c->st>>>(U, c->d_rep_tint.as<int>(), c->d_rep_row.as<int>(), c->d_rep_cat.as<u8>(),
                                                          c->d_rep_hash.as<u64>(), c->d_tabn_off.as<i64>(), c->d_tabn_cap.as<int>(),
@@ -420,7 +420,7 @@ int frs_cprep_run(frs_cprep* c, const frs_cluster_batch* b, int maximum_ilp_size
     const unsigned wg = blocks((i64)S_tot * 32, 256);
     // B starts as a copy, so that the rows of tints that stop changing are valid in both buffers
     CPK(cudaMemcpyAsync(B, A, (size_t)adj_off[T] * 4, cudaMemcpyDeviceToDevice, c->st));
-    k_cp_fill<<<blocks(T, 256), 256, 0, c->st>>>(c->d_active_a.as<int>(), T, 1);
+    k_cp_fill<int><<<blocks(T, 256), 256, 0, c->st>>>(c->d_active_a.as<int>(), T, 1);
     c->launches += 1;
     int* act = c->d_active_a.as<int>();
     int* act_next = c->d_active_b.as<int>();

@@ -348,6 +348,57 @@ int frs_cprep_fetch(frs_cprep* c, const frs_cluster_result* out);
  * [4] incompatible pairs; returns the number of entries */
 int frs_cprep_timings(frs_cprep* c, float* ms, int n);
 
+/* =========================================================================================================
+ * Last row of the scope table: tint construction of freddie_split.py on decoded alignments.
+ * Replaces, for a batch of read groups (what read_sam yields, freddie_split.py:207-244: reads of one contig whose
+ * alignments chain into each other; BAM decoding itself stays with the caller):
+ *   get_transcriptional_intervals  :295-364  (simple intervals = union of the alignment intervals, touching ones
+ *                                   merged; groups joined through multi-interval reads, in the order of their
+ *                                   smallest interval; fewer than 3 reads dropped)
+ *   break_tint                     :246-293  (groups with >= max_intervals intervals or >= max_reads reads: intervals
+ *                                   joined by junctions that >= 2 reads support; per component the reads that
+ *                                   start an alignment in it and all intervals those reads start in)
+ * Sorting (radix), sweeps (scans), union-find and the set unions run in CUDA kernels (kernels_split.cuh); the
+ * final lists are assembled by native host code inside the library.  No CPU fallback.
+ * ========================================================================================================= */
+typedef struct frs_split frs_split;
+
+typedef struct {
+  int32_t n_groups, n_reads;
+  const int32_t* group_read_off; /* [n_groups+1] reads of group g (read id inside a group = index - group_read_off[g]) */
+  const int32_t* read_iv_off;    /* [n_reads+1]  alignment intervals of a read, in target order, at least one */
+  const int32_t* iv_s;           /* [n_intervals] target start (>= 0) */
+  const int32_t* iv_e;           /* [n_intervals] target end (exclusive, > start) */
+  int32_t max_intervals;         /* 100 in the reference (:357); <= 0: that default */
+  int32_t max_reads;             /* 1500 in the reference (:357); <= 0: that default */
+} frs_split_batch;
+
+typedef struct {
+  int64_t n_tints, n_tint_ivs, n_tint_rids;
+  int64_t n_simple;  /* simple intervals over all groups */
+  int32_t n_big;     /* groups that went through break_tint */
+  int32_t launches;  /* kernel launches of this run */
+} frs_split_sizes;
+
+/* caller-allocated host arrays (sizes from frs_split_sizes); tints of group g: group_tint_off[g] .. [g+1], in the
+ * order get_transcriptional_intervals returns them */
+typedef struct {
+  int32_t* group_tint_off; /* [n_groups+1] */
+  int32_t* tint_iv_off;    /* [n_tints+1] */
+  int32_t* tint_iv_s;      /* [n_tint_ivs] tint['intervals'], sorted */
+  int32_t* tint_iv_e;
+  int32_t* tint_rid_off;   /* [n_tints+1] */
+  int32_t* tint_rids;      /* [n_tint_rids] tint['rids'] (ids inside the group), sorted */
+} frs_split_result;
+
+int frs_split_create(int device, frs_split** out);
+void frs_split_destroy(frs_split* c);
+const char* frs_split_last_error(frs_split* c);
+int frs_split_run(frs_split* c, const frs_split_batch* batch, frs_split_sizes* sizes);
+int frs_split_fetch(frs_split* c, const frs_split_result* out);
+/* device milliseconds of the last run (first kernel to last kernel) */
+float frs_split_last_ms(frs_split* c);
+
 #ifdef __cplusplus
 }
 #endif
