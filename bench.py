@@ -306,6 +306,68 @@ def cluster_prep_scope(device, batch, res, cores):
     return obj
 
 
+def _ref_split_one(group):
+    """get_transcriptional_intervals (+ break_tint) of the UNMODIFIED reference on one group (freddie_split.py:295-364,
+    :246-293) -> digest of the canonical serialisation."""
+    from oracle import build_ref
+    from oracle import split_tints_oracle as sto
+    fs = build_ref.reference_split_module()
+    reads = [dict(id=i, name="r%d" % i, contig="c", strand="+", simple_tints=list(), tint=None,
+                  intervals=[(s, e, 0, e - s, [(0, e - s)]) for s, e in ivs]) for i, ivs in enumerate(group)]
+    return sto.digest_of([(t["intervals"], t["rids"]) for t in fs.get_transcriptional_intervals(reads=reads)])
+
+
+def split_tints_scope(device, tints, cores):
+    """tint construction of the split stage for the reads of the workload, re-grouped the way read_sam
+    would hand them over (runs of 8 neighbouring tints of the synthetic contig form one group, reads by start), in
+    ONE frs_split_run; beside it the unmodified reference function on the same groups (one group per task, all host
+    cores), compared digest by digest."""
+    from freddie_b200.split_tints import SplitTints
+    groups = []
+    for k in range(0, len(tints), 8):
+        reads = [[(iv[0], iv[1]) for iv in r["intervals"]] for t in tints[k:k + 8] for r in t["reads"]]
+        reads.sort(key=lambda ivs: ivs[0][0])
+        groups.append(reads)
+    gro, rio, s, e = [0], [0], [], []
+    for reads in groups:
+        for ivs in reads:
+            for a, b in ivs:
+                s.append(a)
+                e.append(b)
+            rio.append(len(s))
+        gro.append(len(rio) - 1)
+    arrs = [np.asarray(x, np.int32) for x in (gro, rio, s, e)]
+    ctx = SplitTints(device)
+    for _ in range(2):
+        res, info, _ = ctx.run_arrays(*arrs)
+    K = 5
+    t0 = time.perf_counter()
+    for _ in range(K):
+        res, info, raw = ctx.run_arrays(*arrs)
+    dt = (time.perf_counter() - t0) / K
+    n_reads = len(rio) - 1
+    obj = dict(value=n_reads / dt, unit="reads/s", seconds=round(dt, 5), device_ms=round(info["device_ms"], 3),
+               scope="host arrays of decoded alignments in -> frs_split_run + frs_split_fetch -> tint lists out (copies, host "
+                     "assembly and the Python list building of the mirror inside the wall clock)",
+               groups=len(groups), reads=n_reads, intervals=len(s), tints=info["n_tints"], simple_intervals=info["n_simple"],
+               broken_groups=info["n_big"], launches=info["launches"])
+    from oracle import build_ref
+    if build_ref.split_available():
+        from multiprocessing import Pool
+        from oracle import split_tints_oracle as sto
+        t0 = time.perf_counter()
+        with Pool(cores) as p:
+            ref = p.map(_ref_split_one, groups, chunksize=1)
+        rdt = time.perf_counter() - t0
+        same = sum(sto.digest_of(res[g]) == ref[g] for g in range(len(groups)))
+        obj["cpu_baseline"] = dict(value=n_reads / rdt, unit="reads/s", cores=cores, kind="reference",
+                                   sample="unmodified get_transcriptional_intervals + break_tint (oracle/_ref/freddie_split.bin), "
+                                          "one group per task on %d processes, all %d groups, %.2f s" % (cores, len(groups), rdt),
+                                   parity="%d of %d groups equal the CUDA path's canonical digest" % (same, len(groups)))
+    ctx.close()
+    return obj
+
+
 def config_dict(args):
     """The same object from both arms (the driver compares them)."""
     return dict(workload=WORKLOADS[args.workload], scale=args.scale, params="defaults (sd=5 tp=0.9 vf=3 mps=50 lo=3)",
@@ -672,6 +734,10 @@ def run_cuda_arm(args):
             line["cluster_prep"] = cluster_prep_scope(local_rank, batches[0], res_lazy[0], cores)
         except Exception as e:  # noqa: BLE001
             line["cluster_prep"] = dict(error=repr(e)[:300])
+        try:  # the last row of the scope table
+            line["split_tints"] = split_tints_scope(local_rank, tints_for_cpu, cores)
+        except Exception as e:  # noqa: BLE001
+            line["split_tints"] = dict(error=repr(e)[:300])
     if world == 1 and not args.no_cpu_baseline and tints_for_cpu is not None:
         from oracle import build_ref
         r, c, sample = oracle_rate(tints_for_cpu, cores, int(os.environ.get("FRS_CPU_SAMPLE_READS", 300 * cores * 8)))

@@ -30,6 +30,10 @@ REF_META = os.path.join(REF_DIR, "MANIFEST.json")
 # called as functions of the compiled module (gurobipy is stubbed when absent: they never touch it)
 REF_CLUSTER_SRC = "/root/reference/py/freddie_cluster.py"
 REF_CLUSTER_PYC = os.path.join(REF_DIR, "freddie_cluster.bin")
+# the split stage's tint construction: get_transcriptional_intervals / break_tint as functions of
+# the compiled module (pysam is stubbed when absent: they never touch it)
+REF_SPLIT_SRC = "/root/reference/py/freddie_split.py"
+REF_SPLIT_PYC = os.path.join(REF_DIR, "freddie_split.bin")
 
 
 def build_ref(quiet: bool = True) -> bool:
@@ -52,6 +56,12 @@ def build_ref(quiet: bool = True) -> bool:
             with open(REF_CLUSTER_SRC, "rb") as fh:
                 meta["cluster"] = dict(source=REF_CLUSTER_SRC, sha256=hashlib.sha256(fh.read()).hexdigest(),
                                        artefact="freddie_cluster.bin")
+        if os.path.exists(REF_SPLIT_SRC):
+            py_compile.compile(REF_SPLIT_SRC, cfile=REF_SPLIT_PYC, doraise=True, optimize=0,
+                               invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+            with open(REF_SPLIT_SRC, "rb") as fh:
+                meta["split"] = dict(source=REF_SPLIT_SRC, sha256=hashlib.sha256(fh.read()).hexdigest(),
+                                     artefact="freddie_split.bin")
         with open(REF_META, "w") as fh:
             json.dump(meta, fh)
         if not quiet:
@@ -93,6 +103,36 @@ def reference_cluster_module():
             loader.exec_module(mod)
         _cluster_mod = mod
     return _cluster_mod
+
+
+def split_available() -> bool:
+    return os.path.exists(REF_SPLIT_PYC)
+
+
+_split_mod = None
+
+
+def reference_split_module():
+    """The unmodified freddie_split module from its compiled artefact (functions only; main() is not run)."""
+    global _split_mod
+    if _split_mod is None:
+        import importlib.machinery
+        import importlib.util
+        import types
+        try:
+            import pysam  # noqa: F401
+        except Exception:
+            stub = types.ModuleType("pysam")  # the module-level tables (:64-101) name the SAM CIGAR operation codes
+            for code, name in enumerate(["CMATCH", "CINS", "CDEL", "CREF_SKIP", "CSOFT_CLIP", "CHARD_CLIP", "CPAD", "CEQUAL",
+                                         "CDIFF", "CBACK"]):
+                setattr(stub, name, code)
+            sys.modules["pysam"] = stub
+        loader = importlib.machinery.SourcelessFileLoader("freddie_split_ref", REF_SPLIT_PYC)
+        spec = importlib.util.spec_from_loader("freddie_split_ref", loader)
+        mod = importlib.util.module_from_spec(spec)
+        loader.exec_module(mod)
+        _split_mod = mod
+    return _split_mod
 
 
 def command(split_dir: str, out_dir: str, threads: int, flags=()):
