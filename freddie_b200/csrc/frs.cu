@@ -1076,6 +1076,7 @@ static int enqueue_run(frs_context* c, Slot& S) {
     A.tab = c->b_tab.as<int>(); A.final_flag = c->b_dpfinal.as<u8>(); A.err = d_err;
     A.cnt = d_cnt; A.caps = cp; A.bases = c->b_bases.as<int>(); A.cursor = c->b_cursor.as<int>();
     A.m_cap = dp_max_n;
+    A.sub_left = c->b_sub_slabs.as<int>();
     const DpWork* wl = c->b_work.as<DpWork>();
     // persistent CTAs per SM of the six classes (development knob: FRS_DP_GRIDS="8,3,6,3,1,1")
     static int dp_cps[DP_CLASSES] = {8, 3, 6, 3, 1, 1};
@@ -1088,6 +1089,12 @@ static int enqueue_run(frs_context* c, Slot& S) {
     // large classes overlap the many short items of the small ones (fork / join with events)
     CK(cudaEventRecord(c->ev_fork, st));
     bool used[FRS_SIDE_STREAMS] = {};
+    // FRS_DP_TIMELINE=1 (development): end of every class's launch relative to the fork, printed after the run
+    static const bool dp_tl = getenv("FRS_DP_TIMELINE") != nullptr;
+    static cudaEvent_t tl_ev[8] = {};
+    if (dp_tl && !tl_ev[0])
+      for (auto& e : tl_ev) cudaEventCreate(&e);
+    if (dp_tl) cudaEventRecord(tl_ev[7], st);
     const int top = (A.m_cap > DP_SMEM_MAX_N) ? DP_CLASSES - 1 : DP_CLASSES - 2;  // class 5 needs n > 56
     for (int k = top; k >= 0; --k) {  // longest-running classes first
       const int sidx = k >= 2 ? k - 2 : 4 + k;  // a stream per class
@@ -1102,6 +1109,7 @@ static int enqueue_run(frs_context* c, Slot& S) {
       }
       LAUNCHED();
       CK(cudaEventRecord(c->ev_join[sidx], ks));
+      if (dp_tl) cudaEventRecord(tl_ev[k], ks);
       used[sidx] = true;
     }
     {
@@ -1114,10 +1122,19 @@ static int enqueue_run(frs_context* c, Slot& S) {
                                                                                  dp_stage_n);
       LAUNCHED();
       CK(cudaEventRecord(c->ev_join[0], ss));
+      if (dp_tl) cudaEventRecord(tl_ev[6], ss);
       used[0] = true;
     }
     for (int k = 0; k < FRS_SIDE_STREAMS; ++k)
       if (used[k]) CK(cudaStreamWaitEvent(st, c->ev_join[k], 0));
+    if (dp_tl) {
+      cudaStreamSynchronize(st);
+      float t[7] = {};
+      for (int k = 0; k <= 6; ++k)
+        if (k == 6 || k <= top) cudaEventElapsedTime(&t[k], tl_ev[7], tl_ev[k]);
+      fprintf(stderr, "[frs dp timeline] ends after the fork (ms): warp8 %.3f  warp16 %.3f  cta128 %.3f  cta256 %.3f  cta1024 %.3f  big %.3f  solve %.3f\n",
+              t[0], t[1], t[2], t[3], t[4], t[5], t[6]);
+    }
   }
 
   // ================= phase 3: refine, final positions, digits =================

@@ -239,7 +239,7 @@ __global__ void k_sub_build(const i64* __restrict__ n_cand_p, const u8* __restri
           cls = dp_class_of(n, words, fused, warp_max_words);
           slabs = fused ? 1 : (words + sw - 1) / sw;
           bucket = dp_bucket_of(n, fused ? words : sw);
-          split = !fused;
+          split = (!fused && cls == DP_CLASSES - 1) ? 1 : 0;  // only n > DP_SMEM_MAX_N needs the separate solver
           t3 = (long long)n * (n - 1) * (n - 2) / 6;
           rc = t3 * R;
           info = cls | (fused << 8) | (bucket << 12) | (sw << 16);
@@ -329,7 +329,7 @@ __global__ void k_sub_fill(const i64* __restrict__ cnt, Caps caps, const int* __
     const int key = 16 + cls * DP_BUCKETS + ((info >> 12) & 7);
     int off = bases[key] + atomicAdd(&cursor[key], slabs);
     for (int s = 0; s < slabs; ++s) work[off + s] = DpWork{p, s};
-    if (!((info >> 8) & 1)) split_list[atomicAdd(&cursor[DP_CLASSES], 1)] = p;
+    if (!((info >> 8) & 1) && cls == DP_CLASSES - 1) split_list[atomicAdd(&cursor[DP_CLASSES], 1)] = p;
   }
 }
 
@@ -523,6 +523,7 @@ struct DpArgs {
   const int* bases;  // [DP_CLASSES] first work item of each class
   int* cursor;       // [8 + class] work-stealing cursors, [8 + DP_CLASSES] the solver's
   int m_cap;         // upper bound of a subproblem's size (max_problem_size + 12, see k_fixed_b)
+  int* sub_left;     // slabs of every split subproblem still to be added to its global tables (starts as sub_slabs)
 };
 
 // shared-memory carve-up of k_dp for (M = largest n of the launch, wc, out table on chip?)
@@ -672,7 +673,7 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 ? 3 : 1)) k_dp(DpArgs A, const DpWork* __restrict__ work_all,
                                                 int cls, int smem_bytes) {
   extern __shared__ __align__(16) unsigned char dsm[];
-  __shared__ int s_n_munit, s_item, s_nq, s_wfull, s_wdead;
+  __shared__ int s_n_munit, s_item, s_nq, s_wfull, s_wdead, s_last;
   if (!dp_caps_ok(A.cnt, A.caps)) return;
   const int n_work = (int)A.cnt[CNT_PLAN + PLAN_WORK + cls];
   if (n_work == 0) return;
@@ -933,12 +934,21 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 
 
     if (!out_on_chip) continue;  // class 5: tables are already in global memory
     if (!fused) {
-      // split mode: add this slab's partial tables to the global ones
+      // split mode: add this slab's partial tables to the global ones; the CTA that finishes the LAST slab of the
+      // subproblem reads the sums back and solves the DP right away (no separate solver launch behind all the
+      // table kernels: the solve of one subproblem runs beside the slabs of the others)
       for (int e = tid; e < p2; e += THREADS) { int v = amb_s[e]; if (v) atomicAdd(&tab_g[e], v); }
       for (int e = tid; e < c3; e += THREADS) { int v = out_s[e]; if (v) atomicAdd(&tab_g[p2 + e], v); }
-      continue;
-    }
-    if (A.keep_tables) {
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) s_last = atomicSub(&A.sub_left[p], 1) == 1;
+      __syncthreads();
+      if (!s_last) continue;
+      __threadfence();
+      for (int e = tid; e < p2; e += THREADS) amb_s[e] = __ldcg(&tab_g[e]);
+      for (int e = tid; e < c3; e += THREADS) out_s[e] = __ldcg(&tab_g[p2 + e]);
+      __syncthreads();
+    } else if (A.keep_tables) {
       for (int e = tid; e < p2; e += THREADS) tab_g[e] = amb_s[e];
       for (int e = tid; e < c3; e += THREADS) tab_g[p2 + e] = out_s[e];
     }
