@@ -14,7 +14,8 @@ import tempfile
 rep, mangled = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-so = os.path.join(root, "freddie_b200", "libfreddie_b200.so")
+so = os.environ.get("FRS_LIB") or os.path.join(root, "freddie_b200", "libfreddie_b200.so")
+src_root = os.environ.get("FRS_SRC") or os.path.join(root, "freddie_b200", "csrc")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, stdout=subprocess.DEVNULL, check=True)
 instrs = None
@@ -67,7 +68,7 @@ src = {}
 for line, v in sorted(smp.items(), key=lambda kv: -kv[1])[:top]:
     text = ""
     if line:
-        p = os.path.join(root, "freddie_b200", "csrc", line[0])
+        p = os.path.join(src_root, line[0])
         if os.path.exists(p):
             src.setdefault(p, open(p).read().split("\n"))
             text = src[p][line[1] - 1].strip()[:100]
