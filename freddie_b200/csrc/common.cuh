@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(1024) k_scan_bsums(i64* __restrict__ bsum, int
 // out[i] = exclusive prefix (TOut), out[n] = total
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const TIn* __restrict__ in, i64 n,
-                                                            const i64* __restrict__ bsum, TOut* __restrict__ out) {
+                                                            const i64* __restrict__ bsum, TOut* __restrict__ out,
+                                                            i64* __restrict__ total_out /* or NULL */) {
   __shared__ i64 sm[40];
   i64 base = (i64)blockIdx.x * SCAN_TILE + (i64)threadIdx.x * SCAN_ITEMS;
   i64 v[SCAN_ITEMS];
@@ -192,13 +193,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const TIn* __restri
     if (base + k < n) out[base + k] = (TOut)ex;
     ex += v[k];
   }
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = (TOut)bsum[gridDim.x];
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    out[n] = (TOut)bsum[gridDim.x];
+    if (total_out) *total_out = bsum[gridDim.x];  // the total also goes to the run's counter block (no copy launch)
+  }
 }
 
 // short arrays (per-tint tables): one CTA, one launch.  out[i] = exclusive prefix, out[n] = total
 #define SCAN_SMALL_MAX 65536
 template <typename TIn, typename TOut>
-__global__ void __launch_bounds__(1024) k_scan_small(const TIn* __restrict__ in, int n, TOut* __restrict__ out) {
+__global__ void __launch_bounds__(1024) k_scan_small(const TIn* __restrict__ in, int n, TOut* __restrict__ out,
+                                                     i64* __restrict__ total_out /* or NULL */) {
   __shared__ i64 sm[40];
   const int per = (n + 1023) / 1024;
   const int i0 = min(n, (int)threadIdx.x * per), i1 = min(n, i0 + per);
@@ -211,7 +216,10 @@ __global__ void __launch_bounds__(1024) k_scan_small(const TIn* __restrict__ in,
     out[i] = (TOut)ex;
     ex += v;
   }
-  if (threadIdx.x == 0) out[n] = (TOut)tot;
+  if (threadIdx.x == 0) {
+    out[n] = (TOut)tot;
+    if (total_out) *total_out = tot;
+  }
 }
 
 // byte-flag compaction, idx_out[rank] = i for every i with flags[i] != 0 (ascending): 16 flags per
@@ -243,8 +251,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_flag_sums(const u8* __restrict
   if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
 }
 __global__ void __launch_bounds__(SCAN_THREADS) k_flag_compact(const u8* __restrict__ flags, i64 n,
-                                                              const i64* __restrict__ bsum, int* __restrict__ idx_out) {
+                                                              const i64* __restrict__ bsum, int* __restrict__ idx_out,
+                                                              i64* __restrict__ count_out /* or NULL */) {
   __shared__ int sm[40];
+  if (count_out && blockIdx.x == 0 && threadIdx.x == 0) *count_out = bsum[gridDim.x];
   const i64 base = (i64)blockIdx.x * FLAG_TILE + (i64)threadIdx.x * FLAG_ITEMS;
   u32 bits = (base < n) ? flag_bits16(flag_load16(flags, base, n)) : 0u;
   i64 ex = (i64)block_exclusive_scan<int>(__popc(bits), (int*)nullptr, sm) + bsum[blockIdx.x];

@@ -91,6 +91,7 @@ struct frs_context {
   cudaEvent_t ev_tfork = nullptr, ev_tjoin = nullptr;
   cudaStream_t side[FRS_SIDE_STREAMS] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[FRS_SIDE_STREAMS] = {};
+  cudaEvent_t ev_cov[3] = {};  // coverage chain on side[0]: fork, block offsets ready, matrix ready
   char err[512] = "";
   bool profiling = false;
   Slot slot[FRS_SLOTS];
@@ -101,7 +102,7 @@ struct frs_context {
   // device buffers (grow-only)
   std::vector<DBuf*> all;
   // intermediates shared by the slots
-  DBuf b_yraw, b_y, b_sflag, b_bsum, b_cand_flat, b_cand_island, b_island_cand_off, b_tint_cand_off, b_thr, b_vbuf,
+  DBuf b_yraw, b_y, b_sflag, b_bsum, b_bsum_cov, b_cand_flat, b_cand_island, b_island_cand_off, b_tint_cand_off, b_thr, b_vbuf,
       b_leaf_len, b_leaf_sum, b_tint_pos_off, b_tile_state, b_fixed0, b_fixed1, b_sub_start,
       b_sub_n, b_sub_tint, b_sub_info, b_sub_slabs, b_sub_tab_off, b_bases, b_work, b_split_list, b_cursor,
       b_cov_sz, b_tint_cov_off, b_P, b_tab, b_dpfinal, b_ref_list, b_ref_list2, b_gbuf, b_pstate, b_final_flat,
@@ -232,9 +233,10 @@ static void dev_copy_word(frs_context* c, cudaStream_t st, i64* dst, const void*
   c->launch_count++;
 }
 template <typename TIn, typename TOut>
-static int scan_exclusive_on(frs_context* c, cudaStream_t st, DBuf& scratch, const TIn* in, i64 n, TOut* out) {
+static int scan_exclusive_on(frs_context* c, cudaStream_t st, DBuf& scratch, const TIn* in, i64 n, TOut* out,
+                             i64* total_out = nullptr /* device: also receives out[n] */) {
   if (n <= SCAN_SMALL_MAX && (const void*)in != (const void*)out) {
-    k_scan_small<TIn, TOut><<<1, 1024, 0, st>>>(in, (int)n, out); LAUNCHED();
+    k_scan_small<TIn, TOut><<<1, 1024, 0, st>>>(in, (int)n, out, total_out); LAUNCHED();
     return 0;
   }
   int nb = cdiv(n > 0 ? n : 1, SCAN_TILE);
@@ -242,12 +244,12 @@ static int scan_exclusive_on(frs_context* c, cudaStream_t st, DBuf& scratch, con
   i64* bs = scratch.as<i64>();
   k_scan_block_sums<TIn><<<nb, SCAN_THREADS, 0, st>>>(in, n, bs); LAUNCHED();
   k_scan_bsums<<<1, 1024, 0, st>>>(bs, nb); LAUNCHED();
-  k_scan_apply<TIn, TOut><<<nb, SCAN_THREADS, 0, st>>>(in, n, bs, out); LAUNCHED();
+  k_scan_apply<TIn, TOut><<<nb, SCAN_THREADS, 0, st>>>(in, n, bs, out, total_out); LAUNCHED();
   return 0;
 }
 template <typename TIn, typename TOut>
-static int scan_exclusive(frs_context* c, const TIn* in, i64 n, TOut* out) {
-  return scan_exclusive_on<TIn, TOut>(c, c->stream, c->b_bsum, in, n, out);
+static int scan_exclusive(frs_context* c, const TIn* in, i64 n, TOut* out, i64* total_out = nullptr) {
+  return scan_exclusive_on<TIn, TOut>(c, c->stream, c->b_bsum, in, n, out, total_out);
 }
 // compaction of byte flags; the count ends up in bsum[nb] and is copied to *count_out (device)
 static int compact_flags(frs_context* c, const u8* flags, i64 n, int* idx_out, i64* count_out) {
@@ -256,8 +258,7 @@ static int compact_flags(frs_context* c, const u8* flags, i64 n, int* idx_out, i
   i64* bs = c->b_bsum.as<i64>();
   k_flag_sums<<<nb, SCAN_THREADS, 0, c->stream>>>(flags, n, bs); LAUNCHED();
   k_scan_bsums<<<1, 1024, 0, c->stream>>>(bs, nb); LAUNCHED();
-  k_flag_compact<<<nb, SCAN_THREADS, 0, c->stream>>>(flags, n, bs, idx_out); LAUNCHED();
-  dev_copy_word(c, c->stream, count_out, bs + nb, 8);
+  k_flag_compact<<<nb, SCAN_THREADS, 0, c->stream>>>(flags, n, bs, idx_out, count_out); LAUNCHED();
   return 0;
 }
 static const char* deverr_text(int code) {
@@ -355,6 +356,7 @@ int frs_create(int device, frs_context** out) {
     cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
   }
   cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+  for (auto& e : c->ev_cov) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   {
     const int big = 227 * 1024 - 256;  // the kernels also hold a few bytes of static shared memory
     cudaError_t ea[7] = {
@@ -406,6 +408,8 @@ void frs_destroy(frs_context* c) {
     if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
   }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  for (auto& e : c->ev_cov)
+    if (e) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->st_in);
   cudaStreamDestroy(c->st_out);
@@ -993,9 +997,18 @@ static int enqueue_run(frs_context* c, Slot& S) {
     u32* d_tcnt = d_pmask + (size_t)S.n_tiles * TILE_WORDS;
     dev_zero(c, st, d_gsum, n_groups * 8);
     const size_t sm = (size_t)p1_smem_layout(lw).total;
-    if (sm > 48 * 1024) CK(cudaFuncSetAttribute(k_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_smooth<<<S.n_tiles, GAUSS_THREADS, sm, st>>>(S.b_tiles.as<TileWork>(), d_island_sample_off, c->b_yraw.as<int>(),
-                                                    d_gw, lw, c->b_y.as<double>(), d_cmask, d_pmask, d_tcnt, d_gsum);
+    // FRS_SMOOTH_OCC (dev knob): register budget of k_smooth as CTAs per SM
+    static const int occ = [] { const char* e = getenv("FRS_SMOOTH_OCC"); return e ? atoi(e) : 16; }();
+#define FRS_LAUNCH_SMOOTH(MINB)                                                                                              \
+  do {                                                                                                                       \
+    if (sm > 48 * 1024) CK(cudaFuncSetAttribute(k_smooth<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));      \
+    k_smooth<MINB><<<S.n_tiles, GAUSS_THREADS, sm, st>>>(S.b_tiles.as<TileWork>(), d_island_sample_off, c->b_yraw.as<int>(), \
+                                                         d_gw, lw, c->b_y.as<double>(), d_cmask, d_pmask, d_tcnt, d_gsum);   \
+  } while (0)
+    if (occ == 10) FRS_LAUNCH_SMOOTH(10);
+    else if (occ == 12) FRS_LAUNCH_SMOOTH(12);
+    else FRS_LAUNCH_SMOOTH(16);
+#undef FRS_LAUNCH_SMOOTH
     LAUNCHED();
     stage_begin(c, "lists");
     k_tile_lists<<<S.n_tiles, GAUSS_THREADS, 0, st>>>(S.b_tiles.as<TileWork>(), S.n_tiles, d_island_sample_off,
@@ -1006,20 +1019,42 @@ static int enqueue_run(frs_context* c, Slot& S) {
   }
 
   if (S.tl[7]) cudaEventRecord(S.tl[7], st);
+  // ================= phase 2: fixed candidates, subproblems, coverage, DP =================
+  // (the number of candidates stays on the device: grid-stride launches sized by its upper bound)
+  stage_begin(c, "cand_meta");
+  const i64* d_K = d_cnt + CNT_K;
+  const int g_cand = gs_grid(KMAX, 256);
+  k_cand_meta<<<g_cand, 256, 0, st>>>(c->b_cand_flat.as<int>(), d_K, d_island_sample_off, NI,
+                                      c->b_cand_island.as<int>(), c->b_island_cand_off.as<int>());
+  LAUNCHED();
+  // The coverage matrix only needs the candidate list: its chain (block offsets per tint, scan, k_coverage) runs
+  // on a side stream beside threshold -> fixed -> subproblems, which are short latency-bound kernels; the head
+  // stream takes the offsets back before k_plan_finish and the matrix before the DP fork.
+  {
+    cudaStream_t cs = c->side[0];
+    CK(cudaEventRecord(c->ev_cov[0], st));
+    CK(cudaStreamWaitEvent(cs, c->ev_cov[0], 0));
+    stage_begin(c, "coverage", cs);
+    // coverage block offsets per tint (rows = candidates of the tint, stride Rp)
+    k_tint_cov_sizes<<<cdiv(T + 1, 256), 256, 0, cs>>>(T, d_tint_island_off, c->b_island_cand_off.as<int>(), d_tint_rep_off,
+                                                       c->b_tint_cand_off.as<int>(), c->b_cov_sz.as<i64>());
+    LAUNCHED();
+    { int r = scan_exclusive_on<i64, i64>(c, cs, c->b_bsum_cov, c->b_cov_sz.as<i64>(), T, c->b_tint_cov_off.as<i64>()); if (r) return r; }
+    CK(cudaEventRecord(c->ev_cov[1], cs));
+    k_coverage<<<dim3((unsigned)std::max(S.n_cov_tiles, 1), COV_CHUNKS), COV_THREADS, 0, cs>>>(
+        S.b_cov_tiles.as<RepTile>(), d_tint_rep_off, c->b_tint_cand_off.as<int>(), c->b_tint_cov_off.as<i64>(),
+        S.b_rep_iv_off.as<int>(), S.b_rep_fs.as<int>(), S.b_rep_fe.as<int>(), c->b_cand_flat.as<int>(), c->b_P.as<u32>(),
+        T, S.n_cov_tiles > 0 ? cp.P : -1);
+    LAUNCHED();
+    CK(cudaEventRecord(c->ev_cov[2], cs));
+  }
   stage_begin(c, "threshold");
   k_threshold<<<T, THR_THREADS, 0, st>>>(S.b_tint_order.as<int>(), d_tint_island_off, d_island_sample_off,
                                          c->b_tint_pos_off.as<int>(), prm->vf, c->b_vbuf.as<double>(),
                                          c->b_leaf_len.as<int>(), c->b_leaf_sum.as<double>(), c->b_thr.as<double>());
   LAUNCHED();
 
-  // ================= phase 2: fixed candidates, subproblems, coverage, DP =================
-  // (the number of candidates stays on the device: grid-stride launches sized by its upper bound)
   stage_begin(c, "fixed");
-  const i64* d_K = d_cnt + CNT_K;
-  const int g_cand = gs_grid(KMAX, 256);
-  k_cand_meta<<<g_cand, 256, 0, st>>>(c->b_cand_flat.as<int>(), d_K, d_island_sample_off, NI,
-                                      c->b_cand_island.as<int>(), c->b_island_cand_off.as<int>());
-  LAUNCHED();
   k_fixed_a<<<g_cand, 256, 0, st>>>(d_K, c->b_cand_flat.as<int>(), c->b_cand_island.as<int>(),
                                     c->b_island_cand_off.as<int>(), d_island_tint, c->b_y.as<double>(),
                                     c->b_thr.as<double>(), c->b_fixed0.as<u8>(), c->b_fixed1.as<u8>());
@@ -1038,22 +1073,11 @@ static int enqueue_run(frs_context* c, Slot& S) {
                                       c->b_sub_info.as<int>(), c->b_sub_slabs.as<int>(), c->b_sub_tab_off.as<i64>(),
                                       d_cnt + CNT_PLAN, d_err);
   LAUNCHED();
-  // coverage block offsets per tint (rows = candidates of the tint, stride Rp)
-  k_tint_cov_sizes<<<cdiv(T + 1, 256), 256, 0, st>>>(T, d_tint_island_off, c->b_island_cand_off.as<int>(), d_tint_rep_off,
-                                                     c->b_tint_cand_off.as<int>(), c->b_cov_sz.as<i64>());
-  LAUNCHED();
-  { int r = scan_exclusive<i64, i64>(c, c->b_cov_sz.as<i64>(), T, c->b_tint_cov_off.as<i64>()); if (r) return r; }
+  CK(cudaStreamWaitEvent(st, c->ev_cov[1], 0));  // the offsets of the coverage blocks
   k_plan_finish<<<1, 32, 0, st>>>(d_cnt, c->b_tint_cov_off.as<i64>(), T, c->b_bases.as<int>(), c->b_cursor.as<int>());
   LAUNCHED();
 
   if (S.tl[8]) cudaEventRecord(S.tl[8], st);
-  stage_begin(c, "coverage");
-  k_coverage<<<dim3((unsigned)std::max(S.n_cov_tiles, 1), COV_CHUNKS), COV_THREADS, 0, st>>>(
-      S.b_cov_tiles.as<RepTile>(), d_tint_rep_off, c->b_tint_cand_off.as<int>(), c->b_tint_cov_off.as<i64>(),
-      S.b_rep_iv_off.as<int>(), S.b_rep_fs.as<int>(), S.b_rep_fe.as<int>(), c->b_cand_flat.as<int>(), c->b_P.as<u32>(),
-      d_cnt, S.n_cov_tiles > 0 ? cp.P : -1);
-  LAUNCHED();
-
   k_copy_flags<<<g_cand, 256, 0, st>>>(d_K, c->b_fixed1.as<u8>(), c->b_dpfinal.as<u8>());
   LAUNCHED();
   {
@@ -1087,6 +1111,7 @@ static int enqueue_run(frs_context* c, Slot& S) {
     }
     // the classes are independent: persistent launches on side streams, so that the few long CTAs of the
     // large classes overlap the many short items of the small ones (fork / join with events)
+    CK(cudaStreamWaitEvent(st, c->ev_cov[2], 0));  // the coverage matrix (side stream)
     CK(cudaEventRecord(c->ev_fork, st));
     bool used[FRS_SIDE_STREAMS] = {};
     // FRS_DP_TIMELINE=1 (development): end of every class's launch relative to the fork, printed after the run
@@ -1164,8 +1189,7 @@ static int enqueue_run(frs_context* c, Slot& S) {
   LAUNCHED();
   k_digit_sizes<<<cdiv(T, 256), 256, 0, st>>>(T, d_tint_rep_off, S.b_tint_final_off.as<int>(), c->b_dig_sz.as<i64>());
   LAUNCHED();
-  { int r = scan_exclusive<i64, i64>(c, c->b_dig_sz.as<i64>(), T, S.b_tint_digit_off.as<i64>()); if (r) return r; }
-  dev_copy_word(c, st, d_cnt + CNT_NDIG, S.b_tint_digit_off.as<i64>() + T, 8);
+  { int r = scan_exclusive<i64, i64>(c, c->b_dig_sz.as<i64>(), T, S.b_tint_digit_off.as<i64>(), d_cnt + CNT_NDIG); if (r) return r; }
   k_seg_cuts<<<148 * 4, 256, 0, st>>>(d_nfin, c->b_final_flat.as<int>(), c->b_final_island.as<int>(), d_cut, d_tbl,
                                       prm->thr_table_len, prm->tp, c->b_seg_ty.as<int>(), c->b_seg_tn.as<int>());
   LAUNCHED();
@@ -1182,14 +1206,12 @@ static int enqueue_run(frs_context* c, Slot& S) {
   }
 
   stage_begin(c, "runs");
-  { int r = scan_exclusive<int, int>(c, c->b_run_cnt.as<int>(), NR, c->b_run_off.as<int>()); if (r) return r; }
-  dev_copy_word(c, st, d_cnt + CNT_NRUN, c->b_run_off.as<int>() + NR, 4);
+  { int r = scan_exclusive<int, int>(c, c->b_run_cnt.as<int>(), NR, c->b_run_off.as<int>(), d_cnt + CNT_NRUN); if (r) return r; }
   if (N > 0) {
     k_gap_count<<<cdiv(N, 256), 256, 0, st>>>(N, S.b_read_rep.as<int>(), c->b_run_off.as<int>(), c->b_gap_cnt.as<int>());
     LAUNCHED();
   }
-  { int r = scan_exclusive<int, int>(c, c->b_gap_cnt.as<int>(), N, S.b_read_gap_off.as<int>()); if (r) return r; }
-  dev_copy_word(c, st, d_cnt + CNT_NGAP, S.b_read_gap_off.as<int>() + N, 4);
+  { int r = scan_exclusive<int, int>(c, c->b_gap_cnt.as<int>(), N, S.b_read_gap_off.as<int>(), d_cnt + CNT_NGAP); if (r) return r; }
   if (NR > 0) {
     k_run_fill<<<cdiv((i64)NR * 32, 256), 256, 0, st>>>(NR, S.b_rep_tint.as<int>(), d_tint_rep_off,
                                                         S.b_tint_final_off.as<int>(), S.b_tint_digit_off.as<i64>(),
@@ -1235,8 +1257,7 @@ static int enqueue_run(frs_context* c, Slot& S) {
       stage_begin(c, "clip_fetch", tl);
       // compact offsets of the clips' plane words (total at [2N]), then the words themselves, straight from
       // the caller's pinned planes
-      { int r = scan_exclusive_on<int, i64>(c, tl, S.b_bsum_tail, S.b_clip_words.as<int>(), (i64)N * 2, S.b_clip_off.as<i64>()); if (r) return r; }
-      dev_copy_word(c, tl, d_cnt + CNT_CLIPW, S.b_clip_off.as<i64>() + (i64)N * 2, 8);
+      { int r = scan_exclusive_on<int, i64>(c, tl, S.b_bsum_tail, S.b_clip_words.as<int>(), (i64)N * 2, S.b_clip_off.as<i64>(), d_cnt + CNT_CLIPW); if (r) return r; }
       // a few CTAs only: the kernel waits on the bus (the bus allows a few hundred reads in flight, not tens of
       // thousands), and loads from host memory that are pending for microseconds fill the miss queues of the SM
       // they run on -- the other SMs belong to the head of the next batch meanwhile

@@ -26,8 +26,10 @@ __global__ void __launch_bounds__(COV_THREADS) k_coverage(const RepTile* __restr
                                                          const int* __restrict__ rep_iv_off,
                                                          const int* __restrict__ iv_fs, const int* __restrict__ iv_fe,
                                                          const int* __restrict__ cand_flat, u32* __restrict__ P,
-                                                         const i64* __restrict__ cnt, i64 cap_P) {
-  if (cnt[CNT_COV] > cap_P) return;  // the matrix does not fit its buffer: the host grows it and repeats the run
+                                                         int n_tints, i64 cap_P) {
+  // the matrix does not fit its buffer: the host grows it and repeats the run (the total is read from the scan,
+  // not from the counters: the kernel runs on a side stream before k_plan_finish copies it there)
+  if (tint_cov_off[n_tints] > cap_P) return;
   const RepTile tl = tiles[blockIdx.x];
   const int r0 = tint_rep_off[tl.tint];
   const int R = tint_rep_off[tl.tint + 1] - r0;

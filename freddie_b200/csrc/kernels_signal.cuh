@@ -193,7 +193,8 @@ __device__ double gauss_global(const int* __restrict__ yr, int n, int x, const d
 
 #define TILE_GROUP 1024  // tiles per group of the two-level count prefix
 
-__global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __restrict__ tiles,
+template <int MINB>  // CTAs per SM the register budget is cut for (16 -> 32 registers, 12 -> 40, 10 -> 48)
+__global__ void __launch_bounds__(GAUSS_THREADS, MINB) k_smooth(const TileWork* __restrict__ tiles,
                                                          const int* __restrict__ island_sample_off,
                                                          const int* __restrict__ y_raw,
                                                          const double* __restrict__ gw, int lw,
@@ -219,10 +220,17 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __rest
   const int span_r = (span + GAUSS_THREADS - 1) / GAUSS_THREADS * GAUSS_THREADS;
   const bool interior = first >= 0 && first + span <= n;
   const int n2 = 2 * n;
-  for (int s = tid; s < span_r; s += GAUSS_THREADS) {  // whole warps: the ballot needs every lane
+  for (int s0 = warp * 32; s0 < span_r; s0 += GAUSS_THREADS) {  // whole warps: the ballot needs every lane
+    const int s = s0 + lane;
+    const int j00 = first + s0;
     int v = 0;
-    if (s < span) {
-      const int j0 = first + s;
+    if (j00 >= 0 && j00 + 31 < n && s0 + 31 < span) {
+      // warp-uniform fast path: the 32 samples lie inside the island (most tiles touch an island end, so a
+      // CTA-wide `interior` test sent 94 % of them through the reflect arithmetic below)
+      v = yr[j00 + lane];
+      ext[s] = v;
+    } else if (s < span) {
+      const int j0 = j00 + lane;
       int j = j0;
       if (!interior) {
         // scipy's reflect (d c b a | a b c d | d c b a): one fold covers every island longer than the halo
@@ -238,7 +246,7 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __rest
       ext[s] = v;
     }
     const u32 m = __ballot_sync(0xffffffffu, v != 0);
-    if (lane == 0) nz[s >> 5] = m;
+    if (lane == 0) nz[s0 >> 5] = m;
   }
   if (tid < 2) nz[(span_r >> 5) + tid] = 0u;
   __syncthreads();
@@ -251,27 +259,38 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __rest
     wm = ((unsigned long long)hi32 << 32) | lo32;
   }
   // ---- Gaussian: a warp owns 256 consecutive samples, 32 per step (coalesced 256-byte stores) ----
-  u32 live = 0;  // bit it: step `it` of this warp has a non-zero input near its window (else its y is all 0)
+  // bit it of live: step `it` of this warp has a non-zero input near its window (else its y is all 0).  Lane `it`
+  // tests its step once (64-bit shifts), one ballot hands the eight answers to the warp.
+  u32 live;
+  {
+    bool any = false;
+    const int xb = warp * (TILE_SAMPLES / 4) + lane * 32;
+    if (lane < TILE_WORDS / 4 && xb < cnt) {
+      // inputs of the step: staged samples [xb + 1, xb + 32 + 2*lw]; testing the whole mask words that
+      // hold them is conservative (a false positive only runs the sparse filter over zeros: same bits)
+      const int w_a = (xb + 1) >> 5, w_b = (xb + 32 + 2 * lw) >> 5;  // w_b - w_a <= 14
+      any = ((wm >> w_a) & ((2ull << (w_b - w_a)) - 1ull)) != 0ull;
+    }
+    live = __ballot_sync(0xffffffffu, any);
+  }
   for (int it = 0; it < TILE_WORDS / 4; ++it) {
     const int xb = warp * (TILE_SAMPLES / 4) + it * 32;
     if (xb >= cnt) break;
     const int x = xb + lane;
-    // inputs of this step: staged samples [xb + 1, xb + 32 + 2*lw]; testing the whole mask words that
-    // hold them is conservative (a false positive only runs the sparse filter over zeros: same bits)
-    const int w_a = (xb + 1) >> 5, w_b = (xb + 32 + 2 * lw) >> 5;  // w_b - w_a <= 14
-    const bool any = ((wm >> w_a) & ((2ull << (w_b - w_a)) - 1ull)) != 0ull;
     double v = 0.0;
-    if (any) {
-      live |= 1u << it;
-      if (x < cnt) v = gauss_sparse(ext, nz, wd, lw, lw + 1 + x);
-    }
+    if (((live >> it) & 1u) && x < cnt) v = gauss_sparse(ext, nz, wd, lw, lw + 1 + x);
     if (x < cnt) {
       y[f0 + tw.lo + x] = v;
       yout[1 + x] = v;
     }
   }
-  if (tid == GAUSS_THREADS - 2) yout[0] = gauss_sparse(ext, nz, wd, lw, lw);              // sample lo - 1
-  if (tid == GAUSS_THREADS - 1) yout[cnt + 1] = gauss_sparse(ext, nz, wd, lw, lw + 1 + cnt);  // sample lo + cnt
+  // the neighbours of the tile's first and last sample: only read when the tile does not start / end its island
+  // (an island end is a candidate by rule and never looks at its neighbours)
+  if (tid >= GAUSS_THREADS - 2) {
+    const bool left = tid == GAUSS_THREADS - 2;
+    if (left ? tw.lo > 0 : tw.lo + cnt < n)
+      yout[left ? 0 : cnt + 1] = gauss_sparse(ext, nz, wd, lw, left ? lw : lw + 1 + cnt);
+  }
   __syncthreads();
   // ---- candidates and positives ----
   auto Y = [&](int X) -> double {  // island-local sample, 0 <= X < n
@@ -281,13 +300,26 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __rest
   int nc = 0, np = 0;
   u32* cm_out = cmask + (size_t)blockIdx.x * TILE_WORDS;
   u32* pm_out = pmask + (size_t)blockIdx.x * TILE_WORDS;
-  for (int it = 0; it < TILE_WORDS / 4; ++it) {
+  // dead steps first (the same warp smoothed these samples: a dead step is all zeros): no positives, and only an
+  // island's first / last sample can be a candidate -- lane `it` writes the two words of step `it`, no ballots
+  {
+    const int wi = warp * (TILE_WORDS / 4) + lane;
+    u32 cm = 0u;
+    if (lane < TILE_WORDS / 4 && wi * 32 < cnt && !((live >> lane) & 1u)) {
+      const int X0 = tw.lo + wi * 32, e = n - 1 - X0;
+      cm = (X0 == 0 ? 1u : 0u) | ((unsigned)e < 32u ? 1u << e : 0u);
+      cm_out[wi] = cm;
+      pm_out[wi] = 0u;
+    }
+    nc = __popc(cm);  // summed over the lanes below
+  }
+  for (u32 lv = live; lv; lv &= lv - 1u) {
+    const int it = __ffs(lv) - 1;
     const int wi = warp * (TILE_WORDS / 4) + it;
-    if (wi * 32 >= cnt) break;  // a median island is half a tile: k_tile_lists only reads the words a tile has
     const int x = wi * 32 + lane, X = tw.lo + x;
     bool is_c = false, is_p = false;
-    if (x < cnt) is_c = (X == 0 || X == n - 1);
-    if (((live >> it) & 1u) && x < cnt) {  // the same warp smoothed these samples: a dead step is all zeros
+    if (x < cnt) {
+      is_c = (X == 0 || X == n - 1);
       const double v = yout[1 + x];
       is_p = v > 0.0;
       if (!is_c && is_p) {
@@ -302,11 +334,12 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_smooth(const TileWork* __rest
       }
     }
     const u32 cm = __ballot_sync(0xffffffffu, is_c), pm = __ballot_sync(0xffffffffu, is_p);
-    if (lane == 0) { cm_out[wi] = cm; pm_out[wi] = pm; }
-    nc += __popc(cm);
-    np += __popc(pm);
+    if (lane == 0) { cm_out[wi] = cm; pm_out[wi] = pm; nc += __popc(cm); np += __popc(pm); }
   }
-  if (lane == 0) red[warp] = nc | (np << 16);
+  nc += np << 16;
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) nc += __shfl_xor_sync(0xffffffffu, nc, o);  // lanes 0..7 hold the dead steps' counts
+  if (lane == 0) red[warp] = nc;
   __syncthreads();
   if (tid == 0) {
     const u32 v = (u32)(red[0] + red[1] + red[2] + red[3]);  // candidates | positives << 16

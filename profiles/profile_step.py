@@ -27,7 +27,8 @@ steps = int(os.environ.get("STEPS", "1"))
 tints = synth.make_config({"cfg2": 2, "cfg3": 3, "cfg4": 4}[workload], scale=scale, seed=2, workers=16)
 batch = pack_tints(tints).pin()
 eng = Engine(0)
-eng.set_option(_lib.OPT_LAZY_SEQ, 0)
+if not os.environ.get("E2E"):
+    eng.set_option(_lib.OPT_LAZY_SEQ, 0)
 prm = SegmentParams()
 for _ in range(3):
     eng.segment_batch(batch, prm, pinned=True)
@@ -38,7 +39,10 @@ torch.cuda.synchronize()
 rt = torch.cuda.cudart()
 rt.cudaProfilerStart()
 for _ in range(steps):
-    eng.run(prm)
+    if os.environ.get("E2E"):  # host buffers in, host results out: the prep kernels and the clip fetch are in the list
+        eng.segment_batch(batch, prm, pinned=True)
+    else:
+        eng.run(prm)
 torch.cuda.synchronize()
 rt.cudaProfilerStop()
 print("profiled %d step(s): %d reads, %d launches per step" % (steps, batch.n_reads, eng.launch_count()))
