@@ -781,7 +781,7 @@ static int enqueue_prep(frs_context* c, Slot& S, cudaStream_t st) {
       T, NI, NR, N, S.b_tint_island_off.as<int>(), S.b_tint_rep_off.as<int>(), S.b_tint_read_off.as<int>(),
       S.b_island_tint.as<int>(), S.b_rep_tint.as<int>(), S.b_read_tint.as<int>());
   if (S.prep_derive_riv && N > 0)
-    k_derive_riv<<<cdiv(N, 256), 256, 0, st>>>(N, NI, S.b_read_rep.as<int>(), S.b_read_iv_off.as<int>(),
+    k_derive_riv<<<cdiv((i64)N * 8, 256), 256, 0, st>>>(N, NI, S.b_read_rep.as<int>(), S.b_read_iv_off.as<int>(),
                                                S.b_rep_iv_off.as<int>(), S.b_rep_fs.as<int>(), S.b_rep_fe.as<int>(),
                                                S.b_island_sample_off.as<int>(), S.b_island_start.as<int>(),
                                                S.b_riv_ts.as<int>(), S.b_riv_te.as<int>());
@@ -872,7 +872,7 @@ static int enqueue_run(frs_context* c, Slot& S) {
   ENS(b_vbuf, L * 8);
   ENS(b_tint_pos_off, (size_t)(T + 1) * 4);
   const size_t n_groups = (size_t)S.n_tiles / TILE_GROUP + 1;
-  ENS(b_tile_state, n_groups * 8 + (size_t)S.n_tiles * (2 * TILE_WORDS * 4 + 4) + 64);
+  ENS(b_tile_state, n_groups * 8 + (size_t)S.n_tiles * (8 + 2 * TILE_WORDS * 4 + 4) + 64);
   ENS(b_thr, (size_t)T * 8);
   {
     size_t nh = (size_t)L / 8 + 64 * (size_t)T + 64;  // heap scratch of the giant tints (see k_threshold)
@@ -964,8 +964,29 @@ static int enqueue_run(frs_context* c, Slot& S) {
   }
 
   i64* d_cnt = S.b_counters.as<i64>();
-  dev_zero(c, st, d_cnt, CNT_SLOTS * 8);
   int* d_err = (int*)(d_cnt + CNT_ERR);
+  stage_begin(c, "signal");
+  {
+    // every zero fill of the run in one launch (largest region first: the raw signal), charged to the stage
+    // that needs the largest one
+    ZeroList z;
+    z.n = 0;
+    size_t acc = 0;
+    auto add = [&](void* p, size_t bytes) {
+      if (!bytes) return;
+      acc += (bytes + 15) / 16;  // every buffer has at least 256 bytes of slack behind `bytes`
+      z.p[z.n] = (uint4*)p;
+      z.end16[z.n++] = acc;
+    };
+    add(c->b_yraw.p, (size_t)L * 4);
+    add(c->b_sflag.p, (size_t)L);
+    add(c->b_run_cnt.p, (size_t)std::max(NR, 1) * 4);
+    add(c->b_tile_state.p, n_groups * 8);  // group sums of k_smooth
+    add(d_cnt, CNT_SLOTS * 8);
+    const size_t g = (acc + 255) / 256;
+    k_zero_multi<<<(unsigned)(g < (size_t)c->n_sm * 16 ? g : (size_t)c->n_sm * 16), 256, 0, st>>>(z);
+    LAUNCHED();
+  }
 
   const int* d_tint_island_off = S.b_tint_island_off.as<int>();
   const int* d_tint_rep_off = S.b_tint_rep_off.as<int>();
@@ -973,8 +994,6 @@ static int enqueue_run(frs_context* c, Slot& S) {
   const int* d_island_tint = S.b_island_tint.as<int>();
 
   // ================= phase 1: signal -> smoothed signal -> candidates, threshold =================
-  stage_begin(c, "signal");
-  dev_zero(c, st, c->b_yraw.p, L * 4);
   if (S.n_sig_work > 0) {
     k_signal<<<S.n_sig_work, SIG_THREADS, SIG_BINS * 4, st>>>(S.b_sig_work.as<SigWork>(), S.b_rep_iv_off.as<int>(),
                                                                S.b_rep_weight.as<int>(), S.b_rep_fs.as<int>(),
@@ -992,10 +1011,10 @@ static int enqueue_run(frs_context* c, Slot& S) {
   {
     // group totals | per tile: candidate / positive ballot words, packed counts
     unsigned long long* d_gsum = c->b_tile_state.as<unsigned long long>();
-    u32* d_cmask = (u32*)(d_gsum + n_groups);
+    int2* d_toff = (int2*)(d_gsum + n_groups);  // (candidates, positives) before every tile (k_tile_prefix)
+    u32* d_cmask = (u32*)(d_toff + S.n_tiles);
     u32* d_pmask = d_cmask + (size_t)S.n_tiles * TILE_WORDS;
     u32* d_tcnt = d_pmask + (size_t)S.n_tiles * TILE_WORDS;
-    dev_zero(c, st, d_gsum, n_groups * 8);
     const size_t sm = (size_t)p1_smem_layout(lw).total;
     // FRS_SMOOTH_OCC (dev knob): register budget of k_smooth as CTAs per SM
     static const int occ = [] { const char* e = getenv("FRS_SMOOTH_OCC"); return e ? atoi(e) : 16; }();
@@ -1011,9 +1030,11 @@ static int enqueue_run(frs_context* c, Slot& S) {
 #undef FRS_LAUNCH_SMOOTH
     LAUNCHED();
     stage_begin(c, "lists");
+    k_tile_prefix<<<(unsigned)n_groups, TILE_GROUP, 0, st>>>(S.n_tiles, d_tcnt, d_gsum, d_toff);
+    LAUNCHED();
     k_tile_lists<<<S.n_tiles, GAUSS_THREADS, 0, st>>>(S.b_tiles.as<TileWork>(), S.n_tiles, d_island_sample_off,
                                                        d_island_tint, d_tint_island_off, T, d_cmask, d_pmask, d_tcnt,
-                                                       d_gsum, c->b_y.as<double>(), c->b_cand_flat.as<int>(),
+                                                       d_toff, c->b_y.as<double>(), c->b_cand_flat.as<int>(),
                                                        c->b_vbuf.as<double>(), c->b_tint_pos_off.as<int>(), d_cnt + CNT_K);
     LAUNCHED();
   }
@@ -1165,7 +1186,6 @@ static int enqueue_run(frs_context* c, Slot& S) {
   // ================= phase 3: refine, final positions, digits =================
   if (S.tl[9]) cudaEventRecord(S.tl[9], st);
   stage_begin(c, "refine");
-  dev_zero(c, st, c->b_sflag.p, L);
   int* d_ref_cnt = (int*)(d_cnt + CNT_REF);
   int* d_ref_cnt2 = (int*)(d_cnt + CNT_REF2);
   k_final_mark<<<g_cand, 256, 0, st>>>(d_K, c->b_dpfinal.as<u8>(), c->b_cand_flat.as<int>(),
@@ -1196,7 +1216,6 @@ static int enqueue_run(frs_context* c, Slot& S) {
 
   if (S.tl[10]) cudaEventRecord(S.tl[10], st);
   stage_begin(c, "digits");
-  dev_zero(c, st, c->b_run_cnt.p, (size_t)std::max(NR, 1) * 4);
   if (S.n_dig_tiles > 0) {
     k_digits<<<dim3((unsigned)S.n_dig_tiles, DIG_CHUNKS), DIG_THREADS, 0, st>>>(
         S.b_dig_tiles.as<RepTile>(), d_tint_rep_off, S.b_tint_final_off.as<int>(), S.b_tint_digit_off.as<i64>(),

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(SIG_THREADS) k_signal(const SigWork* __restric
 //   3. per 32 samples one ballot word of candidates and one of positive samples (the input of the
 //      variance threshold, :757-759), plus the two counts of the tile.
 // k_tile_lists then writes the ordered candidate list and the ordered positive samples from the
-// masks (its offsets come from a two-level sum of the tile counts, no device-wide scan).  HBM traffic
+// masks (its offsets: k_tile_prefix, a two-level sum of the tile counts, no device-wide scan).  HBM traffic
 // of the two: 4 B read + 8 B written per sample, 1/4 B of masks, and the positive samples once more.
 // (Tried on B200 and dropped, byte-identical but slower: ordered lists by decoupled look-back inside k_smooth;
 // one persistent launch with a grid barrier between the two phases, 382 us against 263 + 91 us; the same with
@@ -349,37 +349,48 @@ __global__ void __launch_bounds__(GAUSS_THREADS, MINB) k_smooth(const TileWork* 
   }
 }
 
+// (candidates, positives) before every tile: one CTA per group of TILE_GROUP tiles adds the totals of the groups before
+// it (k_smooth's atomics) and scans its own tiles' counts.  k_tile_lists then reads its two offsets with one load; when
+// every tile summed up to TILE_GROUP counts by itself, that prefix was two thirds of its instructions.
+__global__ void __launch_bounds__(TILE_GROUP) k_tile_prefix(int n_tiles, const u32* __restrict__ tile_cnt,
+                                                            const unsigned long long* __restrict__ group_sum,
+                                                            int2* __restrict__ tile_off) {
+  __shared__ i64 sm[40];
+  __shared__ i64 before_sm;
+  const int g = blockIdx.x, tile = g * TILE_GROUP + threadIdx.x;
+  i64 s = 0;
+  for (int k = threadIdx.x; k < g; k += TILE_GROUP) s += (i64)group_sum[k];  // positives << 32 | candidates, no carries
+  i64 tot;
+  block_exclusive_scan<i64>(s, &tot, sm);
+  if (threadIdx.x == 0) before_sm = tot;
+  i64 v = 0;
+  if (tile < n_tiles) {
+    const u32 c = tile_cnt[tile];
+    v = ((i64)(c >> 16) << 32) | (i64)(c & 0xffffu);
+  }
+  const i64 ex = block_exclusive_scan<i64>(v, (i64*)nullptr, sm);  // (its first barrier publishes before_sm)
+  const i64 off = before_sm + ex;
+  if (tile < n_tiles) tile_off[tile] = make_int2((int)(off & 0xffffffffll), (int)(off >> 32));
+}
+
 // Ordered candidate list and ordered positive samples of one tile from its ballot words.  The tile's
-// offsets into the two lists = totals of the tile groups before its group (k_smooth's atomics) + counts
-// of the earlier tiles of its own group: at most (n_tiles / TILE_GROUP + TILE_GROUP) cached loads per
-// CTA instead of a device-wide scan.  Also: per-tint offsets of the positive list and the totals.
+// offsets into the two lists come from k_tile_prefix.  Also: per-tint offsets of the positive list and the totals.
 __global__ void __launch_bounds__(GAUSS_THREADS) k_tile_lists(const TileWork* __restrict__ tiles, int n_tiles,
                                                              const int* __restrict__ island_sample_off,
                                                              const int* __restrict__ island_tint,
                                                              const int* __restrict__ tint_island_off, int n_tints,
                                                              const u32* __restrict__ cmask, const u32* __restrict__ pmask,
                                                              const u32* __restrict__ tile_cnt,
-                                                             const unsigned long long* __restrict__ group_sum,
+                                                             const int2* __restrict__ tile_off,
                                                              const double* __restrict__ y, int* __restrict__ cand_flat,
                                                              double* __restrict__ vbuf, int* __restrict__ tint_pos_off,
                                                              i64* __restrict__ n_cand_out) {
   __shared__ int pre_c[TILE_WORDS], pre_p[TILE_WORDS];
-  __shared__ unsigned long long red[GAUSS_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x;
   const u32* cm_in = cmask + (size_t)tile * TILE_WORDS;
   const u32* pm_in = pmask + (size_t)tile * TILE_WORDS;
-  // ---- (candidates, positives) before this tile ----
-  unsigned long long s = 0;
-  const int g = tile / TILE_GROUP;
-  for (int k = tid; k < g; k += GAUSS_THREADS) s += group_sum[k];
-  for (int k = g * TILE_GROUP + tid; k < tile; k += GAUSS_THREADS) {
-    const u32 v = tile_cnt[k];
-    s += ((unsigned long long)(v >> 16) << 32) | (unsigned long long)(v & 0xffffu);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) red[warp] = s;
+  const int2 off = tile_off[tile];  // (candidates, positives) before this tile (k_tile_prefix)
   const TileWork tw = tiles[tile];
   const int nwords = (min(TILE_SAMPLES, tw.n - tw.lo) + 31) >> 5;  // k_smooth wrote only these
   if (warp == 0) {
@@ -394,8 +405,7 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_tile_lists(const TileWork* __
     pre_p[lane] = p - p0;
   }
   __syncthreads();
-  const unsigned long long before = red[0] + red[1] + red[2] + red[3];
-  const int off_c = (int)(before & 0xffffffffull), off_p = (int)(before >> 32);
+  const int off_c = off.x, off_p = off.y;
   if (tid == 0) {
     if (tw.lo == 0) {
       const int t = island_tint[tw.island];
