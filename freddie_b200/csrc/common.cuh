@@ -10,6 +10,20 @@ typedef unsigned char u8;
 
 #define FRS_NEG_INF (-0x3fffffff)  // "-inf" of the DP (scores fit in 30 bits)
 
+// Programmatic dependent launch (sm_90+): first statement of every kernel.  `wait` holds the grid until the grid
+// before it in the stream has completed and its writes are visible; `launch_dependents` then lets the NEXT kernel of
+// the stream (when it was launched with cudaLaunchAttributeProgrammaticStreamSerialization, see launch_k in frs.cu)
+// become resident as soon as every CTA of this grid has passed that point.  The stream keeps its sequential
+// meaning -- what overlaps is the launch latency and the CTA ramp-up of a kernel with the execution of its
+// predecessor (a run is ~60 short launches).  The order matters: with the trigger BEFORE the wait a grid's grandchild
+// can become resident while the grandparent still runs, and that faulted on B200 (illegal address in the run);
+// wait-then-trigger keeps at most two grids of a stream in flight and is bit-exact on the whole GPU suite.  Both
+// instructions are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;");
+}
+
 // device-side assert channel: first failing code wins
 enum {
   DEVERR_NONE = 0,
@@ -83,6 +97,7 @@ __device__ __forceinline__ void length_cuts(int len, const double* __restrict__ 
 // replaces the fp64 divides in the kernels that need cuts per candidate pair / per segment.
 #define CUT_TAB_N 8192
 __global__ void k_cut_table(const double* __restrict__ tbl, int tbl_len, double tp, int2* __restrict__ cut_tab) {
+  pdl_prologue();
   const int len = blockIdx.x * blockDim.x + threadIdx.x;
   if (len >= CUT_TAB_N) return;
   int ty = 0x7fffffff, tn = -1;
@@ -142,6 +157,7 @@ __device__ __forceinline__ T block_exclusive_scan(T v, T* total_out, T* smem /* 
 template <typename TIn>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_block_sums(const TIn* __restrict__ in, i64 n,
                                                                  i64* __restrict__ bsum) {
+  pdl_prologue();
   __shared__ i64 sm[40];
   i64 base = (i64)blockIdx.x * SCAN_TILE + (i64)threadIdx.x * SCAN_ITEMS;
   i64 s = 0;
@@ -155,6 +171,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_block_sums(const TIn* __r
 
 // single CTA: in-place exclusive scan of bsum[0..nb), total written to bsum[nb]
 __global__ void __launch_bounds__(1024) k_scan_bsums(i64* __restrict__ bsum, int nb) {
+  pdl_prologue();
   __shared__ i64 sm[40];
   __shared__ i64 carry;
   if (threadIdx.x == 0) carry = 0;
@@ -178,6 +195,7 @@ template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const TIn* __restrict__ in, i64 n,
                                                             const i64* __restrict__ bsum, TOut* __restrict__ out,
                                                             i64* __restrict__ total_out /* or NULL */) {
+  pdl_prologue();
   __shared__ i64 sm[40];
   i64 base = (i64)blockIdx.x * SCAN_TILE + (i64)threadIdx.x * SCAN_ITEMS;
   i64 v[SCAN_ITEMS];
@@ -204,6 +222,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const TIn* __restri
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(1024) k_scan_small(const TIn* __restrict__ in, int n, TOut* __restrict__ out,
                                                      i64* __restrict__ total_out /* or NULL */) {
+  pdl_prologue();
   __shared__ i64 sm[40];
   const int per = (n + 1023) / 1024;
   const int i0 = min(n, (int)threadIdx.x * per), i1 = min(n, i0 + per);
@@ -243,6 +262,7 @@ __device__ __forceinline__ u32 flag_bits16(uint4 v) {  // bit k = flag k != 0
   return nzb(v.x) | (nzb(v.y) << 4) | (nzb(v.z) << 8) | (nzb(v.w) << 12);
 }
 __global__ void __launch_bounds__(SCAN_THREADS) k_flag_sums(const u8* __restrict__ flags, i64 n, i64* __restrict__ bsum) {
+  pdl_prologue();
   __shared__ int sm[40];
   const i64 base = (i64)blockIdx.x * FLAG_TILE + (i64)threadIdx.x * FLAG_ITEMS;
   const int s = (base < n) ? __popc(flag_bits16(flag_load16(flags, base, n))) : 0;
@@ -253,6 +273,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_flag_sums(const u8* __restrict
 __global__ void __launch_bounds__(SCAN_THREADS) k_flag_compact(const u8* __restrict__ flags, i64 n,
                                                               const i64* __restrict__ bsum, int* __restrict__ idx_out,
                                                               i64* __restrict__ count_out /* or NULL */) {
+  pdl_prologue();
   __shared__ int sm[40];
   if (count_out && blockIdx.x == 0 && threadIdx.x == 0) *count_out = bsum[gridDim.x];
   const i64 base = (i64)blockIdx.x * FLAG_TILE + (i64)threadIdx.x * FLAG_ITEMS;
@@ -269,6 +290,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_flag_compact(const u8* __restr
 // and the previous one out (a cudaMemsetAsync / device-to-device cudaMemcpyAsync of a run queues behind
 // those transfers: measured, the head of a pipelined run took 2.7 ms instead of 1.9 ms).
 __global__ void k_zero16(uint4* __restrict__ p, size_t n16) {
+  pdl_prologue();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
     p[i] = make_uint4(0u, 0u, 0u, 0u);
 }
@@ -276,6 +298,7 @@ __global__ void k_zero16(uint4* __restrict__ p, size_t n16) {
 // run counts) are all free when the run starts, so they share the large fill's launch instead of paying ~4 us each
 struct ZeroList { uint4* p[6]; size_t end16[6]; int n; };  // end16[k] = running total of 16-byte words up to region k
 __global__ void k_zero_multi(ZeroList z) {
+  pdl_prologue();
   const size_t total = z.end16[z.n - 1];
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int k = 0;
@@ -286,21 +309,25 @@ __global__ void k_zero_multi(ZeroList z) {
 // dst[k] = (i64) value at src[k] for up to 4 scattered words: the totals of scans into the counter block
 struct CopyWords { i64* dst[4]; const void* src[4]; int bytes[4]; int n; };
 __global__ void k_copy_words(CopyWords w) {
+  pdl_prologue();
   const int k = threadIdx.x;
   if (k < w.n) *w.dst[k] = w.bytes[k] == 8 ? *(const i64*)w.src[k] : (i64)*(const int*)w.src[k];
 }
 // final flags of the DP start as the fixed flags (only the candidates that exist)
 __global__ void k_copy_flags(const i64* __restrict__ n_p, const u8* __restrict__ src, u8* __restrict__ dst) {
+  pdl_prologue();
   const i64 n = *n_p;
   for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
 // compact batch encodings -> the arrays the kernels read (frs_batch.cigar16 / riv_cig_n / qe_from_cigar)
 __global__ void k_widen_u16(const unsigned short* __restrict__ in, i64 n, u32* __restrict__ out) {
+  pdl_prologue();
   for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) out[i] = in[i];
 }
 __global__ void k_derive_qe(i64 n_ivs, const int* __restrict__ qs, const int* __restrict__ cig_off,
                             const u32* __restrict__ cigar, int* __restrict__ qe) {
+  pdl_prologue();
   for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < n_ivs; k += (i64)gridDim.x * blockDim.x) {
     int q = qs[k];
     for (int c = cig_off[k]; c < cig_off[k + 1]; ++c) {
@@ -333,6 +360,7 @@ __device__ __forceinline__ int upper_row64(const i64* __restrict__ off, int n, i
 __global__ void k_owner_tables(int T, int n_islands, int n_reps, int n_reads, const int* __restrict__ tint_island_off,
                                const int* __restrict__ tint_rep_off, const int* __restrict__ tint_read_off,
                                int* __restrict__ island_tint, int* __restrict__ rep_tint, int* __restrict__ read_tint) {
+  pdl_prologue();
   long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < n_islands) { island_tint[e] = upper_row(tint_island_off, T, (int)e); return; }
   e -= n_islands;
@@ -350,6 +378,7 @@ __global__ void k_derive_riv(int n_reads, int n_islands, const int* __restrict__
                              const int* __restrict__ rep_iv_off, const int* __restrict__ rep_fs, const int* __restrict__ rep_fe,
                              const int* __restrict__ island_sample_off, const int* __restrict__ island_start,
                              int* __restrict__ riv_ts, int* __restrict__ riv_te) {
+  pdl_prologue();
   const int g = threadIdx.x & 7;
   const int r = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3);
   if (r >= n_reads) return;

@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(COV_THREADS) k_coverage(const RepTile* __restr
                                                          const int* __restrict__ iv_fs, const int* __restrict__ iv_fe,
                                                          const int* __restrict__ cand_flat, u32* __restrict__ P,
                                                          int n_tints, i64 cap_P) {
+  pdl_prologue();
   // the matrix does not fit its buffer: the host grows it and repeats the run (the total is read from the scan,
   // not from the counters: the kernel runs on a side stream before k_plan_finish copies it there)
   if (tint_cov_off[n_tints] > cap_P) return;
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(COV_THREADS) k_coverage(const RepTile* __restr
 __global__ void k_tint_cov_sizes(int T, const int* __restrict__ tint_island_off, const int* __restrict__ island_cand_off,
                                  const int* __restrict__ tint_rep_off, int* __restrict__ tint_cand_off,
                                  i64* __restrict__ cov_sz) {
+  pdl_prologue();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t > T) return;
   int q = island_cand_off[tint_island_off[t]];
@@ -86,6 +88,7 @@ __global__ void k_fixed_a(const i64* __restrict__ n_cand_p, const int* __restric
                           const int* __restrict__ island_cand_off, const int* __restrict__ island_tint,
                           const double* __restrict__ y, const double* __restrict__ thr, u8* __restrict__ fixed0,
                           u8* __restrict__ fixed1) {
+  pdl_prologue();
   const int n_cand = (int)*n_cand_p;
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_cand; q += gridDim.x * blockDim.x) {
     int isl = cand_island[q];
@@ -99,6 +102,7 @@ __global__ void k_fixed_a(const i64* __restrict__ n_cand_p, const int* __restric
 __global__ void k_fixed_b(const i64* __restrict__ n_cand_p, const int* __restrict__ cand_flat, const int* __restrict__ cand_island,
                           const int* __restrict__ island_cand_off, const double* __restrict__ y, int mps,
                           const u8* __restrict__ fixed0, u8* __restrict__ fixed1, int* __restrict__ err) {
+  pdl_prologue();
   const int n_cand = (int)*n_cand_p;
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_cand; q += gridDim.x * blockDim.x) {
     if (!fixed0[q]) continue;
@@ -216,6 +220,7 @@ __global__ void k_sub_build(const i64* __restrict__ n_cand_p, const u8* __restri
                             int warp_max_words, int keep_tables, int* __restrict__ sub_start, int* __restrict__ sub_n,
                             int* __restrict__ sub_tint, int* __restrict__ sub_info, int* __restrict__ sub_slabs,
                             i64* __restrict__ sub_tab_off, i64* __restrict__ plan, int* __restrict__ err) {
+  pdl_prologue();
   const int n_cand = (int)*n_cand_p;
   const int lane = threadIdx.x & 31;
   // CTA-uniform trip count: every lane of a warp reaches the ballots
@@ -297,6 +302,7 @@ __global__ void k_sub_build(const i64* __restrict__ n_cand_p, const u8* __restri
 __global__ void k_plan_finish(i64* __restrict__ cnt, const i64* __restrict__ tint_cov_off, int n_tints,
                               int* __restrict__ bases /* [16 + DP_CLASSES * DP_BUCKETS]: classes, then (class, bucket) */,
                               int* __restrict__ cursor /* [16 + DP_CLASSES * DP_BUCKETS] */) {
+  pdl_prologue();
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     i64 acc = 0;
     for (int k = 0; k < DP_CLASSES; ++k) {
@@ -323,6 +329,7 @@ __device__ __forceinline__ bool dp_caps_ok(const i64* __restrict__ cnt, const Ca
 __global__ void k_sub_fill(const i64* __restrict__ cnt, Caps caps, const int* __restrict__ sub_info,
                            const int* __restrict__ sub_slabs, const int* __restrict__ bases, int* __restrict__ cursor,
                            DpWork* __restrict__ work, int* __restrict__ split_list) {
+  pdl_prologue();
   if (!dp_caps_ok(cnt, caps)) return;
   const int n_sub = (int)cnt[CNT_PLAN + PLAN_NSUB];
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_sub; p += gridDim.x * blockDim.x) {
@@ -337,6 +344,7 @@ __global__ void k_sub_fill(const i64* __restrict__ cnt, Caps caps, const int* __
 
 // zeroes the global DP tables of the run (their size is only known on the device)
 __global__ void k_zero_tab(const i64* __restrict__ cnt, Caps caps, int* __restrict__ tab) {
+  pdl_prologue();
   if (!dp_caps_ok(cnt, caps)) return;
   const i64 n = cnt[CNT_PLAN + PLAN_TAB];
   for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (i64)gridDim.x * blockDim.x) tab[e] = 0;
@@ -674,6 +682,7 @@ __device__ __forceinline__ void dp_triple_phase(const int n, const int nw, const
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 128 ? 6 : THREADS == 256 ? 3 : 1)) k_dp(DpArgs A, const DpWork* __restrict__ work_all,
                                                 int cls, int smem_bytes) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char dsm[];
   __shared__ int s_n_munit, s_item, s_nq, s_wfull, s_wdead, s_last;
   if (!dp_caps_ok(A.cnt, A.caps)) return;
@@ -987,6 +996,7 @@ struct DpWarpSmem {
 
 template <int MAXN>
 __global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWork* __restrict__ work_all, int cls) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char dsm[];
   __shared__ uchar2 s_ji[(MAXN - 1) * (MAXN - 2) / 2];  // (middle j, left i) of every lane slot of the triple phase
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1165,6 +1175,7 @@ __global__ void __launch_bounds__(DPW_WARPS * 32) k_dp_warp(DpArgs A, const DpWo
 #define DPS_THREADS 256
 __global__ void __launch_bounds__(DPS_THREADS) k_dp_solve(DpArgs A, const int* __restrict__ split_list, int max_n,
                                                           int stage_max_n) {
+  pdl_prologue();
   extern __shared__ __align__(16) int ssm[];
   __shared__ int s_item;
   if (!dp_caps_ok(A.cnt, A.caps)) return;

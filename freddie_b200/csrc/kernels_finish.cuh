@@ -11,6 +11,7 @@
 __global__ void k_final_mark(const i64* __restrict__ n_cand_p, const u8* __restrict__ dpfinal, const int* __restrict__ cand_flat,
                              const int* __restrict__ cand_island, const int* __restrict__ island_cand_off,
                              u8* __restrict__ sflag, int2* __restrict__ ref_list, int* __restrict__ ref_cnt) {
+  pdl_prologue();
   const int n_cand = (int)*n_cand_p;
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_cand; q += gridDim.x * blockDim.x) {
     if (!dpfinal[q]) continue;
@@ -42,6 +43,7 @@ __global__ void k_final_mark(const i64* __restrict__ n_cand_p, const u8* __restr
 // list of stage B (one CTA per segment).
 __global__ void k_refine_filter(const int2* __restrict__ in_list, const int* __restrict__ in_cnt,
                                 const int* __restrict__ y_raw, int2* __restrict__ out_list, int* __restrict__ out_cnt) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int nw = (gridDim.x * blockDim.x) >> 5;
   const int n = *in_cnt;
@@ -152,6 +154,7 @@ __global__ void __launch_bounds__(REF_THREADS) k_refine(const int2* __restrict__
                                                        const int* __restrict__ y_raw, const double* __restrict__ rw,
                                                        int rad, double sigma, double* __restrict__ gbuf,
                                                        u8* __restrict__ pstate, u8* __restrict__ sflag) {
+  pdl_prologue();
   __shared__ int sm_red[REF_THREADS / 32];
   __shared__ int sm_flag;
   const int n_work = *ref_cnt;
@@ -167,6 +170,7 @@ __global__ void k_final_meta(const i64* __restrict__ n_final_p, const int* __res
                              const int* __restrict__ island_tint, const int* __restrict__ tint_island_off, int n_islands,
                              int n_tints, int* __restrict__ final_pos, int* __restrict__ final_island,
                              int* __restrict__ tint_final_off) {
+  pdl_prologue();
   const int n_final = (int)*n_final_p;  // device-side count: no host round trip before this launch
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e <= n_final; e += gridDim.x * blockDim.x) {
     if (e == n_final) { tint_final_off[n_tints] = n_final; break; }
@@ -182,6 +186,7 @@ __global__ void k_final_meta(const i64* __restrict__ n_final_p, const int* __res
 // per tint: digit block size = n_reps * (n_final - 1)
 __global__ void k_digit_sizes(int n_tints, const int* __restrict__ tint_rep_off, const int* __restrict__ tint_final_off,
                               i64* __restrict__ sz) {
+  pdl_prologue();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tints) return;
   i64 S = tint_final_off[t + 1] - tint_final_off[t] - 1;
@@ -193,6 +198,7 @@ __global__ void k_seg_cuts(const i64* __restrict__ n_final_p, const int* __restr
                            const int* __restrict__ final_island, const int2* __restrict__ cut_tab,
                            const double* __restrict__ tbl, int tbl_len, double tp,
                            int* __restrict__ seg_ty, int* __restrict__ seg_tn) {
+  pdl_prologue();
   const int n_final = (int)*n_final_p;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_final; e += gridDim.x * blockDim.x) {
     int ty = 0x7fffffff, tn = -2;  // tn == -2 marks "no segment" (island separator or tint end)
@@ -237,6 +243,7 @@ __global__ void __launch_bounds__(DIG_THREADS) k_digits(const RepTile* __restric
                                                        const int* __restrict__ seg_ty, const int* __restrict__ seg_tn,
                                                        u8* __restrict__ digits, int* __restrict__ run_cnt /* zeroed */,
                                                        int* __restrict__ err, const i64* __restrict__ cnt, Caps caps) {
+  pdl_prologue();
   __shared__ u8 tile[DIG_THREADS][DIG_SEGS + 1];
   if (!digits_fit(cnt, caps)) return;
   const RepTile tl = tiles[blockIdx.x];
@@ -317,6 +324,7 @@ __global__ void k_run_fill(int n_reps, const int* __restrict__ rep_tint, const i
                            const int* __restrict__ tint_final_off, const i64* __restrict__ tint_digit_off,
                            const u8* __restrict__ digits, const int* __restrict__ run_off, int2* __restrict__ runs,
                            const i64* __restrict__ cnt, Caps caps) {
+  pdl_prologue();
   int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (r >= n_reps || !runs_fit(cnt, caps)) return;
@@ -346,6 +354,7 @@ __global__ void k_run_fill(int n_reps, const int* __restrict__ rep_tint, const i
 
 __global__ void k_gap_count(int n_reads, const int* __restrict__ read_rep, const int* __restrict__ run_off,
                             int* __restrict__ gap_cnt) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_reads) return;
   int r = read_rep[i];
@@ -485,6 +494,7 @@ __host__ __device__ __forceinline__ ClipGeo clip_geometry(int L, int n, bool is_
 // clip bounds by CIGAR threading, unaligned gaps between consecutive 1-runs, and the scan tasks.
 // head[3] = q_ssc and head[6] = q_esc are provisional; k_gap_finish rewrites them.
 __global__ void __launch_bounds__(128) k_gap_prep(GapArgs A) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < A.n_reads && gaps_fit(A.cnt, A.caps)) {
     int* head = A.read_head + (i64)i * 8;
@@ -539,6 +549,7 @@ __global__ void __launch_bounds__(128) k_gap_prep(GapArgs A) {
 
 // K11a': one thread per unaligned-gap record: "{l1}-{f2}:{size}" (:455-471)
 __global__ void k_gap_sizes(GapArgs A) {
+  pdl_prologue();
   if (!gaps_fit(A.cnt, A.caps)) return;
   const int n_gaps = (int)A.cnt[CNT_NGAP];  // device-side count: the launch is a grid-stride loop
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n_gaps; g += gridDim.x * blockDim.x) {
@@ -566,6 +577,7 @@ __global__ void k_gap_sizes(GapArgs A) {
 // planes), so the requests coalesce into whole sectors.  No host round trip, no host gather.
 __global__ void __launch_bounds__(256) k_clip_gather(GapArgs A, const u32* __restrict__ host_a, const u32* __restrict__ host_t,
                                                      u32* __restrict__ out_a, u32* __restrict__ out_t) {
+  pdl_prologue();
   if (!clips_fit(A.cnt, A.caps)) return;
   const i64 total = A.cnt[CNT_CLIPW];
   const int n_clip = A.n_reads * 2;
@@ -586,6 +598,7 @@ __global__ void __launch_bounds__(256) k_clip_gather(GapArgs A, const u32* __res
 // clips of random sequence).  The test is word-parallel: v & v>>1 & v>>2 & v>>3 & v>>4 over the
 // plane words, carried across word boundaries.  Survivors are counted per length class.
 __global__ void __launch_bounds__(128) k_poly_filter(GapArgs A, u8* __restrict__ pass_flag) {
+  pdl_prologue();
   __shared__ int sh_cnt[POLY_CLASSES];
   for (int k = threadIdx.x; k < POLY_CLASSES; k += blockDim.x) sh_cnt[k] = 0;
   __syncthreads();
@@ -627,6 +640,7 @@ __global__ void __launch_bounds__(128) k_poly_filter(GapArgs A, u8* __restrict__
 
 // one warp: class bases, LONGEST class first; cls_count[c] becomes the base, cursors start at 0
 __global__ void k_poly_bases(int* __restrict__ cls_count, int long_class, int* __restrict__ stat /* [2] */) {
+  pdl_prologue();
   if (threadIdx.x == 0) {
     int acc = 0;
     for (int c = POLY_CLASSES - 1; c >= 0; --c) { int v = cls_count[c]; cls_count[c] = acc; acc += v; }
@@ -638,6 +652,7 @@ __global__ void k_poly_bases(int* __restrict__ cls_count, int long_class, int* _
 
 __global__ void k_poly_scatter(int n_slots, const int* __restrict__ clip_n, const u8* __restrict__ pass_flag,
                                int* __restrict__ cls_count, int* __restrict__ order, const i64* __restrict__ cnt, Caps caps) {
+  pdl_prologue();
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_slots || !clips_fit(cnt, caps) || !pass_flag[s]) return;
   int c = poly_class_dev(clip_n[s >> 1]);
@@ -652,6 +667,7 @@ __global__ void k_poly_scatter(int n_slots, const int* __restrict__ clip_n, cons
 
 // K11b: one thread per scan task (clips shorter than 1024 bases)
 __global__ void __launch_bounds__(128) k_poly_scan(GapArgs A) {
+  pdl_prologue();
   // tasks of the long classes (front of the order) belong to k_poly_long
   const int e = A.cls_count[A.long_class - 1] + blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= A.cls_count[2 * POLY_CLASSES] || !clips_fit(A.cnt, A.caps)) return;
@@ -741,6 +757,7 @@ __device__ __forceinline__ void poly_offer(PolyRes& best, int i0, int pk, int pk
 }
 
 __global__ void __launch_bounds__(128) k_poly_long(GapArgs A) {
+  pdl_prologue();
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -826,6 +843,7 @@ __global__ void __launch_bounds__(128) k_poly_long(GapArgs A) {
 // K11c: per read, pick the poly candidates (A offered before T, first maximum of p wins, :392-408)
 // and write the final head fields (:407-420, :438-454).
 __global__ void k_gap_finish(GapArgs A) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n_reads || !clips_fit(A.cnt, A.caps)) return;
   int* head = A.read_head + (i64)i * 8;

@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(SIG_THREADS) k_signal(const SigWork* __restric
                                                        const int* __restrict__ rep_weight,
                                                        const int* __restrict__ iv_fs, const int* __restrict__ iv_fe,
                                                        int ignore_ends, int* __restrict__ y_raw) {
+  pdl_prologue();
   extern __shared__ int hist[];  // SIG_BINS ints (dynamic: above the 48 KB static limit)
   const SigWork wk = work[blockIdx.x];
   const int nb = wk.win_hi - wk.win_lo;
@@ -201,6 +202,7 @@ __global__ void __launch_bounds__(GAUSS_THREADS, MINB) k_smooth(const TileWork* 
                                                          double* __restrict__ y, u32* __restrict__ cmask,
                                                          u32* __restrict__ pmask, u32* __restrict__ tile_cnt,
                                                          unsigned long long* __restrict__ group_sum /* zeroed */) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char p1sm[];
   const P1Smem Lo = p1_smem_layout(lw);
   double* wd = (double*)(p1sm + Lo.wd);
@@ -355,6 +357,7 @@ __global__ void __launch_bounds__(GAUSS_THREADS, MINB) k_smooth(const TileWork* 
 __global__ void __launch_bounds__(TILE_GROUP) k_tile_prefix(int n_tiles, const u32* __restrict__ tile_cnt,
                                                             const unsigned long long* __restrict__ group_sum,
                                                             int2* __restrict__ tile_off) {
+  pdl_prologue();
   __shared__ i64 sm[40];
   __shared__ i64 before_sm;
   const int g = blockIdx.x, tile = g * TILE_GROUP + threadIdx.x;
@@ -385,6 +388,7 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_tile_lists(const TileWork* __
                                                              const double* __restrict__ y, int* __restrict__ cand_flat,
                                                              double* __restrict__ vbuf, int* __restrict__ tint_pos_off,
                                                              i64* __restrict__ n_cand_out) {
+  pdl_prologue();
   __shared__ int pre_c[TILE_WORDS], pre_p[TILE_WORDS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x;
@@ -434,6 +438,7 @@ __global__ void __launch_bounds__(GAUSS_THREADS) k_tile_lists(const TileWork* __
 __global__ void k_cand_meta(const int* __restrict__ cand_flat, const i64* __restrict__ n_cand_p,
                             const int* __restrict__ island_sample_off, int n_islands, int* __restrict__ cand_island,
                             int* __restrict__ island_cand_off) {
+  pdl_prologue();
   const int n_cand = (int)*n_cand_p;
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q <= n_cand; q += gridDim.x * blockDim.x) {
     if (q == n_cand) { island_cand_off[n_islands] = n_cand; break; }
@@ -540,6 +545,7 @@ __global__ void __launch_bounds__(THR_THREADS) k_threshold(const int* __restrict
                                                           const int* __restrict__ tint_pos_off, double vf,
                                                           const double* __restrict__ vbuf, int* __restrict__ heap_len,
                                                           double* __restrict__ heap_val, double* __restrict__ thr) {
+  pdl_prologue();
   __shared__ int s_len[THR_HEAP_SMEM];
   __shared__ double s_val[THR_HEAP_SMEM];
   const int t = tint_order[blockIdx.x];  // largest tints first: the longest CTA must not start last
