@@ -296,15 +296,14 @@ __global__ void k_zero16(uint4* __restrict__ p, size_t n16) {
 }
 // several zero fills in ONE launch: the buffers a run needs zeroed (counters, raw signal, group sums, refine flags,
 // run counts) are all free when the run starts, so they share the large fill's launch instead of paying ~4 us each
-struct ZeroList { uint4* p[6]; size_t end16[6]; int n; };  // end16[k] = running total of 16-byte words up to region k
+struct ZeroList { uint4* p[6]; size_t n16[6]; int n; };  // n16[k] = 16-byte words of region k
 __global__ void k_zero_multi(ZeroList z) {
   pdl_prologue();
-  const size_t total = z.end16[z.n - 1];
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    int k = 0;
-    while (i >= z.end16[k]) ++k;
-    z.p[k][i - (k ? z.end16[k - 1] : 0)] = make_uint4(0u, 0u, 0u, 0u);
-  }
+  const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+#pragma unroll  // constant indices: the list stays in the parameter bank (a runtime index copies it to local memory)
+  for (int k = 0; k < 6; ++k)
+    if (k < z.n)
+      for (size_t i = t0; i < z.n16[k]; i += stride) z.p[k][i] = make_uint4(0u, 0u, 0u, 0u);
 }
 // dst[k] = (i64) value at src[k] for up to 4 scattered words: the totals of scans into the counter block
 struct CopyWords { i64* dst[4]; const void* src[4]; int bytes[4]; int n; };

@@ -1018,9 +1018,10 @@ static int enqueue_run(frs_context* c, Slot& S) {
     size_t acc = 0;
     auto add = [&](void* p, size_t bytes) {
       if (!bytes) return;
-      acc += (bytes + 15) / 16;  // every buffer has at least 256 bytes of slack behind `bytes`
+      const size_t n16 = (bytes + 15) / 16;  // every buffer has at least 256 bytes of slack behind `bytes`
+      acc = std::max(acc, n16);
       z.p[z.n] = (uint4*)p;
-      z.end16[z.n++] = acc;
+      z.n16[z.n++] = n16;
     };
     add(c->b_yraw.p, (size_t)L * 4);
     add(c->b_sflag.p, (size_t)L);

@@ -12,8 +12,8 @@ import json
 import sys
 
 STAGE = [  # first match wins
-    ("k_signal", "signal"), ("k_smooth", "smooth"), ("k_tile_lists", "lists"), ("k_threshold", "threshold"),
-    ("k_cand_meta", "fixed"), ("k_fixed", "fixed"), ("k_sub_build", "subproblems"), ("k_tint_cov", "subproblems"),
+    ("k_zero_multi", "signal"), ("k_signal", "signal"), ("k_smooth", "smooth"), ("k_tile_prefix", "lists"), ("k_tile_lists", "lists"), ("k_threshold", "threshold"),
+    ("k_cand_meta", "cand_meta"), ("k_fixed", "fixed"), ("k_sub_build", "subproblems"), ("k_tint_cov", "coverage"),
     ("k_coverage", "coverage"), ("k_sub_fill", "dp_plan"), ("k_dp_solve", "dp_solve"), ("k_dp", "dp"),
     ("k_final_mark", "refine"), ("k_refine", "refine"), ("k_flag_", "finals"), ("k_final_meta", "finals"), ("k_digit_sizes", "finals"),
     ("k_seg_cuts", "finals"), ("k_digits", "digits"), ("k_gap_count", "runs"), ("k_run_fill", "runs"),
