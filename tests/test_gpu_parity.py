@@ -61,6 +61,21 @@ def test_cli_directory_equals_reference_manifest(name, golden_set, manifest, tmp
     assert sha_dir(out) == manifest[name]["outputs"]
 
 
+@pytest.mark.parametrize("mode", ["0", "2"])
+@pytest.mark.parametrize("name", ["cfg2_small", "cfg4_mini", "dup_heavy"])
+def test_cli_equals_reference_manifest_in_every_launch_mode(name, mode, golden_set, manifest, tmp_path):
+    """Programmatic dependent launch never (FRS_PDL=0) and always (FRS_PDL=2, also with several batches in
+    flight) must give the bytes of the default policy, i.e. the reference's: the launch attribute only moves
+    WHEN a kernel becomes resident, never what it reads."""
+    _, flags, split_dir = golden_set(name)
+    out = str(tmp_path / "seg")
+    env = dict(os.environ, FRS_PDL=mode)
+    r = subprocess.run([sys.executable, "-m", "freddie_b200.segment", "-s", split_dir, "-o", out, "-t", "4"] + flags,
+                       cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert sha_dir(out) == manifest[name]["outputs"]
+
+
 def test_cfg1_taps_equal_reference_intermediates(golden_set, eng):
     """Per-step taps against the intermediates dumped from the reference's own functions."""
     from freddie_b200 import _lib
