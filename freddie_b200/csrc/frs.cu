@@ -1308,7 +1308,7 @@ static int enqueue_run(frs_context* c, Slot& S) {
     G.edge = S.edge_words ? S.b_seq_edge.as<u32>() : nullptr;
     G.edge_words = S.edge_words;
     G.clip_eoff = S.edge_words ? S.b_clip_eoff.as<int>() : nullptr;
-    launch_k(k_gap_prep, cdiv(N, 128), 128, 0, st, G); LAUNCHED();
+    launch_k(k_gap_prep, cdiv((i64)N * 2, 128), 128, 0, st, G); LAUNCHED();
     launch_k(k_gap_sizes, gs_grid((i64)N * 2, 128, 148 * 8), 128, 0, st, G); LAUNCHED();
     stage_end(c);
     // ---- TAIL of the run, on its own stream: it touches only buffers of this slot, so the head of the next

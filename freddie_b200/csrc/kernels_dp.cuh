@@ -303,19 +303,45 @@ __global__ void k_plan_finish(i64* __restrict__ cnt, const i64* __restrict__ tin
                               int* __restrict__ bases /* [16 + DP_CLASSES * DP_BUCKETS]: classes, then (class, bucket) */,
                               int* __restrict__ cursor /* [16 + DP_CLASSES * DP_BUCKETS] */) {
   pdl_prologue();
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    i64 acc = 0;
-    for (int k = 0; k < DP_CLASSES; ++k) {
-      bases[k] = (int)(acc < 0x7fffffffLL ? acc : 0x7fffffffLL);
-      for (int b = DP_BUCKETS - 1; b >= 0; --b) {  // heaviest bucket first
-        bases[16 + k * DP_BUCKETS + b] = (int)(acc < 0x7fffffffLL ? acc : 0x7fffffffLL);
-        acc += cnt[CNT_BUCKET + k * DP_BUCKETS + b];
-      }
-    }
-    cnt[CNT_NWORK] = acc;
-    cnt[CNT_COV] = tint_cov_off[n_tints];
-    for (int k = 0; k < 16 + DP_CLASSES * DP_BUCKETS; ++k) cursor[k] = 0;
+  // one warp (launched <<<1, 32>>>): exclusive prefix of the (class, bucket) counts in list order -- class by class,
+  // heaviest bucket first -- with the loads of all entries in flight together (one thread walking the 48 counters
+  // was a chain of dependent loads: 8 us)
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  constexpr int NE = DP_CLASSES * DP_BUCKETS, NJ = (NE + 31) / 32;
+  i64 v[NJ], ex[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int e = lane + 32 * j;  // list position: class e / DP_BUCKETS, bucket DP_BUCKETS - 1 - e % DP_BUCKETS
+    v[j] = e < NE ? cnt[CNT_BUCKET + (e / DP_BUCKETS) * DP_BUCKETS + (DP_BUCKETS - 1 - e % DP_BUCKETS)] : 0;
   }
+  i64 carry = 0;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    i64 x = v[j];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const i64 y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    ex[j] = carry + x - v[j];
+    carry += __shfl_sync(0xffffffffu, x, 31);
+  }
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int e = lane + 32 * j;
+    if (e < NE) {
+      const int k = e / DP_BUCKETS, b = DP_BUCKETS - 1 - e % DP_BUCKETS;
+      const int base = (int)(ex[j] < 0x7fffffffLL ? ex[j] : 0x7fffffffLL);
+      bases[16 + k * DP_BUCKETS + b] = base;
+      if (b == DP_BUCKETS - 1) bases[k] = base;  // a class starts with its heaviest bucket
+    }
+  }
+  if (lane == 0) {
+    cnt[CNT_NWORK] = carry;
+    cnt[CNT_COV] = tint_cov_off[n_tints];
+  }
+  for (int k = lane; k < 16 + NE; k += 32) cursor[k] = 0;
 }
 
 // every data-dependent buffer of the DP stage fits its capacity (else the stage is skipped and repeated)
@@ -332,11 +358,28 @@ __global__ void k_sub_fill(const i64* __restrict__ cnt, Caps caps, const int* __
   pdl_prologue();
   if (!dp_caps_ok(cnt, caps)) return;
   const int n_sub = (int)cnt[CNT_PLAN + PLAN_NSUB];
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_sub; p += gridDim.x * blockDim.x) {
-    const int info = sub_info[p];
-    const int cls = info & 0xff, slabs = sub_slabs[p];
-    const int key = 16 + cls * DP_BUCKETS + ((info >> 12) & 7);
-    int off = bases[key] + atomicAdd(&cursor[key], slabs);
+  const int lane = threadIdx.x & 31;
+  // warp-uniform loop; the single-slab items of a warp that share a (class, bucket) key bump its cursor with ONE
+  // atomic (32 k atomics on ~48 addresses serialised in L2: 25 us for 0.2 M instructions); multi-slab items keep
+  // their own (a unique match key)
+  for (int p0 = blockIdx.x * blockDim.x + threadIdx.x - lane; p0 < n_sub; p0 += gridDim.x * blockDim.x) {
+    const int p = p0 + lane;
+    const bool valid = p < n_sub;
+    int info = 0, cls = 0, slabs = 0, key = 0;
+    if (valid) {
+      info = sub_info[p];
+      cls = info & 0xff;
+      slabs = sub_slabs[p];
+      key = 16 + cls * DP_BUCKETS + ((info >> 12) & 7);
+    }
+    const bool single = valid && slabs == 1;
+    const unsigned peers = __match_any_sync(0xffffffffu, single ? key : -1 - lane);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (valid && lane == leader) base = atomicAdd(&cursor[key], single ? __popc(peers) : slabs);
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!valid) continue;
+    const int off = bases[key] + base + (single ? __popc(peers & ((1u << lane) - 1u)) : 0);
     for (int s = 0; s < slabs; ++s) work[off + s] = DpWork{p, s};
     if (!((info >> 8) & 1) && cls == DP_CLASSES - 1) split_list[atomicAdd(&cursor[DP_CLASSES], 1)] = p;
   }

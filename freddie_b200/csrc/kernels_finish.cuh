@@ -495,56 +495,63 @@ __host__ __device__ __forceinline__ ClipGeo clip_geometry(int L, int n, bool is_
 // head[3] = q_ssc and head[6] = q_esc are provisional; k_gap_finish rewrites them.
 __global__ void __launch_bounds__(128) k_gap_prep(GapArgs A) {
   pdl_prologue();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < A.n_reads && gaps_fit(A.cnt, A.caps)) {
-    int* head = A.read_head + (i64)i * 8;
-    for (int k = 0; k < 8; ++k) head[k] = 0;
-    int* cn = A.clip_n + (i64)i * 2;
-    int* cw = A.clip_words + (i64)i * 2;
-    cn[0] = cn[1] = 0;
-    cw[0] = cw[1] = 0;
+  // two lanes per read: lane 0 threads the CIGAR to the start of the first 1-run, lane 1 to the end of the last one
+  // (two independent chains of dependent loads), each then owns its side's clip and half of the gap records
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = gt >> 1, side = gt & 1;
+  const bool act = i < A.n_reads && gaps_fit(A.cnt, A.caps);
+  int q = 0, L = 0, ra = 0, rb = 0;
+  bool ok = true, has = false;
+  if (act) {
+    int* head = A.read_head + (i64)i * 8 + side * 4;
+    head[0] = head[1] = head[2] = head[3] = 0;
+    A.clip_n[(i64)i * 2 + side] = 0;
+    A.clip_words[(i64)i * 2 + side] = 0;
     const int rep = A.read_rep[i];
-    const int ra = A.run_off[rep], rb = A.run_off[rep + 1];
-    if (ra != rb) {  // else: no '1' digit, empty gaps (:372)
+    ra = A.run_off[rep];
+    rb = A.run_off[rep + 1];
+    has = ra != rb;  // else: no '1' digit, empty gaps (:372)
+    if (has) {
       const int t = A.read_tint[i];
       const int* fpos = A.final_pos + A.tint_final_off[t];  // segs[s] = (fpos[s], fpos[s+1])
       const int i0 = A.read_iv_off[i], i1 = A.read_iv_off[i + 1];
-      const int L = A.read_len[i];
-      int q_ssc = 0, q_esc = 0, slack;
-      bool ok = true;
-      if (!interval_start(A, i0, i1, fpos[A.runs[ra].x], q_ssc, slack)) { dev_fail(A.err, DEVERR_THREAD_CIGAR, i); ok = false; }
-      if (ok && !interval_end(A, i0, i1, fpos[A.runs[rb - 1].y + 1], q_esc, slack)) { dev_fail(A.err, DEVERR_THREAD_CIGAR, i); ok = false; }
-      if (ok && !(0 <= q_ssc && q_ssc <= q_esc && q_esc <= L)) { dev_fail(A.err, DEVERR_Q_RANGE, i); ok = false; }
-      if (ok) {
-        head[0] = 1;
-        head[3] = q_ssc;
-        head[6] = q_esc;
-        const int ns = q_ssc, ne = L - q_esc;
-        const bool minus = A.read_strand[i] != 0;
-        const int nwr = (L + 31) >> 5;  // plane words of the read
-        for (int side = 0; side < 2; ++side) {  // 0: start clip, 1: end clip
-          const int nb = side == 0 ? ns : ne;
-          if (nb < 20) continue;
-          cn[side] = nb;
-          const ClipGeo g = clip_geometry(L, nb, side == 0, minus);
-          if (A.edge && g.n_words <= A.edge_words) {
-            // the clip lies inside the read's first or last edge_words plane words: read it from the edge store
-            const bool at_begin = (side == 0) != minus;
-            const int idx = at_begin ? 0 : g.w_first - max(0, nwr - A.edge_words);
-            A.clip_eoff[2 * (i64)i + side] = (int)((((i64)i * 2 + (at_begin ? 0 : 1)) * 2) * A.edge_words + idx);
-            cw[side] = 0;
-          } else {
-            if (A.edge) A.clip_eoff[2 * (i64)i + side] = -1;
-            cw[side] = g.n_words;
-            if (A.seq_resident) A.clip_off[2 * (i64)i + side] = A.read_seq_off[i] + g.w_first;
-          }
-        }
-        // unaligned gaps between consecutive 1-runs (:455-471): (l1, f2, owner); k_gap_sizes fills the size
-        int* rec = A.gap_rec + (i64)A.read_gap_off[i] * 3;
-        for (int k = ra; k + 1 < rb; ++k, rec += 3) { rec[0] = A.runs[k].y; rec[1] = A.runs[k + 1].x; rec[2] = i; }
+      L = A.read_len[i];
+      int slack;
+      ok = side == 0 ? interval_start(A, i0, i1, fpos[A.runs[ra].x], q, slack)
+                     : interval_end(A, i0, i1, fpos[A.runs[rb - 1].y + 1], q, slack);
+    }
+  }
+  const int q_other = __shfl_xor_sync(0xffffffffu, q, 1);
+  const bool ok_other = __shfl_xor_sync(0xffffffffu, (int)ok, 1) != 0;
+  if (!act || !has) return;
+  const int q_ssc = side == 0 ? q : q_other, q_esc = side == 0 ? q_other : q;
+  if (!(ok && ok_other)) { if (side == 0) dev_fail(A.err, DEVERR_THREAD_CIGAR, i); return; }
+  if (!(0 <= q_ssc && q_ssc <= q_esc && q_esc <= L)) { if (side == 0) dev_fail(A.err, DEVERR_Q_RANGE, i); return; }
+  int* head = A.read_head + (i64)i * 8;
+  if (side == 0) { head[0] = 1; head[3] = q_ssc; }
+  else head[6] = q_esc;
+  {
+    const int nb = side == 0 ? q_ssc : L - q_esc;  // 0: start clip, 1: end clip
+    if (nb >= 20) {
+      const bool minus = A.read_strand[i] != 0;
+      const int nwr = (L + 31) >> 5;  // plane words of the read
+      A.clip_n[(i64)i * 2 + side] = nb;
+      const ClipGeo g = clip_geometry(L, nb, side == 0, minus);
+      if (A.edge && g.n_words <= A.edge_words) {
+        // the clip lies inside the read's first or last edge_words plane words: read it from the edge store
+        const bool at_begin = (side == 0) != minus;
+        const int idx = at_begin ? 0 : g.w_first - max(0, nwr - A.edge_words);
+        A.clip_eoff[2 * (i64)i + side] = (int)((((i64)i * 2 + (at_begin ? 0 : 1)) * 2) * A.edge_words + idx);
+      } else {
+        if (A.edge) A.clip_eoff[2 * (i64)i + side] = -1;
+        A.clip_words[(i64)i * 2 + side] = g.n_words;
+        if (A.seq_resident) A.clip_off[2 * (i64)i + side] = A.read_seq_off[i] + g.w_first;
       }
     }
   }
+  // unaligned gaps between consecutive 1-runs (:455-471): (l1, f2, owner); k_gap_sizes fills the size
+  int* rec = A.gap_rec + ((i64)A.read_gap_off[i] + side) * 3;
+  for (int k = ra + side; k + 1 < rb; k += 2, rec += 6) { rec[0] = A.runs[k].y; rec[1] = A.runs[k + 1].x; rec[2] = i; }
 }
 
 // K11a': one thread per unaligned-gap record: "{l1}-{f2}:{size}" (:455-471)
@@ -638,31 +645,65 @@ __global__ void __launch_bounds__(128) k_poly_filter(GapArgs A, u8* __restrict__
     if (sh_cnt[k]) atomicAdd(&A.cls_count[k], sh_cnt[k]);
 }
 
-// one warp: class bases, LONGEST class first; cls_count[c] becomes the base, cursors start at 0
+// one warp: class bases, LONGEST class first; cls_count[c] becomes the base, cursors start at 0.  Three classes per
+// lane and a warp scan (one thread walking the 96 counters was a chain of dependent loads).
 __global__ void k_poly_bases(int* __restrict__ cls_count, int long_class, int* __restrict__ stat /* [2] */) {
   pdl_prologue();
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int c = POLY_CLASSES - 1; c >= 0; --c) { int v = cls_count[c]; cls_count[c] = acc; acc += v; }
-    cls_count[2 * POLY_CLASSES] = acc;  // total tasks
-    stat[0] = acc;                       // scan tasks that survived the filter
-    stat[1] = cls_count[long_class - 1]; // of which warp-scanned (long clips)
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  constexpr int PER = (POLY_CLASSES + 31) / 32;
+  int v[PER], sum = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {  // list position e = lane * PER + j holds class POLY_CLASSES - 1 - e
+    const int e = lane * PER + j;
+    v[j] = e < POLY_CLASSES ? cls_count[POLY_CLASSES - 1 - e] : 0;
+    sum += v[j];
+  }
+  int x = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  const int total = __shfl_sync(0xffffffffu, x, 31);
+  int acc = x - sum;
+  __syncwarp();  // every count is read before any base is written
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int e = lane * PER + j;
+    if (e < POLY_CLASSES) {
+      const int c = POLY_CLASSES - 1 - e;
+      cls_count[c] = acc;
+      if (c == long_class - 1) stat[1] = acc;  // tasks that are warp-scanned (long clips) come before this class
+      acc += v[j];
+    }
+  }
+  if (lane == 0) {
+    cls_count[2 * POLY_CLASSES] = total;  // total tasks
+    stat[0] = total;                       // scan tasks that survived the filter
   }
 }
 
-__global__ void k_poly_scatter(int n_slots, const int* __restrict__ clip_n, const u8* __restrict__ pass_flag,
+// order[] = the surviving tasks, longest class first.  The cursor of a class is bumped once per CTA and class
+// (shared-memory counters first): per-warp bumps were ~50 k atomics on a dozen addresses, serialised in L2.
+__global__ void __launch_bounds__(256) k_poly_scatter(int n_slots, const int* __restrict__ clip_n, const u8* __restrict__ pass_flag,
                                int* __restrict__ cls_count, int* __restrict__ order, const i64* __restrict__ cnt, Caps caps) {
   pdl_prologue();
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_slots || !clips_fit(cnt, caps) || !pass_flag[s]) return;
-  int c = poly_class_dev(clip_n[s >> 1]);
-  // warp-aggregate the cursor bump of lanes that share a class
-  unsigned peers = __match_any_sync(__activemask(), c);
-  int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
-  int base = 0;
-  if (lane == leader) base = atomicAdd(&cls_count[POLY_CLASSES + c], __popc(peers));
-  base = __shfl_sync(peers, base, leader);
-  order[cls_count[c] + base + __popc(peers & ((1u << lane) - 1u))] = s;
+  __shared__ int sh_cnt[POLY_CLASSES], sh_base[POLY_CLASSES];
+  for (int k = threadIdx.x; k < POLY_CLASSES; k += blockDim.x) sh_cnt[k] = 0;
+  __syncthreads();
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool pass = s < n_slots && clips_fit(cnt, caps) && pass_flag[s];
+  int c = 0, rank = 0;
+  if (pass) {
+    c = poly_class_dev(clip_n[s >> 1]);
+    rank = atomicAdd(&sh_cnt[c], 1);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < POLY_CLASSES; k += blockDim.x)
+    if (sh_cnt[k]) sh_base[k] = atomicAdd(&cls_count[POLY_CLASSES + k], sh_cnt[k]);
+  __syncthreads();
+  if (pass) order[cls_count[c] + sh_base[c] + rank] = s;
 }
 
 // K11b: one thread per scan task (clips shorter than 1024 bases)
