@@ -91,7 +91,7 @@ struct frs_context {
   cudaEvent_t ev_tfork = nullptr, ev_tjoin = nullptr;
   cudaStream_t side[FRS_SIDE_STREAMS] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[FRS_SIDE_STREAMS] = {};
-  cudaEvent_t ev_cov[3] = {};  // coverage chain on side[0]: fork, block offsets ready, matrix ready
+  cudaEvent_t ev_cov[4] = {};  // coverage chain on side[0]: fork, block offsets ready, matrix ready, threshold done
   char err[512] = "";
   bool profiling = false;
   Slot slot[FRS_SLOTS];
@@ -1093,32 +1093,34 @@ static int enqueue_run(frs_context* c, Slot& S) {
   launch_k(k_cand_meta, g_cand, 256, 0, st, c->b_cand_flat.as<int>(), d_K, d_island_sample_off, NI,
                                       c->b_cand_island.as<int>(), c->b_island_cand_off.as<int>());
   LAUNCHED();
-  // The coverage matrix only needs the candidate list: its chain (block offsets per tint, scan, k_coverage) runs
-  // on a side stream beside threshold -> fixed -> subproblems, which are short latency-bound kernels; the head
-  // stream takes the offsets back before k_plan_finish and the matrix before the DP fork.
-  {
-    cudaStream_t cs = c->side[0];
-    CK(cudaEventRecord(c->ev_cov[0], st));
-    CK(cudaStreamWaitEvent(cs, c->ev_cov[0], 0));
-    stage_begin(c, "coverage", cs);
-    // coverage block offsets per tint (rows = candidates of the tint, stride Rp)
-    launch_k(k_tint_cov_sizes, cdiv(T + 1, 256), 256, 0, cs, T, d_tint_island_off, c->b_island_cand_off.as<int>(), d_tint_rep_off,
-                                                       c->b_tint_cand_off.as<int>(), c->b_cov_sz.as<i64>());
-    LAUNCHED();
-    { int r = scan_exclusive_on<i64, i64>(c, cs, c->b_bsum_cov, c->b_cov_sz.as<i64>(), T, c->b_tint_cov_off.as<i64>()); if (r) return r; }
-    CK(cudaEventRecord(c->ev_cov[1], cs));
-    launch_k(k_coverage, dim3((unsigned)std::max(S.n_cov_tiles, 1), COV_CHUNKS), COV_THREADS, 0, cs, 
-        S.b_cov_tiles.as<RepTile>(), d_tint_rep_off, c->b_tint_cand_off.as<int>(), c->b_tint_cov_off.as<i64>(),
-        S.b_rep_iv_off.as<int>(), S.b_rep_fs.as<int>(), S.b_rep_fe.as<int>(), c->b_cand_flat.as<int>(), c->b_P.as<u32>(),
-        T, S.n_cov_tiles > 0 ? cp.P : -1);
-    LAUNCHED();
-    CK(cudaEventRecord(c->ev_cov[2], cs));
-  }
+  // The coverage matrix only needs the candidate list, and its chain (block offsets per tint, scan, k_coverage) runs
+  // on a side stream.  k_threshold fills the SMs by itself (beside it k_coverage only doubled both times), so the
+  // tiny offset kernels run beside k_threshold and k_coverage starts when it ends, beside fixed -> subproblems ->
+  // plan, which are short latency-bound kernels.  The head stream takes the offsets back before k_plan_finish and
+  // the matrix before the DP fork.
+  cudaStream_t cs = c->side[0];
+  CK(cudaEventRecord(c->ev_cov[0], st));
+  CK(cudaStreamWaitEvent(cs, c->ev_cov[0], 0));
+  // coverage block offsets per tint (rows = candidates of the tint, stride Rp)
+  launch_k(k_tint_cov_sizes, cdiv(T + 1, 256), 256, 0, cs, T, d_tint_island_off, c->b_island_cand_off.as<int>(), d_tint_rep_off,
+           c->b_tint_cand_off.as<int>(), c->b_cov_sz.as<i64>());
+  LAUNCHED();
+  { int r = scan_exclusive_on<i64, i64>(c, cs, c->b_bsum_cov, c->b_cov_sz.as<i64>(), T, c->b_tint_cov_off.as<i64>()); if (r) return r; }
+  CK(cudaEventRecord(c->ev_cov[1], cs));
   stage_begin(c, "threshold");
   launch_k(k_threshold, T, THR_THREADS, 0, st, S.b_tint_order.as<int>(), d_tint_island_off, d_island_sample_off,
                                          c->b_tint_pos_off.as<int>(), prm->vf, c->b_vbuf.as<double>(),
                                          c->b_leaf_len.as<int>(), c->b_leaf_sum.as<double>(), c->b_thr.as<double>());
   LAUNCHED();
+  CK(cudaEventRecord(c->ev_cov[3], st));
+  CK(cudaStreamWaitEvent(cs, c->ev_cov[3], 0));
+  stage_begin(c, "coverage", cs);
+  launch_k(k_coverage, dim3((unsigned)std::max(S.n_cov_tiles, 1), COV_CHUNKS), COV_THREADS, 0, cs,
+           S.b_cov_tiles.as<RepTile>(), d_tint_rep_off, c->b_tint_cand_off.as<int>(), c->b_tint_cov_off.as<i64>(),
+           S.b_rep_iv_off.as<int>(), S.b_rep_fs.as<int>(), S.b_rep_fe.as<int>(), c->b_cand_flat.as<int>(), c->b_P.as<u32>(),
+           T, S.n_cov_tiles > 0 ? cp.P : -1);
+  LAUNCHED();
+  CK(cudaEventRecord(c->ev_cov[2], cs));
 
   stage_begin(c, "fixed");
   launch_k(k_fixed_a, g_cand, 256, 0, st, d_K, c->b_cand_flat.as<int>(), c->b_cand_island.as<int>(),
