@@ -222,15 +222,18 @@ __global__ void __launch_bounds__(GAUSS_THREADS, MINB) k_smooth(const TileWork* 
   const int span_r = (span + GAUSS_THREADS - 1) / GAUSS_THREADS * GAUSS_THREADS;
   const bool interior = first >= 0 && first + span <= n;
   const int n2 = 2 * n;
-  for (int s0 = warp * 32; s0 < span_r; s0 += GAUSS_THREADS) {  // whole warps: the ballot needs every lane
+  // Staging in two passes.  (1) every lane issues ALL its 4-byte global -> shared copies asynchronously (cp.async):
+  // with a register in between, the store of chunk k stalled the warp until its load returned and the 5 - 9 loads of a
+  // lane went out one latency after the other (29 % of the kernel's stall samples).  (2) after cp.async.wait_all each
+  // lane reads back its OWN elements (no cross-lane visibility needed) and the warp ballots the non-zero mask.
+  const unsigned ext_sh = (unsigned)__cvta_generic_to_shared(ext);
+  for (int s0 = warp * 32; s0 < span_r; s0 += GAUSS_THREADS) {
     const int s = s0 + lane;
     const int j00 = first + s0;
-    int v = 0;
     if (j00 >= 0 && j00 + 31 < n && s0 + 31 < span) {
       // warp-uniform fast path: the 32 samples lie inside the island (most tiles touch an island end, so a
       // CTA-wide `interior` test sent 94 % of them through the reflect arithmetic below)
-      v = yr[j00 + lane];
-      ext[s] = v;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ext_sh + 4u * (unsigned)s), "l"(yr + j00 + lane) : "memory");
     } else if (s < span) {
       const int j0 = j00 + lane;
       int j = j0;
@@ -244,9 +247,13 @@ __global__ void __launch_bounds__(GAUSS_THREADS, MINB) k_smooth(const TileWork* 
           if (j >= n) j = n2 - 1 - j;
         }
       }
-      v = yr[j];
-      ext[s] = v;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ext_sh + 4u * (unsigned)s), "l"(yr + j) : "memory");
     }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  for (int s0 = warp * 32; s0 < span_r; s0 += GAUSS_THREADS) {  // whole warps: the ballot needs every lane
+    const int s = s0 + lane;
+    const int v = s < span ? ext[s] : 0;
     const u32 m = __ballot_sync(0xffffffffu, v != 0);
     if (lane == 0) nz[s0 >> 5] = m;
   }
