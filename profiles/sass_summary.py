@@ -16,7 +16,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "freddie_b200", "libfreddie_b200.so")
-WATCH = ["ACQBULK", "PREEXIT", "UBLKCP", "SYNCS", "DFMA", "DMUL", "DADD", "MUFU", "VOTE", "POPC", "LOP3", "REDUX", "MATCH", "ATOMS", "ATOMG", "RED",
+WATCH = ["ACQBULK", "PREEXIT", "UBLKCP", "LDGSTS", "SYNCS", "DFMA", "DMUL", "DADD", "MUFU", "VOTE", "POPC", "LOP3", "REDUX", "MATCH", "ATOMS", "ATOMG", "RED",
          "LDG", "STG", "LDS", "STS", "BAR", "SHFL", "NANOSLEEP"]
 txt = subprocess.run(["cuobjdump", "-sass", lib], stdout=subprocess.PIPE, text=True, check=True).stdout
 archs = sorted(set(re.findall(r"arch = (sm_\w+)", txt)))
